@@ -1,0 +1,323 @@
+"""ctypes bindings for the parity oracle (TEST INFRASTRUCTURE ONLY).
+
+Two libraries are bound here:
+  * ``oracle/liboracle.so``      -- our plain-C restatement of the reference's hot path (hs_oracle.c)
+  * ``oracle/_ref/libhsref_*.so`` -- the UNMODIFIED reference compiled from /root/reference by
+                                    oracle/Makefile (present wherever it was built; travels to the
+                                    GPU box as a prebuilt file)
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
+module; nothing under hairsplitter_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_P = np.ctypeslib.ndpointer
+
+
+def build(ref: bool = True) -> None:
+    """Compile liboracle.so (and _ref/ when the reference sources are present)."""
+    subprocess.run(["make", "-s", "-C", HERE, "liboracle.so"], check=True)
+    if ref and os.path.exists("/root/reference/src/call_variants.cpp"):
+        subprocess.run(["make", "-s", "-j8", "-C", HERE, "ref"], check=True)
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Oracle:
+    """liboracle.so"""
+
+    def __init__(self):
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        L = self.lib = C.CDLL(path)
+        L.hso_pileup.restype = C.c_int64
+        L.hso_pileup.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]
+        L.hso_mean_distance.restype = C.c_float
+        L.hso_mean_distance.argtypes = [C.c_int64, C.c_int64]
+        L.hso_ref_codes.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.hso_rh_order.restype = C.c_int
+        L.hso_rh_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.hso_sort_desc.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.hso_column_rank.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.hso_call_variants.restype = C.c_int32
+        L.hso_call_variants.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.hso_distance.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_int32, C.c_void_p]
+        L.hso_chi_square.restype = C.c_float
+        L.hso_chi_square.argtypes = [C.c_int32] * 4
+        L.hso_rescue_prefilter.restype = C.c_int
+        L.hso_rescue_prefilter.argtypes = [C.c_int32, C.c_int32]
+        L.hso_read_pair_counts.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 7
+
+    # -- pileup ---------------------------------------------------------------------------------
+    def pileup(self, cb):
+        """cb: synth.ContigBatch. Returns dict(col_off, read_idx, code, stats, read_end)."""
+        Lc = cb.length
+        contig = _arr(cb.contig, np.uint8)
+        rb = _arr(cb.read_bases, np.uint8)
+        ro = _arr(cb.read_off, np.int64)
+        cg = _arr(cb.cigar, np.uint32)
+        co = _arr(cb.cigar_off, np.int64)
+        st = _arr(cb.start, np.int32)
+        sd = _arr(cb.strand, np.uint8)
+        col_off = np.zeros(Lc + 1, dtype=np.int64)
+        stats = np.zeros(2, dtype=np.int64)
+        read_end = np.zeros(cb.n_reads, dtype=np.int32)
+        args = [contig.ctypes.data, Lc, cb.n_reads, rb.ctypes.data, ro.ctypes.data, cg.ctypes.data, co.ctypes.data,
+                st.ctypes.data, sd.ctypes.data]
+        n = self.lib.hso_pileup(*args, 0, col_off.ctypes.data, None, None, stats.ctypes.data, read_end.ctypes.data)
+        read_idx = np.zeros(max(n, 1), dtype=np.uint32)
+        code = np.zeros(max(n, 1), dtype=np.uint8)
+        self.lib.hso_pileup(*args, n, col_off.ctypes.data, read_idx.ctypes.data, code.ctypes.data, stats.ctypes.data,
+                            read_end.ctypes.data)
+        return dict(col_off=col_off, read_idx=read_idx[:n], code=code[:n], stats=stats, read_end=read_end)
+
+    def mean_distance(self, dist, alen):
+        return float(np.float32(self.lib.hso_mean_distance(int(dist), int(alen))))
+
+    def ref_codes(self, contig):
+        contig = _arr(contig, np.uint8)
+        out = np.zeros(contig.shape[0], dtype=np.uint8)
+        self.lib.hso_ref_codes(contig.ctypes.data, contig.shape[0], out.ctypes.data)
+        return out
+
+    def rh_order(self, keys):
+        keys = _arr(keys, np.uint8)
+        out = np.zeros(keys.shape[0] + 8, dtype=np.uint8)
+        n = self.lib.hso_rh_order(keys.ctypes.data, keys.shape[0], out.ctypes.data)
+        return out[:n]
+
+    def sort_desc(self, keys, counts):
+        keys = _arr(keys, np.uint8).copy()
+        counts = _arr(counts, np.int32).copy()
+        self.lib.hso_sort_desc(keys.ctypes.data, counts.ctypes.data, keys.shape[0])
+        return keys, counts
+
+    def column_rank(self, codes):
+        codes = _arr(codes, np.uint8)
+        out = np.zeros(5, dtype=np.int32)
+        self.lib.hso_column_rank(codes.ctypes.data, codes.shape[0], out.ctypes.data)
+        return out
+
+    def call_variants(self, col_off, code, mean_error, auto_threshold=0.33):
+        col_off = _arr(col_off, np.int64)
+        code = _arr(code, np.uint8)
+        Lc = col_off.shape[0] - 1
+        ref_base = np.zeros(Lc, dtype=np.uint8)
+        second_base = np.zeros(Lc, dtype=np.uint8)
+        cap = Lc // 6 + 8
+        pos = np.zeros(cap, dtype=np.int32)
+        is_auto = np.zeros(cap, dtype=np.uint8)
+        depth = np.zeros(1, dtype=np.int64)
+        n = self.lib.hso_call_variants(col_off.ctypes.data, code.ctypes.data, Lc, float(mean_error),
+                                       float(auto_threshold), ref_base.ctypes.data, second_base.ctypes.data,
+                                       pos.ctypes.data, is_auto.ctypes.data, cap, depth.ctypes.data)
+        return dict(ref_base=ref_base, second_base=second_base, suspect_pos=pos[:n], suspect_is_auto=is_auto[:n],
+                    depth_sum=int(depth[0]))
+
+    def distance(self, p_idx, p_state, p_more, p_less, c_idx, c_code, ref_base):
+        p_idx = _arr(p_idx, np.int32)
+        p_state = _arr(p_state, np.int16)
+        p_more = _arr(p_more, np.int32)
+        p_less = _arr(p_less, np.int32)
+        c_idx = _arr(c_idx, np.uint32)
+        c_code = _arr(c_code, np.uint8)
+        out = np.zeros(10, dtype=np.int32)
+        self.lib.hso_distance(p_idx.shape[0], p_idx.ctypes.data, p_state.ctypes.data, p_more.ctypes.data,
+                              p_less.ctypes.data, c_idx.shape[0], c_idx.ctypes.data, c_code.ctypes.data,
+                              int(ref_base), out.ctypes.data)
+        return out
+
+    def chi_square(self, n00, n01, n10, n11):
+        return float(np.float32(self.lib.hso_chi_square(int(n00), int(n01), int(n10), int(n11))))
+
+    def rescue_prefilter(self, ref_base, second_base):
+        return bool(self.lib.hso_rescue_prefilter(int(ref_base), int(second_base)))
+
+    def read_pair_counts(self, n_reads, snp_off, read_idx, code, ref_base, second_base):
+        snp_off = _arr(snp_off, np.int64)
+        read_idx = _arr(read_idx, np.uint32)
+        code = _arr(code, np.uint8)
+        ref_base = _arr(ref_base, np.uint8)
+        second_base = _arr(second_base, np.uint8)
+        sim = np.zeros((n_reads, n_reads), dtype=np.int32)
+        diff = np.zeros((n_reads, n_reads), dtype=np.int32)
+        self.lib.hso_read_pair_counts(n_reads, snp_off.shape[0] - 1, snp_off.ctypes.data, read_idx.ctypes.data,
+                                      code.ctypes.data, ref_base.ctypes.data, second_base.ctypes.data,
+                                      sim.ctypes.data, diff.ctypes.data)
+        return sim, diff
+
+
+def ref_available() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libhsref_cv.so"))
+
+
+class RefCV:
+    """The reference's own call_variants.cpp functions through oracle/ref_shim_cv.cpp."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(HERE, "_ref", "libhsref_cv.so"))
+            L.hsref_cv_create.restype = C.c_void_p
+            L.hsref_cv_create.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.hsref_cv_destroy.argtypes = [C.c_void_p]
+            L.hsref_cv_mean_distance.restype = C.c_float
+            L.hsref_cv_mean_distance.argtypes = [C.c_void_p]
+            L.hsref_cv_n_columns.restype = C.c_long
+            L.hsref_cv_n_columns.argtypes = [C.c_void_p]
+            L.hsref_cv_n_cells.restype = C.c_long
+            L.hsref_cv_n_cells.argtypes = [C.c_void_p]
+            L.hsref_cv_get_pileup.argtypes = [C.c_void_p] * 4
+            L.hsref_cv_get_newref.argtypes = [C.c_void_p] * 2
+            L.hsref_cv_get_read_ends.argtypes = [C.c_void_p] * 3
+            L.hsref_cv_call_variants.restype = C.c_int
+            L.hsref_cv_call_variants.argtypes = [C.c_void_p, C.c_float, C.c_float]
+            L.hsref_cv_depth.restype = C.c_float
+            L.hsref_cv_depth.argtypes = [C.c_void_p]
+            L.hsref_cv_get_column_bases.argtypes = [C.c_void_p] * 3
+            L.hsref_cv_list_size.restype = C.c_int
+            L.hsref_cv_list_size.argtypes = [C.c_void_p, C.c_int]
+            L.hsref_cv_list_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.hsref_cv_robust.restype = C.c_int
+            L.hsref_cv_robust.argtypes = [C.c_void_p, C.c_float]
+            L.hsref_cv_part_size.restype = C.c_int
+            L.hsref_cv_part_size.argtypes = [C.c_void_p, C.c_int]
+            L.hsref_cv_part_get.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+            L.hsref_cv_distance.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+            L.hsref_cv_distance_custom.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+            L.hsref_chi_square.restype = C.c_float
+            L.hsref_chi_square.argtypes = [C.c_int] * 4
+            L.hsref_rh_order.restype = C.c_int
+            L.hsref_rh_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+            L.hsref_sort_desc.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, cb):
+        L = self.lib()
+        n = cb.n_reads
+        reads = (C.c_char_p * n)(*[cb.read_str(i).encode() for i in range(n)])
+        cigars = (C.c_char_p * n)(*[cb.cigar_str(i).encode() for i in range(n)])
+        st = _arr(cb.start, np.int32)
+        sd = _arr(cb.strand, np.uint8)
+        self.h = L.hsref_cv_create(cb.contig_str().encode(), n, reads, cigars, st.ctypes.data, sd.ctypes.data)
+        self.n_reads = n
+        self.L = L.hsref_cv_n_columns(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib().hsref_cv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def mean_distance(self):
+        return float(np.float32(self.lib().hsref_cv_mean_distance(self.h)))
+
+    def pileup(self):
+        L = self.lib()
+        n = L.hsref_cv_n_cells(self.h)
+        col_off = np.zeros(self.L + 1, dtype=np.int64)
+        read_idx = np.zeros(max(n, 1), dtype=np.uint32)
+        code = np.zeros(max(n, 1), dtype=np.uint8)
+        L.hsref_cv_get_pileup(self.h, col_off.ctypes.data, read_idx.ctypes.data, code.ctypes.data)
+        return dict(col_off=col_off, read_idx=read_idx[:n], code=code[:n])
+
+    def newref(self):
+        out = np.zeros(self.L, dtype=np.uint8)
+        self.lib().hsref_cv_get_newref(self.h, out.ctypes.data)
+        return out
+
+    def read_limits(self):
+        s = np.zeros(self.n_reads, dtype=np.int32)
+        e = np.zeros(self.n_reads, dtype=np.int32)
+        self.lib().hsref_cv_get_read_ends(self.h, s.ctypes.data, e.ctypes.data)
+        return s, e
+
+    def call_variants(self, mean_error=-1.0, auto_threshold=0.33):
+        L = self.lib()
+        L.hsref_cv_call_variants(self.h, float(mean_error), float(auto_threshold))
+        ref_base = np.zeros(self.L, dtype=np.uint8)
+        second_base = np.zeros(self.L, dtype=np.uint8)
+        L.hsref_cv_get_column_bases(self.h, ref_base.ctypes.data, second_base.ctypes.data)
+        return dict(ref_base=ref_base, second_base=second_base, suspects=self.get_list(0), automatic=self.get_list(1),
+                    depth=float(np.float32(L.hsref_cv_depth(self.h))))
+
+    def get_list(self, which):
+        L = self.lib()
+        n = L.hsref_cv_list_size(self.h, which)
+        pos = np.zeros(n, dtype=np.int32)
+        rb = np.zeros(n, dtype=np.uint8)
+        sb = np.zeros(n, dtype=np.uint8)
+        L.hsref_cv_list_get(self.h, which, pos.ctypes.data, rb.ctypes.data, sb.ctypes.data)
+        return dict(pos=pos, ref_base=rb, second_base=sb)
+
+    def robust(self, mean_error=-1.0):
+        """keep_only_robust_variants + merge; returns (partitions, filtered, merged)."""
+        L = self.lib()
+        npart = L.hsref_cv_robust(self.h, float(mean_error))
+        parts = []
+        for p in range(npart):
+            n = L.hsref_cv_part_size(self.h, p)
+            idx = np.zeros(n, dtype=np.int32)
+            state = np.zeros(n, dtype=np.int16)
+            more = np.zeros(n, dtype=np.int32)
+            less = np.zeros(n, dtype=np.int32)
+            lr = np.zeros(2, dtype=np.int32)
+            L.hsref_cv_part_get(self.h, p, idx.ctypes.data, state.ctypes.data, more.ctypes.data, less.ctypes.data,
+                                lr.ctypes.data)
+            parts.append(dict(read_idx=idx, state=state, more=more, less=less, left=int(lr[0]), right=int(lr[1])))
+        return parts, self.get_list(2), self.get_list(3)
+
+    def distance(self, p, col, ref_base):
+        out = np.zeros(10, dtype=np.int32)
+        self.lib().hsref_cv_distance(self.h, p, col, int(ref_base), out.ctypes.data)
+        return out
+
+    def distance_custom(self, idx, state, more, less, col, ref_base):
+        idx = _arr(idx, np.int32)
+        state = _arr(state, np.int16)
+        more = _arr(more, np.int32)
+        less = _arr(less, np.int32)
+        out = np.zeros(10, dtype=np.int32)
+        self.lib().hsref_cv_distance_custom(self.h, idx.shape[0], idx.ctypes.data, state.ctypes.data,
+                                            more.ctypes.data, less.ctypes.data, col, int(ref_base), out.ctypes.data)
+        return out
+
+    @classmethod
+    def chi_square(cls, n00, n01, n10, n11):
+        return float(np.float32(cls.lib().hsref_chi_square(int(n00), int(n01), int(n10), int(n11))))
+
+    @classmethod
+    def rh_order(cls, keys):
+        keys = _arr(keys, np.uint8)
+        out = np.zeros(keys.shape[0] + 8, dtype=np.uint8)
+        n = cls.lib().hsref_rh_order(keys.ctypes.data, keys.shape[0], out.ctypes.data)
+        return out[:n]
+
+    @classmethod
+    def sort_desc(cls, keys, counts):
+        keys = _arr(keys, np.uint8).copy()
+        counts = _arr(counts, np.int32).copy()
+        cls.lib().hsref_sort_desc(keys.ctypes.data, counts.ctypes.data, keys.shape[0])
+        return keys, counts
