@@ -1,0 +1,419 @@
+"""ctypes binding of libhsgpu.so (include/hsgpu.h) for the Python test and benchmark harness.
+
+The product is the C-ABI library; this module only marshals numpy arrays to it. It fails loudly when
+the library is missing or when no sm_100 GPU is present -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhsgpu.so")
+
+_lib = None
+
+
+class HsgpuError(RuntimeError):
+    pass
+
+
+class PileupInput(C.Structure):
+    _fields_ = [
+        ("n_contigs", C.c_int32),
+        ("contig_len", C.c_void_p),
+        ("contig_bases", C.c_void_p),
+        ("contig_word_off", C.c_void_p),
+        ("contig_read_off", C.c_void_p),
+        ("n_reads", C.c_int64),
+        ("read_bases", C.c_void_p),
+        ("read_word_off", C.c_void_p),
+        ("read_len", C.c_void_p),
+        ("cigar", C.c_void_p),
+        ("cigar_off", C.c_void_p),
+        ("read_start", C.c_void_p),
+        ("read_strand", C.c_void_p),
+    ]
+
+
+class Partitions(C.Structure):
+    _fields_ = [
+        ("n_parts", C.c_int32),
+        ("part_off", C.c_void_p),
+        ("read_idx", C.c_void_p),
+        ("state", C.c_void_p),
+        ("more", C.c_void_p),
+        ("less", C.c_void_p),
+    ]
+
+
+DISTANCE_DTYPE = np.dtype(
+    [("n00", "<i4"), ("n01", "<i4"), ("n10", "<i4"), ("n11", "<i4"), ("solid00", "<i4"), ("solid01", "<i4"),
+     ("solid10", "<i4"), ("solid11", "<i4"), ("second_base", "u1"), ("augmented", "u1"), ("pad", "u1", (2,)),
+     ("chi_square", "<f4")]
+)
+EDLIB_RESULT_DTYPE = np.dtype(
+    [("status", "<i4"), ("edit_distance", "<i4"), ("n_locations", "<i4"), ("alignment_length", "<i4"),
+     ("loc_off", "<i8"), ("aln_off", "<i8")]
+)
+
+# every symbol include/hsgpu.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "hsgpu_ctx_create", "hsgpu_ctx_destroy", "hsgpu_last_error", "hsgpu_sync", "hsgpu_launch_count", "hsgpu_stream",
+    "hsgpu_host_alloc", "hsgpu_host_free", "hsgpu_pack_bases_ascii", "hsgpu_pack_bases_codes", "hsgpu_parse_cigar",
+    "hsgpu_pileup_create", "hsgpu_pileup_destroy", "hsgpu_pileup_build", "hsgpu_pileup_stats", "hsgpu_mean_distance",
+    "hsgpu_pileup_read_ends", "hsgpu_pileup_export", "hsgpu_pileup_extract_columns", "hsgpu_column_rank",
+    "hsgpu_column_counts", "hsgpu_suspects", "hsgpu_column_summary", "hsgpu_partition_tables", "hsgpu_robust_filter",
+    "hsgpu_read_pair_counts", "hsgpu_edlib_align_batch",
+]
+
+
+def load():
+    """Loads libhsgpu.so (building it is __graft_entry__.build()'s job) and declares prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HsgpuError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(make -C hairsplitter_b200/csrc). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    L.hsgpu_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.hsgpu_ctx_destroy.argtypes = [vp]
+    L.hsgpu_ctx_destroy.restype = None
+    L.hsgpu_last_error.argtypes = [vp]
+    L.hsgpu_last_error.restype = C.c_char_p
+    L.hsgpu_sync.argtypes = [vp]
+    L.hsgpu_launch_count.argtypes = [vp]
+    L.hsgpu_launch_count.restype = i64
+    L.hsgpu_stream.argtypes = [vp]
+    L.hsgpu_stream.restype = vp
+    L.hsgpu_host_alloc.argtypes = [C.POINTER(vp), i64]
+    L.hsgpu_host_free.argtypes = [vp]
+    L.hsgpu_host_free.restype = None
+    L.hsgpu_pack_bases_ascii.argtypes = [C.c_char_p, i64, vp]
+    L.hsgpu_pack_bases_ascii.restype = None
+    L.hsgpu_pack_bases_codes.argtypes = [vp, i64, vp]
+    L.hsgpu_pack_bases_codes.restype = None
+    L.hsgpu_parse_cigar.argtypes = [C.c_char_p, vp, i64]
+    L.hsgpu_parse_cigar.restype = i64
+    L.hsgpu_pileup_create.argtypes = [vp, C.POINTER(PileupInput), C.POINTER(vp)]
+    L.hsgpu_pileup_destroy.argtypes = [vp]
+    L.hsgpu_pileup_destroy.restype = None
+    L.hsgpu_pileup_build.argtypes = [vp]
+    L.hsgpu_pileup_stats.argtypes = [vp, vp, vp, vp]
+    L.hsgpu_mean_distance.argtypes = [i64, i64]
+    L.hsgpu_mean_distance.restype = f32
+    L.hsgpu_pileup_read_ends.argtypes = [vp, vp]
+    L.hsgpu_pileup_export.argtypes = [vp, i32, i64, vp, vp, vp]
+    L.hsgpu_pileup_extract_columns.argtypes = [vp, i32, i32, vp, i64, vp, vp, vp]
+    L.hsgpu_column_rank.argtypes = [vp, vp, f32]
+    L.hsgpu_column_counts.argtypes = [vp, vp, vp]
+    L.hsgpu_suspects.argtypes = [vp, i32, i32, vp, vp]
+    L.hsgpu_column_summary.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.hsgpu_partition_tables.argtypes = [vp, i32, C.POINTER(Partitions), i32, vp, vp]
+    L.hsgpu_robust_filter.argtypes = [vp, i32, C.POINTER(Partitions), i32, vp, i32, vp, vp]
+    L.hsgpu_read_pair_counts.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.hsgpu_edlib_align_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, i64]
+    for name in ("hsgpu_debug_rank_column", "hsgpu_debug_rh_order", "hsgpu_debug_sort_desc"):
+        getattr(L, name).restype = C.c_int if name == "hsgpu_debug_rh_order" else None
+    L.hsgpu_debug_rank_column.argtypes = [vp, C.c_int, vp]
+    L.hsgpu_debug_rh_order.argtypes = [vp, C.c_int, vp]
+    L.hsgpu_debug_sort_desc.argtypes = [vp, vp, C.c_int]
+    _lib = L
+    return L
+
+
+def _a(x, dt):
+    return np.ascontiguousarray(x, dtype=dt)
+
+
+def pack_codes(codes: np.ndarray) -> np.ndarray:
+    """u8 base codes -> 2-bit packed u32 words (vectorised equivalent of hsgpu_pack_bases_codes)."""
+    codes = _a(codes, np.uint8)
+    n = codes.shape[0]
+    nw = (n + 15) // 16
+    pad = np.zeros(nw * 16, dtype=np.uint32)
+    pad[:n] = codes & 3
+    sh = (2 * np.arange(16, dtype=np.uint32))[None, :]
+    return np.bitwise_or.reduce(pad.reshape(nw, 16) << sh, axis=1).astype(np.uint32)
+
+
+class PackedBatch:
+    """Host-side packing of a list of synth.ContigBatch into the flat arrays of hsgpu_pileup_input."""
+
+    def __init__(self, chunks):
+        L = load()
+        nc = len(chunks)
+        self.n_contigs = nc
+        self.contig_len = np.array([c.length for c in chunks], dtype=np.int32)
+        cw = [(c.length + 15) // 16 for c in chunks]
+        self.contig_word_off = np.zeros(nc + 1, dtype=np.int64)
+        np.cumsum(cw, out=self.contig_word_off[1:])
+        self.contig_bases = np.zeros(max(1, int(self.contig_word_off[-1])), dtype=np.uint32)
+        nreads = [c.n_reads for c in chunks]
+        self.contig_read_off = np.zeros(nc + 1, dtype=np.int64)
+        np.cumsum(nreads, out=self.contig_read_off[1:])
+        nr = int(self.contig_read_off[-1])
+        self.n_reads = nr
+        self.read_len = np.concatenate([c.read_len() for c in chunks]).astype(np.int32) if nr else np.zeros(0, np.int32)
+        rw = (self.read_len.astype(np.int64) + 15) // 16
+        self.read_word_off = np.zeros(nr + 1, dtype=np.int64)
+        np.cumsum(rw, out=self.read_word_off[1:])
+        self.read_bases = np.zeros(max(1, int(self.read_word_off[-1])), dtype=np.uint32)
+        self.read_start = np.concatenate([c.start for c in chunks]).astype(np.int32) if nr else np.zeros(0, np.int32)
+        self.read_strand = np.concatenate([c.strand for c in chunks]).astype(np.uint8) if nr else np.zeros(0, np.uint8)
+        self.cigar = np.concatenate([c.cigar for c in chunks]).astype(np.uint32) if nr else np.zeros(1, np.uint32)
+        cn = np.concatenate([np.diff(c.cigar_off) for c in chunks]) if nr else np.zeros(0, np.int64)
+        self.cigar_off = np.zeros(nr + 1, dtype=np.int64)
+        np.cumsum(cn, out=self.cigar_off[1:])
+        r = 0
+        for ci, c in enumerate(chunks):
+            w0 = int(self.contig_word_off[ci])
+            contig = _a(c.contig, np.uint8)
+            L.hsgpu_pack_bases_codes(contig.ctypes.data, c.length, self.contig_bases[w0:].ctypes.data)
+            rb = _a(c.read_bases, np.uint8)
+            # pack read by read so that every read starts on a word boundary
+            ro = c.read_off
+            for i in range(c.n_reads):
+                L.hsgpu_pack_bases_codes(rb[ro[i]:].ctypes.data, int(ro[i + 1] - ro[i]),
+                                         self.read_bases[int(self.read_word_off[r]):].ctypes.data)
+                r += 1
+        self.input_bytes = sum(int(a.nbytes) for a in (self.contig_len, self.contig_bases, self.contig_word_off,
+                                                       self.contig_read_off, self.read_bases, self.read_word_off,
+                                                       self.read_len, self.cigar, self.cigar_off, self.read_start,
+                                                       self.read_strand))
+
+    def struct(self) -> PileupInput:
+        s = PileupInput()
+        s.n_contigs = self.n_contigs
+        s.contig_len = self.contig_len.ctypes.data
+        s.contig_bases = self.contig_bases.ctypes.data
+        s.contig_word_off = self.contig_word_off.ctypes.data
+        s.contig_read_off = self.contig_read_off.ctypes.data
+        s.n_reads = self.n_reads
+        s.read_bases = self.read_bases.ctypes.data
+        s.read_word_off = self.read_word_off.ctypes.data
+        s.read_len = self.read_len.ctypes.data
+        s.cigar = self.cigar.ctypes.data
+        s.cigar_off = self.cigar_off.ctypes.data
+        s.read_start = self.read_start.ctypes.data
+        s.read_strand = self.read_strand.ctypes.data
+        return s
+
+
+def make_partitions(parts):
+    """parts: list of dicts(read_idx, state, more, less) -> (Partitions struct, keepalive arrays)."""
+    n = len(parts)
+    off = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        np.cumsum([len(p["read_idx"]) for p in parts], out=off[1:])
+    cat = lambda k, dt: (np.concatenate([_a(p[k], dt) for p in parts]) if n and off[-1] else np.zeros(1, dt))
+    idx, st, mo, le = cat("read_idx", np.int32), cat("state", np.int16), cat("more", np.int32), cat("less", np.int32)
+    s = Partitions()
+    s.n_parts = n
+    s.part_off = off.ctypes.data
+    s.read_idx = idx.ctypes.data
+    s.state = st.ctypes.data
+    s.more = mo.ctypes.data
+    s.less = le.ctypes.data
+    return s, (off, idx, st, mo, le)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.hsgpu_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise HsgpuError(f"hsgpu_ctx_create failed ({rc}): {self.lib.hsgpu_last_error(None).decode()}")
+        self.h = h
+
+    def check(self, rc, what=""):
+        if rc != 0:
+            raise HsgpuError(f"{what} failed ({rc}): {self.lib.hsgpu_last_error(self.h).decode()}")
+
+    def sync(self):
+        self.check(self.lib.hsgpu_sync(self.h), "hsgpu_sync")
+
+    def launches(self) -> int:
+        return int(self.lib.hsgpu_launch_count(self.h))
+
+    def stream(self) -> int:
+        return int(self.lib.hsgpu_stream(self.h) or 0)
+
+    def close(self):
+        if self.h:
+            self.lib.hsgpu_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- read x read counts ------------------------------------------------------------------
+    def read_pair_counts(self, n_reads, snp_off, read_idx, code, ref_base, second_base):
+        snp_off = _a(snp_off, np.int64)
+        read_idx = _a(read_idx, np.uint32)
+        code = _a(code, np.uint8)
+        ref_base = _a(ref_base, np.uint8)
+        second_base = _a(second_base, np.uint8)
+        sim = np.zeros((n_reads, n_reads), dtype=np.int32)
+        diff = np.zeros((n_reads, n_reads), dtype=np.int32)
+        self.check(self.lib.hsgpu_read_pair_counts(self.h, n_reads, snp_off.shape[0] - 1, snp_off.ctypes.data,
+                                                   read_idx.ctypes.data, code.ctypes.data, ref_base.ctypes.data,
+                                                   second_base.ctypes.data, sim.ctypes.data, diff.ctypes.data),
+                   "hsgpu_read_pair_counts")
+        return sim, diff
+
+    # -- edlib ---------------------------------------------------------------------------------
+    def edlib_align_batch(self, queries, targets, k=-1, mode=2, task=2):
+        """queries/targets: lists of bytes. Returns (results structured array, ends, starts, alignment)."""
+        n = len(queries)
+        qo = np.zeros(n + 1, dtype=np.int64)
+        to = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(q) for q in queries], out=qo[1:])
+        np.cumsum([len(t) for t in targets], out=to[1:])
+        qb = np.frombuffer(b"".join(queries) or b"\0", dtype=np.uint8)
+        tb = np.frombuffer(b"".join(targets) or b"\0", dtype=np.uint8)
+        res = np.zeros(n, dtype=EDLIB_RESULT_DTYPE)
+        loc_cap = int(to[-1]) + n + 8
+        aln_cap = int(qo[-1] + to[-1]) + 8
+        ends = np.zeros(loc_cap, dtype=np.int32)
+        starts = np.zeros(loc_cap, dtype=np.int32)
+        aln = np.zeros(aln_cap, dtype=np.uint8)
+        self.check(self.lib.hsgpu_edlib_align_batch(self.h, n, qb.ctypes.data, qo.ctypes.data, tb.ctypes.data,
+                                                    to.ctypes.data, k, mode, task, res.ctypes.data, ends.ctypes.data,
+                                                    starts.ctypes.data, loc_cap, aln.ctypes.data, aln_cap),
+                   "hsgpu_edlib_align_batch")
+        return res, ends, starts, aln
+
+
+class Pileup:
+    """hsgpu_pileup: a batch of contig chunks resident on the device."""
+
+    def __init__(self, ctx: Context, packed: PackedBatch):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.packed = packed
+        h = C.c_void_p()
+        s = packed.struct()
+        ctx.check(self.lib.hsgpu_pileup_create(ctx.h, C.byref(s), C.byref(h)), "hsgpu_pileup_create")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.hsgpu_pileup_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def build(self):
+        self.ctx.check(self.lib.hsgpu_pileup_build(self.h), "hsgpu_pileup_build")
+
+    def stats(self):
+        nc = self.packed.n_contigs
+        cells = np.zeros(nc, np.int64)
+        dist = np.zeros(nc, np.int64)
+        alen = np.zeros(nc, np.int64)
+        self.ctx.check(self.lib.hsgpu_pileup_stats(self.h, cells.ctypes.data, dist.ctypes.data, alen.ctypes.data),
+                       "hsgpu_pileup_stats")
+        return cells, dist, alen
+
+    def mean_distance(self, dist, alen) -> float:
+        return float(np.float32(self.lib.hsgpu_mean_distance(int(dist), int(alen))))
+
+    def read_ends(self):
+        out = np.zeros(self.packed.n_reads, np.int32)
+        self.ctx.check(self.lib.hsgpu_pileup_read_ends(self.h, out.ctypes.data), "hsgpu_pileup_read_ends")
+        return out
+
+    def column_rank(self, mean_error=None, auto_threshold=0.33):
+        me = None
+        if mean_error is not None:
+            me = _a(mean_error, np.float32)
+        self.ctx.check(self.lib.hsgpu_column_rank(self.h, me.ctypes.data if me is not None else None,
+                                                  float(auto_threshold)), "hsgpu_column_rank")
+
+    def column_counts(self):
+        nc = self.packed.n_contigs
+        ns = np.zeros(nc, np.int32)
+        ds = np.zeros(nc, np.int64)
+        self.ctx.check(self.lib.hsgpu_column_counts(self.h, ns.ctypes.data, ds.ctypes.data), "hsgpu_column_counts")
+        return ns, ds
+
+    def suspects(self, contig):
+        cap = int(self.packed.contig_len[contig]) // 6 + 2
+        pos = np.zeros(cap, np.int32)
+        au = np.zeros(cap, np.uint8)
+        ns, _ = self.column_counts()
+        self.ctx.check(self.lib.hsgpu_suspects(self.h, contig, cap, pos.ctypes.data, au.ctypes.data), "hsgpu_suspects")
+        n = int(ns[contig])
+        return pos[:n], au[:n]
+
+    def column_summary(self, contig):
+        Lc = int(self.packed.contig_len[contig])
+        rb = np.zeros(Lc, np.uint8)
+        sb = np.zeros(Lc, np.uint8)
+        cnt = np.zeros(3 * Lc, np.uint32)
+        dep = np.zeros(Lc, np.uint32)
+        self.ctx.check(self.lib.hsgpu_column_summary(self.h, contig, rb.ctypes.data, sb.ctypes.data, cnt.ctypes.data,
+                                                     dep.ctypes.data), "hsgpu_column_summary")
+        return dict(ref_base=rb, second_base=sb, counts=cnt.reshape(Lc, 3), depth=dep)
+
+    def export(self, contig):
+        Lc = int(self.packed.contig_len[contig])
+        col_off = np.zeros(Lc + 1, np.int64)
+        rc = self.lib.hsgpu_pileup_export(self.h, contig, 0, col_off.ctypes.data, None, None)
+        if rc not in (0, -4):
+            self.ctx.check(rc, "hsgpu_pileup_export")
+        n = int(col_off[-1])
+        idx = np.zeros(max(n, 1), np.uint32)
+        code = np.zeros(max(n, 1), np.uint8)
+        self.ctx.check(self.lib.hsgpu_pileup_export(self.h, contig, n, col_off.ctypes.data, idx.ctypes.data,
+                                                    code.ctypes.data), "hsgpu_pileup_export")
+        return dict(col_off=col_off, read_idx=idx[:n], code=code[:n])
+
+    def extract_columns(self, contig, pos):
+        pos = _a(pos, np.int32)
+        off = np.zeros(pos.shape[0] + 1, np.int64)
+        rc = self.lib.hsgpu_pileup_extract_columns(self.h, contig, pos.shape[0], pos.ctypes.data, 0, off.ctypes.data,
+                                                   None, None)
+        if rc not in (0, -4):
+            self.ctx.check(rc, "hsgpu_pileup_extract_columns")
+        n = int(off[-1])
+        idx = np.zeros(max(n, 1), np.uint32)
+        code = np.zeros(max(n, 1), np.uint8)
+        self.ctx.check(self.lib.hsgpu_pileup_extract_columns(self.h, contig, pos.shape[0], pos.ctypes.data, n,
+                                                             off.ctypes.data, idx.ctypes.data, code.ctypes.data),
+                       "hsgpu_pileup_extract_columns")
+        return off, idx[:n], code[:n]
+
+    def partition_tables(self, contig, parts, pos):
+        pos = _a(pos, np.int32)
+        s, keep = make_partitions(parts)
+        out = np.zeros((pos.shape[0], len(parts)), dtype=DISTANCE_DTYPE)
+        self.ctx.check(self.lib.hsgpu_partition_tables(self.h, contig, C.byref(s), pos.shape[0], pos.ctypes.data,
+                                                       out.ctypes.data), "hsgpu_partition_tables")
+        del keep
+        return out
+
+    def robust_filter(self, contig, parts, suspect_pos):
+        suspect_pos = _a(suspect_pos, np.int32)
+        s, keep = make_partitions(parts)
+        cap = int(self.packed.contig_len[contig])
+        kept = np.zeros(cap + 1, np.int32)
+        n = np.zeros(1, np.int32)
+        self.ctx.check(self.lib.hsgpu_robust_filter(self.h, contig, C.byref(s), suspect_pos.shape[0],
+                                                    suspect_pos.ctypes.data, cap, kept.ctypes.data, n.ctypes.data),
+                       "hsgpu_robust_filter")
+        del keep
+        return kept[: int(n[0])]

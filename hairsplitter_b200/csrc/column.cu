@@ -1,0 +1,517 @@
+// Per-column allele counting and ranking: the body of call_variants (reference
+// src/call_variants.cpp:447-567), plus export of the pileup in the reference's column layout.
+//
+// One CTA per 128-column tile, one thread per column. The tile's rows (reads overlapping it, in
+// ascending neighbour order) are staged through shared memory 64 rows at a time with aligned 16-byte
+// loads; each thread walks down its column updating a private 125-bin histogram that lives in shared
+// memory ([code][column] layout, so the common case "all reads agree" is conflict-free) and
+// recording the order in which codes first appear -- that order is the insertion order of the
+// reference's robin_hood map and decides ties (rank.cuh).
+#include "common.cuh"
+#include "rank.cuh"
+
+#define COL_ROWS 64  // rows staged per batch
+
+struct ColumnArgs {
+    int64_t n_tiles;
+    const int32_t* tile_contig;
+    const int64_t* tile_base;
+    const int64_t* col_base;
+    const int32_t* contig_len;
+    const int64_t* tile_off;
+    const int32_t* tile_reads;
+    const int32_t* read_start;
+    const int32_t* read_end;
+    const int64_t* row_base;
+    const uint8_t* codes;
+    const int32_t* min_reads;
+    float auto_threshold;
+    uint8_t* k0;
+    uint8_t* k1;
+    uint8_t* flags;
+    uint32_t* counts;
+    uint32_t* depth;
+    unsigned long long* depth_sum;
+    int32_t* error_flag;
+};
+
+// stage rows [b0, b0+nrows) of the tile into s_tile[row][128]
+__device__ __forceinline__ void stage_rows(uint4* s_tile, const int32_t* __restrict__ tile_reads, int64_t list_off,
+                                           int b0, int nrows, int q0, const int32_t* __restrict__ read_start,
+                                           const int32_t* __restrict__ read_end, const int64_t* __restrict__ row_base,
+                                           const uint8_t* __restrict__ codes, int tid, int nthreads) {
+    for (int v = tid; v < nrows * (HS_TILE / 16); v += nthreads) {
+        const int row = v >> 3, part = v & 7;
+        const int32_t r = __ldg(tile_reads + list_off + b0 + row);
+        const int s = __ldg(read_start + r) & ~(HS_ALIGN - 1);
+        const int e = (__ldg(read_end + r) + HS_ALIGN - 1) & ~(HS_ALIGN - 1);
+        const int qv = q0 + 16 * part;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (qv >= s && qv < e) val = __ldg(reinterpret_cast<const uint4*>(codes + __ldg(row_base + r) + qv));
+        s_tile[v] = val;
+    }
+}
+
+// the suspect predicate of :525-528 without the spacing rule, and the rescue pre-filter of :751-752
+__device__ __forceinline__ bool central_base_differs(int k0, int k1) {
+    return (k0 % 5 != k1 % 5) && (((k1 - '!') % 5 != 4) || ((k1 / 5 % 5 != k0 % 5) && (k1 / 25 % 5 != k0 % 5)));
+}
+
+__global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint4* s_tile = reinterpret_cast<uint4*>(smem);                                   // COL_ROWS * 128 B
+    uint16_t* s_hist = reinterpret_cast<uint16_t*>(smem + COL_ROWS * HS_TILE);        // [125][128] u16
+    uint8_t* s_order = smem + COL_ROWS * HS_TILE + HS_NCODES * HS_TILE * 2;           // [125][128] u8
+    __shared__ unsigned long long s_depth;
+
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int c = a.tile_contig[tile];
+    const int q0 = (int)(tile - a.tile_base[c]) * HS_TILE;
+    const int L = a.contig_len[c];
+    const int64_t list_off = a.tile_off[tile];
+    const int nlist = (int)(a.tile_off[tile + 1] - list_off);
+    if (tid == 0) {
+        s_depth = 0;
+        if (nlist > 65535) atomicExch(a.error_flag, 1);  // u16 histogram bins; the reference's own loop is a `short` (:479)
+    }
+    {
+        uint4* h4 = reinterpret_cast<uint4*>(s_hist);
+        for (int i = tid; i < HS_NCODES * HS_TILE * 2 / 16; i += HS_TILE) h4[i] = make_uint4(0, 0, 0, 0);
+    }
+    int m = 0;
+    unsigned int depth = 0;
+    const unsigned char* s_bytes = reinterpret_cast<const unsigned char*>(s_tile);
+    for (int b0 = 0; b0 < nlist; b0 += COL_ROWS) {
+        const int nrows = min(COL_ROWS, nlist - b0);
+        __syncthreads();
+        stage_rows(s_tile, a.tile_reads, list_off, b0, nrows, q0, a.read_start, a.read_end, a.row_base, a.codes, tid,
+                   HS_TILE);
+        __syncthreads();
+        for (int row = 0; row < nrows; row++) {
+            const int code = s_bytes[row * HS_TILE + tid];
+            if (code) {
+                const int idx = code - HS_CODE0;
+                const unsigned int cnt = s_hist[idx * HS_TILE + tid];
+                if (cnt == 0) s_order[(m++) * HS_TILE + tid] = (uint8_t)idx;
+                s_hist[idx * HS_TILE + tid] = (uint16_t)(cnt + 1);
+                depth++;
+            }
+        }
+    }
+    const int q = q0 + tid;
+    if (q < L) {
+        // top three counts; keys 0,1,2 are the reference's dummy entries with count 0 (:492-494)
+        unsigned int c0 = 0, c1 = 0, c2 = 0;
+        int k0 = 0, k1 = 0;
+        for (int k = 0; k < m; k++) {
+            const int idx = s_order[k * HS_TILE + tid];
+            const unsigned int cnt = s_hist[idx * HS_TILE + tid];
+            if (cnt > c0) { c2 = c1; c1 = c0; k1 = k0; c0 = cnt; k0 = idx + HS_CODE0; }
+            else if (cnt > c1) { c2 = c1; c1 = cnt; k1 = idx + HS_CODE0; }
+            else if (cnt > c2) { c2 = cnt; }
+        }
+        if (c0 == c1 || c1 == c2) {
+            // ties among the ranks that matter: replay the reference's map + sort
+            HsRhTable t;
+            hs_rh_new(t);
+            for (int k = 0; k < m; k++) hs_rh_insert(t, (uint8_t)(s_order[k * HS_TILE + tid] + HS_CODE0));
+            hs_rh_insert(t, 0);
+            hs_rh_insert(t, 1);
+            hs_rh_insert(t, 2);
+            uint8_t it[HS_RH_MAXKEYS];
+            uint32_t kc[HS_RH_MAXKEYS];
+            const int n = hs_rh_iterate(t, it);
+            for (int i = 0; i < n; i++) {
+                const int key = it[i];
+                const unsigned int cnt = key >= HS_CODE0 ? s_hist[(key - HS_CODE0) * HS_TILE + tid] : 0u;
+                kc[i] = (cnt << 8) | (unsigned)key;
+            }
+            hs_kc_std_sort(kc, n);
+            k0 = kc[0] & 0xff;
+            k1 = kc[1] & 0xff;
+            c0 = kc[0] >> 8;
+            c1 = kc[1] >> 8;
+            c2 = kc[2] >> 8;
+        }
+        const int64_t g = a.col_base[c] + q;
+        a.k0[g] = (uint8_t)k0;
+        a.k1[g] = (uint8_t)k1;
+        a.counts[3 * g + 0] = c0;
+        a.counts[3 * g + 1] = c1;
+        a.counts[3 * g + 2] = c2;
+        a.depth[g] = depth;
+        const int mr = a.min_reads[c];
+        const bool cbd = central_base_differs(k0, k1);
+        unsigned f = 0;
+        if (cbd) f |= HS_FLAG_RESCUE;
+        if ((int)c1 > mr && ((int)c1 > (int)c2 * 5 || mr == 2) && cbd) {
+            f |= HS_FLAG_CANDIDATE;
+            if ((float)(int)c1 > __fmul_rn(a.auto_threshold, (float)(int)c0)) f |= HS_FLAG_AUTO;  // :531
+        }
+        a.flags[g] = (uint8_t)f;
+    }
+    // depthOfCoverage numerator (:486,565)
+    unsigned long long d = depth;
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if ((tid & 31) == 0 && d) atomicAdd(&s_depth, d);
+    __syncthreads();
+    if (tid == 0 && s_depth) atomicAdd(a.depth_sum + c, s_depth);
+}
+
+// minimumNumberOfReadsToBeConsideredSuspect (:463-466) from generate_msa's float return value
+__global__ void min_reads_kernel(int n_contigs, const unsigned long long* __restrict__ stats,
+                                 const float* __restrict__ mean_error, int32_t* __restrict__ min_reads) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_contigs) return;
+    float me;
+    if (mean_error) {
+        me = mean_error[c];
+    } else {
+        const unsigned long long dsum = stats[3 * c + 0];
+        const float total_distance = (float)(dsum > 16777216ull ? 16777216ull : dsum);
+        const double total_length = __dadd_rn(1.0, (double)stats[3 * c + 1]);
+        me = (float)__ddiv_rn((double)total_distance, total_length);
+    }
+    min_reads[c] = ((double)me < 0.015) ? 3 : 5;
+}
+
+// The spacing rule `position - posoflastsnp > 5` (:470,529,535) is a greedy left-to-right scan; one
+// warp per contig walks the candidate flags 32 columns at a time.
+__global__ void __launch_bounds__(32) suspect_scan_kernel(const int32_t* __restrict__ contig_len,
+                                                          const int64_t* __restrict__ col_base,
+                                                          const int64_t* __restrict__ suspect_base,
+                                                          uint8_t* __restrict__ flags, int32_t* __restrict__ suspect_pos,
+                                                          uint8_t* __restrict__ suspect_auto,
+                                                          int32_t* __restrict__ n_suspects) {
+    const int c = blockIdx.x, lane = threadIdx.x;
+    const int L = contig_len[c];
+    const int64_t g0 = col_base[c], sb = suspect_base[c];
+    int last = -5, n = 0;
+    for (int q0 = 0; q0 < L; q0 += 32) {
+        const int q = q0 + lane;
+        const unsigned f = (q < L) ? flags[g0 + q] : 0u;
+        unsigned m = __ballot_sync(0xffffffffu, (f & HS_FLAG_CANDIDATE) != 0);
+        unsigned acc = 0;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            if (q0 + b - last > 5) {
+                acc |= 1u << b;
+                last = q0 + b;
+            }
+        }
+        if ((acc >> lane) & 1u) {
+            const int i = n + __popc(acc & ((1u << lane) - 1u));
+            suspect_pos[sb + i] = q;
+            suspect_auto[sb + i] = (f & HS_FLAG_AUTO) ? 1 : 0;
+            flags[g0 + q] = (uint8_t)(f | HS_FLAG_SUSPECT);
+        }
+        n += __popc(acc);
+    }
+    if (lane == 0) n_suspects[c] = n;
+}
+
+// ---- export in the reference's column-major layout ------------------------------------------------
+__global__ void __launch_bounds__(HS_TILE) export_kernel(int contig, int64_t tile0, const int64_t* __restrict__ col_base,
+                                                         const int32_t* __restrict__ contig_len,
+                                                         const int64_t* __restrict__ contig_read_off,
+                                                         const int64_t* __restrict__ tile_off,
+                                                         const int32_t* __restrict__ tile_reads,
+                                                         const int32_t* __restrict__ read_start,
+                                                         const int32_t* __restrict__ read_end,
+                                                         const int64_t* __restrict__ row_base,
+                                                         const uint8_t* __restrict__ codes,
+                                                         const int64_t* __restrict__ col_off,
+                                                         uint32_t* __restrict__ out_idx, uint8_t* __restrict__ out_code) {
+    __shared__ uint4 s_tile[COL_ROWS * HS_TILE / 16];
+    __shared__ int32_t s_reads[COL_ROWS];
+    const int tid = threadIdx.x;
+    const int64_t tile = tile0 + blockIdx.x;
+    const int q0 = blockIdx.x * HS_TILE;
+    const int L = contig_len[contig];
+    const int64_t list_off = tile_off[tile];
+    const int nlist = (int)(tile_off[tile + 1] - list_off);
+    const int64_t g0 = col_base[contig];
+    const int64_t r0 = contig_read_off[contig];
+    const int q = q0 + tid;
+    int64_t w = (q < L) ? col_off[g0 + q] - col_off[g0] : 0;
+    const unsigned char* s_bytes = reinterpret_cast<const unsigned char*>(s_tile);
+    for (int b0 = 0; b0 < nlist; b0 += COL_ROWS) {
+        const int nrows = min(COL_ROWS, nlist - b0);
+        __syncthreads();
+        stage_rows(s_tile, tile_reads, list_off, b0, nrows, q0, read_start, read_end, row_base, codes, tid, HS_TILE);
+        if (tid < nrows) s_reads[tid] = tile_reads[list_off + b0 + tid];
+        __syncthreads();
+        if (q < L) {
+            for (int row = 0; row < nrows; row++) {
+                const int code = s_bytes[row * HS_TILE + tid];
+                if (code) {
+                    out_idx[w] = (uint32_t)(s_reads[row] - r0);
+                    out_code[w] = (uint8_t)code;
+                    w++;
+                }
+            }
+        }
+    }
+}
+
+// one warp per requested column
+__global__ void __launch_bounds__(256) extract_kernel(int n_cols, const int32_t* __restrict__ pos, int64_t tile0,
+                                                      int64_t read0, const int64_t* __restrict__ tile_off,
+                                                      const int32_t* __restrict__ tile_reads,
+                                                      const int32_t* __restrict__ read_start,
+                                                      const int32_t* __restrict__ read_end,
+                                                      const int64_t* __restrict__ row_base,
+                                                      const uint8_t* __restrict__ codes, const int64_t* __restrict__ off,
+                                                      uint32_t* __restrict__ out_idx, uint8_t* __restrict__ out_code) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n_cols) return;
+    const int q = pos[i];
+    const int64_t tile = tile0 + q / HS_TILE;
+    const int64_t l0 = tile_off[tile], l1 = tile_off[tile + 1];
+    int64_t w = off[i];
+    for (int64_t lb = l0; lb < l1; lb += 32) {
+        const int64_t l = lb + lane;
+        bool hit = false;
+        int32_t r = 0;
+        if (l < l1) {
+            r = tile_reads[l];
+            hit = read_start[r] <= q && q < read_end[r];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const int64_t o = w + __popc(m & ((1u << lane) - 1u));
+            out_idx[o] = (uint32_t)(r - read0);
+            out_code[o] = codes[row_base[r] + q];
+        }
+        w += __popc(m);
+    }
+}
+
+__global__ void gather_depth_kernel(int n, const int32_t* __restrict__ pos, int64_t g0, const uint32_t* __restrict__ depth,
+                                    int64_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = depth[g0 + pos[i]];
+}
+
+static const int kColumnSmem = COL_ROWS * HS_TILE + HS_NCODES * HS_TILE * 2 + HS_NCODES * HS_TILE;
+
+extern "C" {
+
+int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_snp_threshold) {
+    if (!p) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = p->ctx;
+    if (!p->built) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_column_rank: call hsgpu_pileup_build first");
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nc = p->n_contigs;
+    if (!p->d_k0) {
+        HS_CUDA(ctx, hs_alloc(ctx, &p->d_k0, p->n_cols));
+        HS_CUDA(ctx, hs_alloc(ctx, &p->d_k1, p->n_cols));
+        HS_CUDA(ctx, hs_alloc(ctx, &p->d_flags, p->n_cols));
+        HS_CUDA(ctx, hs_alloc(ctx, &p->d_counts, 3 * p->n_cols));
+        HS_CUDA(ctx, hs_alloc(ctx, &p->d_depth, p->n_cols));
+        HS_CUDA(ctx, hs_alloc(ctx, &p->d_min_reads, nc + 1));  // last entry = device error flag
+        HS_CUDA(ctx, hs_alloc(ctx, &p->d_suspect_pos, p->h_suspect_base[nc]));
+        HS_CUDA(ctx, hs_alloc(ctx, &p->d_suspect_auto, p->h_suspect_base[nc]));
+        HS_CUDA(ctx, hs_alloc(ctx, &p->d_n_suspects, nc));
+        HS_CUDA(ctx, hs_alloc(ctx, &p->d_depth_sum, nc));
+    }
+    p->ranked = false;
+    p->have_col_off = false;
+    p->auto_threshold = automatic_snp_threshold;
+    float* d_me = nullptr;
+    if (mean_error) {
+        HS_CUDA(ctx, hs_alloc(ctx, &d_me, nc));
+        HS_CUDA(ctx, hs_h2d(ctx, d_me, mean_error, nc));
+    }
+    HS_CUDA(ctx, cudaMemsetAsync(p->d_depth_sum, 0, sizeof(unsigned long long) * nc, ctx->stream));
+    HS_CUDA(ctx, cudaMemsetAsync(p->d_min_reads + nc, 0, sizeof(int32_t), ctx->stream));
+    min_reads_kernel<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(nc, p->d_stats, d_me, p->d_min_reads);
+    HS_LAUNCH_CHECK(ctx);
+    if (mean_error) {
+        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // mean_error is caller memory
+        hs_free(ctx, d_me);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        HS_CUDA(ctx, cudaFuncSetAttribute(column_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kColumnSmem));
+        attr_set = true;
+    }
+    if (p->n_tiles > 0) {
+        ColumnArgs a;
+        a.n_tiles = p->n_tiles;
+        a.tile_contig = p->d_tile_contig;
+        a.tile_base = p->d_tile_base;
+        a.col_base = p->d_col_base;
+        a.contig_len = p->d_contig_len;
+        a.tile_off = p->d_tile_off;
+        a.tile_reads = p->d_tile_reads;
+        a.read_start = p->d_read_start;
+        a.read_end = p->d_read_end;
+        a.row_base = p->d_row_base;
+        a.codes = p->d_codes;
+        a.min_reads = p->d_min_reads;
+        a.auto_threshold = automatic_snp_threshold;
+        a.k0 = p->d_k0;
+        a.k1 = p->d_k1;
+        a.flags = p->d_flags;
+        a.counts = p->d_counts;
+        a.depth = p->d_depth;
+        a.depth_sum = p->d_depth_sum;
+        a.error_flag = p->d_min_reads + nc;
+        column_rank_kernel<<<(unsigned)p->n_tiles, HS_TILE, kColumnSmem, ctx->stream>>>(a);
+        HS_LAUNCH_CHECK(ctx);
+    }
+    suspect_scan_kernel<<<nc, 32, 0, ctx->stream>>>(p->d_contig_len, p->d_col_base, p->d_suspect_base, p->d_flags,
+                                                    p->d_suspect_pos, p->d_suspect_auto, p->d_n_suspects);
+    HS_LAUNCH_CHECK(ctx);
+    p->ranked = true;
+    return HSGPU_OK;
+}
+
+int hsgpu_column_counts(hsgpu_pileup* p, int32_t* n_suspects, int64_t* depth_sum) {
+    if (!p) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = p->ctx;
+    if (!p->ranked) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_column_counts: call hsgpu_column_rank first");
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int32_t err = 0;
+    HS_CUDA(ctx, hs_d2h(ctx, &err, p->d_min_reads + p->n_contigs, 1));
+    if (n_suspects) HS_CUDA(ctx, hs_d2h(ctx, n_suspects, p->d_n_suspects, p->n_contigs));
+    if (depth_sum) HS_CUDA(ctx, hs_d2h(ctx, (unsigned long long*)depth_sum, p->d_depth_sum, p->n_contigs));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err) HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_column_rank: more than 65535 reads over one 128-column tile");
+    return HSGPU_OK;
+}
+
+int hsgpu_suspects(hsgpu_pileup* p, int32_t contig, int32_t capacity, int32_t* pos, uint8_t* is_automatic) {
+    if (!p || contig < 0 || contig >= p->n_contigs) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = p->ctx;
+    if (!p->ranked) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_suspects: call hsgpu_column_rank first");
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int32_t n = 0;
+    HS_CUDA(ctx, hs_d2h(ctx, &n, p->d_n_suspects + contig, 1));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n > capacity) HS_FAIL(ctx, HSGPU_ERR_CAPACITY, "hsgpu_suspects: capacity too small");
+    if (pos) HS_CUDA(ctx, hs_d2h(ctx, pos, p->d_suspect_pos + p->h_suspect_base[contig], n));
+    if (is_automatic) HS_CUDA(ctx, hs_d2h(ctx, is_automatic, p->d_suspect_auto + p->h_suspect_base[contig], n));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HSGPU_OK;
+}
+
+int hsgpu_column_summary(hsgpu_pileup* p, int32_t contig, uint8_t* ref_base, uint8_t* second_base, uint32_t* counts,
+                         uint32_t* depth) {
+    if (!p || contig < 0 || contig >= p->n_contigs) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = p->ctx;
+    if (!p->ranked) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_column_summary: call hsgpu_column_rank first");
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t g0 = p->h_col_base[contig], L = p->h_contig_len[contig];
+    if (ref_base) HS_CUDA(ctx, hs_d2h(ctx, ref_base, p->d_k0 + g0, L));
+    if (second_base) HS_CUDA(ctx, hs_d2h(ctx, second_base, p->d_k1 + g0, L));
+    if (counts) HS_CUDA(ctx, hs_d2h(ctx, counts, p->d_counts + 3 * g0, 3 * L));
+    if (depth) HS_CUDA(ctx, hs_d2h(ctx, depth, p->d_depth + g0, L));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HSGPU_OK;
+}
+
+static int ensure_col_off(hsgpu_pileup* p) {
+    hsgpu_ctx* ctx = p->ctx;
+    if (p->have_col_off) return HSGPU_OK;
+    if (!p->d_col_off) HS_CUDA(ctx, hs_alloc(ctx, &p->d_col_off, p->n_cols + 1));
+    int rc = hs_exclusive_scan_u32_to_i64(ctx, p->d_depth, p->d_col_off, p->n_cols, p->d_col_off + p->n_cols);
+    if (rc) return rc;
+    p->have_col_off = true;
+    return HSGPU_OK;
+}
+
+int hsgpu_pileup_export(hsgpu_pileup* p, int32_t contig, int64_t cell_capacity, int64_t* col_off, uint32_t* read_idx,
+                        uint8_t* code) {
+    if (!p || contig < 0 || contig >= p->n_contigs || !col_off) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = p->ctx;
+    if (!p->ranked) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_pileup_export: call hsgpu_column_rank first");
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_col_off(p);
+    if (rc) return rc;
+    const int64_t g0 = p->h_col_base[contig], L = p->h_contig_len[contig];
+    HS_CUDA(ctx, hs_d2h(ctx, col_off, p->d_col_off + g0, L + 1));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t first = col_off[0];
+    for (int64_t i = 0; i <= L; i++) col_off[i] -= first;
+    const int64_t n = col_off[L];
+    if (n > cell_capacity || !read_idx || !code) {
+        if (n == 0) return HSGPU_OK;
+        HS_FAIL(ctx, HSGPU_ERR_CAPACITY, "hsgpu_pileup_export: cell_capacity too small");
+    }
+    if (n == 0) return HSGPU_OK;
+    uint32_t* d_idx = nullptr;
+    uint8_t* d_code = nullptr;
+    HS_CUDA(ctx, hs_alloc(ctx, &d_idx, n));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_code, n));
+    const int64_t ntile = (L + HS_TILE - 1) / HS_TILE;
+    export_kernel<<<(unsigned)ntile, HS_TILE, 0, ctx->stream>>>(contig, p->h_tile_base[contig], p->d_col_base,
+                                                               p->d_contig_len, p->d_contig_read_off, p->d_tile_off,
+                                                               p->d_tile_reads, p->d_read_start, p->d_read_end,
+                                                               p->d_row_base, p->d_codes, p->d_col_off, d_idx, d_code);
+    HS_LAUNCH_CHECK(ctx);
+    HS_CUDA(ctx, hs_d2h(ctx, read_idx, d_idx, n));
+    HS_CUDA(ctx, hs_d2h(ctx, code, d_code, n));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    hs_free(ctx, d_idx);
+    hs_free(ctx, d_code);
+    return HSGPU_OK;
+}
+
+int hsgpu_pileup_extract_columns(hsgpu_pileup* p, int32_t contig, int32_t n_cols, const int32_t* pos,
+                                 int64_t cell_capacity, int64_t* off, uint32_t* read_idx, uint8_t* code) {
+    if (!p || contig < 0 || contig >= p->n_contigs || n_cols < 0 || !off) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = p->ctx;
+    if (!p->ranked) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_pileup_extract_columns: call hsgpu_column_rank first");
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    off[0] = 0;
+    if (n_cols == 0) return HSGPU_OK;
+    const int64_t L = p->h_contig_len[contig];
+    for (int i = 0; i < n_cols; i++)
+        if (pos[i] < 0 || pos[i] >= L) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pileup_extract_columns: position out of range");
+    int32_t* d_pos = nullptr;
+    int64_t* d_off = nullptr;
+    HS_CUDA(ctx, hs_alloc(ctx, &d_pos, n_cols));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_off, n_cols + 1));
+    HS_CUDA(ctx, hs_h2d(ctx, d_pos, pos, n_cols));
+    gather_depth_kernel<<<(n_cols + 255) / 256, 256, 0, ctx->stream>>>(n_cols, d_pos, p->h_col_base[contig], p->d_depth,
+                                                                       d_off);
+    HS_LAUNCH_CHECK(ctx);
+    HS_CUDA(ctx, hs_d2h(ctx, off + 1, d_off, n_cols));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n_cols; i++) off[i + 1] += off[i];  // depths -> offsets (n_cols is small)
+    const int64_t n = off[n_cols];
+    int rc = HSGPU_OK;
+    if (n > cell_capacity || !read_idx || !code) {
+        if (n > 0) {
+            hs_set_error(ctx, "hsgpu_pileup_extract_columns: cell_capacity too small");
+            rc = HSGPU_ERR_CAPACITY;
+        }
+    } else if (n > 0) {
+        uint32_t* d_idx = nullptr;
+        uint8_t* d_code = nullptr;
+        HS_CUDA(ctx, hs_alloc(ctx, &d_idx, n));
+        HS_CUDA(ctx, hs_alloc(ctx, &d_code, n));
+        HS_CUDA(ctx, hs_h2d(ctx, d_off, off, n_cols + 1));
+        extract_kernel<<<(n_cols + 7) / 8, 256, 0, ctx->stream>>>(n_cols, d_pos, p->h_tile_base[contig],
+                                                                  p->h_contig_read_off[contig], p->d_tile_off,
+                                                                  p->d_tile_reads, p->d_read_start, p->d_read_end,
+                                                                  p->d_row_base, p->d_codes, d_off, d_idx, d_code);
+        HS_LAUNCH_CHECK(ctx);
+        HS_CUDA(ctx, hs_d2h(ctx, read_idx, d_idx, n));
+        HS_CUDA(ctx, hs_d2h(ctx, code, d_code, n));
+        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        hs_free(ctx, d_idx);
+        hs_free(ctx, d_code);
+    }
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    hs_free(ctx, d_pos);
+    hs_free(ctx, d_off);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// Shared host/device plumbing for libhsgpu (sm_100a only; no CPU fallback anywhere in this library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hsgpu.h"
+
+#define HS_TILE 128        // columns per pileup tile (one CTA of the column kernels)
+#define HS_ALIGN 16        // every pileup row is padded to 16-byte boundaries in column space
+#define HS_NCODES 125      // 3-mer codes '!'..'!'+124
+#define HS_CODE0 33
+
+struct hsgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 0;
+};
+
+void hs_set_error(hsgpu_ctx* ctx, const std::string& msg);
+int hs_cuda_fail(hsgpu_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
+
+#define HS_CUDA(ctx, call)                                                        \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) return hs_cuda_fail((ctx), _e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define HS_LAUNCH_CHECK(ctx)                                                      \
+    do {                                                                          \
+        (ctx)->launches++;                                                        \
+        cudaError_t _e = cudaGetLastError();                                      \
+        if (_e != cudaSuccess) return hs_cuda_fail((ctx), _e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define HS_FAIL(ctx, code, msg)      \
+    do {                             \
+        hs_set_error((ctx), (msg));  \
+        return (code);               \
+    } while (0)
+
+// stream-ordered device allocation helpers
+template <typename T>
+static inline cudaError_t hs_alloc(hsgpu_ctx* ctx, T** p, int64_t n) {
+    if (n <= 0) n = 1;
+    return cudaMallocAsync((void**)p, (size_t)n * sizeof(T), ctx->stream);
+}
+template <typename T>
+static inline void hs_free(hsgpu_ctx* ctx, T*& p) {
+    if (p) cudaFreeAsync((void*)p, ctx->stream);
+    p = nullptr;
+}
+template <typename T>
+static inline cudaError_t hs_h2d(hsgpu_ctx* ctx, T* dst, const T* src, int64_t n) {
+    if (n <= 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+}
+template <typename T>
+static inline cudaError_t hs_d2h(hsgpu_ctx* ctx, T* dst, const T* src, int64_t n) {
+    if (n <= 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream);
+}
+
+// exclusive prefix sums on the device (scan.cu). out may alias in. total (device pointer, may be
+// null) receives the grand total.
+int hs_exclusive_scan_i64(hsgpu_ctx* ctx, const int64_t* in, int64_t* out, int64_t n, int64_t* total);
+int hs_exclusive_scan_u32_to_i64(hsgpu_ctx* ctx, const uint32_t* in, int64_t* out, int64_t n, int64_t* total);
+
+// ---- device helpers ----------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ int hs_base2(const uint32_t* __restrict__ words, int64_t i) {
+    return (int)((__ldg(words + (i >> 4)) >> (2 * (int)(i & 15))) & 3u);
+}
+__device__ __forceinline__ int hs_warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ long long hs_warp_incl_scan64(long long v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        long long t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ long long hs_warp_sum64(long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+#endif
+
+// the device-resident pileup of a batch of contigs
+struct hsgpu_pileup {
+    hsgpu_ctx* ctx = nullptr;
+    int32_t n_contigs = 0;
+    int64_t n_reads = 0;
+    int64_t n_cols = 0;    // sum of contig lengths
+    int64_t n_tiles = 0;
+    int64_t n_cigar = 0;
+    bool built = false, ranked = false;
+    float auto_threshold = 0.33f;
+
+    // host mirrors of the small per-contig arrays
+    std::vector<int32_t> h_contig_len;
+    std::vector<int64_t> h_contig_read_off, h_col_base, h_tile_base;
+    std::vector<int64_t> h_stats;  // 3 per contig: distance, aligned, cells
+
+    // inputs on the device
+    int32_t* d_contig_len = nullptr;
+    uint32_t* d_contig_bases = nullptr;
+    int64_t* d_contig_word_off = nullptr;
+    int64_t* d_contig_read_off = nullptr;
+    int64_t* d_col_base = nullptr;
+    int64_t* d_tile_base = nullptr;
+    int32_t* d_tile_contig = nullptr;
+    int32_t* d_read_contig = nullptr;
+    uint32_t* d_read_bases = nullptr;
+    int64_t* d_read_word_off = nullptr;
+    int32_t* d_read_len = nullptr;
+    uint32_t* d_cigar = nullptr;
+    int64_t* d_cigar_off = nullptr;
+    int32_t* d_read_start = nullptr;
+    uint8_t* d_read_strand = nullptr;
+
+    // pileup proper
+    int32_t* d_read_end = nullptr;    // positionOfReads[n].second
+    int64_t* d_row_alloc = nullptr;   // bytes reserved per read (multiple of 16), then its exclusive scan
+    int64_t* d_row_base = nullptr;    // codes[row_base[r] + q] = cell of read r at column q (row_base % 16 == 0)
+    uint8_t* d_codes = nullptr;
+    int64_t codes_bytes = 0;
+    unsigned long long* d_stats = nullptr;  // 3 per contig
+
+    // tile index: reads overlapping each 128-column tile, ascending
+    int64_t* d_tile_off = nullptr;
+    int32_t* d_tile_reads = nullptr;
+    int64_t tile_entries = 0;
+
+    // column summaries (call_variants)
+    uint8_t* d_k0 = nullptr;
+    uint8_t* d_k1 = nullptr;
+    uint8_t* d_flags = nullptr;
+    uint32_t* d_counts = nullptr;  // c0,c1,c2 per column
+    uint32_t* d_depth = nullptr;   // cells per column
+    int32_t* d_min_reads = nullptr;
+    int32_t* d_suspect_pos = nullptr;   // per contig region [col_base[c]/6 + 8c ...)
+    uint8_t* d_suspect_auto = nullptr;
+    int32_t* d_n_suspects = nullptr;
+    unsigned long long* d_depth_sum = nullptr;
+    std::vector<int64_t> h_suspect_base;
+    int64_t* d_suspect_base = nullptr;
+    int64_t* d_col_off = nullptr;  // exclusive scan of d_depth (lazy, for export)
+    bool have_col_off = false;
+};
+
+// column flags
+#define HS_FLAG_CANDIDATE 1  // passes :525-528 (everything but the spacing rule)
+#define HS_FLAG_AUTO 2       // c1 > u*c0 (:531)
+#define HS_FLAG_RESCUE 4     // rescue pre-filter of loop 4 (:751-752)
+#define HS_FLAG_SUSPECT 8    // candidate that also passed the spacing rule (:529)

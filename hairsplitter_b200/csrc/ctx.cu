@@ -1,0 +1,232 @@
+// Context management, host-side packing helpers and device prefix sums.
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+static thread_local std::string g_tls_error;
+
+void hs_set_error(hsgpu_ctx* ctx, const std::string& msg) {
+    g_tls_error = msg;
+    if (ctx) ctx->err = msg;
+}
+
+int hs_cuda_fail(hsgpu_ctx* ctx, cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    hs_set_error(ctx, buf);
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? HSGPU_ERR_NO_DEVICE : HSGPU_ERR_CUDA;
+}
+
+extern "C" {
+
+int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
+    if (!out) return HSGPU_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        hs_set_error(nullptr, "libhsgpu: no CUDA device available (this library has no CPU fallback)");
+        return HSGPU_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        hs_set_error(nullptr, "libhsgpu: device index out of range");
+        return HSGPU_ERR_ARG;
+    }
+    cudaDeviceProp prop;
+    HS_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "libhsgpu: device %d (%s) is sm_%d%d; kernels are built for sm_100a only", device,
+                 prop.name, prop.major, prop.minor);
+        hs_set_error(nullptr, buf);
+        return HSGPU_ERR_NO_DEVICE;
+    }
+    HS_CUDA(nullptr, cudaSetDevice(device));
+    hsgpu_ctx* ctx = new hsgpu_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return hs_cuda_fail(nullptr, e, "cudaStreamCreate", __FILE__, __LINE__);
+    }
+    // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return HSGPU_OK;
+}
+
+void hsgpu_ctx_destroy(hsgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* hsgpu_last_error(hsgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_tls_error.c_str(); }
+
+int hsgpu_sync(hsgpu_ctx* ctx) {
+    if (!ctx) return HSGPU_ERR_ARG;
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HSGPU_OK;
+}
+
+int64_t hsgpu_launch_count(hsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* hsgpu_stream(hsgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int hsgpu_host_alloc(void** out, int64_t bytes) {
+    if (!out || bytes < 0) return HSGPU_ERR_ARG;
+    cudaError_t e = cudaHostAlloc(out, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault);
+    if (e != cudaSuccess) return hs_cuda_fail(nullptr, e, "cudaHostAlloc", __FILE__, __LINE__);
+    return HSGPU_OK;
+}
+void hsgpu_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+void hsgpu_pack_bases_ascii(const char* seq, int64_t n, uint32_t* out) {
+    int64_t nw = (n + 15) / 16;
+    for (int64_t w = 0; w < nw; w++) {
+        uint32_t v = 0;
+        int64_t lim = n - w * 16 < 16 ? n - w * 16 : 16;
+        for (int64_t j = 0; j < lim; j++) {
+            uint32_t b;
+            switch (seq[w * 16 + j]) {  // src/sequence.cpp:16-21: anything but A, C, G packs as T
+                case 'A': b = 0; break;
+                case 'C': b = 1; break;
+                case 'G': b = 2; break;
+                default: b = 3; break;
+            }
+            v |= b << (2 * j);
+        }
+        out[w] = v;
+    }
+}
+
+void hsgpu_pack_bases_codes(const uint8_t* codes, int64_t n, uint32_t* out) {
+    int64_t nw = (n + 15) / 16;
+    for (int64_t w = 0; w < nw; w++) {
+        uint32_t v = 0;
+        int64_t lim = n - w * 16 < 16 ? n - w * 16 : 16;
+        for (int64_t j = 0; j < lim; j++) v |= (uint32_t)(codes[w * 16 + j] & 3) << (2 * j);
+        out[w] = v;
+    }
+}
+
+int64_t hsgpu_parse_cigar(const char* cigar, uint32_t* out, int64_t capacity) {
+    if (!cigar) return HSGPU_ERR_ARG;
+    if (cigar[0] == '*' && cigar[1] == 0) return 0;  // src/tools.cpp:29-31
+    static const char* letters = "MIDNSHP=X";
+    int64_t n = 0;
+    uint64_t num = 0;
+    bool have = false;
+    for (const char* c = cigar; *c; c++) {
+        if (*c >= '0' && *c <= '9') {
+            num = num * 10 + (uint64_t)(*c - '0');
+            have = true;
+            if (num >= (1ull << 28)) return HSGPU_ERR_LIMIT;
+        } else {
+            const char* l = strchr(letters, *c);
+            if (!l || !have) return HSGPU_ERR_ARG;
+            if (n >= capacity) return HSGPU_ERR_CAPACITY;
+            out[n++] = (uint32_t)(num << 4) | (uint32_t)(l - letters);
+            num = 0;
+            have = false;
+        }
+    }
+    return n;
+}
+
+}  // extern "C"
+
+// ---- device exclusive scan ----------------------------------------------------------------------
+// Three-phase scan with 1024-thread blocks handling 4096 elements each; recursion over block sums.
+#define SCAN_THREADS 1024
+#define SCAN_ITEMS 4
+#define SCAN_BLOCK (SCAN_THREADS * SCAN_ITEMS)
+
+template <typename TIn>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_kernel(const TIn* __restrict__ in, int64_t* __restrict__ out,
+                                                                  int64_t n, int64_t* __restrict__ block_sums) {
+    __shared__ long long warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)tid * SCAN_ITEMS;
+    long long v[SCAN_ITEMS];
+    long long s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = (base + i < n) ? (long long)in[base + i] : 0;
+        s += v[i];
+    }
+    long long incl = hs_warp_incl_scan64(s, lane);
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        long long w = warp_tot[lane];
+        long long wi = hs_warp_incl_scan64(w, lane);
+        warp_tot[lane] = wi - w;
+        if (lane == 31 && block_sums) block_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    long long run = warp_tot[wid] + incl - s;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+}
+
+__global__ void scan_add_kernel(int64_t* __restrict__ out, int64_t n, const int64_t* __restrict__ block_off) {
+    int64_t i = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    long long add = block_off[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++, i += SCAN_THREADS)
+        if (i < n) out[i] += add;
+}
+
+__global__ void scan_total_kernel(const int64_t* block_off, const int64_t* block_sums, int64_t nb, int64_t* total) {
+    *total = block_off[nb - 1] + block_sums[nb - 1];
+}
+
+template <typename TIn>
+static int scan_impl(hsgpu_ctx* ctx, const TIn* in, int64_t* out, int64_t n, int64_t* total) {
+    if (n <= 0) {
+        if (total) HS_CUDA(ctx, cudaMemsetAsync(total, 0, sizeof(int64_t), ctx->stream));
+        return HSGPU_OK;
+    }
+    int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    int64_t* sums = nullptr;
+    int64_t* offs = nullptr;
+    HS_CUDA(ctx, hs_alloc(ctx, &sums, nb));
+    HS_CUDA(ctx, hs_alloc(ctx, &offs, nb));
+    scan_block_kernel<TIn><<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, sums);
+    HS_LAUNCH_CHECK(ctx);
+    if (nb > 1) {
+        int rc = scan_impl<int64_t>(ctx, sums, offs, nb, nullptr);
+        if (rc) return rc;
+        scan_add_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(out, n, offs);
+        HS_LAUNCH_CHECK(ctx);
+    } else {
+        HS_CUDA(ctx, cudaMemsetAsync(offs, 0, sizeof(int64_t), ctx->stream));
+    }
+    if (total) {
+        scan_total_kernel<<<1, 1, 0, ctx->stream>>>(offs, sums, nb, total);
+        HS_LAUNCH_CHECK(ctx);
+    }
+    hs_free(ctx, sums);
+    hs_free(ctx, offs);
+    return HSGPU_OK;
+}
+
+int hs_exclusive_scan_i64(hsgpu_ctx* ctx, const int64_t* in, int64_t* out, int64_t n, int64_t* total) {
+    return scan_impl<int64_t>(ctx, in, out, n, total);
+}
+int hs_exclusive_scan_u32_to_i64(hsgpu_ctx* ctx, const uint32_t* in, int64_t* out, int64_t n, int64_t* total) {
+    return scan_impl<uint32_t>(ctx, in, out, n, total);
+}

@@ -1,0 +1,187 @@
+/* libhsgpu -- B200 (sm_100a) implementation of HairSplitter's data-parallel core behind a C ABI.
+ *
+ * Reference = RolandFaure/Hairsplitter v1.9.22 (paths below are relative to its repository root).
+ * The reference has no plugin API; the boundary this library replaces is the set of C++ module
+ * functions on the hot path (src/call_variants.h:12-76, src/separate_reads.h:13-90) plus the one
+ * real C ABI in the tree, edlib (src/edlib/include/edlib.h:146-271). Each entry point below names
+ * the reference interface it stands in for. INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - every function returns 0 (HSGPU_OK) or a negative hsgpu_status; no exceptions cross the ABI;
+ *     hsgpu_last_error() gives the message of the last failure on that context.
+ *   - plain pointers and sizes only. Input buffers are HOST memory owned by the caller (pageable or
+ *     pinned; hsgpu_host_alloc gives pinned memory) unless a parameter says "device".
+ *   - one hsgpu_ctx per (host thread, GPU); calls on one context are serialised on its CUDA stream,
+ *     different contexts run concurrently, so the reference's OpenMP-over-contigs loops can call in.
+ *   - there is NO CPU fallback: without a usable sm_100-class device hsgpu_ctx_create fails.
+ *
+ * Encodings (identical to the reference's in-memory forms)
+ *   bases   2-bit code of `Sequence` (src/sequence.cpp:13-23): A=0 C=1 G=2 T/other=3, 16 bases per
+ *           little-endian u32 word (base j in bits 2*(j%16)); reverse complement = reversed, 3-b.
+ *   CIGAR   u32 per op = len<<4 | op, op = index in "MIDNSHP=X" (the BAM encoding of the SAM CIGAR
+ *           the reference keeps as a string, src/read.h:23 / src/tools.cpp:27-57).
+ *   codes   pileup cell = '!' + 5*i(c-2) + i(c-1) + 25*i(c0) over "ACGT-" (src/call_variants.cpp:238).
+ */
+#ifndef HSGPU_H
+#define HSGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    HSGPU_OK = 0,
+    HSGPU_ERR_CUDA = -1,       /* a CUDA runtime call failed */
+    HSGPU_ERR_NO_DEVICE = -2,  /* no CUDA device / not compute capability 10.x */
+    HSGPU_ERR_ARG = -3,        /* invalid argument */
+    HSGPU_ERR_CAPACITY = -4,   /* caller buffer too small; sizes were written so the call can be retried */
+    HSGPU_ERR_STATE = -5,      /* stage called out of order (e.g. rank before build) */
+    HSGPU_ERR_LIMIT = -6       /* input exceeds a documented limit */
+} hsgpu_status;
+
+typedef struct hsgpu_ctx hsgpu_ctx;
+typedef struct hsgpu_pileup hsgpu_pileup;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int hsgpu_ctx_create(int device, hsgpu_ctx** out);
+void hsgpu_ctx_destroy(hsgpu_ctx* ctx);
+const char* hsgpu_last_error(hsgpu_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
+int hsgpu_sync(hsgpu_ctx* ctx);
+/* number of kernels launched on this context so far (bench.py's gpu_launches) */
+int64_t hsgpu_launch_count(hsgpu_ctx* ctx);
+/* the CUDA stream of the context as an opaque handle (cudaStream_t), for event timing */
+void* hsgpu_stream(hsgpu_ctx* ctx);
+/* pinned host memory for staging inputs/outputs */
+int hsgpu_host_alloc(void** out, int64_t bytes);
+void hsgpu_host_free(void* p);
+
+/* ---- host-side packing (replaces Sequence::Sequence(string&), src/sequence.cpp:13-23, and the
+ * string form of the CIGAR) ------------------------------------------------------------------ */
+void hsgpu_pack_bases_ascii(const char* seq, int64_t n, uint32_t* out_words); /* ceil(n/16) words */
+void hsgpu_pack_bases_codes(const uint8_t* codes, int64_t n, uint32_t* out_words);
+/* parses a SAM CIGAR string into BAM ops; returns the number of ops or <0; "*" gives 0 ops */
+int64_t hsgpu_parse_cigar(const char* cigar, uint32_t* out_ops, int64_t capacity);
+
+/* ---- pileup: generate_msa (src/call_variants.cpp:50-437) -------------------------------------
+ * A batch of contig chunks with the reads aligned on them (what parse_SAM + parse_reads_on_contig
+ * leave in allOverlaps/allreads for each backbone, src/input_output.cpp:274-569). Reads of contig c
+ * are [contig_read_off[c], contig_read_off[c+1]) and keep the neighbour order n of the reference. */
+typedef struct {
+    int32_t n_contigs;
+    const int32_t* contig_len;        /* [n_contigs] columns L */
+    const uint32_t* contig_bases;     /* packed; contig c starts at word contig_word_off[c] */
+    const int64_t* contig_word_off;   /* [n_contigs+1] */
+    const int64_t* contig_read_off;   /* [n_contigs+1] */
+    int64_t n_reads;
+    const uint32_t* read_bases;       /* packed, ORIGINAL orientation; read r starts at word read_word_off[r] */
+    const int64_t* read_word_off;     /* [n_reads+1] */
+    const int32_t* read_len;          /* [n_reads] bases */
+    const uint32_t* cigar;            /* all ops, concatenated */
+    const int64_t* cigar_off;         /* [n_reads+1] */
+    const int32_t* read_start;        /* [n_reads] Overlap.position_2_1 = POS-1 */
+    const uint8_t* read_strand;       /* [n_reads] Overlap.strand, 1 = forward */
+} hsgpu_pileup_input;
+
+/* copies the batch to the device (asynchronous on the context's stream) */
+int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pileup** out);
+void hsgpu_pileup_destroy(hsgpu_pileup* p);
+
+/* runs the CIGAR walk of every read and writes the device-resident pileup (hot loop A) */
+int hsgpu_pileup_build(hsgpu_pileup* p);
+
+/* per contig: total cells, and the integer sums behind generate_msa's return value
+ * (totalDistance numerator, totalLengthOfAlignment without its initial 1). Any pointer may be NULL. */
+int hsgpu_pileup_stats(hsgpu_pileup* p, int64_t* n_cells, int64_t* distance_sum, int64_t* aligned_sum);
+/* generate_msa's float return value from the two sums (float accumulator, :67-68,434) */
+float hsgpu_mean_distance(int64_t distance_sum, int64_t aligned_sum);
+/* positionOfReads[n].second of every read (:354), i.e. readLimits */
+int hsgpu_pileup_read_ends(hsgpu_pileup* p, int32_t* read_end);
+
+/* the whole pileup of one contig in the reference's own layout (vector<Column>: per column the
+ * ascending neighbour indices and their codes). col_off has L+1 entries and is always written;
+ * cells are written when cell_capacity >= col_off[L], else HSGPU_ERR_CAPACITY. Needs column_rank. */
+int hsgpu_pileup_export(hsgpu_pileup* p, int32_t contig, int64_t cell_capacity, int64_t* col_off,
+                        uint32_t* read_idx, uint8_t* code);
+/* the same for a sorted subset of columns (what output_files / Partition need for SNP columns) */
+int hsgpu_pileup_extract_columns(hsgpu_pileup* p, int32_t contig, int32_t n_cols, const int32_t* pos,
+                                 int64_t cell_capacity, int64_t* off, uint32_t* read_idx, uint8_t* code);
+
+/* ---- allele counting: call_variants (src/call_variants.cpp:447-567) ---------------------------
+ * Per column: histogram of codes, ranking with the reference's tie-breaking (robin_hood iteration
+ * order + libstdc++ std::sort), ref_base/second_base, suspect predicate (:525-529) and "automatic"
+ * flag (:531). mean_error may be NULL (then generate_msa's own value per contig is used, as in
+ * main() :1307-1322), else [n_contigs] floats. Results stay on the device for the next stages. */
+int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_snp_threshold);
+
+/* per-contig results of call_variants: number of suspect columns, depth numerator (cells counted) */
+int hsgpu_column_counts(hsgpu_pileup* p, int32_t* n_suspects, int64_t* depth_sum);
+/* suspect positions of one contig (ascending) and whether each is an "automatic" SNP */
+int hsgpu_suspects(hsgpu_pileup* p, int32_t contig, int32_t capacity, int32_t* pos, uint8_t* is_automatic);
+/* per-column summary of one contig; any pointer may be NULL. counts = c0,c1,c2 interleaved [3L] */
+int hsgpu_column_summary(hsgpu_pileup* p, int32_t contig, uint8_t* ref_base, uint8_t* second_base,
+                         uint32_t* counts, uint32_t* depth);
+
+/* ---- partition x column contingency: distance(Partition&,Column&,char) + computeChiSquare
+ * (src/call_variants.cpp:778-967,1135-1163), as used by keep_only_robust_variants (:577-768) -------
+ * Partitions of one contig as the reference's parallel vectors (Partition::getReads/getPartition/
+ * getMore/getLess, src/Partition.h:36-41): partition k = entries [part_off[k], part_off[k+1]). */
+typedef struct {
+    int32_t n_parts;
+    const int64_t* part_off;   /* [n_parts+1] */
+    const int32_t* read_idx;   /* ascending neighbour indices */
+    const int16_t* state;      /* mostFrequentBases: 1, -1, 0, -2 (masked) */
+    const int32_t* more;       /* moreFrequence */
+    const int32_t* less;       /* lessFrequence */
+} hsgpu_partitions;
+
+typedef struct {
+    int32_t n00, n01, n10, n11;
+    int32_t solid00, solid01, solid10, solid11;
+    uint8_t second_base; /* distancePartition.secondBase; 0 when not augmented */
+    uint8_t augmented;
+    uint8_t pad[2];
+    float chi_square;    /* computeChiSquare of this table */
+} hsgpu_distance;
+
+/* tables for every (column in pos[], partition) pair against ref_base = the column's own ref_base
+ * (how loops 3 and 4 call it, :725,755); out is [n_cols * n_parts], column-major by position. */
+int hsgpu_partition_tables(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions* parts, int32_t n_cols,
+                           const int32_t* pos, hsgpu_distance* out);
+
+/* loops 3+4 of keep_only_robust_variants fused (:721-764): given the suspect positions (snps_in) and
+ * the final partitions, returns the ascending positions of snps_out. kept_capacity bounds `kept`;
+ * *n_kept is always written. */
+int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions* parts, int32_t n_suspects,
+                        const int32_t* suspect_pos, int32_t kept_capacity, int32_t* kept, int32_t* n_kept);
+
+/* ---- read x read counts: list_similarities_and_differences_between_reads3
+ * (src/separate_reads.cpp:374-433) --------------------------------------------------------------
+ * SNP columns of one contig as parsed from the .col file (parse_column_file, :46-190): CSR over SNPs
+ * with neighbour indices and codes, plus ref_base/second_base per SNP. sim/diff are dense
+ * n_reads x n_reads int32 (row-major): similarity = 3*A*At + R*Rt, difference = A*Rt + R*At, zero diagonal. */
+int hsgpu_read_pair_counts(hsgpu_ctx* ctx, int32_t n_reads, int32_t n_snps, const int64_t* snp_off,
+                           const uint32_t* read_idx, const uint8_t* code, const uint8_t* ref_base,
+                           const uint8_t* second_base, int32_t* sim, int32_t* diff);
+
+/* ---- realignment: edlibAlign (src/edlib/include/edlib.h:146-271, src/edlib/src/edlib.cpp:142-297)
+ * Batch of (query, target) pairs, results with edlib's exact field semantics. Modes/tasks use edlib's
+ * numeric values: mode 0 NW, 1 SHW, 2 HW; task 0 DISTANCE, 1 LOC, 2 PATH. */
+typedef struct {
+    int32_t status;         /* EDLIB_STATUS_OK = 0 */
+    int32_t edit_distance;  /* -1 if larger than k */
+    int32_t n_locations;
+    int32_t alignment_length;
+    int64_t loc_off;        /* offset into end_locations / start_locations */
+    int64_t aln_off;        /* offset into alignment */
+} hsgpu_edlib_result;
+
+int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const char* queries, const int64_t* query_off,
+                            const char* targets, const int64_t* target_off, int32_t k, int32_t mode, int32_t task,
+                            hsgpu_edlib_result* results, int32_t* end_locations, int32_t* start_locations,
+                            int64_t loc_capacity, uint8_t* alignment, int64_t aln_capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSGPU_H */

@@ -509,6 +509,47 @@ int hso_rescue_prefilter(int32_t ref_base, int32_t second_base) {
             (second_base / 5 % 5 != ref_base % 5 && second_base / 25 % 5 != ref_base % 5));
 }
 
+/* Loops 3 and 4 of keep_only_robust_variants, src/call_variants.cpp:718-764, given the final
+ * partitions (loops 1-2 are sequential host logic and are not restated here). */
+int32_t hso_robust_filter(int32_t L, const int64_t* col_off, const uint32_t* read_idx, const uint8_t* code,
+                          const uint8_t* ref_base, const uint8_t* second_base, int32_t n_parts,
+                          const int64_t* part_off, const int32_t* p_idx, const int16_t* p_state,
+                          const int32_t* p_more, const int32_t* p_less, int32_t n_suspects,
+                          const int32_t* suspect_pos, int32_t* kept) {
+    if (n_parts == 0) return 0; /* :640-642 */
+    int32_t* tmp = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_suspects + 1));
+    int32_t ntmp = 0, nk = 0, d[10];
+    for (int32_t i = 0; i < n_suspects; i++) { /* :721-738 */
+        int32_t pos = suspect_pos[i];
+        int32_t nc = (int32_t)(col_off[pos + 1] - col_off[pos]);
+        for (int32_t p = 0; p < n_parts; p++) {
+            int64_t a = part_off[p];
+            hso_distance((int32_t)(part_off[p + 1] - a), p_idx + a, p_state + a, p_more + a, p_less + a, nc,
+                         read_idx + col_off[pos], code + col_off[pos], ref_base[pos], d);
+            float chisqu = hso_chi_square(d[0], d[1], d[2], d[3]);
+            if (d[0] + d[1] + d[2] + d[3] > 0.5 * nc && chisqu > 15) { tmp[ntmp++] = pos; break; }
+        }
+    }
+    int32_t idx = 0;
+    for (int32_t pos = 0; pos < L; pos++) { /* :745-764 */
+        if (idx < ntmp && tmp[idx] == pos) { kept[nk++] = pos; idx++; }
+        else if (hso_rescue_prefilter(ref_base[pos], second_base[pos])) {
+            int32_t nc = (int32_t)(col_off[pos + 1] - col_off[pos]);
+            for (int32_t p = 0; p < n_parts; p++) {
+                int64_t a = part_off[p];
+                hso_distance((int32_t)(part_off[p + 1] - a), p_idx + a, p_state + a, p_more + a, p_less + a, nc,
+                             read_idx + col_off[pos], code + col_off[pos], ref_base[pos], d);
+                if (hso_chi_square(d[0], d[1], d[2], d[3]) > 20.0 && d[2] + d[0] > 4 && d[1] + d[3] > 4) {
+                    kept[nk++] = pos;
+                    break;
+                }
+            }
+        }
+    }
+    free(tmp);
+    return nk;
+}
+
 /* ---------------------------------------------------------------------------------------------
  * Read x read counts: list_similarities_and_differences_between_reads3, src/separate_reads.cpp:374-433.
  * similarity = 3*A*At + R*Rt, difference = A*Rt + R*At, diagonals zeroed; A[r,s] = content==second_base,

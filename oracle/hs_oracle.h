@@ -70,6 +70,14 @@ float hso_chi_square(int32_t n00, int32_t n01, int32_t n10, int32_t n11);
  * indel next to a homopolymer. */
 int hso_rescue_prefilter(int32_t ref_base, int32_t second_base);
 
+/* Loops 3+4 of keep_only_robust_variants (:718-764) for given final partitions (concatenated arrays,
+ * partition p = [part_off[p], part_off[p+1])) and suspect positions; kept receives snps_out positions. */
+int32_t hso_robust_filter(int32_t L, const int64_t* col_off, const uint32_t* read_idx, const uint8_t* code,
+                          const uint8_t* ref_base, const uint8_t* second_base, int32_t n_parts,
+                          const int64_t* part_off, const int32_t* p_idx, const int16_t* p_state,
+                          const int32_t* p_more, const int32_t* p_less, int32_t n_suspects,
+                          const int32_t* suspect_pos, int32_t* kept);
+
 /* list_similarities_and_differences_between_reads3, src/separate_reads.cpp:374-433, dense output.
  * SNP columns given as CSR (snp_off, read_idx, code) with per-SNP ref_base/second_base.
  * sim/diff are n_reads x n_reads int32, row-major (symmetric, zero diagonal). */

@@ -59,6 +59,10 @@ class Oracle:
         L.hso_chi_square.argtypes = [C.c_int32] * 4
         L.hso_rescue_prefilter.restype = C.c_int
         L.hso_rescue_prefilter.argtypes = [C.c_int32, C.c_int32]
+        L.hso_robust_filter.restype = C.c_int32
+        L.hso_robust_filter.argtypes = [C.c_int32] + [C.c_void_p] * 5 + [C.c_int32] + [C.c_void_p] * 5 + [C.c_int32,
+                                                                                                       C.c_void_p,
+                                                                                                       C.c_void_p]
         L.hso_read_pair_counts.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 7
 
     # -- pileup ---------------------------------------------------------------------------------
@@ -145,6 +149,27 @@ class Oracle:
 
     def rescue_prefilter(self, ref_base, second_base):
         return bool(self.lib.hso_rescue_prefilter(int(ref_base), int(second_base)))
+
+    def robust_filter(self, col_off, read_idx, code, ref_base, second_base, parts, suspect_pos):
+        col_off = _arr(col_off, np.int64)
+        read_idx = _arr(read_idx, np.uint32)
+        code = _arr(code, np.uint8)
+        ref_base = _arr(ref_base, np.uint8)
+        second_base = _arr(second_base, np.uint8)
+        suspect_pos = _arr(suspect_pos, np.int32)
+        n = len(parts)
+        off = np.zeros(n + 1, dtype=np.int64)
+        if n:
+            np.cumsum([len(q["read_idx"]) for q in parts], out=off[1:])
+        cat = lambda k, dt: (np.concatenate([_arr(q[k], dt) for q in parts]) if n and off[-1] else np.zeros(1, dt))
+        idx, st, mo, le = cat("read_idx", np.int32), cat("state", np.int16), cat("more", np.int32), cat("less", np.int32)
+        Lc = col_off.shape[0] - 1
+        kept = np.zeros(Lc + 1, dtype=np.int32)
+        nk = self.lib.hso_robust_filter(Lc, col_off.ctypes.data, read_idx.ctypes.data, code.ctypes.data,
+                                        ref_base.ctypes.data, second_base.ctypes.data, n, off.ctypes.data,
+                                        idx.ctypes.data, st.ctypes.data, mo.ctypes.data, le.ctypes.data,
+                                        suspect_pos.shape[0], suspect_pos.ctypes.data, kept.ctypes.data)
+        return kept[:nk]
 
     def read_pair_counts(self, n_reads, snp_off, read_idx, code, ref_base, second_base):
         snp_off = _arr(snp_off, np.int64)

@@ -1,0 +1,100 @@
+"""CPU tests of the host side of libhsgpu: the library loads without a GPU, exports every symbol the
+header declares, fails loudly instead of falling back, and its ranking code (rank.cuh, the same source
+the kernels compile) agrees with the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from hairsplitter_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.load()
+    header = open(os.path.join(ROOT, "include", "hsgpu.h")).read()
+    declared = sorted(set(re.findall(r"\b(hsgpu_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(declared) == sorted(api.EXPORTS)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.HsgpuError):
+        api.Context(0)
+
+
+def test_pack_bases_and_parse_cigar():
+    lib = api.load()
+    seq = b"ACGTNACGTTTGACCAGTNNA"
+    out = np.zeros(2, np.uint32)
+    lib.hsgpu_pack_bases_ascii(seq, len(seq), out.ctypes.data)
+    codes = np.array([{65: 0, 67: 1, 71: 2}.get(c, 3) for c in seq], dtype=np.uint8)
+    assert np.array_equal(out, api.pack_codes(codes))
+    out2 = np.zeros(2, np.uint32)
+    lib.hsgpu_pack_bases_codes(codes.ctypes.data, len(seq), out2.ctypes.data)
+    assert np.array_equal(out, out2)
+    unpacked = [(int(out[j // 16]) >> (2 * (j % 16))) & 3 for j in range(len(seq))]
+    assert unpacked == list(codes)
+    ops = np.zeros(16, np.uint32)
+    n = lib.hsgpu_parse_cigar(b"12S30M2I1D5=1X7H", ops.ctypes.data, 16)
+    assert n == 7
+    assert [(int(o) >> 4, "MIDNSHP=X"[int(o) & 15]) for o in ops[:n]] == [(12, "S"), (30, "M"), (2, "I"), (1, "D"),
+                                                                           (5, "="), (1, "X"), (7, "H")]
+    assert lib.hsgpu_parse_cigar(b"*", ops.ctypes.data, 16) == 0
+    assert lib.hsgpu_parse_cigar(b"5M", ops.ctypes.data, 0) == -4
+    assert lib.hsgpu_parse_cigar(b"5Q", ops.ctypes.data, 16) == -3
+
+
+def test_mean_distance_float_semantics(oracle):
+    lib = api.load()
+    for d, a in [(0, 0), (5, 100), (1234567, 17000000), (16777216, 2 ** 27), (20000000, 2 ** 28)]:
+        assert np.float32(lib.hsgpu_mean_distance(d, a)).tobytes() == np.float32(oracle.mean_distance(d, a)).tobytes()
+
+
+def test_ranking_source_matches_oracle(oracle):
+    """rank.cuh compiled for the host (the kernels compile the same header)"""
+    lib = api.load()
+    rng = np.random.default_rng(0)
+    for it in range(3000):
+        n = int(rng.integers(1, 40 if it % 20 else 126))
+        keys = (rng.permutation(125)[:n] + 33).astype(np.uint8)
+        out = np.zeros(140, np.uint8)
+        k = lib.hsgpu_debug_rh_order(keys.ctypes.data, n, out.ctypes.data)
+        assert np.array_equal(out[:k], oracle.rh_order(keys))
+    for it in range(3000):
+        n = int(rng.integers(1, 129))
+        keys = rng.permutation(256)[:n].astype(np.uint8)
+        counts = rng.integers(0, rng.integers(1, 8), n).astype(np.int32)
+        k2, c2 = keys.copy(), counts.copy()
+        lib.hsgpu_debug_sort_desc(k2.ctypes.data, c2.ctypes.data, n)
+        a = oracle.sort_desc(keys, counts)
+        assert np.array_equal(a[0], k2) and np.array_equal(a[1], c2)
+    for it in range(3000):
+        depth = int(rng.integers(0, 90))
+        ncodes = int(rng.integers(1, 30 if it % 10 else 125))
+        alphabet = (rng.permutation(125)[:ncodes] + 33).astype(np.uint8)
+        w = rng.random(ncodes) ** 3
+        col = rng.choice(alphabet, size=depth, p=w / w.sum()).astype(np.uint8)
+        out = np.zeros(5, np.int32)
+        lib.hsgpu_debug_rank_column(col.ctypes.data, depth, out.ctypes.data)
+        assert np.array_equal(out, oracle.column_rank(col)), col
+
+
+def test_synthetic_generator_is_self_consistent():
+    """every CIGAR consumes exactly its read and stays inside the contig"""
+    import cases
+    for cb in (cases.small_case(), cases.hifi_case(), cases.small_case(seed=12, eqx=True)):
+        rl = cb.read_len()
+        for i in range(cb.n_reads):
+            ops = cb.cigar[cb.cigar_off[i]:cb.cigar_off[i + 1]]
+            ln, op = ops >> 4, ops & 15
+            assert int(ln[np.isin(op, [0, 1, 4, 5, 7, 8])].sum()) == int(rl[i])
+            assert cb.start[i] + int(ln[np.isin(op, [0, 2, 7, 8])].sum()) <= cb.length
