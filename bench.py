@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on B200 (contract: see the task statement / DESIGN.md section "Measurement").
+
+A step = one pass of the pileup path (generate_msa + call_variants counting/ranking, hot loops A+B of
+SURVEY.md section 8) over one batch of synthetic input: BASELINE.json configs[1], a 5 Mb bacterial genome
+cut into 17 contig chunks (<= 300 kb), 2 strains 1 % apart, ONT-like reads (10 kb mean, 10 % error), 60x.
+Metric: pileup windows/s, window = 2000 columns x depth, value = columns / 2000 / s.
+
+  value   inputs resident in HBM, CUDA-event timed on the library's stream (hsgpu_pileup_build +
+          hsgpu_column_rank per step)
+  e2e     the same through the C ABI from pinned HOST buffers: hsgpu_pileup_create (H2D) + build + rank +
+          D2H of the per-contig results (suspect lists, counts), every step
+  roofline / kernels   per-kernel event timing (hsgpu_profile_enable) over a second pass of the same steps
+  cpu_baseline         the reference's own generate_msa + call_variants (oracle/_ref) or the C oracle
+                       port, on the host cores, on a bounded sample of the same workload
+
+`--impl reference` times only the CPU reference arm and prints the same JSON shape.
+Multi-GPU (torchrun): contig chunks shard with no data-path collective; every rank processes its own
+genome of the same shape (weak scaling); value = columns of all ranks / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WINDOW = 2000  # sizeOfWindow, reference src/separate_reads.cpp:1485
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (testing only)")
+    ap.add_argument("--cpu-sample-chunks", type=int, default=0, help="chunks in the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for i, n in enumerate(names):
+                    if r[5 + i].lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(chunks, n_threads, repeat=1):
+    """generate_msa + call_variants of the reference (oracle/_ref) -- or the C oracle port when the
+    compiled reference did not travel -- over `chunks`, one chunk per thread at a time.
+    Returns (windows/s, kind, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    use_ref = pyoracle.ref_available()
+    if use_ref:
+        import ctypes as C
+        L = pyoracle.RefCV.lib()
+        prepared = []
+        for cb in chunks:  # string marshalling is not part of the measured work
+            n = cb.n_reads
+            reads = (C.c_char_p * n)(*[cb.read_str(i).encode() for i in range(n)])
+            cigars = (C.c_char_p * n)(*[cb.cigar_str(i).encode() for i in range(n)])
+            st = np.ascontiguousarray(cb.start, np.int32)
+            sd = np.ascontiguousarray(cb.strand, np.uint8)
+            prepared.append((cb.contig_str().encode(), n, reads, cigars, st, sd))
+
+        def work(a):
+            h = L.hsref_cv_create(a[0], a[1], a[2], a[3], a[4].ctypes.data, a[5].ctypes.data)  # generate_msa
+            L.hsref_cv_call_variants(h, -1.0, 0.33)                                             # call_variants
+            L.hsref_cv_destroy(h)
+    else:
+        O = pyoracle.Oracle()
+        prepared = chunks
+
+        def work(cb):
+            p = O.pileup(cb)
+            O.call_variants(p["col_off"], p["code"], O.mean_distance(*p["stats"]))
+    cols = sum(cb.length for cb in chunks) * repeat
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=n_threads) as ex:
+        for _ in range(repeat):
+            list(ex.map(work, prepared))
+    dt = time.perf_counter() - t0
+    return cols / WINDOW / dt, ("reference" if use_ref else "port"), dt
+
+
+def workload_description(info, chunks):
+    return (f"BASELINE configs[1]: synthetic {info['genome'] / 1e6:g} Mb bacterial genome, {info['strains']} strains "
+            f"1% apart, ONT-like reads {info['mean_len'] / 1000:g} kb mean, {int(info['error'] * 100)}% error, "
+            f"{info['depth']}x; {len(chunks)} contig chunks <= 300 kb")
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads."""
+    if rank != 0:
+        return
+    from hairsplitter_b200 import synth
+    cores = host_cores()
+    n_sample = args.cpu_sample_chunks or max(1, min(cores, 8))
+    chunks, info = synth.make_config(args.config, scale=args.scale, seed=args.config, n_chunks=n_sample)
+    n_threads = min(cores, len(chunks))
+    for _ in range(args.warmup if args.warmup < 1 else 1):  # one warm-up pass is enough for a CPU code path
+        cpu_reference_rate(chunks[:n_threads], n_threads)
+    t_total, cols = 0.0, 0
+    kind = "port"
+    for _ in range(args.steps):
+        rate, kind, dt = cpu_reference_rate(chunks, n_threads)
+        t_total += dt
+        cols += sum(c.length for c in chunks)
+    value = cols / WINDOW / t_total
+    sample = (f"{len(chunks)} of the workload's chunks ({sum(c.length for c in chunks)} columns, "
+              f"{sum(c.n_reads for c in chunks)} reads) per step, generate_msa + call_variants per chunk, "
+              f"one chunk per thread")
+    line = {
+        "impl": "reference", "metric": "pileup_windows_per_s", "value": value, "unit": "windows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_description(info, chunks) if args.scale == 1.0 else f"scaled x{args.scale}",
+                   "window": "2000 columns x depth", "timing": "host wall clock (CPU code path)"},
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": n_threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from hairsplitter_b200 import api, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- workload: every rank gets its own genome of the configured shape (weak scaling) ----
+    t_gen = time.perf_counter()
+    chunks, info = synth.make_config(args.config, scale=args.scale, seed=args.config + 1000 * rank)
+    packed = api.PackedBatch(chunks)
+    t_gen = time.perf_counter() - t_gen
+    n_cols = int(packed.contig_len.sum())
+    ctx = api.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+
+    def step(pu):
+        pu.build()
+        pu.column_rank()
+
+    # ---- value: inputs resident in HBM ----
+    pu = api.Pileup(ctx, packed)
+    for _ in range(max(args.warmup, 0)):
+        step(pu)
+    ctx.sync()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    l0 = ctx.launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step(pu)
+    ev1.record(stream)
+    ctx.sync()
+    barrier()
+    clk = clocks.stop()
+    launches = ctx.launches() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    cells, dist_sum, alen = pu.stats()
+    n_sus, depth_sum = pu.column_counts()
+    assert int(depth_sum.sum()) == int(cells.sum()), "depth numerator must equal the number of pileup cells"
+    assert int(n_sus.sum()) > 0
+
+    # ---- per-kernel timing over a second pass of the same steps ----
+    ctx.profile(True)
+    for _ in range(args.steps):
+        step(pu)
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    n_cells = int(cells.sum())
+    tile_entries = None
+    alg_bytes = {
+        # 1 B code out + 2-bit read base in + 2-bit contig base in per cell, 4 B per CIGAR op, ~48 B metadata per read
+        "pileup_kernel": n_cells * 1.0 + packed.read_bases.nbytes + n_cells * 0.25 + packed.cigar.nbytes
+        + packed.n_reads * 48,
+        # 1 B code in per cell (+ tile padding not counted), 4 B per (tile, read) index entry, 19 B summary out per column
+        "column_rank_kernel": n_cells * 1.0 + (n_cells / 128.0 + packed.n_reads) * 4 + n_cols * 19.0,
+    }
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    kernels = []
+    for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        k = {"name": name, "launches_per_step": n / max(args.steps, 1), "ms_per_step": ms / max(args.steps, 1)}
+        if name in alg_bytes and n:
+            k["alg_bytes_per_launch"] = alg_bytes[name]
+            k["achieved_gbs"] = alg_bytes[name] / (ms / n * 1e-3) / 1e9
+            k["frac_of_hbm_peak"] = k["achieved_gbs"] / hbm_peak
+        kernels.append(k)
+    dom = kernels[0] if kernels else None
+    roofline = None
+    if dom and "achieved_gbs" in dom:
+        roofline = {"kernel": dom["name"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": hbm_peak,
+                    "unit": "GB/s", "frac": dom["achieved_gbs"] / hbm_peak, "peak_source": peak_src,
+                    "traffic": traffic.get(dom["name"]),
+                    "share_of_step": dom["ms_per_step"] / sum(k["ms_per_step"] for k in kernels),
+                    "note": "per-launch duration from CUDA events on the launching stream, second pass of the same steps"}
+    pu.close()
+
+    # ---- e2e: host buffers -> C ABI -> host results, every step ----
+    pinned = api.PackedBatch.__new__(api.PackedBatch)
+    pinned.__dict__.update(packed.__dict__)
+    keep = []
+    for name in ("contig_len", "contig_bases", "contig_word_off", "contig_read_off", "read_bases", "read_word_off",
+                 "read_len", "cigar", "cigar_off", "read_start", "read_strand"):
+        src = getattr(packed, name)
+        t = torch.empty(max(src.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        arr = t.numpy()[:src.nbytes].view(src.dtype).reshape(src.shape)
+        arr[...] = src
+        keep.append(t)
+        setattr(pinned, name, arr)
+
+    def e2e_step():
+        p = api.Pileup(ctx, pinned)      # H2D of the whole batch
+        p.build()
+        p.column_rank()
+        ns, ds = p.column_counts()       # D2H
+        got = 0
+        for ci in range(pinned.n_contigs):
+            pos, au = p.suspects(ci)     # D2H of the call_variants result
+            got += pos.nbytes + au.nbytes
+        p.close()
+        return got + ns.nbytes + ds.nbytes
+
+    for _ in range(min(args.warmup, 3)):
+        d2h_bytes = e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        d2h_bytes = e2e_step()
+    e1.record(stream)
+    ctx.sync()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    # ---- max over ranks ----
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
+    cols_t = torch.tensor([float(n_cols)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cols_t, op=dist.ReduceOp.SUM)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    total_cols = float(cols_t[0])
+
+    if rank == 0:
+        value = total_cols * args.steps / WINDOW / (ms_total * 1e-3)
+        e2e_value = total_cols * args.steps / WINDOW / (e2e_ms * 1e-3)
+        line = {
+            "metric": "pileup_windows_per_s", "value": value, "unit": "windows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {
+                "workload": workload_description(info, chunks) if args.scale == 1.0 else f"configs[{args.config - 1}] scaled x{args.scale}",
+                "window": "2000 columns x depth", "columns_per_gpu": n_cols, "reads_per_gpu": packed.n_reads,
+                "cells_per_gpu": n_cells, "step": "hsgpu_pileup_build + hsgpu_column_rank (generate_msa + call_variants)",
+                "l2": "inputs + pileup per step (%.0f MB) exceed the 126 MB L2; no explicit flush" %
+                      ((packed.input_bytes + n_cells) / 1e6),
+                "sharding": "independent contig chunks per rank, no data-path collective",
+                "generation_s": round(t_gen, 1),
+            },
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "windows/s", "ms_per_step": e2e_ms / max(args.steps, 1),
+                    "h2d_bytes_per_step": int(packed.input_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "path": "hsgpu_pileup_create(pinned host buffers) + build + column_rank + column_counts + suspects"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "kernels": kernels,
+        }
+        if world == 1:
+            cores = host_cores()
+            n_sample = args.cpu_sample_chunks or max(1, min(cores, 8, len(chunks)))
+            sample = chunks[:n_sample]
+            n_threads = min(cores, len(sample))
+            rate, kind, dt = cpu_reference_rate(sample, n_threads)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "windows/s", "cores": n_threads, "kind": kind, "seconds": round(dt, 2),
+                "sample": f"first {len(sample)} chunks of the workload ({sum(c.length for c in sample)} columns), "
+                          f"generate_msa + call_variants, one chunk per thread",
+            }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,7 +62,7 @@ EDLIB_RESULT_DTYPE = np.dtype(
 # every symbol include/hsgpu.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "hsgpu_ctx_create", "hsgpu_ctx_destroy", "hsgpu_last_error", "hsgpu_sync", "hsgpu_launch_count", "hsgpu_stream",
-    "hsgpu_host_alloc", "hsgpu_host_free", "hsgpu_pack_bases_ascii", "hsgpu_pack_bases_codes", "hsgpu_parse_cigar",
+    "hsgpu_profile_enable", "hsgpu_profile_report", "hsgpu_host_alloc", "hsgpu_host_free", "hsgpu_pack_bases_ascii", "hsgpu_pack_bases_codes", "hsgpu_parse_cigar",
     "hsgpu_pileup_create", "hsgpu_pileup_destroy", "hsgpu_pileup_build", "hsgpu_pileup_stats", "hsgpu_mean_distance",
     "hsgpu_pileup_read_ends", "hsgpu_pileup_export", "hsgpu_pileup_extract_columns", "hsgpu_column_rank",
     "hsgpu_column_counts", "hsgpu_suspects", "hsgpu_column_summary", "hsgpu_partition_tables", "hsgpu_robust_filter",
@@ -90,6 +90,9 @@ def load():
     L.hsgpu_launch_count.restype = i64
     L.hsgpu_stream.argtypes = [vp]
     L.hsgpu_stream.restype = vp
+    L.hsgpu_profile_enable.argtypes = [vp, C.c_int]
+    L.hsgpu_profile_report.argtypes = [vp]
+    L.hsgpu_profile_report.restype = C.c_char_p
     L.hsgpu_host_alloc.argtypes = [C.POINTER(vp), i64]
     L.hsgpu_host_free.argtypes = [vp]
     L.hsgpu_host_free.restype = None
@@ -243,6 +246,17 @@ class Context:
 
     def stream(self) -> int:
         return int(self.lib.hsgpu_stream(self.h) or 0)
+
+    def profile(self, on: bool):
+        self.check(self.lib.hsgpu_profile_enable(self.h, 1 if on else 0), "hsgpu_profile_enable")
+
+    def profile_report(self):
+        """{kernel name: (launches, total_ms)} since the last report"""
+        out = {}
+        for line in self.lib.hsgpu_profile_report(self.h).decode().splitlines():
+            name, n, ms = line.split("\t")
+            out[name] = (int(n), float(ms))
+        return out
 
     def close(self):
         if self.h:

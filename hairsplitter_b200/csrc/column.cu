@@ -328,8 +328,7 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
     }
     HS_CUDA(ctx, cudaMemsetAsync(p->d_depth_sum, 0, sizeof(unsigned long long) * nc, ctx->stream));
     HS_CUDA(ctx, cudaMemsetAsync(p->d_min_reads + nc, 0, sizeof(int32_t), ctx->stream));
-    min_reads_kernel<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(nc, p->d_stats, d_me, p->d_min_reads);
-    HS_LAUNCH_CHECK(ctx);
+    HS_KERNEL(ctx, "min_reads_kernel", min_reads_kernel<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(nc, p->d_stats, d_me, p->d_min_reads));
     if (mean_error) {
         HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // mean_error is caller memory
         hs_free(ctx, d_me);
@@ -361,12 +360,10 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
         a.depth = p->d_depth;
         a.depth_sum = p->d_depth_sum;
         a.error_flag = p->d_min_reads + nc;
-        column_rank_kernel<<<(unsigned)p->n_tiles, HS_TILE, kColumnSmem, ctx->stream>>>(a);
-        HS_LAUNCH_CHECK(ctx);
+        HS_KERNEL(ctx, "column_rank_kernel", column_rank_kernel<<<(unsigned)p->n_tiles, HS_TILE, kColumnSmem, ctx->stream>>>(a));
     }
-    suspect_scan_kernel<<<nc, 32, 0, ctx->stream>>>(p->d_contig_len, p->d_col_base, p->d_suspect_base, p->d_flags,
-                                                    p->d_suspect_pos, p->d_suspect_auto, p->d_n_suspects);
-    HS_LAUNCH_CHECK(ctx);
+    HS_KERNEL(ctx, "suspect_scan_kernel", suspect_scan_kernel<<<nc, 32, 0, ctx->stream>>>(p->d_contig_len, p->d_col_base, p->d_suspect_base, p->d_flags,
+                                                    p->d_suspect_pos, p->d_suspect_auto, p->d_n_suspects));
     p->ranked = true;
     return HSGPU_OK;
 }
@@ -449,11 +446,10 @@ int hsgpu_pileup_export(hsgpu_pileup* p, int32_t contig, int64_t cell_capacity, 
     HS_CUDA(ctx, hs_alloc(ctx, &d_idx, n));
     HS_CUDA(ctx, hs_alloc(ctx, &d_code, n));
     const int64_t ntile = (L + HS_TILE - 1) / HS_TILE;
-    export_kernel<<<(unsigned)ntile, HS_TILE, 0, ctx->stream>>>(contig, p->h_tile_base[contig], p->d_col_base,
+    HS_KERNEL(ctx, "export_kernel", export_kernel<<<(unsigned)ntile, HS_TILE, 0, ctx->stream>>>(contig, p->h_tile_base[contig], p->d_col_base,
                                                                p->d_contig_len, p->d_contig_read_off, p->d_tile_off,
                                                                p->d_tile_reads, p->d_read_start, p->d_read_end,
-                                                               p->d_row_base, p->d_codes, p->d_col_off, d_idx, d_code);
-    HS_LAUNCH_CHECK(ctx);
+                                                               p->d_row_base, p->d_codes, p->d_col_off, d_idx, d_code));
     HS_CUDA(ctx, hs_d2h(ctx, read_idx, d_idx, n));
     HS_CUDA(ctx, hs_d2h(ctx, code, d_code, n));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -478,9 +474,8 @@ int hsgpu_pileup_extract_columns(hsgpu_pileup* p, int32_t contig, int32_t n_cols
     HS_CUDA(ctx, hs_alloc(ctx, &d_pos, n_cols));
     HS_CUDA(ctx, hs_alloc(ctx, &d_off, n_cols + 1));
     HS_CUDA(ctx, hs_h2d(ctx, d_pos, pos, n_cols));
-    gather_depth_kernel<<<(n_cols + 255) / 256, 256, 0, ctx->stream>>>(n_cols, d_pos, p->h_col_base[contig], p->d_depth,
-                                                                       d_off);
-    HS_LAUNCH_CHECK(ctx);
+    HS_KERNEL(ctx, "gather_depth_kernel", gather_depth_kernel<<<(n_cols + 255) / 256, 256, 0, ctx->stream>>>(n_cols, d_pos, p->h_col_base[contig], p->d_depth,
+                                                                       d_off));
     HS_CUDA(ctx, hs_d2h(ctx, off + 1, d_off, n_cols));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < n_cols; i++) off[i + 1] += off[i];  // depths -> offsets (n_cols is small)
@@ -497,11 +492,10 @@ int hsgpu_pileup_extract_columns(hsgpu_pileup* p, int32_t contig, int32_t n_cols
         HS_CUDA(ctx, hs_alloc(ctx, &d_idx, n));
         HS_CUDA(ctx, hs_alloc(ctx, &d_code, n));
         HS_CUDA(ctx, hs_h2d(ctx, d_off, off, n_cols + 1));
-        extract_kernel<<<(n_cols + 7) / 8, 256, 0, ctx->stream>>>(n_cols, d_pos, p->h_tile_base[contig],
+        HS_KERNEL(ctx, "extract_kernel", extract_kernel<<<(n_cols + 7) / 8, 256, 0, ctx->stream>>>(n_cols, d_pos, p->h_tile_base[contig],
                                                                   p->h_contig_read_off[contig], p->d_tile_off,
                                                                   p->d_tile_reads, p->d_read_start, p->d_read_end,
-                                                                  p->d_row_base, p->d_codes, d_off, d_idx, d_code);
-        HS_LAUNCH_CHECK(ctx);
+                                                                  p->d_row_base, p->d_codes, d_off, d_idx, d_code));
         HS_CUDA(ctx, hs_d2h(ctx, read_idx, d_idx, n));
         HS_CUDA(ctx, hs_d2h(ctx, code, d_code, n));
         HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

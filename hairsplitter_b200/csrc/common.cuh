@@ -13,13 +13,25 @@
 #define HS_NCODES 125      // 3-mer codes '!'..'!'+124
 #define HS_CODE0 33
 
+struct HsProfEntry {
+    const char* name;
+    cudaEvent_t begin, end;
+};
+
 struct hsgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
     int sm_count = 0;
+    // optional per-kernel timing (hsgpu_profile_enable): one event pair per launch
+    bool profiling = false;
+    std::vector<HsProfEntry> prof;
+    std::string prof_report;
 };
+
+void hs_prof_begin(hsgpu_ctx* ctx, const char* name);
+void hs_prof_end(hsgpu_ctx* ctx);
 
 void hs_set_error(hsgpu_ctx* ctx, const std::string& msg);
 int hs_cuda_fail(hsgpu_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
@@ -35,6 +47,15 @@ int hs_cuda_fail(hsgpu_ctx* ctx, cudaError_t e, const char* what, const char* fi
         (ctx)->launches++;                                                        \
         cudaError_t _e = cudaGetLastError();                                      \
         if (_e != cudaSuccess) return hs_cuda_fail((ctx), _e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+// launch a kernel: counts it, checks the launch, and brackets it with events when profiling is on
+#define HS_KERNEL(ctx, name, ...)                  \
+    do {                                           \
+        if ((ctx)->profiling) hs_prof_begin((ctx), (name)); \
+        __VA_ARGS__;                               \
+        if ((ctx)->profiling) hs_prof_end((ctx));  \
+        HS_LAUNCH_CHECK(ctx);                      \
     } while (0)
 
 #define HS_FAIL(ctx, code, msg)      \

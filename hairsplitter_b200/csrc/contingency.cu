@@ -483,8 +483,7 @@ int hsgpu_partition_tables(hsgpu_pileup* p, int32_t contig, const hsgpu_partitio
     a.codes = p->d_codes;
     a.k0 = p->d_k0;
     a.out = d_out;
-    partition_tables_kernel<<<n_cols, 128, kTablesSmem, ctx->stream>>>(a);
-    HS_LAUNCH_CHECK(ctx);
+    HS_KERNEL(ctx, "partition_tables_kernel", partition_tables_kernel<<<n_cols, 128, kTablesSmem, ctx->stream>>>(a));
     HS_CUDA(ctx, hs_d2h(ctx, out, d_out, n_out));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     hs_free(ctx, d_pst);
@@ -520,8 +519,7 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     HS_CUDA(ctx, hs_h2d(ctx, d_pos, suspect_pos, n_suspects));
     const int64_t g0 = p->h_col_base[contig];
     if (n_suspects > 0) {
-        set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 1);
-        HS_LAUNCH_CHECK(ctx);
+        HS_KERNEL(ctx, "set_inlist_kernel", set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 1));
     }
     static bool attr = false;
     if (!attr) {
@@ -548,13 +546,10 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     a.depth = p->d_depth;
     a.kept = d_kept;
     const unsigned ntile = (unsigned)((L + HS_TILE - 1) / HS_TILE);
-    robust_filter_kernel<<<ntile, 128, kFilterSmem, ctx->stream>>>(a);
-    HS_LAUNCH_CHECK(ctx);
-    kept_scan_kernel<<<1, 32, 0, ctx->stream>>>((int)L, d_kept, kept_capacity, d_list, d_list + kept_capacity);
-    HS_LAUNCH_CHECK(ctx);
+    HS_KERNEL(ctx, "robust_filter_kernel", robust_filter_kernel<<<ntile, 128, kFilterSmem, ctx->stream>>>(a));
+    HS_KERNEL(ctx, "kept_scan_kernel", kept_scan_kernel<<<1, 32, 0, ctx->stream>>>((int)L, d_kept, kept_capacity, d_list, d_list + kept_capacity));
     if (n_suspects > 0) {
-        set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 0);
-        HS_LAUNCH_CHECK(ctx);
+        HS_KERNEL(ctx, "set_inlist_kernel", set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 0));
     }
     HS_CUDA(ctx, hs_d2h(ctx, n_kept, d_list + kept_capacity, 1));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

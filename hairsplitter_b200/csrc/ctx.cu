@@ -18,7 +18,56 @@ int hs_cuda_fail(hsgpu_ctx* ctx, cudaError_t e, const char* what, const char* fi
     return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? HSGPU_ERR_NO_DEVICE : HSGPU_ERR_CUDA;
 }
 
+void hs_prof_begin(hsgpu_ctx* ctx, const char* name) {
+    HsProfEntry e;
+    e.name = name;
+    cudaEventCreate(&e.begin);
+    cudaEventCreate(&e.end);
+    cudaEventRecord(e.begin, ctx->stream);
+    ctx->prof.push_back(e);
+}
+void hs_prof_end(hsgpu_ctx* ctx) { cudaEventRecord(ctx->prof.back().end, ctx->stream); }
+
 extern "C" {
+
+int hsgpu_profile_enable(hsgpu_ctx* ctx, int on) {
+    if (!ctx) return HSGPU_ERR_ARG;
+    ctx->profiling = on != 0;
+    return HSGPU_OK;
+}
+
+// "name\tlaunches\ttotal_ms\n" per kernel, accumulated since the last report; clears the log
+const char* hsgpu_profile_report(hsgpu_ctx* ctx) {
+    if (!ctx) return "";
+    cudaStreamSynchronize(ctx->stream);
+    std::vector<std::string> names;
+    std::vector<double> ms;
+    std::vector<int64_t> cnt;
+    for (auto& e : ctx->prof) {
+        float t = 0;
+        cudaEventElapsedTime(&t, e.begin, e.end);
+        cudaEventDestroy(e.begin);
+        cudaEventDestroy(e.end);
+        size_t i = 0;
+        for (; i < names.size(); i++)
+            if (names[i] == e.name) break;
+        if (i == names.size()) {
+            names.push_back(e.name);
+            ms.push_back(0);
+            cnt.push_back(0);
+        }
+        ms[i] += t;
+        cnt[i]++;
+    }
+    ctx->prof.clear();
+    ctx->prof_report.clear();
+    for (size_t i = 0; i < names.size(); i++) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s\t%lld\t%.6f\n", names[i].c_str(), (long long)cnt[i], ms[i]);
+        ctx->prof_report += buf;
+    }
+    return ctx->prof_report.c_str();
+}
 
 int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
     if (!out) return HSGPU_ERR_ARG;
@@ -205,19 +254,16 @@ static int scan_impl(hsgpu_ctx* ctx, const TIn* in, int64_t* out, int64_t n, int
     int64_t* offs = nullptr;
     HS_CUDA(ctx, hs_alloc(ctx, &sums, nb));
     HS_CUDA(ctx, hs_alloc(ctx, &offs, nb));
-    scan_block_kernel<TIn><<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, sums);
-    HS_LAUNCH_CHECK(ctx);
+    HS_KERNEL(ctx, "scan_block_kernel<TIn>", scan_block_kernel<TIn><<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, sums));
     if (nb > 1) {
         int rc = scan_impl<int64_t>(ctx, sums, offs, nb, nullptr);
         if (rc) return rc;
-        scan_add_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(out, n, offs);
-        HS_LAUNCH_CHECK(ctx);
+        HS_KERNEL(ctx, "scan_add_kernel", scan_add_kernel<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(out, n, offs));
     } else {
         HS_CUDA(ctx, cudaMemsetAsync(offs, 0, sizeof(int64_t), ctx->stream));
     }
     if (total) {
-        scan_total_kernel<<<1, 1, 0, ctx->stream>>>(offs, sums, nb, total);
-        HS_LAUNCH_CHECK(ctx);
+        HS_KERNEL(ctx, "scan_total_kernel", scan_total_kernel<<<1, 1, 0, ctx->stream>>>(offs, sums, nb, total));
     }
     hs_free(ctx, sums);
     hs_free(ctx, offs);

@@ -165,12 +165,10 @@ extern "C" int hsgpu_read_pair_counts(hsgpu_ctx* ctx, int32_t n_reads, int32_t n
         HS_CUDA(ctx, hs_h2d(ctx, d_code, code, n_cells));
         HS_CUDA(ctx, hs_h2d(ctx, d_rb, ref_base, n_snps));
         HS_CUDA(ctx, hs_h2d(ctx, d_sb, second_base, n_snps));
-        onehot_kernel<<<n_snps, 128, 0, ctx->stream>>>(n_snps, d_off, d_idx, d_code, d_rb, d_sb, s_pad, ld, U, Vs, Vd);
-        HS_LAUNCH_CHECK(ctx);
+        HS_KERNEL(ctx, "onehot_kernel", onehot_kernel<<<n_snps, 128, 0, ctx->stream>>>(n_snps, d_off, d_idx, d_code, d_rb, d_sb, s_pad, ld, U, Vs, Vd));
     }
     dim3 grid(n_pad / PG_BN, n_pad / PG_BM);
-    pair_gemm_kernel<<<grid, 256, 0, ctx->stream>>>(n_reads, ld, K, U, Vs, Vd, d_sim, d_diff);
-    HS_LAUNCH_CHECK(ctx);
+    HS_KERNEL(ctx, "pair_gemm_kernel", pair_gemm_kernel<<<grid, 256, 0, ctx->stream>>>(n_reads, ld, K, U, Vs, Vd, d_sim, d_diff));
     HS_CUDA(ctx, hs_d2h(ctx, sim, d_sim, (int64_t)n_reads * n_reads));
     HS_CUDA(ctx, hs_d2h(ctx, diff, d_diff, (int64_t)n_reads * n_reads));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

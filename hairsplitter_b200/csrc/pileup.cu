@@ -352,17 +352,15 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     int64_t* d_totals = nullptr;
     HS_CUDA(ctx, hs_alloc(ctx, &d_totals, 2));
     if (nr > 0) {
-        span_kernel<<<rblocks, 256, 0, ctx->stream>>>(nr, p->d_cigar, p->d_cigar_off, p->d_read_start, p->d_read_contig,
-                                                      p->d_contig_len, p->d_read_end, p->d_row_alloc);
-        HS_LAUNCH_CHECK(ctx);
+        HS_KERNEL(ctx, "span_kernel", span_kernel<<<rblocks, 256, 0, ctx->stream>>>(nr, p->d_cigar, p->d_cigar_off, p->d_read_start, p->d_read_contig,
+                                                      p->d_contig_len, p->d_read_end, p->d_row_alloc));
     }
     int rc = hs_exclusive_scan_i64(ctx, p->d_row_alloc, p->d_row_alloc, nr, d_totals);
     if (rc) return rc;
     if (p->n_tiles > 0) {
-        tile_index_kernel<false><<<(unsigned)((p->n_tiles + 7) / 8), 256, 0, ctx->stream>>>(
+        HS_KERNEL(ctx, "tile_index_kernel<false>", tile_index_kernel<false><<<(unsigned)((p->n_tiles + 7) / 8), 256, 0, ctx->stream>>>(
             p->n_tiles, p->d_tile_contig, p->d_tile_base, p->d_contig_read_off, p->d_read_start, p->d_read_end,
-            p->d_tile_off, nullptr);
-        HS_LAUNCH_CHECK(ctx);
+            p->d_tile_off, nullptr));
     }
     rc = hs_exclusive_scan_i64(ctx, p->d_tile_off, p->d_tile_off, p->n_tiles, d_totals + 1);
     if (rc) return rc;
@@ -395,14 +393,12 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
         a.row_base = p->d_row_base;
         a.codes = p->d_codes;
         a.stats = p->d_stats;
-        pileup_kernel<<<rblocks, 256, 0, ctx->stream>>>(a);
-        HS_LAUNCH_CHECK(ctx);
+        HS_KERNEL(ctx, "pileup_kernel", pileup_kernel<<<rblocks, 256, 0, ctx->stream>>>(a));
     }
     if (p->n_tiles > 0) {
-        tile_index_kernel<true><<<(unsigned)((p->n_tiles + 7) / 8), 256, 0, ctx->stream>>>(
+        HS_KERNEL(ctx, "tile_index_kernel<true>", tile_index_kernel<true><<<(unsigned)((p->n_tiles + 7) / 8), 256, 0, ctx->stream>>>(
             p->n_tiles, p->d_tile_contig, p->d_tile_base, p->d_contig_read_off, p->d_read_start, p->d_read_end,
-            p->d_tile_off, p->d_tile_reads);
-        HS_LAUNCH_CHECK(ctx);
+            p->d_tile_off, p->d_tile_reads));
     }
     p->built = true;
     return HSGPU_OK;

@@ -52,6 +52,11 @@ int hsgpu_sync(hsgpu_ctx* ctx);
 int64_t hsgpu_launch_count(hsgpu_ctx* ctx);
 /* the CUDA stream of the context as an opaque handle (cudaStream_t), for event timing */
 void* hsgpu_stream(hsgpu_ctx* ctx);
+/* per-kernel timing: when enabled every kernel launch on the context is bracketed by CUDA events;
+ * hsgpu_profile_report returns "name\tlaunches\ttotal_ms\n" lines accumulated since the last report
+ * (the string is owned by the context and valid until the next call) */
+int hsgpu_profile_enable(hsgpu_ctx* ctx, int on);
+const char* hsgpu_profile_report(hsgpu_ctx* ctx);
 /* pinned host memory for staging inputs/outputs */
 int hsgpu_host_alloc(void** out, int64_t bytes);
 void hsgpu_host_free(void* p);
