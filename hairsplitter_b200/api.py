@@ -122,7 +122,7 @@ def load():
     L.hsgpu_edlib_align_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, i64]
     for name in ("hsgpu_debug_rank_column", "hsgpu_debug_rh_order", "hsgpu_debug_sort_desc"):
         getattr(L, name).restype = C.c_int if name == "hsgpu_debug_rh_order" else None
-    L.hsgpu_debug_rank_column.argtypes = [vp, C.c_int, vp]
+    L.hsgpu_debug_rank_column.argtypes = [vp, C.c_int, vp, C.c_int]
     L.hsgpu_debug_rh_order.argtypes = [vp, C.c_int, vp]
     L.hsgpu_debug_sort_desc.argtypes = [vp, vp, C.c_int]
     _lib = L

@@ -33,6 +33,17 @@ struct ColumnArgs {
     uint32_t* depth;
     unsigned long long* depth_sum;
     int32_t* error_flag;
+    const HsRankLut* lut;
+    int32_t* work;             // global column ids that need the literal replay
+    unsigned int* n_work;
+};
+
+struct SmemAcc {
+    const uint8_t* order;
+    const uint16_t* hist;
+    int col;
+    __device__ __forceinline__ int key(int k) const { return order[k * HS_TILE + col] + HS_CODE0; }
+    __device__ __forceinline__ unsigned count(int key) const { return hist[(key - HS_CODE0) * HS_TILE + col]; }
 };
 
 // stage rows [b0, b0+nrows) of the tile into s_tile[row][128]
@@ -57,12 +68,33 @@ __device__ __forceinline__ bool central_base_differs(int k0, int k1) {
     return (k0 % 5 != k1 % 5) && (((k1 - '!') % 5 != 4) || ((k1 / 5 % 5 != k0 % 5) && (k1 / 25 % 5 != k0 % 5)));
 }
 
+__device__ __forceinline__ void write_column(const ColumnArgs& a, int64_t g, int k0, int k1, unsigned c0, unsigned c1,
+                                             unsigned c2, int mr) {
+    a.k0[g] = (uint8_t)k0;
+    a.k1[g] = (uint8_t)k1;
+    a.counts[3 * g + 0] = c0;
+    a.counts[3 * g + 1] = c1;
+    a.counts[3 * g + 2] = c2;
+    const bool cbd = central_base_differs(k0, k1);
+    unsigned f = 0;
+    if (cbd) f |= HS_FLAG_RESCUE;
+    if ((int)c1 > mr && ((int)c1 > (int)c2 * 5 || mr == 2) && cbd) {
+        f |= HS_FLAG_CANDIDATE;
+        if ((float)(int)c1 > __fmul_rn(a.auto_threshold, (float)(int)c0)) f |= HS_FLAG_AUTO;  // :531
+    }
+    a.flags[g] = (uint8_t)f;
+}
+
 __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint4* s_tile = reinterpret_cast<uint4*>(smem);                                   // COL_ROWS * 128 B
     uint16_t* s_hist = reinterpret_cast<uint16_t*>(smem + COL_ROWS * HS_TILE);        // [125][128] u16
     uint8_t* s_order = smem + COL_ROWS * HS_TILE + HS_NCODES * HS_TILE * 2;           // [125][128] u8
     __shared__ unsigned long long s_depth;
+    __shared__ HsRankLut s_lut;
+    __shared__ uint8_t s_work[HS_TILE];
+    __shared__ int s_nwork;
+    __shared__ unsigned s_gbase;
 
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -99,57 +131,38 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
             }
         }
     }
+    // ---- ranking. Ties are decided by the bucket table (rank.cuh); the few columns that need the literal
+    // replay of the reference's map + sort are appended to a global work list and handled by
+    // column_rank_literal_kernel, so that no CTA waits for a straggling replay.
+    __syncthreads();
+    for (int i = tid; i < (int)sizeof(HsRankLut); i += HS_TILE)
+        reinterpret_cast<uint8_t*>(&s_lut)[i] = reinterpret_cast<const uint8_t*>(a.lut)[i];
+    if (tid == 0) s_nwork = 0;
+    __syncthreads();
     const int q = q0 + tid;
+    const int mr = a.min_reads[c];
+    const int64_t gbase = a.col_base[c];
+    bool literal = false;
     if (q < L) {
-        // top three counts; keys 0,1,2 are the reference's dummy entries with count 0 (:492-494)
-        unsigned int c0 = 0, c1 = 0, c2 = 0;
-        int k0 = 0, k1 = 0;
-        for (int k = 0; k < m; k++) {
-            const int idx = s_order[k * HS_TILE + tid];
-            const unsigned int cnt = s_hist[idx * HS_TILE + tid];
-            if (cnt > c0) { c2 = c1; c1 = c0; k1 = k0; c0 = cnt; k0 = idx + HS_CODE0; }
-            else if (cnt > c1) { c2 = c1; c1 = cnt; k1 = idx + HS_CODE0; }
-            else if (cnt > c2) { c2 = cnt; }
-        }
-        if (c0 == c1 || c1 == c2) {
-            // ties among the ranks that matter: replay the reference's map + sort
-            HsRhTable t;
-            hs_rh_new(t);
-            for (int k = 0; k < m; k++) hs_rh_insert(t, (uint8_t)(s_order[k * HS_TILE + tid] + HS_CODE0));
-            hs_rh_insert(t, 0);
-            hs_rh_insert(t, 1);
-            hs_rh_insert(t, 2);
-            uint8_t it[HS_RH_MAXKEYS];
-            uint32_t kc[HS_RH_MAXKEYS];
-            const int n = hs_rh_iterate(t, it);
-            for (int i = 0; i < n; i++) {
-                const int key = it[i];
-                const unsigned int cnt = key >= HS_CODE0 ? s_hist[(key - HS_CODE0) * HS_TILE + tid] : 0u;
-                kc[i] = (cnt << 8) | (unsigned)key;
-            }
-            hs_kc_std_sort(kc, n);
-            k0 = kc[0] & 0xff;
-            k1 = kc[1] & 0xff;
-            c0 = kc[0] >> 8;
-            c1 = kc[1] >> 8;
-            c2 = kc[2] >> 8;
-        }
-        const int64_t g = a.col_base[c] + q;
-        a.k0[g] = (uint8_t)k0;
-        a.k1[g] = (uint8_t)k1;
-        a.counts[3 * g + 0] = c0;
-        a.counts[3 * g + 1] = c1;
-        a.counts[3 * g + 2] = c2;
-        a.depth[g] = depth;
-        const int mr = a.min_reads[c];
-        const bool cbd = central_base_differs(k0, k1);
-        unsigned f = 0;
-        if (cbd) f |= HS_FLAG_RESCUE;
-        if ((int)c1 > mr && ((int)c1 > (int)c2 * 5 || mr == 2) && cbd) {
-            f |= HS_FLAG_CANDIDATE;
-            if ((float)(int)c1 > __fmul_rn(a.auto_threshold, (float)(int)c0)) f |= HS_FLAG_AUTO;  // :531
-        }
-        a.flags[g] = (uint8_t)f;
+        SmemAcc acc{s_order, s_hist, tid};
+        int k0, k1;
+        unsigned c0, c1, c2;
+        literal = hs_rank_fast(acc, m, &s_lut, k0, k1, c0, c1, c2) != 0;
+        if (!literal) write_column(a, gbase + q, k0, k1, c0, c1, c2, mr);
+        a.depth[gbase + q] = depth;
+    }
+    {
+        const unsigned lm = __ballot_sync(0xffffffffu, literal);
+        int wbase = 0;
+        if ((tid & 31) == 0 && lm) wbase = atomicAdd(&s_nwork, __popc(lm));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (literal) s_work[wbase + __popc(lm & ((1u << (tid & 31)) - 1u))] = (uint8_t)tid;
+    }
+    __syncthreads();
+    if (s_nwork > 0) {
+        if (tid == 0) s_gbase = atomicAdd(a.n_work, (unsigned)s_nwork);
+        __syncthreads();
+        if (tid < s_nwork) a.work[s_gbase + tid] = (int32_t)(gbase + q0 + s_work[tid]);
     }
     // depthOfCoverage numerator (:486,565)
     unsigned long long d = depth;
@@ -157,6 +170,61 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
     if ((tid & 31) == 0 && d) atomicAdd(&s_depth, d);
     __syncthreads();
     if (tid == 0 && s_depth) atomicAdd(a.depth_sum + c, s_depth);
+}
+
+// Deferred literal replay: one thread per listed column. The column is re-read from the pileup (a few
+// dozen byte loads) in ascending read order, then the reference's map + sort are replayed (rank.cuh).
+struct LiteralArgs {
+    const int32_t* work;
+    const unsigned int* n_work;
+    int n_contigs;
+    const int64_t* col_base;
+    const int64_t* tile_base;
+    const int64_t* tile_off;
+    const int32_t* tile_reads;
+    const int32_t* read_start;
+    const int32_t* read_end;
+    const int64_t* row_base;
+    const uint8_t* codes;
+    ColumnArgs col;
+};
+
+struct LocalAcc {
+    const uint8_t* order;
+    const uint16_t* cnt;
+    __device__ __forceinline__ int key(int k) const { return order[k]; }
+    __device__ __forceinline__ unsigned count(int key) const { return cnt[key - HS_CODE0]; }
+};
+
+__global__ void __launch_bounds__(128) column_rank_literal_kernel(LiteralArgs a) {
+    const unsigned n = *a.n_work;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int64_t g = a.work[i];
+        int lo = 0, hi = a.n_contigs - 1;  // contig of this column
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (a.col_base[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        const int c = lo;
+        const int q = (int)(g - a.col_base[c]);
+        const int64_t tile = a.tile_base[c] + q / HS_TILE;
+        uint16_t cnt[HS_NCODES];
+        uint8_t order[HS_NCODES];
+        for (int k = 0; k < HS_NCODES; k++) cnt[k] = 0;
+        int m = 0;
+        for (int64_t l = a.tile_off[tile]; l < a.tile_off[tile + 1]; l++) {
+            const int32_t r = a.tile_reads[l];
+            if (a.read_start[r] <= q && q < a.read_end[r]) {
+                const int code = a.codes[a.row_base[r] + q];
+                if (cnt[code - HS_CODE0]++ == 0) order[m++] = (uint8_t)code;
+            }
+        }
+        LocalAcc acc{order, cnt};
+        int k0, k1;
+        unsigned c0, c1, c2;
+        hs_rank_literal(acc, m, k0, k1, c0, c1, c2);
+        write_column(a.col, g, k0, k1, c0, c1, c2, a.col.min_reads[c]);
+    }
 }
 
 // minimumNumberOfReadsToBeConsideredSuspect (:463-466) from generate_msa's float return value
@@ -176,40 +244,81 @@ __global__ void min_reads_kernel(int n_contigs, const unsigned long long* __rest
     min_reads[c] = ((double)me < 0.015) ? 3 : 5;
 }
 
-// The spacing rule `position - posoflastsnp > 5` (:470,529,535) is a greedy left-to-right scan; one
-// warp per contig walks the candidate flags 32 columns at a time.
-__global__ void __launch_bounds__(32) suspect_scan_kernel(const int32_t* __restrict__ contig_len,
-                                                          const int64_t* __restrict__ col_base,
-                                                          const int64_t* __restrict__ suspect_base,
-                                                          uint8_t* __restrict__ flags, int32_t* __restrict__ suspect_pos,
-                                                          uint8_t* __restrict__ suspect_auto,
-                                                          int32_t* __restrict__ n_suspects) {
-    const int c = blockIdx.x, lane = threadIdx.x;
+// The spacing rule `position - posoflastsnp > 5` (:470,529,535) is a greedy left-to-right scan, but its
+// dependencies are short: a candidate with no other candidate in the 5 columns before it is accepted
+// whatever happened earlier, so it starts an independent segment. One thread per column; the thread of a
+// segment head walks its segment (it ends at the first gap of more than 5 candidate-free columns).
+// Column 0 can never be accepted because posoflastsnp starts at -5 (:470).
+__device__ __forceinline__ bool is_candidate(const uint8_t* __restrict__ flags, int64_t g0, int q) {
+    return q > 0 && (flags[g0 + q] & HS_FLAG_CANDIDATE);
+}
+
+__global__ void __launch_bounds__(HS_TILE) suspect_mark_kernel(const int32_t* __restrict__ tile_contig,
+                                                               const int64_t* __restrict__ tile_base,
+                                                               const int64_t* __restrict__ col_base,
+                                                               const int32_t* __restrict__ contig_len,
+                                                               uint8_t* __restrict__ flags) {
+    const int64_t tile = blockIdx.x;
+    const int c = tile_contig[tile];
     const int L = contig_len[c];
-    const int64_t g0 = col_base[c], sb = suspect_base[c];
-    int last = -5, n = 0;
-    for (int q0 = 0; q0 < L; q0 += 32) {
-        const int q = q0 + lane;
-        const unsigned f = (q < L) ? flags[g0 + q] : 0u;
-        unsigned m = __ballot_sync(0xffffffffu, (f & HS_FLAG_CANDIDATE) != 0);
-        unsigned acc = 0;
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            if (q0 + b - last > 5) {
-                acc |= 1u << b;
-                last = q0 + b;
+    const int64_t g0 = col_base[c];
+    const int q = (int)(tile - tile_base[c]) * HS_TILE + threadIdx.x;
+    if (q >= L || !is_candidate(flags, g0, q)) return;
+    for (int d = 1; d <= 5; d++)
+        if (q - d > 0 && (flags[g0 + q - d] & HS_FLAG_CANDIDATE)) return;  // not a segment head
+    flags[g0 + q] |= HS_FLAG_SUSPECT;
+    int last = q, pc = q, p = q;
+    for (;;) {
+        p++;
+        if (p >= L || p - pc > 5) break;
+        if (flags[g0 + p] & HS_FLAG_CANDIDATE) {
+            if (p - last > 5) {
+                flags[g0 + p] |= HS_FLAG_SUSPECT;
+                last = p;
             }
+            pc = p;
         }
-        if ((acc >> lane) & 1u) {
-            const int i = n + __popc(acc & ((1u << lane) - 1u));
-            suspect_pos[sb + i] = q;
-            suspect_auto[sb + i] = (f & HS_FLAG_AUTO) ? 1 : 0;
-            flags[g0 + q] = (uint8_t)(f | HS_FLAG_SUSPECT);
-        }
-        n += __popc(acc);
     }
-    if (lane == 0) n_suspects[c] = n;
+}
+
+// ordered compaction of the accepted columns: count per tile, scan, fill
+template <bool FILL>
+__global__ void __launch_bounds__(HS_TILE) suspect_compact_kernel(const int32_t* __restrict__ tile_contig,
+                                                                  const int64_t* __restrict__ tile_base,
+                                                                  const int64_t* __restrict__ col_base,
+                                                                  const int32_t* __restrict__ contig_len,
+                                                                  const int64_t* __restrict__ suspect_base,
+                                                                  const uint8_t* __restrict__ flags,
+                                                                  int64_t* __restrict__ tile_cnt_or_off,
+                                                                  int32_t* __restrict__ suspect_pos,
+                                                                  uint8_t* __restrict__ suspect_auto) {
+    __shared__ int s_warp[4];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t tile = blockIdx.x;
+    const int c = tile_contig[tile];
+    const int L = contig_len[c];
+    const int64_t g0 = col_base[c];
+    const int q = (int)(tile - tile_base[c]) * HS_TILE + tid;
+    const unsigned f = (q < L) ? flags[g0 + q] : 0u;
+    const bool acc = (f & HS_FLAG_SUSPECT) != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, acc);
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    if (!FILL) {
+        if (tid == 0) tile_cnt_or_off[tile] = s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
+    } else if (acc) {
+        int before = __popc(m & ((1u << lane) - 1u));
+        for (int w = 0; w < wid; w++) before += s_warp[w];
+        const int64_t i = suspect_base[c] + (tile_cnt_or_off[tile] - tile_cnt_or_off[tile_base[c]]) + before;
+        suspect_pos[i] = q;
+        suspect_auto[i] = (f & HS_FLAG_AUTO) ? 1 : 0;
+    }
+}
+
+__global__ void suspect_count_kernel(int n_contigs, const int64_t* __restrict__ tile_base,
+                                     const int64_t* __restrict__ tile_sus_off, int32_t* __restrict__ n_suspects) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_contigs) n_suspects[c] = (int32_t)(tile_sus_off[tile_base[c + 1]] - tile_sus_off[tile_base[c]]);
 }
 
 // ---- export in the reference's column-major layout ------------------------------------------------
@@ -360,10 +469,45 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
         a.depth = p->d_depth;
         a.depth_sum = p->d_depth_sum;
         a.error_flag = p->d_min_reads + nc;
+        a.lut = (const HsRankLut*)ctx->d_rank_lut;
+        if (!p->d_work) HS_CUDA(ctx, hs_alloc(ctx, &p->d_work, p->n_cols + 1));
+        a.work = p->d_work + 1;
+        a.n_work = reinterpret_cast<unsigned int*>(p->d_work);
+        HS_CUDA(ctx, cudaMemsetAsync(p->d_work, 0, sizeof(int32_t), ctx->stream));
         HS_KERNEL(ctx, "column_rank_kernel", column_rank_kernel<<<(unsigned)p->n_tiles, HS_TILE, kColumnSmem, ctx->stream>>>(a));
+        LiteralArgs la;
+        la.work = a.work;
+        la.n_work = a.n_work;
+        la.n_contigs = nc;
+        la.col_base = p->d_col_base;
+        la.tile_base = p->d_tile_base;
+        la.tile_off = p->d_tile_off;
+        la.tile_reads = p->d_tile_reads;
+        la.read_start = p->d_read_start;
+        la.read_end = p->d_read_end;
+        la.row_base = p->d_row_base;
+        la.codes = p->d_codes;
+        la.col = a;
+        HS_KERNEL(ctx, "column_rank_literal_kernel",
+                  column_rank_literal_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(la));
     }
-    HS_KERNEL(ctx, "suspect_scan_kernel", suspect_scan_kernel<<<nc, 32, 0, ctx->stream>>>(p->d_contig_len, p->d_col_base, p->d_suspect_base, p->d_flags,
-                                                    p->d_suspect_pos, p->d_suspect_auto, p->d_n_suspects));
+    if (p->n_tiles > 0) {
+        if (!p->d_tile_sus) HS_CUDA(ctx, hs_alloc(ctx, &p->d_tile_sus, p->n_tiles + 1));
+        HS_KERNEL(ctx, "suspect_mark_kernel", suspect_mark_kernel<<<(unsigned)p->n_tiles, HS_TILE, 0, ctx->stream>>>(
+            p->d_tile_contig, p->d_tile_base, p->d_col_base, p->d_contig_len, p->d_flags));
+        HS_KERNEL(ctx, "suspect_compact_kernel<0>", suspect_compact_kernel<false><<<(unsigned)p->n_tiles, HS_TILE, 0, ctx->stream>>>(
+            p->d_tile_contig, p->d_tile_base, p->d_col_base, p->d_contig_len, p->d_suspect_base, p->d_flags,
+            p->d_tile_sus, nullptr, nullptr));
+        int rc = hs_exclusive_scan_i64(ctx, p->d_tile_sus, p->d_tile_sus, p->n_tiles, p->d_tile_sus + p->n_tiles);
+        if (rc) return rc;
+        HS_KERNEL(ctx, "suspect_compact_kernel<1>", suspect_compact_kernel<true><<<(unsigned)p->n_tiles, HS_TILE, 0, ctx->stream>>>(
+            p->d_tile_contig, p->d_tile_base, p->d_col_base, p->d_contig_len, p->d_suspect_base, p->d_flags,
+            p->d_tile_sus, p->d_suspect_pos, p->d_suspect_auto));
+        HS_KERNEL(ctx, "suspect_count_kernel", suspect_count_kernel<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(
+            nc, p->d_tile_base, p->d_tile_sus, p->d_n_suspects));
+    } else {
+        HS_CUDA(ctx, cudaMemsetAsync(p->d_n_suspects, 0, sizeof(int32_t) * nc, ctx->stream));
+    }
     p->ranked = true;
     return HSGPU_OK;
 }

@@ -28,6 +28,7 @@ struct hsgpu_ctx {
     bool profiling = false;
     std::vector<HsProfEntry> prof;
     std::string prof_report;
+    void* d_rank_lut = nullptr;  // HsRankLut (rank.cuh), built once per context
 };
 
 void hs_prof_begin(hsgpu_ctx* ctx, const char* name);
@@ -179,6 +180,8 @@ struct hsgpu_pileup {
     std::vector<int64_t> h_suspect_base;
     int64_t* d_suspect_base = nullptr;
     int64_t* d_col_off = nullptr;  // exclusive scan of d_depth (lazy, for export)
+    int32_t* d_work = nullptr;     // [0] = count, then column ids for the literal ranking replay
+    int64_t* d_tile_sus = nullptr; // accepted suspects per tile, then its exclusive scan
     bool have_col_off = false;
 };
 

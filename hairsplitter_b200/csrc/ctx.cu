@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "rank.cuh"
 
 static thread_local std::string g_tls_error;
 
@@ -106,6 +107,21 @@ int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    {
+        static HsRankLut lut;  // identical for every context
+        static bool have = false;
+        if (!have) {
+            hs_build_rank_lut(lut);
+            have = true;
+        }
+        e = cudaMalloc(&ctx->d_rank_lut, sizeof(HsRankLut));
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->d_rank_lut, &lut, sizeof(HsRankLut), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaStreamDestroy(ctx->stream);
+            delete ctx;
+            return hs_cuda_fail(nullptr, e, "rank table upload", __FILE__, __LINE__);
+        }
+    }
     *out = ctx;
     return HSGPU_OK;
 }
@@ -115,6 +131,7 @@ void hsgpu_ctx_destroy(hsgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->d_rank_lut) cudaFree(ctx->d_rank_lut);
     delete ctx;
 }
 

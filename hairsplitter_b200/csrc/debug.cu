@@ -6,30 +6,40 @@
 
 extern "C" {
 
-// out = k0, k1, c0, c1, c2 of one column (codes in the reference's in-column order)
-void hsgpu_debug_rank_column(const uint8_t* codes, int n, int32_t* out) {
+struct HostAcc {
+    const uint8_t* order;
+    const uint32_t* cnt;
+    int key(int k) const { return order[k]; }
+    unsigned count(int key) const { return cnt[key]; }
+};
+
+// out = k0, k1, c0, c1, c2 of one column (codes in the reference's in-column order), out[5] = 1 when the
+// literal replay was needed, 0 when the bucket table decided. mode 0 = fast path with fallback (what the
+// kernel does), 1 = always literal.
+void hsgpu_debug_rank_column(const uint8_t* codes, int n, int32_t* out, int mode) {
+    static HsRankLut lut;
+    static bool have = false;
+    if (!have) {
+        hs_build_rank_lut(lut);
+        have = true;
+    }
     uint32_t cnt[256] = {0};
     uint8_t order[HS_RH_MAXKEYS];
     int m = 0;
     for (int i = 0; i < n; i++) {
         if (cnt[codes[i]]++ == 0) order[m++] = codes[i];
     }
-    HsRhTable t;
-    hs_rh_new(t);
-    for (int k = 0; k < m; k++) hs_rh_insert(t, order[k]);
-    hs_rh_insert(t, 0);
-    hs_rh_insert(t, 1);
-    hs_rh_insert(t, 2);
-    uint8_t it[HS_RH_MAXKEYS];
-    uint32_t kc[HS_RH_MAXKEYS];
-    const int k = hs_rh_iterate(t, it);
-    for (int i = 0; i < k; i++) kc[i] = (cnt[it[i]] << 8) | it[i];
-    hs_kc_std_sort(kc, k);
-    out[0] = kc[0] & 0xff;
-    out[1] = kc[1] & 0xff;
-    out[2] = kc[0] >> 8;
-    out[3] = kc[1] >> 8;
-    out[4] = kc[2] >> 8;
+    HostAcc acc{order, cnt};
+    int k0 = 0, k1 = 0;
+    unsigned c0 = 0, c1 = 0, c2 = 0;
+    int lit = mode == 1 ? 1 : hs_rank_fast(acc, m, &lut, k0, k1, c0, c1, c2);
+    if (lit) hs_rank_literal(acc, m, k0, k1, c0, c1, c2);
+    out[0] = k0;
+    out[1] = k1;
+    out[2] = (int32_t)c0;
+    out[3] = (int32_t)c1;
+    out[4] = (int32_t)c2;
+    out[5] = lit;
 }
 
 int hsgpu_debug_rh_order(const uint8_t* keys, int n, uint8_t* out) {

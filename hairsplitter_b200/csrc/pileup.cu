@@ -252,6 +252,8 @@ void hsgpu_pileup_destroy(hsgpu_pileup* p) {
     hs_free(ctx, p->d_depth_sum);
     hs_free(ctx, p->d_suspect_base);
     hs_free(ctx, p->d_col_off);
+    hs_free(ctx, p->d_tile_sus);
+    hs_free(ctx, p->d_work);
     delete p;
 }
 

@@ -260,3 +260,141 @@ HS_HD void hs_kc_std_sort(uint32_t* v, int n) {
         hs_kc_insertion_sort(v, 0, n);
     }
 }
+
+// ---- column ranking: fast tie resolution + literal replay fallback ---------------------------------
+// For n = m + 3 keys (m distinct codes, then the dummy keys 0,1,2; src/call_variants.cpp:477-494) the
+// final robin_hood table has 8 / 16 / 32 buckets for n <= 6 / 12 / 25 and has been rehashed 0 / 1 / 2
+// times (each rehash advances the hash multiplier, robin_hood.h:2446-2449). A flat robin-hood table
+// without wrap-around keeps its entries sorted by home bucket, so two keys with DIFFERENT home buckets
+// iterate in bucket order whatever the insertion history was. For n <= 16 libstdc++'s std::sort is a
+// plain (stable) insertion sort, so equal counts keep the iteration order. Hence: ties between keys with
+// pairwise distinct home buckets are decided by the precomputed bucket table below; everything else
+// (shared bucket, n > 16 where introsort is unstable) replays the reference's map + sort literally.
+struct HsRankLut {
+    uint8_t home[3][160];  // home bucket of key k in the table incarnation `level`
+    uint8_t single[128];   // m == 1: second_base (a dummy key) for code 33 + i
+    uint8_t empty[2];      // m == 0: ref_base, second_base
+};
+
+HS_HD int hs_rank_level(int n) { return n <= 6 ? 0 : (n <= 12 ? 1 : 2); }
+
+// literal replay: keys in first-seen order via acc.key(k), counts via acc.count(key)
+template <class Acc>
+HS_HD void hs_rank_literal(const Acc& acc, int m, int& k0, int& k1, unsigned& c0, unsigned& c1, unsigned& c2) {
+    HsRhTable t;
+    hs_rh_new(t);
+    for (int k = 0; k < m; k++) hs_rh_insert(t, (uint8_t)acc.key(k));
+    hs_rh_insert(t, 0);
+    hs_rh_insert(t, 1);
+    hs_rh_insert(t, 2);
+    uint8_t it[HS_RH_MAXKEYS];
+    uint32_t kc[HS_RH_MAXKEYS];
+    const int n = hs_rh_iterate(t, it);
+    for (int i = 0; i < n; i++) {
+        const int key = it[i];
+        const unsigned cnt = key >= 33 ? acc.count(key) : 0u;
+        kc[i] = (cnt << 8) | (unsigned)key;
+    }
+    hs_kc_std_sort(kc, n);
+    k0 = kc[0] & 0xff;
+    k1 = kc[1] & 0xff;
+    c0 = kc[0] >> 8;
+    c1 = kc[1] >> 8;
+    c2 = kc[2] >> 8;
+}
+
+// returns 0 when resolved on the fast path, 1 when the literal replay is needed (outputs then unset)
+template <class Acc>
+HS_HD int hs_rank_fast(const Acc& acc, int m, const HsRankLut* lut, int& k0, int& k1, unsigned& c0, unsigned& c1,
+                       unsigned& c2) {
+    if (m == 0) {
+        k0 = lut->empty[0];
+        k1 = lut->empty[1];
+        c0 = c1 = c2 = 0;
+        return 0;
+    }
+    if (m == 1) {
+        k0 = acc.key(0);
+        k1 = lut->single[k0 - 33];
+        c0 = acc.count(k0);
+        c1 = c2 = 0;
+        return 0;
+    }
+    c0 = c1 = c2 = 0;
+    k0 = k1 = 0;
+    for (int k = 0; k < m; k++) {
+        const int key = acc.key(k);
+        const unsigned cnt = acc.count(key);
+        if (cnt > c0) { c2 = c1; c1 = c0; k1 = k0; c0 = cnt; k0 = key; }
+        else if (cnt > c1) { c2 = c1; c1 = cnt; k1 = key; }
+        else if (cnt > c2) { c2 = cnt; }
+    }
+    if (c0 > c1 && c1 > c2) return 0;  // both ranks unique
+    const int n = m + 3;
+    if (n > 16) return 1;
+    const uint8_t* home = lut->home[hs_rank_level(n)];
+    // T0 = keys with count c0, T1 = keys with count c1 (< c0); order inside a set = home bucket order
+    unsigned mask0 = 0, mask1 = 0;
+    int n0 = 0, n1 = 0, a0 = 0, a1 = 0, b0 = 0, h_a0 = 256, h_a1 = 256, h_b0 = 256;
+    bool dup0 = false, dup1 = false;
+    for (int k = 0; k < m; k++) {
+        const int key = acc.key(k);
+        const unsigned cnt = acc.count(key);
+        const int h = home[key];
+        if (cnt == c0) {
+            n0++;
+            if (mask0 & (1u << h)) dup0 = true;
+            mask0 |= 1u << h;
+            if (h < h_a0) { h_a1 = h_a0; a1 = a0; h_a0 = h; a0 = key; }
+            else if (h < h_a1) { h_a1 = h; a1 = key; }
+        } else if (cnt == c1) {
+            n1++;
+            if (mask1 & (1u << h)) dup1 = true;
+            mask1 |= 1u << h;
+            if (h < h_b0) { h_b0 = h; b0 = key; }
+        }
+    }
+    if (n0 >= 2) {
+        if (dup0) return 1;
+        k0 = a0;
+        k1 = a1;
+    } else {
+        k0 = a0;
+        if (n1 >= 2) {
+            if (dup1) return 1;
+            k1 = b0;
+        }  // n1 == 1: k1 from the first pass is that key
+    }
+    return 0;
+}
+
+// host only: builds the tables by replaying the reference behaviour
+struct HsRankOneKey {
+    int code;
+    HS_HD int key(int) const { return code; }
+    HS_HD unsigned count(int) const { return 1; }
+};
+inline void hs_build_rank_lut(HsRankLut& lut) {
+    for (int level = 0; level < 3; level++) {
+        HsRhTable t;
+        hs_rh_new(t);
+        t.mask = (8u << level) - 1;
+        for (int l = 0; l < level; l++) t.mult += 0xc4ceb9fe1a85ec54ull;
+        for (int key = 0; key < 160; key++) {
+            uint32_t idx, info;
+            hs_rh_key_to_idx(t, (uint8_t)key, idx, info);
+            lut.home[level][key] = (uint8_t)idx;
+        }
+    }
+    for (int i = 0; i < 128; i++) {
+        int k0 = 0, k1 = 0;
+        unsigned c0, c1, c2;
+        HsRankOneKey acc{33 + i};
+        hs_rank_literal(acc, i < 125 ? 1 : 0, k0, k1, c0, c1, c2);
+        lut.single[i] = (uint8_t)k1;
+        if (i == 127) {
+            lut.empty[0] = (uint8_t)k0;
+            lut.empty[1] = (uint8_t)k1;
+        }
+    }
+}

@@ -85,6 +85,15 @@ void hso_read_pair_counts(int32_t n_reads, int32_t n_snps, const int64_t* snp_of
                           const uint8_t* code, const uint8_t* ref_base, const uint8_t* second_base,
                           int32_t* sim, int32_t* diff);
 
+/* edlibAlign (src/edlib/src/edlib.cpp:142-297) restated as a full dynamic program (hs_oracle_edlib.c).
+ * mode 0 NW / 1 SHW / 2 HW, task 0 DISTANCE / 1 LOC / 2 PATH, k < 0 = unbounded. Output arrays must hold
+ * n+1 locations and m+n alignment bytes. Returns 0, or 2 when the path lies in edlib's Hirschberg regime
+ * (alignment then not produced; everything else is still filled). */
+int32_t hso_edlib_align(const char* query, int32_t m, const char* target, int32_t n, int32_t k, int32_t mode,
+                        int32_t task, int32_t* edit_distance, int32_t* alphabet_length, int32_t* n_locations,
+                        int32_t* end_locations, int32_t* start_locations, int32_t* alignment_length,
+                        uint8_t* alignment);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,9 @@ class Oracle:
                                                                                                        C.c_void_p,
                                                                                                        C.c_void_p]
         L.hso_read_pair_counts.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 7
+        L.hso_edlib_align.restype = C.c_int32
+        L.hso_edlib_align.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [
+            C.c_void_p] * 7
 
     # -- pileup ---------------------------------------------------------------------------------
     def pileup(self, cb):
@@ -183,6 +186,72 @@ class Oracle:
                                       code.ctypes.data, ref_base.ctypes.data, second_base.ctypes.data,
                                       sim.ctypes.data, diff.ctypes.data)
         return sim, diff
+
+
+    def edlib_align(self, query: bytes, target: bytes, k=-1, mode=2, task=2):
+        m, n = len(query), len(target)
+        ed = np.zeros(1, np.int32)
+        al = np.zeros(1, np.int32)
+        nl = np.zeros(1, np.int32)
+        ends = np.zeros(n + 2, np.int32)
+        starts = np.zeros(n + 2, np.int32)
+        alen = np.zeros(1, np.int32)
+        aln = np.zeros(m + n + 2, np.uint8)
+        st = self.lib.hso_edlib_align(query, m, target, n, k, mode, task, ed.ctypes.data, al.ctypes.data,
+                                      nl.ctypes.data, ends.ctypes.data, starts.ctypes.data, alen.ctypes.data,
+                                      aln.ctypes.data)
+        nloc = int(nl[0])
+        has_start = task >= 1 and m > 0 and n > 0 and int(ed[0]) >= 0  # NULL in edlib's early-return cases (:162-180)
+        return dict(status=int(st), edit_distance=int(ed[0]), alphabet_length=int(al[0]),
+                    end_locations=ends[:nloc].copy(), start_locations=starts[:nloc].copy() if has_start else None,
+                    alignment=aln[:int(alen[0])].copy() if task == 2 else None)
+
+
+class EdlibAlignConfig(C.Structure):
+    _fields_ = [("k", C.c_int), ("mode", C.c_int), ("task", C.c_int), ("additionalEqualities", C.c_void_p),
+                ("additionalEqualitiesLength", C.c_int)]
+
+
+class EdlibAlignResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("editDistance", C.c_int), ("endLocations", C.POINTER(C.c_int)),
+                ("startLocations", C.POINTER(C.c_int)), ("numLocations", C.c_int),
+                ("alignment", C.POINTER(C.c_ubyte)), ("alignmentLength", C.c_int), ("alphabetLength", C.c_int)]
+
+
+class RefEdlib:
+    """The vendored edlib itself (reference src/edlib), compiled into oracle/_ref/libhsref_edlib.so."""
+
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(HERE, "_ref", "libhsref_edlib.so"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(HERE, "_ref", "libhsref_edlib.so"))
+            L.edlibAlign.restype = EdlibAlignResult
+            L.edlibAlign.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, EdlibAlignConfig]
+            L.edlibFreeAlignResult.argtypes = [EdlibAlignResult]
+            L.edlibFreeAlignResult.restype = None
+            cls._lib = L
+        return cls._lib
+
+    @classmethod
+    def align(cls, query: bytes, target: bytes, k=-1, mode=2, task=2):
+        L = cls.lib()
+        cfg = EdlibAlignConfig(k, mode, task, None, 0)
+        r = L.edlibAlign(query, len(query), target, len(target), cfg)
+        n = r.numLocations
+        out = dict(status=r.status, edit_distance=r.editDistance, alphabet_length=r.alphabetLength,
+                   end_locations=np.array([r.endLocations[i] for i in range(n)], np.int32) if r.endLocations else np.zeros(0, np.int32),
+                   start_locations=(np.array([r.startLocations[i] for i in range(n)], np.int32)
+                                    if r.startLocations else None),
+                   alignment=(np.ctypeslib.as_array(r.alignment, shape=(r.alignmentLength,)).copy()
+                              if r.alignment and r.alignmentLength else (np.zeros(0, np.uint8) if task == 2 else None)))
+        L.edlibFreeAlignResult(r)
+        return out
 
 
 def ref_available() -> bool:
