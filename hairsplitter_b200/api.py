@@ -56,7 +56,7 @@ DISTANCE_DTYPE = np.dtype(
 )
 EDLIB_RESULT_DTYPE = np.dtype(
     [("status", "<i4"), ("edit_distance", "<i4"), ("n_locations", "<i4"), ("alignment_length", "<i4"),
-     ("loc_off", "<i8"), ("aln_off", "<i8")]
+     ("alphabet_length", "<i4"), ("has_start_locations", "<i4"), ("loc_off", "<i8"), ("aln_off", "<i8")]
 )
 
 # every symbol include/hsgpu.h declares (tests check that the library exports all of them)

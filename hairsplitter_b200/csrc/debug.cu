@@ -9,8 +9,8 @@ extern "C" {
 struct HostAcc {
     const uint8_t* order;
     const uint32_t* cnt;
-    int key(int k) const { return order[k]; }
-    unsigned count(int key) const { return cnt[key]; }
+    HS_HD int key(int k) const { return order[k]; }
+    HS_HD unsigned count(int key) const { return cnt[key]; }
 };
 
 // out = k0, k1, c0, c1, c2 of one column (codes in the reference's in-column order), out[5] = 1 when the

@@ -1,7 +1,515 @@
-// placeholder until the Myers kernel lands (next commit): fails loudly, never falls back to a CPU
+// Batched realignment with edlib's semantics: edlibAlign (reference src/edlib/src/edlib.cpp:142-297,
+// header src/edlib/include/edlib.h:146-271) for a batch of (query, target) pairs.
+//
+// One warp per pair. The query is cut into 64-row blocks, one block per lane (Myers/Hyyro bit-vectors,
+// calculateBlock :411-446); the lanes run the columns of the DP matrix as a skewed wavefront -- at step
+// s lane b computes column s-b -- so that the horizontal delta leaving block b-1 reaches block b through
+// one warp shuffle together with the target symbol. edlib's Ukkonen band only prunes work, it does not
+// change results, so the kernel computes the full matrix and reproduces edlib's observable rules
+// (restated and pinned against the vendored edlib in oracle/hs_oracle_edlib.c):
+//   * HW/SHW: every target position whose bottom-row score equals the minimum, ascending; position -1
+//     (the empty prefix) competes only when the query length is not a multiple of 64, because edlib pads
+//     the query with W wildcard rows and reads column c-W of the padded bottom row (:665-702);
+//   * HW start locations: reverse SHW pass per end location, LAST minimal position (:226-259);
+//   * path: NW on target[start0..end0], traceback priority up (insert) > left (delete) > diagonal
+//     (obtainAlignmentTraceback :947-1146). The traceback only needs "vertical delta is +1" and
+//     "horizontal delta is +1" per cell, so the NW pass stores the two bit-vectors Pv and Ph per
+//     (block, column), 2 bits per cell, in a per-warp scratch slab laid out [block][column] so that the
+//     walk loads 32 consecutive columns of the block it is in with one coalesced request.
+//   Pairs whose path falls in edlib's Hirschberg regime ((20*blocks+8)*columns >= 1 MiB, :1193-1195) get
+//   status 2 and no alignment: Hirschberg picks the split row by its own tie rule, not implemented here.
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
-extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t, const char*, const int64_t*, const char*, const int64_t*,
-                                       int32_t, int32_t, int32_t, hsgpu_edlib_result*, int32_t*, int32_t*, int64_t,
-                                       uint8_t*, int64_t) {
-    HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_edlib_align_batch: not implemented in this build");
+
+#define ED_WARPS 4          // warps (pairs in flight) per CTA
+#define ED_MAXBLOCKS 32     // one 64-row block per lane -> queries up to 2048
+#define ED_SMEM_SYMS 8      // alphabets up to this size keep Peq in shared memory
+#define ED_TRACE_BYTES (52429ll * 16)  // per-warp traceback slab: blocks*columns < 2^20/20 entries of 16 B
+
+struct EdArgs {
+    int n_pairs;
+    const uint8_t* q;
+    const int64_t* q_off;
+    const uint8_t* t;
+    const int64_t* t_off;
+    int k, mode, task;
+    hsgpu_edlib_result* res;
+    unsigned int* bitmask;        // end-position bits per pair
+    const int64_t* bm_off;        // [n_pairs+1] word offsets
+    int32_t* ends;
+    int32_t* starts;
+    uint8_t* aln_tmp;             // per pair region of qlen + tlen bytes (ops in reverse order)
+    const int64_t* aln_tmp_off;
+    uint64_t* peq_big;            // per resident warp: 256 * 32 words, for alphabets > ED_SMEM_SYMS
+    uint8_t* trace;               // per resident warp: ED_TRACE_BYTES
+    unsigned int* counter;        // dynamic pair scheduler
+};
+
+struct WarpCtx {
+    uint64_t* peq;        // [sym][32]
+    const uint8_t* lut;   // byte -> symbol
+    int lane;
+};
+
+// symbol table of a pair: lut[byte] = rank of the byte among the bytes present (any consistent numbering
+// gives the same Peq behaviour; edlib numbers by first appearance, :1440-1459). Returns alphabet size.
+__device__ int build_alphabet(const uint8_t* q, int m, const uint8_t* t, int n, uint8_t* lut, int lane) {
+    unsigned int present[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = lane; i < m; i += 32) { const int c = q[i]; present[c >> 5] |= 1u << (c & 31); }
+    for (int i = lane; i < n; i += 32) { const int c = t[i]; present[c >> 5] |= 1u << (c & 31); }
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        unsigned int v = present[w];
+        for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+        present[w] = v;
+    }
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const unsigned int v = present[w];
+        lut[w * 32 + lane] = (uint8_t)(base + __popc(v & ((1u << lane) - 1u)));
+        base += __popc(v);
+    }
+    total = base;
+    __syncwarp();
+    return total;
+}
+
+// Peq[sym][block]: bit i of block b set iff query row 64*b+i carries sym (buildPeq :357-385; padding rows
+// stay 0 -- they never influence the real rows because carries only travel towards higher rows)
+__device__ void build_peq(const WarpCtx& w, const uint8_t* q, int m, int nb, int n_sym, bool reversed) {
+    for (int i = w.lane; i < n_sym * 32; i += 32) w.peq[i] = 0ull;
+    __syncwarp();
+    if (w.lane < nb) {
+        const int r0 = w.lane * 64;
+        const int r1 = min(m, r0 + 64);
+        for (int r = r0; r < r1; r++) {
+            const int c = reversed ? q[m - 1 - r] : q[r];
+            w.peq[w.lut[c] * 32 + w.lane] |= 1ull << (r - r0);
+        }
+    }
+    __syncwarp();
+}
+
+enum { PASS_SEMIGLOBAL = 0, PASS_NW_SCORE = 1, PASS_REV_SHW = 2, PASS_NW_STORE = 3 };
+
+struct PassOut {
+    int best;       // minimum bottom-row score (semi-global) / D[m][n] (NW)
+    int first_j;    // first column index j (0..n) reaching best
+    int last_j;     // last column index reaching best
+    int count;      // number of columns with score == best, j >= first_j
+};
+
+// One sweep over the columns. tget(c) = target symbol index source: forward t[c], or t[rev_end - c].
+// start_hin: +1 when the top row is penalised (NW, SHW), 0 for HW. consider_j0: position -1 competes.
+template <int KIND>
+__device__ PassOut dp_pass(const WarpCtx& w, int m, int nb, const uint8_t* t, int n, int rev_end, int start_hin,
+                           bool consider_j0, unsigned int* bitmask, ulonglong2* trace) {
+    const int lane = w.lane;
+    uint64_t Pv = ~0ull, Mv = 0ull;
+    const int lb = (m - 1) & 63;
+    int score = m;  // D[m][0]
+    PassOut o;
+    o.best = consider_j0 ? m : 0x3fffffff;
+    o.first_j = 0;
+    o.last_j = 0;
+    o.count = consider_j0 ? 1 : 0;
+    unsigned int bits = consider_j0 ? 1u : 0u;  // bit (j & 31) of the word being assembled
+    int packed = 0;
+    int tchunk = 0;
+    const int steps = n + nb - 1;
+    for (int s = 0; s < steps; s++) {
+        if ((s & 31) == 0) {
+            const int idx = s + lane;
+            tchunk = 0;
+            if (idx < n) tchunk = w.lut[rev_end >= 0 ? t[rev_end - idx] : t[idx]];
+        }
+        const int sym0 = __shfl_sync(0xffffffffu, tchunk, s & 31);
+        const int pk = __shfl_up_sync(0xffffffffu, packed, 1);
+        const int sym = lane == 0 ? sym0 : (pk >> 2);
+        const int hin = lane == 0 ? start_hin : ((pk & 3) - 1);
+        const int c = s - lane;
+        if (lane < nb && c >= 0 && c < n) {
+            uint64_t Eq = w.peq[sym * 32 + lane];
+            const uint64_t hneg = hin < 0 ? 1ull : 0ull, hpos = hin > 0 ? 1ull : 0ull;
+            const uint64_t Xv = Eq | Mv;
+            Eq |= hneg;
+            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            uint64_t Ph = Mv | ~(Xh | Pv);
+            uint64_t Mh = Pv & Xh;
+            const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+            packed = (sym << 2) | (hout + 1);
+            if (lane == nb - 1) {
+                score += (int)((Ph >> lb) & 1ull) - (int)((Mh >> lb) & 1ull);
+                const int j = c + 1;
+                if (KIND == PASS_SEMIGLOBAL) {
+                    if ((j & 31) == 0) bits = 0;
+                    if (score < o.best) { o.best = score; o.first_j = j; o.count = 0; }
+                    if (score == o.best) { o.count++; o.last_j = j; bits |= 1u << (j & 31); }
+                    if ((j & 31) == 31 || j == n) bitmask[j >> 5] = bits;
+                } else if (KIND == PASS_REV_SHW) {
+                    if (score < o.best) { o.best = score; o.first_j = j; }
+                    if (score == o.best) o.last_j = j;
+                } else {
+                    o.best = score;  // NW: value after the last column is D[m][n]
+                }
+            }
+            const uint64_t Phs = (Ph << 1) | hpos;
+            const uint64_t Mhs = (Mh << 1) | hneg;
+            Pv = Mhs | ~(Xv | Phs);
+            Mv = Phs & Xv;
+            if (KIND == PASS_NW_STORE) trace[(size_t)lane * n + c] = make_ulonglong2(Pv, Ph);
+        }
+    }
+    // results live in lane nb-1
+    o.best = __shfl_sync(0xffffffffu, o.best, nb - 1);
+    o.first_j = __shfl_sync(0xffffffffu, o.first_j, nb - 1);
+    o.last_j = __shfl_sync(0xffffffffu, o.last_j, nb - 1);
+    o.count = __shfl_sync(0xffffffffu, o.count, nb - 1);
+    return o;
+}
+
+// ---- phase A: distance + end positions ------------------------------------------------------------
+__global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_kernel(EdArgs a) {
+    __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32];
+    __shared__ uint8_t s_lut[ED_WARPS][256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gw = blockIdx.x * ED_WARPS + wid;
+    WarpCtx w;
+    w.lane = lane;
+    w.lut = s_lut[wid];
+    for (;;) {
+        int pair = 0;
+        if (lane == 0) pair = (int)atomicAdd(a.counter, 1u);
+        pair = __shfl_sync(0xffffffffu, pair, 0);
+        if (pair >= a.n_pairs) break;
+        const uint8_t* q = a.q + a.q_off[pair];
+        const uint8_t* t = a.t + a.t_off[pair];
+        const int m = (int)(a.q_off[pair + 1] - a.q_off[pair]);
+        const int n = (int)(a.t_off[pair + 1] - a.t_off[pair]);
+        unsigned int* bm = a.bitmask + a.bm_off[pair];
+        __syncwarp();
+        const int n_sym = build_alphabet(q, m, t, n, s_lut[wid], lane);
+        hsgpu_edlib_result r;
+        r.status = 0;
+        r.edit_distance = -1;
+        r.n_locations = 0;
+        r.alignment_length = 0;
+        r.alphabet_length = n_sym;
+        r.has_start_locations = 0;
+        r.loc_off = 0;
+        r.aln_off = 0;
+        if (m == 0 || n == 0) {  // :162-180
+            if (a.mode == 0) r.edit_distance = max(m, n);
+            else r.edit_distance = m;
+            r.n_locations = 1;
+            if (lane == 0) {
+                // bit j <-> position j-1: NW reports n-1, SHW/HW report -1
+                const int j = a.mode == 0 ? n : 0;
+                bm[j >> 5] = 1u << (j & 31);
+                a.res[pair] = r;
+            }
+            continue;
+        }
+        const int nb = (m + 63) >> 6;
+        w.peq = n_sym <= ED_SMEM_SYMS ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32;
+        build_peq(w, q, m, nb, n_sym, false);
+        const bool unbounded = a.k < 0;
+        if (a.mode == 0) {
+            int kk = unbounded ? 0x3fffffff : a.k;
+            if (!(kk < abs(n - m))) {  // :741-744
+                kk = min(kk, max(m, n));
+                const PassOut o = dp_pass<PASS_NW_SCORE>(w, m, nb, t, n, -1, 1, false, nullptr, nullptr);
+                if (o.best <= kk) {
+                    r.edit_distance = o.best;
+                    r.n_locations = 1;
+                    if (lane == 0) bm[n >> 5] = 1u << (n & 31);
+                }
+            }
+        } else {
+            const bool j0 = (m & 63) != 0;  // W > 0
+            const PassOut o = dp_pass<PASS_SEMIGLOBAL>(w, m, nb, t, n, -1, a.mode == 2 ? 0 : 1, j0, bm, nullptr);
+            int kk = unbounded ? 0x3fffffff : a.k;
+            if (a.mode == 2) kk = min(kk, m);  // :565-567
+            if (o.best <= kk) {
+                r.edit_distance = o.best;
+                r.n_locations = o.count;
+                // remember where the valid bits start: stale bits of worse minima lie before first_j
+                r.loc_off = o.first_j;
+            }
+        }
+        if (lane == 0) a.res[pair] = r;
+    }
+}
+
+// ---- phase B: locations, start locations, path -------------------------------------------------------
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
+    const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// warp-uniform traceback from (m, n) over the stored Pv/Ph bit-vectors; ops are written in reverse order
+__device__ int traceback(const ulonglong2* trace, const uint8_t* q, int m, const uint8_t* t, int n, uint8_t* out,
+                         int lane) {
+    int i = m, j = n, len = 0;
+    unsigned int pend = 0;  // op of output position len - (len & 31) + lane
+    int win_block = -1, win_j0 = -1;
+    uint64_t wPv = 0, wPh = 0;
+    while (i > 0 && j > 0) {
+        const int b = (i - 1) >> 6;
+        if (b != win_block || j > win_j0 || j <= win_j0 - 32) {
+            win_block = b;
+            win_j0 = j;
+            const int jj = j - lane;  // lane l holds column j0 - l
+            ulonglong2 v = make_ulonglong2(0ull, 0ull);
+            if (jj >= 1) v = trace[(size_t)b * n + (jj - 1)];
+            wPv = v.x;
+            wPh = v.y;
+        }
+        const int src = win_j0 - j;
+        const uint64_t pv = shfl64(wPv, src), ph = shfl64(wPh, src);
+        const int bit = (i - 1) & 63;
+        int op;
+        if ((pv >> bit) & 1ull) { op = 1; i--; }            // up: insertion (:1024-1056)
+        else if ((ph >> bit) & 1ull) { op = 2; j--; }       // left: deletion (:1057-1088)
+        else { op = (q[i - 1] == t[j - 1]) ? 0 : 3; i--; j--; }  // diagonal (:1089-1135)
+        if ((len & 31) == lane) pend = (unsigned)op;
+        len++;
+        if ((len & 31) == 0) out[len - 32 + lane] = (uint8_t)pend;
+    }
+    // boundary: the rest of the query is inserted / the rest of the target deleted
+    const int rest = i > 0 ? i : j;
+    const int rest_op = i > 0 ? 1 : 2;
+    for (int r = 0; r < rest; r++) {
+        if ((len & 31) == lane) pend = (unsigned)rest_op;
+        len++;
+        if ((len & 31) == 0) out[len - 32 + lane] = (uint8_t)pend;
+    }
+    if (lane < (len & 31)) out[(len & ~31) + lane] = (uint8_t)pend;
+    return len;
+}
+
+__global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_kernel(EdArgs a) {
+    __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32];
+    __shared__ uint8_t s_lut[ED_WARPS][256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gw = blockIdx.x * ED_WARPS + wid;
+    WarpCtx w;
+    w.lane = lane;
+    w.lut = s_lut[wid];
+    for (;;) {
+        int pair = 0;
+        if (lane == 0) pair = (int)atomicAdd(a.counter, 1u);
+        pair = __shfl_sync(0xffffffffu, pair, 0);
+        if (pair >= a.n_pairs) break;
+        hsgpu_edlib_result r = a.res[pair];
+        if (r.edit_distance < 0) continue;
+        const uint8_t* q = a.q + a.q_off[pair];
+        const uint8_t* t = a.t + a.t_off[pair];
+        const int m = (int)(a.q_off[pair + 1] - a.q_off[pair]);
+        const int n = (int)(a.t_off[pair + 1] - a.t_off[pair]);
+        const unsigned int* bm = a.bitmask + a.bm_off[pair];
+        int32_t* ends = a.ends + r.loc_off;
+        int32_t* starts = a.starts + r.loc_off;
+        const int first_j = r.aln_off < 0 ? 0 : (int)r.aln_off;  // phase A parked first_j here (moved by the host)
+        // end locations: set bits j >= first_j, position = j - 1
+        __syncwarp();
+        int found = 0;
+        for (int j0 = first_j & ~31; j0 <= n && found < r.n_locations; j0 += 32) {
+            unsigned int word = bm[j0 >> 5];
+            if (j0 < first_j) word &= ~((1u << (first_j - j0)) - 1u);
+            if (lane == 0) {
+                while (word && found < r.n_locations) {
+                    const int bpos = __ffs(word) - 1;
+                    word &= word - 1;
+                    ends[found++] = j0 + bpos - 1;
+                }
+            }
+            found = __shfl_sync(0xffffffffu, found, 0);
+        }
+        __syncwarp();
+        if (m == 0 || n == 0 || a.task == 0) continue;
+        r.has_start_locations = 1;
+        const int nb = (m + 63) >> 6;
+        const int n_sym = build_alphabet(q, m, t, n, s_lut[wid], lane);
+        w.peq = n_sym <= ED_SMEM_SYMS ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32;
+        if (a.mode == 2) {
+            build_peq(w, q, m, nb, n_sym, true);
+            const bool j0c = (m & 63) != 0;
+            for (int l = 0; l < r.n_locations; l++) {
+                const int e = ends[l];
+                int st = 0;
+                if (e >= 0) {
+                    const PassOut o = dp_pass<PASS_REV_SHW>(w, m, nb, t, e + 1, e, 1, j0c, nullptr, nullptr);
+                    st = e - (o.last_j - 1);  // :254-256 last position
+                }
+                if (lane == 0) starts[l] = st;
+            }
+        } else {
+            for (int l = lane; l < r.n_locations; l += 32) starts[l] = 0;
+        }
+        __syncwarp();
+        if (a.task == 2) {
+            const int s0 = starts[0], e0 = ends[0];
+            const int an = e0 - s0 + 1;
+            uint8_t* out = a.aln_tmp + a.aln_tmp_off[pair];
+            if (an <= 0) {  // obtainAlignment's empty-target case (:1173-1180)
+                for (int i = lane; i < m; i += 32) out[i] = 1;
+                r.alignment_length = m;
+            } else if ((2ll * 8 + 4) * nb * an + 8ll * an >= 1024 * 1024) {
+                r.status = 2;  // Hirschberg regime
+            } else {
+                build_peq(w, q, m, nb, n_sym, false);
+                ulonglong2* trace = reinterpret_cast<ulonglong2*>(a.trace + (size_t)gw * ED_TRACE_BYTES);
+                dp_pass<PASS_NW_STORE>(w, m, nb, t + s0, an, -1, 1, false, nullptr, trace);
+                __syncwarp();
+                r.alignment_length = traceback(trace, q, m, t + s0, an, out, lane);
+            }
+        }
+        if (lane == 0) a.res[pair] = r;
+    }
+}
+
+// final[aln_off + x] = tmp[len - 1 - x]
+__global__ void edlib_gather_kernel(int n_pairs, const hsgpu_edlib_result* __restrict__ res,
+                                    const uint8_t* __restrict__ tmp, const int64_t* __restrict__ tmp_off,
+                                    uint8_t* __restrict__ out) {
+    const int pair = blockIdx.x;
+    const int len = res[pair].alignment_length;
+    const uint8_t* src = tmp + tmp_off[pair];
+    uint8_t* dst = out + res[pair].aln_off;
+    for (int x = threadIdx.x; x < len; x += blockDim.x) dst[x] = src[len - 1 - x];
+}
+
+extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const char* queries, const int64_t* query_off,
+                                       const char* targets, const int64_t* target_off, int32_t k, int32_t mode,
+                                       int32_t task, hsgpu_edlib_result* results, int32_t* end_locations,
+                                       int32_t* start_locations, int64_t loc_capacity, uint8_t* alignment,
+                                       int64_t aln_capacity) {
+    if (!ctx || n_pairs < 0 || !query_off || !target_off || !results) return HSGPU_ERR_ARG;
+    if (mode < 0 || mode > 2 || task < 0 || task > 2) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_edlib_align_batch: bad mode/task");
+    if (n_pairs == 0) return HSGPU_OK;
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int64_t> bm_off((size_t)n_pairs + 1), tmp_off((size_t)n_pairs + 1);
+    int64_t bmw = 0, tmpb = 0;
+    for (int i = 0; i < n_pairs; i++) {
+        const int64_t m = query_off[i + 1] - query_off[i], n = target_off[i + 1] - target_off[i];
+        if (m < 0 || n < 0) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_edlib_align_batch: offsets must be non-decreasing");
+        if (m > 64 * ED_MAXBLOCKS)
+            HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_edlib_align_batch: queries longer than 2048 are not supported yet");
+        bm_off[i] = bmw;
+        tmp_off[i] = tmpb;
+        bmw += (n + 1 + 31) / 32 + 1;
+        tmpb += (m + n + 32 + 15) & ~15ll;
+    }
+    bm_off[n_pairs] = bmw;
+    tmp_off[n_pairs] = tmpb;
+    const int64_t qbytes = query_off[n_pairs], tbytes = target_off[n_pairs];
+    const int grid = ctx->sm_count * 4;
+    const int n_warps = grid * ED_WARPS;
+    uint8_t *d_q = nullptr, *d_t = nullptr, *d_aln_tmp = nullptr, *d_trace = nullptr, *d_aln = nullptr;
+    int64_t *d_qo = nullptr, *d_to = nullptr, *d_bmo = nullptr, *d_tmpo = nullptr, *d_scan = nullptr;
+    hsgpu_edlib_result* d_res = nullptr;
+    unsigned int *d_bm = nullptr, *d_counter = nullptr;
+    int32_t *d_ends = nullptr, *d_starts = nullptr;
+    uint64_t* d_peq = nullptr;
+    HS_CUDA(ctx, hs_alloc(ctx, &d_q, qbytes));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_t, tbytes));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_qo, n_pairs + 1));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_to, n_pairs + 1));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_bmo, n_pairs + 1));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_res, n_pairs));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_bm, bmw));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_counter, 2));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_peq, (int64_t)n_warps * 256 * 32));
+    HS_CUDA(ctx, hs_h2d(ctx, d_q, (const uint8_t*)queries, qbytes));
+    HS_CUDA(ctx, hs_h2d(ctx, d_t, (const uint8_t*)targets, tbytes));
+    HS_CUDA(ctx, hs_h2d(ctx, d_qo, query_off, n_pairs + 1));
+    HS_CUDA(ctx, hs_h2d(ctx, d_to, target_off, n_pairs + 1));
+    HS_CUDA(ctx, hs_h2d(ctx, d_bmo, bm_off.data(), n_pairs + 1));
+    HS_CUDA(ctx, cudaMemsetAsync(d_bm, 0, sizeof(unsigned int) * bmw, ctx->stream));
+    HS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned int), ctx->stream));
+    EdArgs a;
+    a.n_pairs = n_pairs;
+    a.q = d_q;
+    a.q_off = d_qo;
+    a.t = d_t;
+    a.t_off = d_to;
+    a.k = k;
+    a.mode = mode;
+    a.task = task;
+    a.res = d_res;
+    a.bitmask = d_bm;
+    a.bm_off = d_bmo;
+    a.ends = nullptr;
+    a.starts = nullptr;
+    a.aln_tmp = nullptr;
+    a.aln_tmp_off = nullptr;
+    a.peq_big = d_peq;
+    a.trace = nullptr;
+    a.counter = d_counter;
+    HS_KERNEL(ctx, "edlib_phase_a_kernel", edlib_phase_a_kernel<<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
+    // sizes -> offsets on the host (n_pairs structs; the location lists are usually 1-3 entries each)
+    HS_CUDA(ctx, hs_d2h(ctx, results, d_res, n_pairs));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t nloc = 0;
+    for (int i = 0; i < n_pairs; i++) {
+        results[i].aln_off = results[i].loc_off;  // first_j parked by phase A
+        results[i].loc_off = nloc;
+        nloc += results[i].n_locations;
+    }
+    int rc = HSGPU_OK;
+    if (nloc > loc_capacity || !end_locations || (task >= 1 && !start_locations)) {
+        hs_set_error(ctx, "hsgpu_edlib_align_batch: loc_capacity too small");
+        rc = HSGPU_ERR_CAPACITY;
+    }
+    if (rc == HSGPU_OK) {
+        HS_CUDA(ctx, hs_alloc(ctx, &d_ends, nloc));
+        HS_CUDA(ctx, hs_alloc(ctx, &d_starts, nloc));
+        HS_CUDA(ctx, hs_h2d(ctx, d_res, results, n_pairs));
+        if (task == 2) {
+            HS_CUDA(ctx, hs_alloc(ctx, &d_aln_tmp, tmpb));
+            HS_CUDA(ctx, hs_alloc(ctx, &d_tmpo, n_pairs + 1));
+            HS_CUDA(ctx, hs_alloc(ctx, &d_trace, (int64_t)n_warps * ED_TRACE_BYTES));
+            HS_CUDA(ctx, hs_h2d(ctx, d_tmpo, tmp_off.data(), n_pairs + 1));
+        }
+        a.ends = d_ends;
+        a.starts = d_starts;
+        a.aln_tmp = d_aln_tmp;
+        a.aln_tmp_off = d_tmpo;
+        a.trace = d_trace;
+        a.counter = d_counter + 1;
+        HS_KERNEL(ctx, "edlib_phase_b_kernel", edlib_phase_b_kernel<<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
+        HS_CUDA(ctx, hs_d2h(ctx, results, d_res, n_pairs));
+        HS_CUDA(ctx, hs_d2h(ctx, end_locations, d_ends, nloc));
+        if (task >= 1) HS_CUDA(ctx, hs_d2h(ctx, start_locations, d_starts, nloc));
+        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int64_t naln = 0;
+        for (int i = 0; i < n_pairs; i++) {
+            results[i].aln_off = naln;
+            naln += results[i].alignment_length;
+        }
+        if (task == 2) {
+            if (naln > aln_capacity || !alignment) {
+                hs_set_error(ctx, "hsgpu_edlib_align_batch: aln_capacity too small");
+                rc = HSGPU_ERR_CAPACITY;
+            } else if (naln > 0) {
+                HS_CUDA(ctx, hs_alloc(ctx, &d_aln, naln));
+                HS_CUDA(ctx, hs_h2d(ctx, d_res, results, n_pairs));
+                HS_KERNEL(ctx, "edlib_gather_kernel",
+                          edlib_gather_kernel<<<n_pairs, 128, 0, ctx->stream>>>(n_pairs, d_res, d_aln_tmp, d_tmpo, d_aln));
+                HS_CUDA(ctx, hs_d2h(ctx, alignment, d_aln, naln));
+                HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+        }
+    }
+    hs_free(ctx, d_q); hs_free(ctx, d_t); hs_free(ctx, d_qo); hs_free(ctx, d_to); hs_free(ctx, d_bmo);
+    hs_free(ctx, d_res); hs_free(ctx, d_bm); hs_free(ctx, d_counter); hs_free(ctx, d_peq); hs_free(ctx, d_ends);
+    hs_free(ctx, d_starts); hs_free(ctx, d_aln_tmp); hs_free(ctx, d_tmpo); hs_free(ctx, d_trace); hs_free(ctx, d_aln);
+    hs_free(ctx, d_scan);
+    return rc;
 }

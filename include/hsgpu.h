@@ -173,12 +173,15 @@ int hsgpu_read_pair_counts(hsgpu_ctx* ctx, int32_t n_reads, int32_t n_snps, cons
  * Batch of (query, target) pairs, results with edlib's exact field semantics. Modes/tasks use edlib's
  * numeric values: mode 0 NW, 1 SHW, 2 HW; task 0 DISTANCE, 1 LOC, 2 PATH. */
 typedef struct {
-    int32_t status;         /* EDLIB_STATUS_OK = 0 */
-    int32_t edit_distance;  /* -1 if larger than k */
+    int32_t status;               /* 0 = EDLIB_STATUS_OK; 2 = OK but the path lies in edlib's Hirschberg regime
+                                     ((20*ceil(q/64)+8)*columns >= 1 MiB, edlib.cpp:1193-1195) and was not produced */
+    int32_t edit_distance;        /* -1 if larger than k */
     int32_t n_locations;
     int32_t alignment_length;
-    int64_t loc_off;        /* offset into end_locations / start_locations */
-    int64_t aln_off;        /* offset into alignment */
+    int32_t alphabet_length;      /* EdlibAlignResult.alphabetLength */
+    int32_t has_start_locations;  /* 0 where edlib leaves startLocations NULL (DISTANCE task, empty sequence) */
+    int64_t loc_off;              /* offset into end_locations / start_locations */
+    int64_t aln_off;              /* offset into alignment */
 } hsgpu_edlib_result;
 
 int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const char* queries, const int64_t* query_off,

@@ -1,0 +1,126 @@
+"""GPU parity of hsgpu_edlib_align_batch against the edlib oracle (oracle/hs_oracle_edlib.c, pinned to the
+vendored edlib) and, where it travelled with the snapshot, against the vendored edlib itself."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ALPHA = b"ACGT"
+
+
+def _rnd(rng, n, alpha=ALPHA):
+    return bytes(rng.choice(list(alpha), n).tolist())
+
+
+def _mutate(rng, s, e):
+    out = bytearray()
+    for c in s:
+        u = rng.random()
+        if u < e / 3:
+            out.append(int(rng.choice(list(ALPHA))))
+        elif u < 2 * e / 3:
+            pass
+        elif u < e:
+            out.append(c)
+            out.append(int(rng.choice(list(ALPHA))))
+        else:
+            out.append(c)
+    return bytes(out)
+
+
+def _check_batch(gpu_ctx, oracle, queries, targets, k, mode, task, use_ref=True):
+    from oracle import pyoracle
+    res, ends, starts, aln = gpu_ctx.edlib_align_batch(queries, targets, k=k, mode=mode, task=task)
+    ref = pyoracle.RefEdlib if (use_ref and pyoracle.RefEdlib.available()) else None
+    for i, (q, t) in enumerate(zip(queries, targets)):
+        want = oracle.edlib_align(q, t, k, mode, task)
+        r = res[i]
+        ctx = (i, len(q), len(t), k, mode, task)
+        assert int(r["edit_distance"]) == want["edit_distance"], ctx
+        assert int(r["alphabet_length"]) == want["alphabet_length"], ctx
+        lo, nl = int(r["loc_off"]), int(r["n_locations"])
+        assert np.array_equal(ends[lo:lo + nl], want["end_locations"]), ctx
+        if want["start_locations"] is not None:
+            assert int(r["has_start_locations"]) == 1, ctx
+            assert np.array_equal(starts[lo:lo + nl], want["start_locations"]), ctx
+        else:
+            assert int(r["has_start_locations"]) == 0, ctx
+        if task == 2 and want["edit_distance"] >= 0 and len(q) and len(t):
+            assert int(r["status"]) == want["status"], ctx
+            if want["status"] == 0:
+                ao, al = int(r["aln_off"]), int(r["alignment_length"])
+                assert np.array_equal(aln[ao:ao + al], want["alignment"]), ctx
+        if ref is not None:
+            b = ref.align(q, t, k, mode, task)
+            assert int(r["edit_distance"]) == b["edit_distance"], ctx
+            assert np.array_equal(ends[lo:lo + nl], b["end_locations"]), ctx
+            if b["start_locations"] is not None:
+                assert np.array_equal(starts[lo:lo + nl], b["start_locations"]), ctx
+            if task == 2 and b["edit_distance"] >= 0 and int(r["status"]) == 0 and len(q) and len(t):
+                ao, al = int(r["aln_off"]), int(r["alignment_length"])
+                assert np.array_equal(aln[ao:ao + al], b["alignment"]), ctx
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("task", [0, 1, 2])
+def test_random_pairs_all_modes(gpu_ctx, oracle, mode, task):
+    rng = np.random.default_rng(100 + 10 * mode + task)
+    for k in (-1, 0, 5, 40, 1000):
+        qs, ts = [], []
+        for it in range(60):
+            qlen = int(rng.choice([0, 1, 5, 30, 63, 64, 65, 100, 127, 128, 129, 200, 300, 640]))
+            tlen = int(rng.choice([0, 1, 10, 64, 150, 400, 700]))
+            t = _rnd(rng, tlen)
+            if rng.random() < 0.7 and tlen > qlen > 0:
+                s = int(rng.integers(0, tlen - qlen + 1))
+                q = _mutate(rng, t[s:s + qlen], float(rng.choice([0, 0.05, 0.2])))
+            else:
+                q = _rnd(rng, qlen, ALPHA if rng.random() < 0.8 else b"ACGTNRY-*")
+            qs.append(q)
+            ts.append(t)
+        _check_batch(gpu_ctx, oracle, qs, ts, k, mode, task)
+
+
+def test_in_pipeline_shape_hw_path(gpu_ctx, oracle):
+    """the four call sites of the reference: <=300 bp query, HW, PATH, ~2.3 kb target
+    (src/create_new_contigs.cpp:557-630, src/tools.cpp:508-536)"""
+    rng = np.random.default_rng(7)
+    qs, ts = [], []
+    for it in range(40):
+        t = _rnd(rng, 2300)
+        s = int(rng.integers(0, 2000))
+        q = _mutate(rng, t[s:s + int(rng.choice([200, 300]))], float(rng.choice([0.0, 0.05, 0.15])))
+        if it % 10 == 0:
+            q = _rnd(rng, 300)  # unrelated query: distance close to the query length, many tied locations
+        qs.append(q)
+        ts.append(t)
+    _check_batch(gpu_ctx, oracle, qs, ts, -1, 2, 2)
+
+
+def test_benchmark_shape_read_chunk_on_window(gpu_ctx, oracle):
+    """1536-base read chunk on its contig window + 15 % slack, 10 % error"""
+    rng = np.random.default_rng(8)
+    qs, ts = [], []
+    for it in range(12):
+        t = _rnd(rng, 1766)
+        q = _mutate(rng, t[115:115 + 1536], 0.10)[:1536]
+        qs.append(q)
+        ts.append(t)
+    _check_batch(gpu_ctx, oracle, qs, ts, -1, 2, 2, use_ref=True)
+    _check_batch(gpu_ctx, oracle, qs, ts, -1, 0, 2, use_ref=True)
+
+
+def test_hirschberg_regime_is_flagged_not_faked(gpu_ctx, oracle):
+    rng = np.random.default_rng(9)
+    t = _rnd(rng, 2600)
+    q = _mutate(rng, t[:2040], 0.02)[:2048]
+    res, ends, starts, aln = gpu_ctx.edlib_align_batch([q], [t], k=-1, mode=0, task=2)
+    want = oracle.edlib_align(q, t, -1, 0, 2)
+    assert int(res[0]["edit_distance"]) == want["edit_distance"]
+    assert want["status"] == 2 and int(res[0]["status"]) == 2 and int(res[0]["alignment_length"]) == 0
+
+
+def test_query_longer_than_limit_fails_loudly(gpu_ctx):
+    from hairsplitter_b200 import api
+    with pytest.raises(api.HsgpuError):
+        gpu_ctx.edlib_align_batch([b"A" * 2049], [b"ACGT" * 10], k=-1, mode=0, task=0)
