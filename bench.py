@@ -140,6 +140,142 @@ def cpu_reference_rate(chunks, n_threads, repeat=1):
     return cols / WINDOW / dt, ("reference" if use_ref else "port"), dt
 
 
+def make_realign_pairs(rng, contig, n_pairs, qlen=1536, slack=0.15, err=0.10):
+    """read-chunk x contig-window pairs of the realignment benchmark shape: a `qlen`-base
+    chunk of an ONT-like read (10 % error, 1/3 each mismatch/insertion/deletion) against the contig window
+    it came from plus 15 % slack. Returns (list of query bytes, list of target bytes)."""
+    L = contig.shape[0]
+    tlen = int(round(qlen * (1 + slack)))
+    seg = qlen + 160
+    margin = (tlen - qlen) // 2
+    starts = rng.integers(0, L - seg - tlen, n_pairs)
+    src = contig[starts[:, None] + margin + np.arange(seg)[None, :]]
+    u = rng.random((n_pairs, seg))
+    mism = u < err / 3
+    dele = (u >= err / 3) & (u < 2 * err / 3)
+    ins = (u >= 2 * err / 3) & (u < err)
+    obs = np.where(mism, (src + rng.integers(1, 4, src.shape)) & 3, src).astype(np.uint8)
+    vals = np.stack([obs, rng.integers(0, 4, src.shape, dtype=np.uint8)], axis=2).reshape(n_pairs, 2 * seg)
+    valid = np.stack([~dele, ins], axis=2).reshape(n_pairs, 2 * seg)
+    keep = valid & (np.cumsum(valid, axis=1) <= qlen)
+    assert (keep.sum(axis=1) == qlen).all()
+    ascii_ = np.frombuffer(b"ACGT", dtype=np.uint8)
+    q = ascii_[vals[keep].reshape(n_pairs, qlen)]
+    t = ascii_[contig[starts[:, None] + np.arange(tlen)[None, :]]]
+    return [row.tobytes() for row in q], [row.tobytes() for row in t]
+
+
+def run_stages(ctx, stream, chunks, args, hbm_peak):
+    """realignment (edlib-compatible Myers kernel) and the partition x column contingency filter, each with
+    its own CPU baseline; both verified against the reference inside the run when oracle/_ref is present."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from hairsplitter_b200 import api
+    from oracle import pyoracle
+    out = {}
+    cores = host_cores()
+    rng = np.random.default_rng(12345)
+
+    # ---- realign: HW + PATH, 1536-base read chunks on 1766-base windows ----
+    n_pairs = max(64, int(20000 * min(1.0, args.scale * 4)))
+    qs, ts = make_realign_pairs(rng, chunks[0].contig, n_pairs)
+    cells = float(sum(len(q) * len(t) for q, t in zip(qs, ts)))
+    ctx.edlib_align_batch(qs[:256], ts[:256], k=-1, mode=2, task=2)  # warm-up (allocations, code load)
+    ctx.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    res, ends, starts, aln = ctx.edlib_align_batch(qs, ts, k=-1, mode=2, task=2)
+    e1.record(stream)
+    ctx.sync()
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    ms_e2e = e0.elapsed_time(e1)
+    ms_kernel = sum(v[1] for kname, v in prof.items() if kname.startswith("edlib_"))
+    n_cpu = min(n_pairs, 250 * cores)
+    t0 = time.perf_counter()
+    if pyoracle.RefEdlib.available():
+        kind = "reference"
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            cpu = list(ex.map(lambda i: pyoracle.RefEdlib.align(qs[i], ts[i], -1, 2, 2), range(n_cpu)))
+    else:
+        kind = "port"
+        O = pyoracle.Oracle()
+        n_cpu = min(n_cpu, 8 * cores)
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            cpu = list(ex.map(lambda i: O.edlib_align(qs[i], ts[i], -1, 2, 2), range(n_cpu)))
+    dt = time.perf_counter() - t0
+    for i in range(n_cpu):  # parity of the timed results
+        r = res[i]
+        assert int(r["edit_distance"]) == cpu[i]["edit_distance"]
+        lo, nl = int(r["loc_off"]), int(r["n_locations"])
+        assert np.array_equal(ends[lo:lo + nl], cpu[i]["end_locations"])
+        assert np.array_equal(starts[lo:lo + nl], cpu[i]["start_locations"])
+        ao, al = int(r["aln_off"]), int(r["alignment_length"])
+        assert np.array_equal(aln[ao:ao + al], cpu[i]["alignment"])
+    cpu_cells = float(sum(len(qs[i]) * len(ts[i]) for i in range(n_cpu)))
+    out["realign"] = {
+        "metric": "realign_gcups", "unit": "GCUPS (|query| x |target| cells per pair, full matrix, counted once)",
+        "shape": f"{n_pairs} pairs, query 1536 (read chunk, 10% error) x target 1766 (window + 15% slack), HW + PATH",
+        "kernel_gcups": cells / (ms_kernel * 1e-3) / 1e9, "e2e_gcups": cells / (ms_e2e * 1e-3) / 1e9,
+        "kernel_ms": ms_kernel, "e2e_ms": ms_e2e,
+        "kernels": {kname: {"launches": v[0], "ms": v[1]} for kname, v in prof.items()},
+        "cpu_baseline": {"value": cpu_cells / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
+                         "sample": f"first {n_cpu} pairs, edlibAlign HW+PATH, one pair per thread at a time",
+                         "verified_pairs": n_cpu},
+    }
+
+    # ---- contingency: loops 3+4 of keep_only_robust_variants on one 300 kb chunk ----
+    cb = chunks[0]
+    pk = api.PackedBatch([cb])
+    pu = api.Pileup(ctx, pk)
+    pu.build()
+    pu.column_rank()
+    pos, _ = pu.suspects(0)
+    parts = None
+    cpu_s = None
+    filt = None
+    if pyoracle.ref_available():
+        R = pyoracle.RefCV(cb)
+        rc = R.call_variants()
+        t0 = time.perf_counter()
+        parts, filt, merged = R.robust()   # the reference's keep_only_robust_variants (85 % of its run time)
+        cpu_s = time.perf_counter() - t0
+        assert np.array_equal(rc["suspects"]["pos"], pos)
+    else:
+        # no compiled reference on this box: partitions from the strain of origin of the reads
+        ends_ = pu.read_ends()
+        parts = []
+        for w0 in range(0, cb.length, 3000):
+            idx = np.nonzero((cb.start < w0 + 3000) & (ends_ > w0))[0].astype(np.int32)
+            st = np.where(cb.strain[idx] == 0, 1, -1).astype(np.int16)
+            parts.append(dict(read_idx=idx, state=st, more=np.full(idx.size, 3, np.int32), less=np.zeros(idx.size, np.int32)))
+    pu.robust_filter(0, parts, pos)  # warm-up
+    ctx.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    kept = pu.robust_filter(0, parts, pos)
+    e1.record(stream)
+    ctx.sync()
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    if filt is not None:
+        assert np.array_equal(kept, filt["pos"]), "snps_out differs from the reference"
+    cells0, _, _ = pu.stats()
+    kms = prof.get("robust_filter_kernel", (0, 0.0))[1]
+    out["contingency"] = {
+        "metric": "robust_filter (loops 3+4 of keep_only_robust_variants) on one chunk",
+        "shape": f"{cb.length} columns, {cb.n_reads} reads, {len(parts)} partitions, {pos.size} suspects -> {kept.size} kept",
+        "e2e_ms": e0.elapsed_time(e1), "kernel_ms": kms,
+        "kernel_gbs_algorithmic": (float(cells0[0]) + 3 * cb.length) / (kms * 1e-3) / 1e9 if kms else None,
+        "frac_of_hbm_peak": ((float(cells0[0]) + 3 * cb.length) / (kms * 1e-3) / 1e9 / hbm_peak) if kms else None,
+        "verified_against_reference": filt is not None,
+        "cpu_baseline": ({"value": cpu_s, "unit": "s for the whole keep_only_robust_variants (loops 1-4) on the same chunk",
+                          "cores": 1, "kind": "reference"} if cpu_s is not None else None),
+    }
+    pu.close()
+    return out
+
+
 def workload_description(info, chunks):
     return (f"BASELINE configs[1]: synthetic {info['genome'] / 1e6:g} Mb bacterial genome, {info['strains']} strains "
             f"1% apart, ONT-like reads {info['mean_len'] / 1000:g} kb mean, {int(info['error'] * 100)}% error, "
@@ -323,6 +459,11 @@ def main():
     barrier()
     e2e_ms = e0.elapsed_time(e1)
 
+    # ---- the other stages of the hot path (reported beside the headline, rank 0 / 1 GPU only) ----
+    stages = {}
+    if rank == 0 and world == 1:
+        stages = run_stages(ctx, stream, chunks, args, hbm_peak)
+
     # ---- max over ranks ----
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
     cols_t = torch.tensor([float(n_cols)], dtype=torch.float64, device="cuda")
@@ -355,6 +496,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "kernels": kernels,
+            "stages": stages,
         }
         if world == 1:
             cores = host_cores()
