@@ -49,12 +49,16 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
     }
 }
 
-// ---- K3: the CIGAR walk. One warp per read. ------------------------------------------------------
-// Ops are taken 32 at a time (one per lane); warp scans give every op its first contig column, read
-// offset and position in the expanded alignment; the expanded alignment is then processed 32
-// positions at a time, each lane locating its op by binary search in shared memory. The 3-mer
-// context of a cell is the two previously pushed symbols (M/=/X/I push the read base, D pushes '-',
-// S/H push nothing, :234-236,283-285,332-334), fetched from the lanes below via ballot + shuffle.
+// ---- K3: the CIGAR walk. One warp per read, one LANE per run of consecutive alignment positions. ----
+// The alignment of a read is the sequence of its M/=/X, I and D positions (S/H only move the read
+// cursor; :226-342). The warp takes the CIGAR in windows of up to 128 ops (four per lane), prefix-
+// scans them into (alignment position, contig column, read offset) and keeps the compacted M/I/D ops in
+// shared memory. The window's positions are then cut into 32 equal runs; every lane walks its run one
+// position per step with a branch-free state machine: the 16 next read bases and contig bases live in
+// two registers that all lanes refill together every 16 steps, the 3-mer context (the two symbols
+// pushed before, :234-238) is carried in registers, and each lane starts two positions early to warm
+// its context up. Codes go to a warp-private staging row in shared memory and leave for HBM as whole
+// aligned 16-byte vectors, so every row byte is written exactly once and fully coalesced.
 struct PileupArgs {
     int64_t n_reads;
     const int32_t* contig_len;
@@ -75,101 +79,216 @@ struct PileupArgs {
     unsigned long long* stats;
 };
 
-__global__ void __launch_bounds__(256) pileup_kernel(PileupArgs a) {
-    __shared__ int s_e[8][33];
-    __shared__ int s_q[8][32];
-    __shared__ int s_t[8][32];
-    __shared__ int s_ty[8][32];
+#define PW_WARPS 8
+#define PW_NOPS 128                  // CIGAR ops per window (4 per lane)
+#define PW_PMAX 46                   // positions per lane and window, at most (46 + 2 warm-up = 3 x 16 steps)
+#define PW_EMAX (32 * PW_PMAX)
+#define PW_BUF (PW_EMAX + 64)        // staging row: a carried partial vector + one window of columns
+enum { PK_M = 0, PK_I = 1, PK_D = 2, PK_SKIP = 3, PK_NONE = 4 };
+
+__device__ __forceinline__ uint32_t pw_word(const uint32_t* __restrict__ w, int i, int n) {
+    return (i >= 0 && i < n) ? __ldg(w + i) : 0u;
+}
+// sixteen 2-bit symbols starting at base i (i may be negative or run past the end: zeros)
+__device__ __forceinline__ uint32_t pw_window(const uint32_t* __restrict__ w, int nw, int i) {
+    const int wi = i >> 4;
+    return __funnelshift_r(pw_word(w, wi, nw), pw_word(w, wi + 1, nw), (i & 15) * 2);
+}
+// the 16 read symbols of alignment read offsets tp .. tp+15 (reverse strand: complement, read backwards)
+__device__ __forceinline__ uint32_t pw_read_window(const uint32_t* __restrict__ rb, int nw, int rlen, int tp, int strand) {
+    uint32_t x;
+    int nvalid;
+    if (strand) {
+        x = pw_window(rb, nw, tp);
+        nvalid = rlen - tp;
+    } else {
+        const int j = rlen - 1 - tp;  // first base wanted; the window is bases j-15 .. j, reversed
+        x = pw_window(rb, nw, j - 15);
+        x = __brev(x);
+        x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+        x = ~x;
+        nvalid = j + 1;
+    }
+    // a CIGAR longer than the read is malformed (the reference reads past the string); those symbols are 0
+    if (nvalid < 16) x = (nvalid <= 0) ? 0u : (x & ((1u << (2 * nvalid)) - 1u));
+    return x;
+}
+
+__global__ void __launch_bounds__(32 * PW_WARPS) pileup_kernel(PileupArgs a) {
+    __shared__ int4 s_ops[PW_WARPS][PW_NOPS + 1];  // {first position, first column, first read offset, len<<9|slot<<2|kind}
+    __shared__ __align__(16) uint8_t s_buf[PW_WARPS][PW_BUF];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * 8 + wid;
+    const int64_t r = (int64_t)blockIdx.x * PW_WARPS + wid;
     if (r >= a.n_reads) return;  // whole warps leave together; only __syncwarp is used below
+    int4* __restrict__ ops = s_ops[wid];
+    uint8_t* __restrict__ buf = s_buf[wid];
     const int c = a.read_contig[r];
     const int L = a.contig_len[c];
     const uint32_t* __restrict__ cb = a.contig_bases + a.contig_word_off[c];
+    const int ncw = (L + 15) >> 4;
     const uint32_t* __restrict__ rb = a.read_bases + a.read_word_off[r];
     const int rlen = a.read_len[r];
+    const int nrw = (rlen + 15) >> 4;
     const int strand = a.read_strand[r];
     const int start = a.read_start[r];
     const int end = a.read_end[r];
     const int64_t row_base = a.row_off[r] - (int64_t)(start & ~(HS_ALIGN - 1));
     if (lane == 0) a.row_base[r] = row_base;
     uint8_t* __restrict__ row = a.codes + row_base;
-    if (end > start) {  // zero the alignment pads so that tiles can be staged with whole 16-byte vectors
-        for (int q = (start & ~(HS_ALIGN - 1)) + lane; q < start; q += 32) row[q] = 0;
-        const int b = (end + HS_ALIGN - 1) & ~(HS_ALIGN - 1);
-        for (int q = end + lane; q < b; q += 32) row[q] = 0;
-    }
-    const int64_t k0 = a.cigar_off[r], k1 = a.cigar_off[r + 1];
-    int q = start, t = 0;
-    int carry1 = 2, carry2 = 1;  // context 'A','C','G': most recent = G, before it C (:212-214)
+    const int64_t k1 = a.cigar_off[r + 1];
+    int64_t kop = a.cigar_off[r];  // first op of the next window
+    int off0 = 0;                  // positions of op kop that earlier windows already consumed
+    int q0 = start, t0 = 0;        // contig column / read offset at the start of the window
+    int carry1 = 2, carry2 = 1;    // context 'A','C','G': most recent = G, before it C (:212-214)
+    int bufbase = start & ~(HS_ALIGN - 1);  // column of buf[0]
     unsigned int dist = 0, alen = 0;
-    for (int64_t kb = k0; kb < k1 && q < L; kb += 32) {
-        const int64_t k = kb + lane;
-        uint32_t op = (k < k1) ? __ldg(a.cigar + k) : (uint32_t)OP_P;
-        const int len = (int)(op >> 4), ty = (int)(op & 15);
-        const bool cq = op_consumes_q(ty), ct = op_consumes_t(ty);
-        const int qa = cq ? len : 0, ta = ct ? len : 0, ea = (cq || ct) ? len : 0;
-        const int qi = hs_warp_incl_scan(qa, lane), ti = hs_warp_incl_scan(ta, lane), ei = hs_warp_incl_scan(ea, lane);
-        s_q[wid][lane] = q + qi - qa;
-        s_t[wid][lane] = t + ti - ta;
-        s_e[wid][lane] = ei - ea;
-        s_ty[wid][lane] = ty;
-        const int E = __shfl_sync(0xffffffffu, ei, 31);
-        __syncwarp();
-        for (int e0 = 0; e0 < E; e0 += 32) {
-            const int e = e0 + lane;
-            int lo = 0, hi = 31;
+    if (lane < HS_ALIGN) buf[lane] = 0;  // the pad in front of the first cell
+    __syncwarp();
+    while (kop < k1 && q0 < L) {
+        // ---- the window's ops: classify, scan, compact into shared memory --------------------------
+        int len[4], kind[4];
+        int term = PW_NOPS;
 #pragma unroll
-            for (int it = 0; it < 5; it++) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (s_e[wid][mid] <= e) lo = mid; else hi = mid - 1;
-            }
-            const int off = e - s_e[wid][lo];
-            const int oty = s_ty[wid][lo];
-            const bool ocq = op_consumes_q(oty), oct = op_consumes_t(oty);
-            const int qp = s_q[wid][lo] + (ocq ? off : 0);
-            const int tp = s_t[wid][lo] + (oct ? off : 0);
-            const bool active = (e < E) && (qp < L);
-            const bool push = active && (ocq || oty == OP_I);
-            int sym = 0;
-            if (push) {
-                if (oty == OP_D) sym = 4;
-                else if (tp < rlen) {  // a CIGAR longer than the read is malformed; the reference reads past the string
-                    sym = strand ? hs_base2(rb, tp) : 3 - hs_base2(rb, (int64_t)rlen - 1 - tp);
-                }
-            }
-            const unsigned pm = __ballot_sync(0xffffffffu, push);
-            const unsigned below = pm & ((1u << lane) - 1u);
-            const int l1 = below ? 31 - __clz(below) : -1;
-            const unsigned below2 = (l1 >= 0) ? (below & ~(1u << l1)) : 0u;
-            const int l2 = below2 ? 31 - __clz(below2) : -1;
-            const int s1 = __shfl_sync(0xffffffffu, sym, l1 < 0 ? 0 : l1);
-            const int s2 = __shfl_sync(0xffffffffu, sym, l2 < 0 ? 0 : l2);
-            const int prev1 = (l1 < 0) ? carry1 : s1;
-            const int prev2 = (l1 < 0) ? carry2 : ((l2 < 0) ? carry1 : s2);
-            if (active) {
-                if (ocq) {
-                    row[qp] = (uint8_t)(HS_CODE0 + 5 * prev2 + prev1 + 25 * sym);  // :238,287
-                    alen++;
-                    if (oty == OP_D) dist++;
-                    else if (sym != hs_base2(cb, qp)) dist++;  // :254-256
-                } else if (oty == OP_I) {
-                    dist++;  // :337-338
-                    alen++;
-                }
-            }
-            if (pm) {  // warp-uniform
-                const int last = 31 - __clz(pm);
-                const unsigned rest = pm & ~(1u << last);
-                const int sl = __shfl_sync(0xffffffffu, sym, last);
-                const int sr = __shfl_sync(0xffffffffu, sym, rest ? 31 - __clz(rest) : 0);
-                carry2 = rest ? sr : carry1;
-                carry1 = sl;
-            }
+        for (int j = 0; j < 4; j++) {
+            const int slot = 4 * lane + j;
+            const int64_t k = kop + slot;
+            const uint32_t op = (k < k1) ? __ldg(a.cigar + k) : (uint32_t)OP_P;
+            const int ty = (int)(op & 15);
+            len[j] = (int)(op >> 4);
+            kind[j] = (ty == OP_M || ty == OP_EQ || ty == OP_X) ? PK_M
+                      : (ty == OP_I) ? PK_I : (ty == OP_D) ? PK_D : (ty == OP_S || ty == OP_H) ? PK_SKIP : PK_NONE;
+            if (slot == 0) len[j] -= off0;
+            // a clip moves the read cursor: it ends the window unless it leads it (walks assume contiguous offsets)
+            if (kind[j] == PK_SKIP && slot > 0 && slot < term) term = slot;
         }
-        q += __shfl_sync(0xffffffffu, qi, 31);
-        t += __shfl_sync(0xffffffffu, ti, 31);
+        term = __reduce_min_sync(0xffffffffu, term);
+        int es = 0, qs = 0, ts = 0, ns = 0;
+        int e_in[4], q_in[4], t_in[4], n_in[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (4 * lane + j >= term) { kind[j] = PK_NONE; len[j] = 0; }
+            const bool pos = kind[j] <= PK_D && len[j] > 0;
+            const int lc = pos ? min(len[j], PW_EMAX + 1) : len[j];  // the window ends inside anything longer
+            e_in[j] = es; q_in[j] = qs; t_in[j] = ts; n_in[j] = ns;
+            es += pos ? lc : 0;
+            qs += (kind[j] == PK_M || kind[j] == PK_D) ? lc : 0;
+            ts += (kind[j] == PK_M || kind[j] == PK_I || kind[j] == PK_SKIP) ? lc : 0;
+            ns += pos ? 1 : 0;
+            len[j] = lc;
+        }
+        const int ei = hs_warp_incl_scan(es, lane), qi = hs_warp_incl_scan(qs, lane);
+        const int ti = hs_warp_incl_scan(ts, lane), ni = hs_warp_incl_scan(ns, lane);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (kind[j] <= PK_D && len[j] > 0)
+                ops[ni - ns + n_in[j]] = make_int4(ei - es + e_in[j], q0 + qi - qs + q_in[j], t0 + ti - ts + t_in[j],
+                                                   (len[j] << 9) | ((4 * lane + j) << 2) | kind[j]);
+        }
+        const int Etot = __shfl_sync(0xffffffffu, ei, 31), Qtot = __shfl_sync(0xffffffffu, qi, 31);
+        const int Ttot = __shfl_sync(0xffffffffu, ti, 31), ncomp = __shfl_sync(0xffffffffu, ni, 31);
+        const int nwin = (int)min((int64_t)term, k1 - kop);
+        if (lane == 0) ops[ncomp] = make_int4(0x7fffffff, 0, 0, (0x3fffff << 9) | PK_M);  // sentinel
         __syncwarp();
+        if (Etot == 0) {  // nothing but clips / padding
+            kop += nwin; off0 = 0; q0 += Qtot; t0 += Ttot;
+            continue;
+        }
+        // ---- cut the window's positions into 32 runs ---------------------------------------------
+        int P, E;
+        if (Etot >= 32 * PW_PMAX) { P = PW_PMAX; E = 32 * PW_PMAX; }
+        else if (Etot >= 32 * 30) { P = 30; E = 32 * 30; }
+        else { P = max(2, (Etot + 31) >> 5); E = Etot; }
+        const int own = lane * P;                  // first position this lane emits
+        const int ehi = min(E, own + P);
+        int e = lane ? own - 2 : 0;                // two warm-up positions rebuild the 3-mer context
+        int k;
+        {
+            int lo = 0, hi = ncomp - 1;
+#pragma unroll
+            for (int it = 0; it < 7; it++) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (ops[mid].x <= e) lo = mid; else hi = mid - 1;
+            }
+            k = lo;
+        }
+        int4 ent = ops[k];
+        int kd = ent.w & 3;
+        int rem = (ent.w >> 9) - (e - ent.x);
+        int q = ent.y + (kd != PK_I ? e - ent.x : 0);
+        int tp = ent.z + (kd != PK_D ? e - ent.x : 0);
+        int p1 = carry1, ctx = HS_CODE0 + 5 * carry2 + carry1;  // ctx = '!' + 5*b(-2) + b(-1)
+        const int nsteps = P + 2;
+        const int cnt = max(0, ehi - own);  // positions this lane emits
+        int eo = e - own;           // -2 or 0: position relative to the first emitted one
+        uint8_t* __restrict__ out = buf - bufbase;
+        for (int s0 = 0; s0 < nsteps; s0 += 16) {
+            uint32_t rw = pw_read_window(rb, nrw, rlen, tp, strand);
+            uint32_t cw = pw_window(cb, ncw, q);
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                if (rem == 0) {  // next op; the list ends with a sentinel, so lanes past their run stay in bounds
+                    k++;
+                    const int m = ops[k].w;
+                    rem = m >> 9;
+                    kd = m & 3;
+                }
+                const int b = (int)(rw & 3u), cbase = (int)(cw & 3u);
+                const int sym = (kd == PK_D) ? 4 : b;
+                const bool em = ((unsigned)(eo + u) < (unsigned)cnt) && (q < L);
+                if (em) {
+                    if (kd != PK_I) out[q] = (uint8_t)(ctx + 25 * sym);  // :238,287
+                    alen++;
+                    if (kd != PK_M || b != cbase) dist++;  // :254-256, :305, :337-338
+                }
+                if (kd != PK_D) { rw >>= 2; tp++; }
+                if (kd != PK_I) { cw >>= 2; q++; }
+                if (eo + u < cnt) {  // the context freezes after the lane's last position (it may be the carry)
+                    ctx = HS_CODE0 + 5 * p1 + sym;
+                    p1 = sym;
+                }
+                rem--;
+            }
+            eo += 16;
+        }
+        const int p2 = (ctx - HS_CODE0 - p1) / 5;
+        const int last = (E - 1) / P;  // the lane that pushed the window's last symbol
+        carry1 = __shfl_sync(0xffffffffu, p1, last);
+        carry2 = __shfl_sync(0xffffffffu, p2, last);
+        // ---- where the next window starts ----------------------------------------------------------
+        if (E == Etot) {
+            kop += nwin; off0 = 0; q0 += Qtot; t0 += Ttot;
+        } else {
+            int lo = 0, hi = ncomp - 1;
+#pragma unroll
+            for (int it = 0; it < 7; it++) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (ops[mid].x <= E) lo = mid; else hi = mid - 1;
+            }
+            const int4 en = ops[lo];
+            const int d = E - en.x, slot = (en.w >> 2) & 127, kn = en.w & 3;
+            off0 = (slot == 0 ? off0 : 0) + d;
+            kop += slot;
+            q0 = en.y + (kn != PK_I ? d : 0);
+            t0 = en.z + (kn != PK_D ? d : 0);
+        }
+        // ---- flush the complete 16-byte vectors, keep the partial one --------------------------------
+        __syncwarp();
+        const int wr_end = min(q0, L);
+        const int nvec = ((wr_end & ~(HS_ALIGN - 1)) - bufbase) >> 4;
+        for (int v = lane; v < nvec; v += 32)
+            *reinterpret_cast<uint4*>(row + bufbase + 16 * v) = *reinterpret_cast<const uint4*>(buf + 16 * v);
+        uint8_t keep = 0;
+        if (lane < HS_ALIGN) keep = buf[16 * nvec + lane];
+        __syncwarp();
+        if (lane < HS_ALIGN) buf[lane] = keep;
+        bufbase += 16 * nvec;
+        __syncwarp();
+    }
+    if (end > start && (end & (HS_ALIGN - 1))) {  // the last, zero-padded vector
+        const int o = end - bufbase;              // 0 < o < 16: every complete vector has been flushed
+        if (lane >= o && lane < HS_ALIGN) buf[lane] = 0;
+        __syncwarp();
+        if (lane < 4) reinterpret_cast<uint32_t*>(row + bufbase)[lane] = reinterpret_cast<const uint32_t*>(buf)[lane];
     }
     long long d64 = hs_warp_sum64((long long)dist), a64 = hs_warp_sum64((long long)alen);
     if (lane == 0) {
@@ -346,6 +465,7 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t nr = p->n_reads;
     const unsigned rblocks = (unsigned)((nr + 7) / 8);
+    static_assert(PW_WARPS == 8, "span_kernel and pileup_kernel share the 8-reads-per-CTA grid");
     // rebuilt from scratch on every call (bench steps call this repeatedly on resident inputs)
     hs_free(ctx, p->d_codes);
     hs_free(ctx, p->d_tile_reads);
