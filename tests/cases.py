@@ -45,3 +45,38 @@ def ragged_cases():
     # a 1-column contig
     d = small_case(seed=55, length=130, depth=8, mean_len=60)
     return [a, b, c, d]
+
+
+def walk_edge_case(seed=71, length=5000):
+    """hand-made CIGARs for the windowed CIGAR walk of pileup_kernel: ops longer than one window, windows
+    ending inside I/D ops, > 128 ops, long and mid-alignment clips, N/P ops, a CIGAR longer than its read,
+    reads that run off the contig end or start at it, reads without any cell"""
+    rng = np.random.default_rng(seed)
+    letters = "MIDNSHP=X"
+    consumes_read = set("MIS=X")
+    spec = [
+        (10, 1, "3000S2500M", 0), (100, 0, "10H5S1500M1600D50M1700I100M7S", 0), (0, 1, "1M1I1M1D" * 300, 0),
+        (4000, 0, "100M50S100M", 0), (4900, 1, "300M", -200), (2000, 1, "20I5N30M4P2D10M", 0),
+        (1000, 0, "200=1X200=", 0), (300, 1, "50S20I", 0), (length, 1, "10M", 0), (length - 1, 0, "10M", 0),
+        (0, 1, "1472M", 0), (16, 0, "1473M", 0), (32, 1, "960M", 0), (33, 0, "959M", 0), (47, 1, "961M", 0),
+        (5, 1, "1M", 0), (6, 0, "2M", 0), (7, 1, "3M", 0), (64, 1, "1470M10I10M", 0), (65, 0, "1470M10D10M", 0),
+        (66, 1, "958M5I5M", 0), (67, 0, "958M5D5M", 0), (1, 1, "2I1D2I1D1M" * 150, 0), (3, 0, "31M1D" * 140, 0),
+        (2, 1, "1471M1I1D1M", 0), (15, 0, "2943M1I1M", 0), (200, 1, "4000S40M", 0),
+    ]
+    import re
+    starts, strands, cig, cig_off, bases, read_off = [], [], [], [0], [], [0]
+    for start, strand, s, extra in spec:
+        ops = [(int(n), letters.index(c)) for n, c in re.findall(r"(\d+)([MIDNSHP=X])", s)]
+        rl = max(1, sum(n for n, c in ops if letters[c] in consumes_read) + extra)
+        cig += [(n << 4) | c for n, c in ops]
+        cig_off.append(len(cig))
+        bases.append(rng.integers(0, 4, rl).astype(np.uint8))
+        read_off.append(read_off[-1] + rl)
+        starts.append(start)
+        strands.append(strand)
+    contig = rng.integers(0, 4, length).astype(np.uint8)
+    n = len(spec)
+    return synth.ContigBatch(contig=contig, read_bases=np.concatenate(bases), read_off=np.array(read_off, np.int64),
+                             cigar=np.array(cig, np.uint32), cigar_off=np.array(cig_off, np.int64),
+                             start=np.array(starts, np.int32), strand=np.array(strands, np.uint8),
+                             strain=np.zeros(n, np.int32), name="walk_edges")

@@ -45,10 +45,11 @@ def _check_contig(oracle, pu, ci, cb):
     return o, oc, md
 
 
-@pytest.mark.parametrize("case", ["small", "small_eqx", "medium", "hifi", "deep"])
+@pytest.mark.parametrize("case", ["small", "small_eqx", "medium", "hifi", "deep", "walk_edges"])
 def test_pileup_and_ranking_match_oracle(gpu_ctx, oracle, case):
     cb = {"small": cases.small_case, "small_eqx": lambda: cases.small_case(seed=12, eqx=True),
-          "medium": cases.medium_case, "hifi": cases.hifi_case, "deep": cases.deep_case}[case]()
+          "medium": cases.medium_case, "hifi": cases.hifi_case, "deep": cases.deep_case,
+          "walk_edges": cases.walk_edge_case}[case]()
     pk, pu = _build(gpu_ctx, [cb])
     o, oc, md = _check_contig(oracle, pu, 0, cb)
     off = 0
@@ -65,7 +66,7 @@ def test_pileup_and_ranking_match_oracle(gpu_ctx, oracle, case):
 
 
 def test_batch_of_ragged_contigs(gpu_ctx, oracle):
-    chunks = cases.ragged_cases() + [cases.small_case(seed=61)]
+    chunks = cases.ragged_cases() + [cases.small_case(seed=61), cases.walk_edge_case(seed=72, length=3100)]
     pk, pu = _build(gpu_ctx, chunks)
     for ci, cb in enumerate(chunks):
         _check_contig(oracle, pu, ci, cb)
