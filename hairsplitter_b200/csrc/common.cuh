@@ -155,6 +155,10 @@ struct hsgpu_pileup {
 
     // pileup proper
     int32_t* d_read_end = nullptr;    // positionOfReads[n].second
+    int32_t* d_read_tlead = nullptr;  // read offset of the first aligned base (leading clips)
+    uint8_t* d_read_flags = nullptr;  // HS_READ_IRREGULAR: clips between aligned parts
+    unsigned int* d_next_read = nullptr;  // work counter of pileup_kernel's persistent warps
+    int64_t n_irregular = 0;
     int64_t* d_row_alloc = nullptr;   // bytes reserved per read (multiple of 16), then its exclusive scan
     int64_t* d_row_base = nullptr;    // codes[row_base[r] + q] = cell of read r at column q (row_base % 16 == 0)
     uint8_t* d_codes = nullptr;

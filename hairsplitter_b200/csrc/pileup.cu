@@ -22,21 +22,52 @@ __device__ __forceinline__ bool op_consumes_t(int ty) {
 }
 
 // ---- K1: contig span of every read (sum of M/=/X/D lengths, clipped at the contig end, :217) ----
+// Also classifies the CIGAR: a read is REGULAR when its clips (S/H) only lead or trail the aligned part,
+// which is what SAM allows; its leading clip length is the read offset of the first aligned base
+// (S and H both advance the read cursor in the reference, :269-273). Anything else is IRREGULAR and
+// goes through pileup_generic_kernel.
+#define HS_READ_IRREGULAR 1
 __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32_t* __restrict__ cigar,
                                                    const int64_t* __restrict__ cigar_off,
                                                    const int32_t* __restrict__ read_start,
                                                    const int32_t* __restrict__ read_contig,
                                                    const int32_t* __restrict__ contig_len,
-                                                   int32_t* __restrict__ read_end, int64_t* __restrict__ row_alloc) {
+                                                   int32_t* __restrict__ read_end, int64_t* __restrict__ row_alloc,
+                                                   int32_t* __restrict__ read_tlead, uint8_t* __restrict__ read_flags,
+                                                   unsigned long long* __restrict__ n_irregular) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= n_reads) return;
+    const int64_t k0 = cigar_off[r], k1 = cigar_off[r + 1];
     long long sum = 0;
-    for (int64_t k = cigar_off[r] + lane; k < cigar_off[r + 1]; k += 32) {
-        uint32_t op = __ldg(cigar + k);
-        if (op_consumes_q((int)(op & 15))) sum += op >> 4;
+    long long first = k1, last = -1;  // first / last op that is an alignment position (M,=,X,I,D)
+    for (int64_t k = k0 + lane; k < k1; k += 32) {
+        const uint32_t op = __ldg(cigar + k);
+        const int ty = (int)(op & 15);
+        if (op_consumes_q(ty)) sum += op >> 4;
+        if ((op_consumes_q(ty) || ty == OP_I) && (op >> 4) > 0) {
+            if (k < first) first = k;
+            last = k;
+        }
     }
     sum = hs_warp_sum64(sum);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+    }
+    long long tlead = 0;
+    int irregular = 0;
+    for (int64_t k = k0 + lane; k < k1; k += 32) {
+        const uint32_t op = __ldg(cigar + k);
+        const int ty = (int)(op & 15);
+        if ((ty == OP_S || ty == OP_H) && (op >> 4) > 0) {
+            if (k < first) tlead += op >> 4;
+            else if (k < last) irregular = 1;
+        }
+    }
+    tlead = hs_warp_sum64(tlead);
+    irregular = __any_sync(0xffffffffu, irregular) || tlead > 0x3fffffff;
     if (lane == 0) {
         const int L = contig_len[read_contig[r]];
         const int start = read_start[r];
@@ -46,19 +77,12 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
         long long alloc = 0;
         if (end > start) alloc = ((end + HS_ALIGN - 1) & ~(long long)(HS_ALIGN - 1)) - (start & ~(HS_ALIGN - 1));
         row_alloc[r] = alloc;
+        read_tlead[r] = (int32_t)tlead;
+        read_flags[r] = irregular ? HS_READ_IRREGULAR : 0;
+        if (irregular) atomicAdd(n_irregular, 1ull);
     }
 }
 
-// ---- K3: the CIGAR walk. One warp per read, one LANE per run of consecutive alignment positions. ----
-// The alignment of a read is the sequence of its M/=/X, I and D positions (S/H only move the read
-// cursor; :226-342). The warp takes the CIGAR in windows of up to 128 ops (four per lane), prefix-
-// scans them into (alignment position, contig column, read offset) and keeps the compacted M/I/D ops in
-// shared memory. The window's positions are then cut into 32 equal runs; every lane walks its run one
-// position per step with a branch-free state machine: the 16 next read bases and contig bases live in
-// two registers that all lanes refill together every 16 steps, the 3-mer context (the two symbols
-// pushed before, :234-238) is carried in registers, and each lane starts two positions early to warm
-// its context up. Codes go to a warp-private staging row in shared memory and leave for HBM as whole
-// aligned 16-byte vectors, so every row byte is written exactly once and fully coalesced.
 struct PileupArgs {
     int64_t n_reads;
     const int32_t* contig_len;
@@ -73,17 +97,33 @@ struct PileupArgs {
     const int32_t* read_start;
     const uint8_t* read_strand;
     const int32_t* read_end;
+    const int32_t* read_tlead;
+    const uint8_t* read_flags;
     const int64_t* row_off;
     int64_t* row_base;
     uint8_t* codes;
     unsigned long long* stats;
+    unsigned int* next_read;  // work counter of the persistent warps
 };
 
+// ---- K3: the CIGAR walk. Persistent warps, one read at a time, one LANE per run of 30 positions. ----
+// The alignment of a read is the sequence of its M/=/X, I and D positions (:226-342). A warp takes the
+// CIGAR in windows of up to 192 ops (six per lane, kept in registers), prefix-scans their lengths and
+// turns the window's first 960 positions into two bit masks in shared memory (is-insertion,
+// is-deletion; warp-private, set with shared-memory atomics). Prefix popcounts of the masks give every
+// lane the contig column and the read offset at which its run of 30 positions starts, so no lane ever
+// searches for "its" op. Each lane then walks 2 warm-up positions (they rebuild the 3-mer context, the
+// two symbols pushed before, :234-238) and its 30 positions with a branch-free step of ~13
+// instructions: the 16 next read symbols and contig symbols sit in two registers that all lanes refill
+// together, the op kind of step u is bit u of the two masks. Codes go to a warp-private staging row in
+// shared memory and leave for HBM as whole aligned 16-byte vectors: every row byte is written exactly
+// once, fully coalesced.
 #define PW_WARPS 8
-#define PW_NOPS 128                  // CIGAR ops per window (4 per lane)
-#define PW_PMAX 46                   // positions per lane and window, at most (46 + 2 warm-up = 3 x 16 steps)
-#define PW_EMAX (32 * PW_PMAX)
-#define PW_BUF (PW_EMAX + 64)        // staging row: a carried partial vector + one window of columns
+#define PW_OPL 6                  // CIGAR ops per lane and window
+#define PW_NOPS (32 * PW_OPL)
+#define PW_P 30                   // positions per lane and window (+2 warm-up = 32 steps)
+#define PW_E (32 * PW_P)
+#define PW_BUF 1024               // staging row: a carried partial vector + one window of columns (<= 16 + 960 + 16)
 enum { PK_M = 0, PK_I = 1, PK_D = 2, PK_SKIP = 3, PK_NONE = 4 };
 
 __device__ __forceinline__ uint32_t pw_word(const uint32_t* __restrict__ w, int i, int n) {
@@ -114,181 +154,374 @@ __device__ __forceinline__ uint32_t pw_read_window(const uint32_t* __restrict__ 
     return x;
 }
 
+// set bits [a, b) of a warp-private bit array in shared memory
+__device__ __forceinline__ void pw_set_bits(unsigned int* __restrict__ bits, int a, int b) {
+    int w = a >> 5;
+    const int w1 = (b - 1) >> 5;
+    unsigned int m = 0xffffffffu << (a & 31);
+    const unsigned int mlast = 0xffffffffu >> (31 - ((b - 1) & 31));
+    while (w < w1) {
+        atomicOr(bits + w, m);
+        m = 0xffffffffu;
+        w++;
+    }
+    atomicOr(bits + w, m & mlast);
+}
+
+// One step of the FAST walk, as PTX so that it stays the 14 predicated instructions it is meant to be
+// (the compiler otherwise re-derives the column from the mask bits and branches around the store).
+//   pI/pD = this step is an insertion / a deletion (bit BIT of the masks)
+//   sym   = '-' for a deletion, else the next read symbol;  code = ctx + 25*sym, ctx = '!' + 5*b(-2) + b(-1)  (:238,287)
+//   a mismatch is counted for M and D positions ('-' never matches, :254-256,305); insertions are counted from the mask
+//   p1x   = 5*b(-1) + '!' of the next step
+#define PW_STEP_HEAD(BIT)                                   \
+    "and.b32 t, %6, " #BIT ";\n\t"                          \
+    "setp.ne.u32 pI, t, 0;\n\t"                             \
+    "and.b32 t, %7, " #BIT ";\n\t"                          \
+    "setp.ne.u32 pD, t, 0;\n\t"                             \
+    "and.b32 b, %0, 3;\n\t"                                 \
+    "selp.b32 sym, 4, b, pD;\n\t"
+#define PW_STEP_EMIT                                        \
+    "and.b32 c, %1, 3;\n\t"                                 \
+    "mad.lo.s32 code, sym, 25, %3;\n\t"                     \
+    "@!pI st.shared.u8 [%2], code;\n\t"                     \
+    "setp.ne.and.s32 pm, sym, c, !pI;\n\t"                  \
+    "@pm add.s32 %5, %5, 1;\n\t"
+#define PW_STEP_TAIL                                        \
+    "@!pD shr.u32 %0, %0, 2;\n\t"                           \
+    "@!pI shr.u32 %1, %1, 2;\n\t"                           \
+    "@!pI add.s32 %2, %2, 1;\n\t"                           \
+    "add.s32 %3, %4, sym;\n\t"                              \
+    "mad.lo.s32 %4, sym, 5, 33;\n\t"
+#define PW_STEP_REGS "{\n\t.reg .pred pI, pD, pm;\n\t.reg .b32 t, b, c, sym, code;\n\t"
+#define PW_STEP_OPS : "+r"(rw), "+r"(cw), "+r"(qa), "+r"(ctx), "+r"(p1x), "+r"(dist) : "r"(mI), "r"(mD)
+#define PW_WARM(BIT) asm volatile(PW_STEP_REGS PW_STEP_HEAD(BIT) PW_STEP_TAIL "}" PW_STEP_OPS)
+#define PW_STEP(BIT) asm volatile(PW_STEP_REGS PW_STEP_HEAD(BIT) PW_STEP_EMIT PW_STEP_TAIL "}" PW_STEP_OPS)
+
+// the 32 steps of one lane of a FAST window (a full window that cannot reach the contig end: every lane
+// emits exactly PW_P positions, nothing is predicated on counts or on the column)
+__device__ __forceinline__ void pw_walk_fast(const uint32_t mI, const uint32_t mD, const int lane, const int carry_ctx,
+                                             const int carry_p1x, const uint32_t* __restrict__ rb, const int nrw,
+                                             const int rlen, const int strand, int tp, const uint32_t* __restrict__ cb,
+                                             const int ncw, const int q, unsigned int qa, int& ctx_out, int& p1x_out,
+                                             unsigned int& dist) {
+    int ctx = 0, p1x = 0;  // rebuilt by the two warm-up steps
+    uint32_t rw = pw_read_window(rb, nrw, rlen, tp, strand);
+    uint32_t cw = pw_window(cb, ncw, q);
+    PW_WARM(0x1); PW_WARM(0x2);
+    if (lane == 0) {  // lane 0 warmed up on two virtual positions: its context is the carry
+        ctx = carry_ctx;
+        p1x = carry_p1x;
+    }
+    PW_STEP(0x4); PW_STEP(0x8); PW_STEP(0x10); PW_STEP(0x20); PW_STEP(0x40); PW_STEP(0x80);
+    PW_STEP(0x100); PW_STEP(0x200); PW_STEP(0x400); PW_STEP(0x800); PW_STEP(0x1000); PW_STEP(0x2000);
+    PW_STEP(0x4000); PW_STEP(0x8000);
+    const int lowI = __popc(mI & 0xffffu), lowD = __popc(mD & 0xffffu);
+    rw = pw_read_window(rb, nrw, rlen, tp + 16 - lowD, strand);
+    cw = pw_window(cb, ncw, q + 16 - lowI);
+    PW_STEP(0x10000); PW_STEP(0x20000); PW_STEP(0x40000); PW_STEP(0x80000); PW_STEP(0x100000); PW_STEP(0x200000);
+    PW_STEP(0x400000); PW_STEP(0x800000); PW_STEP(0x1000000); PW_STEP(0x2000000); PW_STEP(0x4000000);
+    PW_STEP(0x8000000); PW_STEP(0x10000000); PW_STEP(0x20000000); PW_STEP(0x40000000); PW_STEP(0x80000000);
+    ctx_out = ctx;
+    p1x_out = p1x;
+}
+
+// the general walk: partial windows and windows that reach the contig end
+__device__ __forceinline__ void pw_walk_slow(const uint32_t mI, const uint32_t mD, const int cnt, const int lane,
+                                             const int carry_ctx, const int carry_p1x, const uint32_t* __restrict__ rb,
+                                             const int nrw, const int rlen, const int strand, int tp,
+                                             const uint32_t* __restrict__ cb, const int ncw, int q, const int L,
+                                             uint8_t* __restrict__ out, int& ctx_out, int& p1x_out, unsigned int& dist,
+                                             unsigned int& alen) {
+    int ctx = 0, p1x = 0;
+#pragma unroll 1
+    for (int blk = 0; blk < 2; blk++) {
+        uint32_t rw = pw_read_window(rb, nrw, rlen, tp, strand);
+        uint32_t cw = pw_window(cb, ncw, q);
+#pragma unroll 4
+        for (int uu = 0; uu < 16; uu++) {
+            const int u = 16 * blk + uu;
+            if (u == 2 && lane == 0) {
+                ctx = carry_ctx;
+                p1x = carry_p1x;
+            }
+            const bool iI = (mI >> u) & 1u, iD = (mD >> u) & 1u;
+            const int b = (int)(rw & 3u), c = (int)(cw & 3u);
+            const int sym = iD ? 4 : b;
+            const bool mine = u - 2 < cnt;
+            if (u >= 2 && mine && q < L) {
+                if (!iI) out[q] = (uint8_t)(ctx + 25 * sym);
+                alen++;
+                if (iI || sym != c) dist++;  // :254-256, :305, :337-338
+            }
+            if (mine) {  // the context freezes after the lane's last position (it may be the carry)
+                ctx = p1x + sym;
+                p1x = 5 * sym + HS_CODE0;
+            }
+            if (!iD) { rw >>= 2; tp++; }
+            if (!iI) { cw >>= 2; q++; }
+        }
+    }
+    ctx_out = ctx;
+    p1x_out = p1x;
+}
+
 __global__ void __launch_bounds__(32 * PW_WARPS) pileup_kernel(PileupArgs a) {
-    __shared__ int4 s_ops[PW_WARPS][PW_NOPS + 1];  // {first position, first column, first read offset, len<<9|slot<<2|kind}
+    __shared__ unsigned int s_bits[PW_WARPS][2][32];
     __shared__ __align__(16) uint8_t s_buf[PW_WARPS][PW_BUF];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * PW_WARPS + wid;
-    if (r >= a.n_reads) return;  // whole warps leave together; only __syncwarp is used below
-    int4* __restrict__ ops = s_ops[wid];
+    unsigned int* __restrict__ sI = s_bits[wid][0];
+    unsigned int* __restrict__ sD = s_bits[wid][1];
     uint8_t* __restrict__ buf = s_buf[wid];
+    for (;;) {
+        unsigned int grab = 0;
+        if (lane == 0) grab = atomicAdd(a.next_read, 1u);
+        const int64_t r = __shfl_sync(0xffffffffu, grab, 0);
+        if (r >= a.n_reads) break;  // whole warps leave together; only __syncwarp is used
+        const int start = a.read_start[r];
+        const int64_t row_base = a.row_off[r] - (int64_t)(start & ~(HS_ALIGN - 1));
+        if (lane == 0) a.row_base[r] = row_base;
+        if (a.read_flags[r] & HS_READ_IRREGULAR) continue;  // pileup_generic_kernel writes this row
+        const int c = a.read_contig[r];
+        const int L = a.contig_len[c];
+        const uint32_t* __restrict__ cb = a.contig_bases + a.contig_word_off[c];
+        const int ncw = (L + 15) >> 4;
+        const uint32_t* __restrict__ rb = a.read_bases + a.read_word_off[r];
+        const int rlen = a.read_len[r];
+        const int nrw = (rlen + 15) >> 4;
+        const int strand = a.read_strand[r];
+        const int end = a.read_end[r];
+        uint8_t* __restrict__ row = a.codes + row_base;
+        const int64_t k1 = a.cigar_off[r + 1];
+        int64_t kop = a.cigar_off[r];  // first op of the next window
+        int off0 = 0;                  // positions of op kop that earlier windows already consumed
+        int q0 = start, t0 = a.read_tlead[r];  // contig column / read offset of the window's first position
+        int carry_ctx = HS_CODE0 + 5 * 1 + 2, carry_p1x = 5 * 2 + HS_CODE0;  // context 'A','C','G' (:212-214)
+        int bufbase = start & ~(HS_ALIGN - 1);               // column of buf[0]
+        unsigned int dist = 0, alen = 0;    // per lane
+        unsigned int udist = 0, ualen = 0;  // per warp (same value in every lane)
+        if (lane < HS_ALIGN) buf[lane] = 0;  // the pad in front of the first cell
+        __syncwarp();
+        while (kop < k1 && q0 < L) {
+            // ---- the window's ops: classify, scan the position counts -------------------------------
+            int klen[PW_OPL], kd[PW_OPL], e_in[PW_OPL];
+            int es = 0;
+#pragma unroll
+            for (int j = 0; j < PW_OPL; j++) {
+                const int slot = PW_OPL * lane + j;
+                const int64_t k = kop + slot;
+                const uint32_t op = (k < k1) ? __ldg(a.cigar + k) : (uint32_t)OP_P;
+                const int ty = (int)(op & 15);
+                int ln = (int)(op >> 4);
+                if (slot == 0) ln -= off0;
+                const int kind = (ty == OP_M || ty == OP_EQ || ty == OP_X) ? PK_M : (ty == OP_I) ? PK_I : (ty == OP_D) ? PK_D : PK_NONE;
+                kd[j] = kind;
+                klen[j] = (kind != PK_NONE) ? min(ln, 1024) : 0;  // the window ends inside anything longer than PW_E
+                e_in[j] = es;
+                es += klen[j];
+            }
+            const int ei = hs_warp_incl_scan(es, lane);
+            const int ebase = ei - es;
+            const int Etot = __shfl_sync(0xffffffffu, ei, 31);
+            const int nload = (int)min((int64_t)PW_NOPS, k1 - kop);
+            if (Etot == 0) {  // nothing but clips / padding
+                kop += nload;
+                off0 = 0;
+                continue;
+            }
+            const int Enew = min(Etot, PW_E);
+            const bool full = Enew == PW_E;
+            const int P = full ? PW_P : max(2, (Enew + 31) >> 5);
+            // ---- insertion / deletion masks over window positions (bit 0,1 = virtual warm-up of lane 0) ---
+            sI[lane] = 0;
+            sD[lane] = 0;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < PW_OPL; j++) {
+                if ((kd[j] == PK_I || kd[j] == PK_D) && klen[j] > 0) {
+                    const int pa = ebase + e_in[j], pb = min(pa + klen[j], Enew);
+                    if (pa < pb) pw_set_bits(kd[j] == PK_I ? sI : sD, pa + 2, pb + 2);
+                }
+            }
+            __syncwarp();
+            const unsigned int wI = sI[lane], wD = sD[lane];
+            const int pk = __popc(wI) | (__popc(wD) << 16);
+            const int pki = hs_warp_incl_scan(pk, lane);
+            const int tot = __shfl_sync(0xffffffffu, pki, 31);
+            const int totI = tot & 0xffff, totD = tot >> 16;
+            const int ws = lane * P;  // window position of the lane's first warm-up step
+            const int wi = ws >> 5, bit = ws & 31;
+            const unsigned int loI = __shfl_sync(0xffffffffu, wI, wi), hiI = __shfl_sync(0xffffffffu, wI, (wi + 1) & 31);
+            const unsigned int loD = __shfl_sync(0xffffffffu, wD, wi), hiD = __shfl_sync(0xffffffffu, wD, (wi + 1) & 31);
+            const int pre = __shfl_sync(0xffffffffu, pki - pk, wi);
+            const unsigned int below = (1u << bit) - 1u;
+            const int preI = (pre & 0xffff) + __popc(loI & below), preD = (pre >> 16) + __popc(loD & below);
+            const uint32_t mI = __funnelshift_r(loI, hiI, bit), mD = __funnelshift_r(loD, hiD, bit);
+            const int q = q0 - 2 + ws - preI;   // the two virtual positions count as plain matches
+            const int tp = t0 - 2 + ws - preD;
+            const int cnt = max(0, min(P, Enew - ws));
+            const int qend = q0 + Enew - totI;
+            int ctx, p1x;
+            if (full && qend <= L) {
+                const unsigned int qa = (unsigned int)__cvta_generic_to_shared(buf) + (unsigned int)(q - bufbase);
+                pw_walk_fast(mI, mD, lane, carry_ctx, carry_p1x, rb, nrw, rlen, strand, tp, cb, ncw, q, qa, ctx, p1x, dist);
+                ualen += Enew;
+                udist += totI;  // deletions count in the walk ('-' never equals the contig base)
+            } else {
+                pw_walk_slow(mI, mD, cnt, lane, carry_ctx, carry_p1x, rb, nrw, rlen, strand, tp, cb, ncw, q, L,
+                             buf - bufbase, ctx, p1x, dist, alen);
+            }
+            const int last = (Enew - 1) / P;  // the lane that pushed the window's last symbol
+            carry_ctx = __shfl_sync(0xffffffffu, ctx, last);
+            carry_p1x = __shfl_sync(0xffffffffu, p1x, last);
+            // ---- where the next window starts ------------------------------------------------------
+            if (Enew == Etot) {
+                kop += nload;
+                off0 = 0;
+            } else {
+                int myslot = -1, myd = 0;
+#pragma unroll
+                for (int j = 0; j < PW_OPL; j++) {
+                    const int pa = ebase + e_in[j];
+                    if (klen[j] > 0 && pa <= Enew && Enew < pa + klen[j]) { myslot = PW_OPL * lane + j; myd = Enew - pa; }
+                }
+                const unsigned int who = __ballot_sync(0xffffffffu, myslot >= 0);
+                const int src = __ffs(who) - 1;
+                const int slot = __shfl_sync(0xffffffffu, myslot, src);
+                const int d = __shfl_sync(0xffffffffu, myd, src);
+                off0 = (slot == 0 ? off0 : 0) + d;
+                kop += slot;
+            }
+            q0 = qend;
+            t0 += Enew - totD;
+            // ---- flush the complete 16-byte vectors, keep the partial one ----------------------------
+            __syncwarp();
+            const int wr_end = min(q0, L);
+            const int nvec = ((wr_end & ~(HS_ALIGN - 1)) - bufbase) >> 4;
+            for (int v = lane; v < nvec; v += 32)
+                *reinterpret_cast<uint4*>(row + bufbase + 16 * v) = *reinterpret_cast<const uint4*>(buf + 16 * v);
+            uint8_t keep = 0;
+            if (lane < HS_ALIGN) keep = buf[16 * nvec + lane];
+            __syncwarp();
+            if (lane < HS_ALIGN) buf[lane] = keep;
+            bufbase += 16 * nvec;
+            __syncwarp();
+        }
+        if (end > start && (end & (HS_ALIGN - 1))) {  // the last, zero-padded vector
+            const int o = end - bufbase;              // 0 < o < 16: every complete vector has been flushed
+            if (lane >= o && lane < HS_ALIGN) buf[lane] = 0;
+            __syncwarp();
+            if (lane < 4) reinterpret_cast<uint32_t*>(row + bufbase)[lane] = reinterpret_cast<const uint32_t*>(buf)[lane];
+        }
+        __syncwarp();
+        long long d64 = hs_warp_sum64((long long)dist) + udist, a64 = hs_warp_sum64((long long)alen) + ualen;
+        if (lane == 0) {
+            if (d64) atomicAdd(a.stats + 3 * c + 0, (unsigned long long)d64);
+            if (a64) atomicAdd(a.stats + 3 * c + 1, (unsigned long long)a64);
+            if (end > start) atomicAdd(a.stats + 3 * c + 2, (unsigned long long)(end - start));
+        }
+    }
+}
+
+// ---- K3b: generic walk for irregular CIGARs (clips between aligned parts). One warp per read; the ----
+// expanded alignment is processed 32 positions at a time, each lane locating its op by binary search in
+// shared memory, context via ballot + shuffle. Slow, exact for any op sequence.
+__global__ void __launch_bounds__(256) pileup_generic_kernel(PileupArgs a) {
+    __shared__ int s_e[8][33];
+    __shared__ int s_q[8][32];
+    __shared__ int s_t[8][32];
+    __shared__ int s_ty[8][32];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + wid;
+    if (r >= a.n_reads) return;  // whole warps leave together; only __syncwarp is used below
+    if (!(a.read_flags[r] & HS_READ_IRREGULAR)) return;
     const int c = a.read_contig[r];
     const int L = a.contig_len[c];
     const uint32_t* __restrict__ cb = a.contig_bases + a.contig_word_off[c];
-    const int ncw = (L + 15) >> 4;
     const uint32_t* __restrict__ rb = a.read_bases + a.read_word_off[r];
     const int rlen = a.read_len[r];
-    const int nrw = (rlen + 15) >> 4;
     const int strand = a.read_strand[r];
     const int start = a.read_start[r];
     const int end = a.read_end[r];
     const int64_t row_base = a.row_off[r] - (int64_t)(start & ~(HS_ALIGN - 1));
     if (lane == 0) a.row_base[r] = row_base;
     uint8_t* __restrict__ row = a.codes + row_base;
-    const int64_t k1 = a.cigar_off[r + 1];
-    int64_t kop = a.cigar_off[r];  // first op of the next window
-    int off0 = 0;                  // positions of op kop that earlier windows already consumed
-    int q0 = start, t0 = 0;        // contig column / read offset at the start of the window
-    int carry1 = 2, carry2 = 1;    // context 'A','C','G': most recent = G, before it C (:212-214)
-    int bufbase = start & ~(HS_ALIGN - 1);  // column of buf[0]
-    unsigned int dist = 0, alen = 0;
-    if (lane < HS_ALIGN) buf[lane] = 0;  // the pad in front of the first cell
-    __syncwarp();
-    while (kop < k1 && q0 < L) {
-        // ---- the window's ops: classify, scan, compact into shared memory --------------------------
-        int len[4], kind[4];
-        int term = PW_NOPS;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int slot = 4 * lane + j;
-            const int64_t k = kop + slot;
-            const uint32_t op = (k < k1) ? __ldg(a.cigar + k) : (uint32_t)OP_P;
-            const int ty = (int)(op & 15);
-            len[j] = (int)(op >> 4);
-            kind[j] = (ty == OP_M || ty == OP_EQ || ty == OP_X) ? PK_M
-                      : (ty == OP_I) ? PK_I : (ty == OP_D) ? PK_D : (ty == OP_S || ty == OP_H) ? PK_SKIP : PK_NONE;
-            if (slot == 0) len[j] -= off0;
-            // a clip moves the read cursor: it ends the window unless it leads it (walks assume contiguous offsets)
-            if (kind[j] == PK_SKIP && slot > 0 && slot < term) term = slot;
-        }
-        term = __reduce_min_sync(0xffffffffu, term);
-        int es = 0, qs = 0, ts = 0, ns = 0;
-        int e_in[4], q_in[4], t_in[4], n_in[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (4 * lane + j >= term) { kind[j] = PK_NONE; len[j] = 0; }
-            const bool pos = kind[j] <= PK_D && len[j] > 0;
-            const int lc = pos ? min(len[j], PW_EMAX + 1) : len[j];  // the window ends inside anything longer
-            e_in[j] = es; q_in[j] = qs; t_in[j] = ts; n_in[j] = ns;
-            es += pos ? lc : 0;
-            qs += (kind[j] == PK_M || kind[j] == PK_D) ? lc : 0;
-            ts += (kind[j] == PK_M || kind[j] == PK_I || kind[j] == PK_SKIP) ? lc : 0;
-            ns += pos ? 1 : 0;
-            len[j] = lc;
-        }
-        const int ei = hs_warp_incl_scan(es, lane), qi = hs_warp_incl_scan(qs, lane);
-        const int ti = hs_warp_incl_scan(ts, lane), ni = hs_warp_incl_scan(ns, lane);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (kind[j] <= PK_D && len[j] > 0)
-                ops[ni - ns + n_in[j]] = make_int4(ei - es + e_in[j], q0 + qi - qs + q_in[j], t0 + ti - ts + t_in[j],
-                                                   (len[j] << 9) | ((4 * lane + j) << 2) | kind[j]);
-        }
-        const int Etot = __shfl_sync(0xffffffffu, ei, 31), Qtot = __shfl_sync(0xffffffffu, qi, 31);
-        const int Ttot = __shfl_sync(0xffffffffu, ti, 31), ncomp = __shfl_sync(0xffffffffu, ni, 31);
-        const int nwin = (int)min((int64_t)term, k1 - kop);
-        if (lane == 0) ops[ncomp] = make_int4(0x7fffffff, 0, 0, (0x3fffff << 9) | PK_M);  // sentinel
-        __syncwarp();
-        if (Etot == 0) {  // nothing but clips / padding
-            kop += nwin; off0 = 0; q0 += Qtot; t0 += Ttot;
-            continue;
-        }
-        // ---- cut the window's positions into 32 runs ---------------------------------------------
-        int P, E;
-        if (Etot >= 32 * PW_PMAX) { P = PW_PMAX; E = 32 * PW_PMAX; }
-        else if (Etot >= 32 * 30) { P = 30; E = 32 * 30; }
-        else { P = max(2, (Etot + 31) >> 5); E = Etot; }
-        const int own = lane * P;                  // first position this lane emits
-        const int ehi = min(E, own + P);
-        int e = lane ? own - 2 : 0;                // two warm-up positions rebuild the 3-mer context
-        int k;
-        {
-            int lo = 0, hi = ncomp - 1;
-#pragma unroll
-            for (int it = 0; it < 7; it++) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (ops[mid].x <= e) lo = mid; else hi = mid - 1;
-            }
-            k = lo;
-        }
-        int4 ent = ops[k];
-        int kd = ent.w & 3;
-        int rem = (ent.w >> 9) - (e - ent.x);
-        int q = ent.y + (kd != PK_I ? e - ent.x : 0);
-        int tp = ent.z + (kd != PK_D ? e - ent.x : 0);
-        int p1 = carry1, ctx = HS_CODE0 + 5 * carry2 + carry1;  // ctx = '!' + 5*b(-2) + b(-1)
-        const int nsteps = P + 2;
-        const int cnt = max(0, ehi - own);  // positions this lane emits
-        int eo = e - own;           // -2 or 0: position relative to the first emitted one
-        uint8_t* __restrict__ out = buf - bufbase;
-        for (int s0 = 0; s0 < nsteps; s0 += 16) {
-            uint32_t rw = pw_read_window(rb, nrw, rlen, tp, strand);
-            uint32_t cw = pw_window(cb, ncw, q);
-#pragma unroll
-            for (int u = 0; u < 16; u++) {
-                if (rem == 0) {  // next op; the list ends with a sentinel, so lanes past their run stay in bounds
-                    k++;
-                    const int m = ops[k].w;
-                    rem = m >> 9;
-                    kd = m & 3;
-                }
-                const int b = (int)(rw & 3u), cbase = (int)(cw & 3u);
-                const int sym = (kd == PK_D) ? 4 : b;
-                const bool em = ((unsigned)(eo + u) < (unsigned)cnt) && (q < L);
-                if (em) {
-                    if (kd != PK_I) out[q] = (uint8_t)(ctx + 25 * sym);  // :238,287
-                    alen++;
-                    if (kd != PK_M || b != cbase) dist++;  // :254-256, :305, :337-338
-                }
-                if (kd != PK_D) { rw >>= 2; tp++; }
-                if (kd != PK_I) { cw >>= 2; q++; }
-                if (eo + u < cnt) {  // the context freezes after the lane's last position (it may be the carry)
-                    ctx = HS_CODE0 + 5 * p1 + sym;
-                    p1 = sym;
-                }
-                rem--;
-            }
-            eo += 16;
-        }
-        const int p2 = (ctx - HS_CODE0 - p1) / 5;
-        const int last = (E - 1) / P;  // the lane that pushed the window's last symbol
-        carry1 = __shfl_sync(0xffffffffu, p1, last);
-        carry2 = __shfl_sync(0xffffffffu, p2, last);
-        // ---- where the next window starts ----------------------------------------------------------
-        if (E == Etot) {
-            kop += nwin; off0 = 0; q0 += Qtot; t0 += Ttot;
-        } else {
-            int lo = 0, hi = ncomp - 1;
-#pragma unroll
-            for (int it = 0; it < 7; it++) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (ops[mid].x <= E) lo = mid; else hi = mid - 1;
-            }
-            const int4 en = ops[lo];
-            const int d = E - en.x, slot = (en.w >> 2) & 127, kn = en.w & 3;
-            off0 = (slot == 0 ? off0 : 0) + d;
-            kop += slot;
-            q0 = en.y + (kn != PK_I ? d : 0);
-            t0 = en.z + (kn != PK_D ? d : 0);
-        }
-        // ---- flush the complete 16-byte vectors, keep the partial one --------------------------------
-        __syncwarp();
-        const int wr_end = min(q0, L);
-        const int nvec = ((wr_end & ~(HS_ALIGN - 1)) - bufbase) >> 4;
-        for (int v = lane; v < nvec; v += 32)
-            *reinterpret_cast<uint4*>(row + bufbase + 16 * v) = *reinterpret_cast<const uint4*>(buf + 16 * v);
-        uint8_t keep = 0;
-        if (lane < HS_ALIGN) keep = buf[16 * nvec + lane];
-        __syncwarp();
-        if (lane < HS_ALIGN) buf[lane] = keep;
-        bufbase += 16 * nvec;
-        __syncwarp();
+    if (end > start) {  // zero the alignment pads so that tiles can be staged with whole 16-byte vectors
+        for (int q = (start & ~(HS_ALIGN - 1)) + lane; q < start; q += 32) row[q] = 0;
+        const int b = (end + HS_ALIGN - 1) & ~(HS_ALIGN - 1);
+        for (int q = end + lane; q < b; q += 32) row[q] = 0;
     }
-    if (end > start && (end & (HS_ALIGN - 1))) {  // the last, zero-padded vector
-        const int o = end - bufbase;              // 0 < o < 16: every complete vector has been flushed
-        if (lane >= o && lane < HS_ALIGN) buf[lane] = 0;
+    const int64_t k0 = a.cigar_off[r], k1 = a.cigar_off[r + 1];
+    int q = start, t = 0;
+    int carry1 = 2, carry2 = 1;  // context 'A','C','G': most recent = G, before it C (:212-214)
+    unsigned int dist = 0, alen = 0;
+    for (int64_t kb = k0; kb < k1 && q < L; kb += 32) {
+        const int64_t k = kb + lane;
+        uint32_t op = (k < k1) ? __ldg(a.cigar + k) : (uint32_t)OP_P;
+        const int len = (int)(op >> 4), ty = (int)(op & 15);
+        const bool cq = op_consumes_q(ty), ct = op_consumes_t(ty);
+        const int qa = cq ? len : 0, ta = ct ? len : 0, ea = (cq || ct) ? len : 0;
+        const int qi = hs_warp_incl_scan(qa, lane), ti = hs_warp_incl_scan(ta, lane), ei = hs_warp_incl_scan(ea, lane);
+        s_q[wid][lane] = q + qi - qa;
+        s_t[wid][lane] = t + ti - ta;
+        s_e[wid][lane] = ei - ea;
+        s_ty[wid][lane] = ty;
+        const int E = __shfl_sync(0xffffffffu, ei, 31);
         __syncwarp();
-        if (lane < 4) reinterpret_cast<uint32_t*>(row + bufbase)[lane] = reinterpret_cast<const uint32_t*>(buf)[lane];
+        for (int e0 = 0; e0 < E; e0 += 32) {
+            const int e = e0 + lane;
+            int lo = 0, hi = 31;
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_e[wid][mid] <= e) lo = mid; else hi = mid - 1;
+            }
+            const int off = e - s_e[wid][lo];
+            const int oty = s_ty[wid][lo];
+            const bool ocq = op_consumes_q(oty), oct = op_consumes_t(oty);
+            const int qp = s_q[wid][lo] + (ocq ? off : 0);
+            const int tp = s_t[wid][lo] + (oct ? off : 0);
+            const bool active = (e < E) && (qp < L);
+            const bool push = active && (ocq || oty == OP_I);
+            int sym = 0;
+            if (push) {
+                if (oty == OP_D) sym = 4;
+                else if (tp < rlen) {  // a CIGAR longer than the read is malformed; the reference reads past the string
+                    sym = strand ? hs_base2(rb, tp) : 3 - hs_base2(rb, (int64_t)rlen - 1 - tp);
+                }
+            }
+            const unsigned pm = __ballot_sync(0xffffffffu, push);
+            const unsigned below = pm & ((1u << lane) - 1u);
+            const int l1 = below ? 31 - __clz(below) : -1;
+            const unsigned below2 = (l1 >= 0) ? (below & ~(1u << l1)) : 0u;
+            const int l2 = below2 ? 31 - __clz(below2) : -1;
+            const int s1 = __shfl_sync(0xffffffffu, sym, l1 < 0 ? 0 : l1);
+            const int s2 = __shfl_sync(0xffffffffu, sym, l2 < 0 ? 0 : l2);
+            const int prev1 = (l1 < 0) ? carry1 : s1;
+            const int prev2 = (l1 < 0) ? carry2 : ((l2 < 0) ? carry1 : s2);
+            if (active) {
+                if (ocq) {
+                    row[qp] = (uint8_t)(HS_CODE0 + 5 * prev2 + prev1 + 25 * sym);  // :238,287
+                    alen++;
+                    if (oty == OP_D) dist++;
+                    else if (sym != hs_base2(cb, qp)) dist++;  // :254-256
+                } else if (oty == OP_I) {
+                    dist++;  // :337-338
+                    alen++;
+                }
+            }
+            if (pm) {  // warp-uniform
+                const int last = 31 - __clz(pm);
+                const unsigned rest = pm & ~(1u << last);
+                const int sl = __shfl_sync(0xffffffffu, sym, last);
+                const int sr = __shfl_sync(0xffffffffu, sym, rest ? 31 - __clz(rest) : 0);
+                carry2 = rest ? sr : carry1;
+                carry1 = sl;
+            }
+        }
+        q += __shfl_sync(0xffffffffu, qi, 31);
+        t += __shfl_sync(0xffffffffu, ti, 31);
+        __syncwarp();
     }
     long long d64 = hs_warp_sum64((long long)dist), a64 = hs_warp_sum64((long long)alen);
     if (lane == 0) {
@@ -297,6 +530,7 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pileup_kernel(PileupArgs a) {
         if (end > start) atomicAdd(a.stats + 3 * c + 2, (unsigned long long)(end - start));
     }
 }
+
 
 // ---- tile index: for every 128-column tile, the reads overlapping it in ascending order ----------
 // One warp per tile scans the reads of the tile's contig (a few thousand) with an ordered
@@ -353,6 +587,9 @@ void hsgpu_pileup_destroy(hsgpu_pileup* p) {
     hs_free(ctx, p->d_read_start);
     hs_free(ctx, p->d_read_strand);
     hs_free(ctx, p->d_read_end);
+    hs_free(ctx, p->d_read_tlead);
+    hs_free(ctx, p->d_read_flags);
+    hs_free(ctx, p->d_next_read);
     hs_free(ctx, p->d_row_alloc);
     hs_free(ctx, p->d_row_base);
     hs_free(ctx, p->d_codes);
@@ -434,7 +671,7 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
     A(d_contig_read_off, nc + 1); A(d_col_base, nc + 1); A(d_tile_base, nc + 1); A(d_tile_contig, tiles);
     A(d_read_contig, nr); A(d_read_bases, read_words); A(d_read_word_off, nr + 1); A(d_read_len, nr);
     A(d_cigar, p->n_cigar); A(d_cigar_off, nr + 1); A(d_read_start, nr); A(d_read_strand, nr);
-    A(d_read_end, nr); A(d_row_alloc, nr + 1); A(d_row_base, nr); A(d_stats, 3 * nc);
+    A(d_read_end, nr); A(d_read_tlead, nr); A(d_read_flags, nr); A(d_next_read, 1); A(d_row_alloc, nr + 1); A(d_row_base, nr); A(d_stats, 3 * nc);
     A(d_tile_off, tiles + 1); A(d_suspect_base, nc + 1);
 #undef A
     HS_CUDA(ctx, hs_h2d(ctx, p->d_contig_len, in->contig_len, nc));
@@ -471,11 +708,14 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     hs_free(ctx, p->d_tile_reads);
     p->built = p->ranked = p->have_col_off = false;
     HS_CUDA(ctx, cudaMemsetAsync(p->d_stats, 0, sizeof(unsigned long long) * 3 * p->n_contigs, ctx->stream));
-    int64_t* d_totals = nullptr;
-    HS_CUDA(ctx, hs_alloc(ctx, &d_totals, 2));
+    int64_t* d_totals = nullptr;  // codes bytes, tile index entries, irregular reads
+    HS_CUDA(ctx, hs_alloc(ctx, &d_totals, 3));
+    HS_CUDA(ctx, cudaMemsetAsync(d_totals, 0, 3 * sizeof(int64_t), ctx->stream));
+    HS_CUDA(ctx, cudaMemsetAsync(p->d_next_read, 0, sizeof(unsigned int), ctx->stream));
     if (nr > 0) {
-        HS_KERNEL(ctx, "span_kernel", span_kernel<<<rblocks, 256, 0, ctx->stream>>>(nr, p->d_cigar, p->d_cigar_off, p->d_read_start, p->d_read_contig,
-                                                      p->d_contig_len, p->d_read_end, p->d_row_alloc));
+        HS_KERNEL(ctx, "span_kernel", span_kernel<<<rblocks, 256, 0, ctx->stream>>>(
+            nr, p->d_cigar, p->d_cigar_off, p->d_read_start, p->d_read_contig, p->d_contig_len, p->d_read_end,
+            p->d_row_alloc, p->d_read_tlead, p->d_read_flags, reinterpret_cast<unsigned long long*>(d_totals + 2)));
     }
     int rc = hs_exclusive_scan_i64(ctx, p->d_row_alloc, p->d_row_alloc, nr, d_totals);
     if (rc) return rc;
@@ -486,12 +726,13 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     }
     rc = hs_exclusive_scan_i64(ctx, p->d_tile_off, p->d_tile_off, p->n_tiles, d_totals + 1);
     if (rc) return rc;
-    int64_t totals[2] = {0, 0};
-    HS_CUDA(ctx, hs_d2h(ctx, totals, d_totals, 2));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the only host round trip of the build: two sizes
+    int64_t totals[3] = {0, 0, 0};
+    HS_CUDA(ctx, hs_d2h(ctx, totals, d_totals, 3));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the only host round trip of the build: three counts
     hs_free(ctx, d_totals);
     p->codes_bytes = totals[0];
     p->tile_entries = totals[1];
+    p->n_irregular = totals[2];
     HS_CUDA(ctx, hs_alloc(ctx, &p->d_codes, p->codes_bytes + HS_ALIGN));
     HS_CUDA(ctx, hs_alloc(ctx, &p->d_tile_reads, p->tile_entries));
     HS_CUDA(ctx, cudaMemcpyAsync(p->d_tile_off + p->n_tiles, &p->tile_entries, sizeof(int64_t), cudaMemcpyHostToDevice,
@@ -511,11 +752,23 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
         a.read_start = p->d_read_start;
         a.read_strand = p->d_read_strand;
         a.read_end = p->d_read_end;
+        a.read_tlead = p->d_read_tlead;
+        a.read_flags = p->d_read_flags;
         a.row_off = p->d_row_alloc;
         a.row_base = p->d_row_base;
         a.codes = p->d_codes;
         a.stats = p->d_stats;
-        HS_KERNEL(ctx, "pileup_kernel", pileup_kernel<<<rblocks, 256, 0, ctx->stream>>>(a));
+        a.next_read = p->d_next_read;
+        // persistent warps pull reads from a counter: read lengths vary by an order of magnitude
+        static int ctas_per_sm = 0;
+        if (!ctas_per_sm) {
+            HS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_kernel, 32 * PW_WARPS, 0));
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+        }
+        const unsigned pgrid = (unsigned)std::min<int64_t>(rblocks, (int64_t)ctx->sm_count * ctas_per_sm);
+        HS_KERNEL(ctx, "pileup_kernel", pileup_kernel<<<pgrid, 32 * PW_WARPS, 0, ctx->stream>>>(a));
+        if (p->n_irregular > 0)
+            HS_KERNEL(ctx, "pileup_generic_kernel", pileup_generic_kernel<<<rblocks, 256, 0, ctx->stream>>>(a));
     }
     if (p->n_tiles > 0) {
         HS_KERNEL(ctx, "tile_index_kernel<true>", tile_index_kernel<true><<<(unsigned)((p->n_tiles + 7) / 8), 256, 0, ctx->stream>>>(
