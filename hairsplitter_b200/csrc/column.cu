@@ -7,10 +7,12 @@
 // memory ([code][column] layout, so the common case "all reads agree" is conflict-free) and
 // recording the order in which codes first appear -- that order is the insertion order of the
 // reference's robin_hood map and decides ties (rank.cuh).
+#include <algorithm>
+
 #include "common.cuh"
 #include "rank.cuh"
 
-#define COL_ROWS 64  // rows staged per batch
+#define COL_ROWS 64  // rows staged per batch (export_kernel)
 
 struct ColumnArgs {
     int64_t n_tiles;
@@ -34,16 +36,13 @@ struct ColumnArgs {
     unsigned long long* depth_sum;
     int32_t* error_flag;
     const HsRankLut* lut;
-    int32_t* work;             // global column ids that need the literal replay
-    unsigned int* n_work;
-};
-
-struct SmemAcc {
-    const uint8_t* order;
-    const uint16_t* hist;
-    int col;
-    __device__ __forceinline__ int key(int k) const { return order[k * HS_TILE + col] + HS_CODE0; }
-    __device__ __forceinline__ unsigned count(int key) const { return hist[(key - HS_CODE0) * HS_TILE + col]; }
+    // deferred tie resolution: columns the bucket table cannot decide leave their (code, count) list, in
+    // first-seen order, in an arena; the few that do not fit are listed for a re-read of the column
+    uint32_t* arena;
+    unsigned int arena_words;
+    unsigned int* counters;    // [0] arena words used, [1] arena items, [2] re-read items
+    uint32_t* item_off;        // arena offset of every item
+    int32_t* reread;           // global column ids
 };
 
 // stage rows [b0, b0+nrows) of the tile into s_tile[row][128]
@@ -85,16 +84,44 @@ __device__ __forceinline__ void write_column(const ColumnArgs& a, int64_t g, int
     a.flags[g] = (uint8_t)f;
 }
 
+// ---- the column histogram kernel -----------------------------------------------------------------------
+// One CTA per 128-column tile, one thread per column. Row metadata (row pointer, which of the eight
+// 16-byte vectors of the tile the read covers) is resolved once per 128 list entries; the rows then stream
+// through a double-buffered shared-memory stage with cp.async (16 rows per batch, one 16-byte copy per
+// thread, zero-fill where the read does not reach), so the loads of batch b+1 overlap the histogram
+// updates of batch b. Histogram: u16 [126][128] in shared memory, bin 0 = "no cell here" so the update is
+// branch-free; the first CR_ORD distinct codes of a column are kept in first-seen order.
+#define CR_ROWS 16
+#define CR_ORD 32
+#define CR_BINS (HS_NCODES + 1)
+#define CR_META 128
+
+struct SmemAcc {
+    const uint8_t* order;   // [CR_ORD][128] codes in first-seen order
+    const uint16_t* hist;   // [CR_BINS][128], bin = code - 32
+    int col;
+    __device__ __forceinline__ int key(int k) const { return order[k * HS_TILE + col]; }
+    __device__ __forceinline__ unsigned count(int key) const { return hist[(key - 32) * HS_TILE + col]; }
+};
+
+static const int kColumnSmem = 2 * CR_ROWS * HS_TILE + CR_BINS * HS_TILE * 2 + CR_ORD * HS_TILE + CR_META * 8 + CR_META;
+
+__device__ __forceinline__ void cr_cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
 __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint4* s_tile = reinterpret_cast<uint4*>(smem);                                   // COL_ROWS * 128 B
-    uint16_t* s_hist = reinterpret_cast<uint16_t*>(smem + COL_ROWS * HS_TILE);        // [125][128] u16
-    uint8_t* s_order = smem + COL_ROWS * HS_TILE + HS_NCODES * HS_TILE * 2;           // [125][128] u8
+    unsigned char* s_rows = smem;                                                        // 2 x 16 x 128 B
+    uint16_t* s_hist = reinterpret_cast<uint16_t*>(smem + 2 * CR_ROWS * HS_TILE);        // [126][128] u16
+    uint8_t* s_order = smem + 2 * CR_ROWS * HS_TILE + CR_BINS * HS_TILE * 2;             // [32][128] u8
+    const uint8_t** s_ptr = reinterpret_cast<const uint8_t**>(s_order + CR_ORD * HS_TILE);  // [128]
+    uint8_t* s_vmask = reinterpret_cast<uint8_t*>(s_ptr + CR_META);                      // [128]
     __shared__ unsigned long long s_depth;
     __shared__ HsRankLut s_lut;
-    __shared__ uint8_t s_work[HS_TILE];
-    __shared__ int s_nwork;
-    __shared__ unsigned s_gbase;
+    __shared__ int s_scan[4];
+    __shared__ unsigned int s_base[2];
 
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -105,78 +132,190 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
     const int nlist = (int)(a.tile_off[tile + 1] - list_off);
     if (tid == 0) {
         s_depth = 0;
-        if (nlist > 65535) atomicExch(a.error_flag, 1);  // u16 histogram bins; the reference's own loop is a `short` (:479)
+        if (nlist > 65000) atomicExch(a.error_flag, 1);  // u16 histogram bins; the reference's own loop is a `short` (:479)
     }
     {
         uint4* h4 = reinterpret_cast<uint4*>(s_hist);
-        for (int i = tid; i < HS_NCODES * HS_TILE * 2 / 16; i += HS_TILE) h4[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < CR_BINS * HS_TILE * 2 / 16; i += HS_TILE) h4[i] = make_uint4(0, 0, 0, 0);
     }
-    int m = 0;
-    unsigned int depth = 0;
-    const unsigned char* s_bytes = reinterpret_cast<const unsigned char*>(s_tile);
-    for (int b0 = 0; b0 < nlist; b0 += COL_ROWS) {
-        const int nrows = min(COL_ROWS, nlist - b0);
+    __syncthreads();
+    s_hist[tid] = 1;  // bin 0 ("no cell") never looks like a first sighting
+    int m = 0, rows_done = 0;
+    uint16_t* const hcol = s_hist + tid;
+    const int crow = tid >> 3, cpart = tid & 7;  // this thread's copy slot in a batch: row, 16-byte part
+    for (int sb = 0; sb < nlist; sb += CR_META) {
+        const int nmeta = min(CR_META, nlist - sb);
+        __syncthreads();  // the previous super-batch's copies have all been issued and consumed
+        if (tid < nmeta) {
+            const int32_t r = __ldg(a.tile_reads + list_off + sb + tid);
+            const int s = __ldg(a.read_start + r) & ~(HS_ALIGN - 1);
+            const int e = (__ldg(a.read_end + r) + HS_ALIGN - 1) & ~(HS_ALIGN - 1);
+            unsigned vm = 0;
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                const int qv = q0 + 16 * p;
+                if (qv >= s && qv < e) vm |= 1u << p;
+            }
+            s_ptr[tid] = a.codes + __ldg(a.row_base + r) + q0;
+            s_vmask[tid] = (uint8_t)vm;
+        }
         __syncthreads();
-        stage_rows(s_tile, a.tile_reads, list_off, b0, nrows, q0, a.read_start, a.read_end, a.row_base, a.codes, tid,
-                   HS_TILE);
-        __syncthreads();
-        for (int row = 0; row < nrows; row++) {
-            const int code = s_bytes[row * HS_TILE + tid];
-            if (code) {
-                const int idx = code - HS_CODE0;
-                const unsigned int cnt = s_hist[idx * HS_TILE + tid];
-                if (cnt == 0) s_order[(m++) * HS_TILE + tid] = (uint8_t)idx;
-                s_hist[idx * HS_TILE + tid] = (uint16_t)(cnt + 1);
-                depth++;
+        const int nb = (nmeta + CR_ROWS - 1) / CR_ROWS;
+        rows_done += nb * CR_ROWS;  // the rows past the list's end are zero-filled: they count as "no cell"
+        // issue batch 0
+        {
+            const int row = crow;
+            const bool ok = row < nmeta && ((s_vmask[row] >> cpart) & 1);
+            cr_cp_async16(s_rows + (crow * HS_TILE + 16 * cpart), ok ? (const void*)(s_ptr[row] + 16 * cpart) : (const void*)a.codes,
+                          ok ? 16 : 0);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        for (int b = 0; b < nb; b++) {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncthreads();  // batch b has landed for everyone; everyone is done with batch b-1
+            if (b + 1 < nb) {
+                const int row = (b + 1) * CR_ROWS + crow;
+                const bool ok = row < nmeta && ((s_vmask[row] >> cpart) & 1);
+                cr_cp_async16(s_rows + (((b + 1) & 1) * CR_ROWS * HS_TILE + crow * HS_TILE + 16 * cpart),
+                              ok ? (const void*)(s_ptr[row] + 16 * cpart) : (const void*)a.codes, ok ? 16 : 0);
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+            }
+            const unsigned char* colp = s_rows + (b & 1) * CR_ROWS * HS_TILE + tid;
+            int code[CR_ROWS];
+#pragma unroll
+            for (int row = 0; row < CR_ROWS; row++) code[row] = colp[row * HS_TILE];
+#pragma unroll
+            for (int row = 0; row < CR_ROWS; row++) {
+                const int bin = max(code[row], 32) - 32;
+                const unsigned int cnt = hcol[bin * HS_TILE];
+                if (cnt == 0) {
+                    if (m < CR_ORD) s_order[m * HS_TILE + tid] = (uint8_t)code[row];
+                    m++;
+                }
+                hcol[bin * HS_TILE] = (uint16_t)(cnt + 1);
             }
         }
     }
-    // ---- ranking. Ties are decided by the bucket table (rank.cuh); the few columns that need the literal
-    // replay of the reference's map + sort are appended to a global work list and handled by
-    // column_rank_literal_kernel, so that no CTA waits for a straggling replay.
+    // ---- ranking. Ties are decided by the bucket table (rank.cuh); the columns it cannot decide are
+    // deferred, so that no CTA waits for a straggling replay.
     __syncthreads();
     for (int i = tid; i < (int)sizeof(HsRankLut); i += HS_TILE)
         reinterpret_cast<uint8_t*>(&s_lut)[i] = reinterpret_cast<const uint8_t*>(a.lut)[i];
-    if (tid == 0) s_nwork = 0;
     __syncthreads();
     const int q = q0 + tid;
     const int mr = a.min_reads[c];
     const int64_t gbase = a.col_base[c];
-    bool literal = false;
+    const unsigned int depth = (unsigned int)(rows_done + 1) - hcol[0];
+    int defer = 0;  // 1: arena item, 2: re-read
     if (q < L) {
-        SmemAcc acc{s_order, s_hist, tid};
-        int k0, k1;
-        unsigned c0, c1, c2;
-        literal = hs_rank_fast(acc, m, &s_lut, k0, k1, c0, c1, c2) != 0;
-        if (!literal) write_column(a, gbase + q, k0, k1, c0, c1, c2, mr);
+        if (m > CR_ORD) {
+            defer = 2;
+        } else {
+            SmemAcc acc{s_order, s_hist, tid};
+            int k0, k1;
+            unsigned c0, c1, c2;
+            if (hs_rank_fast(acc, m, &s_lut, k0, k1, c0, c1, c2) != 0) defer = 1;
+            else write_column(a, gbase + q, k0, k1, c0, c1, c2, mr);
+        }
         a.depth[gbase + q] = depth;
     }
     {
-        const unsigned lm = __ballot_sync(0xffffffffu, literal);
-        int wbase = 0;
-        if ((tid & 31) == 0 && lm) wbase = atomicAdd(&s_nwork, __popc(lm));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (literal) s_work[wbase + __popc(lm & ((1u << (tid & 31)) - 1u))] = (uint8_t)tid;
-    }
-    __syncthreads();
-    if (s_nwork > 0) {
-        if (tid == 0) s_gbase = atomicAdd(a.n_work, (unsigned)s_nwork);
+        // arena space for the deferred columns of this tile: block-wide exclusive scan of the word counts
+        const int lane = tid & 31, wid = tid >> 5;
+        const int need = defer == 1 ? 2 + m : 0;
+        const int incl = hs_warp_incl_scan(need, lane);
+        const unsigned dm = __ballot_sync(0xffffffffu, defer == 1);
+        if (lane == 31) s_scan[wid] = incl;
         __syncthreads();
-        if (tid < s_nwork) a.work[s_gbase + tid] = (int32_t)(gbase + q0 + s_work[tid]);
+        int woff = 0, total = 0, iwoff = 0, itotal = 0;
+        for (int w = 0; w < 4; w++) {
+            const int t = s_scan[w];
+            if (w < wid) woff += t;
+            total += t;
+        }
+        __syncthreads();
+        if (lane == 0) s_scan[wid] = __popc(dm);
+        __syncthreads();
+        for (int w = 0; w < 4; w++) {
+            const int t = s_scan[w];
+            if (w < wid) iwoff += t;
+            itotal += t;
+        }
+        if (tid == 0 && total > 0) {
+            s_base[0] = atomicAdd(a.counters + 0, (unsigned)total);
+            s_base[1] = atomicAdd(a.counters + 1, (unsigned)itotal);
+        }
+        __syncthreads();
+        if (defer == 1) {
+            const unsigned int off = s_base[0] + woff + incl - need;
+            if (s_base[0] + (unsigned)total <= a.arena_words) {
+                a.arena[off] = (uint32_t)(gbase + q);
+                a.arena[off + 1] = (uint32_t)m;
+                for (int k = 0; k < m; k++) {
+                    const int key = s_order[k * HS_TILE + tid];
+                    a.arena[off + 2 + k] = ((uint32_t)hcol[(key - 32) * HS_TILE] << 8) | (uint32_t)key;
+                }
+                a.item_off[s_base[1] + iwoff + __popc(dm & ((1u << lane) - 1u))] = off;
+            } else {
+                a.item_off[s_base[1] + iwoff + __popc(dm & ((1u << lane) - 1u))] = 0xffffffffu;  // arena full
+                defer = 2;
+            }
+        }
+        if (defer == 2) a.reread[atomicAdd(a.counters + 2, 1u)] = (int32_t)(gbase + q);
     }
     // depthOfCoverage numerator (:486,565)
-    unsigned long long d = depth;
+    unsigned long long d = (q < L) ? depth : 0;
     for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
     if ((tid & 31) == 0 && d) atomicAdd(&s_depth, d);
     __syncthreads();
     if (tid == 0 && s_depth) atomicAdd(a.depth_sum + c, s_depth);
 }
 
+// Deferred tie resolution, one thread per arena item: the hash-bit table first (rank.cuh), the literal
+// replay of the reference's map + sort for what is left (about 1 % of the columns at 10 % error, 60x).
+struct ItemAcc {
+    const uint8_t* order;
+    const uint16_t* cnt;
+    __device__ __forceinline__ int key(int k) const { return order[k]; }
+    __device__ __forceinline__ unsigned count(int key) const { return cnt[key - HS_CODE0]; }
+};
+
+__global__ void __launch_bounds__(128) column_rank_deferred_kernel(ColumnArgs a, int n_contigs) {
+    __shared__ HsRankLut s_lut;
+    for (int i = threadIdx.x; i < (int)sizeof(HsRankLut); i += blockDim.x)
+        reinterpret_cast<uint8_t*>(&s_lut)[i] = reinterpret_cast<const uint8_t*>(a.lut)[i];
+    __syncthreads();
+    const unsigned n = a.counters[1];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned off = a.item_off[i];
+        if (off == 0xffffffffu) continue;  // went to the re-read list
+        const int64_t g = a.arena[off];
+        const int m = (int)a.arena[off + 1];
+        uint16_t cnt[HS_NCODES];
+        uint8_t order[CR_ORD];
+        for (int k = 0; k < m; k++) {
+            const uint32_t e = a.arena[off + 2 + k];
+            order[k] = (uint8_t)(e & 0xff);
+            cnt[(e & 0xff) - HS_CODE0] = (uint16_t)(e >> 8);
+        }
+        int lo = 0, hi = n_contigs - 1;  // contig of this column
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (a.col_base[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        ItemAcc acc{order, cnt};
+        int k0, k1;
+        unsigned c0, c1, c2;
+        if (hs_rank_hashbits(acc, m, &s_lut, k0, k1, c0, c1, c2)) hs_rank_literal(acc, m, k0, k1, c0, c1, c2);
+        write_column(a, g, k0, k1, c0, c1, c2, a.min_reads[lo]);
+    }
+}
+
 // Deferred literal replay: one thread per listed column. The column is re-read from the pileup (a few
 // dozen byte loads) in ascending read order, then the reference's map + sort are replayed (rank.cuh).
 struct LiteralArgs {
     const int32_t* work;
-    const unsigned int* n_work;
+    const unsigned int* n_work;  // re-read list (columns with more than CR_ORD codes, or arena overflow)
     int n_contigs;
     const int64_t* col_base;
     const int64_t* tile_base;
@@ -405,7 +544,6 @@ __global__ void gather_depth_kernel(int n, const int32_t* __restrict__ pos, int6
     if (i < n) out[i] = depth[g0 + pos[i]];
 }
 
-static const int kColumnSmem = COL_ROWS * HS_TILE + HS_NCODES * HS_TILE * 2 + HS_NCODES * HS_TILE;
 
 extern "C" {
 
@@ -470,14 +608,25 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
         a.depth_sum = p->d_depth_sum;
         a.error_flag = p->d_min_reads + nc;
         a.lut = (const HsRankLut*)ctx->d_rank_lut;
-        if (!p->d_work) HS_CUDA(ctx, hs_alloc(ctx, &p->d_work, p->n_cols + 1));
-        a.work = p->d_work + 1;
-        a.n_work = reinterpret_cast<unsigned int*>(p->d_work);
-        HS_CUDA(ctx, cudaMemsetAsync(p->d_work, 0, sizeof(int32_t), ctx->stream));
+        // d_work: [0..3] counters (arena words, arena items, re-read items), then the re-read list
+        if (!p->d_work) HS_CUDA(ctx, hs_alloc(ctx, &p->d_work, p->n_cols + 4));
+        if (!p->d_arena) {
+            p->arena_words = (unsigned int)std::min<int64_t>(2 * p->n_cols + 1024, 0x7fffffff);
+            HS_CUDA(ctx, hs_alloc(ctx, &p->d_arena, p->arena_words));
+            HS_CUDA(ctx, hs_alloc(ctx, &p->d_item_off, p->n_cols));
+        }
+        a.arena = p->d_arena;
+        a.arena_words = p->arena_words;
+        a.counters = reinterpret_cast<unsigned int*>(p->d_work);
+        a.item_off = p->d_item_off;
+        a.reread = p->d_work + 4;
+        HS_CUDA(ctx, cudaMemsetAsync(p->d_work, 0, 4 * sizeof(int32_t), ctx->stream));
         HS_KERNEL(ctx, "column_rank_kernel", column_rank_kernel<<<(unsigned)p->n_tiles, HS_TILE, kColumnSmem, ctx->stream>>>(a));
+        HS_KERNEL(ctx, "column_rank_deferred_kernel",
+                  column_rank_deferred_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a, nc));
         LiteralArgs la;
-        la.work = a.work;
-        la.n_work = a.n_work;
+        la.work = a.reread;
+        la.n_work = a.counters + 2;
         la.n_contigs = nc;
         la.col_base = p->d_col_base;
         la.tile_base = p->d_tile_base;
@@ -489,7 +638,7 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
         la.codes = p->d_codes;
         la.col = a;
         HS_KERNEL(ctx, "column_rank_literal_kernel",
-                  column_rank_literal_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(la));
+                  column_rank_literal_kernel<<<ctx->sm_count * 2, 128, 0, ctx->stream>>>(la));
     }
     if (p->n_tiles > 0) {
         if (!p->d_tile_sus) HS_CUDA(ctx, hs_alloc(ctx, &p->d_tile_sus, p->n_tiles + 1));
@@ -522,7 +671,7 @@ int hsgpu_column_counts(hsgpu_pileup* p, int32_t* n_suspects, int64_t* depth_sum
     if (n_suspects) HS_CUDA(ctx, hs_d2h(ctx, n_suspects, p->d_n_suspects, p->n_contigs));
     if (depth_sum) HS_CUDA(ctx, hs_d2h(ctx, (unsigned long long*)depth_sum, p->d_depth_sum, p->n_contigs));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (err) HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_column_rank: more than 65535 reads over one 128-column tile");
+    if (err) HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_column_rank: more than 65000 reads over one 128-column tile");
     return HSGPU_OK;
 }
 

@@ -184,7 +184,10 @@ struct hsgpu_pileup {
     std::vector<int64_t> h_suspect_base;
     int64_t* d_suspect_base = nullptr;
     int64_t* d_col_off = nullptr;  // exclusive scan of d_depth (lazy, for export)
-    int32_t* d_work = nullptr;     // [0] = count, then column ids for the literal ranking replay
+    int32_t* d_work = nullptr;     // [0..3] counters, then column ids for the re-read literal replay
+    uint32_t* d_arena = nullptr;   // (code, count) lists of the columns whose ties are resolved by the deferred kernel
+    uint32_t* d_item_off = nullptr;
+    unsigned int arena_words = 0;
     int64_t* d_tile_sus = nullptr; // accepted suspects per tile, then its exclusive scan
     bool have_col_off = false;
 };

@@ -610,6 +610,8 @@ void hsgpu_pileup_destroy(hsgpu_pileup* p) {
     hs_free(ctx, p->d_col_off);
     hs_free(ctx, p->d_tile_sus);
     hs_free(ctx, p->d_work);
+    hs_free(ctx, p->d_arena);
+    hs_free(ctx, p->d_item_off);
     delete p;
 }
 

@@ -272,6 +272,7 @@ HS_HD void hs_kc_std_sort(uint32_t* v, int n) {
 // (shared bucket, n > 16 where introsort is unstable) replays the reference's map + sort literally.
 struct HsRankLut {
     uint8_t home[3][160];  // home bucket of key k in the table incarnation `level`
+    uint8_t hbits[3][160]; // the 5 hash bits robin_hood keeps in the info byte (robin_hood.h:1349-1356)
     uint8_t single[128];   // m == 1: second_base (a dummy key) for code 33 + i
     uint8_t empty[2];      // m == 0: ref_base, second_base
 };
@@ -368,6 +369,76 @@ HS_HD int hs_rank_fast(const Acc& acc, int m, const HsRankLut* lut, int& k0, int
     return 0;
 }
 
+// Second-level tie resolution for n <= 16: keys that share a home bucket. insertKeyPrepareEmptySpot skips
+// occupants whose info byte is >= the new key's (robin_hood.h:2339-2343); the info byte is
+// (distance+1)*32 + 5 hash bits, so inside one home bucket the entries end up ordered by those hash bits,
+// descending, and only keys that agree in bucket AND hash bits fall back on the insertion history. The
+// 5-bit comparison holds as long as the final table incarnation never widened its info bytes
+// (try_increase_info, :2385), i.e. while no entry sits 6 or more slots from home; displacements only
+// grow, so checking the final layout is enough. Returns 0 when resolved, 1 when the literal replay is
+// still needed. Keys/counts are given in first-seen order, like for hs_rank_literal.
+template <class Acc>
+HS_HD int hs_rank_hashbits(const Acc& acc, int m, const HsRankLut* lut, int& k0, int& k1, unsigned& c0, unsigned& c1,
+                           unsigned& c2) {
+    const int n = m + 3;
+    if (m < 2 || n > 16) return 1;
+    const int level = hs_rank_level(n);
+    const uint8_t* home = lut->home[level];
+    const uint8_t* hbits = lut->hbits[level];
+    // final layout: bucket occupancy as 4-bit counters (n <= 16 keys, up to 32 buckets)
+    unsigned long long occ_lo = 0, occ_hi = 0;
+    for (int k = -3; k < m; k++) {
+        const int key = k < 0 ? k + 3 : acc.key(k);  // the dummy keys 0,1,2 (:477-494) sit in the table too
+        const int h = home[key];
+        if (h < 16) occ_lo += 1ull << (4 * h); else occ_hi += 1ull << (4 * (h - 16));
+    }
+    int next_free = 0, maxd = 0;
+    const int nb = 8 << level;
+    for (int b = 0; b < nb; b++) {
+        const int cnt = (int)(((b < 16) ? (occ_lo >> (4 * b)) : (occ_hi >> (4 * (b - 16)))) & 15ull);
+        if (next_free < b) next_free = b;
+        next_free += cnt;
+        if (cnt && next_free - 1 - b > maxd) maxd = next_free - 1 - b;
+    }
+    if (maxd >= 6) return 1;
+    c0 = c1 = c2 = 0;
+    k0 = k1 = 0;
+    for (int k = 0; k < m; k++) {
+        const unsigned cnt = acc.count(acc.key(k));
+        if (cnt > c0) { c2 = c1; c1 = c0; c0 = cnt; }
+        else if (cnt > c1) { c2 = c1; c1 = cnt; }
+        else if (cnt > c2) { c2 = cnt; }
+    }
+    // iteration rank of a key: (home bucket, 31 - hash bits); the three smallest among count == c0 and the
+    // two smallest among count == c1 decide
+    int a0 = 0, a1 = 0, b0 = 0, ra0 = 4096, ra1 = 4096, ra2 = 4096, rb0 = 4096, rb1 = 4096, n0 = 0, n1 = 0;
+    for (int k = 0; k < m; k++) {
+        const int key = acc.key(k);
+        const unsigned cnt = acc.count(key);
+        const int rk = home[key] * 32 + 31 - hbits[key];
+        if (cnt == c0) {
+            n0++;
+            if (rk < ra0) { ra2 = ra1; ra1 = ra0; a1 = a0; ra0 = rk; a0 = key; }
+            else if (rk < ra1) { ra2 = ra1; ra1 = rk; a1 = key; }
+            else if (rk < ra2) { ra2 = rk; }
+        } else if (cnt == c1) {
+            n1++;
+            if (rk < rb0) { rb1 = rb0; rb0 = rk; b0 = key; }
+            else if (rk < rb1) { rb1 = rk; }
+        }
+    }
+    if (n0 >= 2) {  // c1 == c0 here: ranks 0 and 1 are the first two of the c0 set
+        if (ra0 == ra1 || ra1 == ra2) return 1;
+        k0 = a0;
+        k1 = a1;
+    } else {
+        k0 = a0;
+        if (n1 >= 2 && rb0 == rb1) return 1;
+        k1 = b0;
+    }
+    return 0;
+}
+
 // host only: builds the tables by replaying the reference behaviour
 struct HsRankOneKey {
     int code;
@@ -384,6 +455,7 @@ inline void hs_build_rank_lut(HsRankLut& lut) {
             uint32_t idx, info;
             hs_rh_key_to_idx(t, (uint8_t)key, idx, info);
             lut.home[level][key] = (uint8_t)idx;
+            lut.hbits[level][key] = (uint8_t)(info - t.info_inc);
         }
     }
     for (int i = 0; i < 128; i++) {

@@ -91,6 +91,19 @@ def test_ranking_source_matches_oracle(oracle):
             assert np.array_equal(out[:5], want), (mode, col)
             n_fast += (mode == 0 and out[5] == 0)
     assert n_fast > 2000  # the table decides the large majority of columns
+    # tie-heavy columns: every code once or twice, so the rank is decided by the iteration order of the
+    # reference's table alone (home bucket, then the hash bits kept in the info byte, then history)
+    n_table = 0
+    for it in range(8000):
+        ncodes = int(rng.integers(2, 14))
+        alphabet = (rng.permutation(125)[:ncodes] + 33).astype(np.uint8)
+        col = rng.permutation(np.repeat(alphabet, rng.integers(1, 3, ncodes))).astype(np.uint8)
+        want = oracle.column_rank(col)
+        out = np.zeros(6, np.int32)
+        lib.hsgpu_debug_rank_column(col.ctypes.data, col.shape[0], out.ctypes.data, 0)
+        assert np.array_equal(out[:5], want), col
+        n_table += out[5] == 0
+    assert n_table > 6000
 
 
 def test_synthetic_generator_is_self_consistent():
