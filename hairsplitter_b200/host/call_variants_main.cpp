@@ -1,0 +1,296 @@
+// HS_call_variants -- drop-in for the reference executable of the same name (src/call_variants.cpp:1215-1386,
+// called by hairsplitter.py with 11 positional arguments). Parsing, partition building and the writers run
+// on the host; the pileup (generate_msa), the per-column allele ranking (call_variants) and the
+// partition x column filtering (loops 3+4 of keep_only_robust_variants) run on the GPU through the
+// C ABI of libhsgpu (include/hsgpu.h). Contigs are sharded over the visible GPUs, heaviest first.
+#include <omp.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/hsgpu.h"
+#include "hs_io.h"
+#include "hs_partition.h"
+
+using namespace hs;
+
+#define GPU_CHECK(ctx, call)                                                                        \
+    do {                                                                                            \
+        const int _rc = (call);                                                                     \
+        if (_rc != HSGPU_OK) {                                                                      \
+            std::cout << "ERROR: " #call " failed (" << _rc << "): " << hsgpu_last_error(ctx) << std::endl; \
+            std::exit(1);                                                                           \
+        }                                                                                           \
+    } while (0)
+
+struct ContigResult {
+    float mean_distance = 0;
+    float depth = 0;
+    std::vector<Column> merged;
+};
+
+static void fetch_columns(hsgpu_ctx* ctx, hsgpu_pileup* pu, int c, const std::vector<int32_t>& pos,
+                          const std::vector<uint8_t>& k0, const std::vector<uint8_t>& k1, std::vector<Column>& out) {
+    out.clear();
+    const int n = (int)pos.size();
+    if (n == 0) return;
+    std::vector<int64_t> off(n + 1, 0);
+    // first call sizes the cell buffers
+    int rc = hsgpu_pileup_extract_columns(pu, c, n, pos.data(), 0, off.data(), nullptr, nullptr);
+    if (rc != HSGPU_OK && rc != HSGPU_ERR_CAPACITY) GPU_CHECK(ctx, rc);
+    std::vector<uint32_t> idx((size_t)std::max<int64_t>(off[n], 1));
+    std::vector<uint8_t> code((size_t)std::max<int64_t>(off[n], 1));
+    GPU_CHECK(ctx, hsgpu_pileup_extract_columns(pu, c, n, pos.data(), off[n], off.data(), idx.data(), code.data()));
+    out.resize(n);
+    for (int i = 0; i < n; i++) {
+        Column& col = out[i];
+        col.pos = pos[i];
+        col.ref_base = k0[pos[i]];
+        col.second_base = k1[pos[i]];
+        col.readIdxs.assign(idx.begin() + off[i], idx.begin() + off[i + 1]);
+        col.content.assign(code.begin() + off[i], code.begin() + off[i + 1]);
+    }
+}
+
+// one batch of contigs on one GPU
+static void process_batch(hsgpu_ctx* ctx, const Store& st, const std::string& reads_path, const std::vector<int>& batch,
+                          float auto_threshold, std::vector<ContigResult>& results) {
+    const int nc = (int)batch.size();
+    std::ifstream reads_file(reads_path);
+    std::vector<int32_t> contig_len(nc), read_len, read_start;
+    std::vector<int64_t> contig_word_off(nc + 1, 0), contig_read_off(nc + 1, 0), read_word_off(1, 0), cigar_off(1, 0);
+    std::vector<uint32_t> contig_bases, read_bases, cigar, ops;
+    std::vector<uint8_t> read_strand;
+    std::vector<std::string> seqs;
+    for (int b = 0; b < nc; b++) {
+        const SeqRec& contig = st.seqs[st.contigs[batch[b]]];
+        contig_len[b] = (int32_t)contig.sequence.size();
+        const int64_t w = ((int64_t)contig.sequence.size() + 15) / 16;
+        contig_bases.resize((size_t)(contig_word_off[b] + w));
+        hsgpu_pack_bases_ascii(contig.sequence.data(), (int64_t)contig.sequence.size(), contig_bases.data() + contig_word_off[b]);
+        contig_word_off[b + 1] = contig_word_off[b] + w;
+        load_read_sequences(reads_file, st, st.contigs[batch[b]], seqs);
+        for (size_t n = 0; n < contig.alns.size(); n++) {
+            const Alignment& a = st.alns[contig.alns[n]];
+            const std::string& s = seqs[n];
+            const int64_t rw = ((int64_t)s.size() + 15) / 16;
+            read_bases.resize((size_t)(read_word_off.back() + rw));
+            hsgpu_pack_bases_ascii(s.data(), (int64_t)s.size(), read_bases.data() + read_word_off.back());
+            read_word_off.push_back(read_word_off.back() + rw);
+            read_len.push_back((int32_t)s.size());
+            cigar_ops(a.cigar, ops);
+            cigar.insert(cigar.end(), ops.begin(), ops.end());
+            cigar_off.push_back((int64_t)cigar.size());
+            read_start.push_back(a.pos_2_1);
+            read_strand.push_back(a.strand ? 1 : 0);
+        }
+        contig_read_off[b + 1] = (int64_t)read_len.size();
+    }
+    if (contig_bases.empty()) contig_bases.push_back(0);
+    if (read_bases.empty()) read_bases.push_back(0);
+    if (cigar.empty()) cigar.push_back(0);
+    hsgpu_pileup_input in;
+    std::memset(&in, 0, sizeof(in));
+    in.n_contigs = nc;
+    in.contig_len = contig_len.data();
+    in.contig_bases = contig_bases.data();
+    in.contig_word_off = contig_word_off.data();
+    in.contig_read_off = contig_read_off.data();
+    in.n_reads = (int64_t)read_len.size();
+    in.read_bases = read_bases.data();
+    in.read_word_off = read_word_off.data();
+    in.read_len = read_len.data();
+    in.cigar = cigar.data();
+    in.cigar_off = cigar_off.data();
+    in.read_start = read_start.data();
+    in.read_strand = read_strand.data();
+    hsgpu_pileup* pu = nullptr;
+    GPU_CHECK(ctx, hsgpu_pileup_create(ctx, &in, &pu));
+    GPU_CHECK(ctx, hsgpu_pileup_build(pu));                            // generate_msa
+    GPU_CHECK(ctx, hsgpu_column_rank(pu, nullptr, auto_threshold));    // call_variants
+    std::vector<int64_t> cells(nc), dist(nc), alen(nc), depth_sum(nc);
+    std::vector<int32_t> n_suspects(nc);
+    GPU_CHECK(ctx, hsgpu_pileup_stats(pu, cells.data(), dist.data(), alen.data()));
+    GPU_CHECK(ctx, hsgpu_column_counts(pu, n_suspects.data(), depth_sum.data()));
+
+    // phase A: suspect columns of every contig (device -> host)
+    std::vector<std::vector<Column>> suspects(nc);
+    std::vector<std::vector<uint8_t>> is_auto(nc), k0(nc), k1(nc);
+    std::vector<std::vector<int32_t>> suspect_pos(nc);
+    for (int b = 0; b < nc; b++) {
+        const int L = contig_len[b];
+        k0[b].resize(std::max(L, 1));
+        k1[b].resize(std::max(L, 1));
+        GPU_CHECK(ctx, hsgpu_column_summary(pu, b, k0[b].data(), k1[b].data(), nullptr, nullptr));
+        suspect_pos[b].resize(std::max(n_suspects[b], 1));
+        is_auto[b].resize(std::max(n_suspects[b], 1));
+        GPU_CHECK(ctx, hsgpu_suspects(pu, b, n_suspects[b], suspect_pos[b].data(), is_auto[b].data()));
+        suspect_pos[b].resize(n_suspects[b]);
+        is_auto[b].resize(n_suspects[b]);
+        fetch_columns(ctx, pu, b, suspect_pos[b], k0[b], k1[b], suspects[b]);
+    }
+    // phase B: partitions (loops 1+2 of keep_only_robust_variants), contigs in parallel on the host
+    std::vector<std::vector<Partition>> parts(nc);
+    std::vector<float> mean_distance(nc);
+    for (int b = 0; b < nc; b++) mean_distance[b] = hsgpu_mean_distance(dist[b], alen[b]);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < nc; b++) build_partitions(suspects[b], mean_distance[b], parts[b]);
+    // phase C: loops 3+4 on the device, then the merge with the automatic SNPs (main(), :1334-1352)
+    for (int b = 0; b < nc; b++) {
+        ContigResult& res = results[batch[b]];
+        res.mean_distance = mean_distance[b];
+        res.depth = (float)((double)depth_sum[b] / (size_t)contig_len[b]);
+        std::vector<Column> filtered;
+        if (!parts[b].empty()) {
+            std::vector<int64_t> part_off(1, 0);
+            std::vector<int32_t> idx, more, less;
+            std::vector<int16_t> state;
+            for (const Partition& p : parts[b]) {
+                idx.insert(idx.end(), p.readIdx.begin(), p.readIdx.end());
+                state.insert(state.end(), p.state.begin(), p.state.end());
+                more.insert(more.end(), p.more.begin(), p.more.end());
+                less.insert(less.end(), p.less.begin(), p.less.end());
+                part_off.push_back((int64_t)idx.size());
+            }
+            hsgpu_partitions hp;
+            hp.n_parts = (int32_t)parts[b].size();
+            hp.part_off = part_off.data();
+            hp.read_idx = idx.data();
+            hp.state = state.data();
+            hp.more = more.data();
+            hp.less = less.data();
+            std::vector<int32_t> kept((size_t)std::max(contig_len[b], 1));
+            int32_t n_kept = 0;
+            GPU_CHECK(ctx, hsgpu_robust_filter(pu, b, &hp, n_suspects[b], suspect_pos[b].data(), contig_len[b], kept.data(), &n_kept));
+            kept.resize(n_kept);
+            fetch_columns(ctx, pu, b, kept, k0[b], k1[b], filtered);
+        }
+        size_t ia = 0, jf = 0;
+        std::vector<const Column*> automatic;
+        for (size_t i = 0; i < suspects[b].size(); i++)
+            if (is_auto[b][i]) automatic.push_back(&suspects[b][i]);
+        // the reference's merge stops as soon as either list is exhausted (:1337-1352)
+        while (ia < automatic.size() && jf < filtered.size()) {
+            if (automatic[ia]->pos < filtered[jf].pos) res.merged.push_back(*automatic[ia++]);
+            else if (automatic[ia]->pos > filtered[jf].pos) res.merged.push_back(std::move(filtered[jf++]));
+            else { res.merged.push_back(*automatic[ia++]); jf++; }
+        }
+    }
+    hsgpu_pileup_destroy(pu);
+}
+
+int main(int argc, char* argv[]) {
+    if (argc < 12) {
+        std::cout << "Usage: ./call_variants <gfa_file> <reads_file> <sam_file> <num_threads> <tmpDir> <error_rate_out> "
+                     "<amplicon> <DEBUG> <file_out> <vcfFile> <automatic_snp_threshold>\n";
+        return 0;
+    }
+    const std::string gfa_file = argv[1], reads_file = argv[2], sam_file = argv[3];
+    const int num_threads = std::stoi(argv[4]);
+    const std::string error_rate_out = argv[6];
+    const bool amplicon = bool(std::stoi(argv[7]));
+    const std::string file_out = argv[9], vcf_file = argv[10];
+    const float auto_threshold = std::stof(argv[11]);
+    { std::ofstream out(file_out); }
+    {
+        std::ofstream vcf(vcf_file);
+        vcf << "##fileformat=VCFv4.2\n##source=call_variants\n"
+               "##INFO=<ID=DP,Number=1,Type=Integer,Description=\"Total Depth\">\n"
+               "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n";
+    }
+    Store st;
+    std::cout << " - Loading all reads from " << reads_file << " in memory\n";
+    parse_reads(reads_file, st);
+    std::cout << " - Loading all contigs from " << gfa_file << " in memory\n";
+    parse_assembly(gfa_file, st);
+    std::cout << " - Loading alignments of the reads on the contigs from " << sam_file << "\n";
+    if (sam_file.size() >= 4 && sam_file.substr(sam_file.size() - 4, 4) == ".paf") {
+        std::cout << "ERROR: please provide a .sam file as input for the alignments of the reads on the contigs." << std::endl;
+        std::exit(EXIT_FAILURE);
+    } else if (sam_file.size() >= 4 && sam_file.substr(sam_file.size() - 4, 4) == ".sam") {
+        parse_sam(sam_file, st, amplicon);
+    } else {
+        std::cout << "ERROR: the file containing the alignments on the assembly should be .sam" << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
+    std::cout << " - Calling variants on each contig\n";
+    omp_set_num_threads(std::max(1, num_threads));
+
+    // the contigs to process (the reference skips one hard-coded debugging name, :1282)
+    std::vector<int> todo;
+    for (int ci = 0; ci < (int)st.contigs.size(); ci++)
+        if (st.seqs[st.contigs[ci]].name != "edge_124@009") todo.push_back(ci);
+    // shard over GPUs: heaviest contig first onto the least loaded device, then cut each device's list
+    // into batches bounded by pileup cells
+    int n_gpus = 1;
+    if (const char* e = std::getenv("HSGPU_NGPUS")) n_gpus = std::max(1, std::atoi(e));
+    int first_device = 0;
+    if (const char* e = std::getenv("HSGPU_DEVICE")) first_device = std::atoi(e);
+    std::vector<double> weight(st.contigs.size(), 0.0);
+    for (int ci : todo) {
+        double w = (double)st.seqs[st.contigs[ci]].sequence.size();
+        for (int64_t id : st.seqs[st.contigs[ci]].alns) w += (double)(st.alns[id].pos_2_2 - st.alns[id].pos_2_1);
+        weight[ci] = w;
+    }
+    std::vector<int> by_weight(todo);
+    std::stable_sort(by_weight.begin(), by_weight.end(), [&](int a, int b) { return weight[a] > weight[b]; });
+    std::vector<std::vector<int>> shard(n_gpus);
+    std::vector<double> load(n_gpus, 0.0);
+    for (int ci : by_weight) {
+        const int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        shard[g].push_back(ci);
+        load[g] += weight[ci];
+    }
+    const double batch_cells = 3e9;
+    std::vector<ContigResult> results(st.contigs.size());
+    std::vector<std::string> errors(n_gpus);
+#pragma omp parallel for num_threads(n_gpus) schedule(static, 1)
+    for (int g = 0; g < n_gpus; g++) {
+        if (shard[g].empty()) continue;
+        hsgpu_ctx* ctx = nullptr;
+        if (hsgpu_ctx_create(first_device + g, &ctx) != HSGPU_OK) {
+            std::cout << "ERROR: no usable GPU " << first_device + g << ": " << hsgpu_last_error(nullptr) << std::endl;
+            std::exit(1);  // there is no CPU fallback
+        }
+        std::sort(shard[g].begin(), shard[g].end());
+        std::vector<int> batch;
+        double cells = 0;
+        for (size_t i = 0; i < shard[g].size(); i++) {
+            batch.push_back(shard[g][i]);
+            cells += weight[shard[g][i]];
+            if (cells >= batch_cells || i + 1 == shard[g].size()) {
+                process_batch(ctx, st, reads_file, batch, auto_threshold, results);
+                batch.clear();
+                cells = 0;
+            }
+        }
+        hsgpu_ctx_destroy(ctx);
+    }
+
+    // same accumulation order as the reference at one thread: contig by contig
+    float total_error_rate = 0;
+    int n_rated = 0;
+    std::unordered_map<int, std::vector<Column>> variants;
+    for (int ci : todo) {
+        if (results[ci].mean_distance > 0) {
+            total_error_rate += results[ci].mean_distance;
+            n_rated += 1;
+        }
+        st.seqs[st.contigs[ci]].depth = results[ci].depth;
+        variants[(int)st.contigs[ci]] = std::move(results[ci].merged);
+    }
+    std::ofstream error_file(error_rate_out);
+    std::cout << "total error rate : " << total_error_rate << " number of contigs : " << n_rated << std::endl;
+    error_file << total_error_rate / n_rated << std::endl;
+    error_file.close();
+    write_outputs(st, variants, file_out, vcf_file);
+    return 0;
+}

@@ -1,0 +1,77 @@
+// C entry points over the host logic, for the CPU test-suite (ctypes): the partition builder on flat
+// arrays and a dump of what the parsers keep. Not part of the product ABI (include/hsgpu.h).
+#include <fstream>
+
+#include "hs_io.h"
+#include "hs_partition.h"
+
+using namespace hs;
+
+struct PartSet {
+    std::vector<Partition> parts;
+};
+
+extern "C" {
+
+void* hshost_build_partitions(int n_cols, const int64_t* off, const uint32_t* read_idx, const uint8_t* code,
+                              const int32_t* pos, const uint8_t* ref_base, const uint8_t* second_base, float mean_error) {
+    std::vector<Column> cols(n_cols);
+    for (int i = 0; i < n_cols; i++) {
+        cols[i].pos = pos[i];
+        cols[i].ref_base = ref_base[i];
+        cols[i].second_base = second_base[i];
+        cols[i].readIdxs.assign(read_idx + off[i], read_idx + off[i + 1]);
+        cols[i].content.assign(code + off[i], code + off[i + 1]);
+    }
+    PartSet* ps = new PartSet();
+    build_partitions(cols, mean_error, ps->parts);
+    return ps;
+}
+int hshost_parts_count(void* h) { return (int)((PartSet*)h)->parts.size(); }
+int hshost_part_size(void* h, int p) { return (int)((PartSet*)h)->parts[p].readIdx.size(); }
+void hshost_part_get(void* h, int p, int32_t* read_idx, int16_t* state, int32_t* more, int32_t* less, int32_t* left_right) {
+    const Partition& pt = ((PartSet*)h)->parts[p];
+    for (size_t i = 0; i < pt.readIdx.size(); i++) {
+        read_idx[i] = pt.readIdx[i];
+        state[i] = pt.state[i];
+        more[i] = pt.more[i];
+        less[i] = pt.less[i];
+    }
+    left_right[0] = pt.pos_left;
+    left_right[1] = pt.pos_right;
+}
+void hshost_parts_free(void* h) { delete (PartSet*)h; }
+
+float hshost_chi_square(int n00, int n01, int n10, int n11) {
+    Distance d;
+    d.n00 = n00; d.n01 = n01; d.n10 = n10; d.n11 = n11;
+    return chi_square(d);
+}
+
+// CONTIG / READ lines exactly as output_files prints them (depth left out), one block per contig in GFA order
+int hshost_parse_dump(const char* gfa, const char* reads, const char* sam, int amplicon, const char* out_path) {
+    try {
+        Store st;
+        parse_reads(reads, st);
+        parse_assembly(gfa, st);
+        parse_sam(sam, st, amplicon != 0);
+        std::ofstream out(out_path);
+        std::ifstream rf(reads);
+        std::vector<std::string> seqs;
+        for (int64_t c : st.contigs) {
+            out << "CONTIG\t" << st.seqs[c].name << "\t" << st.seqs[c].sequence.size() << "\n";
+            load_read_sequences(rf, st, c, seqs);
+            size_t n = 0;
+            for (int64_t id : st.seqs[c].alns) {
+                const Alignment& a = st.alns[id];
+                out << "READ\t" << st.seqs[a.read].name << "\t" << a.pos_1_1 << "\t" << a.pos_1_2 << "\t" << a.pos_2_1 << "\t"
+                    << a.pos_2_2 << "\t" << a.strand << "\t" << seqs[n++].size() << "\n";
+            }
+        }
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+#include "hs_io.h"
+
+#include <cstdlib>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+
+namespace hs {
+
+using std::string;
+
+static string up_to_first_blank(const string& s) {
+    const size_t p = s.find(' ');
+    return p == string::npos ? s : s.substr(0, p);
+}
+
+// src/input_output.cpp:39-110. Records are delimited by header lines ('>' for *.fa / *.fasta, '@'
+// otherwise; a '@' line only opens a FASTQ record when the record in progress is complete or the
+// previous line was not the '+' separator). A record keeps its name (header up to the first blank), the
+// length of its FIRST sequence line and the file offset of that line; the sequence itself is read
+// back on demand.
+void parse_reads(const string& path, Store& st) {
+    char format = '@';
+    if ((path.size() > 6 && path.substr(path.size() - 6, 6) == ".fasta") || path.substr(path.size() - 3, 3) == ".fa")
+        format = '>';
+    std::ifstream in(path);
+    if (!in) {
+        std::cout << "problem reading files in index_reads, while trying to read " << path << std::endl;
+        throw std::invalid_argument("Input file could not be read");
+    }
+    std::vector<string> record;
+    string line;
+    int64_t record_start = 0, offset = 0;
+    char previous_first = '+';
+    auto flush = [&]() {
+        SeqRec r;
+        r.name = up_to_first_blank(record.at(0).substr(1));
+        r.length = (int64_t)record.at(1).size();
+        r.file_pos = record_start + (int64_t)record[0].size() + 1;
+        st.index[r.name] = (int64_t)st.seqs.size();
+        st.seqs.push_back(std::move(r));
+    };
+    while (std::getline(in, line)) {
+        const bool header = !line.empty() && line[0] == format && record.size() >= 2 &&
+                            (format == '>' || previous_first != '+' || record.size() == 4);
+        if (header) {
+            flush();
+            record_start = offset;
+            record.clear();
+        }
+        record.push_back(line);
+        if (!line.empty()) previous_first = line[0];
+        offset += 1 + (int64_t)line.size();
+    }
+    flush();
+}
+
+// src/input_output.cpp:120-263: S lines give contigs (name up to the first blank, sequence, optional
+// dp:/DP: depth tag); L lines must name known segments.
+void parse_assembly(const string& path, Store& st) {
+    std::ifstream in(path);
+    if (!in) {
+        std::cout << "problem reading files in index_reads, while trying to read " << path << std::endl;
+        throw std::invalid_argument("Input file could not be read");
+    }
+    string line;
+    while (std::getline(in, line)) {
+        if (line.empty()) continue;
+        if (line[0] == 'S') {
+            std::istringstream fields(line);
+            string field, name;
+            int k = 0;
+            while (std::getline(fields, field, '\t')) {
+                if (k == 1) {
+                    name = up_to_first_blank(field);
+                } else if (k == 2) {
+                    SeqRec r;
+                    r.name = name;
+                    r.length = (int64_t)field.size();
+                    r.sequence = field;
+                    st.index[name] = (int64_t)st.seqs.size();
+                    st.contigs.push_back((int64_t)st.seqs.size());
+                    st.seqs.push_back(std::move(r));
+                } else if (field.substr(0, 2) == "dp" || field.substr(0, 2) == "DP") {
+                    st.seqs[st.contigs.back()].depth = (float)std::atoi(field.substr(5, field.size() - 5).c_str());
+                }
+                k++;
+            }
+        } else if (line[0] == 'L') {
+            std::istringstream fields(line);
+            string field, n1, n2;
+            int k = 0;
+            bool ok = true;
+            while (std::getline(fields, field, '\t')) {
+                if (k == 1) n1 = field;
+                else if (k == 3) n2 = field;
+                else if (k == 2 || k == 4) {
+                    const string& nm = (k == 2) ? n1 : n2;
+                    if ((field != "+" && field != "-") || st.index.find(nm) == st.index.end()) ok = false;
+                }
+                k++;
+            }
+            if (!ok) {
+                std::cout << "Problem in reading the link : " << line << std::endl;
+                std::cout << "Problem while reading GFA file " + path +
+                                 ". Ensure that all the contigs described in 'L' lines are present in 'S' lines."
+                          << std::endl;
+                throw std::invalid_argument("Invalid GFA");
+            }
+        }
+    }
+}
+
+void cigar_ops(const string& cigar, std::vector<uint32_t>& ops) {
+    ops.clear();
+    if (cigar == "*") return;
+    static const string letters = "MIDNSHP=X";
+    string num;
+    for (char c : cigar) {
+        if (c >= '0' && c <= '9') {
+            num += c;
+            continue;
+        }
+        int n = 0;
+        try {
+            n = std::stoi(num);
+        } catch (...) {
+            std::cout << "ERROR : could not convert " << cigar << " to int" << std::endl;
+            std::exit(1);
+        }
+        size_t op = letters.find(c);
+        if (op == string::npos) op = 6;  // a letter no loop of the reference looks at behaves like padding
+        if (n > 0) ops.push_back(((uint32_t)n << 4) | (uint32_t)op);
+        num.clear();
+    }
+}
+
+// length of the run of `letter` ops at the start / end of the CIGAR, the way parse_SAM measures clips
+// (src/input_output.cpp:387-470): only the first op counts at the start; at the end everything behind
+// the last letter that is not `letter` is taken as one number.
+static int clip_at_start(const string& cigar, char letter) {
+    string digits;
+    for (size_t i = 0; i < cigar.size(); i++) {
+        if (cigar[i] > '9' || cigar[i] < '0') {
+            if (cigar[i] != letter) digits.clear();
+            break;
+        }
+        digits += cigar[i];
+    }
+    return digits.empty() ? 0 : std::stoi(digits);
+}
+static int clip_at_end(const string& cigar, char letter) {
+    string tail;
+    for (int i = (int)cigar.size() - 1; i >= 0; i--) {
+        if ((cigar[i] > '9' || cigar[i] < '0') && cigar[i] != letter) break;
+        tail = cigar[i] + tail;
+    }
+    if (tail.empty()) return 0;
+    tail = tail.substr(0, tail.size() - 1);
+    return std::stoi(tail);
+}
+
+// src/input_output.cpp:274-536
+void parse_sam(const string& path, Store& st, bool amplicon) {
+    std::ifstream in(path);
+    if (!in) {
+        std::cout << "problem reading SAM file " << path << std::endl;
+        throw std::invalid_argument("Input file '" + path + "' could not be read");
+    }
+    string line;
+    std::vector<uint32_t> ops;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line[0] == '@') continue;
+        std::istringstream fields(line);
+        string field, cigar;
+        int64_t read = -1, contig = -2;
+        int read_length = 0, pos = -1, flag = 0, nonmatching = 0, k = 0;
+        bool forward = true, good = true;
+        while (std::getline(fields, field, '\t')) {
+            if (k == 0) {
+                if (st.index.find(field) == st.index.end()) {
+                    std::cout << "WARNING: read in the sam file not found in reads file, ignoring: " << field << std::endl;
+                    good = false;
+                }
+                read = st.index[field];  // like the reference's map access this registers the name (index 0)
+            } else if (k == 1) {
+                flag = std::stoi(field);
+                if (flag % 8 >= 4) good = false;
+                if (flag % 32 >= 16) forward = false;
+            } else if (k == 2) {
+                contig = st.index[field];
+            } else if (k == 3) {
+                pos = std::stoi(field);
+            } else if (k == 5) {
+                cigar = field;
+            } else if (field.substr(0, 5) == "LN:i:") {
+                read_length = std::stoi(field.substr(5, field.size() - 5));
+            } else if (field.substr(0, 5) == "NM:i:") {
+                nonmatching = std::stoi(field.substr(5, field.size() - 5));
+            }
+            k++;
+        }
+        if (!(good && k > 10 && contig != read)) continue;
+        cigar_ops(cigar, ops);
+        int h_start = clip_at_start(cigar, 'H'), h_end = clip_at_end(cigar, 'H');
+        if (!forward) std::swap(h_start, h_end);
+        int s_start = clip_at_start(cigar, 'S'), s_end = clip_at_end(cigar, 'S');
+        if (!forward) std::swap(s_start, s_end);
+        if (h_start + h_end > 0.2 * read_length && flag < 2048) good = false;
+        else if (flag % 512 >= 256) good = false;
+        if (amplicon && nonmatching > 0.2 * read_length) good = false;
+        if (!good) continue;
+        int on_read = 0, on_contig = 0;
+        for (uint32_t op : ops) {
+            const int n = (int)(op >> 4), ty = (int)(op & 15);
+            if (ty == 0 || ty == 7 || ty == 8) { on_read += n; on_contig += n; }
+            else if (ty == 1) on_read += n;
+            else if (ty == 2) on_contig += n;
+        }
+        Alignment a;
+        a.read = read;
+        a.contig = contig;
+        a.pos_1_1 = s_start + h_start;
+        a.pos_1_2 = s_start + h_start + on_read;
+        a.pos_2_1 = pos - 1;
+        a.pos_2_2 = pos + on_contig;
+        a.strand = forward;
+        a.cigar = cigar;
+        const int64_t id = (int64_t)st.alns.size();
+        st.seqs[read].alns.push_back(id);
+        st.seqs[contig].alns.push_back(id);
+        st.alns.push_back(std::move(a));
+    }
+}
+
+void load_read_sequences(std::ifstream& reads_file, const Store& st, int64_t contig, std::vector<string>& out) {
+    out.clear();
+    string line;
+    for (int64_t id : st.seqs[contig].alns) {
+        const Alignment& a = st.alns[id];
+        const int64_t read = (a.read != contig) ? a.read : a.contig;
+        reads_file.clear();
+        reads_file.seekg(st.seqs[read].file_pos);
+        std::getline(reads_file, line);
+        out.push_back(line);
+    }
+}
+
+// src/call_variants.cpp:1174-1213. Alleles are written as decimal integers, lists end with a comma, every
+// contig block ends with an empty line; the .vcf is reopened, which drops the header written earlier.
+void write_outputs(const Store& st, const std::unordered_map<int, std::vector<Column>>& variants,
+                   const string& col_file, const string& vcf_file) {
+    std::ofstream out(col_file);
+    std::ofstream vcf(vcf_file);
+    string idxs, bases;
+    for (const auto& kv : variants) {
+        const SeqRec& contig = st.seqs[kv.first];
+        out << "CONTIG\t" << contig.name << "\t" << contig.sequence.size() << "\t" << contig.depth << "\n";
+        for (int64_t id : contig.alns) {
+            const Alignment& a = st.alns[id];
+            out << "READ\t" << st.seqs[a.read].name << "\t" << a.pos_1_1 << "\t" << a.pos_1_2 << "\t" << a.pos_2_1 << "\t"
+                << a.pos_2_2 << "\t" << a.strand << "\n";
+        }
+        for (const Column& c : kv.second) {
+            out << "SNPS\t" << c.pos << "\t" << (int)c.ref_base << "\t" << (int)c.second_base << "\t";
+            idxs.clear();
+            bases.clear();
+            for (size_t r = 0; r < c.readIdxs.size(); r++) {
+                idxs += std::to_string(c.readIdxs[r]);
+                idxs += ',';
+                bases += std::to_string((int)c.content[r]);
+                bases += ',';
+            }
+            out << idxs << "\t" << bases << "\n";
+            vcf << contig.name << "\t" << c.pos << "\t.\t" << "ACGT-"[(c.ref_base - '!') % 5] << "\t"
+                << "ACGT-"[(c.second_base - '!') % 5] << "\t.\t.\tDP=" << c.readIdxs.size() << "\n";
+        }
+        out << std::endl;
+        vcf << std::endl;
+    }
+}
+
+}  // namespace hs

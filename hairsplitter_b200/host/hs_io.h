@@ -1,0 +1,26 @@
+// Parsers and writers of the HS_call_variants drop-in. Same observable behaviour as the reference's
+// parse_reads / parse_assembly / parse_SAM / parse_reads_on_contig (src/input_output.cpp:39-569) and
+// output_files (src/call_variants.cpp:1174-1213), restated over the flat Store.
+#pragma once
+#include <fstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "hs_types.h"
+
+namespace hs {
+
+void parse_reads(const std::string& path, Store& st);
+void parse_assembly(const std::string& path, Store& st);
+void parse_sam(const std::string& path, Store& st, bool amplicon);
+// SAM CIGAR string -> BAM ops (len<<4 | index in "MIDNSHP=X"); "*" gives no ops. Exits like
+// convert_cigar (src/tools.cpp:27-57) when a length is missing.
+void cigar_ops(const std::string& cigar, std::vector<uint32_t>& ops);
+// the sequence lines of the reads aligned on `contig`, in neighbour order (parse_reads_on_contig)
+void load_read_sequences(std::ifstream& reads_file, const Store& st, int64_t contig, std::vector<std::string>& out);
+// .col and .vcf, contigs in the iteration order of the reference's own container
+void write_outputs(const Store& st, const std::unordered_map<int, std::vector<Column>>& variants,
+                   const std::string& col_file, const std::string& vcf_file);
+
+}  // namespace hs

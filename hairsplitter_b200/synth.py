@@ -252,9 +252,10 @@ def make_config(config: int, scale: float = 1.0, seed: int | None = None, n_chun
     return chunks, info
 
 
-def write_files(chunks, prefix: str):
-    """GFA + FASTA + SAM in the form the reference executables read (LN:i / NM:i tags appended)."""
-    with open(prefix + ".gfa", "w") as gfa, open(prefix + ".fasta", "w") as fa, open(prefix + ".sam", "w") as sam:
+def write_files(chunks, prefix: str, fastq: bool = False):
+    """GFA + FASTA (or FASTQ) + SAM in the form the reference executables read (LN:i / NM:i tags appended)."""
+    ext = ".fastq" if fastq else ".fasta"
+    with open(prefix + ".gfa", "w") as gfa, open(prefix + ext, "w") as fa, open(prefix + ".sam", "w") as sam:
         for c in chunks:
             gfa.write(f"S\t{c.name}\t{c.contig_str()}\n")
             sam.write(f"@SQ\tSN:{c.name}\tLN:{c.length}\n")
@@ -262,10 +263,14 @@ def write_files(chunks, prefix: str):
             rl = c.read_len()
             for i in range(c.n_reads):
                 rname = f"{c.name}_r{i}"
-                fa.write(f">{rname}\n{c.read_str(i)}\n")
+                if fastq:  # quality lines that start with '@' exercise the record detection of parse_reads
+                    seq = c.read_str(i)
+                    fa.write(f"@{rname} some comment\n{seq}\n+\n{'@' if i % 3 == 0 else 'I'}{'I' * (len(seq) - 1)}\n")
+                else:
+                    fa.write(f">{rname}\n{c.read_str(i)}\n")
                 flag = 0 if c.strand[i] else 16
                 sam.write(
                     f"{rname}\t{flag}\t{c.name}\t{int(c.start[i]) + 1}\t60\t{c.cigar_str(i)}\t*\t0\t0\t*\t*\t"
                     f"NM:i:0\tLN:i:{int(rl[i])}\n"
                 )
-    return prefix + ".gfa", prefix + ".fasta", prefix + ".sam"
+    return prefix + ".gfa", prefix + ext, prefix + ".sam"

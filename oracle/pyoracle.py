@@ -264,6 +264,10 @@ class RefCV:
     _lib = None
 
     @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(HERE, "_ref", "libhsref_cv.so"))
+
+    @classmethod
     def lib(cls):
         if cls._lib is None:
             L = C.CDLL(os.path.join(HERE, "_ref", "libhsref_cv.so"))

@@ -1,0 +1,56 @@
+"""End-to-end drop-in test: our HS_call_variants (host C++ over libhsgpu, hairsplitter_b200/bin) against the
+reference executable compiled from /root/reference (oracle/_ref/HS_call_variants) on the same GFA + reads
++ SAM. The .col, .vcf and error-rate files must be byte-identical (reference run with one thread, whose
+contig order ours reproduces)."""
+import filecmp
+import os
+import subprocess
+
+import pytest
+
+import cases
+from hairsplitter_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "hairsplitter_b200", "bin", "HS_call_variants")
+REF = os.path.join(ROOT, "oracle", "_ref", "HS_call_variants")
+
+
+def _run(exe, files, tmp, tag, threads=1, amplicon=0, thr="0.33"):
+    gfa, reads, sam = files
+    col, vcf, err = [os.path.join(tmp, f"{tag}.{e}") for e in ("col", "vcf", "err")]
+    subprocess.run([exe, gfa, reads, sam, str(threads), tmp, err, str(amplicon), "0", col, vcf, thr], check=True,
+                   stdout=subprocess.DEVNULL)
+    return col, vcf, err
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", ["ont_multi", "hifi_fastq", "edges"])
+def test_col_vcf_error_rate_identical_to_reference(tmp_path, case):
+    assert os.path.exists(OURS), "build hairsplitter_b200/host first (python -c 'import __graft_entry__ as g; g.build()')"
+    if case == "ont_multi":
+        chunks = [cases.small_case(seed=91, length=20000, depth=50, mean_len=5000, error=0.06), cases.medium_case(),
+                  cases.small_case(seed=5, length=3000, depth=12, mean_len=900, hard=0.4)]
+        fastq = False
+    elif case == "hifi_fastq":
+        chunks = [cases.hifi_case(), cases.small_case(seed=12, eqx=True)]
+        fastq = True
+    else:
+        chunks = cases.ragged_cases() + [cases.deep_case()]
+        fastq = False
+    for i, c in enumerate(chunks):
+        c.name = f"ctg{i}"
+    files = synth.write_files(chunks, os.path.join(str(tmp_path), "in"), fastq=fastq)
+    ref = _run(REF, files, str(tmp_path), "ref")
+    ours = _run(OURS, files, str(tmp_path), "ours", threads=4)
+    for a, b in zip(ref, ours):
+        assert filecmp.cmp(a, b, shallow=False), (a, b)
+    assert os.path.getsize(ref[0]) > 1000
+
+
+def test_usage_and_version_probe_return_zero():
+    """hairsplitter.py's dependency check runs the executable with --version and expects status 0 (:229-239)"""
+    r = subprocess.run([OURS, "--version"], stdout=subprocess.PIPE)
+    assert r.returncode == 0 and b"Usage" in r.stdout
