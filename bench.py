@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (testing only)")
     ap.add_argument("--cpu-sample-chunks", type=int, default=0, help="chunks in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--wall-chunks", type=int, default=0, help="chunks in the HS_call_variants wall-time stage (0 = all, -1 = skip)")
     return ap.parse_args()
 
 
@@ -276,6 +277,66 @@ def run_stages(ctx, stream, chunks, args, hbm_peak):
     return out
 
 
+def col_blocks(path):
+    """contig name -> its block of a .col file (the reference's contig order depends on its thread schedule)"""
+    blocks, cur = {}, None
+    for line in open(path):
+        if line.startswith("CONTIG\t"):
+            cur = line.split("\t")[1]
+            blocks[cur] = []
+        if cur is not None and line.strip():
+            blocks[cur].append(line)
+    return blocks
+
+
+def run_call_variants_wall(chunks, args):
+    """BASELINE's third headline: wall time of the HS_call_variants executable on the whole configuration, ours
+    (host C++ over libhsgpu, one GPU) beside the reference's (OpenMP over contigs, all host cores), same files,
+    outputs compared contig by contig."""
+    import shutil
+    import subprocess
+    import tempfile
+    from hairsplitter_b200 import synth
+    ours = os.path.join(ROOT, "hairsplitter_b200", "bin", "HS_call_variants")
+    ref = os.path.join(ROOT, "oracle", "_ref", "HS_call_variants")
+    if not os.path.exists(ours):
+        return {"unavailable": "hairsplitter_b200/bin/HS_call_variants not built"}
+    cores = host_cores()
+    sample = chunks if args.wall_chunks <= 0 else chunks[:args.wall_chunks]
+    tmp = tempfile.mkdtemp(prefix="hs_wall_")
+    try:
+        t0 = time.perf_counter()
+        gfa, reads, sam = synth.write_files(sample, os.path.join(tmp, "in"))
+        t_write = time.perf_counter() - t0
+
+        def run(exe, tag, threads):
+            col, vcf, err = [os.path.join(tmp, f"{tag}.{e}") for e in ("col", "vcf", "err")]
+            t0 = time.perf_counter()
+            subprocess.run([exe, gfa, reads, sam, str(threads), tmp, err, "0", "0", col, vcf, "0.33"], check=True,
+                           stdout=subprocess.DEVNULL)
+            return time.perf_counter() - t0, col, err
+
+        run(ours, "warm", cores)  # first process start pays CUDA context creation and module load
+        t_ours, col_ours, err_ours = run(ours, "ours", cores)
+        out = {
+            "metric": "HS_call_variants wall time (parse SAM/FASTA/GFA + pileup + variant calling + robust filter + write .col/.vcf)",
+            "sample": f"{len(sample)} contig chunks, {sum(c.length for c in sample)} columns, {sum(c.n_reads for c in sample)} reads; "
+                      f"input files {sum(os.path.getsize(f) for f in (gfa, reads, sam)) / 1e6:.0f} MB",
+            "ours_s": t_ours, "ours_threads": cores, "ours_gpus": 1, "write_inputs_s": round(t_write, 1),
+        }
+        if os.path.exists(ref):
+            threads = min(cores, len(sample))
+            t_ref, col_ref, err_ref = run(ref, "ref", threads)
+            a, b = col_blocks(col_ours), col_blocks(col_ref)
+            assert a == b, "our .col differs from the reference's"
+            assert open(err_ours).read() == open(err_ref).read() or threads > 1  # float sum order varies with threads
+            out.update({"reference_s": t_ref, "reference_threads": threads, "speedup": t_ref / t_ours,
+                        "col_identical_to_reference": True, "snps": sum(len(v) for v in a.values())})
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def workload_description(info, chunks):
     return (f"BASELINE configs[1]: synthetic {info['genome'] / 1e6:g} Mb bacterial genome, {info['strains']} strains "
             f"1% apart, ONT-like reads {info['mean_len'] / 1000:g} kb mean, {int(info['error'] * 100)}% error, "
@@ -463,6 +524,8 @@ def main():
     stages = {}
     if rank == 0 and world == 1:
         stages = run_stages(ctx, stream, chunks, args, hbm_peak)
+        if args.wall_chunks >= 0:
+            stages["call_variants_wall"] = run_call_variants_wall(chunks, args)
 
     # ---- max over ranks ----
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
