@@ -11,6 +11,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <future>
 #include <numeric>
 #include <string>
 #include <unordered_map>
@@ -21,6 +22,16 @@
 #include "hs_partition.h"
 
 using namespace hs;
+
+// HS_TIMING=1 prints the wall time of every phase on stderr
+static double g_t0 = 0;
+static bool g_timing = false;
+static void phase(const char* name) {
+    if (!g_timing) return;
+    const double t = omp_get_wtime();
+    if (g_t0 > 0) fprintf(stderr, "[hs timing] %-28s %8.3f s\n", name, t - g_t0);
+    g_t0 = t;
+}
 
 #define GPU_CHECK(ctx, call)                                                                        \
     do {                                                                                            \
@@ -64,35 +75,54 @@ static void fetch_columns(hsgpu_ctx* ctx, hsgpu_pileup* pu, int c, const std::ve
 static void process_batch(hsgpu_ctx* ctx, const Store& st, const std::string& reads_path, const std::vector<int>& batch,
                           float auto_threshold, std::vector<ContigResult>& results) {
     const int nc = (int)batch.size();
-    std::ifstream reads_file(reads_path);
     std::vector<int32_t> contig_len(nc), read_len, read_start;
     std::vector<int64_t> contig_word_off(nc + 1, 0), contig_read_off(nc + 1, 0), read_word_off(1, 0), cigar_off(1, 0);
-    std::vector<uint32_t> contig_bases, read_bases, cigar, ops;
+    std::vector<uint32_t> contig_bases, read_bases, cigar;
     std::vector<uint8_t> read_strand;
-    std::vector<std::string> seqs;
-    for (int b = 0; b < nc; b++) {
-        const SeqRec& contig = st.seqs[st.contigs[batch[b]]];
-        contig_len[b] = (int32_t)contig.sequence.size();
-        const int64_t w = ((int64_t)contig.sequence.size() + 15) / 16;
-        contig_bases.resize((size_t)(contig_word_off[b] + w));
-        hsgpu_pack_bases_ascii(contig.sequence.data(), (int64_t)contig.sequence.size(), contig_bases.data() + contig_word_off[b]);
-        contig_word_off[b + 1] = contig_word_off[b] + w;
-        load_read_sequences(reads_file, st, st.contigs[batch[b]], seqs);
-        for (size_t n = 0; n < contig.alns.size(); n++) {
-            const Alignment& a = st.alns[contig.alns[n]];
-            const std::string& s = seqs[n];
-            const int64_t rw = ((int64_t)s.size() + 15) / 16;
-            read_bases.resize((size_t)(read_word_off.back() + rw));
-            hsgpu_pack_bases_ascii(s.data(), (int64_t)s.size(), read_bases.data() + read_word_off.back());
-            read_word_off.push_back(read_word_off.back() + rw);
-            read_len.push_back((int32_t)s.size());
-            cigar_ops(a.cigar, ops);
-            cigar.insert(cigar.end(), ops.begin(), ops.end());
-            cigar_off.push_back((int64_t)cigar.size());
-            read_start.push_back(a.pos_2_1);
-            read_strand.push_back(a.strand ? 1 : 0);
+    {
+        // the reads of every contig: sequence lines and CIGAR ops, contigs in parallel (each thread its own
+        // file handle), then one pass for the offsets, then the 2-bit packing in parallel again
+        std::vector<std::vector<std::string>> seqs(nc);
+        std::vector<std::vector<std::vector<uint32_t>>> ops(nc);
+#pragma omp parallel
+        {
+            std::ifstream reads_file(reads_path);
+#pragma omp for schedule(dynamic, 1)
+            for (int b = 0; b < nc; b++) {
+                const SeqRec& contig = st.seqs[st.contigs[batch[b]]];
+                load_read_sequences(reads_file, st, st.contigs[batch[b]], seqs[b]);
+                ops[b].resize(contig.alns.size());
+                for (size_t n = 0; n < contig.alns.size(); n++) cigar_ops(st.alns[contig.alns[n]].cigar, ops[b][n]);
+            }
         }
-        contig_read_off[b + 1] = (int64_t)read_len.size();
+        std::vector<int64_t> first_read(nc + 1, 0);
+        for (int b = 0; b < nc; b++) {
+            const SeqRec& contig = st.seqs[st.contigs[batch[b]]];
+            contig_len[b] = (int32_t)contig.sequence.size();
+            contig_word_off[b + 1] = contig_word_off[b] + ((int64_t)contig.sequence.size() + 15) / 16;
+            for (size_t n = 0; n < contig.alns.size(); n++) {
+                const Alignment& a = st.alns[contig.alns[n]];
+                read_word_off.push_back(read_word_off.back() + ((int64_t)seqs[b][n].size() + 15) / 16);
+                read_len.push_back((int32_t)seqs[b][n].size());
+                cigar_off.push_back(cigar_off.back() + (int64_t)ops[b][n].size());
+                read_start.push_back(a.pos_2_1);
+                read_strand.push_back(a.strand ? 1 : 0);
+            }
+            contig_read_off[b + 1] = (int64_t)read_len.size();
+        }
+        contig_bases.resize((size_t)contig_word_off[nc]);
+        read_bases.resize((size_t)read_word_off.back());
+        cigar.resize((size_t)cigar_off.back());
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int b = 0; b < nc; b++) {
+            const SeqRec& contig = st.seqs[st.contigs[batch[b]]];
+            hsgpu_pack_bases_ascii(contig.sequence.data(), (int64_t)contig.sequence.size(), contig_bases.data() + contig_word_off[b]);
+            for (size_t n = 0; n < contig.alns.size(); n++) {
+                const int64_t r = contig_read_off[b] + (int64_t)n;
+                hsgpu_pack_bases_ascii(seqs[b][n].data(), (int64_t)seqs[b][n].size(), read_bases.data() + read_word_off[r]);
+                std::copy(ops[b][n].begin(), ops[b][n].end(), cigar.begin() + cigar_off[r]);
+            }
+        }
     }
     if (contig_bases.empty()) contig_bases.push_back(0);
     if (read_bases.empty()) read_bases.push_back(0);
@@ -112,6 +142,7 @@ static void process_batch(hsgpu_ctx* ctx, const Store& st, const std::string& re
     in.cigar_off = cigar_off.data();
     in.read_start = read_start.data();
     in.read_strand = read_strand.data();
+    phase("  load+pack reads");
     hsgpu_pileup* pu = nullptr;
     GPU_CHECK(ctx, hsgpu_pileup_create(ctx, &in, &pu));
     GPU_CHECK(ctx, hsgpu_pileup_build(pu));                            // generate_msa
@@ -121,6 +152,7 @@ static void process_batch(hsgpu_ctx* ctx, const Store& st, const std::string& re
     GPU_CHECK(ctx, hsgpu_pileup_stats(pu, cells.data(), dist.data(), alen.data()));
     GPU_CHECK(ctx, hsgpu_column_counts(pu, n_suspects.data(), depth_sum.data()));
 
+    phase("  gpu pileup+rank");
     // phase A: suspect columns of every contig (device -> host)
     std::vector<std::vector<Column>> suspects(nc);
     std::vector<std::vector<uint8_t>> is_auto(nc), k0(nc), k1(nc);
@@ -137,12 +169,14 @@ static void process_batch(hsgpu_ctx* ctx, const Store& st, const std::string& re
         is_auto[b].resize(n_suspects[b]);
         fetch_columns(ctx, pu, b, suspect_pos[b], k0[b], k1[b], suspects[b]);
     }
+    phase("  fetch suspect columns");
     // phase B: partitions (loops 1+2 of keep_only_robust_variants), contigs in parallel on the host
     std::vector<std::vector<Partition>> parts(nc);
     std::vector<float> mean_distance(nc);
     for (int b = 0; b < nc; b++) mean_distance[b] = hsgpu_mean_distance(dist[b], alen[b]);
 #pragma omp parallel for schedule(dynamic, 1)
     for (int b = 0; b < nc; b++) build_partitions(suspects[b], mean_distance[b], parts[b]);
+    phase("  build partitions");
     // phase C: loops 3+4 on the device, then the merge with the automatic SNPs (main(), :1334-1352)
     for (int b = 0; b < nc; b++) {
         ContigResult& res = results[batch[b]];
@@ -184,6 +218,7 @@ static void process_batch(hsgpu_ctx* ctx, const Store& st, const std::string& re
             else { res.merged.push_back(*automatic[ia++]); jf++; }
         }
     }
+    phase("  robust filter + fetch");
     hsgpu_pileup_destroy(pu);
 }
 
@@ -206,11 +241,29 @@ int main(int argc, char* argv[]) {
                "##INFO=<ID=DP,Number=1,Type=Integer,Description=\"Total Depth\">\n"
                "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n";
     }
+    omp_set_num_threads(std::max(1, num_threads));
+    omp_set_max_active_levels(2);
+    g_timing = std::getenv("HS_TIMING") != nullptr;
+    phase("start");
+    // CUDA context creation and module load take about a second: start them now, parse meanwhile
+    int n_gpus = 1;
+    if (const char* e = std::getenv("HSGPU_NGPUS")) n_gpus = std::max(1, std::atoi(e));
+    int first_device = 0;
+    if (const char* e = std::getenv("HSGPU_DEVICE")) first_device = std::atoi(e);
+    std::vector<std::future<hsgpu_ctx*>> contexts;
+    for (int g = 0; g < n_gpus; g++)
+        contexts.push_back(std::async(std::launch::async, [=]() {
+            hsgpu_ctx* ctx = nullptr;
+            if (hsgpu_ctx_create(first_device + g, &ctx) != HSGPU_OK) return (hsgpu_ctx*)nullptr;
+            return ctx;
+        }));
     Store st;
     std::cout << " - Loading all reads from " << reads_file << " in memory\n";
     parse_reads(reads_file, st);
+    phase("parse_reads");
     std::cout << " - Loading all contigs from " << gfa_file << " in memory\n";
     parse_assembly(gfa_file, st);
+    phase("parse_assembly");
     std::cout << " - Loading alignments of the reads on the contigs from " << sam_file << "\n";
     if (sam_file.size() >= 4 && sam_file.substr(sam_file.size() - 4, 4) == ".paf") {
         std::cout << "ERROR: please provide a .sam file as input for the alignments of the reads on the contigs." << std::endl;
@@ -221,8 +274,8 @@ int main(int argc, char* argv[]) {
         std::cout << "ERROR: the file containing the alignments on the assembly should be .sam" << std::endl;
         std::exit(EXIT_FAILURE);
     }
+    phase("parse_sam");
     std::cout << " - Calling variants on each contig\n";
-    omp_set_num_threads(std::max(1, num_threads));
 
     // the contigs to process (the reference skips one hard-coded debugging name, :1282)
     std::vector<int> todo;
@@ -230,10 +283,6 @@ int main(int argc, char* argv[]) {
         if (st.seqs[st.contigs[ci]].name != "edge_124@009") todo.push_back(ci);
     // shard over GPUs: heaviest contig first onto the least loaded device, then cut each device's list
     // into batches bounded by pileup cells
-    int n_gpus = 1;
-    if (const char* e = std::getenv("HSGPU_NGPUS")) n_gpus = std::max(1, std::atoi(e));
-    int first_device = 0;
-    if (const char* e = std::getenv("HSGPU_DEVICE")) first_device = std::atoi(e);
     std::vector<double> weight(st.contigs.size(), 0.0);
     for (int ci : todo) {
         double w = (double)st.seqs[st.contigs[ci]].sequence.size();
@@ -254,12 +303,18 @@ int main(int argc, char* argv[]) {
     std::vector<std::string> errors(n_gpus);
 #pragma omp parallel for num_threads(n_gpus) schedule(static, 1)
     for (int g = 0; g < n_gpus; g++) {
-        if (shard[g].empty()) continue;
-        hsgpu_ctx* ctx = nullptr;
-        if (hsgpu_ctx_create(first_device + g, &ctx) != HSGPU_OK) {
+        phase("shard setup");
+        omp_set_num_threads(std::max(1, num_threads / n_gpus));  // host threads of this shard's inner loops
+        hsgpu_ctx* ctx = contexts[g].get();
+        if (!ctx) {
             std::cout << "ERROR: no usable GPU " << first_device + g << ": " << hsgpu_last_error(nullptr) << std::endl;
             std::exit(1);  // there is no CPU fallback
         }
+        if (shard[g].empty()) {
+            hsgpu_ctx_destroy(ctx);
+            continue;
+        }
+        phase("  ctx create");
         std::sort(shard[g].begin(), shard[g].end());
         std::vector<int> batch;
         double cells = 0;
@@ -275,6 +330,7 @@ int main(int argc, char* argv[]) {
         hsgpu_ctx_destroy(ctx);
     }
 
+    phase("gpu shards total");
     // same accumulation order as the reference at one thread: contig by contig
     float total_error_rate = 0;
     int n_rated = 0;
@@ -292,5 +348,6 @@ int main(int argc, char* argv[]) {
     error_file << total_error_rate / n_rated << std::endl;
     error_file.close();
     write_outputs(st, variants, file_out, vcf_file);
+    phase("write_outputs");
     return 0;
 }

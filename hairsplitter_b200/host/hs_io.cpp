@@ -1,7 +1,9 @@
 #include "hs_io.h"
 
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
+#include <iterator>
 #include <sstream>
 #include <stdexcept>
 
@@ -160,72 +162,130 @@ static int clip_at_end(const string& cigar, char letter) {
     return std::stoi(tail);
 }
 
-// src/input_output.cpp:274-536
+// src/input_output.cpp:274-536. Everything that depends on one line only (field splitting, flag tests, clip
+// lengths, aligned lengths) is done for all lines in parallel; the name lookups that can CHANGE the index
+// (the reference's map access registers unknown names with index 0, so a second record of an unknown read
+// lands on read 0) and the bookkeeping are replayed in file order afterwards.
+namespace {
+struct SamRecord {
+    std::string read_name, contig_name, cigar;
+    int64_t read = -1, contig = -1;  // -1: name not in the index when the line was parsed
+    int pos_1_1 = 0, pos_1_2 = 0, pos_2_1 = 0, pos_2_2 = 0;
+    bool forward = true, good = true, enough_fields = false;
+    int n_fields = 0;
+};
+
+void parse_sam_line(const char* p, const char* end, const Store& st, bool amplicon, SamRecord& rec) {
+    std::string field, cigar;
+    std::vector<uint32_t> ops;
+    int read_length = 0, pos = -1, flag = 0, nonmatching = 0, k = 0;
+    while (p <= end) {  // std::getline semantics: a trailing tab does not open an empty last field
+        const char* q = (const char*)memchr(p, '\t', (size_t)(end - p));
+        if (!q) q = end;
+        if (q == end && p == end) break;
+        field.assign(p, q);
+        if (k == 0) {
+            rec.read_name = field;
+            auto it = st.index.find(field);
+            if (it != st.index.end()) rec.read = it->second;
+        } else if (k == 1) {
+            flag = std::stoi(field);
+            if (flag % 8 >= 4) rec.good = false;
+            if (flag % 32 >= 16) rec.forward = false;
+        } else if (k == 2) {
+            rec.contig_name = field;
+            auto it = st.index.find(field);
+            if (it != st.index.end()) rec.contig = it->second;
+        } else if (k == 3) {
+            pos = std::stoi(field);
+        } else if (k == 5) {
+            cigar = field;
+        } else if (field.compare(0, 5, "LN:i:") == 0) {
+            read_length = std::stoi(field.substr(5, field.size() - 5));
+        } else if (field.compare(0, 5, "NM:i:") == 0) {
+            nonmatching = std::stoi(field.substr(5, field.size() - 5));
+        }
+        k++;
+        p = q + 1;
+    }
+    rec.enough_fields = k > 10;
+    rec.n_fields = k;
+    if (!rec.good || !rec.enough_fields) return;
+    cigar_ops(cigar, ops);
+    int h_start = clip_at_start(cigar, 'H'), h_end = clip_at_end(cigar, 'H');
+    if (!rec.forward) std::swap(h_start, h_end);
+    int s_start = clip_at_start(cigar, 'S'), s_end = clip_at_end(cigar, 'S');
+    if (!rec.forward) std::swap(s_start, s_end);
+    if (h_start + h_end > 0.2 * read_length && flag < 2048) rec.good = false;
+    else if (flag % 512 >= 256) rec.good = false;
+    if (amplicon && nonmatching > 0.2 * read_length) rec.good = false;
+    if (!rec.good) return;
+    int on_read = 0, on_contig = 0;
+    for (uint32_t op : ops) {
+        const int n = (int)(op >> 4), ty = (int)(op & 15);
+        if (ty == 0 || ty == 7 || ty == 8) { on_read += n; on_contig += n; }
+        else if (ty == 1) on_read += n;
+        else if (ty == 2) on_contig += n;
+    }
+    rec.pos_1_1 = s_start + h_start;
+    rec.pos_1_2 = s_start + h_start + on_read;
+    rec.pos_2_1 = pos - 1;
+    rec.pos_2_2 = pos + on_contig;
+    rec.cigar.swap(cigar);
+}
+}  // namespace
+
 void parse_sam(const string& path, Store& st, bool amplicon) {
-    std::ifstream in(path);
+    std::ifstream in(path, std::ios::binary);
     if (!in) {
         std::cout << "problem reading SAM file " << path << std::endl;
         throw std::invalid_argument("Input file '" + path + "' could not be read");
     }
-    string line;
-    std::vector<uint32_t> ops;
-    while (std::getline(in, line)) {
-        if (!line.empty() && line[0] == '@') continue;
-        std::istringstream fields(line);
-        string field, cigar;
-        int64_t read = -1, contig = -2;
-        int read_length = 0, pos = -1, flag = 0, nonmatching = 0, k = 0;
-        bool forward = true, good = true;
-        while (std::getline(fields, field, '\t')) {
-            if (k == 0) {
-                if (st.index.find(field) == st.index.end()) {
-                    std::cout << "WARNING: read in the sam file not found in reads file, ignoring: " << field << std::endl;
-                    good = false;
-                }
-                read = st.index[field];  // like the reference's map access this registers the name (index 0)
-            } else if (k == 1) {
-                flag = std::stoi(field);
-                if (flag % 8 >= 4) good = false;
-                if (flag % 32 >= 16) forward = false;
-            } else if (k == 2) {
-                contig = st.index[field];
-            } else if (k == 3) {
-                pos = std::stoi(field);
-            } else if (k == 5) {
-                cigar = field;
-            } else if (field.substr(0, 5) == "LN:i:") {
-                read_length = std::stoi(field.substr(5, field.size() - 5));
-            } else if (field.substr(0, 5) == "NM:i:") {
-                nonmatching = std::stoi(field.substr(5, field.size() - 5));
+    string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    in.close();
+    // line starts
+    std::vector<size_t> starts;
+    for (size_t p = 0; p < text.size();) {
+        starts.push_back(p);
+        const void* nl = memchr(text.data() + p, '\n', text.size() - p);
+        p = nl ? (size_t)((const char*)nl - text.data()) + 1 : text.size();
+    }
+    const size_t n_lines = starts.size();
+    starts.push_back(text.size() + 1);  // as if the last line ended with a newline
+    std::vector<SamRecord> recs(n_lines);
+    std::vector<char> is_record(n_lines, 0);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (size_t i = 0; i < n_lines; i++) {
+        const char* p = text.data() + starts[i];
+        const char* end = text.data() + std::min(starts[i + 1] - 1, text.size());  // the newline (or the end)
+        if (p < end && *p == '@') continue;
+        is_record[i] = 1;
+        parse_sam_line(p, end, st, amplicon, recs[i]);
+    }
+    for (size_t i = 0; i < n_lines; i++) {
+        if (!is_record[i]) continue;
+        SamRecord& rec = recs[i];
+        bool good = rec.good;
+        if (rec.n_fields == 0) continue;  // an empty line: the reference looks nothing up
+        int64_t read = rec.read, contig = rec.contig;
+        if (read < 0) {
+            if (st.index.find(rec.read_name) == st.index.end()) {
+                std::cout << "WARNING: read in the sam file not found in reads file, ignoring: " << rec.read_name << std::endl;
+                good = false;
             }
-            k++;
+            read = st.index[rec.read_name];  // registers the name (index 0), like the reference's map access
         }
-        if (!(good && k > 10 && contig != read)) continue;
-        cigar_ops(cigar, ops);
-        int h_start = clip_at_start(cigar, 'H'), h_end = clip_at_end(cigar, 'H');
-        if (!forward) std::swap(h_start, h_end);
-        int s_start = clip_at_start(cigar, 'S'), s_end = clip_at_end(cigar, 'S');
-        if (!forward) std::swap(s_start, s_end);
-        if (h_start + h_end > 0.2 * read_length && flag < 2048) good = false;
-        else if (flag % 512 >= 256) good = false;
-        if (amplicon && nonmatching > 0.2 * read_length) good = false;
-        if (!good) continue;
-        int on_read = 0, on_contig = 0;
-        for (uint32_t op : ops) {
-            const int n = (int)(op >> 4), ty = (int)(op & 15);
-            if (ty == 0 || ty == 7 || ty == 8) { on_read += n; on_contig += n; }
-            else if (ty == 1) on_read += n;
-            else if (ty == 2) on_contig += n;
-        }
+        if (contig < 0 && rec.n_fields >= 3) contig = st.index[rec.contig_name];
+        if (!(good && rec.enough_fields && contig != read)) continue;
         Alignment a;
         a.read = read;
         a.contig = contig;
-        a.pos_1_1 = s_start + h_start;
-        a.pos_1_2 = s_start + h_start + on_read;
-        a.pos_2_1 = pos - 1;
-        a.pos_2_2 = pos + on_contig;
-        a.strand = forward;
-        a.cigar = cigar;
+        a.pos_1_1 = rec.pos_1_1;
+        a.pos_1_2 = rec.pos_1_2;
+        a.pos_2_1 = rec.pos_2_1;
+        a.pos_2_2 = rec.pos_2_2;
+        a.strand = rec.forward;
+        a.cigar.swap(rec.cigar);
         const int64_t id = (int64_t)st.alns.size();
         st.seqs[read].alns.push_back(id);
         st.seqs[contig].alns.push_back(id);

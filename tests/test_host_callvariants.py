@@ -120,3 +120,51 @@ def test_parsers_match_reference_read_lines(hostlib, tmp_path, fastq):
             cur.append(tuple(f[1:7]))
     assert got == want
     assert sum(len(v) for v in want.values()) > 10
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref not built")
+@pytest.mark.parametrize("amplicon", [0, 1])
+def test_sam_filters_and_index_quirks_match_reference(hostlib, tmp_path, amplicon):
+    """unmapped / secondary / supplementary flags, hard-clip and NM limits, short lines, '*' CIGARs, unknown
+    read names (the second record of an unknown read lands on read 0 in the reference) and blank lines"""
+    chunks = [cases.small_case(seed=7, length=2500, depth=10, mean_len=700, hard=0.5),
+              cases.small_case(seed=8, length=1200, depth=6, mean_len=500)]
+    for i, c in enumerate(chunks):
+        c.name = f"ctg{i}"
+    gfa, reads, sam = synth.write_files(chunks, os.path.join(str(tmp_path), "in"))
+    r0, r1 = "ctg0_r0", "ctg1_r1"
+    extra = [
+        f"{r0}\t4\tctg0\t10\t60\t50M\t*\t0\t0\t*\t*\tNM:i:0\tLN:i:700",            # unmapped
+        f"{r0}\t256\tctg0\t10\t60\t50M\t*\t0\t0\t*\t*\tNM:i:0\tLN:i:700",          # secondary
+        f"{r0}\t2048\tctg1\t5\t60\t400H30M2D10M300H\t*\t0\t0\t*\t*\tNM:i:2\tLN:i:740",  # supplementary keeps its H
+        f"{r0}\t0\tctg1\t5\t60\t400H30M300H\t*\t0\t0\t*\t*\tNM:i:2\tLN:i:730",     # too much H for a primary record
+        f"{r1}\t16\tctg0\t100\t60\t5S40M3I20M7S\t*\t0\t0\t*\t*\tNM:i:30\tLN:i:75",  # NM > 20 % (amplicon only)
+        f"{r1}\t16\tctg0\t300\t60\t3H5S40M7S2H\t*\t0\t0\t*\t*\tNM:i:1\tLN:i:57",   # S hidden behind H at the end
+        f"{r1}\t0\tctg0\t200\t60\t*\t*\t0\t0\t*\t*\tNM:i:0\tLN:i:500",              # no CIGAR
+        f"{r1}\t0\tctg0\t200\t60\t20M\t*\t0\t0",                                     # too few fields
+        "ghost_read\t0\tctg0\t50\t60\t30M\t*\t0\t0\t*\t*\tNM:i:0\tLN:i:30",          # unknown: ignored, registered
+        "ghost_read\t0\tctg0\t60\t60\t30M\t*\t0\t0\t*\t*\tNM:i:0\tLN:i:30",          # ... and now it is read 0
+        "",
+        f"{r0}\t0\tctg0\t900\t60\t25M1I25M\t*\t0\t0\t*\t*\tNM:i:1\tLN:i:700\t",     # trailing tab
+    ]
+    with open(sam, "a") as f:
+        f.write("\n".join(extra) + "\n")
+    col, vcf, err = [os.path.join(str(tmp_path), n) for n in ("ref.col", "ref.vcf", "ref.err")]
+    subprocess.run([REF_EXE, gfa, reads, sam, "1", str(tmp_path), err, str(amplicon), "0", col, vcf, "0.33"], check=True,
+                   stdout=subprocess.DEVNULL)
+    dump = os.path.join(str(tmp_path), "ours.dump")
+    assert hostlib.hshost_parse_dump(gfa.encode(), reads.encode(), sam.encode(), amplicon, dump.encode()) == 0
+
+    def blocks(path, ncol):
+        out, cur = {}, None
+        for line in open(path):
+            f = line.rstrip("\n").split("\t")
+            if f[0] == "CONTIG":
+                cur = out.setdefault(f[1], [])
+            elif f[0] == "READ":
+                cur.append(tuple(f[1:ncol]))
+        return out
+    want, got = blocks(col, 7), blocks(dump, 7)
+    assert got == want
+    n_extra = sum(len(v) for v in want.values()) - sum(c.n_reads for c in chunks)
+    assert n_extra == (5 if amplicon else 6)
