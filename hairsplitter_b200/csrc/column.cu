@@ -96,26 +96,37 @@ __device__ __forceinline__ void write_column(const ColumnArgs& a, int64_t g, int
 #define CR_BINS (HS_NCODES + 1)
 #define CR_META 128
 
+template <typename H>
 struct SmemAcc {
     const uint8_t* order;   // [CR_ORD][128] codes in first-seen order
-    const uint16_t* hist;   // [CR_BINS][128], bin = code - 32
+    const H* hist;          // [CR_BINS][128], bin = code - 32
     int col;
     __device__ __forceinline__ int key(int k) const { return order[k * HS_TILE + col]; }
     __device__ __forceinline__ unsigned count(int key) const { return hist[(key - 32) * HS_TILE + col]; }
 };
 
-static const int kColumnSmem = 2 * CR_ROWS * HS_TILE + CR_BINS * HS_TILE * 2 + CR_ORD * HS_TILE + CR_META * 8 + CR_META;
+// Histogram bins are bytes for tiles covered by at most CR_U8_MAX reads (every tile at ordinary sequencing
+// depths: the histogram is what bounds the CTAs per SM) and 16-bit for deeper tiles (amplicons); the two
+// instantiations are launched over the same grid and each CTA leaves at once when the tile is not its kind.
+#define CR_U8_MAX 240
+template <typename H>
+constexpr int column_smem() {
+    return 2 * CR_ROWS * HS_TILE + CR_BINS * HS_TILE * (int)sizeof(H) + CR_ORD * HS_TILE + CR_META * 8 + CR_META;
+}
 
 __device__ __forceinline__ void cr_cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
     const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 
+template <typename H>
 __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
+    const int64_t list_off0 = a.tile_off[blockIdx.x];
+    if (((int)(a.tile_off[blockIdx.x + 1] - list_off0) <= CR_U8_MAX) != (sizeof(H) == 1)) return;
     unsigned char* s_rows = smem;                                                        // 2 x 16 x 128 B
-    uint16_t* s_hist = reinterpret_cast<uint16_t*>(smem + 2 * CR_ROWS * HS_TILE);        // [126][128] u16
-    uint8_t* s_order = smem + 2 * CR_ROWS * HS_TILE + CR_BINS * HS_TILE * 2;             // [32][128] u8
+    H* s_hist = reinterpret_cast<H*>(smem + 2 * CR_ROWS * HS_TILE);                      // [126][128]
+    uint8_t* s_order = smem + 2 * CR_ROWS * HS_TILE + CR_BINS * HS_TILE * (int)sizeof(H);  // [32][128] u8
     const uint8_t** s_ptr = reinterpret_cast<const uint8_t**>(s_order + CR_ORD * HS_TILE);  // [128]
     uint8_t* s_vmask = reinterpret_cast<uint8_t*>(s_ptr + CR_META);                      // [128]
     __shared__ unsigned long long s_depth;
@@ -136,12 +147,12 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
     }
     {
         uint4* h4 = reinterpret_cast<uint4*>(s_hist);
-        for (int i = tid; i < CR_BINS * HS_TILE * 2 / 16; i += HS_TILE) h4[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < CR_BINS * HS_TILE * (int)sizeof(H) / 16; i += HS_TILE) h4[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     s_hist[tid] = 1;  // bin 0 ("no cell") never looks like a first sighting
     int m = 0, rows_done = 0;
-    uint16_t* const hcol = s_hist + tid;
+    H* const hcol = s_hist + tid;
     const int crow = tid >> 3, cpart = tid & 7;  // this thread's copy slot in a batch: row, 16-byte part
     for (int sb = 0; sb < nlist; sb += CR_META) {
         const int nmeta = min(CR_META, nlist - sb);
@@ -192,7 +203,7 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
                     if (m < CR_ORD) s_order[m * HS_TILE + tid] = (uint8_t)code[row];
                     m++;
                 }
-                hcol[bin * HS_TILE] = (uint16_t)(cnt + 1);
+                hcol[bin * HS_TILE] = (H)(cnt + 1);
             }
         }
     }
@@ -211,7 +222,7 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
         if (m > CR_ORD) {
             defer = 2;
         } else {
-            SmemAcc acc{s_order, s_hist, tid};
+            SmemAcc<H> acc{s_order, s_hist, tid};
             int k0, k1;
             unsigned c0, c1, c2;
             if (hs_rank_fast(acc, m, &s_lut, k0, k1, c0, c1, c2) != 0) defer = 1;
@@ -582,7 +593,8 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
     }
     static bool attr_set = false;
     if (!attr_set) {
-        HS_CUDA(ctx, cudaFuncSetAttribute(column_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kColumnSmem));
+        HS_CUDA(ctx, cudaFuncSetAttribute(column_rank_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          column_smem<uint16_t>()));
         attr_set = true;
     }
     if (p->n_tiles > 0) {
@@ -621,7 +633,9 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
         a.item_off = p->d_item_off;
         a.reread = p->d_work + 4;
         HS_CUDA(ctx, cudaMemsetAsync(p->d_work, 0, 4 * sizeof(int32_t), ctx->stream));
-        HS_KERNEL(ctx, "column_rank_kernel", column_rank_kernel<<<(unsigned)p->n_tiles, HS_TILE, kColumnSmem, ctx->stream>>>(a));
+        HS_KERNEL(ctx, "column_rank_kernel", column_rank_kernel<uint8_t><<<(unsigned)p->n_tiles, HS_TILE, column_smem<uint8_t>(), ctx->stream>>>(a));
+        if (p->max_tile_reads > CR_U8_MAX)  // deep tiles (amplicons): 16-bit bins
+            HS_KERNEL(ctx, "column_rank_kernel<u16>", column_rank_kernel<uint16_t><<<(unsigned)p->n_tiles, HS_TILE, column_smem<uint16_t>(), ctx->stream>>>(a));
         HS_KERNEL(ctx, "column_rank_deferred_kernel",
                   column_rank_deferred_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a, nc));
         LiteralArgs la;

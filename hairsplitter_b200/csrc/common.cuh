@@ -159,6 +159,7 @@ struct hsgpu_pileup {
     uint8_t* d_read_flags = nullptr;  // HS_READ_IRREGULAR: clips between aligned parts
     unsigned int* d_next_read = nullptr;  // work counter of pileup_kernel's persistent warps
     int64_t n_irregular = 0;
+    int64_t max_tile_reads = 0;       // most reads over one 128-column tile (picks the histogram width)
     int64_t* d_row_alloc = nullptr;   // bytes reserved per read (multiple of 16), then its exclusive scan
     int64_t* d_row_base = nullptr;    // codes[row_base[r] + q] = cell of read r at column q (row_base % 16 == 0)
     uint8_t* d_codes = nullptr;

@@ -266,7 +266,7 @@ __device__ __forceinline__ void pw_walk_slow(const uint32_t mI, const uint32_t m
     p1x_out = p1x;
 }
 
-__global__ void __launch_bounds__(32 * PW_WARPS) pileup_kernel(PileupArgs a) {
+__global__ void __launch_bounds__(32 * PW_WARPS, 4) pileup_kernel(PileupArgs a) {
     __shared__ unsigned int s_bits[PW_WARPS][2][32];
     __shared__ __align__(16) uint8_t s_buf[PW_WARPS][PW_BUF];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -292,8 +292,9 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pileup_kernel(PileupArgs a) {
         const int strand = a.read_strand[r];
         const int end = a.read_end[r];
         uint8_t* __restrict__ row = a.codes + row_base;
-        const int64_t k1 = a.cigar_off[r + 1];
-        int64_t kop = a.cigar_off[r];  // first op of the next window
+        const uint32_t* __restrict__ cig = a.cigar + a.cigar_off[r];
+        const int nops = (int)(a.cigar_off[r + 1] - a.cigar_off[r]);
+        int kop = 0;                   // first op of the window
         int off0 = 0;                  // positions of op kop that earlier windows already consumed
         int q0 = start, t0 = a.read_tlead[r];  // contig column / read offset of the window's first position
         int carry_ctx = HS_CODE0 + 5 * 1 + 2, carry_p1x = 5 * 2 + HS_CODE0;  // context 'A','C','G' (:212-214)
@@ -302,19 +303,24 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pileup_kernel(PileupArgs a) {
         unsigned int udist = 0, ualen = 0;  // per warp (same value in every lane)
         if (lane < HS_ALIGN) buf[lane] = 0;  // the pad in front of the first cell
         __syncwarp();
-        while (kop < k1 && q0 < L) {
+        // the window's ops live in registers; the next window's are requested before the walk of this one
+        uint32_t opw[PW_OPL];
+#pragma unroll
+        for (int j = 0; j < PW_OPL; j++) {
+            const int k = kop + PW_OPL * lane + j;
+            opw[j] = (k < nops) ? __ldg(cig + k) : (uint32_t)OP_P;
+        }
+        while (kop < nops && q0 < L) {
             // ---- the window's ops: classify, scan the position counts -------------------------------
             int klen[PW_OPL], kd[PW_OPL], e_in[PW_OPL];
             int es = 0;
 #pragma unroll
             for (int j = 0; j < PW_OPL; j++) {
-                const int slot = PW_OPL * lane + j;
-                const int64_t k = kop + slot;
-                const uint32_t op = (k < k1) ? __ldg(a.cigar + k) : (uint32_t)OP_P;
-                const int ty = (int)(op & 15);
-                int ln = (int)(op >> 4);
-                if (slot == 0) ln -= off0;
-                const int kind = (ty == OP_M || ty == OP_EQ || ty == OP_X) ? PK_M : (ty == OP_I) ? PK_I : (ty == OP_D) ? PK_D : PK_NONE;
+                const int ty = (int)(opw[j] & 15);
+                int ln = (int)(opw[j] >> 4);
+                if (j == 0 && lane == 0) ln -= off0;
+                // M,=,X -> PK_M; I -> PK_I; D -> PK_D; everything else takes no alignment position
+                const int kind = (ty < 8) ? (int)((0x04444210u >> (4 * ty)) & 15u) : (ty == OP_X ? PK_M : PK_NONE);
                 kd[j] = kind;
                 klen[j] = (kind != PK_NONE) ? min(ln, 1024) : 0;  // the window ends inside anything longer than PW_E
                 e_in[j] = es;
@@ -323,13 +329,32 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pileup_kernel(PileupArgs a) {
             const int ei = hs_warp_incl_scan(es, lane);
             const int ebase = ei - es;
             const int Etot = __shfl_sync(0xffffffffu, ei, 31);
-            const int nload = (int)min((int64_t)PW_NOPS, k1 - kop);
-            if (Etot == 0) {  // nothing but clips / padding
-                kop += nload;
-                off0 = 0;
-                continue;
-            }
+            const int nload = min(PW_NOPS, nops - kop);
             const int Enew = min(Etot, PW_E);
+            // ---- where the next window starts; its ops are requested now and used after the walk --------
+            int kop_next = kop + nload, off0_next = 0;
+            if (Enew < Etot) {
+                int myslot = -1, myd = 0;
+#pragma unroll
+                for (int j = 0; j < PW_OPL; j++) {
+                    const int pa = ebase + e_in[j];
+                    if (klen[j] > 0 && pa <= Enew && Enew < pa + klen[j]) { myslot = PW_OPL * lane + j; myd = Enew - pa; }
+                }
+                const unsigned int who = __ballot_sync(0xffffffffu, myslot >= 0);
+                const int src = __ffs(who) - 1;
+                const int slot = __shfl_sync(0xffffffffu, myslot, src);
+                const int d = __shfl_sync(0xffffffffu, myd, src);
+                off0_next = (slot == 0 ? off0 : 0) + d;
+                kop_next = kop + slot;
+            }
+#pragma unroll
+            for (int j = 0; j < PW_OPL; j++) {
+                const int k = kop_next + PW_OPL * lane + j;
+                opw[j] = (k < nops) ? __ldg(cig + k) : (uint32_t)OP_P;
+            }
+            kop = kop_next;
+            off0 = off0_next;
+            if (Etot == 0) continue;  // nothing but clips / padding
             const bool full = Enew == PW_E;
             const int P = full ? PW_P : max(2, (Enew + 31) >> 5);
             // ---- insertion / deletion masks over window positions (bit 0,1 = virtual warm-up of lane 0) ---
@@ -374,24 +399,6 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pileup_kernel(PileupArgs a) {
             const int last = (Enew - 1) / P;  // the lane that pushed the window's last symbol
             carry_ctx = __shfl_sync(0xffffffffu, ctx, last);
             carry_p1x = __shfl_sync(0xffffffffu, p1x, last);
-            // ---- where the next window starts ------------------------------------------------------
-            if (Enew == Etot) {
-                kop += nload;
-                off0 = 0;
-            } else {
-                int myslot = -1, myd = 0;
-#pragma unroll
-                for (int j = 0; j < PW_OPL; j++) {
-                    const int pa = ebase + e_in[j];
-                    if (klen[j] > 0 && pa <= Enew && Enew < pa + klen[j]) { myslot = PW_OPL * lane + j; myd = Enew - pa; }
-                }
-                const unsigned int who = __ballot_sync(0xffffffffu, myslot >= 0);
-                const int src = __ffs(who) - 1;
-                const int slot = __shfl_sync(0xffffffffu, myslot, src);
-                const int d = __shfl_sync(0xffffffffu, myd, src);
-                off0 = (slot == 0 ? off0 : 0) + d;
-                kop += slot;
-            }
             q0 = qend;
             t0 += Enew - totD;
             // ---- flush the complete 16-byte vectors, keep the partial one ----------------------------
@@ -542,7 +549,8 @@ __global__ void __launch_bounds__(256) tile_index_kernel(int64_t n_tiles, const 
                                                          const int32_t* __restrict__ read_start,
                                                          const int32_t* __restrict__ read_end,
                                                          int64_t* __restrict__ tile_cnt_or_off,
-                                                         int32_t* __restrict__ tile_reads) {
+                                                         int32_t* __restrict__ tile_reads,
+                                                         unsigned long long* __restrict__ max_count) {
     const int lane = threadIdx.x & 31;
     const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (tile >= n_tiles) return;
@@ -550,6 +558,7 @@ __global__ void __launch_bounds__(256) tile_index_kernel(int64_t n_tiles, const 
     const int q0 = (int)(tile - tile_base[c]) * HS_TILE, q1 = q0 + HS_TILE;
     const int64_t r0 = contig_read_off[c], r1 = contig_read_off[c + 1];
     int64_t out = FILL ? tile_cnt_or_off[tile] : 0;
+#pragma unroll 4
     for (int64_t rb = r0; rb < r1; rb += 32) {
         const int64_t r = rb + lane;
         bool hit = false;
@@ -561,7 +570,10 @@ __global__ void __launch_bounds__(256) tile_index_kernel(int64_t n_tiles, const 
         if (FILL && hit) tile_reads[out + __popc(m & ((1u << lane) - 1u))] = (int32_t)r;
         out += __popc(m);
     }
-    if (!FILL && lane == 0) tile_cnt_or_off[tile] = out;
+    if (!FILL && lane == 0) {
+        tile_cnt_or_off[tile] = out;
+        if (max_count && out > 0) atomicMax(max_count, (unsigned long long)out);
+    }
 }
 
 // ---- host side --------------------------------------------------------------------------------
@@ -710,9 +722,9 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     hs_free(ctx, p->d_tile_reads);
     p->built = p->ranked = p->have_col_off = false;
     HS_CUDA(ctx, cudaMemsetAsync(p->d_stats, 0, sizeof(unsigned long long) * 3 * p->n_contigs, ctx->stream));
-    int64_t* d_totals = nullptr;  // codes bytes, tile index entries, irregular reads
-    HS_CUDA(ctx, hs_alloc(ctx, &d_totals, 3));
-    HS_CUDA(ctx, cudaMemsetAsync(d_totals, 0, 3 * sizeof(int64_t), ctx->stream));
+    int64_t* d_totals = nullptr;  // codes bytes, tile index entries, irregular reads, most reads over one tile
+    HS_CUDA(ctx, hs_alloc(ctx, &d_totals, 4));
+    HS_CUDA(ctx, cudaMemsetAsync(d_totals, 0, 4 * sizeof(int64_t), ctx->stream));
     HS_CUDA(ctx, cudaMemsetAsync(p->d_next_read, 0, sizeof(unsigned int), ctx->stream));
     if (nr > 0) {
         HS_KERNEL(ctx, "span_kernel", span_kernel<<<rblocks, 256, 0, ctx->stream>>>(
@@ -724,17 +736,18 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     if (p->n_tiles > 0) {
         HS_KERNEL(ctx, "tile_index_kernel<false>", tile_index_kernel<false><<<(unsigned)((p->n_tiles + 7) / 8), 256, 0, ctx->stream>>>(
             p->n_tiles, p->d_tile_contig, p->d_tile_base, p->d_contig_read_off, p->d_read_start, p->d_read_end,
-            p->d_tile_off, nullptr));
+            p->d_tile_off, nullptr, reinterpret_cast<unsigned long long*>(d_totals + 3)));
     }
     rc = hs_exclusive_scan_i64(ctx, p->d_tile_off, p->d_tile_off, p->n_tiles, d_totals + 1);
     if (rc) return rc;
-    int64_t totals[3] = {0, 0, 0};
-    HS_CUDA(ctx, hs_d2h(ctx, totals, d_totals, 3));
+    int64_t totals[4] = {0, 0, 0, 0};
+    HS_CUDA(ctx, hs_d2h(ctx, totals, d_totals, 4));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the only host round trip of the build: three counts
     hs_free(ctx, d_totals);
     p->codes_bytes = totals[0];
     p->tile_entries = totals[1];
     p->n_irregular = totals[2];
+    p->max_tile_reads = totals[3];
     HS_CUDA(ctx, hs_alloc(ctx, &p->d_codes, p->codes_bytes + HS_ALIGN));
     HS_CUDA(ctx, hs_alloc(ctx, &p->d_tile_reads, p->tile_entries));
     HS_CUDA(ctx, cudaMemcpyAsync(p->d_tile_off + p->n_tiles, &p->tile_entries, sizeof(int64_t), cudaMemcpyHostToDevice,
@@ -775,7 +788,7 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     if (p->n_tiles > 0) {
         HS_KERNEL(ctx, "tile_index_kernel<true>", tile_index_kernel<true><<<(unsigned)((p->n_tiles + 7) / 8), 256, 0, ctx->stream>>>(
             p->n_tiles, p->d_tile_contig, p->d_tile_base, p->d_contig_read_off, p->d_read_start, p->d_read_end,
-            p->d_tile_off, p->d_tile_reads));
+            p->d_tile_off, p->d_tile_reads, nullptr));
     }
     p->built = true;
     return HSGPU_OK;
