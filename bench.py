@@ -484,41 +484,90 @@ def main():
     pu.close()
 
     # ---- e2e: host buffers -> C ABI -> host results, every step ----
-    pinned = api.PackedBatch.__new__(api.PackedBatch)
-    pinned.__dict__.update(packed.__dict__)
+    # The way a caller drives the library: the batch is cut into groups of contig chunks, each group goes
+    # through its own hsgpu context (one per host thread, as the header prescribes), so that the H2D copy of
+    # one group overlaps the kernels of another; CIGARs travel in the 16-bit form.
+    import threading
+    n_groups = max(1, min(4, len(chunks)))
+    n_lanes = min(2, n_groups)
+    groups = []
     keep = []
-    for name in ("contig_len", "contig_bases", "contig_word_off", "contig_read_off", "read_bases", "read_word_off",
-                 "read_len", "cigar", "cigar_off", "read_start", "read_strand"):
-        src = getattr(packed, name)
-        t = torch.empty(max(src.nbytes, 1), dtype=torch.uint8, pin_memory=True)
-        arr = t.numpy()[:src.nbytes].view(src.dtype).reshape(src.shape)
-        arr[...] = src
-        keep.append(t)
-        setattr(pinned, name, arr)
+    for g in range(n_groups):
+        pb = api.PackedBatch(chunks[g::n_groups]).use_compact_cigar()
+        for name in ("contig_len", "contig_bases", "contig_word_off", "contig_read_off", "read_bases", "read_word_off",
+                     "read_len", "cigar16", "cigar16_off", "read_start", "read_strand"):
+            src = getattr(pb, name)
+            t = torch.empty(max(src.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            arr = t.numpy()[:src.nbytes].view(src.dtype).reshape(src.shape)
+            arr[...] = src
+            keep.append(t)
+            setattr(pb, name, arr)
+        groups.append(pb)
+    h2d_bytes = sum(int(pb.input_bytes) for pb in groups)
+    lanes = [ctx] + [api.Context(local_rank) for _ in range(n_lanes - 1)]
+    lane_streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local_rank)) for c in lanes]
+    e2e_out = [0] * n_groups
+    e2e_sus = [0] * n_groups
 
-    def e2e_step():
-        p = api.Pileup(ctx, pinned)      # H2D of the whole batch
+    def e2e_group(lane, g):
+        p = api.Pileup(lanes[lane], groups[g])   # H2D of the group
         p.build()
         p.column_rank()
-        ns, ds = p.column_counts()       # D2H
+        ns, ds = p.column_counts()               # D2H
         got = 0
-        for ci in range(pinned.n_contigs):
-            pos, au = p.suspects(ci)     # D2H of the call_variants result
+        for ci in range(groups[g].n_contigs):
+            pos, au = p.suspects(ci)             # D2H of the call_variants result
             got += pos.nbytes + au.nbytes
         p.close()
-        return got + ns.nbytes + ds.nbytes
+        e2e_out[g] = got + ns.nbytes + ds.nbytes
+        e2e_sus[g] = int(ns.sum())
+
+    def e2e_step():
+        def work(lane):
+            for g in range(lane, n_groups, n_lanes):
+                e2e_group(lane, g)
+        ts = [threading.Thread(target=work, args=(lane,)) for lane in range(1, n_lanes)]
+        for t in ts:
+            t.start()
+        work(0)
+        for t in ts:
+            t.join()
+        return sum(e2e_out)
 
     for _ in range(min(args.warmup, 3)):
         d2h_bytes = e2e_step()
+    assert sum(e2e_sus) == int(n_sus.sum()), "the grouped e2e path must find the same suspect columns"
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    t_e2e = time.perf_counter()
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+    for ev, st_ in zip(e0, lane_streams):
+        ev.record(st_)
     for _ in range(args.steps):
         d2h_bytes = e2e_step()
-    e1.record(stream)
-    ctx.sync()
+    for ev, st_ in zip(e1, lane_streams):
+        ev.record(st_)
+    for c in lanes:
+        c.sync()
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    t_e2e = (time.perf_counter() - t_e2e) * 1e3
+    # device time of the slowest lane; the host wall clock around the same region is reported beside it
+    e2e_ms = max(a.elapsed_time(b) for a, b in zip(e0, e1))
+    for c in lanes[1:]:
+        c.close()
+    # the floor of the e2e step on this box: the same bytes from pinned memory with nothing else going on
+    src = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
+    dst = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_floor_ms = c0.elapsed_time(c1) / 3
+    del src, dst
 
     # ---- the other stages of the hot path (reported beside the headline, rank 0 / 1 GPU only) ----
     stages = {}
@@ -554,8 +603,12 @@ def main():
             },
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "windows/s", "ms_per_step": e2e_ms / max(args.steps, 1),
-                    "h2d_bytes_per_step": int(packed.input_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                    "path": "hsgpu_pileup_create(pinned host buffers) + build + column_rank + column_counts + suspects"},
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "host_wall_ms_per_step": t_e2e / max(args.steps, 1),
+                    "h2d_copy_floor_ms": h2d_floor_ms, "h2d_gbs": h2d_bytes / (h2d_floor_ms * 1e-3) / 1e9,
+                    "path": f"{n_groups} groups of chunks over {n_lanes} hsgpu contexts (one host thread each): "
+                            "hsgpu_pileup_create(pinned host buffers, 16-bit CIGAR) + build + column_rank + "
+                            "column_counts + suspects"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "kernels": kernels,

@@ -35,6 +35,7 @@ class PileupInput(C.Structure):
         ("cigar_off", C.c_void_p),
         ("read_start", C.c_void_p),
         ("read_strand", C.c_void_p),
+        ("cigar16", C.c_void_p),
     ]
 
 
@@ -144,6 +145,23 @@ def pack_codes(codes: np.ndarray) -> np.ndarray:
     return np.bitwise_or.reduce(pad.reshape(nw, 16) << sh, axis=1).astype(np.uint32)
 
 
+def compact_cigar(cigar: np.ndarray, cigar_off: np.ndarray):
+    """u32 BAM ops -> the optional u16 form of hsgpu_pileup_input.cigar16 (ops longer than 4095 are split)."""
+    ln = (cigar >> 4).astype(np.int64)
+    op = (cigar & 15).astype(np.uint16)
+    reps = np.maximum((ln + 4094) // 4095, 1)
+    if int(reps.max(initial=1)) == 1:
+        return ((ln.astype(np.uint16) << 4) | op), cigar_off
+    first = np.cumsum(reps) - reps                      # index of the first piece of every op
+    total = int(reps.sum())
+    piece_len = np.full(total, 4095, dtype=np.int64)
+    last = first + reps - 1
+    piece_len[last] = ln - 4095 * (reps - 1)
+    out = (piece_len.astype(np.uint16) << 4) | np.repeat(op, reps)
+    new_off = np.concatenate([first, [total]])[cigar_off]
+    return out, new_off.astype(np.int64)
+
+
 class PackedBatch:
     """Host-side packing of a list of synth.ContigBatch into the flat arrays of hsgpu_pileup_input."""
 
@@ -189,6 +207,12 @@ class PackedBatch:
                                                        self.read_len, self.cigar, self.cigar_off, self.read_start,
                                                        self.read_strand))
 
+    def use_compact_cigar(self):
+        """switches the batch to the 16-bit CIGAR form (half the CIGAR bytes over PCIe)"""
+        self.cigar16, self.cigar16_off = compact_cigar(self.cigar, self.cigar_off)
+        self.input_bytes += int(self.cigar16.nbytes) - int(self.cigar.nbytes)
+        return self
+
     def struct(self) -> PileupInput:
         s = PileupInput()
         s.n_contigs = self.n_contigs
@@ -200,8 +224,14 @@ class PackedBatch:
         s.read_bases = self.read_bases.ctypes.data
         s.read_word_off = self.read_word_off.ctypes.data
         s.read_len = self.read_len.ctypes.data
-        s.cigar = self.cigar.ctypes.data
-        s.cigar_off = self.cigar_off.ctypes.data
+        if getattr(self, "cigar16", None) is not None:
+            s.cigar = None
+            s.cigar16 = self.cigar16.ctypes.data
+            s.cigar_off = self.cigar16_off.ctypes.data
+        else:
+            s.cigar = self.cigar.ctypes.data
+            s.cigar16 = None
+            s.cigar_off = self.cigar_off.ctypes.data
         s.read_start = self.read_start.ctypes.data
         s.read_strand = self.read_strand.ctypes.data
         return s

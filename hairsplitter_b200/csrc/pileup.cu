@@ -576,6 +576,14 @@ __global__ void __launch_bounds__(256) tile_index_kernel(int64_t n_tiles, const 
     }
 }
 
+__global__ void cigar_expand_kernel(int64_t n, const uint16_t* __restrict__ in, uint32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t v = in[i];
+        out[i] = ((v >> 4) << 4) | (v & 15u);  // same bit layout, wider length field
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------
 extern "C" {
 
@@ -700,7 +708,17 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_bases, in->read_bases, read_words));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_word_off, in->read_word_off, nr + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_len, in->read_len, nr));
-    HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar, in->cigar, p->n_cigar));
+    uint16_t* d_cigar16 = nullptr;
+    if (in->cigar16) {
+        HS_CUDA(ctx, hs_alloc(ctx, &d_cigar16, p->n_cigar));
+        HS_CUDA(ctx, hs_h2d(ctx, d_cigar16, in->cigar16, p->n_cigar));
+        if (p->n_cigar > 0)
+            HS_KERNEL(ctx, "cigar_expand_kernel", cigar_expand_kernel<<<(unsigned)((p->n_cigar + 255) / 256), 256, 0, ctx->stream>>>(
+                p->n_cigar, d_cigar16, p->d_cigar));
+        hs_free(ctx, d_cigar16);
+    } else {
+        HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar, in->cigar, p->n_cigar));
+    }
     HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar_off, in->cigar_off, nr + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_start, in->read_start, nr));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_strand, in->read_strand, nr));

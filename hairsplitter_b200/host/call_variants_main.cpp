@@ -42,6 +42,20 @@ static void phase(const char* name) {
         }                                                                                           \
     } while (0)
 
+// the 16-bit CIGAR form of hsgpu_pileup_input (ops longer than 4095 become several ops of the same kind)
+static void compact_ops(const std::vector<uint32_t>& ops, std::vector<uint16_t>& out) {
+    out.clear();
+    for (uint32_t op : ops) {
+        uint32_t n = op >> 4;
+        const uint16_t ty = (uint16_t)(op & 15);
+        while (n > 4095) {
+            out.push_back((uint16_t)((4095u << 4) | ty));
+            n -= 4095;
+        }
+        out.push_back((uint16_t)((n << 4) | ty));
+    }
+}
+
 struct ContigResult {
     float mean_distance = 0;
     float depth = 0;
@@ -77,13 +91,14 @@ static void process_batch(hsgpu_ctx* ctx, const Store& st, const std::string& re
     const int nc = (int)batch.size();
     std::vector<int32_t> contig_len(nc), read_len, read_start;
     std::vector<int64_t> contig_word_off(nc + 1, 0), contig_read_off(nc + 1, 0), read_word_off(1, 0), cigar_off(1, 0);
-    std::vector<uint32_t> contig_bases, read_bases, cigar;
+    std::vector<uint32_t> contig_bases, read_bases;
+    std::vector<uint16_t> cigar;
     std::vector<uint8_t> read_strand;
     {
         // the reads of every contig: sequence lines and CIGAR ops, contigs in parallel (each thread its own
         // file handle), then one pass for the offsets, then the 2-bit packing in parallel again
         std::vector<std::vector<std::string>> seqs(nc);
-        std::vector<std::vector<std::vector<uint32_t>>> ops(nc);
+        std::vector<std::vector<std::vector<uint16_t>>> ops(nc);
 #pragma omp parallel
         {
             std::ifstream reads_file(reads_path);
@@ -92,7 +107,11 @@ static void process_batch(hsgpu_ctx* ctx, const Store& st, const std::string& re
                 const SeqRec& contig = st.seqs[st.contigs[batch[b]]];
                 load_read_sequences(reads_file, st, st.contigs[batch[b]], seqs[b]);
                 ops[b].resize(contig.alns.size());
-                for (size_t n = 0; n < contig.alns.size(); n++) cigar_ops(st.alns[contig.alns[n]].cigar, ops[b][n]);
+                std::vector<uint32_t> wide;
+                for (size_t n = 0; n < contig.alns.size(); n++) {
+                    cigar_ops(st.alns[contig.alns[n]].cigar, wide);
+                    compact_ops(wide, ops[b][n]);
+                }
             }
         }
         std::vector<int64_t> first_read(nc + 1, 0);
@@ -138,7 +157,7 @@ static void process_batch(hsgpu_ctx* ctx, const Store& st, const std::string& re
     in.read_bases = read_bases.data();
     in.read_word_off = read_word_off.data();
     in.read_len = read_len.data();
-    in.cigar = cigar.data();
+    in.cigar16 = cigar.data();
     in.cigar_off = cigar_off.data();
     in.read_start = read_start.data();
     in.read_strand = read_strand.data();

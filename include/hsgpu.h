@@ -86,6 +86,10 @@ typedef struct {
     const int64_t* cigar_off;         /* [n_reads+1] */
     const int32_t* read_start;        /* [n_reads] Overlap.position_2_1 = POS-1 */
     const uint8_t* read_strand;       /* [n_reads] Overlap.strand, 1 = forward */
+    /* optional compact CIGAR: u16 per op = len<<4 | op with len <= 4095 (longer ops are written as several
+     * ops of the same kind, which every loop of the reference treats the same way). When non-NULL it replaces
+     * `cigar` (which may then be NULL), cigar_off indexes it, and half as many bytes cross PCIe. */
+    const uint16_t* cigar16;
 } hsgpu_pileup_input;
 
 /* copies the batch to the device (asynchronous on the context's stream) */

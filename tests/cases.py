@@ -61,7 +61,8 @@ def walk_edge_case(seed=71, length=5000):
         (0, 1, "1472M", 0), (16, 0, "1473M", 0), (32, 1, "960M", 0), (33, 0, "959M", 0), (47, 1, "961M", 0),
         (5, 1, "1M", 0), (6, 0, "2M", 0), (7, 1, "3M", 0), (64, 1, "1470M10I10M", 0), (65, 0, "1470M10D10M", 0),
         (66, 1, "958M5I5M", 0), (67, 0, "958M5D5M", 0), (1, 1, "2I1D2I1D1M" * 150, 0), (3, 0, "31M1D" * 140, 0),
-        (2, 1, "1471M1I1D1M", 0), (15, 0, "2943M1I1M", 0), (200, 1, "4000S40M", 0),
+        (2, 1, "1471M1I1D1M", 0), (15, 0, "2943M1I1M", 0), (200, 1, "4000S40M", 0), (0, 1, "4999M", 0),
+        (1, 0, "4200S4100M4300S", 0),
     ]
     import re
     starts, strands, cig, cig_off, bases, read_off = [], [], [], [0], [], [0]

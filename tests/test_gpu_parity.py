@@ -219,3 +219,18 @@ def test_golden_fixtures(gpu_ctx):
         kept = pu.robust_filter(0, parts, pos)
         assert np.array_equal(kept, g["filtered_pos"])
         pu.close()
+
+
+@pytest.mark.parametrize("case", ["hifi", "walk_edges"])
+def test_compact_cigar_input_gives_the_same_pileup(gpu_ctx, oracle, case):
+    """hsgpu_pileup_input.cigar16 (ops longer than 4095 split) is only another encoding of the same alignment"""
+    cb = {"hifi": cases.hifi_case, "walk_edges": cases.walk_edge_case}[case]()
+    pk = api.PackedBatch([cb]).use_compact_cigar()
+    assert pk.cigar16.dtype == np.uint16
+    if case == "walk_edges":  # ops longer than 4095 are split
+        assert pk.cigar16.shape[0] > pk.cigar.shape[0]
+    pu = api.Pileup(gpu_ctx, pk)
+    pu.build()
+    pu.column_rank()
+    _check_contig(oracle, pu, 0, cb)
+    pu.close()

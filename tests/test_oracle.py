@@ -174,3 +174,23 @@ def test_read_pair_counts_definition(oracle):
     np.fill_diagonal(ws, 0)
     np.fill_diagonal(wd, 0)
     assert np.array_equal(sim, ws) and np.array_equal(diff, wd)
+
+
+def test_splitting_long_cigar_ops_does_not_change_the_pileup(oracle):
+    """the 16-bit CIGAR form of the C ABI splits ops longer than 4095; the oracle must not see a difference"""
+    import copy
+    from hairsplitter_b200 import api
+    cb = cases.walk_edge_case()
+    long_cb = copy.deepcopy(cb)
+    # stretch one read's match so that it needs splitting, on a longer contig
+    c16, off16 = api.compact_cigar(np.array([(9000 << 4) | 0, (5000 << 4) | 2, (4096 << 4) | 1, (3 << 4) | 0], np.uint32),
+                                   np.array([0, 4], np.int64))
+    assert [(int(x) >> 4, int(x) & 15) for x in c16] == [(4095, 0), (4095, 0), (810, 0), (4095, 2), (905, 2), (4095, 1), (1, 1), (3, 0)]
+    assert list(off16) == [0, 8]
+    split, split_off = api.compact_cigar(cb.cigar, cb.cigar_off)
+    long_cb.cigar = split.astype(np.uint32)
+    long_cb.cigar_off = split_off
+    a, b = oracle.pileup(cb), oracle.pileup(long_cb)
+    for k in ("col_off", "read_idx", "code", "read_end"):
+        assert np.array_equal(a[k], b[k])
+    assert list(a["stats"]) == list(b["stats"])
