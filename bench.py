@@ -576,14 +576,10 @@ def main():
         if args.wall_chunks >= 0:
             stages["call_variants_wall"] = run_call_variants_wall(chunks, args)
 
-    # ---- max over ranks ----
-    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
-    cols_t = torch.tensor([float(n_cols)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cols_t, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
-    total_cols = float(cols_t[0])
+    # ---- max over ranks of the time, sum over ranks of the columns (hairsplitter_b200/sharding.py) ----
+    from hairsplitter_b200 import sharding
+    ms_total, total_cols = sharding.reduce_step(ms_total, float(n_cols), device="cuda")
+    e2e_ms, _ = sharding.reduce_step(e2e_ms, 0.0, device="cuda")
 
     if rank == 0:
         value = total_cols * args.steps / WINDOW / (ms_total * 1e-3)

@@ -54,3 +54,24 @@ def test_usage_and_version_probe_return_zero():
     """hairsplitter.py's dependency check runs the executable with --version and expects status 0 (:229-239)"""
     r = subprocess.run([OURS, "--version"], stdout=subprocess.PIPE)
     assert r.returncode == 0 and b"Usage" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref not built")
+def test_two_gpus_give_the_same_files(tmp_path):
+    """contigs sharded over two GPUs (HSGPU_NGPUS=2), heaviest first: same bytes as the reference"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    chunks = [cases.small_case(seed=91, length=20000, depth=50, mean_len=5000, error=0.06), cases.medium_case(),
+              cases.hifi_case(), cases.small_case(seed=5, length=3000, depth=12, mean_len=900, hard=0.4)]
+    for i, c in enumerate(chunks):
+        c.name = f"ctg{i}"
+    files = synth.write_files(chunks, os.path.join(str(tmp_path), "in"))
+    ref = _run(REF, files, str(tmp_path), "ref")
+    os.environ["HSGPU_NGPUS"] = "2"
+    try:
+        ours = _run(OURS, files, str(tmp_path), "ours", threads=8)
+    finally:
+        del os.environ["HSGPU_NGPUS"]
+    for a, b in zip(ref, ours):
+        assert filecmp.cmp(a, b, shallow=False), (a, b)
