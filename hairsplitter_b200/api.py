@@ -67,8 +67,10 @@ EXPORTS = [
     "hsgpu_pileup_create", "hsgpu_pileup_destroy", "hsgpu_pileup_build", "hsgpu_pileup_stats", "hsgpu_mean_distance",
     "hsgpu_pileup_read_ends", "hsgpu_pileup_export", "hsgpu_pileup_extract_columns", "hsgpu_column_rank",
     "hsgpu_column_counts", "hsgpu_suspects", "hsgpu_column_summary", "hsgpu_partition_tables", "hsgpu_robust_filter",
-    "hsgpu_read_pair_counts", "hsgpu_edlib_align_batch",
+    "hsgpu_read_pair_counts", "hsgpu_pairs_create", "hsgpu_pairs_compute", "hsgpu_pairs_fetch", "hsgpu_pairs_info",
+    "hsgpu_pairs_destroy", "hsgpu_edlib_align_batch",
 ]
+PAIRS_DENSE, PAIRS_KEEP_ORDER, PAIRS_SIMT = 1, 2, 4
 
 
 def load():
@@ -120,6 +122,12 @@ def load():
     L.hsgpu_partition_tables.argtypes = [vp, i32, C.POINTER(Partitions), i32, vp, vp]
     L.hsgpu_robust_filter.argtypes = [vp, i32, C.POINTER(Partitions), i32, vp, i32, vp, vp]
     L.hsgpu_read_pair_counts.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.hsgpu_pairs_create.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, C.POINTER(vp)]
+    L.hsgpu_pairs_compute.argtypes = [vp]
+    L.hsgpu_pairs_fetch.argtypes = [vp, i32, vp, vp]
+    L.hsgpu_pairs_info.argtypes = [vp, vp]
+    L.hsgpu_pairs_destroy.argtypes = [vp]
+    L.hsgpu_pairs_destroy.restype = None
     L.hsgpu_edlib_align_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, i64]
     for name in ("hsgpu_debug_rank_column", "hsgpu_debug_rh_order", "hsgpu_debug_sort_desc"):
         getattr(L, name).restype = C.c_int if name == "hsgpu_debug_rh_order" else None
@@ -335,6 +343,59 @@ class Context:
                                                     starts.ctypes.data, loc_cap, aln.ctypes.data, aln_cap),
                    "hsgpu_edlib_align_batch")
         return res, ends, starts, aln
+
+
+class Pairs:
+    """hsgpu_pairs: read x read SNP agreement counts of a batch of contigs, operands and results on the device.
+    contigs: list of (n_reads, snp_off, read_idx, code, ref_base, second_base) with contig-local read indices."""
+
+    def __init__(self, ctx: Context, contigs, flags=0):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.n_reads = _a([c[0] for c in contigs], np.int32)
+        n_snps = [int(np.asarray(c[1]).shape[0]) - 1 for c in contigs]
+        self.snp_base = np.zeros(len(contigs) + 1, np.int64)
+        self.snp_base[1:] = np.cumsum(n_snps)
+        offs, cell0 = [np.zeros(1, np.int64)], 0
+        for c in contigs:
+            so = _a(c[1], np.int64)
+            offs.append(so[1:] - so[0] + cell0)
+            cell0 += int(so[-1] - so[0])
+        self.snp_off = np.concatenate(offs)
+        cat = lambda k, dt: (np.concatenate([_a(c[k], dt) for c in contigs]) if contigs else np.zeros(0, dt))
+        self.read_idx, self.code = cat(2, np.uint32), cat(3, np.uint8)
+        self.ref_base, self.second_base = cat(4, np.uint8), cat(5, np.uint8)
+        h = C.c_void_p()
+        ctx.check(self.lib.hsgpu_pairs_create(ctx.h, len(contigs), self.n_reads.ctypes.data, self.snp_base.ctypes.data,
+                                              self.snp_off.ctypes.data, self.read_idx.ctypes.data, self.code.ctypes.data,
+                                              self.ref_base.ctypes.data, self.second_base.ctypes.data, flags, C.byref(h)),
+                  "hsgpu_pairs_create")
+        self.h = h
+
+    def compute(self):
+        self.ctx.check(self.lib.hsgpu_pairs_compute(self.h), "hsgpu_pairs_compute")
+
+    def fetch(self, contig):
+        n = int(self.n_reads[contig])
+        sim, diff = np.zeros((n, n), np.int32), np.zeros((n, n), np.int32)
+        self.ctx.check(self.lib.hsgpu_pairs_fetch(self.h, contig, sim.ctypes.data, diff.ctypes.data), "hsgpu_pairs_fetch")
+        return sim, diff
+
+    def info(self):
+        v = np.zeros(8, np.int64)
+        self.ctx.check(self.lib.hsgpu_pairs_info(self.h, v.ctypes.data), "hsgpu_pairs_info")
+        return dict(zip(("tile_pairs", "tile_pairs_dense", "kblocks", "kblocks_dense", "rows", "k_ld", "out_elems",
+                         "identity"), (int(x) for x in v)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hsgpu_pairs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Pileup:

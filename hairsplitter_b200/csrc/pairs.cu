@@ -4,175 +4,706 @@
 //   A[r,s] = 1 iff read r carries second_base at SNP s, R[r,s] = 1 iff it carries ref_base (:384-394)
 //   similarity = 3*A*At + R*Rt,   difference = A*Rt + R*At,   diagonals zeroed (:414-432)
 //
-// Both products share the left operand U = [A | R] (n x 2S, int8, K-contiguous):
-//   similarity = U * [3A | R]^T,   difference = U * [R | A]^T
-// so one kernel streams U once and feeds two int8 IMMA accumulators (mma.sync.m16n8k32.s8, exact
-// int32 accumulation), one 128x128 output tile of each matrix per CTA.
+// B200 formulation. A and R are two K-major u8 matrices in HBM (one row per read, one byte per SNP), all
+// contigs of a batch stacked, every contig padded to whole 128-row tiles. One work item = one pair of
+// row tiles (i <= j) of one contig and the range of 128-SNP blocks in which both tiles have cells. A
+// persistent, warp-specialised CTA per SM walks its share of the work list:
+//   warp 0   TMA producer: four 128 x 128-byte boxes per stage (A_i, R_i, A_j, R_j; 128-byte swizzle)
+//            through a 3-stage mbarrier ring -- the minimum bytes per SNP block, each tile loaded once;
+//   warp 1   tcgen05.mma.kind::i8 issuer (one lane). Accumulators in TMEM, 384 columns:
+//              [0,128)   = A_i * A_j^T      [128,256) = A_i * R_j^T + R_i * A_j^T      [256,384) = R_i * R_j^T
+//            two M128 x N256 x K32 instructions per 32 SNPs: A_i x [A_j;R_j] lands on columns 0..255,
+//            R_i x [A_j;R_j] on columns 128..383, so the middle block accumulates both cross products;
+//   warps 2-5 epilogue: tcgen05.ld the three blocks, sim = 3*acc0 + acc2, diff = acc1, zero the
+//            diagonal, store tile (i,j) row-wise and, by symmetry, tile (j,i) column-wise (coalesced).
+// Reads are ordered by their first SNP before tiling (the output is written back through the
+// permutation), so tiles far from the diagonal share no SNP block and are never scheduled: the work is
+// the band of overlapping reads, not R^2 * S.
+#include <cuda.h>  // CUtensorMap and its enums only; the encoder is fetched from the driver at run time
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
 #include "common.cuh"
 
-#define PG_BM 128
-#define PG_BN 128
-#define PG_BK 64
-#define PG_LD 80  // padded row stride in bytes (20 words: conflict-free fragment loads)
+#define PG_TILE 128                     // rows per tile (UMMA M, and N per operand half)
+#define PG_BK 128                       // SNPs (= bytes of K) per pipeline stage: one 128-byte swizzle row
+#define PG_SUB (PG_TILE * PG_BK)        // one operand sub-tile: 16 KB
+#define PG_STAGE_BYTES (4 * PG_SUB)     // A_i, R_i, A_j, R_j
+#define PG_STAGES 3
+#define PG_THREADS 192
+#define PG_TMEM_COLS 512
+#define PG_SMEM (PG_STAGES * PG_STAGE_BYTES + 1024 + 256)
 
-__global__ void onehot_kernel(int n_snps, const int64_t* __restrict__ snp_off, const uint32_t* __restrict__ read_idx,
-                              const uint8_t* __restrict__ code, const uint8_t* __restrict__ ref_base,
-                              const uint8_t* __restrict__ second_base, int s_pad, int64_t ld, int8_t* __restrict__ U,
-                              int8_t* __restrict__ Vs, int8_t* __restrict__ Vd) {
-    const int s = blockIdx.x;
-    if (s >= n_snps) return;
+struct PairWork {
+    int32_t contig;
+    int32_t ti, tj;    // row tiles within the contig, ti <= tj
+    int32_t kb0, kb1;  // SNP blocks [kb0, kb1)
+};
+
+struct PairContig {
+    int64_t row0;     // first row of the contig in the stacked operand matrices
+    int64_t out_off;  // element offset of the contig's n_pad x n_pad block in sim / diff
+    int32_t n, n_pad;
+    int32_t identity;  // reads already in first-SNP order: rows map to themselves
+    int32_t pad;
+};
+
+struct hsgpu_pairs {
+    hsgpu_ctx* ctx = nullptr;
+    int32_t n_contigs = 0;
+    int32_t flags = 0;
+    int64_t total_rows = 0, k_ld = 0, n_cells = 0, out_elems = 0, n_work = 0;
+    int64_t kblocks_listed = 0, kblocks_dense = 0, tiles_dense = 0;
+    std::vector<PairContig> h_contigs;
+    uint8_t *d_A = nullptr, *d_R = nullptr;
+    int32_t* d_rowmap = nullptr;   // stacked row -> read index in the contig (-1 = padding)
+    int32_t* d_rowof = nullptr;    // per contig-local read: stacked row (inverse map, for the one-hot scatter)
+    PairContig* d_contigs = nullptr;
+    PairWork* d_work = nullptr;
+    int32_t *d_sim = nullptr, *d_diff = nullptr;
+    int32_t* d_err = nullptr;
+    // the SNP columns (inputs), kept until the operands are built
+    int64_t *d_snp_off = nullptr, *d_snp_base = nullptr;
+    uint32_t* d_read_idx = nullptr;
+    uint8_t *d_code = nullptr, *d_rb = nullptr, *d_sb = nullptr;
+    int32_t* d_snp_contig = nullptr;
+    int64_t total_snps = 0;
+    CUtensorMap tmapA, tmapR;
+    bool computed = false;
+};
+
+// ---- operand construction ---------------------------------------------------------------------------------
+__global__ void onehot_kernel(int64_t total_snps, const int32_t* __restrict__ snp_contig,
+                              const int64_t* __restrict__ snp_base, const int64_t* __restrict__ snp_off,
+                              const uint32_t* __restrict__ read_idx, const uint8_t* __restrict__ code,
+                              const uint8_t* __restrict__ ref_base, const uint8_t* __restrict__ second_base,
+                              const int64_t* __restrict__ read_base, const int32_t* __restrict__ rowof, int64_t ld,
+                              uint8_t* __restrict__ A, uint8_t* __restrict__ R) {
+    const int64_t s = blockIdx.x;
+    if (s >= total_snps) return;
+    const int c = snp_contig[s];
+    const int64_t k = s - snp_base[c];  // SNP index within its contig = byte of K
     const int rb = ref_base[s], sb = second_base[s];
+    const int64_t rb0 = read_base[c];
     for (int64_t i = snp_off[s] + threadIdx.x; i < snp_off[s + 1]; i += blockDim.x) {
-        const int64_t r = read_idx[i];
-        const int c = code[i];
-        if (c == rb) {  // ref is tested first (:386)
-            U[r * ld + s_pad + s] = 1;
-            Vs[r * ld + s_pad + s] = 1;
-            Vd[r * ld + s] = 1;
-        } else if (c == sb) {
-            U[r * ld + s] = 1;
-            Vs[r * ld + s] = 3;
-            Vd[r * ld + s_pad + s] = 1;
-        }
+        const int64_t row = rowof[rb0 + read_idx[i]];
+        const int cd = code[i];
+        if (cd == rb) R[row * ld + k] = 1;  // ref is tested first (:386)
+        else if (cd == sb) A[row * ld + k] = 1;
     }
 }
 
-__device__ __forceinline__ void mma_s8(int (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pg_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pg_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pg_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pg_smem(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
-        "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(pg_smem(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// a wait that cannot hang the device: after ~4 s of spinning the kernel reports and traps
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int32_t* err, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000ll) {
+            atomicExch(err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(pg_smem(dst)), "l"(tmap), "r"(pg_smem(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address
+    d |= (uint64_t)1 << 16;                    // leading byte offset (not used by swizzled K-major layouts)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset
+    d |= (uint64_t)1 << 46;                    // descriptor version of sm_100
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor for kind::i8: u8 x u8 -> s32, both operands K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+    return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(PG_TILE >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(pg_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
 }
 
-// C tiles: sim[bm.., bn..] and diff[bm.., bn..]; 8 warps as 4 (m) x 2 (n), warp tile 32 x 64
-__global__ void __launch_bounds__(256) pair_gemm_kernel(int n, int64_t ld, int K, const int8_t* __restrict__ U,
-                                                        const int8_t* __restrict__ Vs, const int8_t* __restrict__ Vd,
-                                                        int32_t* __restrict__ sim, int32_t* __restrict__ diff) {
-    __shared__ __align__(16) unsigned char sU[PG_BM * PG_LD];
-    __shared__ __align__(16) unsigned char sS[PG_BN * PG_LD];
-    __shared__ __align__(16) unsigned char sD[PG_BN * PG_LD];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int wm = wid & 3, wn = wid >> 2;
-    const int g = lane >> 2, t = lane & 3;
-    const int bm = blockIdx.y * PG_BM, bn = blockIdx.x * PG_BN;
-    int accS[2][8][4], accD[2][8][4];
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) accS[i][j][k] = accD[i][j][k] = 0;
+// ---- the contraction ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PG_THREADS, 1)
+pair_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapR,
+                 const PairWork* __restrict__ work, int n_work, const PairContig* __restrict__ contigs,
+                 const int32_t* __restrict__ rowmap, int32_t* __restrict__ sim, int32_t* __restrict__ diff,
+                 int32_t* __restrict__ err) {
+    extern __shared__ unsigned char pg_raw[];
+    // 1024-byte alignment: the swizzle pattern is a function of the shared-memory address
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pg_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PG_STAGES * PG_STAGE_BYTES);
+    uint64_t* full = bars;                   // [PG_STAGES] TMA -> MMA
+    uint64_t* empty = bars + PG_STAGES;      // [PG_STAGES] MMA -> TMA
+    uint64_t* acc_full = bars + 2 * PG_STAGES;   // MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 1;          // epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    __shared__ int32_t s_colmap[PG_TILE];
 
-    for (int k0 = 0; k0 < K; k0 += PG_BK) {
-        __syncthreads();
-        // 128 rows x 64 bytes = 512 uint4 per operand; 256 threads -> 2 each
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int v = tid + 256 * i;
-            const int row = v >> 2, part = v & 3;
-            const uint4 u = *reinterpret_cast<const uint4*>(U + (int64_t)(bm + row) * ld + k0 + 16 * part);
-            const uint4 s = *reinterpret_cast<const uint4*>(Vs + (int64_t)(bn + row) * ld + k0 + 16 * part);
-            const uint4 d = *reinterpret_cast<const uint4*>(Vd + (int64_t)(bn + row) * ld + k0 + 16 * part);
-            *reinterpret_cast<uint4*>(sU + row * PG_LD + 16 * part) = u;
-            *reinterpret_cast<uint4*>(sS + row * PG_LD + 16 * part) = s;
-            *reinterpret_cast<uint4*>(sD + row * PG_LD + 16 * part) = d;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PG_STAGES; s++) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
         }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < PG_BK; kk += 32) {
-            uint32_t af[2][4];
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const unsigned char* base = sU + (wm * 32 + i * 16 + g) * PG_LD + kk + 4 * t;
-                af[i][0] = *reinterpret_cast<const uint32_t*>(base);
-                af[i][1] = *reinterpret_cast<const uint32_t*>(base + 8 * PG_LD);
-                af[i][2] = *reinterpret_cast<const uint32_t*>(base + 16);
-                af[i][3] = *reinterpret_cast<const uint32_t*>(base + 8 * PG_LD + 16);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int off = (wn * 64 + j * 8 + g) * PG_LD + kk + 4 * t;
-                uint32_t bs[2], bd[2];
-                bs[0] = *reinterpret_cast<const uint32_t*>(sS + off);
-                bs[1] = *reinterpret_cast<const uint32_t*>(sS + off + 16);
-                bd[0] = *reinterpret_cast<const uint32_t*>(sD + off);
-                bd[1] = *reinterpret_cast<const uint32_t*>(sD + off + 16);
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    mma_s8(accS[i][j], af[i], bs);
-                    mma_s8(accD[i][j], af[i], bd);
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pg_smem(tmem_slot)),
+                     "r"(PG_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const PairWork wk = work[w];
+                const int row_i = (int)(contigs[wk.contig].row0) + wk.ti * PG_TILE;
+                const int row_j = (int)(contigs[wk.contig].row0) + wk.tj * PG_TILE;
+                for (int kb = wk.kb0; kb < wk.kb1; kb++) {
+                    mbar_wait(empty + stage, phase ^ 1, err, 1);
+                    mbar_arrive_expect_tx(full + stage, PG_STAGE_BYTES);
+                    unsigned char* st = smem + stage * PG_STAGE_BYTES;
+                    tma_load_2d(st + 0 * PG_SUB, &tmapA, full + stage, kb * PG_BK, row_i);
+                    tma_load_2d(st + 1 * PG_SUB, &tmapR, full + stage, kb * PG_BK, row_i);
+                    tma_load_2d(st + 2 * PG_SUB, &tmapA, full + stage, kb * PG_BK, row_j);
+                    tma_load_2d(st + 3 * PG_SUB, &tmapR, full + stage, kb * PG_BK, row_j);
+                    if (++stage == PG_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
-    }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            constexpr uint32_t idesc256 = umma_idesc(256), idesc128 = umma_idesc(128);
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const PairWork wk = work[w];
+                mbar_wait(acc_empty, acc_phase ^ 1, err, 2);  // the epilogue has drained the previous tile
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = wk.kb0; kb < wk.kb1; kb++) {
+                    mbar_wait(full + stage, phase, err, 3);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = pg_smem(smem + stage * PG_STAGE_BYTES);
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+                    for (int k = 0; k < PG_BK / 32; k++) {
+                        const uint64_t dAi = umma_desc(st + 0 * PG_SUB + 32 * k);
+                        const uint64_t dRi = umma_desc(st + 1 * PG_SUB + 32 * k);
+                        const uint64_t dAj = umma_desc(st + 2 * PG_SUB + 32 * k);  // N = 256 runs on into R_j
+                        const uint64_t dRj = umma_desc(st + 3 * PG_SUB + 32 * k);
+                        if (kb == wk.kb0 && k == 0) {
+                            umma_i8(tmem + 0, dAi, dAj, idesc256, 0);    // acc0 = Ai Aj^T, acc1 = Ai Rj^T
+                            umma_i8(tmem + 128, dRi, dAj, idesc128, 1);  // acc1 += Ri Aj^T
+                            umma_i8(tmem + 256, dRi, dRj, idesc128, 0);  // acc2 = Ri Rj^T
+                        } else {
+                            umma_i8(tmem + 0, dAi, dAj, idesc256, 1);
+                            umma_i8(tmem + 128, dRi, dAj, idesc256, 1);
+                        }
+                    }
+                    umma_commit(empty + stage);  // frees the stage once these MMAs have read it
+                    if (++stage == PG_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(acc_full);
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps, warp (w % 4) owns TMEM lanes 32*(w % 4) .. +31 =====
+        const int quarter = warp & 3;
+        const int t = quarter * 32 + lane;  // row of the tile
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const PairWork wk = work[w];
+            const PairContig pc = contigs[wk.contig];
+            const int64_t ld = pc.n_pad;
+            int orow, ocol_t;
+            if (pc.identity) {
+                orow = wk.ti * PG_TILE + t;
+                ocol_t = wk.tj * PG_TILE + t;
+            } else {
+                orow = rowmap[pc.row0 + wk.ti * PG_TILE + t];
+                ocol_t = rowmap[pc.row0 + wk.tj * PG_TILE + t];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with the previous tile's map
+            s_colmap[t] = ocol_t;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(acc_full, acc_phase, err, 4);
+            acc_phase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int32_t* const sim_c = sim + pc.out_off;
+            int32_t* const diff_c = diff + pc.out_off;
+            const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int cb = 0; cb < 4; cb++) {
+                uint32_t v0[32], v1[32], v2[32];
+                tmem_ld32(lane_addr + cb * 32, v0);
+                tmem_ld32(lane_addr + 128 + cb * 32, v1);
+                tmem_ld32(lane_addr + 256 + cb * 32, v2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cb == 3) {
+                    // the accumulators are in registers: hand TMEM back before the stores
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                }
 #pragma unroll
-        for (int j = 0; j < 8; j++)
+                for (int c = 0; c < 32; c++) {
+                    const int oc = s_colmap[cb * 32 + c];
+                    const bool dead = (oc == orow);  // :417-432
+                    v0[c] = dead ? 0u : 3u * v0[c] + v2[c];
+                    v1[c] = dead ? 0u : v1[c];
+                }
+                if (pc.identity) {
+                    // rows of the padded output exist up to n_pad: no bounds to check
+                    int4* ps = reinterpret_cast<int4*>(sim_c + (int64_t)orow * ld + wk.tj * PG_TILE + cb * 32);
+                    int4* pd = reinterpret_cast<int4*>(diff_c + (int64_t)orow * ld + wk.tj * PG_TILE + cb * 32);
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int row = bm + wm * 32 + i * 16 + g + 8 * h;
-                const int col = bn + wn * 64 + j * 8 + 2 * t;
-                if (row < n) {
+                    for (int c = 0; c < 8; c++) {
+                        ps[c] = make_int4((int)v0[4 * c], (int)v0[4 * c + 1], (int)v0[4 * c + 2], (int)v0[4 * c + 3]);
+                        pd[c] = make_int4((int)v1[4 * c], (int)v1[4 * c + 1], (int)v1[4 * c + 2], (int)v1[4 * c + 3]);
+                    }
+                    if (wk.ti != wk.tj) {
 #pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        if (col + e < n) {
-                            const bool diag = row == col + e;  // :417-432
-                            sim[(int64_t)row * n + col + e] = diag ? 0 : accS[i][j][2 * h + e];
-                            diff[(int64_t)row * n + col + e] = diag ? 0 : accD[i][j][2 * h + e];
+                        for (int c = 0; c < 32; c++) {
+                            const int64_t o = (int64_t)(wk.tj * PG_TILE + cb * 32 + c) * ld + orow;
+                            sim_c[o] = (int)v0[c];
+                            diff_c[o] = (int)v1[c];
+                        }
+                    }
+                } else if (orow >= 0) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const int oc = s_colmap[cb * 32 + c];
+                        if (oc >= 0) {
+                            sim_c[(int64_t)orow * ld + oc] = (int)v0[c];
+                            diff_c[(int64_t)orow * ld + oc] = (int)v1[c];
+                            if (wk.ti != wk.tj) {
+                                sim_c[(int64_t)oc * ld + orow] = (int)v0[c];
+                                diff_c[(int64_t)oc * ld + orow] = (int)v1[c];
+                            }
                         }
                     }
                 }
             }
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(PG_TMEM_COLS) : "memory");
+    }
 }
 
-extern "C" int hsgpu_read_pair_counts(hsgpu_ctx* ctx, int32_t n_reads, int32_t n_snps, const int64_t* snp_off,
-                                      const uint32_t* read_idx, const uint8_t* code, const uint8_t* ref_base,
-                                      const uint8_t* second_base, int32_t* sim, int32_t* diff) {
-    if (!ctx || n_reads < 0 || n_snps < 0 || !sim || !diff) return HSGPU_ERR_ARG;
-    if (n_reads == 0) return HSGPU_OK;
-    if (n_reads > 46000) HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_read_pair_counts: dense n x n output limited to 46000 reads");
-    HS_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int64_t n_cells = n_snps > 0 ? snp_off[n_snps] : 0;
-    for (int64_t i = 0; i < n_cells; i++)
-        if (read_idx[i] >= (uint32_t)n_reads) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_read_pair_counts: read index out of range");
-    const int n_pad = (n_reads + PG_BM - 1) / PG_BM * PG_BM;
-    const int s_pad = (n_snps + 31) / 32 * 32;
-    const int K = 2 * s_pad;
-    const int64_t ld = K > 0 ? K : 64;
-    int8_t *U = nullptr, *Vs = nullptr, *Vd = nullptr;
-    int32_t *d_sim = nullptr, *d_diff = nullptr;
-    int64_t* d_off = nullptr;
-    uint32_t* d_idx = nullptr;
-    uint8_t *d_code = nullptr, *d_rb = nullptr, *d_sb = nullptr;
-    const int64_t opbytes = (int64_t)n_pad * ld;
-    HS_CUDA(ctx, hs_alloc(ctx, &U, opbytes));
-    HS_CUDA(ctx, hs_alloc(ctx, &Vs, opbytes));
-    HS_CUDA(ctx, hs_alloc(ctx, &Vd, opbytes));
-    HS_CUDA(ctx, hs_alloc(ctx, &d_sim, (int64_t)n_reads * n_reads));
-    HS_CUDA(ctx, hs_alloc(ctx, &d_diff, (int64_t)n_reads * n_reads));
-    HS_CUDA(ctx, cudaMemsetAsync(U, 0, opbytes, ctx->stream));
-    HS_CUDA(ctx, cudaMemsetAsync(Vs, 0, opbytes, ctx->stream));
-    HS_CUDA(ctx, cudaMemsetAsync(Vd, 0, opbytes, ctx->stream));
-    if (n_snps > 0) {
-        HS_CUDA(ctx, hs_alloc(ctx, &d_off, n_snps + 1));
-        HS_CUDA(ctx, hs_alloc(ctx, &d_idx, n_cells));
-        HS_CUDA(ctx, hs_alloc(ctx, &d_code, n_cells));
-        HS_CUDA(ctx, hs_alloc(ctx, &d_rb, n_snps));
-        HS_CUDA(ctx, hs_alloc(ctx, &d_sb, n_snps));
-        HS_CUDA(ctx, hs_h2d(ctx, d_off, snp_off, n_snps + 1));
-        HS_CUDA(ctx, hs_h2d(ctx, d_idx, read_idx, n_cells));
-        HS_CUDA(ctx, hs_h2d(ctx, d_code, code, n_cells));
-        HS_CUDA(ctx, hs_h2d(ctx, d_rb, ref_base, n_snps));
-        HS_CUDA(ctx, hs_h2d(ctx, d_sb, second_base, n_snps));
-        HS_KERNEL(ctx, "onehot_kernel", onehot_kernel<<<n_snps, 128, 0, ctx->stream>>>(n_snps, d_off, d_idx, d_code, d_rb, d_sb, s_pad, ld, U, Vs, Vd));
+// Plain SIMT statement of the same contraction over the same operands (dp4a, one thread per output
+// element). Only reachable with HSGPU_PAIRS_SIMT: the A/B check of the tensor-core kernel in the tests.
+__global__ void __launch_bounds__(256) pair_simt_kernel(const PairContig* __restrict__ contigs, int contig, int64_t ld_k,
+                                                        const uint8_t* __restrict__ A, const uint8_t* __restrict__ R,
+                                                        const int32_t* __restrict__ rowmap, int32_t* __restrict__ sim,
+                                                        int32_t* __restrict__ diff) {
+    const PairContig pc = contigs[contig];
+    const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+    if (i >= pc.n_pad || j >= pc.n_pad) return;
+    const int oi = rowmap[pc.row0 + i], oj = rowmap[pc.row0 + j];
+    if (oi < 0 || oj < 0) return;
+    const uint32_t* ai = reinterpret_cast<const uint32_t*>(A + (pc.row0 + i) * ld_k);
+    const uint32_t* ri = reinterpret_cast<const uint32_t*>(R + (pc.row0 + i) * ld_k);
+    const uint32_t* aj = reinterpret_cast<const uint32_t*>(A + (pc.row0 + j) * ld_k);
+    const uint32_t* rj = reinterpret_cast<const uint32_t*>(R + (pc.row0 + j) * ld_k);
+    unsigned aa = 0, rr = 0, x = 0;
+    for (int64_t k = 0; k < ld_k / 4; k++) {
+        const uint32_t a0 = ai[k], r0 = ri[k], a1 = aj[k], r1 = rj[k];
+        aa = __dp4a(a0, a1, aa);
+        rr = __dp4a(r0, r1, rr);
+        x = __dp4a(a0, r1, x);
+        x = __dp4a(r0, a1, x);
     }
-    dim3 grid(n_pad / PG_BN, n_pad / PG_BM);
-    HS_KERNEL(ctx, "pair_gemm_kernel", pair_gemm_kernel<<<grid, 256, 0, ctx->stream>>>(n_reads, ld, K, U, Vs, Vd, d_sim, d_diff));
-    HS_CUDA(ctx, hs_d2h(ctx, sim, d_sim, (int64_t)n_reads * n_reads));
-    HS_CUDA(ctx, hs_d2h(ctx, diff, d_diff, (int64_t)n_reads * n_reads));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    hs_free(ctx, U); hs_free(ctx, Vs); hs_free(ctx, Vd); hs_free(ctx, d_sim); hs_free(ctx, d_diff);
-    hs_free(ctx, d_off); hs_free(ctx, d_idx); hs_free(ctx, d_code); hs_free(ctx, d_rb); hs_free(ctx, d_sb);
+    const bool dead = oi == oj;
+    sim[pc.out_off + (int64_t)oi * pc.n_pad + oj] = dead ? 0 : (int)(3 * aa + rr);
+    diff[pc.out_off + (int64_t)oi * pc.n_pad + oj] = dead ? 0 : (int)x;
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+typedef CUresult (*PgEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int pg_make_tmap(hsgpu_ctx* ctx, CUtensorMap* tm, void* base, int64_t k_ld, int64_t rows) {
+    static PgEncodeTiled enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        HS_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess)
+            HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu_pairs: the driver does not export cuTensorMapEncodeTiled");
+        enc = (PgEncodeTiled)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)k_ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)k_ld};
+    const cuuint32_t box[2] = {PG_BK, PG_TILE};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[128];
+        snprintf(buf, sizeof(buf), "hsgpu_pairs: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        HS_FAIL(ctx, HSGPU_ERR_CUDA, buf);
+    }
     return HSGPU_OK;
 }
+
+extern "C" {
+
+void hsgpu_pairs_destroy(hsgpu_pairs* h) {
+    if (!h) return;
+    hsgpu_ctx* ctx = h->ctx;
+    cudaSetDevice(ctx->device);
+    hs_free(ctx, h->d_A); hs_free(ctx, h->d_R); hs_free(ctx, h->d_rowmap); hs_free(ctx, h->d_rowof);
+    hs_free(ctx, h->d_contigs); hs_free(ctx, h->d_work); hs_free(ctx, h->d_sim); hs_free(ctx, h->d_diff);
+    hs_free(ctx, h->d_err); hs_free(ctx, h->d_snp_off); hs_free(ctx, h->d_snp_base); hs_free(ctx, h->d_read_idx);
+    hs_free(ctx, h->d_code); hs_free(ctx, h->d_rb); hs_free(ctx, h->d_sb); hs_free(ctx, h->d_snp_contig);
+    cudaStreamSynchronize(ctx->stream);
+    delete h;
+}
+
+int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads, const int64_t* snp_base,
+                       const int64_t* snp_off, const uint32_t* read_idx, const uint8_t* code, const uint8_t* ref_base,
+                       const uint8_t* second_base, int32_t flags, hsgpu_pairs** out) {
+    if (!ctx || !out || n_contigs < 0 || (n_contigs > 0 && (!n_reads || !snp_base))) return HSGPU_ERR_ARG;
+    *out = nullptr;
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t total_snps = n_contigs > 0 ? snp_base[n_contigs] : 0;
+    if (total_snps > 0 && (!snp_off || !ref_base || !second_base)) return HSGPU_ERR_ARG;
+    const int64_t n_cells = total_snps > 0 ? snp_off[total_snps] : 0;
+    if (n_cells > 0 && (!read_idx || !code)) return HSGPU_ERR_ARG;
+    const bool dense = (flags & HSGPU_PAIRS_DENSE) != 0, keep_order = (flags & HSGPU_PAIRS_KEEP_ORDER) != 0;
+
+    hsgpu_pairs* h = new hsgpu_pairs();
+    h->ctx = ctx;
+    h->n_contigs = n_contigs;
+    h->flags = flags;
+    h->total_snps = total_snps;
+    h->n_cells = n_cells;
+    h->h_contigs.resize(n_contigs);
+    std::vector<int64_t> read_base(n_contigs + 1, 0);
+    int64_t max_snps = 0, rows = 0, out_elems = 0;
+    for (int c = 0; c < n_contigs; c++) {
+        if (n_reads[c] < 0 || snp_base[c + 1] < snp_base[c]) {
+            delete h;
+            HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pairs_create: negative read or SNP count");
+        }
+        if (n_reads[c] > 46000) {
+            delete h;
+            HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_pairs_create: dense n x n output limited to 46000 reads per contig");
+        }
+        read_base[c + 1] = read_base[c] + n_reads[c];
+        max_snps = std::max(max_snps, snp_base[c + 1] - snp_base[c]);
+        PairContig& pc = h->h_contigs[c];
+        pc.n = n_reads[c];
+        pc.n_pad = (n_reads[c] + PG_TILE - 1) / PG_TILE * PG_TILE;
+        pc.row0 = rows;
+        pc.out_off = out_elems;
+        pc.identity = 1;
+        pc.pad = 0;
+        rows += pc.n_pad;
+        out_elems += (int64_t)pc.n_pad * pc.n_pad;
+    }
+    if (rows >= (int64_t)1 << 31) {
+        delete h;
+        HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_pairs_create: more than 2^31 operand rows in one batch");
+    }
+    h->total_rows = rows;
+    h->out_elems = out_elems;
+    h->k_ld = std::max<int64_t>(PG_BK, (max_snps + PG_BK - 1) / PG_BK * PG_BK);
+    const int64_t total_reads = read_base[n_contigs];
+
+    // first / last SNP of every read (contig-local SNP indices), then the row order: by first SNP
+    std::vector<int32_t> first(total_reads, INT32_MAX), last(total_reads, -1), snp_contig(total_snps);
+    for (int c = 0; c < n_contigs; c++) {
+        for (int64_t s = snp_base[c]; s < snp_base[c + 1]; s++) {
+            snp_contig[s] = c;
+            const int32_t k = (int32_t)(s - snp_base[c]);
+            if (snp_off[s + 1] < snp_off[s]) {
+                delete h;
+                HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pairs_create: snp_off is not ascending");
+            }
+            for (int64_t i = snp_off[s]; i < snp_off[s + 1]; i++) {
+                if (read_idx[i] >= (uint32_t)n_reads[c]) {
+                    delete h;
+                    HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pairs_create: read index out of range");
+                }
+                const int64_t r = read_base[c] + read_idx[i];
+                if (first[r] == INT32_MAX) first[r] = k;
+                last[r] = k;  // SNPs are visited in ascending order
+            }
+        }
+    }
+    std::vector<int32_t> rowmap(rows, -1), rowof(std::max<int64_t>(total_reads, 1), 0);
+    std::vector<PairWork> work;
+    int64_t kb_listed = 0, kb_dense = 0, tiles_dense = 0;
+    for (int c = 0; c < n_contigs; c++) {
+        PairContig& pc = h->h_contigs[c];
+        const int64_t rb0 = read_base[c];
+        std::vector<int32_t> order(pc.n);
+        std::iota(order.begin(), order.end(), 0);
+        if (!keep_order) {
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return first[rb0 + a] < first[rb0 + b]; });
+            for (int32_t r = 0; r < pc.n; r++)
+                if (order[r] != r) {
+                    pc.identity = 0;
+                    break;
+                }
+        }
+        for (int32_t r = 0; r < pc.n; r++) {
+            rowmap[pc.row0 + r] = order[r];
+            rowof[rb0 + order[r]] = (int32_t)(pc.row0 + r);
+        }
+        const int nt = pc.n_pad / PG_TILE;
+        const int nkb = (int)((snp_base[c + 1] - snp_base[c] + PG_BK - 1) / PG_BK);
+        std::vector<int32_t> klo(nt, INT32_MAX), khi(nt, 0);
+        for (int32_t r = 0; r < pc.n; r++) {
+            const int64_t g = rb0 + order[r];
+            if (last[g] < 0) continue;
+            klo[r / PG_TILE] = std::min(klo[r / PG_TILE], first[g] / PG_BK);
+            khi[r / PG_TILE] = std::max(khi[r / PG_TILE], last[g] / PG_BK + 1);
+        }
+        for (int i = 0; i < nt; i++)
+            for (int j = i; j < nt; j++) {
+                tiles_dense++;
+                kb_dense += nkb;
+                int k0 = dense ? 0 : std::max(klo[i], klo[j]);
+                int k1 = dense ? nkb : std::min(khi[i], khi[j]);
+                if (k0 >= k1) continue;
+                work.push_back(PairWork{c, i, j, k0, k1});
+                kb_listed += k1 - k0;
+            }
+    }
+    // longest items first: the static round-robin over the persistent CTAs then ends evenly
+    std::stable_sort(work.begin(), work.end(), [](const PairWork& a, const PairWork& b) { return a.kb1 - a.kb0 > b.kb1 - b.kb0; });
+    h->n_work = (int64_t)work.size();
+    h->kblocks_listed = kb_listed;
+    h->kblocks_dense = kb_dense;
+    h->tiles_dense = tiles_dense;
+
+#define PG_TRY(call)                                                               \
+    do {                                                                           \
+        cudaError_t _e = (call);                                                   \
+        if (_e != cudaSuccess) {                                                   \
+            hsgpu_pairs_destroy(h);                                                \
+            return hs_cuda_fail(ctx, _e, #call, __FILE__, __LINE__);               \
+        }                                                                          \
+    } while (0)
+    PG_TRY(hs_alloc(ctx, &h->d_A, rows * h->k_ld));
+    PG_TRY(hs_alloc(ctx, &h->d_R, rows * h->k_ld));
+    PG_TRY(hs_alloc(ctx, &h->d_rowmap, rows));
+    PG_TRY(hs_alloc(ctx, &h->d_rowof, total_reads));
+    PG_TRY(hs_alloc(ctx, &h->d_contigs, n_contigs));
+    PG_TRY(hs_alloc(ctx, &h->d_work, h->n_work));
+    PG_TRY(hs_alloc(ctx, &h->d_sim, out_elems));
+    PG_TRY(hs_alloc(ctx, &h->d_diff, out_elems));
+    PG_TRY(hs_alloc(ctx, &h->d_err, 1));
+    PG_TRY(hs_alloc(ctx, &h->d_snp_off, total_snps + 1));
+    PG_TRY(hs_alloc(ctx, &h->d_snp_base, n_contigs + 1));
+    PG_TRY(hs_alloc(ctx, &h->d_read_idx, n_cells));
+    PG_TRY(hs_alloc(ctx, &h->d_code, n_cells));
+    PG_TRY(hs_alloc(ctx, &h->d_rb, total_snps));
+    PG_TRY(hs_alloc(ctx, &h->d_sb, total_snps));
+    PG_TRY(hs_alloc(ctx, &h->d_snp_contig, total_snps));
+    int64_t* d_read_base = nullptr;
+    PG_TRY(hs_alloc(ctx, &d_read_base, n_contigs + 1));
+    PG_TRY(hs_h2d(ctx, h->d_rowmap, rowmap.data(), rows));
+    PG_TRY(hs_h2d(ctx, h->d_rowof, rowof.data(), total_reads));
+    PG_TRY(hs_h2d(ctx, h->d_contigs, h->h_contigs.data(), n_contigs));
+    PG_TRY(hs_h2d(ctx, h->d_work, work.data(), h->n_work));
+    if (total_snps > 0) PG_TRY(hs_h2d(ctx, h->d_snp_off, snp_off, total_snps + 1));
+    if (n_contigs > 0) PG_TRY(hs_h2d(ctx, h->d_snp_base, snp_base, n_contigs + 1));
+    PG_TRY(hs_h2d(ctx, h->d_read_idx, read_idx, n_cells));
+    PG_TRY(hs_h2d(ctx, h->d_code, code, n_cells));
+    PG_TRY(hs_h2d(ctx, h->d_rb, ref_base, total_snps));
+    PG_TRY(hs_h2d(ctx, h->d_sb, second_base, total_snps));
+    PG_TRY(hs_h2d(ctx, h->d_snp_contig, snp_contig.data(), total_snps));
+    PG_TRY(hs_h2d(ctx, d_read_base, read_base.data(), n_contigs + 1));
+    PG_TRY(cudaMemsetAsync(h->d_A, 0, (size_t)std::max<int64_t>(rows * h->k_ld, 1), ctx->stream));
+    PG_TRY(cudaMemsetAsync(h->d_R, 0, (size_t)std::max<int64_t>(rows * h->k_ld, 1), ctx->stream));
+    PG_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), ctx->stream));
+    if (total_snps > 0) {
+        if (ctx->profiling) hs_prof_begin(ctx, "onehot_kernel");
+        onehot_kernel<<<(unsigned)total_snps, 128, 0, ctx->stream>>>(total_snps, h->d_snp_contig, h->d_snp_base, h->d_snp_off,
+                                                                      h->d_read_idx, h->d_code, h->d_rb, h->d_sb, d_read_base,
+                                                                      h->d_rowof, h->k_ld, h->d_A, h->d_R);
+        if (ctx->profiling) hs_prof_end(ctx);
+        ctx->launches++;
+        PG_TRY(cudaGetLastError());
+    }
+    // host vectors above are pageable: the copies must have left them before we return
+    PG_TRY(cudaStreamSynchronize(ctx->stream));
+    hs_free(ctx, d_read_base);
+#undef PG_TRY
+    if (rows > 0) {
+        int rc = pg_make_tmap(ctx, &h->tmapA, h->d_A, h->k_ld, rows);
+        if (!rc) rc = pg_make_tmap(ctx, &h->tmapR, h->d_R, h->k_ld, rows);
+        if (rc) {
+            hsgpu_pairs_destroy(h);
+            return rc;
+        }
+    }
+    *out = h;
+    return HSGPU_OK;
+}
+
+int hsgpu_pairs_compute(hsgpu_pairs* h) {
+    if (!h) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = h->ctx;
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    h->computed = false;
+    if (h->out_elems > 0 && !(h->flags & HSGPU_PAIRS_DENSE)) {
+        // unscheduled tile pairs share no SNP block: their counts are zero
+        HS_CUDA(ctx, cudaMemsetAsync(h->d_sim, 0, (size_t)h->out_elems * sizeof(int32_t), ctx->stream));
+        HS_CUDA(ctx, cudaMemsetAsync(h->d_diff, 0, (size_t)h->out_elems * sizeof(int32_t), ctx->stream));
+    }
+    if (h->flags & HSGPU_PAIRS_SIMT) {
+        HS_CUDA(ctx, cudaMemsetAsync(h->d_sim, 0, (size_t)h->out_elems * sizeof(int32_t), ctx->stream));
+        HS_CUDA(ctx, cudaMemsetAsync(h->d_diff, 0, (size_t)h->out_elems * sizeof(int32_t), ctx->stream));
+        for (int c = 0; c < h->n_contigs; c++) {
+            const int np = h->h_contigs[c].n_pad;
+            if (np == 0) continue;
+            dim3 grid(np / 16, np / 16), block(16, 16);
+            HS_KERNEL(ctx, "pair_simt_kernel", pair_simt_kernel<<<grid, block, 0, ctx->stream>>>(h->d_contigs, c, h->k_ld, h->d_A, h->d_R,
+                                                                                                h->d_rowmap, h->d_sim, h->d_diff));
+        }
+    } else if (h->n_work > 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            HS_CUDA(ctx, cudaFuncSetAttribute(pair_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+            attr_set = true;
+        }
+        const int grid = (int)std::min<int64_t>(h->n_work, ctx->sm_count);
+        HS_KERNEL(ctx, "pair_umma_kernel", pair_umma_kernel<<<grid, PG_THREADS, PG_SMEM, ctx->stream>>>(
+            h->tmapA, h->tmapR, h->d_work, (int)h->n_work, h->d_contigs, h->d_rowmap, h->d_sim, h->d_diff, h->d_err));
+    }
+    h->computed = true;
+    return HSGPU_OK;
+}
+
+int hsgpu_pairs_fetch(hsgpu_pairs* h, int32_t contig, int32_t* sim, int32_t* diff) {
+    if (!h || contig < 0 || contig >= h->n_contigs) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = h->ctx;
+    if (!h->computed) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_pairs_fetch: call hsgpu_pairs_compute first");
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const PairContig& pc = h->h_contigs[contig];
+    if (pc.n > 0) {
+        const size_t w = (size_t)pc.n * sizeof(int32_t), sp = (size_t)pc.n_pad * sizeof(int32_t);
+        if (sim) HS_CUDA(ctx, cudaMemcpy2DAsync(sim, w, h->d_sim + pc.out_off, sp, w, pc.n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (diff) HS_CUDA(ctx, cudaMemcpy2DAsync(diff, w, h->d_diff + pc.out_off, sp, w, pc.n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    int32_t err = 0;
+    HS_CUDA(ctx, hs_d2h(ctx, &err, h->d_err, 1));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu_pairs: the tensor-core kernel timed out on a barrier");
+    return HSGPU_OK;
+}
+
+int hsgpu_pairs_info(hsgpu_pairs* h, int64_t* info) {
+    if (!h || !info) return HSGPU_ERR_ARG;
+    info[0] = h->n_work;          // tile pairs scheduled
+    info[1] = h->tiles_dense;     // tile pairs of the full upper triangles
+    info[2] = h->kblocks_listed;  // 128-SNP blocks executed (each = 2 x 4 MMAs of 128x256x32)
+    info[3] = h->kblocks_dense;   // the same for the full upper triangles over all SNPs
+    info[4] = h->total_rows;
+    info[5] = h->k_ld;
+    info[6] = h->out_elems;
+    int ident = 1;
+    for (const PairContig& pc : h->h_contigs) ident &= pc.identity;
+    info[7] = ident;
+    return HSGPU_OK;
+}
+
+int hsgpu_read_pair_counts(hsgpu_ctx* ctx, int32_t n_reads, int32_t n_snps, const int64_t* snp_off,
+                           const uint32_t* read_idx, const uint8_t* code, const uint8_t* ref_base,
+                           const uint8_t* second_base, int32_t* sim, int32_t* diff) {
+    if (!ctx || n_reads < 0 || n_snps < 0 || !sim || !diff) return HSGPU_ERR_ARG;
+    if (n_reads == 0) return HSGPU_OK;
+    const int64_t base[2] = {0, n_snps};
+    hsgpu_pairs* h = nullptr;
+    int rc = hsgpu_pairs_create(ctx, 1, &n_reads, base, snp_off, read_idx, code, ref_base, second_base, 0, &h);
+    if (rc) return rc;
+    rc = hsgpu_pairs_compute(h);
+    if (!rc) rc = hsgpu_pairs_fetch(h, 0, sim, diff);
+    hsgpu_pairs_destroy(h);
+    return rc;
+}
+
+}  // extern "C"

@@ -173,6 +173,29 @@ int hsgpu_read_pair_counts(hsgpu_ctx* ctx, int32_t n_reads, int32_t n_snps, cons
                            const uint32_t* read_idx, const uint8_t* code, const uint8_t* ref_base,
                            const uint8_t* second_base, int32_t* sim, int32_t* diff);
 
+/* The same contraction for a batch of contigs with the operands and results resident on the device
+ * (HS_separate_reads calls ..._reads3 once per contig inside its OpenMP loop, src/separate_reads.cpp:1507-1560;
+ * a batch is what one GPU receives from the contig sharding). SNPs of all contigs are concatenated:
+ * contig c owns SNPs [snp_base[c], snp_base[c+1]) (snp_base has n_contigs+1 entries), snp_off has one
+ * entry per SNP plus one and indexes read_idx/code; read_idx is local to the contig (< n_reads[c]).
+ * create uploads the columns and builds the one-hot operands, compute runs the tensor-core kernel
+ * (asynchronous on the context's stream, may be repeated), fetch copies one contig's n x n row-major
+ * matrices to the host and synchronises. */
+typedef struct hsgpu_pairs hsgpu_pairs;
+#define HSGPU_PAIRS_DENSE 1      /* schedule every tile pair over every SNP block (no band pruning): measurement */
+#define HSGPU_PAIRS_KEEP_ORDER 2 /* do not reorder reads by their first SNP */
+#define HSGPU_PAIRS_SIMT 4       /* plain integer-pipe kernel instead of tcgen05: the A/B check used by the tests */
+int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads, const int64_t* snp_base,
+                       const int64_t* snp_off, const uint32_t* read_idx, const uint8_t* code, const uint8_t* ref_base,
+                       const uint8_t* second_base, int32_t flags, hsgpu_pairs** out);
+int hsgpu_pairs_compute(hsgpu_pairs* h);
+int hsgpu_pairs_fetch(hsgpu_pairs* h, int32_t contig, int32_t* sim, int32_t* diff);
+/* info[8]: tile pairs scheduled, tile pairs of the full upper triangles, 128-SNP blocks executed, the
+ * same for the full triangles, operand rows, operand row stride (bytes), output elements per matrix,
+ * 1 if no contig needed reordering */
+int hsgpu_pairs_info(hsgpu_pairs* h, int64_t* info);
+void hsgpu_pairs_destroy(hsgpu_pairs* h);
+
 /* ---- realignment: edlibAlign (src/edlib/include/edlib.h:146-271, src/edlib/src/edlib.cpp:142-297)
  * Batch of (query, target) pairs, results with edlib's exact field semantics. Modes/tasks use edlib's
  * numeric values: mode 0 NW, 1 SHW, 2 HW; task 0 DISTANCE, 1 LOC, 2 PATH. */
