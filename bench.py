@@ -274,6 +274,83 @@ def run_stages(ctx, stream, chunks, args, hbm_peak):
                           "cores": 1, "kind": "reference"} if cpu_s is not None else None),
     }
     pu.close()
+
+    # ---- read x read counts: list_similarities_and_differences_between_reads3 for every chunk ----
+    # SNP columns = the suspect columns our own pipeline finds on each chunk (what the .col file hands to
+    # HS_separate_reads); all chunks go through one hsgpu_pairs batch.
+    pk = api.PackedBatch(chunks)
+    pu = api.Pileup(ctx, pk)
+    pu.build()
+    pu.column_rank()
+    cols = []
+    for ci, cb in enumerate(chunks):
+        pos, _ = pu.suspects(ci)
+        off, idx, code = pu.extract_columns(ci, pos)
+        summ = pu.column_summary(ci)
+        cols.append((cb.n_reads, off, idx, code, summ["ref_base"][pos], summ["second_base"][pos]))
+    pu.close()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # int8 tensor peak: MEASURED_PEAKS.json has no int8 figure; the nominal dense int8 rate of the part is
+    # 4.5 POP/s = 2x bf16, so the measured-derived denominator is 2x the measured cuBLAS bf16 burst figure
+    int8_peak_tops = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+    pairs = {}
+    for tag, flags in (("band", 0), ("dense", api.PAIRS_DENSE)):
+        P = api.Pairs(ctx, cols, flags)
+        info = P.info()
+        for _ in range(3):
+            P.compute()
+        ctx.sync()
+        ctx.profile(True)
+        reps = 10 if tag == "band" else 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            P.compute()
+        e1.record(stream)
+        ctx.sync()
+        prof = ctx.profile_report()
+        ctx.profile(False)
+        kms = prof.get("pair_umma_kernel", (0, 0.0))[1] / reps
+        # every 128-SNP block of a tile pair = 2 x 4 tcgen05.mma of M128 x N256 x K32
+        macs = info["kblocks"] * 128.0 * 2 * 128 * 256
+        pairs[tag] = {
+            "ms_per_batch": e0.elapsed_time(e1) / reps, "kernel_ms": kms,
+            "tile_pairs": info["tile_pairs"], "snp_blocks": info["kblocks"],
+            "executed_tops": 2 * macs / (kms * 1e-3) / 1e12 if kms else None,
+            "frac_of_int8_peak": (2 * macs / (kms * 1e-3) / 1e12 / int8_peak_tops) if kms else None,
+            "output_gbs": 2 * info["out_elems"] * 4 / (e0.elapsed_time(e1) / reps * 1e-3) / 1e9,
+        }
+        if tag == "band":
+            n_chk = min(2, len(cols))
+            cpu_t = None
+            for ci in range(n_chk):  # parity of the timed results against the reference's Eigen code
+                sim, diff = P.fetch(ci)
+                if pyoracle.RefSR.available():
+                    t0 = time.perf_counter()
+                    rs, rd = pyoracle.RefSR.read_pair_counts(*cols[ci])
+                    cpu_t = (cpu_t or 0.0) + time.perf_counter() - t0
+                else:
+                    rs, rd = pyoracle.Oracle().read_pair_counts(*cols[ci])
+                assert np.array_equal(sim, rs) and np.array_equal(diff, rd), "read-pair counts differ from the reference"
+            pairs["verified_chunks"] = n_chk
+            pairs["cpu_baseline"] = ({"value": cpu_t / n_chk * 1e3, "unit": "ms per chunk (Eigen sparse products + densify)",
+                                      "cores": 1, "kind": "reference"} if cpu_t else None)
+            pairs["identity_order"] = bool(info["identity"])
+            pairs["dense_equivalent_macs"] = 4.0 * sum(float(c[0]) ** 2 * (c[1].size - 1) for c in cols)
+        P.close()
+    n_snps = sum(c[1].size - 1 for c in cols)
+    out["read_pairs"] = {
+        "metric": "list_similarities_and_differences_between_reads3 over all chunks (one hsgpu_pairs batch)",
+        "shape": f"{len(cols)} chunks, {sum(c[0] for c in cols)} reads, {n_snps} SNP columns, "
+                 f"{sum(int(c[1][-1]) for c in cols)} cells",
+        "int8_peak_tops": int8_peak_tops,
+        "int8_peak_source": "2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json); nominal dense int8 is 4500",
+        **pairs,
+    }
     return out
 
 

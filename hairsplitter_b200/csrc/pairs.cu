@@ -62,7 +62,13 @@ struct hsgpu_pairs {
     int32_t* d_rowof = nullptr;    // per contig-local read: stacked row (inverse map, for the one-hot scatter)
     PairContig* d_contigs = nullptr;
     PairWork* d_work = nullptr;
-    int32_t *d_sim = nullptr, *d_diff = nullptr;
+    int32_t *d_sim = nullptr, *d_diff = nullptr;    // results in the caller's read order (what fetch returns)
+    int32_t *d_psim = nullptr, *d_pdiff = nullptr;  // results in tile order; alias d_sim/d_diff when no contig was reordered
+    bool all_identity = true;
+    uint8_t* d_sched = nullptr;      // per contig nt x nt: 1 where the tile pair was scheduled
+    int64_t* d_sched_off = nullptr;
+    int32_t* d_row_contig = nullptr;  // stacked row -> contig
+    int64_t* d_read_base = nullptr;
     int32_t* d_err = nullptr;
     // the SNP columns (inputs), kept until the operands are built
     int64_t *d_snp_off = nullptr, *d_snp_base = nullptr;
@@ -181,8 +187,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __global__ void __launch_bounds__(PG_THREADS, 1)
 pair_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapR,
                  const PairWork* __restrict__ work, int n_work, const PairContig* __restrict__ contigs,
-                 const int32_t* __restrict__ rowmap, int32_t* __restrict__ sim, int32_t* __restrict__ diff,
-                 int32_t* __restrict__ err) {
+                 int32_t* __restrict__ sim, int32_t* __restrict__ diff, int32_t* __restrict__ err) {
     extern __shared__ unsigned char pg_raw[];
     // 1024-byte alignment: the swizzle pattern is a function of the shared-memory address
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pg_raw) + 1023) & ~(uintptr_t)1023);
@@ -192,7 +197,6 @@ pair_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     uint64_t* acc_full = bars + 2 * PG_STAGES;   // MMA -> epilogue
     uint64_t* acc_empty = acc_full + 1;          // epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
-    __shared__ int32_t s_colmap[PG_TILE];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -281,6 +285,9 @@ pair_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         }
     } else {
         // ===== epilogue: 4 warps, warp (w % 4) owns TMEM lanes 32*(w % 4) .. +31 =====
+        // Output in tile (= first-SNP) order, n_pad x n_pad per contig: thread t owns row t of the tile, so tile
+        // (i,j) goes out as 16-byte pieces of its row and the mirror tile (j,i) as one column per store, the
+        // 32 lanes of a warp writing 32 consecutive ints.
         const int quarter = warp & 3;
         const int t = quarter * 32 + lane;  // row of the tile
         uint32_t acc_phase = 0;
@@ -288,17 +295,8 @@ pair_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
             const PairWork wk = work[w];
             const PairContig pc = contigs[wk.contig];
             const int64_t ld = pc.n_pad;
-            int orow, ocol_t;
-            if (pc.identity) {
-                orow = wk.ti * PG_TILE + t;
-                ocol_t = wk.tj * PG_TILE + t;
-            } else {
-                orow = rowmap[pc.row0 + wk.ti * PG_TILE + t];
-                ocol_t = rowmap[pc.row0 + wk.tj * PG_TILE + t];
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with the previous tile's map
-            s_colmap[t] = ocol_t;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int orow = wk.ti * PG_TILE + t;
+            const int ocol0 = wk.tj * PG_TILE;
             mbar_wait(acc_full, acc_phase, err, 4);
             acc_phase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -320,40 +318,23 @@ pair_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                 }
 #pragma unroll
                 for (int c = 0; c < 32; c++) {
-                    const int oc = s_colmap[cb * 32 + c];
-                    const bool dead = (oc == orow);  // :417-432
+                    const bool dead = (ocol0 + cb * 32 + c == orow);  // :417-432
                     v0[c] = dead ? 0u : 3u * v0[c] + v2[c];
                     v1[c] = dead ? 0u : v1[c];
                 }
-                if (pc.identity) {
-                    // rows of the padded output exist up to n_pad: no bounds to check
-                    int4* ps = reinterpret_cast<int4*>(sim_c + (int64_t)orow * ld + wk.tj * PG_TILE + cb * 32);
-                    int4* pd = reinterpret_cast<int4*>(diff_c + (int64_t)orow * ld + wk.tj * PG_TILE + cb * 32);
+                int4* ps = reinterpret_cast<int4*>(sim_c + (int64_t)orow * ld + ocol0 + cb * 32);
+                int4* pd = reinterpret_cast<int4*>(diff_c + (int64_t)orow * ld + ocol0 + cb * 32);
 #pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        ps[c] = make_int4((int)v0[4 * c], (int)v0[4 * c + 1], (int)v0[4 * c + 2], (int)v0[4 * c + 3]);
-                        pd[c] = make_int4((int)v1[4 * c], (int)v1[4 * c + 1], (int)v1[4 * c + 2], (int)v1[4 * c + 3]);
-                    }
-                    if (wk.ti != wk.tj) {
-#pragma unroll
-                        for (int c = 0; c < 32; c++) {
-                            const int64_t o = (int64_t)(wk.tj * PG_TILE + cb * 32 + c) * ld + orow;
-                            sim_c[o] = (int)v0[c];
-                            diff_c[o] = (int)v1[c];
-                        }
-                    }
-                } else if (orow >= 0) {
+                for (int c = 0; c < 8; c++) {
+                    ps[c] = make_int4((int)v0[4 * c], (int)v0[4 * c + 1], (int)v0[4 * c + 2], (int)v0[4 * c + 3]);
+                    pd[c] = make_int4((int)v1[4 * c], (int)v1[4 * c + 1], (int)v1[4 * c + 2], (int)v1[4 * c + 3]);
+                }
+                if (wk.ti != wk.tj) {
 #pragma unroll
                     for (int c = 0; c < 32; c++) {
-                        const int oc = s_colmap[cb * 32 + c];
-                        if (oc >= 0) {
-                            sim_c[(int64_t)orow * ld + oc] = (int)v0[c];
-                            diff_c[(int64_t)orow * ld + oc] = (int)v1[c];
-                            if (wk.ti != wk.tj) {
-                                sim_c[(int64_t)oc * ld + orow] = (int)v0[c];
-                                diff_c[(int64_t)oc * ld + orow] = (int)v1[c];
-                            }
-                        }
+                        const int64_t o = (int64_t)(ocol0 + cb * 32 + c) * ld + orow;
+                        sim_c[o] = (int)v0[c];
+                        diff_c[o] = (int)v1[c];
                     }
                 }
             }
@@ -365,6 +346,44 @@ pair_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(PG_TMEM_COLS) : "memory");
+    }
+}
+
+// Back to the caller's read order: out[r][k] = P[row(r)][row(k)] where the tile pair of (row(r), row(k)) was
+// scheduled, else 0. One CTA per output row; the source row of P is contiguous (n_pad ints), so the scattered
+// 4-byte reads stay inside a few KB that L1 holds, and every output row is written once, coalesced.
+__global__ void __launch_bounds__(256) pair_unpermute_kernel(const PairContig* __restrict__ contigs,
+                                                             const int32_t* __restrict__ row_contig,
+                                                             const int64_t* __restrict__ read_base,
+                                                             const int32_t* __restrict__ rowof,
+                                                             const uint8_t* __restrict__ sched,
+                                                             const int64_t* __restrict__ sched_off,
+                                                             const int32_t* __restrict__ psim, const int32_t* __restrict__ pdiff,
+                                                             int32_t* __restrict__ sim, int32_t* __restrict__ diff) {
+    const int64_t g = blockIdx.x;  // stacked row = (contig, read r in the caller's numbering)
+    const int c = row_contig[g];
+    const PairContig pc = contigs[c];
+    const int r = (int)(g - pc.row0);
+    if (r >= pc.n) return;
+    const int64_t rb0 = read_base[c];
+    const int ir = rowof[rb0 + r] - (int)pc.row0;
+    const int nt = pc.n_pad / PG_TILE;
+    const uint8_t* sc = sched + sched_off[c] + (int64_t)(ir / PG_TILE) * nt;
+    const int32_t* ps = psim + pc.out_off + (int64_t)ir * pc.n_pad;
+    const int32_t* pd = pdiff + pc.out_off + (int64_t)ir * pc.n_pad;
+    int32_t* os = sim + pc.out_off + (int64_t)r * pc.n_pad;
+    int32_t* od = diff + pc.out_off + (int64_t)r * pc.n_pad;
+    for (int k = threadIdx.x; k < pc.n_pad; k += blockDim.x) {
+        int vs = 0, vd = 0;
+        if (k < pc.n) {
+            const int ik = rowof[rb0 + k] - (int)pc.row0;
+            if (sc[ik / PG_TILE]) {
+                vs = ps[ik];
+                vd = pd[ik];
+            }
+        }
+        os[k] = vs;
+        od[k] = vd;
     }
 }
 
@@ -432,7 +451,10 @@ void hsgpu_pairs_destroy(hsgpu_pairs* h) {
     hsgpu_ctx* ctx = h->ctx;
     cudaSetDevice(ctx->device);
     hs_free(ctx, h->d_A); hs_free(ctx, h->d_R); hs_free(ctx, h->d_rowmap); hs_free(ctx, h->d_rowof);
-    hs_free(ctx, h->d_contigs); hs_free(ctx, h->d_work); hs_free(ctx, h->d_sim); hs_free(ctx, h->d_diff);
+    hs_free(ctx, h->d_contigs); hs_free(ctx, h->d_work);
+    if (h->d_psim != h->d_sim) { hs_free(ctx, h->d_psim); hs_free(ctx, h->d_pdiff); }
+    hs_free(ctx, h->d_sim); hs_free(ctx, h->d_diff);
+    hs_free(ctx, h->d_sched); hs_free(ctx, h->d_sched_off); hs_free(ctx, h->d_row_contig); hs_free(ctx, h->d_read_base);
     hs_free(ctx, h->d_err); hs_free(ctx, h->d_snp_off); hs_free(ctx, h->d_snp_base); hs_free(ctx, h->d_read_idx);
     hs_free(ctx, h->d_code); hs_free(ctx, h->d_rb); hs_free(ctx, h->d_sb); hs_free(ctx, h->d_snp_contig);
     cudaStreamSynchronize(ctx->stream);
@@ -513,10 +535,18 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
     }
     std::vector<int32_t> rowmap(rows, -1), rowof(std::max<int64_t>(total_reads, 1), 0);
     std::vector<PairWork> work;
+    std::vector<int32_t> row_contig(std::max<int64_t>(rows, 1), 0);
+    std::vector<int64_t> sched_off(n_contigs + 1, 0);
+    for (int c = 0; c < n_contigs; c++) {
+        const int64_t nt = h->h_contigs[c].n_pad / PG_TILE;
+        sched_off[c + 1] = sched_off[c] + nt * nt;
+    }
+    std::vector<uint8_t> sched(std::max<int64_t>(sched_off[n_contigs], 1), 0);
     int64_t kb_listed = 0, kb_dense = 0, tiles_dense = 0;
     for (int c = 0; c < n_contigs; c++) {
         PairContig& pc = h->h_contigs[c];
         const int64_t rb0 = read_base[c];
+        std::fill(row_contig.begin() + pc.row0, row_contig.begin() + pc.row0 + pc.n_pad, c);
         std::vector<int32_t> order(pc.n);
         std::iota(order.begin(), order.end(), 0);
         if (!keep_order) {
@@ -548,6 +578,7 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
                 int k1 = dense ? nkb : std::min(khi[i], khi[j]);
                 if (k0 >= k1) continue;
                 work.push_back(PairWork{c, i, j, k0, k1});
+                sched[sched_off[c] + (int64_t)i * nt + j] = sched[sched_off[c] + (int64_t)j * nt + i] = 1;
                 kb_listed += k1 - k0;
             }
     }
@@ -557,6 +588,7 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
     h->kblocks_listed = kb_listed;
     h->kblocks_dense = kb_dense;
     h->tiles_dense = tiles_dense;
+    for (const PairContig& pc : h->h_contigs) h->all_identity = h->all_identity && pc.identity;
 
 #define PG_TRY(call)                                                               \
     do {                                                                           \
@@ -574,6 +606,21 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
     PG_TRY(hs_alloc(ctx, &h->d_work, h->n_work));
     PG_TRY(hs_alloc(ctx, &h->d_sim, out_elems));
     PG_TRY(hs_alloc(ctx, &h->d_diff, out_elems));
+    if (h->all_identity) {
+        h->d_psim = h->d_sim;
+        h->d_pdiff = h->d_diff;
+    } else {
+        PG_TRY(hs_alloc(ctx, &h->d_psim, out_elems));
+        PG_TRY(hs_alloc(ctx, &h->d_pdiff, out_elems));
+    }
+    PG_TRY(hs_alloc(ctx, &h->d_sched, (int64_t)sched.size()));
+    PG_TRY(hs_alloc(ctx, &h->d_sched_off, n_contigs + 1));
+    PG_TRY(hs_alloc(ctx, &h->d_row_contig, (int64_t)row_contig.size()));
+    PG_TRY(hs_alloc(ctx, &h->d_read_base, n_contigs + 1));
+    PG_TRY(hs_h2d(ctx, h->d_sched, sched.data(), (int64_t)sched.size()));
+    PG_TRY(hs_h2d(ctx, h->d_sched_off, sched_off.data(), n_contigs + 1));
+    PG_TRY(hs_h2d(ctx, h->d_row_contig, row_contig.data(), (int64_t)row_contig.size()));
+    PG_TRY(hs_h2d(ctx, h->d_read_base, read_base.data(), n_contigs + 1));
     PG_TRY(hs_alloc(ctx, &h->d_err, 1));
     PG_TRY(hs_alloc(ctx, &h->d_snp_off, total_snps + 1));
     PG_TRY(hs_alloc(ctx, &h->d_snp_base, n_contigs + 1));
@@ -582,8 +629,6 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
     PG_TRY(hs_alloc(ctx, &h->d_rb, total_snps));
     PG_TRY(hs_alloc(ctx, &h->d_sb, total_snps));
     PG_TRY(hs_alloc(ctx, &h->d_snp_contig, total_snps));
-    int64_t* d_read_base = nullptr;
-    PG_TRY(hs_alloc(ctx, &d_read_base, n_contigs + 1));
     PG_TRY(hs_h2d(ctx, h->d_rowmap, rowmap.data(), rows));
     PG_TRY(hs_h2d(ctx, h->d_rowof, rowof.data(), total_reads));
     PG_TRY(hs_h2d(ctx, h->d_contigs, h->h_contigs.data(), n_contigs));
@@ -595,14 +640,13 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
     PG_TRY(hs_h2d(ctx, h->d_rb, ref_base, total_snps));
     PG_TRY(hs_h2d(ctx, h->d_sb, second_base, total_snps));
     PG_TRY(hs_h2d(ctx, h->d_snp_contig, snp_contig.data(), total_snps));
-    PG_TRY(hs_h2d(ctx, d_read_base, read_base.data(), n_contigs + 1));
     PG_TRY(cudaMemsetAsync(h->d_A, 0, (size_t)std::max<int64_t>(rows * h->k_ld, 1), ctx->stream));
     PG_TRY(cudaMemsetAsync(h->d_R, 0, (size_t)std::max<int64_t>(rows * h->k_ld, 1), ctx->stream));
     PG_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), ctx->stream));
     if (total_snps > 0) {
         if (ctx->profiling) hs_prof_begin(ctx, "onehot_kernel");
         onehot_kernel<<<(unsigned)total_snps, 128, 0, ctx->stream>>>(total_snps, h->d_snp_contig, h->d_snp_base, h->d_snp_off,
-                                                                      h->d_read_idx, h->d_code, h->d_rb, h->d_sb, d_read_base,
+                                                                      h->d_read_idx, h->d_code, h->d_rb, h->d_sb, h->d_read_base,
                                                                       h->d_rowof, h->k_ld, h->d_A, h->d_R);
         if (ctx->profiling) hs_prof_end(ctx);
         ctx->launches++;
@@ -610,7 +654,6 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
     }
     // host vectors above are pageable: the copies must have left them before we return
     PG_TRY(cudaStreamSynchronize(ctx->stream));
-    hs_free(ctx, d_read_base);
 #undef PG_TRY
     if (rows > 0) {
         int rc = pg_make_tmap(ctx, &h->tmapA, h->d_A, h->k_ld, rows);
@@ -629,14 +672,14 @@ int hsgpu_pairs_compute(hsgpu_pairs* h) {
     hsgpu_ctx* ctx = h->ctx;
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     h->computed = false;
-    if (h->out_elems > 0 && !(h->flags & HSGPU_PAIRS_DENSE)) {
-        // unscheduled tile pairs share no SNP block: their counts are zero
-        HS_CUDA(ctx, cudaMemsetAsync(h->d_sim, 0, (size_t)h->out_elems * sizeof(int32_t), ctx->stream));
-        HS_CUDA(ctx, cudaMemsetAsync(h->d_diff, 0, (size_t)h->out_elems * sizeof(int32_t), ctx->stream));
+    if (h->out_elems == 0) {
+        h->computed = true;
+        return HSGPU_OK;
     }
+    const size_t out_bytes = (size_t)h->out_elems * sizeof(int32_t);
     if (h->flags & HSGPU_PAIRS_SIMT) {
-        HS_CUDA(ctx, cudaMemsetAsync(h->d_sim, 0, (size_t)h->out_elems * sizeof(int32_t), ctx->stream));
-        HS_CUDA(ctx, cudaMemsetAsync(h->d_diff, 0, (size_t)h->out_elems * sizeof(int32_t), ctx->stream));
+        HS_CUDA(ctx, cudaMemsetAsync(h->d_sim, 0, out_bytes, ctx->stream));
+        HS_CUDA(ctx, cudaMemsetAsync(h->d_diff, 0, out_bytes, ctx->stream));
         for (int c = 0; c < h->n_contigs; c++) {
             const int np = h->h_contigs[c].n_pad;
             if (np == 0) continue;
@@ -644,7 +687,16 @@ int hsgpu_pairs_compute(hsgpu_pairs* h) {
             HS_KERNEL(ctx, "pair_simt_kernel", pair_simt_kernel<<<grid, block, 0, ctx->stream>>>(h->d_contigs, c, h->k_ld, h->d_A, h->d_R,
                                                                                                 h->d_rowmap, h->d_sim, h->d_diff));
         }
-    } else if (h->n_work > 0) {
+        h->computed = true;
+        return HSGPU_OK;
+    }
+    if (h->all_identity && !(h->flags & HSGPU_PAIRS_DENSE)) {
+        // tile order is the caller's order: the kernel writes the result in place, and tile pairs that are
+        // not scheduled share no SNP block, so their counts are zero
+        HS_CUDA(ctx, cudaMemsetAsync(h->d_sim, 0, out_bytes, ctx->stream));
+        HS_CUDA(ctx, cudaMemsetAsync(h->d_diff, 0, out_bytes, ctx->stream));
+    }
+    if (h->n_work > 0) {
         static bool attr_set = false;
         if (!attr_set) {
             HS_CUDA(ctx, cudaFuncSetAttribute(pair_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
@@ -652,8 +704,12 @@ int hsgpu_pairs_compute(hsgpu_pairs* h) {
         }
         const int grid = (int)std::min<int64_t>(h->n_work, ctx->sm_count);
         HS_KERNEL(ctx, "pair_umma_kernel", pair_umma_kernel<<<grid, PG_THREADS, PG_SMEM, ctx->stream>>>(
-            h->tmapA, h->tmapR, h->d_work, (int)h->n_work, h->d_contigs, h->d_rowmap, h->d_sim, h->d_diff, h->d_err));
+            h->tmapA, h->tmapR, h->d_work, (int)h->n_work, h->d_contigs, h->d_psim, h->d_pdiff, h->d_err));
     }
+    if (!h->all_identity)
+        HS_KERNEL(ctx, "pair_unpermute_kernel", pair_unpermute_kernel<<<(unsigned)h->total_rows, 256, 0, ctx->stream>>>(
+            h->d_contigs, h->d_row_contig, h->d_read_base, h->d_rowof, h->d_sched, h->d_sched_off, h->d_psim, h->d_pdiff,
+            h->d_sim, h->d_diff));
     h->computed = true;
     return HSGPU_OK;
 }
@@ -685,9 +741,7 @@ int hsgpu_pairs_info(hsgpu_pairs* h, int64_t* info) {
     info[4] = h->total_rows;
     info[5] = h->k_ld;
     info[6] = h->out_elems;
-    int ident = 1;
-    for (const PairContig& pc : h->h_contigs) ident &= pc.identity;
-    info[7] = ident;
+    info[7] = h->all_identity ? 1 : 0;
     return HSGPU_OK;
 }
 

@@ -254,6 +254,39 @@ class RefEdlib:
         return out
 
 
+class RefSR:
+    """The reference's own separate_reads.cpp functions through oracle/ref_shim_sr.cpp."""
+
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(HERE, "_ref", "libhsref_sr.so"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(HERE, "_ref", "libhsref_sr.so"))
+            L.hsref_read_pair_counts.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 7
+            cls._lib = L
+        return cls._lib
+
+    @classmethod
+    def read_pair_counts(cls, n_reads, snp_off, read_idx, code, ref_base, second_base, want_output=True):
+        """list_similarities_and_differences_between_reads3 (src/separate_reads.cpp:374-433), densified"""
+        snp_off = np.ascontiguousarray(snp_off, np.int64)
+        read_idx = np.ascontiguousarray(read_idx, np.uint32)
+        code = np.ascontiguousarray(code, np.uint8)
+        ref_base = np.ascontiguousarray(ref_base, np.uint8)
+        second_base = np.ascontiguousarray(second_base, np.uint8)
+        sim = np.zeros((n_reads, n_reads), np.int32) if want_output else None
+        diff = np.zeros((n_reads, n_reads), np.int32) if want_output else None
+        cls.lib().hsref_read_pair_counts(n_reads, snp_off.shape[0] - 1, snp_off.ctypes.data, read_idx.ctypes.data,
+                                         code.ctypes.data, ref_base.ctypes.data, second_base.ctypes.data,
+                                         sim.ctypes.data if want_output else None, diff.ctypes.data if want_output else None)
+        return sim, diff
+
+
 def ref_available() -> bool:
     return os.path.exists(os.path.join(HERE, "_ref", "libhsref_cv.so"))
 

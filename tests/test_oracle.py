@@ -174,6 +174,31 @@ def test_read_pair_counts_definition(oracle):
     np.fill_diagonal(ws, 0)
     np.fill_diagonal(wd, 0)
     assert np.array_equal(sim, ws) and np.array_equal(diff, wd)
+    # ... and against the reference's own Eigen implementation (oracle/_ref/libhsref_sr.so)
+    from oracle import pyoracle
+    if pyoracle.RefSR.available():
+        rs, rd = pyoracle.RefSR.read_pair_counts(R_, snp_off, np.concatenate(idx), np.concatenate(code), rb, sb)
+        assert np.array_equal(sim, rs) and np.array_equal(diff, rd)
+        col = cases_snp_columns(oracle)
+        a = oracle.read_pair_counts(*col)
+        b = pyoracle.RefSR.read_pair_counts(*col)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and b[0].max() > 0
+
+
+def cases_snp_columns(oracle):
+    """suspect columns of a synthetic contig in the .col layout (same helper as the GPU pair tests)"""
+    o = oracle.pileup(cases.medium_case(seed=101))
+    oc = oracle.call_variants(o["col_off"], o["code"], 0.08)
+    pos = oc["suspect_pos"]
+    snp_off = np.zeros(pos.size + 1, np.int64)
+    idx, code = [], []
+    for j, q in enumerate(pos):
+        a, b = o["col_off"][q], o["col_off"][q + 1]
+        idx.append(o["read_idx"][a:b])
+        code.append(o["code"][a:b])
+        snp_off[j + 1] = snp_off[j] + (b - a)
+    return (o["read_end"].size, snp_off, np.concatenate(idx).astype(np.uint32), np.concatenate(code).astype(np.uint8),
+            oc["ref_base"][pos].astype(np.uint8), oc["second_base"][pos].astype(np.uint8))
 
 
 def test_splitting_long_cigar_ops_does_not_change_the_pileup(oracle):
