@@ -761,3 +761,18 @@ int hsgpu_read_pair_counts(hsgpu_ctx* ctx, int32_t n_reads, int32_t n_snps, cons
 }
 
 }  // extern "C"
+
+// internal view for the read-graph stage (graph.cu): the device-resident result blocks of one contig
+int hs_pairs_contigs(hsgpu_pairs* h) { return h ? h->n_contigs : 0; }
+int hs_pairs_view(hsgpu_pairs* h, int32_t contig, hsgpu_ctx** ctx, const int32_t** sim, const int32_t** diff, int32_t* n,
+                  int32_t* n_pad) {
+    if (!h || contig < 0 || contig >= h->n_contigs) return HSGPU_ERR_ARG;
+    *ctx = h->ctx;
+    if (!h->computed) return HSGPU_ERR_STATE;
+    const PairContig& pc = h->h_contigs[contig];
+    *sim = h->d_sim + pc.out_off;
+    *diff = h->d_diff + pc.out_off;
+    *n = pc.n;
+    *n_pad = pc.n_pad;
+    return HSGPU_OK;
+}

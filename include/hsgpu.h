@@ -196,6 +196,33 @@ int hsgpu_pairs_fetch(hsgpu_pairs* h, int32_t contig, int32_t* sim, int32_t* dif
 int hsgpu_pairs_info(hsgpu_pairs* h, int64_t* info);
 void hsgpu_pairs_destroy(hsgpu_pairs* h);
 
+/* ---- read graph + chinese whispers of the windows of a batch: create_read_graph_matrix
+ * (src/separate_reads.cpp:706-828) and chinese_whispers_high_memory (src/cluster_graph.cpp:240-310) ----
+ * A window is the set of reads that span it (the reference's mask_at_this_position, :1590-1622): window w of
+ * contig win_contig[w] owns the ascending read indices win_reads[win_off[w] .. win_off[w+1]). The similarity /
+ * difference counts are read from the device-resident results of `pairs` (hsgpu_pairs_compute must have run;
+ * `pairs` must outlive the graph). Everything below is expressed in LOCAL indices: position of a read in its
+ * window's list. */
+typedef struct hsgpu_graph hsgpu_graph;
+int hsgpu_graph_create(hsgpu_pairs* pairs, int32_t n_windows, const int32_t* win_contig, const int64_t* win_off,
+                       const int32_t* win_reads, float error_rate, hsgpu_graph** out);
+/* builds the adjacency of every window. n_replayed (may be NULL) receives the number of reads whose neighbour
+ * choice depended on std::sort's order of equal distances and was replayed with the reference's sort. */
+int hsgpu_graph_build(hsgpu_graph* g, int64_t* n_replayed);
+/* the symmetric 0/1 adjacency as a CSR over all masked reads of all windows (rows in window order): neighbours of
+ * masked read i are adj[adj_off[i] .. adj_off[i+1]), local indices, ascending. adj_off has win_off[n_windows]+1
+ * entries; *n_adj is always written; HSGPU_ERR_CAPACITY when capacity < *n_adj. */
+int hsgpu_graph_adjacency(hsgpu_graph* g, int64_t* adj_off, int64_t capacity, int32_t* adj, int64_t* n_adj);
+/* n_runs clusterings. Run i works on window run_window[i] and starts from init_labels (the runs' label vectors
+ * concatenated, m entries each, labels = local indices or negative = "no cluster"); labels_out has the same
+ * layout. Node order of sweep s = the masked reads sorted by order_rank[min(s, n_orders-1)], where order_rank
+ * holds, per contig (concatenated in contig order), n_orders arrays of n_reads positions: order_rank[k][r] = place
+ * of read r in the k-th shuffled order of all reads of the contig (the reference shuffles 0..n_reads-1 afresh in
+ * every sweep, cluster_graph.cpp:255-259, and skips the reads outside the window). */
+int hsgpu_graph_whispers(hsgpu_graph* g, int64_t n_runs, const int32_t* run_window, const int32_t* init_labels,
+                         int32_t n_orders, const int32_t* order_rank, int32_t* labels_out);
+void hsgpu_graph_destroy(hsgpu_graph* g);
+
 /* ---- realignment: edlibAlign (src/edlib/include/edlib.h:146-271, src/edlib/src/edlib.cpp:142-297)
  * Batch of (query, target) pairs, results with edlib's exact field semantics. Modes/tasks use edlib's
  * numeric values: mode 0 NW, 1 SHW, 2 HW; task 0 DISTANCE, 1 LOC, 2 PATH. */
