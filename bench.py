@@ -366,6 +366,43 @@ def col_blocks(path):
     return blocks
 
 
+def run_separate_reads_wall(tmp, col, cores, n_contigs):
+    """wall time of the HS_separate_reads executable on the .col of the whole configuration: ours (host C++ over
+    libhsgpu: read-pair counts, read graphs and chinese-whispers runs on one GPU) beside the reference's (OpenMP over
+    contigs). Both with std::random_device pinned to the same constant (HS_PIN_SEED / oracle/ref_pin_rng.cpp), so
+    the .gro files can be compared contig by contig."""
+    import subprocess
+    ours = os.path.join(ROOT, "hairsplitter_b200", "bin", "HS_separate_reads")
+    ref = os.path.join(ROOT, "oracle", "_ref", "HS_separate_reads_pinned")
+    if not os.path.exists(ours):
+        return {"unavailable": "hairsplitter_b200/bin/HS_separate_reads not built"}
+    from oracle.pyoracle import PIN_SEED
+    env = dict(os.environ, HS_PIN_SEED=str(PIN_SEED), HS_TIMING="1")
+
+    def run(exe, tag, threads):
+        gro = os.path.join(tmp, f"{tag}.gro")
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, col, str(threads), "0.1", os.path.join(tmp, "no_ploidy"), "0", "0", "0", gro, "0"], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+        return time.perf_counter() - t0, gro, r.stderr.decode()
+
+    run(ours, "sr_warm", cores)
+    t_ours, gro_ours, log = run(ours, "sr_ours", cores)
+    out = {"metric": "HS_separate_reads wall time (parse .col + read-pair counts + read graphs + clustering + write .gro)",
+           "ours_s": t_ours, "ours_threads": cores, "ours_gpus": 1,
+           "phases": [l.replace("[hs timing]", "").strip() for l in log.splitlines() if l.startswith("[hs timing]")]}
+    if os.path.exists(ref):
+        threads = min(cores, n_contigs)
+        t_ref, gro_ref, _ = run(ref, "sr_ref", threads)
+        a, b = col_blocks(gro_ours), col_blocks(gro_ref)
+        same = a == b
+        out.update({"reference_s": t_ref, "reference_threads": threads, "speedup": t_ref / t_ours,
+                    "gro_identical_to_pinned_reference": same,
+                    "groups": sum(1 for v in a.values() for l in v if l.startswith("GROUP"))})
+        assert same, "our .gro differs from the pinned reference's"
+    return out
+
+
 def run_call_variants_wall(chunks, args):
     """BASELINE's third headline: wall time of the HS_call_variants executable on the whole configuration, ours
     (host C++ over libhsgpu, one GPU) beside the reference's (OpenMP over contigs, all host cores), same files,
@@ -409,6 +446,7 @@ def run_call_variants_wall(chunks, args):
             assert open(err_ours).read() == open(err_ref).read() or threads > 1  # float sum order varies with threads
             out.update({"reference_s": t_ref, "reference_threads": threads, "speedup": t_ref / t_ours,
                         "col_identical_to_reference": True, "snps": sum(len(v) for v in a.values())})
+        out["separate_reads"] = run_separate_reads_wall(tmp, col_ours, cores, len(sample))
         return out
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

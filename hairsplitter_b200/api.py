@@ -68,7 +68,8 @@ EXPORTS = [
     "hsgpu_pileup_read_ends", "hsgpu_pileup_export", "hsgpu_pileup_extract_columns", "hsgpu_column_rank",
     "hsgpu_column_counts", "hsgpu_suspects", "hsgpu_column_summary", "hsgpu_partition_tables", "hsgpu_robust_filter",
     "hsgpu_read_pair_counts", "hsgpu_pairs_create", "hsgpu_pairs_compute", "hsgpu_pairs_fetch", "hsgpu_pairs_info",
-    "hsgpu_pairs_destroy", "hsgpu_edlib_align_batch",
+    "hsgpu_pairs_destroy", "hsgpu_graph_create", "hsgpu_graph_build", "hsgpu_graph_adjacency", "hsgpu_graph_whispers",
+    "hsgpu_graph_destroy", "hsgpu_edlib_align_batch",
 ]
 PAIRS_DENSE, PAIRS_KEEP_ORDER, PAIRS_SIMT = 1, 2, 4
 
@@ -128,6 +129,12 @@ def load():
     L.hsgpu_pairs_info.argtypes = [vp, vp]
     L.hsgpu_pairs_destroy.argtypes = [vp]
     L.hsgpu_pairs_destroy.restype = None
+    L.hsgpu_graph_create.argtypes = [vp, i32, vp, vp, vp, f32, C.POINTER(vp)]
+    L.hsgpu_graph_build.argtypes = [vp, vp]
+    L.hsgpu_graph_adjacency.argtypes = [vp, vp, i64, vp, vp]
+    L.hsgpu_graph_whispers.argtypes = [vp, i64, vp, vp, i32, vp, vp]
+    L.hsgpu_graph_destroy.argtypes = [vp]
+    L.hsgpu_graph_destroy.restype = None
     L.hsgpu_edlib_align_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, i64]
     for name in ("hsgpu_debug_rank_column", "hsgpu_debug_rh_order", "hsgpu_debug_sort_desc"):
         getattr(L, name).restype = C.c_int if name == "hsgpu_debug_rh_order" else None
@@ -389,6 +396,61 @@ class Pairs:
     def close(self):
         if getattr(self, "h", None):
             self.lib.hsgpu_pairs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Graph:
+    """hsgpu_graph: read graphs (create_read_graph_matrix) and chinese-whispers runs of a batch of windows over the
+    device-resident counts of a Pairs object. windows: list of (contig, ascending read indices spanning the window)."""
+
+    def __init__(self, pairs: Pairs, windows, error_rate):
+        self.ctx, self.lib, self.pairs = pairs.ctx, pairs.lib, pairs
+        self.win_contig = _a([w[0] for w in windows], np.int32)
+        self.win_off = np.zeros(len(windows) + 1, np.int64)
+        self.win_off[1:] = np.cumsum([len(w[1]) for w in windows])
+        self.win_reads = (np.concatenate([_a(w[1], np.int32) for w in windows]) if windows else np.zeros(0, np.int32))
+        h = C.c_void_p()
+        self.ctx.check(self.lib.hsgpu_graph_create(pairs.h, len(windows), self.win_contig.ctypes.data, self.win_off.ctypes.data,
+                                                   self.win_reads.ctypes.data, float(error_rate), C.byref(h)), "hsgpu_graph_create")
+        self.h = h
+        self.replayed = 0
+
+    def build(self):
+        n = C.c_int64(0)
+        self.ctx.check(self.lib.hsgpu_graph_build(self.h, C.byref(n)), "hsgpu_graph_build")
+        self.replayed = int(n.value)
+
+    def adjacency(self):
+        """(adj_off, adj): CSR over all masked reads of all windows, neighbours as local indices"""
+        total = int(self.win_off[-1])
+        adj_off = np.zeros(total + 1, np.int64)
+        n = C.c_int64(0)
+        self.ctx.check(self.lib.hsgpu_graph_adjacency(self.h, adj_off.ctypes.data, 0, None, C.byref(n)), "hsgpu_graph_adjacency")
+        adj = np.zeros(max(int(n.value), 1), np.int32)
+        self.ctx.check(self.lib.hsgpu_graph_adjacency(self.h, None, int(n.value), adj.ctypes.data, C.byref(n)),
+                       "hsgpu_graph_adjacency")
+        return adj_off, adj[:int(n.value)]
+
+    def whispers(self, run_window, init_labels, order_rank, n_orders=1):
+        """run_window[i] = window of run i; init_labels = the runs' local label vectors concatenated;
+        order_rank = per contig n_orders arrays of n_reads positions, concatenated"""
+        run_window = _a(run_window, np.int32)
+        init = _a(init_labels, np.int32)
+        rank = _a(order_rank, np.int32)
+        out = np.zeros(init.size, np.int32)
+        self.ctx.check(self.lib.hsgpu_graph_whispers(self.h, run_window.size, run_window.ctypes.data, init.ctypes.data,
+                                                     int(n_orders), rank.ctypes.data, out.ctypes.data), "hsgpu_graph_whispers")
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hsgpu_graph_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -98,11 +98,11 @@ int64_t hso_read_graph(int32_t n_reads, const int32_t* sim, const int32_t* diff,
 }
 
 // chinese_whispers_high_memory (src/cluster_graph.cpp:240-310) on the graph above. Labels and the graph are in local
-// indices (order-preserving: masked is ascending), the sweep order is the shuffle of ALL n_reads reads seeded with
-// `seed` before every sweep, restricted to the masked ones -- what the reference does when std::random_device
-// always returns `seed`.
+// indices (order-preserving: masked is ascending), the sweep order is the shuffle of ALL n_reads reads, seeded before
+// sweep s with seeds[min(s, n_seeds-1)], restricted to the masked ones -- what the reference does when
+// std::random_device returns that sequence (one constant seed = the pinned reference build).
 void hso_chinese_whispers(int32_t n_reads, int32_t m, const int32_t* masked, const int64_t* adj_off, const int32_t* adj,
-                          const int32_t* init, uint32_t seed, int32_t* labels) {
+                          const int32_t* init, int32_t n_seeds, const uint32_t* seeds, int32_t* labels) {
     std::vector<int> local((size_t)n_reads, -1);
     for (int i = 0; i < m; i++) local[masked[i]] = i;
     std::vector<int> clusters(init, init + m);
@@ -111,7 +111,7 @@ void hso_chinese_whispers(int32_t n_reads, int32_t m, const int32_t* masked, con
         changes = 0;
         std::vector<int> order((size_t)n_reads);
         std::iota(order.begin(), order.end(), 0);
-        std::mt19937 g(seed);
+        std::mt19937 g(seeds[std::min(iterations, n_seeds - 1)]);
         std::shuffle(order.begin(), order.end(), g);
         for (int read : order) {
             const int i = local[read];
@@ -134,6 +134,15 @@ void hso_chinese_whispers(int32_t n_reads, int32_t m, const int32_t* masked, con
         iterations += 1;
     }
     std::memcpy(labels, clusters.data(), sizeof(int32_t) * (size_t)m);
+}
+
+// 0..n-1 after std::shuffle with std::mt19937(seed): the node order of one sweep
+void hso_shuffled_order(int32_t n, uint32_t seed, int32_t* out) {
+    std::vector<int> order((size_t)n);
+    std::iota(order.begin(), order.end(), 0);
+    std::mt19937 g(seed);
+    std::shuffle(order.begin(), order.end(), g);
+    for (int i = 0; i < n; i++) out[i] = order[i];
 }
 }  // extern "C"
 
@@ -191,7 +200,7 @@ static void oracle_stages(void*, const std::vector<hs::ColContig>& contigs, std:
                 hs::snp_start_labels(c.snps[s], mask, start);
                 std::vector<int32_t> init((size_t)m), out((size_t)m);
                 for (int i = 0; i < m; i++) init[i] = loc[start[win.masked[i]]];
-                hso_chinese_whispers(R, m, win.masked.data(), adj_off.data(), adj.data(), init.data(), sh.pin, out.data());
+                hso_chinese_whispers(R, m, win.masked.data(), adj_off.data(), adj.data(), init.data(), 1, &sh.pin, out.data());
                 std::vector<int> full((size_t)R, -2);
                 for (int i = 0; i < m; i++) full[win.masked[i]] = win.masked[out[i]];
                 lc.push_back(std::move(full));

@@ -22,7 +22,7 @@ _P = np.ctypeslib.ndpointer
 
 def build(ref: bool = True) -> None:
     """Compile liboracle.so (and _ref/ when the reference sources are present)."""
-    subprocess.run(["make", "-s", "-C", HERE, "liboracle.so"], check=True)
+    subprocess.run(["make", "-s", "-C", HERE, "liboracle.so", "sr_hostcheck"], check=True)
     if ref and os.path.exists("/root/reference/src/call_variants.cpp"):
         subprocess.run(["make", "-s", "-j8", "-C", HERE, "ref"], check=True)
 
@@ -188,6 +188,43 @@ class Oracle:
         return sim, diff
 
 
+    def read_graph(self, sim, diff, masked, error_rate):
+        """create_read_graph_matrix restated (oracle/hs_oracle_sr.cpp) on dense counts -> (adj_off, adj), local indices"""
+        sim, diff = _arr(sim, np.int32), _arr(diff, np.int32)
+        masked = _arr(masked, np.int32)
+        n = sim.shape[0]
+        adj_off = np.zeros(masked.size + 1, np.int64)
+        f = self.lib.hso_read_graph
+        f.restype = C.c_int64
+        f.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+        cnt = f(n, sim.ctypes.data, diff.ctypes.data, masked.size, masked.ctypes.data, float(error_rate), adj_off.ctypes.data, None)
+        adj = np.zeros(max(int(cnt), 1), np.int32)
+        f(n, sim.ctypes.data, diff.ctypes.data, masked.size, masked.ctypes.data, float(error_rate), adj_off.ctypes.data, adj.ctypes.data)
+        return adj_off, adj[:int(cnt)]
+
+    def shuffled_order(self, n, seed):
+        """0..n-1 after std::shuffle with std::mt19937(seed)"""
+        out = np.zeros(n, np.int32)
+        f = self.lib.hso_shuffled_order
+        f.restype = None
+        f.argtypes = [C.c_int32, C.c_uint32, C.c_void_p]
+        f(n, int(seed), out.ctypes.data)
+        return out
+
+    def chinese_whispers(self, n_reads, masked, adj_off, adj, init_local, seed):
+        """chinese_whispers_high_memory restated, labels as local indices; sweep s is shuffled with seed (an int) or
+        seeds[min(s, len-1)] (a sequence)"""
+        masked = _arr(masked, np.int32)
+        adj_off, adj, init = _arr(adj_off, np.int64), _arr(adj, np.int32), _arr(init_local, np.int32)
+        out = np.zeros(masked.size, np.int32)
+        f = self.lib.hso_chinese_whispers
+        f.restype = None
+        seeds = _arr([seed] if np.isscalar(seed) else seed, np.uint32)
+        f.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        f(n_reads, masked.size, masked.ctypes.data, adj_off.ctypes.data, adj.ctypes.data, init.ctypes.data, seeds.size,
+          seeds.ctypes.data, out.ctypes.data)
+        return out
+
     def edlib_align(self, query: bytes, target: bytes, k=-1, mode=2, task=2):
         m, n = len(query), len(target)
         ed = np.zeros(1, np.int32)
@@ -268,6 +305,10 @@ class RefSR:
         if cls._lib is None:
             L = C.CDLL(os.path.join(HERE, "_ref", "libhsref_sr.so"))
             L.hsref_read_pair_counts.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 7
+            L.hsref_read_graph.restype = C.c_int64
+            L.hsref_read_graph.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+            L.hsref_chinese_whispers.restype = None
+            L.hsref_chinese_whispers.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5
             cls._lib = L
         return cls._lib
 
@@ -285,6 +326,36 @@ class RefSR:
                                          code.ctypes.data, ref_base.ctypes.data, second_base.ctypes.data,
                                          sim.ctypes.data if want_output else None, diff.ctypes.data if want_output else None)
         return sim, diff
+
+
+    @classmethod
+    def read_graph(cls, col, masked, error_rate):
+        """create_read_graph_matrix (src/separate_reads.cpp:706-828) -> (adj_off, adj) over the masked reads, local indices"""
+        n_reads, snp_off, read_idx, code, rb, sb = col
+        snp_off, read_idx = np.ascontiguousarray(snp_off, np.int64), np.ascontiguousarray(read_idx, np.uint32)
+        code, rb, sb = (np.ascontiguousarray(x, np.uint8) for x in (code, rb, sb))
+        masked = np.ascontiguousarray(masked, np.int32)
+        adj_off = np.zeros(masked.size + 1, np.int64)
+        args = [n_reads, snp_off.shape[0] - 1, snp_off.ctypes.data, read_idx.ctypes.data, code.ctypes.data, rb.ctypes.data,
+                sb.ctypes.data, masked.size, masked.ctypes.data, float(error_rate), adj_off.ctypes.data]
+        n = cls.lib().hsref_read_graph(*args, None)
+        adj = np.zeros(max(int(n), 1), np.int32)
+        cls.lib().hsref_read_graph(*args, adj.ctypes.data)
+        return adj_off, adj[:int(n)]
+
+    @classmethod
+    def chinese_whispers(cls, n_reads, masked, adj_off, adj, init_reads):
+        """chinese_whispers_high_memory (src/cluster_graph.cpp:240-310), random_device pinned; labels as read indices"""
+        masked = np.ascontiguousarray(masked, np.int32)
+        adj_off, adj = np.ascontiguousarray(adj_off, np.int64), np.ascontiguousarray(adj, np.int32)
+        init = np.ascontiguousarray(init_reads, np.int32)
+        out = np.zeros(masked.size, np.int32)
+        cls.lib().hsref_chinese_whispers(n_reads, masked.size, masked.ctypes.data, adj_off.ctypes.data, adj.ctypes.data,
+                                         init.ctypes.data, out.ctypes.data)
+        return out
+
+
+PIN_SEED = 20260117  # oracle/ref_pin_rng.cpp
 
 
 def ref_available() -> bool:

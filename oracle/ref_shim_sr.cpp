@@ -6,10 +6,14 @@
 // Reference entry points wrapped here:
 //   list_similarities_and_differences_between_reads3   src/separate_reads.cpp:374  (Eigen sparse products)
 //   list_similarities_and_differences_between_reads2   src/separate_reads.cpp:323  (its dense restatement)
+//   create_read_graph_matrix                           src/separate_reads.cpp:706
+//   chinese_whispers_high_memory                       src/cluster_graph.cpp:240  (std::random_device pinned by
+//                                                      ref_pin_rng.cpp, linked into this library with -Bsymbolic)
 #include <cstdint>
 #include <cstring>
 #include <vector>
 
+#include "cluster_graph.h"
 #include "separate_reads.h"
 
 static std::vector<Column> make_columns(int n_snps, const int64_t* snp_off, const uint32_t* idx, const uint8_t* code,
@@ -43,5 +47,53 @@ int hsref_read_pair_counts(int n_reads, int n_snps, const int64_t* snp_off, cons
     if (sim) densify(similarity, n_reads, sim);
     if (diff) densify(difference, n_reads, diff);
     return 0;
+}
+
+// create_read_graph_matrix on the reference's own sparse count matrices. masked = ascending read indices with
+// mask == true. Output: CSR over the masked reads, neighbours as local indices (Eigen's column iteration order).
+// Returns the number of entries (adj may be NULL).
+int64_t hsref_read_graph(int n_reads, int n_snps, const int64_t* snp_off, const uint32_t* idx, const uint8_t* code,
+                         const uint8_t* rb, const uint8_t* sb, int m, const int32_t* masked, float error_rate,
+                         int64_t* adj_off, int32_t* adj) {
+    std::vector<Column> snps = make_columns(n_snps, snp_off, idx, code, rb, sb);
+    Eigen::SparseMatrix<int> similarity(n_reads, n_reads), difference(n_reads, n_reads), adjacency(n_reads, n_reads);
+    list_similarities_and_differences_between_reads3(snps, similarity, difference);
+    std::vector<bool> mask(n_reads, false);
+    std::vector<int> local(n_reads, -1);
+    for (int i = 0; i < m; i++) {
+        mask[masked[i]] = true;
+        local[masked[i]] = i;
+    }
+    create_read_graph_matrix(mask, 0, 2000, similarity, difference, adjacency, error_rate);
+    int64_t n = 0;
+    for (int i = 0; i < m; i++) {
+        adj_off[i] = n;
+        for (Eigen::SparseMatrix<int>::InnerIterator it(adjacency, masked[i]); it; ++it) {
+            if (it.value() == 0) continue;
+            if (adj) adj[n] = local[it.row()];
+            n++;
+        }
+    }
+    adj_off[m] = n;
+    return n;
+}
+
+// chinese_whispers_high_memory on a graph given as the CSR above; init/labels are per masked read, as READ indices
+void hsref_chinese_whispers(int n_reads, int m, const int32_t* masked, const int64_t* adj_off, const int32_t* adj,
+                            const int32_t* init, int32_t* labels) {
+    std::vector<Eigen::Triplet<int>> trip;
+    for (int i = 0; i < m; i++)
+        for (int64_t e = adj_off[i]; e < adj_off[i + 1]; e++) trip.push_back(Eigen::Triplet<int>(masked[adj[e]], masked[i], 1));
+    Eigen::SparseMatrix<int> adjacency(n_reads, n_reads);
+    adjacency.setFromTriplets(trip.begin(), trip.end());
+    std::vector<bool> mask(n_reads, false);
+    std::vector<int> start(n_reads);
+    for (int r = 0; r < n_reads; r++) start[r] = r;
+    for (int i = 0; i < m; i++) {
+        mask[masked[i]] = true;
+        start[masked[i]] = init[i];
+    }
+    std::vector<int> out = chinese_whispers_high_memory(adjacency, start, mask);
+    for (int i = 0; i < m; i++) labels[i] = out[masked[i]];
 }
 }

@@ -81,3 +81,71 @@ def walk_edge_case(seed=71, length=5000):
                              cigar=np.array(cig, np.uint32), cigar_off=np.array(cig_off, np.int64),
                              start=np.array(starts, np.int32), strand=np.array(strands, np.uint8),
                              strain=np.zeros(n, np.int32), name="walk_edges")
+
+
+# ---- separate_reads stages: SNP columns and windows -------------------------------------------------------------
+def snp_columns(oracle, cb, mean_error=0.08):
+    """the suspect columns of a synthetic contig as (n_reads, snp_off, read_idx, code, ref_base, second_base)"""
+    o = oracle.pileup(cb)
+    oc = oracle.call_variants(o["col_off"], o["code"], mean_error)
+    pos = oc["suspect_pos"]
+    snp_off = np.zeros(pos.size + 1, np.int64)
+    idx, code = [np.zeros(0, np.uint32)], [np.zeros(0, np.uint8)]
+    for j, q in enumerate(pos):
+        a, b = o["col_off"][q], o["col_off"][q + 1]
+        idx.append(o["read_idx"][a:b])
+        code.append(o["code"][a:b])
+        snp_off[j + 1] = snp_off[j] + (b - a)
+    return (cb.n_reads, snp_off, np.concatenate(idx).astype(np.uint32), np.concatenate(code).astype(np.uint8),
+            oc["ref_base"][pos].astype(np.uint8), oc["second_base"][pos].astype(np.uint8)), pos
+
+
+def coarse_columns(rng, n_reads, n_snps, p_alt=0.4, p_other=0.05):
+    """every read covers every SNP, few SNPs: distances take few distinct values, so groups of equal distances
+    straddle the "first five neighbours" cut (the case the CUDA path replays with the reference's sort)"""
+    hap = rng.integers(0, 2, n_reads)
+    rb = rng.integers(33, 158, n_snps).astype(np.uint8)
+    sb = ((rb - 33 + rng.integers(1, 124, n_snps)) % 125 + 33).astype(np.uint8)
+    snp_off = np.arange(n_snps + 1, dtype=np.int64) * n_reads
+    idx = np.tile(np.arange(n_reads, dtype=np.uint32), n_snps)
+    code = np.zeros(n_snps * n_reads, np.uint8)
+    for s in range(n_snps):
+        u = rng.random(n_reads)
+        alt = (hap == 1) ^ (u < p_alt * 0.3)
+        c = np.where(alt, sb[s], rb[s])
+        c = np.where(rng.random(n_reads) < p_other, np.uint8(33 + (int(rb[s]) + 7) % 125), c)
+        code[s * n_reads:(s + 1) * n_reads] = c
+    return (n_reads, snp_off, idx, code, rb, sb)
+
+
+def windows_of(col, pos, size=2000):
+    """windows like the reference's walk: reads present at the first and at the last SNP of each 2 kb window;
+    returns [(masked reads ascending, indices of the window's SNPs)]"""
+    n_reads, snp_off, idx = col[0], col[1], col[2]
+    out = []
+    if pos.size == 0:
+        return out
+    for w0 in range(0, int(pos.max()) + 1, size):
+        inside = np.nonzero((pos >= w0) & (pos < w0 + size))[0]
+        if inside.size == 0:
+            continue
+        first = idx[snp_off[inside[0]]:snp_off[inside[0] + 1]]
+        last = idx[snp_off[inside[-1]]:snp_off[inside[-1] + 1]]
+        masked = np.intersect1d(first, last).astype(np.int32)
+        if masked.size:
+            out.append((masked, inside))
+    return out
+
+
+def start_labels(col, s, masked):
+    """labels a clustering run starts from at SNP s (src/separate_reads.cpp:1680-1693), as LOCAL indices"""
+    n_reads, snp_off, idx, code = col[0], col[1], col[2], col[3]
+    local = np.full(n_reads, -1, np.int64)
+    local[masked] = np.arange(masked.size)
+    lab = np.arange(masked.size, dtype=np.int32)
+    first = {}
+    for r, c in zip(idx[snp_off[s]:snp_off[s + 1]], code[snp_off[s]:snp_off[s + 1]]):
+        if local[r] >= 0:
+            first.setdefault(int(c), int(local[r]))
+            lab[local[r]] = first[int(c)]
+    return lab

@@ -1,0 +1,220 @@
+"""GPU parity of the separate_reads stages through the C ABI: the read graph of every window (hsgpu_graph_build =
+create_read_graph_matrix, reference src/separate_reads.cpp:706-828) and the chinese-whispers runs
+(hsgpu_graph_whispers = chinese_whispers_high_memory, src/cluster_graph.cpp:240-310) against the oracle
+(oracle/hs_oracle_sr.cpp, itself pinned against the compiled reference by tests/test_oracle_sr.py), and the
+HS_separate_reads drop-in executable against the RNG-pinned reference executable: .gro byte-identical.
+Integer / index outputs: tolerance 0."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from hairsplitter_b200 import api, synth
+from oracle.pyoracle import PIN_SEED, Oracle
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "hairsplitter_b200", "bin", "HS_separate_reads")
+REF_CV = os.path.join(ROOT, "oracle", "_ref", "HS_call_variants")
+REF_SR = os.path.join(ROOT, "oracle", "_ref", "HS_separate_reads_pinned")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+def _check_batch(ctx, oracle, cols, windows, error_rate, seeds):
+    """cols: contigs; windows: [(contig, masked, snp indices to start runs from)]"""
+    pairs = api.Pairs(ctx, cols)
+    pairs.compute()
+    g = api.Graph(pairs, [(c, m) for c, m, _ in windows], error_rate)
+    g.build()
+    adj_off, adj = g.adjacency()
+    counts = [oracle.read_pair_counts(*col) for col in cols]
+    base, want_graphs = 0, []
+    for c, masked, _ in windows:
+        o_off, o_adj = oracle.read_graph(counts[c][0], counts[c][1], masked, error_rate)
+        m = masked.size
+        got_off = adj_off[base:base + m + 1] - adj_off[base]
+        assert np.array_equal(got_off, o_off), "degrees differ"
+        assert np.array_equal(adj[adj_off[base]:adj_off[base + m]], o_adj), "neighbours differ"
+        want_graphs.append((o_off, o_adj))
+        base += m
+    # clustering runs
+    run_window, init, want = [], [], []
+    for w, (c, masked, starts) in enumerate(windows):
+        for s in starts:
+            lab = cases.start_labels(cols[c], s, masked)
+            run_window.append(w)
+            init.append(lab)
+            want.append(oracle.chinese_whispers(cols[c][0], masked, want_graphs[w][0], want_graphs[w][1], lab, seeds))
+    rank = []
+    for col in cols:
+        for sd in seeds:
+            o = oracle.shuffled_order(col[0], sd)
+            r = np.zeros(col[0], np.int32)
+            r[o] = np.arange(col[0], dtype=np.int32)
+            rank.append(r)
+    if run_window:
+        got = g.whispers(run_window, np.concatenate(init), np.concatenate(rank), n_orders=len(seeds))
+        assert np.array_equal(got, np.concatenate(want))
+    n_links, replayed = adj.size, g.replayed
+    g.close()
+    pairs.close()
+    return n_links, replayed, len(run_window)
+
+
+@pytest.mark.parametrize("case", ["ont", "hifi"])
+def test_graph_and_whispers_match_oracle(ctx, oracle, case):
+    cbs, err = {"ont": ([cases.small_case(seed=91, length=20000, depth=50, mean_len=5000, error=0.06), cases.medium_case()], 0.06),
+                "hifi": ([cases.hifi_case()], 0.01)}[case]
+    cols, windows = [], []
+    for c, cb in enumerate(cbs):
+        col, pos = cases.snp_columns(oracle, cb, err)
+        cols.append(col)
+        windows += [(c, masked, inside[:5]) for masked, inside in cases.windows_of(col, pos)]
+    assert len(windows) >= 4
+    links, _, runs = _check_batch(ctx, oracle, cols, windows, err, [PIN_SEED])
+    assert links > 0 and runs > 0
+
+
+def test_several_sweep_orders(ctx, oracle):
+    """unpinned mode: a different shuffled order per sweep (n_orders > 1)"""
+    cb = cases.small_case(seed=91, length=20000, depth=50, mean_len=5000, error=0.06)
+    col, pos = cases.snp_columns(oracle, cb, 0.06)
+    windows = [(0, masked, inside[:6]) for masked, inside in cases.windows_of(col, pos)]
+    _check_batch(ctx, oracle, [col], windows, 0.06, [11, 22, 33, 44])
+
+
+def test_tied_distances_are_replayed_exactly(ctx, oracle):
+    """few SNPs -> coarse distances -> equal keys straddle the "first five neighbours" cut; nodes with more than
+    32 neighbours take the shared-memory counting path of the clustering kernel; error rates above 0.5 make the
+    zero distances linkable"""
+    rng = np.random.default_rng(17)
+    total_replayed = 0
+    for n_reads, n_snps, err in [(40, 6, 0.1), (90, 9, 0.15), (33, 4, 0.3), (64, 12, 0.6), (200, 5, 0.2), (1, 3, 0.1), (2, 3, 0.1)]:
+        col = cases.coarse_columns(rng, n_reads, n_snps)
+        keep = max(1, n_reads - 5)
+        masked = np.sort(rng.choice(n_reads, size=keep, replace=False)).astype(np.int32)
+        windows = [(0, masked, list(range(n_snps))), (0, masked[: max(1, keep // 2)], [0, 1])]
+        _, replayed, _ = _check_batch(ctx, oracle, [col], windows, err, [PIN_SEED])
+        total_replayed += replayed
+    assert total_replayed > 0
+
+
+def test_empty_batches(ctx, oracle):
+    rng = np.random.default_rng(3)
+    col = cases.coarse_columns(rng, 20, 4)
+    pairs = api.Pairs(ctx, [col])
+    pairs.compute()
+    g = api.Graph(pairs, [], 0.1)
+    g.build()
+    adj_off, adj = g.adjacency()
+    assert adj_off.tolist() == [0] and adj.size == 0
+    g.close()
+    g = api.Graph(pairs, [(0, np.zeros(0, np.int32)), (0, np.array([3], np.int32))], 0.1)
+    g.build()
+    adj_off, adj = g.adjacency()
+    assert adj_off.tolist() == [0, 0] and adj.size == 0
+    out = g.whispers([1], np.array([0], np.int32), np.arange(20, dtype=np.int32))
+    assert out.tolist() == [0]
+    g.close()
+    pairs.close()
+
+
+def _gro_pair(tmp, chunks, err, low="0", rare="0", amp="0", ploidy=None, threads="4", env=None):
+    for i, c in enumerate(chunks):
+        c.name = f"ctg{i}"
+    gfa, reads, sam = synth.write_files(chunks, os.path.join(tmp, "in"))
+    col = os.path.join(tmp, "a.col")
+    subprocess.run([REF_CV, gfa, reads, sam, "4", tmp, os.path.join(tmp, "err"), amp, "0", col, os.path.join(tmp, "a.vcf"), "0.33"],
+                   check=True, stdout=subprocess.DEVNULL)
+    pl = os.path.join(tmp, "ploidy.txt")
+    if ploidy:
+        with open(pl, "w") as f:
+            f.write("".join(f"{c.name}\t{ploidy}\n" for c in chunks))
+    ref, ours = os.path.join(tmp, "ref.gro"), os.path.join(tmp, "ours.gro")
+    subprocess.run([REF_SR, col, "1", err, pl, low, rare, amp, ref, "0"], check=True, stdout=subprocess.DEVNULL)
+    e = dict(os.environ, HS_PIN_SEED=str(PIN_SEED), **(env or {}))
+    subprocess.run([OURS, col, threads, err, pl, low, rare, amp, ours, "0"], check=True, stdout=subprocess.DEVNULL, env=e)
+    return open(ref, "rb").read(), open(ours, "rb").read()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SR), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", ["ont_multi", "hifi", "low_memory", "rarest", "ploidy", "coverage_over_1000", "amplicon"])
+def test_gro_identical_to_pinned_reference(tmp_path, case):
+    assert os.path.exists(OURS), "build hairsplitter_b200/host first (python -c 'import __graft_entry__ as g; g.build()')"
+    kw = {}
+    if case == "ont_multi":
+        chunks = [cases.small_case(seed=102, length=40000, depth=70, mean_len=7000, error=0.06),
+                  cases.small_case(seed=101, length=60000, depth=60, mean_len=9000, error=0.10, n_strains=2),
+                  cases.small_case(seed=5, length=3000, depth=12, mean_len=900, hard=0.4),
+                  cases.small_case(seed=6, length=90, depth=5, mean_len=60)]
+        err = "0.06"
+    elif case == "hifi":
+        chunks, err = [cases.hifi_case()], "0.01"
+    elif case == "low_memory":
+        chunks, err, kw = [cases.small_case(seed=103, length=12000, depth=40, mean_len=4000, error=0.06)], "0.06", dict(low="1")
+    elif case == "rarest":
+        chunks, err, kw = [cases.small_case(seed=104, length=30000, depth=50, mean_len=5000, error=0.06)], "0.06", dict(rare="0.2")
+    elif case == "ploidy":
+        chunks, err, kw = [cases.small_case(seed=105, length=30000, depth=60, mean_len=5000, error=0.05)], "0.05", dict(ploidy=2)
+    elif case == "coverage_over_1000":
+        chunks, err = [cases.small_case(seed=107, length=1500, depth=1500, mean_len=1400, error=0.05)], "0.05"
+    else:
+        chunks = [cases.small_case(seed=108, length=2500, depth=300, mean_len=2400, error=0.05),
+                  cases.small_case(seed=109, length=1200, depth=30, mean_len=800, error=0.05, n_strains=2)]
+        err, kw = "0.05", dict(amp="1")
+    ref, ours = _gro_pair(str(tmp_path), chunks, err, **kw)
+    assert ref == ours
+    assert ref.count(b"GROUP") >= 1
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SR), reason="oracle/_ref not built")
+def test_two_gpus_give_the_same_gro(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    chunks = [cases.small_case(seed=102, length=40000, depth=70, mean_len=7000, error=0.06),
+              cases.small_case(seed=101, length=60000, depth=60, mean_len=9000, error=0.10, n_strains=2), cases.hifi_case()]
+    ref, ours = _gro_pair(str(tmp_path), chunks, "0.06", env={"HSGPU_NGPUS": "2"})
+    assert ref == ours
+
+
+def test_unpinned_run_is_a_valid_clustering(tmp_path):
+    """without HS_PIN_SEED the sweep orders are random (as in the reference): same windows and reads, labels may differ"""
+    chunks = [cases.small_case(seed=102, length=40000, depth=70, mean_len=7000, error=0.06)]
+    chunks[0].name = "ctg0"
+    tmp = str(tmp_path)
+    gfa, reads, sam = synth.write_files(chunks, os.path.join(tmp, "in"))
+    col = os.path.join(tmp, "a.col")
+    subprocess.run([REF_CV, gfa, reads, sam, "4", tmp, os.path.join(tmp, "err"), "0", "0", col, os.path.join(tmp, "a.vcf"), "0.33"],
+                   check=True, stdout=subprocess.DEVNULL)
+    env = {k: v for k, v in os.environ.items() if k != "HS_PIN_SEED"}
+    out = {}
+    for tag, extra in (("free", {}), ("pin", {"HS_PIN_SEED": str(PIN_SEED)})):
+        path = os.path.join(tmp, tag + ".gro")
+        subprocess.run([OURS, col, "4", "0.06", "none", "0", "0", "0", path, "0"], check=True, stdout=subprocess.DEVNULL,
+                       env=dict(env, **extra))
+        out[tag] = [l.split("\t") for l in open(path) if l.startswith("GROUP")]
+    assert len(out["free"]) == len(out["pin"]) > 5
+    for a, b in zip(out["free"], out["pin"]):
+        assert a[:4] == b[:4]  # window bounds and the reads present
+
+
+def test_usage_and_help_status():
+    r = subprocess.run([OURS, "--help"], stdout=subprocess.PIPE)
+    assert r.returncode == 0 and b"Usage" in r.stdout
+    r = subprocess.run([OURS], stdout=subprocess.PIPE)
+    assert r.returncode == 1
