@@ -130,11 +130,14 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
     const uint8_t** s_ptr = reinterpret_cast<const uint8_t**>(s_order + CR_ORD * HS_TILE);  // [128]
     uint8_t* s_vmask = reinterpret_cast<uint8_t*>(s_ptr + CR_META);                      // [128]
     __shared__ unsigned long long s_depth;
-    __shared__ HsRankLut s_lut;
+    __shared__ __align__(16) uint32_t s_lut_words[HS_RANK_LUT_FAST_BYTES / 4];  // the part of HsRankLut hs_rank_fast reads
     __shared__ int s_scan[4];
     __shared__ unsigned int s_base[2];
 
     const int tid = threadIdx.x;
+    // the column this thread owns: lane l of warp w takes column 4l + w, so that the 32 lanes of a warp sit in
+    // 32 different shared-memory banks whatever bins they touch (byte histogram rows are 128 B = 32 banks)
+    const int col = 4 * (tid & 31) + (tid >> 5);
     const int64_t tile = blockIdx.x;
     const int c = a.tile_contig[tile];
     const int q0 = (int)(tile - a.tile_base[c]) * HS_TILE;
@@ -148,11 +151,13 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
     {
         uint4* h4 = reinterpret_cast<uint4*>(s_hist);
         for (int i = tid; i < CR_BINS * HS_TILE * (int)sizeof(H) / 16; i += HS_TILE) h4[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < HS_RANK_LUT_FAST_BYTES / 4; i += HS_TILE)
+            s_lut_words[i] = __ldg(reinterpret_cast<const uint32_t*>(a.lut) + i);
     }
     __syncthreads();
     s_hist[tid] = 1;  // bin 0 ("no cell") never looks like a first sighting
     int m = 0, rows_done = 0;
-    H* const hcol = s_hist + tid;
+    H* const hcol = s_hist + col;
     const int crow = tid >> 3, cpart = tid & 7;  // this thread's copy slot in a batch: row, 16-byte part
     for (int sb = 0; sb < nlist; sb += CR_META) {
         const int nmeta = min(CR_META, nlist - sb);
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
                               ok ? (const void*)(s_ptr[row] + 16 * cpart) : (const void*)a.codes, ok ? 16 : 0);
                 asm volatile("cp.async.commit_group;\n" ::: "memory");
             }
-            const unsigned char* colp = s_rows + (b & 1) * CR_ROWS * HS_TILE + tid;
+            const unsigned char* colp = s_rows + (b & 1) * CR_ROWS * HS_TILE + col;
             int code[CR_ROWS];
 #pragma unroll
             for (int row = 0; row < CR_ROWS; row++) code[row] = colp[row * HS_TILE];
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
                 const int bin = max(code[row], 32) - 32;
                 const unsigned int cnt = hcol[bin * HS_TILE];
                 if (cnt == 0) {
-                    if (m < CR_ORD) s_order[m * HS_TILE + tid] = (uint8_t)code[row];
+                    if (m < CR_ORD) s_order[m * HS_TILE + col] = (uint8_t)code[row];
                     m++;
                 }
                 hcol[bin * HS_TILE] = (H)(cnt + 1);
@@ -209,11 +214,8 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
     }
     // ---- ranking. Ties are decided by the bucket table (rank.cuh); the columns it cannot decide are
     // deferred, so that no CTA waits for a straggling replay.
-    __syncthreads();
-    for (int i = tid; i < (int)sizeof(HsRankLut); i += HS_TILE)
-        reinterpret_cast<uint8_t*>(&s_lut)[i] = reinterpret_cast<const uint8_t*>(a.lut)[i];
-    __syncthreads();
-    const int q = q0 + tid;
+    const HsRankLut* const s_lut = reinterpret_cast<const HsRankLut*>(s_lut_words);
+    const int q = q0 + col;
     const int mr = a.min_reads[c];
     const int64_t gbase = a.col_base[c];
     const unsigned int depth = (unsigned int)(rows_done + 1) - hcol[0];
@@ -222,10 +224,10 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
         if (m > CR_ORD) {
             defer = 2;
         } else {
-            SmemAcc<H> acc{s_order, s_hist, tid};
+            SmemAcc<H> acc{s_order, s_hist, col};
             int k0, k1;
             unsigned c0, c1, c2;
-            if (hs_rank_fast(acc, m, &s_lut, k0, k1, c0, c1, c2) != 0) defer = 1;
+            if (hs_rank_fast(acc, m, s_lut, k0, k1, c0, c1, c2) != 0) defer = 1;
             else write_column(a, gbase + q, k0, k1, c0, c1, c2, mr);
         }
         a.depth[gbase + q] = depth;
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
                 a.arena[off] = (uint32_t)(gbase + q);
                 a.arena[off + 1] = (uint32_t)m;
                 for (int k = 0; k < m; k++) {
-                    const int key = s_order[k * HS_TILE + tid];
+                    const int key = s_order[k * HS_TILE + col];
                     a.arena[off + 2 + k] = ((uint32_t)hcol[(key - 32) * HS_TILE] << 8) | (uint32_t)key;
                 }
                 a.item_off[s_base[1] + iwoff + __popc(dm & ((1u << lane) - 1u))] = off;
@@ -282,8 +284,9 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
     if (tid == 0 && s_depth) atomicAdd(a.depth_sum + c, s_depth);
 }
 
-// Deferred tie resolution, one thread per arena item: the hash-bit table first (rank.cuh), the literal
-// replay of the reference's map + sort for what is left (about 1 % of the columns at 10 % error, 60x).
+// Deferred tie resolution, one thread per arena item: the hash-bit table (rank.cuh) decides most of them;
+// what is left (about 1 % of the columns at 10 % error, 60x) is compacted into a list for the literal replay
+// of the reference's map + sort, so that the replay runs with full warps.
 struct ItemAcc {
     const uint8_t* order;
     const uint16_t* cnt;
@@ -291,14 +294,28 @@ struct ItemAcc {
     __device__ __forceinline__ unsigned count(int key) const { return cnt[key - HS_CODE0]; }
 };
 
-__global__ void __launch_bounds__(128) column_rank_deferred_kernel(ColumnArgs a, int n_contigs) {
+__device__ __forceinline__ int contig_of_column(const int64_t* __restrict__ col_base, int n_contigs, int64_t g) {
+    int lo = 0, hi = n_contigs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (col_base[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// LITERAL = false: items 0 .. counters[1], hash-bit table, leftovers appended to lit_items (counters[3])
+// LITERAL = true: the items listed in lit_items, literal replay
+template <bool LITERAL>
+__global__ void __launch_bounds__(128) column_rank_deferred_kernel(ColumnArgs a, int n_contigs, uint32_t* lit_items) {
     __shared__ HsRankLut s_lut;
-    for (int i = threadIdx.x; i < (int)sizeof(HsRankLut); i += blockDim.x)
-        reinterpret_cast<uint8_t*>(&s_lut)[i] = reinterpret_cast<const uint8_t*>(a.lut)[i];
-    __syncthreads();
-    const unsigned n = a.counters[1];
+    if (!LITERAL) {
+        for (int i = threadIdx.x; i < (int)(sizeof(HsRankLut) / 4); i += blockDim.x)
+            reinterpret_cast<uint32_t*>(&s_lut)[i] = reinterpret_cast<const uint32_t*>(a.lut)[i];
+        __syncthreads();
+    }
+    const unsigned n = LITERAL ? a.counters[3] : a.counters[1];
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned off = a.item_off[i];
+        const unsigned off = LITERAL ? lit_items[i] : a.item_off[i];
         if (off == 0xffffffffu) continue;  // went to the re-read list
         const int64_t g = a.arena[off];
         const int m = (int)a.arena[off + 1];
@@ -309,16 +326,17 @@ __global__ void __launch_bounds__(128) column_rank_deferred_kernel(ColumnArgs a,
             order[k] = (uint8_t)(e & 0xff);
             cnt[(e & 0xff) - HS_CODE0] = (uint16_t)(e >> 8);
         }
-        int lo = 0, hi = n_contigs - 1;  // contig of this column
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (a.col_base[mid] <= g) lo = mid; else hi = mid - 1;
-        }
         ItemAcc acc{order, cnt};
         int k0, k1;
         unsigned c0, c1, c2;
-        if (hs_rank_hashbits(acc, m, &s_lut, k0, k1, c0, c1, c2)) hs_rank_literal(acc, m, k0, k1, c0, c1, c2);
-        write_column(a, g, k0, k1, c0, c1, c2, a.min_reads[lo]);
+        if (LITERAL) {
+            hs_rank_literal(acc, m, k0, k1, c0, c1, c2);
+        } else if (hs_rank_hashbits(acc, m, &s_lut, k0, k1, c0, c1, c2) &&
+                   hs_rank_slotorder(acc, m, &s_lut, k0, k1, c0, c1, c2)) {
+            lit_items[atomicAdd(a.counters + 3, 1u)] = off;
+            continue;
+        }
+        write_column(a, g, k0, k1, c0, c1, c2, a.min_reads[contig_of_column(a.col_base, n_contigs, g)]);
     }
 }
 
@@ -625,7 +643,7 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
         if (!p->d_arena) {
             p->arena_words = (unsigned int)std::min<int64_t>(2 * p->n_cols + 1024, 0x7fffffff);
             HS_CUDA(ctx, hs_alloc(ctx, &p->d_arena, p->arena_words));
-            HS_CUDA(ctx, hs_alloc(ctx, &p->d_item_off, p->n_cols));
+            HS_CUDA(ctx, hs_alloc(ctx, &p->d_item_off, p->n_cols + p->n_cols / 2 + 512));  // items, then the literal list
         }
         a.arena = p->d_arena;
         a.arena_words = p->arena_words;
@@ -634,10 +652,17 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
         a.reread = p->d_work + 4;
         HS_CUDA(ctx, cudaMemsetAsync(p->d_work, 0, 4 * sizeof(int32_t), ctx->stream));
         HS_KERNEL(ctx, "column_rank_kernel", column_rank_kernel<uint8_t><<<(unsigned)p->n_tiles, HS_TILE, column_smem<uint8_t>(), ctx->stream>>>(a));
+        {
+            const int rc_max = hs_resolve_max_tile_reads(p);
+            if (rc_max) return rc_max;
+        }
         if (p->max_tile_reads > CR_U8_MAX)  // deep tiles (amplicons): 16-bit bins
             HS_KERNEL(ctx, "column_rank_kernel<u16>", column_rank_kernel<uint16_t><<<(unsigned)p->n_tiles, HS_TILE, column_smem<uint16_t>(), ctx->stream>>>(a));
+        uint32_t* lit_items = p->d_item_off + p->n_cols;
         HS_KERNEL(ctx, "column_rank_deferred_kernel",
-                  column_rank_deferred_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a, nc));
+                  column_rank_deferred_kernel<false><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a, nc, lit_items));
+        HS_KERNEL(ctx, "column_rank_deferred_kernel<literal>",
+                  column_rank_deferred_kernel<true><<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(a, nc, lit_items));
         LiteralArgs la;
         la.work = a.reread;
         la.n_work = a.counters + 2;

@@ -29,6 +29,10 @@ struct hsgpu_ctx {
     std::vector<HsProfEntry> prof;
     std::string prof_report;
     void* d_rank_lut = nullptr;  // HsRankLut (rank.cuh), built once per context
+    // one pinned word + event for a value read back without a stream stall (hs_resolve_max_tile_reads)
+    int64_t* h_scratch = nullptr;
+    cudaEvent_t scratch_event = nullptr;
+    struct hsgpu_pileup* scratch_owner = nullptr;
 };
 
 void hs_prof_begin(hsgpu_ctx* ctx, const char* name);
@@ -170,6 +174,9 @@ struct hsgpu_pileup {
     int64_t* d_tile_off = nullptr;
     int32_t* d_tile_reads = nullptr;
     int64_t tile_entries = 0;
+    int64_t n_super = 0;              // super-tiles of 4 tiles (first level of the index build)
+    int64_t* d_super_base = nullptr;  // first super-tile of every contig
+    int64_t* d_super_off = nullptr;
 
     // column summaries (call_variants)
     uint8_t* d_k0 = nullptr;
@@ -192,6 +199,8 @@ struct hsgpu_pileup {
     int64_t* d_tile_sus = nullptr; // accepted suspects per tile, then its exclusive scan
     bool have_col_off = false;
 };
+
+int hs_resolve_max_tile_reads(hsgpu_pileup* p);
 
 // column flags
 #define HS_FLAG_CANDIDATE 1  // passes :525-528 (everything but the spacing rule)

@@ -122,6 +122,12 @@ int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
             return hs_cuda_fail(nullptr, e, "rank table upload", __FILE__, __LINE__);
         }
     }
+    e = cudaHostAlloc((void**)&ctx->h_scratch, 64, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->scratch_event, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        hsgpu_ctx_destroy(ctx);
+        return hs_cuda_fail(nullptr, e, "pinned scratch", __FILE__, __LINE__);
+    }
     *out = ctx;
     return HSGPU_OK;
 }
@@ -130,6 +136,8 @@ void hsgpu_ctx_destroy(hsgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     cudaStreamDestroy(ctx->stream);
     if (ctx->d_rank_lut) cudaFree(ctx->d_rank_lut);
     delete ctx;

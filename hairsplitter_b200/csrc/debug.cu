@@ -15,7 +15,7 @@ struct HostAcc {
 
 // out = k0, k1, c0, c1, c2 of one column (codes in the reference's in-column order), out[5] = 1 when the
 // literal replay was needed, 0 when the bucket table decided. mode 0 = fast path with fallback (what the
-// kernel does), 1 = always literal. out[5]: 0 = decided by the bucket / hash-bit tables, 2 = literal replay
+// kernels do), 1 = always literal, 2 = the slot-order path alone (falls back on the literal replay). out[5]: 0 = decided by the bucket / hash-bit tables, 2 = literal replay
 // after both table passes gave up, 1 = forced literal.
 void hsgpu_debug_rank_column(const uint8_t* codes, int n, int32_t* out, int mode) {
     static HsRankLut lut;
@@ -34,7 +34,11 @@ void hsgpu_debug_rank_column(const uint8_t* codes, int n, int32_t* out, int mode
     int k0 = 0, k1 = 0;
     unsigned c0 = 0, c1 = 0, c2 = 0;
     int lit = mode == 1 ? 1 : hs_rank_fast(acc, m, &lut, k0, k1, c0, c1, c2);
-    if (lit && mode != 1) lit = 2 * hs_rank_hashbits(acc, m, &lut, k0, k1, c0, c1, c2);  // 0 resolved, 2 literal
+    if (mode == 2) lit = 2 * hs_rank_slotorder(acc, m, &lut, k0, k1, c0, c1, c2);  // slot-order path alone
+    else if (lit && mode != 1) {
+        lit = 2 * hs_rank_hashbits(acc, m, &lut, k0, k1, c0, c1, c2);  // 0 resolved, 2 literal
+        if (lit) lit = 2 * hs_rank_slotorder(acc, m, &lut, k0, k1, c0, c1, c2);
+    }
     if (lit) hs_rank_literal(acc, m, k0, k1, c0, c1, c2);
     out[0] = k0;
     out[1] = k1;

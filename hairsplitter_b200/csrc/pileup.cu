@@ -27,6 +27,8 @@ __device__ __forceinline__ bool op_consumes_t(int ty) {
 // (S and H both advance the read cursor in the reference, :269-273). Anything else is IRREGULAR and
 // goes through pileup_generic_kernel.
 #define HS_READ_IRREGULAR 1
+#define HS_SUPER_TILES 4  // tiles per super-tile of the two-level tile index
+#define HS_SUPER_COLS (HS_SUPER_TILES * HS_TILE)
 __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32_t* __restrict__ cigar,
                                                    const int64_t* __restrict__ cigar_off,
                                                    const int32_t* __restrict__ read_start,
@@ -34,7 +36,7 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
                                                    const int32_t* __restrict__ contig_len,
                                                    int32_t* __restrict__ read_end, int64_t* __restrict__ row_alloc,
                                                    int32_t* __restrict__ read_tlead, uint8_t* __restrict__ read_flags,
-                                                   unsigned long long* __restrict__ n_irregular) {
+                                                   unsigned long long* __restrict__ totals) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= n_reads) return;
@@ -79,7 +81,11 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
         row_alloc[r] = alloc;
         read_tlead[r] = (int32_t)tlead;
         read_flags[r] = irregular ? HS_READ_IRREGULAR : 0;
-        if (irregular) atomicAdd(n_irregular, 1ull);
+        if (irregular) atomicAdd(totals + 2, 1ull);
+        if (end > start) {  // exact sizes of the two index levels (tile_index_kernel), known before they are built
+            atomicAdd(totals + 1, (unsigned long long)((end - 1) / HS_TILE - start / HS_TILE + 1));
+            atomicAdd(totals + 4, (unsigned long long)((end - 1) / HS_SUPER_COLS - start / HS_SUPER_COLS + 1));
+        }
     }
 }
 
@@ -540,24 +546,30 @@ __global__ void __launch_bounds__(256) pileup_generic_kernel(PileupArgs a) {
 
 
 // ---- tile index: for every 128-column tile, the reads overlapping it in ascending order ----------
-// One warp per tile scans the reads of the tile's contig (a few thousand) with an ordered
-// ballot-compaction; pass 0 counts, pass 1 fills. No atomics, no sort, deterministic.
+// Two levels, both an ordered ballot-compaction by one warp per unit (pass 0 counts, pass 1 fills; no
+// atomics, no sort, deterministic): first the reads over every super-tile of 4 tiles, found by scanning the
+// reads of the contig (a few thousand); then the reads over every tile, found by scanning the list of its
+// super-tile (about depth x 1.05 entries) instead of the whole contig.
 template <bool FILL>
-__global__ void __launch_bounds__(256) tile_index_kernel(int64_t n_tiles, const int32_t* __restrict__ tile_contig,
-                                                         const int64_t* __restrict__ tile_base,
-                                                         const int64_t* __restrict__ contig_read_off,
-                                                         const int32_t* __restrict__ read_start,
-                                                         const int32_t* __restrict__ read_end,
-                                                         int64_t* __restrict__ tile_cnt_or_off,
-                                                         int32_t* __restrict__ tile_reads,
-                                                         unsigned long long* __restrict__ max_count) {
+__global__ void __launch_bounds__(256) super_index_kernel(int64_t n_super, int n_contigs,
+                                                          const int64_t* __restrict__ super_base,
+                                                          const int64_t* __restrict__ contig_read_off,
+                                                          const int32_t* __restrict__ read_start,
+                                                          const int32_t* __restrict__ read_end,
+                                                          int64_t* __restrict__ super_cnt_or_off,
+                                                          int32_t* __restrict__ super_reads) {
     const int lane = threadIdx.x & 31;
-    const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (tile >= n_tiles) return;
-    const int c = tile_contig[tile];
-    const int q0 = (int)(tile - tile_base[c]) * HS_TILE, q1 = q0 + HS_TILE;
+    const int64_t su = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (su >= n_super) return;
+    int lo = 0, hi = n_contigs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (super_base[mid] <= su) lo = mid; else hi = mid - 1;
+    }
+    const int c = lo;
+    const int q0 = (int)(su - super_base[c]) * HS_SUPER_COLS, q1 = q0 + HS_SUPER_COLS;
     const int64_t r0 = contig_read_off[c], r1 = contig_read_off[c + 1];
-    int64_t out = FILL ? tile_cnt_or_off[tile] : 0;
+    int64_t out = FILL ? super_cnt_or_off[su] : 0;
 #pragma unroll 4
     for (int64_t rb = r0; rb < r1; rb += 32) {
         const int64_t r = rb + lane;
@@ -567,7 +579,43 @@ __global__ void __launch_bounds__(256) tile_index_kernel(int64_t n_tiles, const 
             hit = (e > s) && (s < q1) && (e > q0);
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (FILL && hit) tile_reads[out + __popc(m & ((1u << lane) - 1u))] = (int32_t)r;
+        if (FILL && hit) super_reads[out + __popc(m & ((1u << lane) - 1u))] = (int32_t)r;
+        out += __popc(m);
+    }
+    if (!FILL && lane == 0) super_cnt_or_off[su] = out;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) tile_index_kernel(int64_t n_tiles, const int32_t* __restrict__ tile_contig,
+                                                         const int64_t* __restrict__ tile_base,
+                                                         const int64_t* __restrict__ super_base,
+                                                         const int64_t* __restrict__ super_off,
+                                                         const int32_t* __restrict__ super_reads,
+                                                         const int32_t* __restrict__ read_start,
+                                                         const int32_t* __restrict__ read_end,
+                                                         int64_t* __restrict__ tile_cnt_or_off,
+                                                         int32_t* __restrict__ tile_reads,
+                                                         unsigned long long* __restrict__ max_count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    const int c = tile_contig[tile];
+    const int64_t lt = tile - tile_base[c];
+    const int q0 = (int)lt * HS_TILE, q1 = q0 + HS_TILE;
+    const int64_t su = super_base[c] + lt / HS_SUPER_TILES;
+    const int64_t l0 = super_off[su], l1 = super_off[su + 1];
+    int64_t out = FILL ? tile_cnt_or_off[tile] : 0;
+    for (int64_t lb = l0; lb < l1; lb += 32) {
+        const int64_t l = lb + lane;
+        bool hit = false;
+        int32_t r = 0;
+        if (l < l1) {
+            r = __ldg(super_reads + l);
+            const int s = __ldg(read_start + r), e = __ldg(read_end + r);
+            hit = (s < q1) && (e > q0);  // e > s holds for every listed read
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (FILL && hit) tile_reads[out + __popc(m & ((1u << lane) - 1u))] = r;
         out += __popc(m);
     }
     if (!FILL && lane == 0) {
@@ -585,6 +633,17 @@ __global__ void cigar_expand_kernel(int64_t n, const uint16_t* __restrict__ in, 
 }
 
 // ---- host side --------------------------------------------------------------------------------
+// hsgpu_pileup_build leaves the deepest tile's read count in flight (pinned scratch of the context + event)
+int hs_resolve_max_tile_reads(hsgpu_pileup* p) {
+    hsgpu_ctx* ctx = p->ctx;
+    if (p->max_tile_reads >= 0) return HSGPU_OK;
+    if (ctx->scratch_owner != p) HS_FAIL(ctx, HSGPU_ERR_STATE, "libhsgpu: tile depth of this pileup was lost");
+    HS_CUDA(ctx, cudaEventSynchronize(ctx->scratch_event));
+    p->max_tile_reads = ctx->h_scratch[0];
+    ctx->scratch_owner = nullptr;
+    return HSGPU_OK;
+}
+
 extern "C" {
 
 void hsgpu_pileup_destroy(hsgpu_pileup* p) {
@@ -616,6 +675,9 @@ void hsgpu_pileup_destroy(hsgpu_pileup* p) {
     hs_free(ctx, p->d_stats);
     hs_free(ctx, p->d_tile_off);
     hs_free(ctx, p->d_tile_reads);
+    hs_free(ctx, p->d_super_base);
+    hs_free(ctx, p->d_super_off);
+    if (ctx->scratch_owner == p) ctx->scratch_owner = nullptr;
     hs_free(ctx, p->d_k0);
     hs_free(ctx, p->d_k1);
     hs_free(ctx, p->d_flags);
@@ -654,7 +716,8 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
     p->h_tile_base.resize(nc + 1);
     p->h_suspect_base.resize(nc + 1);
     p->h_stats.assign((size_t)3 * nc, 0);
-    int64_t cols = 0, tiles = 0, sus = 0;
+    int64_t cols = 0, tiles = 0, sus = 0, supers = 0;
+    std::vector<int64_t> super_base((size_t)nc + 1);
     for (int c = 0; c < nc; c++) {
         if (in->contig_len[c] < 0 || in->contig_read_off[c + 1] < in->contig_read_off[c]) {
             delete p;
@@ -663,13 +726,17 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
         p->h_col_base[c] = cols;
         p->h_tile_base[c] = tiles;
         p->h_suspect_base[c] = sus;
+        super_base[c] = supers;
         cols += in->contig_len[c];
         tiles += (in->contig_len[c] + HS_TILE - 1) / HS_TILE;
+        supers += (in->contig_len[c] + HS_SUPER_COLS - 1) / HS_SUPER_COLS;
         sus += in->contig_len[c] / 6 + 2;  // suspects are > 5 columns apart (:529)
     }
     p->h_col_base[nc] = cols;
     p->h_tile_base[nc] = tiles;
     p->h_suspect_base[nc] = sus;
+    super_base[nc] = supers;
+    p->n_super = supers;
     p->n_cols = cols;
     p->n_tiles = tiles;
     p->n_cigar = in->cigar_off[nr];
@@ -694,7 +761,7 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
     A(d_read_contig, nr); A(d_read_bases, read_words); A(d_read_word_off, nr + 1); A(d_read_len, nr);
     A(d_cigar, p->n_cigar); A(d_cigar_off, nr + 1); A(d_read_start, nr); A(d_read_strand, nr);
     A(d_read_end, nr); A(d_read_tlead, nr); A(d_read_flags, nr); A(d_next_read, 1); A(d_row_alloc, nr + 1); A(d_row_base, nr); A(d_stats, 3 * nc);
-    A(d_tile_off, tiles + 1); A(d_suspect_base, nc + 1);
+    A(d_tile_off, tiles + 1); A(d_suspect_base, nc + 1); A(d_super_base, nc + 1); A(d_super_off, supers + 1);
 #undef A
     HS_CUDA(ctx, hs_h2d(ctx, p->d_contig_len, in->contig_len, nc));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_contig_bases, in->contig_bases, contig_words));
@@ -703,6 +770,7 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
     HS_CUDA(ctx, hs_h2d(ctx, p->d_col_base, p->h_col_base.data(), nc + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_tile_base, p->h_tile_base.data(), nc + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_suspect_base, p->h_suspect_base.data(), nc + 1));
+    HS_CUDA(ctx, hs_h2d(ctx, p->d_super_base, super_base.data(), nc + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_tile_contig, tile_contig.data(), tiles));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_contig, read_contig.data(), nr));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_bases, in->read_bases, read_words));
@@ -740,36 +808,60 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     hs_free(ctx, p->d_tile_reads);
     p->built = p->ranked = p->have_col_off = false;
     HS_CUDA(ctx, cudaMemsetAsync(p->d_stats, 0, sizeof(unsigned long long) * 3 * p->n_contigs, ctx->stream));
-    int64_t* d_totals = nullptr;  // codes bytes, tile index entries, irregular reads, most reads over one tile
-    HS_CUDA(ctx, hs_alloc(ctx, &d_totals, 4));
-    HS_CUDA(ctx, cudaMemsetAsync(d_totals, 0, 4 * sizeof(int64_t), ctx->stream));
+    // d_totals: codes bytes, tile index entries, irregular reads, most reads over one tile, super-tile index entries
+    int64_t* d_totals = nullptr;
+    HS_CUDA(ctx, hs_alloc(ctx, &d_totals, 5));
+    HS_CUDA(ctx, cudaMemsetAsync(d_totals, 0, 5 * sizeof(int64_t), ctx->stream));
     HS_CUDA(ctx, cudaMemsetAsync(p->d_next_read, 0, sizeof(unsigned int), ctx->stream));
     if (nr > 0) {
         HS_KERNEL(ctx, "span_kernel", span_kernel<<<rblocks, 256, 0, ctx->stream>>>(
             nr, p->d_cigar, p->d_cigar_off, p->d_read_start, p->d_read_contig, p->d_contig_len, p->d_read_end,
-            p->d_row_alloc, p->d_read_tlead, p->d_read_flags, reinterpret_cast<unsigned long long*>(d_totals + 2)));
+            p->d_row_alloc, p->d_read_tlead, p->d_read_flags, reinterpret_cast<unsigned long long*>(d_totals)));
     }
     int rc = hs_exclusive_scan_i64(ctx, p->d_row_alloc, p->d_row_alloc, nr, d_totals);
     if (rc) return rc;
-    if (p->n_tiles > 0) {
-        HS_KERNEL(ctx, "tile_index_kernel<false>", tile_index_kernel<false><<<(unsigned)((p->n_tiles + 7) / 8), 256, 0, ctx->stream>>>(
-            p->n_tiles, p->d_tile_contig, p->d_tile_base, p->d_contig_read_off, p->d_read_start, p->d_read_end,
-            p->d_tile_off, nullptr, reinterpret_cast<unsigned long long*>(d_totals + 3)));
-    }
-    rc = hs_exclusive_scan_i64(ctx, p->d_tile_off, p->d_tile_off, p->n_tiles, d_totals + 1);
-    if (rc) return rc;
-    int64_t totals[4] = {0, 0, 0, 0};
-    HS_CUDA(ctx, hs_d2h(ctx, totals, d_totals, 4));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the only host round trip of the build: three counts
-    hs_free(ctx, d_totals);
+    int64_t totals[5] = {0, 0, 0, 0, 0};
+    HS_CUDA(ctx, hs_d2h(ctx, totals, d_totals, 5));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the only host round trip of the build: the allocation sizes
     p->codes_bytes = totals[0];
     p->tile_entries = totals[1];
     p->n_irregular = totals[2];
-    p->max_tile_reads = totals[3];
     HS_CUDA(ctx, hs_alloc(ctx, &p->d_codes, p->codes_bytes + HS_ALIGN));
     HS_CUDA(ctx, hs_alloc(ctx, &p->d_tile_reads, p->tile_entries));
-    HS_CUDA(ctx, cudaMemcpyAsync(p->d_tile_off + p->n_tiles, &p->tile_entries, sizeof(int64_t), cudaMemcpyHostToDevice,
-                                 ctx->stream));
+    if (p->n_tiles > 0) {
+        int32_t* d_super_reads = nullptr;
+        HS_CUDA(ctx, hs_alloc(ctx, &d_super_reads, totals[4]));
+        const unsigned sblocks = (unsigned)((p->n_super + 7) / 8), tblocks = (unsigned)((p->n_tiles + 7) / 8);
+        HS_KERNEL(ctx, "super_index_kernel<false>", super_index_kernel<false><<<sblocks, 256, 0, ctx->stream>>>(
+            p->n_super, p->n_contigs, p->d_super_base, p->d_contig_read_off, p->d_read_start, p->d_read_end,
+            p->d_super_off, nullptr));
+        rc = hs_exclusive_scan_i64(ctx, p->d_super_off, p->d_super_off, p->n_super, p->d_super_off + p->n_super);
+        if (rc) return rc;
+        HS_KERNEL(ctx, "super_index_kernel<true>", super_index_kernel<true><<<sblocks, 256, 0, ctx->stream>>>(
+            p->n_super, p->n_contigs, p->d_super_base, p->d_contig_read_off, p->d_read_start, p->d_read_end,
+            p->d_super_off, d_super_reads));
+        HS_KERNEL(ctx, "tile_index_kernel<false>", tile_index_kernel<false><<<tblocks, 256, 0, ctx->stream>>>(
+            p->n_tiles, p->d_tile_contig, p->d_tile_base, p->d_super_base, p->d_super_off, d_super_reads,
+            p->d_read_start, p->d_read_end, p->d_tile_off, nullptr, reinterpret_cast<unsigned long long*>(d_totals + 3)));
+        rc = hs_exclusive_scan_i64(ctx, p->d_tile_off, p->d_tile_off, p->n_tiles, p->d_tile_off + p->n_tiles);
+        if (rc) return rc;
+        HS_KERNEL(ctx, "tile_index_kernel<true>", tile_index_kernel<true><<<tblocks, 256, 0, ctx->stream>>>(
+            p->n_tiles, p->d_tile_contig, p->d_tile_base, p->d_super_base, p->d_super_off, d_super_reads,
+            p->d_read_start, p->d_read_end, p->d_tile_off, p->d_tile_reads, nullptr));
+        hs_free(ctx, d_super_reads);
+        // the deepest tile picks the histogram width of hsgpu_column_rank: read back without stalling the stream
+        if (ctx->scratch_owner && ctx->scratch_owner != p) {
+            rc = hs_resolve_max_tile_reads(ctx->scratch_owner);
+            if (rc) return rc;
+        }
+        HS_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_totals + 3, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        HS_CUDA(ctx, cudaEventRecord(ctx->scratch_event, ctx->stream));
+        ctx->scratch_owner = p;
+        p->max_tile_reads = -1;
+    } else {
+        p->max_tile_reads = 0;
+    }
+    hs_free(ctx, d_totals);
     if (nr > 0) {
         PileupArgs a;
         a.n_reads = nr;
@@ -802,11 +894,6 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
         HS_KERNEL(ctx, "pileup_kernel", pileup_kernel<<<pgrid, 32 * PW_WARPS, 0, ctx->stream>>>(a));
         if (p->n_irregular > 0)
             HS_KERNEL(ctx, "pileup_generic_kernel", pileup_generic_kernel<<<rblocks, 256, 0, ctx->stream>>>(a));
-    }
-    if (p->n_tiles > 0) {
-        HS_KERNEL(ctx, "tile_index_kernel<true>", tile_index_kernel<true><<<(unsigned)((p->n_tiles + 7) / 8), 256, 0, ctx->stream>>>(
-            p->n_tiles, p->d_tile_contig, p->d_tile_base, p->d_contig_read_off, p->d_read_start, p->d_read_end,
-            p->d_tile_off, p->d_tile_reads, nullptr));
     }
     p->built = true;
     return HSGPU_OK;

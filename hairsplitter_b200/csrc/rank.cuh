@@ -270,14 +270,20 @@ HS_HD void hs_kc_std_sort(uint32_t* v, int n) {
 // plain (stable) insertion sort, so equal counts keep the iteration order. Hence: ties between keys with
 // pairwise distinct home buckets are decided by the precomputed bucket table below; everything else
 // (shared bucket, n > 16 where introsort is unstable) replays the reference's map + sort literally.
-struct HsRankLut {
-    uint8_t home[3][160];  // home bucket of key k in the table incarnation `level`
-    uint8_t hbits[3][160]; // the 5 hash bits robin_hood keeps in the info byte (robin_hood.h:1349-1356)
+struct alignas(16) HsRankLut {
+    // the part hs_rank_fast reads (HS_RANK_LUT_FAST_BYTES; the column kernel stages only this much)
+    uint16_t tie[4][160];  // (255 - home) << 8 | key: the tie-breaking half of hs_rank_fast's sort word
     uint8_t single[128];   // m == 1: second_base (a dummy key) for code 33 + i
     uint8_t empty[2];      // m == 0: ref_base, second_base
+    uint8_t pad_[2];
+    // hs_rank_hashbits
+    uint8_t home[4][160];  // home bucket of key k in the table incarnation `level`
+    uint8_t hbits[4][160]; // the 5 hash bits robin_hood keeps in the info byte (robin_hood.h:1349-1356)
 };
+#define HS_RANK_LUT_FAST_BYTES (4 * 160 * 2 + 128 + 4)
 
-HS_HD int hs_rank_level(int n) { return n <= 6 ? 0 : (n <= 12 ? 1 : 2); }
+// 8 / 16 / 32 / 64 buckets hold up to 6 / 12 / 25 / 51 keys (80 % load); larger n never reaches the tables
+HS_HD int hs_rank_level(int n) { return n <= 6 ? 0 : (n <= 12 ? 1 : (n <= 25 ? 2 : 3)); }
 
 // literal replay: keys in first-seen order via acc.key(k), counts via acc.count(key)
 template <class Acc>
@@ -304,7 +310,10 @@ HS_HD void hs_rank_literal(const Acc& acc, int m, int& k0, int& k1, unsigned& c0
     c2 = kc[2] >> 8;
 }
 
-// returns 0 when resolved on the fast path, 1 when the literal replay is needed (outputs then unset)
+// returns 0 when resolved on the fast path, 1 when the literal replay is needed (outputs then unset).
+// Branch-free in the keys: every key becomes one 32-bit word  count << 16 | (255 - home bucket) << 8 | key
+// (lut->tie), so that "larger word" means "earlier in the reference's sorted vector" whenever the two keys
+// differ in count or in home bucket; the three largest words come out of a 5-instruction min/max network.
 template <class Acc>
 HS_HD int hs_rank_fast(const Acc& acc, int m, const HsRankLut* lut, int& k0, int& k1, unsigned& c0, unsigned& c1,
                        unsigned& c2) {
@@ -321,51 +330,29 @@ HS_HD int hs_rank_fast(const Acc& acc, int m, const HsRankLut* lut, int& k0, int
         c1 = c2 = 0;
         return 0;
     }
-    c0 = c1 = c2 = 0;
-    k0 = k1 = 0;
-    for (int k = 0; k < m; k++) {
-        const int key = acc.key(k);
-        const unsigned cnt = acc.count(key);
-        if (cnt > c0) { c2 = c1; c1 = c0; k1 = k0; c0 = cnt; k0 = key; }
-        else if (cnt > c1) { c2 = c1; c1 = cnt; k1 = key; }
-        else if (cnt > c2) { c2 = cnt; }
-    }
-    if (c0 > c1 && c1 > c2) return 0;  // both ranks unique
     const int n = m + 3;
-    if (n > 16) return 1;
-    const uint8_t* home = lut->home[hs_rank_level(n)];
-    // T0 = keys with count c0, T1 = keys with count c1 (< c0); order inside a set = home bucket order
-    unsigned mask0 = 0, mask1 = 0;
-    int n0 = 0, n1 = 0, a0 = 0, a1 = 0, b0 = 0, h_a0 = 256, h_a1 = 256, h_b0 = 256;
-    bool dup0 = false, dup1 = false;
+    const uint16_t* tie = lut->tie[hs_rank_level(n)];
+    uint32_t t0 = 0, t1 = 0, t2 = 0;
     for (int k = 0; k < m; k++) {
         const int key = acc.key(k);
-        const unsigned cnt = acc.count(key);
-        const int h = home[key];
-        if (cnt == c0) {
-            n0++;
-            if (mask0 & (1u << h)) dup0 = true;
-            mask0 |= 1u << h;
-            if (h < h_a0) { h_a1 = h_a0; a1 = a0; h_a0 = h; a0 = key; }
-            else if (h < h_a1) { h_a1 = h; a1 = key; }
-        } else if (cnt == c1) {
-            n1++;
-            if (mask1 & (1u << h)) dup1 = true;
-            mask1 |= 1u << h;
-            if (h < h_b0) { h_b0 = h; b0 = key; }
-        }
+        uint32_t v = ((uint32_t)acc.count(key) << 16) | tie[key];
+        uint32_t hi = t0 > v ? t0 : v;
+        v = t0 > v ? v : t0;
+        t0 = hi;
+        hi = t1 > v ? t1 : v;
+        v = t1 > v ? v : t1;
+        t1 = hi;
+        t2 = t2 > v ? t2 : v;
     }
-    if (n0 >= 2) {
-        if (dup0) return 1;
-        k0 = a0;
-        k1 = a1;
-    } else {
-        k0 = a0;
-        if (n1 >= 2) {
-            if (dup1) return 1;
-            k1 = b0;
-        }  // n1 == 1: k1 from the first pass is that key
-    }
+    c0 = t0 >> 16;
+    c1 = t1 >> 16;
+    c2 = t2 >> 16;
+    k0 = (int)(t0 & 0xffu);
+    k1 = (int)(t1 & 0xffu);
+    if (c0 > c1 && c1 > c2) return 0;  // both ranks unique
+    if (n > 16) return 1;              // introsort is not stable
+    // neighbours in the ranking that agree in count AND home bucket: their slot order depends on the history
+    if ((t0 >> 8) == (t1 >> 8) || (t1 >> 8) == (t2 >> 8)) return 1;
     return 0;
 }
 
@@ -439,6 +426,53 @@ HS_HD int hs_rank_hashbits(const Acc& acc, int m, const HsRankLut* lut, int& k0,
     return 0;
 }
 
+// Third-level resolution for any n <= 51 (the columns whose ties meet libstdc++'s unstable introsort, n > 16):
+// the COMPLETE slot order of the final table incarnation is rebuilt from (home bucket, hash bits) -- under the
+// conditions of hs_rank_hashbits, now required of every key: no two keys agree in bucket and hash bits, no
+// entry 6 or more slots from home -- and the reference's std::sort is replayed on that order. This skips the
+// replay of the map itself (three or four table incarnations), which is most of hs_rank_literal's work.
+#define HS_RANK_SLOT_MAXN 51
+template <class Acc>
+HS_HD int hs_rank_slotorder(const Acc& acc, int m, const HsRankLut* lut, int& k0, int& k1, unsigned& c0, unsigned& c1,
+                            unsigned& c2) {
+    const int n = m + 3;
+    if (m < 2 || n > HS_RANK_SLOT_MAXN) return 1;
+    const int level = hs_rank_level(n);
+    const uint8_t* home = lut->home[level];
+    const uint8_t* hbits = lut->hbits[level];
+    uint32_t e[HS_RANK_SLOT_MAXN];  // (home << 5 | 31 - hash bits) << 8 | key, insertion-sorted ascending
+    for (int i = 0; i < n; i++) {
+        const int key = i < 3 ? i : acc.key(i - 3);  // the dummy keys 0,1,2 (:492-494) sit in the table too
+        const uint32_t v = ((uint32_t)(home[key] * 32 + 31 - hbits[key]) << 8) | (uint32_t)key;
+        int j = i;
+        while (j > 0 && e[j - 1] > v) {
+            e[j] = e[j - 1];
+            j--;
+        }
+        e[j] = v;
+    }
+    int next_free = 0;
+    for (int i = 0; i < n; i++) {
+        const int rk = (int)(e[i] >> 8), h = rk >> 5;
+        if (i > 0 && rk == (int)(e[i - 1] >> 8)) return 1;  // same bucket, same hash bits: history decides
+        const int slot = next_free > h ? next_free : h;
+        if (slot - h >= 6) return 1;  // the info bytes may have been widened (try_increase_info)
+        next_free = slot + 1;
+    }
+    for (int i = 0; i < n; i++) {
+        const int key = (int)(e[i] & 0xffu);
+        const unsigned cnt = key >= 33 ? acc.count(key) : 0u;
+        e[i] = (cnt << 8) | (unsigned)key;
+    }
+    hs_kc_std_sort(e, n);
+    k0 = e[0] & 0xff;
+    k1 = e[1] & 0xff;
+    c0 = e[0] >> 8;
+    c1 = e[1] >> 8;
+    c2 = e[2] >> 8;
+    return 0;
+}
+
 // host only: builds the tables by replaying the reference behaviour
 struct HsRankOneKey {
     int code;
@@ -446,7 +480,7 @@ struct HsRankOneKey {
     HS_HD unsigned count(int) const { return 1; }
 };
 inline void hs_build_rank_lut(HsRankLut& lut) {
-    for (int level = 0; level < 3; level++) {
+    for (int level = 0; level < 4; level++) {
         HsRhTable t;
         hs_rh_new(t);
         t.mask = (8u << level) - 1;
@@ -456,6 +490,7 @@ inline void hs_build_rank_lut(HsRankLut& lut) {
             hs_rh_key_to_idx(t, (uint8_t)key, idx, info);
             lut.home[level][key] = (uint8_t)idx;
             lut.hbits[level][key] = (uint8_t)(info - t.info_inc);
+            lut.tie[level][key] = (uint16_t)(((255u - idx) << 8) | (unsigned)key);
         }
     }
     for (int i = 0; i < 128; i++) {

@@ -77,7 +77,7 @@ def test_ranking_source_matches_oracle(oracle):
         lib.hsgpu_debug_sort_desc(k2.ctypes.data, c2.ctypes.data, n)
         a = oracle.sort_desc(keys, counts)
         assert np.array_equal(a[0], k2) and np.array_equal(a[1], c2)
-    n_fast = 0
+    n_fast = n_slot = 0
     for it in range(6000):
         depth = int(rng.integers(0, 90))
         ncodes = int(rng.integers(1, 30 if it % 10 else 125))
@@ -85,12 +85,31 @@ def test_ranking_source_matches_oracle(oracle):
         w = rng.random(ncodes) ** 3
         col = rng.choice(alphabet, size=depth, p=w / w.sum()).astype(np.uint8)
         want = oracle.column_rank(col)
-        for mode in (0, 1):  # bucket-table fast path with fallback (what the kernel runs), and pure replay
+        # bucket-table fast path with fallbacks (what the kernels run), pure replay, slot-order path alone
+        for mode in (0, 1, 2):
             out = np.zeros(6, np.int32)
             lib.hsgpu_debug_rank_column(col.ctypes.data, depth, out.ctypes.data, mode)
             assert np.array_equal(out[:5], want), (mode, col)
             n_fast += (mode == 0 and out[5] == 0)
+            n_slot += (mode == 2 and out[5] == 0)
     assert n_fast > 2000  # the table decides the large majority of columns
+    assert n_slot > 3000
+    # deep, noisy columns (more than 13 codes: the sorted vector leaves libstdc++'s insertion-sort regime) with
+    # small tied counts: the regime the slot-order path exists for
+    n_slot = 0
+    for it in range(6000):
+        ncodes = int(rng.integers(14, 49))
+        alphabet = (rng.permutation(125)[:ncodes] + 33).astype(np.uint8)
+        reps = rng.integers(1, 4, ncodes)
+        reps[0] += int(rng.integers(0, 40))
+        col = rng.permutation(np.repeat(alphabet, reps)).astype(np.uint8)
+        want = oracle.column_rank(col)
+        for mode in (0, 2):
+            out = np.zeros(6, np.int32)
+            lib.hsgpu_debug_rank_column(col.ctypes.data, col.shape[0], out.ctypes.data, mode)
+            assert np.array_equal(out[:5], want), (mode, col)
+            n_slot += (mode == 2 and out[5] == 0)
+    assert n_slot > 3000
     # tie-heavy columns: every code once or twice, so the rank is decided by the iteration order of the
     # reference's table alone (home bucket, then the hash bits kept in the info byte, then history)
     n_table = 0
