@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (testing only)")
     ap.add_argument("--cpu-sample-chunks", type=int, default=0, help="chunks in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="hsgpu contexts (host threads) of the e2e path")
+    ap.add_argument("--e2e-groups", type=int, default=6, help="groups of contig chunks the e2e path cuts the batch into")
     ap.add_argument("--wall-chunks", type=int, default=0, help="chunks in the HS_call_variants wall-time stage (0 = all, -1 = skip)")
     return ap.parse_args()
 
@@ -452,6 +454,98 @@ def run_call_variants_wall(chunks, args):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def run_e2e(chunks, local_rank, ctx, n_lanes, n_groups, steps, warmup, barrier):
+    """The way a caller drives the library from host buffers: the batch is cut into groups of contig chunks,
+    each group goes through one of `n_lanes` hsgpu contexts (one per host thread, as the header prescribes, like
+    the reference's OpenMP loop over contigs). The library lets one context upload at a time, so the kernels of
+    the group that has its data overlap the upload of the next group; CIGARs travel in the 8-bit form; every
+    group's results (suspect lists, depth numerators) come back through hsgpu_suspects_all. Inputs sit in pinned
+    host memory. Returns the device time of the slowest lane and the host wall clock over `steps` steps."""
+    import threading
+    import torch
+    from hairsplitter_b200 import api
+    n_groups = max(1, min(n_groups, len(chunks)))
+    n_lanes = max(1, min(n_lanes, n_groups))
+    groups = []
+    keep = []
+    for g in range(n_groups):
+        pb = api.PackedBatch(chunks[g::n_groups]).use_cigar8()
+        for name in ("contig_len", "contig_bases", "contig_word_off", "contig_read_off", "read_bases", "read_word_off",
+                     "read_len", "cigar8", "cigar8_off", "read_start", "read_strand"):
+            src = getattr(pb, name)
+            t = torch.empty(max(src.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            arr = t.numpy()[:src.nbytes].view(src.dtype).reshape(src.shape)
+            arr[...] = src
+            keep.append(t)
+            setattr(pb, name, arr)
+        groups.append(pb)
+    h2d_bytes = sum(int(pb.input_bytes) for pb in groups)
+    lanes = [ctx] + [api.Context(local_rank) for _ in range(n_lanes - 1)]
+    lane_streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local_rank)) for c in lanes]
+    e2e_out = [0] * n_groups
+    e2e_sus = [0] * n_groups
+
+    trace = [] if os.environ.get("HS_E2E_TRACE") else None
+
+    def e2e_group(lane, g):
+        t0 = time.perf_counter()
+        p = api.Pileup(lanes[lane], groups[g])   # H2D of the group
+        t1 = time.perf_counter()
+        p.build()
+        t2 = time.perf_counter()
+        p.column_rank()
+        t3 = time.perf_counter()
+        pos, au, off, ds = p.suspects_all()      # D2H of the call_variants results
+        t4 = time.perf_counter()
+        p.close()
+        if trace is not None:
+            trace.append((lane, g, t0, t1, t2, t3, t4, time.perf_counter()))
+        e2e_out[g] = pos.nbytes + au.nbytes + off.nbytes + ds.nbytes
+        e2e_sus[g] = int(off[-1])
+
+    def e2e_step():
+        def work(lane):
+            for g in range(lane, n_groups, n_lanes):
+                e2e_group(lane, g)
+        ts = [threading.Thread(target=work, args=(lane,)) for lane in range(1, n_lanes)]
+        for t in ts:
+            t.start()
+        work(0)
+        for t in ts:
+            t.join()
+        return sum(e2e_out)
+
+    d2h_bytes = 0
+    for _ in range(max(1, min(warmup, 3))):
+        d2h_bytes = e2e_step()
+    barrier()
+    t_e2e = time.perf_counter()
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+    for ev, st_ in zip(e0, lane_streams):
+        ev.record(st_)
+    for _ in range(steps):
+        d2h_bytes = e2e_step()
+    for ev, st_ in zip(e1, lane_streams):
+        ev.record(st_)
+    for c in lanes:
+        c.sync()
+    barrier()
+    t_e2e = (time.perf_counter() - t_e2e) * 1e3
+    # device time of the slowest lane; the host wall clock around the same region is reported beside it
+    e2e_ms = max(a.elapsed_time(b) for a, b in zip(e0, e1))
+    for c in lanes[1:]:
+        c.close()
+    if trace:  # the last step, times in ms from its first call
+        last = sorted(trace[-n_groups:], key=lambda r: r[2])
+        z = last[0][2]
+        for r in last:
+            print("  lane %d group %2d: create %.3f-%.3f build -%.3f rank -%.3f suspects_all -%.3f close -%.3f" %
+                  ((r[0], r[1]) + tuple((x - z) * 1e3 for x in r[2:])), file=sys.stderr)
+    return {"device_ms": e2e_ms, "wall_ms": t_e2e, "h2d_bytes": h2d_bytes, "d2h_bytes": d2h_bytes,
+            "suspects": sum(e2e_sus), "groups": n_groups, "lanes": n_lanes}
+
+
 def workload_description(info, chunks):
     return (f"BASELINE configs[1]: synthetic {info['genome'] / 1e6:g} Mb bacterial genome, {info['strains']} strains "
             f"1% apart, ONT-like reads {info['mean_len'] / 1000:g} kb mean, {int(info['error'] * 100)}% error, "
@@ -599,77 +693,10 @@ def main():
     pu.close()
 
     # ---- e2e: host buffers -> C ABI -> host results, every step ----
-    # The way a caller drives the library: the batch is cut into groups of contig chunks, each group goes
-    # through its own hsgpu context (one per host thread, as the header prescribes), so that the H2D copy of
-    # one group overlaps the kernels of another; CIGARs travel in the 16-bit form.
-    import threading
-    n_groups = max(1, min(4, len(chunks)))
-    n_lanes = min(2, n_groups)
-    groups = []
-    keep = []
-    for g in range(n_groups):
-        pb = api.PackedBatch(chunks[g::n_groups]).use_compact_cigar()
-        for name in ("contig_len", "contig_bases", "contig_word_off", "contig_read_off", "read_bases", "read_word_off",
-                     "read_len", "cigar16", "cigar16_off", "read_start", "read_strand"):
-            src = getattr(pb, name)
-            t = torch.empty(max(src.nbytes, 1), dtype=torch.uint8, pin_memory=True)
-            arr = t.numpy()[:src.nbytes].view(src.dtype).reshape(src.shape)
-            arr[...] = src
-            keep.append(t)
-            setattr(pb, name, arr)
-        groups.append(pb)
-    h2d_bytes = sum(int(pb.input_bytes) for pb in groups)
-    lanes = [ctx] + [api.Context(local_rank) for _ in range(n_lanes - 1)]
-    lane_streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local_rank)) for c in lanes]
-    e2e_out = [0] * n_groups
-    e2e_sus = [0] * n_groups
-
-    def e2e_group(lane, g):
-        p = api.Pileup(lanes[lane], groups[g])   # H2D of the group
-        p.build()
-        p.column_rank()
-        ns, ds = p.column_counts()               # D2H
-        got = 0
-        for ci in range(groups[g].n_contigs):
-            pos, au = p.suspects(ci)             # D2H of the call_variants result
-            got += pos.nbytes + au.nbytes
-        p.close()
-        e2e_out[g] = got + ns.nbytes + ds.nbytes
-        e2e_sus[g] = int(ns.sum())
-
-    def e2e_step():
-        def work(lane):
-            for g in range(lane, n_groups, n_lanes):
-                e2e_group(lane, g)
-        ts = [threading.Thread(target=work, args=(lane,)) for lane in range(1, n_lanes)]
-        for t in ts:
-            t.start()
-        work(0)
-        for t in ts:
-            t.join()
-        return sum(e2e_out)
-
-    for _ in range(min(args.warmup, 3)):
-        d2h_bytes = e2e_step()
-    assert sum(e2e_sus) == int(n_sus.sum()), "the grouped e2e path must find the same suspect columns"
-    barrier()
-    t_e2e = time.perf_counter()
-    e0 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
-    e1 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
-    for ev, st_ in zip(e0, lane_streams):
-        ev.record(st_)
-    for _ in range(args.steps):
-        d2h_bytes = e2e_step()
-    for ev, st_ in zip(e1, lane_streams):
-        ev.record(st_)
-    for c in lanes:
-        c.sync()
-    barrier()
-    t_e2e = (time.perf_counter() - t_e2e) * 1e3
-    # device time of the slowest lane; the host wall clock around the same region is reported beside it
-    e2e_ms = max(a.elapsed_time(b) for a, b in zip(e0, e1))
-    for c in lanes[1:]:
-        c.close()
+    e2e = run_e2e(chunks, local_rank, ctx, args.e2e_lanes, args.e2e_groups, args.steps, args.warmup, barrier)
+    assert e2e["suspects"] == int(n_sus.sum()), "the grouped e2e path must find the same suspect columns"
+    e2e_ms, t_e2e, h2d_bytes, d2h_bytes = e2e["device_ms"], e2e["wall_ms"], e2e["h2d_bytes"], e2e["d2h_bytes"]
+    n_groups, n_lanes = e2e["groups"], e2e["lanes"]
     # the floor of the e2e step on this box: the same bytes from pinned memory with nothing else going on
     src = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
     dst = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
@@ -718,8 +745,8 @@ def main():
                     "host_wall_ms_per_step": t_e2e / max(args.steps, 1),
                     "h2d_copy_floor_ms": h2d_floor_ms, "h2d_gbs": h2d_bytes / (h2d_floor_ms * 1e-3) / 1e9,
                     "path": f"{n_groups} groups of chunks over {n_lanes} hsgpu contexts (one host thread each): "
-                            "hsgpu_pileup_create(pinned host buffers, 16-bit CIGAR) + build + column_rank + "
-                            "column_counts + suspects"},
+                            "hsgpu_pileup_create(pinned host buffers, 8-bit CIGAR; one upload at a time) + build + "
+                            "column_rank + suspects_all"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "kernels": kernels,

@@ -36,6 +36,7 @@ class PileupInput(C.Structure):
         ("read_start", C.c_void_p),
         ("read_strand", C.c_void_p),
         ("cigar16", C.c_void_p),
+        ("cigar8", C.c_void_p),
     ]
 
 
@@ -63,10 +64,10 @@ EDLIB_RESULT_DTYPE = np.dtype(
 # every symbol include/hsgpu.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "hsgpu_ctx_create", "hsgpu_ctx_destroy", "hsgpu_last_error", "hsgpu_sync", "hsgpu_launch_count", "hsgpu_stream",
-    "hsgpu_profile_enable", "hsgpu_profile_report", "hsgpu_host_alloc", "hsgpu_host_free", "hsgpu_pack_bases_ascii", "hsgpu_pack_bases_codes", "hsgpu_parse_cigar",
+    "hsgpu_profile_enable", "hsgpu_profile_report", "hsgpu_host_alloc", "hsgpu_host_free", "hsgpu_pack_bases_ascii", "hsgpu_pack_bases_codes", "hsgpu_parse_cigar", "hsgpu_pack_cigar8",
     "hsgpu_pileup_create", "hsgpu_pileup_destroy", "hsgpu_pileup_build", "hsgpu_pileup_stats", "hsgpu_mean_distance",
     "hsgpu_pileup_read_ends", "hsgpu_pileup_export", "hsgpu_pileup_extract_columns", "hsgpu_column_rank",
-    "hsgpu_column_counts", "hsgpu_suspects", "hsgpu_column_summary", "hsgpu_partition_tables", "hsgpu_robust_filter",
+    "hsgpu_column_counts", "hsgpu_suspects", "hsgpu_suspects_all", "hsgpu_column_summary", "hsgpu_partition_tables", "hsgpu_robust_filter",
     "hsgpu_read_pair_counts", "hsgpu_pairs_create", "hsgpu_pairs_compute", "hsgpu_pairs_fetch", "hsgpu_pairs_info",
     "hsgpu_pairs_destroy", "hsgpu_graph_create", "hsgpu_graph_build", "hsgpu_graph_adjacency", "hsgpu_graph_whispers",
     "hsgpu_graph_destroy", "hsgpu_edlib_align_batch",
@@ -106,6 +107,9 @@ def load():
     L.hsgpu_pack_bases_codes.restype = None
     L.hsgpu_parse_cigar.argtypes = [C.c_char_p, vp, i64]
     L.hsgpu_parse_cigar.restype = i64
+    L.hsgpu_pack_cigar8.argtypes = [vp, i64, vp, i64]
+    L.hsgpu_pack_cigar8.restype = i64
+    L.hsgpu_suspects_all.argtypes = [vp, i64, vp, vp, vp, vp]
     L.hsgpu_pileup_create.argtypes = [vp, C.POINTER(PileupInput), C.POINTER(vp)]
     L.hsgpu_pileup_destroy.argtypes = [vp]
     L.hsgpu_pileup_destroy.restype = None
@@ -177,6 +181,32 @@ def compact_cigar(cigar: np.ndarray, cigar_off: np.ndarray):
     return out, new_off.astype(np.int64)
 
 
+def cigar8(cigar: np.ndarray, cigar_off: np.ndarray):
+    """u32 BAM ops -> the 8-bit form of hsgpu_pileup_input.cigar8 through hsgpu_pack_cigar8, read by read
+    (ops longer than 63 are split, so the offsets change). Raises when an op has no 8-bit form (N, P)."""
+    L = load()
+    cigar = np.ascontiguousarray(cigar, np.uint32)
+    n = int(cigar_off[-1])
+    total = int(L.hsgpu_pack_cigar8(cigar.ctypes.data, n, None, 0))
+    if total < 0:
+        raise HsgpuError("hsgpu_pack_cigar8: the CIGAR has ops without an 8-bit form")
+    out = np.zeros(max(total, 1), np.uint8)
+    new_off = np.zeros(cigar_off.size, np.int64)
+    if total == n:  # nothing was split: one call, same offsets
+        L.hsgpu_pack_cigar8(cigar.ctypes.data, n, out.ctypes.data, total)
+        new_off[:] = cigar_off
+        return out, new_off
+    at = 0
+    for r in range(cigar_off.size - 1):
+        a, b = int(cigar_off[r]), int(cigar_off[r + 1])
+        got = int(L.hsgpu_pack_cigar8(cigar.ctypes.data + 4 * a, b - a, out.ctypes.data + at, total - at))
+        assert got >= 0
+        at += got
+        new_off[r + 1] = at
+    assert at == total
+    return out, new_off
+
+
 class PackedBatch:
     """Host-side packing of a list of synth.ContigBatch into the flat arrays of hsgpu_pileup_input."""
 
@@ -228,6 +258,14 @@ class PackedBatch:
         self.input_bytes += int(self.cigar16.nbytes) - int(self.cigar.nbytes)
         return self
 
+    def use_cigar8(self):
+        """switches the batch to the 8-bit CIGAR form (a quarter of the CIGAR bytes over PCIe)"""
+        before = int(self.cigar16.nbytes) if getattr(self, "cigar16", None) is not None else int(self.cigar.nbytes)
+        self.cigar8, self.cigar8_off = cigar8(self.cigar, self.cigar_off)
+        self.cigar16 = None
+        self.input_bytes += int(self.cigar8.nbytes) - before
+        return self
+
     def struct(self) -> PileupInput:
         s = PileupInput()
         s.n_contigs = self.n_contigs
@@ -239,7 +277,13 @@ class PackedBatch:
         s.read_bases = self.read_bases.ctypes.data
         s.read_word_off = self.read_word_off.ctypes.data
         s.read_len = self.read_len.ctypes.data
-        if getattr(self, "cigar16", None) is not None:
+        s.cigar8 = None
+        if getattr(self, "cigar8", None) is not None:
+            s.cigar = None
+            s.cigar16 = None
+            s.cigar8 = self.cigar8.ctypes.data
+            s.cigar_off = self.cigar8_off.ctypes.data
+        elif getattr(self, "cigar16", None) is not None:
             s.cigar = None
             s.cigar16 = self.cigar16.ctypes.data
             s.cigar_off = self.cigar16_off.ctypes.data
@@ -525,6 +569,19 @@ class Pileup:
         self.ctx.check(self.lib.hsgpu_suspects(self.h, contig, cap, pos.ctypes.data, au.ctypes.data), "hsgpu_suspects")
         n = int(ns[contig])
         return pos[:n], au[:n]
+
+    def suspects_all(self, want_depth=True):
+        """every contig's suspect list in one call: (pos, is_automatic, off[n_contigs+1], depth_sum)"""
+        nc = self.packed.n_contigs
+        cap = int(self.packed.contig_len.astype(np.int64).sum()) // 6 + 2 * nc
+        pos = np.empty(cap, np.int32)
+        au = np.empty(cap, np.uint8)
+        off = np.zeros(nc + 1, np.int64)
+        ds = np.zeros(nc, np.int64)
+        self.ctx.check(self.lib.hsgpu_suspects_all(self.h, cap, pos.ctypes.data, au.ctypes.data, off.ctypes.data,
+                                                   ds.ctypes.data if want_depth else None), "hsgpu_suspects_all")
+        n = int(off[nc])
+        return pos[:n], au[:n], off, ds
 
     def column_summary(self, contig):
         Lc = int(self.packed.contig_len[contig])

@@ -489,6 +489,41 @@ __global__ void suspect_count_kernel(int n_contigs, const int64_t* __restrict__ 
     if (c < n_contigs) n_suspects[c] = (int32_t)(tile_sus_off[tile_base[c + 1]] - tile_sus_off[tile_base[c]]);
 }
 
+// all suspect lists of a batch, packed contig after contig (hsgpu_suspects_all). One CTA per contig; hdr =
+// [error flag, off[0..nc], depth_sum[0..nc-1]] so that one copy brings every per-contig scalar to the host.
+__global__ void __launch_bounds__(256) suspect_gather_kernel(int nc, const int32_t* __restrict__ n_suspects,
+                                                             const int64_t* __restrict__ suspect_base,
+                                                             const int32_t* __restrict__ src_pos,
+                                                             const uint8_t* __restrict__ src_auto,
+                                                             const unsigned long long* __restrict__ depth_sum,
+                                                             const int32_t* __restrict__ error_flag,
+                                                             int32_t* __restrict__ pos, uint8_t* __restrict__ is_auto,
+                                                             int64_t* __restrict__ hdr) {
+    __shared__ long long s_part[8];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    long long before = 0;
+    for (int i = tid; i < c; i += 256) before += n_suspects[i];
+    before = hs_warp_sum64(before);
+    if ((tid & 31) == 0) s_part[tid >> 5] = before;
+    __syncthreads();
+    before = 0;
+    for (int w = 0; w < 8; w++) before += s_part[w];
+    const int n = n_suspects[c];
+    const int64_t src = suspect_base[c];
+    for (int i = tid; i < n; i += 256) {
+        pos[before + i] = src_pos[src + i];
+        is_auto[before + i] = src_auto[src + i];
+    }
+    if (tid == 0) {
+        hdr[1 + c] = before;
+        hdr[nc + 2 + c] = (int64_t)depth_sum[c];
+        if (c == nc - 1) {
+            hdr[1 + nc] = before + n;
+            hdr[0] = *error_flag;
+        }
+    }
+}
+
 // ---- export in the reference's column-major layout ------------------------------------------------
 __global__ void __launch_bounds__(HS_TILE) export_kernel(int contig, int64_t tile0, const int64_t* __restrict__ col_base,
                                                          const int32_t* __restrict__ contig_len,
@@ -582,17 +617,25 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
     if (!p->built) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_column_rank: call hsgpu_pileup_build first");
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     const int nc = p->n_contigs;
-    if (!p->d_k0) {
-        HS_CUDA(ctx, hs_alloc(ctx, &p->d_k0, p->n_cols));
-        HS_CUDA(ctx, hs_alloc(ctx, &p->d_k1, p->n_cols));
-        HS_CUDA(ctx, hs_alloc(ctx, &p->d_flags, p->n_cols));
-        HS_CUDA(ctx, hs_alloc(ctx, &p->d_counts, 3 * p->n_cols));
-        HS_CUDA(ctx, hs_alloc(ctx, &p->d_depth, p->n_cols));
-        HS_CUDA(ctx, hs_alloc(ctx, &p->d_min_reads, nc + 1));  // last entry = device error flag
-        HS_CUDA(ctx, hs_alloc(ctx, &p->d_suspect_pos, p->h_suspect_base[nc]));
-        HS_CUDA(ctx, hs_alloc(ctx, &p->d_suspect_auto, p->h_suspect_base[nc]));
-        HS_CUDA(ctx, hs_alloc(ctx, &p->d_n_suspects, nc));
-        HS_CUDA(ctx, hs_alloc(ctx, &p->d_depth_sum, nc));
+    if (!p->d_rank_block) {  // everything this stage keeps, out of one allocation
+        HsCarve cv;
+        cv.add(&p->d_k0, p->n_cols);
+        cv.add(&p->d_k1, p->n_cols);
+        cv.add(&p->d_flags, p->n_cols);
+        cv.add(&p->d_counts, 3 * p->n_cols);
+        cv.add(&p->d_depth, p->n_cols);
+        cv.add(&p->d_min_reads, nc + 1);  // last entry = device error flag
+        cv.add(&p->d_suspect_pos, p->h_suspect_base[nc]);
+        cv.add(&p->d_suspect_auto, p->h_suspect_base[nc]);
+        cv.add(&p->d_n_suspects, nc);
+        cv.add(&p->d_depth_sum, nc);
+        // d_work: [0..3] counters (arena words, arena items, re-read items), then the re-read list
+        cv.add(&p->d_work, p->n_cols + 4);
+        p->arena_words = (unsigned int)std::min<int64_t>(2 * p->n_cols + 1024, 0x7fffffff);
+        cv.add(&p->d_arena, p->arena_words);
+        cv.add(&p->d_item_off, p->n_cols + p->n_cols / 2 + 512);  // items, then the literal list
+        cv.add(&p->d_tile_sus, p->n_tiles + 1);
+        HS_CUDA(ctx, cv.alloc(ctx, &p->d_rank_block));
     }
     p->ranked = false;
     p->have_col_off = false;
@@ -638,13 +681,6 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
         a.depth_sum = p->d_depth_sum;
         a.error_flag = p->d_min_reads + nc;
         a.lut = (const HsRankLut*)ctx->d_rank_lut;
-        // d_work: [0..3] counters (arena words, arena items, re-read items), then the re-read list
-        if (!p->d_work) HS_CUDA(ctx, hs_alloc(ctx, &p->d_work, p->n_cols + 4));
-        if (!p->d_arena) {
-            p->arena_words = (unsigned int)std::min<int64_t>(2 * p->n_cols + 1024, 0x7fffffff);
-            HS_CUDA(ctx, hs_alloc(ctx, &p->d_arena, p->arena_words));
-            HS_CUDA(ctx, hs_alloc(ctx, &p->d_item_off, p->n_cols + p->n_cols / 2 + 512));  // items, then the literal list
-        }
         a.arena = p->d_arena;
         a.arena_words = p->arena_words;
         a.counters = reinterpret_cast<unsigned int*>(p->d_work);
@@ -680,7 +716,6 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
                   column_rank_literal_kernel<<<ctx->sm_count * 2, 128, 0, ctx->stream>>>(la));
     }
     if (p->n_tiles > 0) {
-        if (!p->d_tile_sus) HS_CUDA(ctx, hs_alloc(ctx, &p->d_tile_sus, p->n_tiles + 1));
         HS_KERNEL(ctx, "suspect_mark_kernel", suspect_mark_kernel<<<(unsigned)p->n_tiles, HS_TILE, 0, ctx->stream>>>(
             p->d_tile_contig, p->d_tile_base, p->d_col_base, p->d_contig_len, p->d_flags));
         HS_KERNEL(ctx, "suspect_compact_kernel<0>", suspect_compact_kernel<false><<<(unsigned)p->n_tiles, HS_TILE, 0, ctx->stream>>>(
@@ -727,6 +762,56 @@ int hsgpu_suspects(hsgpu_pileup* p, int32_t contig, int32_t capacity, int32_t* p
     if (is_automatic) HS_CUDA(ctx, hs_d2h(ctx, is_automatic, p->d_suspect_auto + p->h_suspect_base[contig], n));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return HSGPU_OK;
+}
+
+int hsgpu_suspects_all(hsgpu_pileup* p, int64_t capacity, int32_t* pos, uint8_t* is_automatic, int64_t* off,
+                       int64_t* depth_sum) {
+    if (!p || !off) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = p->ctx;
+    if (!p->ranked) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_suspects_all: call hsgpu_column_rank first");
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nc = p->n_contigs;
+    const int64_t cap_all = p->h_suspect_base[nc];
+    int32_t* d_pos = nullptr;
+    uint8_t* d_auto = nullptr;
+    int64_t* d_hdr = nullptr;
+    HS_CUDA(ctx, hs_alloc(ctx, &d_pos, cap_all));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_auto, cap_all));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_hdr, 2 * nc + 2));
+    HS_KERNEL(ctx, "suspect_gather_kernel", suspect_gather_kernel<<<nc, 256, 0, ctx->stream>>>(
+        nc, p->d_n_suspects, p->d_suspect_base, p->d_suspect_pos, p->d_suspect_auto, p->d_depth_sum,
+        p->d_min_reads + nc, d_pos, d_auto, d_hdr));
+    const size_t hdr_bytes = sizeof(int64_t) * (size_t)(2 * nc + 2);
+    int64_t* h_hdr = reinterpret_cast<int64_t*>(hs_host_stage(ctx, hdr_bytes));
+    if (!h_hdr) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu_suspects_all: pinned staging allocation failed");
+    HS_CUDA(ctx, cudaMemcpyAsync(h_hdr, d_hdr, hdr_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t err = h_hdr[0];
+    std::copy(h_hdr + 1, h_hdr + nc + 2, off);
+    if (depth_sum) std::copy(h_hdr + nc + 2, h_hdr + 2 * nc + 2, depth_sum);
+    const int64_t total = off[nc];
+    int rc = HSGPU_OK;
+    if (err) {
+        hs_set_error(ctx, "hsgpu_column_rank: more than 65000 reads over one 128-column tile");
+        rc = HSGPU_ERR_LIMIT;
+    } else if (total > capacity && (pos || is_automatic)) {
+        hs_set_error(ctx, "hsgpu_suspects_all: capacity too small");
+        rc = HSGPU_ERR_CAPACITY;
+    } else if (total > 0 && (pos || is_automatic)) {
+        // both lists through the pinned staging area: one synchronisation, then plain copies into the caller's arrays
+        const size_t pos_bytes = pos ? sizeof(int32_t) * (size_t)total : 0;
+        uint8_t* h = reinterpret_cast<uint8_t*>(hs_host_stage(ctx, pos_bytes + (size_t)total));
+        if (!h) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu_suspects_all: pinned staging allocation failed");
+        if (pos) HS_CUDA(ctx, cudaMemcpyAsync(h, d_pos, pos_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (is_automatic) HS_CUDA(ctx, cudaMemcpyAsync(h + pos_bytes, d_auto, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (pos) memcpy(pos, h, pos_bytes);
+        if (is_automatic) memcpy(is_automatic, h + pos_bytes, (size_t)total);
+    }
+    hs_free(ctx, d_pos);
+    hs_free(ctx, d_auto);
+    hs_free(ctx, d_hdr);
+    return rc;
 }
 
 int hsgpu_column_summary(hsgpu_pileup* p, int32_t contig, uint8_t* ref_base, uint8_t* second_base, uint32_t* counts,

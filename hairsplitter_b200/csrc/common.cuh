@@ -33,7 +33,13 @@ struct hsgpu_ctx {
     int64_t* h_scratch = nullptr;
     cudaEvent_t scratch_event = nullptr;
     struct hsgpu_pileup* scratch_owner = nullptr;
+    // growable pinned staging area for results that are read back in one piece (hs_host_stage)
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
 };
+
+// pinned staging area of at least `bytes` (contents are not kept when it grows); null on failure
+void* hs_host_stage(hsgpu_ctx* ctx, size_t bytes);
 
 void hs_prof_begin(hsgpu_ctx* ctx, const char* name);
 void hs_prof_end(hsgpu_ctx* ctx);
@@ -80,6 +86,30 @@ static inline void hs_free(hsgpu_ctx* ctx, T*& p) {
     if (p) cudaFreeAsync((void*)p, ctx->stream);
     p = nullptr;
 }
+// several arrays out of ONE stream-ordered allocation (a batch object used to cost ~40 cudaMallocAsync /
+// cudaFreeAsync pairs; the host side of the e2e path is bound by driver calls)
+struct HsCarve {
+    struct Piece { void** slot; size_t bytes; };
+    std::vector<Piece> pieces;
+    template <typename T>
+    void add(T** slot, int64_t n) {
+        if (n <= 0) n = 1;
+        pieces.push_back({reinterpret_cast<void**>(slot), ((size_t)n * sizeof(T) + 255) & ~(size_t)255});
+    }
+    cudaError_t alloc(hsgpu_ctx* ctx, void** base) {
+        size_t total = 0;
+        for (const Piece& q : pieces) total += q.bytes;
+        cudaError_t e = cudaMallocAsync(base, total ? total : 256, ctx->stream);
+        if (e != cudaSuccess) return e;
+        size_t off = 0;
+        for (const Piece& q : pieces) {
+            *q.slot = static_cast<char*>(*base) + off;
+            off += q.bytes;
+        }
+        return cudaSuccess;
+    }
+};
+
 template <typename T>
 static inline cudaError_t hs_h2d(hsgpu_ctx* ctx, T* dst, const T* src, int64_t n) {
     if (n <= 0) return cudaSuccess;
@@ -139,6 +169,11 @@ struct hsgpu_pileup {
     std::vector<int32_t> h_contig_len;
     std::vector<int64_t> h_contig_read_off, h_col_base, h_tile_base;
     std::vector<int64_t> h_stats;  // 3 per contig: distance, aligned, cells
+
+    // carved allocations (HsCarve): everything hsgpu_pileup_create / the first hsgpu_column_rank allocate
+    void* d_create_block = nullptr;
+    void* d_rank_block = nullptr;
+    std::vector<int64_t> h_tables;  // col_base | tile_base | suspect_base | super_base, uploaded in one copy
 
     // inputs on the device
     int32_t* d_contig_len = nullptr;

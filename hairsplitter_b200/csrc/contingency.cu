@@ -386,22 +386,47 @@ __global__ void __launch_bounds__(128) robust_filter_kernel(FilterArgs a) {
     if (q0 + tid < a.L) a.kept[q0 + tid] = (uint8_t)s_keep[tid];
 }
 
-// ascending compaction of the kept columns; one warp
-__global__ void __launch_bounds__(32) kept_scan_kernel(int L, const uint8_t* __restrict__ kept, int capacity,
-                                                       int32_t* __restrict__ out, int32_t* __restrict__ n_out) {
-    const int lane = threadIdx.x;
-    int n = 0;
-    for (int q0 = 0; q0 < L; q0 += 32) {
-        const int q = q0 + lane;
-        const bool k = q < L && kept[q];
-        const unsigned m = __ballot_sync(0xffffffffu, k);
-        if (k) {
-            const int i = n + __popc(m & ((1u << lane) - 1u));
-            if (i < capacity) out[i] = q;
+// ascending compaction of the kept columns: one CTA of 1024 threads; a round covers 16 columns per thread
+// (one 16-byte load of the flags), block-scans the per-thread counts and writes the positions in order
+__global__ void __launch_bounds__(1024) kept_scan_kernel(int L, const uint8_t* __restrict__ kept, int capacity,
+                                                         int32_t* __restrict__ out, int32_t* __restrict__ n_out) {
+    __shared__ int s_warp[32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int n = 0;  // kept columns before this round (same value in every thread)
+    for (int r0 = 0; r0 < L; r0 += 1024 * 16) {
+        const int q0 = r0 + 16 * tid;
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (q0 + 16 <= L) {  // d_kept is its own cudaMallocAsync block: 16-byte aligned
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(kept + q0));
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+            for (int j = 0; q0 + j < L && j < 16; j++) w[j >> 2] |= (kept[q0 + j] ? 1u : 0u) << (8 * (j & 3));
         }
-        n += __popc(m);
+        unsigned bits = 0;  // bit j = column q0 + j is kept
+#pragma unroll
+        for (int j = 0; j < 16; j++) bits |= (((w[j >> 2] >> (8 * (j & 3))) & 0xffu) ? 1u : 0u) << j;
+        const int cnt = __popc(bits);
+        const int incl = hs_warp_incl_scan(cnt, lane);
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const int wi = hs_warp_incl_scan(s_warp[lane], lane);
+            s_warp[lane] = wi - s_warp[lane];
+            if (lane == 31) s_total = wi;
+        }
+        __syncthreads();
+        int i = n + s_warp[wid] + incl - cnt;
+        while (bits) {
+            const int j = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (i < capacity) out[i] = q0 + j;
+            i++;
+        }
+        n += s_total;
+        __syncthreads();
     }
-    if (lane == 0) *n_out = n;
+    if (tid == 0) *n_out = n;
 }
 
 __global__ void set_inlist_kernel(int n, const int32_t* __restrict__ pos, int64_t g0, uint8_t* __restrict__ flags,
@@ -547,7 +572,7 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     a.kept = d_kept;
     const unsigned ntile = (unsigned)((L + HS_TILE - 1) / HS_TILE);
     HS_KERNEL(ctx, "robust_filter_kernel", robust_filter_kernel<<<ntile, 128, kFilterSmem, ctx->stream>>>(a));
-    HS_KERNEL(ctx, "kept_scan_kernel", kept_scan_kernel<<<1, 32, 0, ctx->stream>>>((int)L, d_kept, kept_capacity, d_list, d_list + kept_capacity));
+    HS_KERNEL(ctx, "kept_scan_kernel", kept_scan_kernel<<<1, 1024, 0, ctx->stream>>>((int)L, d_kept, kept_capacity, d_list, d_list + kept_capacity));
     if (n_suspects > 0) {
         HS_KERNEL(ctx, "set_inlist_kernel", set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 0));
     }

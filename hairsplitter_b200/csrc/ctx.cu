@@ -138,6 +138,7 @@ void hsgpu_ctx_destroy(hsgpu_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaStreamDestroy(ctx->stream);
     if (ctx->d_rank_lut) cudaFree(ctx->d_rank_lut);
     delete ctx;
@@ -219,6 +220,47 @@ int64_t hsgpu_parse_cigar(const char* cigar, uint32_t* out, int64_t capacity) {
 
 }  // extern "C"
 
+void* hs_host_stage(hsgpu_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->h_stage_bytes) return ctx->h_stage;
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->h_stage_bytes = 0;
+    size_t want = 1 << 16;
+    while (want < bytes) want <<= 1;
+    if (cudaHostAlloc(&ctx->h_stage, want, cudaHostAllocDefault) != cudaSuccess) {
+        ctx->h_stage = nullptr;
+        return nullptr;
+    }
+    ctx->h_stage_bytes = want;
+    return ctx->h_stage;
+}
+
+extern "C" {
+
+int64_t hsgpu_pack_cigar8(const uint32_t* ops, int64_t n_ops, uint8_t* out, int64_t capacity) {
+    if (!ops && n_ops > 0) return HSGPU_ERR_ARG;
+    // BAM op -> kind: M I D N S H P = X
+    static const int8_t kind_of[16] = {0, 1, 2, -1, 3, 3, -1, 0, 0, -1, -1, -1, -1, -1, -1, -1};
+    int64_t n = 0;
+    for (int64_t i = 0; i < n_ops; i++) {
+        const int kind = kind_of[ops[i] & 15u];
+        if (kind < 0) return HSGPU_ERR_ARG;
+        uint32_t len = ops[i] >> 4;
+        do {  // a zero-length op stays one (empty) op
+            const uint32_t piece = len > 63u ? 63u : len;
+            if (out) {
+                if (n >= capacity) return HSGPU_ERR_CAPACITY;
+                out[n] = (uint8_t)((piece << 2) | (uint32_t)kind);
+            }
+            n++;
+            len -= piece;
+        } while (len > 0);
+    }
+    return n;
+}
+
+}  // extern "C"
+
 // ---- device exclusive scan ----------------------------------------------------------------------
 // Three-phase scan with 1024-thread blocks handling 4096 elements each; recursion over block sums.
 #define SCAN_THREADS 1024
@@ -268,10 +310,56 @@ __global__ void scan_total_kernel(const int64_t* block_off, const int64_t* block
     *total = block_off[nb - 1] + block_sums[nb - 1];
 }
 
+// Short inputs (every per-read / per-tile table of a batch of contig chunks): ONE launch of one CTA that walks
+// the array in pieces of 4096 with a running carry -- 1 driver call instead of the 13 of the recursive scan.
+#define SCAN_SINGLE_MAX (64 * 1024)
+template <typename TIn>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(const TIn* __restrict__ in, int64_t* __restrict__ out,
+                                                                   int64_t n, int64_t* __restrict__ total) {
+    __shared__ long long warp_tot[32];
+    __shared__ long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base0 = 0; base0 < n; base0 += SCAN_BLOCK) {
+        const int64_t base = base0 + (int64_t)tid * SCAN_ITEMS;
+        long long v[SCAN_ITEMS];
+        long long s = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            v[i] = (base + i < n) ? (long long)in[base + i] : 0;
+            s += v[i];
+        }
+        const long long incl = hs_warp_incl_scan64(s, lane);
+        if (lane == 31) warp_tot[wid] = incl;
+        const long long carry = s_carry;
+        __syncthreads();
+        if (wid == 0) {
+            const long long w = warp_tot[lane];
+            const long long wi = hs_warp_incl_scan64(w, lane);
+            warp_tot[lane] = wi - w;
+            if (lane == 31) s_carry = carry + wi;
+        }
+        __syncthreads();
+        long long run = carry + warp_tot[wid] + incl - s;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            if (base + i < n) out[base + i] = run;
+            run += v[i];
+        }
+        __syncthreads();  // warp_tot and s_carry are rewritten by the next piece
+    }
+    if (tid == 0 && total) *total = s_carry;
+}
+
 template <typename TIn>
 static int scan_impl(hsgpu_ctx* ctx, const TIn* in, int64_t* out, int64_t n, int64_t* total) {
     if (n <= 0) {
         if (total) HS_CUDA(ctx, cudaMemsetAsync(total, 0, sizeof(int64_t), ctx->stream));
+        return HSGPU_OK;
+    }
+    if (n <= SCAN_SINGLE_MAX) {
+        HS_KERNEL(ctx, "scan_single_kernel<TIn>", scan_single_kernel<TIn><<<1, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, total));
         return HSGPU_OK;
     }
     int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;

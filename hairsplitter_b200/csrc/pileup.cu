@@ -11,8 +11,11 @@
 // in-column order of the reference.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
+
+static std::mutex g_upload_mutex[64];  // per device, see hsgpu_pileup_create
 
 enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };
 
@@ -632,6 +635,51 @@ __global__ void cigar_expand_kernel(int64_t n, const uint16_t* __restrict__ in, 
     }
 }
 
+// 8-bit form (hsgpu_pack_cigar8): len<<2 | kind, kind 0 M, 1 I, 2 D, 3 S; sixteen ops per thread
+__global__ void cigar8_expand_kernel(int64_t n, const uint8_t* __restrict__ in, uint32_t* __restrict__ out) {
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i0 >= n) return;
+    uint32_t w[4];
+    if (i0 + 16 <= n) {  // `in` is its own allocation: 16-byte aligned
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i0));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+        w[0] = w[1] = w[2] = w[3] = 0;
+        for (int j = 0; i0 + j < n; j++) w[j >> 2] |= (uint32_t)in[i0 + j] << (8 * (j & 3));
+    }
+    uint32_t o[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        const uint32_t kind = b & 3u;
+        o[j] = ((b >> 2) << 4) | (kind == 3u ? (uint32_t)OP_S : kind);
+    }
+    if (i0 + 16 <= n) {  // out + i0 is 64-byte aligned
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            reinterpret_cast<uint4*>(out + i0)[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    } else {
+        for (int j = 0; i0 + j < n; j++) out[i0 + j] = o[j];
+    }
+}
+
+// the contig every read / every tile belongs to: last c with off[c] <= i (empty contigs repeat an offset)
+__device__ __forceinline__ int hs_owner(const int64_t* __restrict__ off, int n, int64_t i) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(256) owner_fill_kernel(int nc, int64_t n_reads, const int64_t* __restrict__ contig_read_off,
+                                                         int32_t* __restrict__ read_contig, int64_t n_tiles,
+                                                         const int64_t* __restrict__ tile_base, int32_t* __restrict__ tile_contig) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_reads) read_contig[i] = hs_owner(contig_read_off, nc, i);
+    else if (i - n_reads < n_tiles) tile_contig[i - n_reads] = hs_owner(tile_base, nc, i - n_reads);
+}
+
 // ---- host side --------------------------------------------------------------------------------
 // hsgpu_pileup_build leaves the deepest tile's read count in flight (pinned scratch of the context + event)
 int hs_resolve_max_tile_reads(hsgpu_pileup* p) {
@@ -650,50 +698,12 @@ void hsgpu_pileup_destroy(hsgpu_pileup* p) {
     if (!p) return;
     hsgpu_ctx* ctx = p->ctx;
     cudaSetDevice(ctx->device);
-    hs_free(ctx, p->d_contig_len);
-    hs_free(ctx, p->d_contig_bases);
-    hs_free(ctx, p->d_contig_word_off);
-    hs_free(ctx, p->d_contig_read_off);
-    hs_free(ctx, p->d_col_base);
-    hs_free(ctx, p->d_tile_base);
-    hs_free(ctx, p->d_tile_contig);
-    hs_free(ctx, p->d_read_contig);
-    hs_free(ctx, p->d_read_bases);
-    hs_free(ctx, p->d_read_word_off);
-    hs_free(ctx, p->d_read_len);
-    hs_free(ctx, p->d_cigar);
-    hs_free(ctx, p->d_cigar_off);
-    hs_free(ctx, p->d_read_start);
-    hs_free(ctx, p->d_read_strand);
-    hs_free(ctx, p->d_read_end);
-    hs_free(ctx, p->d_read_tlead);
-    hs_free(ctx, p->d_read_flags);
-    hs_free(ctx, p->d_next_read);
-    hs_free(ctx, p->d_row_alloc);
-    hs_free(ctx, p->d_row_base);
+    hs_free(ctx, p->d_create_block);
+    hs_free(ctx, p->d_rank_block);
     hs_free(ctx, p->d_codes);
-    hs_free(ctx, p->d_stats);
-    hs_free(ctx, p->d_tile_off);
     hs_free(ctx, p->d_tile_reads);
-    hs_free(ctx, p->d_super_base);
-    hs_free(ctx, p->d_super_off);
     if (ctx->scratch_owner == p) ctx->scratch_owner = nullptr;
-    hs_free(ctx, p->d_k0);
-    hs_free(ctx, p->d_k1);
-    hs_free(ctx, p->d_flags);
-    hs_free(ctx, p->d_counts);
-    hs_free(ctx, p->d_depth);
-    hs_free(ctx, p->d_min_reads);
-    hs_free(ctx, p->d_suspect_pos);
-    hs_free(ctx, p->d_suspect_auto);
-    hs_free(ctx, p->d_n_suspects);
-    hs_free(ctx, p->d_depth_sum);
-    hs_free(ctx, p->d_suspect_base);
     hs_free(ctx, p->d_col_off);
-    hs_free(ctx, p->d_tile_sus);
-    hs_free(ctx, p->d_work);
-    hs_free(ctx, p->d_arena);
-    hs_free(ctx, p->d_item_off);
     delete p;
 }
 
@@ -746,38 +756,54 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
             HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pileup_create: negative read start or length");
         }
     }
-    std::vector<int32_t> read_contig((size_t)nr);
-    for (int c = 0; c < nc; c++)
-        for (int64_t r = in->contig_read_off[c]; r < in->contig_read_off[c + 1]; r++) read_contig[r] = c;
-    std::vector<int32_t> tile_contig((size_t)tiles);
-    for (int c = 0; c < nc; c++)
-        for (int64_t t = p->h_tile_base[c]; t < p->h_tile_base[c + 1]; t++) tile_contig[t] = c;
-
     const int64_t contig_words = in->contig_word_off[nc];
     const int64_t read_words = in->read_word_off[nr];
-#define A(ptr, n) HS_CUDA(ctx, hs_alloc(ctx, &p->ptr, (n)))
-    A(d_contig_len, nc); A(d_contig_bases, contig_words); A(d_contig_word_off, nc + 1);
-    A(d_contig_read_off, nc + 1); A(d_col_base, nc + 1); A(d_tile_base, nc + 1); A(d_tile_contig, tiles);
-    A(d_read_contig, nr); A(d_read_bases, read_words); A(d_read_word_off, nr + 1); A(d_read_len, nr);
-    A(d_cigar, p->n_cigar); A(d_cigar_off, nr + 1); A(d_read_start, nr); A(d_read_strand, nr);
-    A(d_read_end, nr); A(d_read_tlead, nr); A(d_read_flags, nr); A(d_next_read, 1); A(d_row_alloc, nr + 1); A(d_row_base, nr); A(d_stats, 3 * nc);
-    A(d_tile_off, tiles + 1); A(d_suspect_base, nc + 1); A(d_super_base, nc + 1); A(d_super_off, supers + 1);
+    {
+        HsCarve cv;
+#define A(ptr, n) cv.add(&p->ptr, (n))
+        A(d_contig_len, nc); A(d_contig_bases, contig_words); A(d_contig_word_off, nc + 1);
+        A(d_contig_read_off, nc + 1); A(d_col_base, 4 * (nc + 1)); A(d_tile_contig, tiles);
+        A(d_read_contig, nr); A(d_read_bases, read_words); A(d_read_word_off, nr + 1); A(d_read_len, nr);
+        A(d_cigar, p->n_cigar); A(d_cigar_off, nr + 1); A(d_read_start, nr); A(d_read_strand, nr);
+        A(d_read_end, nr); A(d_read_tlead, nr); A(d_read_flags, nr); A(d_next_read, 1); A(d_row_alloc, nr + 1); A(d_row_base, nr); A(d_stats, 3 * nc);
+        A(d_tile_off, tiles + 1); A(d_super_off, supers + 1);
 #undef A
+        HS_CUDA(ctx, cv.alloc(ctx, &p->d_create_block));
+    }
+    // the four per-contig offset tables travel as one array
+    p->d_tile_base = p->d_col_base + (nc + 1);
+    p->d_suspect_base = p->d_col_base + 2 * (nc + 1);
+    p->d_super_base = p->d_col_base + 3 * (nc + 1);
+    p->h_tables.resize((size_t)4 * (nc + 1));
+    std::copy(p->h_col_base.begin(), p->h_col_base.end(), p->h_tables.begin());
+    std::copy(p->h_tile_base.begin(), p->h_tile_base.end(), p->h_tables.begin() + (nc + 1));
+    std::copy(p->h_suspect_base.begin(), p->h_suspect_base.end(), p->h_tables.begin() + 2 * (nc + 1));
+    std::copy(super_base.begin(), super_base.end(), p->h_tables.begin() + 3 * (nc + 1));
+    // One batch upload at a time per device: the e2e path is bound by the host link, and two contexts copying
+    // at once only finish both later. Taking turns lets the kernels of the context that has its data overlap
+    // the upload of the next one (callers drive one context per host thread, include/hsgpu.h).
+    std::lock_guard<std::mutex> upload_turn(g_upload_mutex[ctx->device & 63]);
     HS_CUDA(ctx, hs_h2d(ctx, p->d_contig_len, in->contig_len, nc));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_contig_bases, in->contig_bases, contig_words));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_contig_word_off, in->contig_word_off, nc + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_contig_read_off, in->contig_read_off, nc + 1));
-    HS_CUDA(ctx, hs_h2d(ctx, p->d_col_base, p->h_col_base.data(), nc + 1));
-    HS_CUDA(ctx, hs_h2d(ctx, p->d_tile_base, p->h_tile_base.data(), nc + 1));
-    HS_CUDA(ctx, hs_h2d(ctx, p->d_suspect_base, p->h_suspect_base.data(), nc + 1));
-    HS_CUDA(ctx, hs_h2d(ctx, p->d_super_base, super_base.data(), nc + 1));
-    HS_CUDA(ctx, hs_h2d(ctx, p->d_tile_contig, tile_contig.data(), tiles));
-    HS_CUDA(ctx, hs_h2d(ctx, p->d_read_contig, read_contig.data(), nr));
+    HS_CUDA(ctx, hs_h2d(ctx, p->d_col_base, p->h_tables.data(), 4 * (nc + 1)));
+    // contig of every read and of every tile: looked up on the device (two sorted offset tables)
+    HS_KERNEL(ctx, "owner_fill_kernel", owner_fill_kernel<<<(unsigned)((nr + tiles + 255) / 256 + 1), 256, 0, ctx->stream>>>(
+        nc, nr, p->d_contig_read_off, p->d_read_contig, tiles, p->d_tile_base, p->d_tile_contig));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_bases, in->read_bases, read_words));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_word_off, in->read_word_off, nr + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_len, in->read_len, nr));
     uint16_t* d_cigar16 = nullptr;
-    if (in->cigar16) {
+    if (in->cigar8) {
+        uint8_t* d_cigar8 = nullptr;
+        HS_CUDA(ctx, hs_alloc(ctx, &d_cigar8, p->n_cigar));
+        HS_CUDA(ctx, hs_h2d(ctx, d_cigar8, in->cigar8, p->n_cigar));
+        if (p->n_cigar > 0)
+            HS_KERNEL(ctx, "cigar8_expand_kernel", cigar8_expand_kernel<<<(unsigned)((p->n_cigar + 16 * 256 - 1) / (16 * 256)), 256, 0, ctx->stream>>>(
+                p->n_cigar, d_cigar8, p->d_cigar));
+        hs_free(ctx, d_cigar8);
+    } else if (in->cigar16) {
         HS_CUDA(ctx, hs_alloc(ctx, &d_cigar16, p->n_cigar));
         HS_CUDA(ctx, hs_h2d(ctx, d_cigar16, in->cigar16, p->n_cigar));
         if (p->n_cigar > 0)
@@ -790,7 +816,7 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
     HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar_off, in->cigar_off, nr + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_start, in->read_start, nr));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_strand, in->read_strand, nr));
-    // the local vectors must outlive the async copies from pageable memory
+    // the upload turn ends when the copies have landed (the caller's buffers are free again, too)
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = p;
     return HSGPU_OK;

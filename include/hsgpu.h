@@ -67,6 +67,10 @@ void hsgpu_pack_bases_ascii(const char* seq, int64_t n, uint32_t* out_words); /*
 void hsgpu_pack_bases_codes(const uint8_t* codes, int64_t n, uint32_t* out_words);
 /* parses a SAM CIGAR string into BAM ops; returns the number of ops or <0; "*" gives 0 ops */
 int64_t hsgpu_parse_cigar(const char* cigar, uint32_t* out_ops, int64_t capacity);
+/* BAM ops -> the 8-bit form of hsgpu_pileup_input.cigar8. Returns the number of bytes written (>= n_ops: ops longer
+ * than 63 are split), HSGPU_ERR_CAPACITY, or HSGPU_ERR_ARG when an op has no 8-bit form (N, P: use cigar16).
+ * out == NULL only counts. */
+int64_t hsgpu_pack_cigar8(const uint32_t* ops, int64_t n_ops, uint8_t* out, int64_t capacity);
 
 /* ---- pileup: generate_msa (src/call_variants.cpp:50-437) -------------------------------------
  * A batch of contig chunks with the reads aligned on them (what parse_SAM + parse_reads_on_contig
@@ -90,6 +94,11 @@ typedef struct {
      * ops of the same kind, which every loop of the reference treats the same way). When non-NULL it replaces
      * `cigar` (which may then be NULL), cigar_off indexes it, and half as many bytes cross PCIe. */
     const uint16_t* cigar16;
+    /* optional 8-bit CIGAR: u8 per op = len<<2 | kind, len <= 63, kind 0 = M/=/X, 1 = I, 2 = D, 3 = S/H (the
+     * four classes generate_msa distinguishes, src/call_variants.cpp:226-342; longer ops are split). Made by
+     * hsgpu_pack_cigar8. When non-NULL it replaces `cigar` and `cigar16`, cigar_off indexes it: a quarter of
+     * the CIGAR bytes cross PCIe (the e2e path is bound by that link). */
+    const uint8_t* cigar8;
 } hsgpu_pileup_input;
 
 /* copies the batch to the device (asynchronous on the context's stream) */
@@ -127,6 +136,12 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
 int hsgpu_column_counts(hsgpu_pileup* p, int32_t* n_suspects, int64_t* depth_sum);
 /* suspect positions of one contig (ascending) and whether each is an "automatic" SNP */
 int hsgpu_suspects(hsgpu_pileup* p, int32_t contig, int32_t capacity, int32_t* pos, uint8_t* is_automatic);
+/* the same for every contig of the batch in one call (two host round trips in all instead of two per contig):
+ * contig c's suspects are pos[off[c] .. off[c+1]) (positions inside contig c, ascending); off has n_contigs+1
+ * entries; depth_sum as in hsgpu_column_counts; pos / is_automatic / depth_sum may be NULL. HSGPU_ERR_CAPACITY
+ * (with off filled in) when capacity < off[n_contigs]. */
+int hsgpu_suspects_all(hsgpu_pileup* p, int64_t capacity, int32_t* pos, uint8_t* is_automatic, int64_t* off,
+                       int64_t* depth_sum);
 /* per-column summary of one contig; any pointer may be NULL. counts = c0,c1,c2 interleaved [3L] */
 int hsgpu_column_summary(hsgpu_pileup* p, int32_t contig, uint8_t* ref_base, uint8_t* second_base,
                          uint32_t* counts, uint32_t* depth);

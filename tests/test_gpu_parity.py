@@ -234,3 +234,45 @@ def test_compact_cigar_input_gives_the_same_pileup(gpu_ctx, oracle, case):
     pu.column_rank()
     _check_contig(oracle, pu, 0, cb)
     pu.close()
+
+
+@pytest.mark.parametrize("case", ["hifi", "walk_edges", "clips"])
+def test_cigar8_input_gives_the_same_pileup(gpu_ctx, oracle, case):
+    """hsgpu_pileup_input.cigar8 (M/=/X, I, D, S/H classes; ops longer than 63 split) encodes the same alignment"""
+    if case == "hifi":
+        cb = cases.hifi_case()
+    elif case == "clips":
+        cb = cases.small_case(seed=91, hard=0.6, eqx=True)  # H and S clips, =/X instead of M
+    else:
+        cb = cases.walk_edge_case()
+        ty = cb.cigar & 15
+        keep = (ty != 3) & (ty != 6)  # N and P have no 8-bit form; drop them from the hand-made CIGARs
+        cb.cigar_off = np.concatenate([[0], np.cumsum(keep)])[cb.cigar_off].astype(np.int64)
+        cb.cigar = cb.cigar[keep]
+    pk = api.PackedBatch([cb]).use_cigar8()
+    assert pk.cigar8.dtype == np.uint8 and pk.cigar8.shape[0] >= pk.cigar.shape[0]
+    assert int(pk.cigar8_off[-1]) == pk.cigar8.shape[0] or pk.cigar.shape[0] == 0
+    pu = api.Pileup(gpu_ctx, pk)
+    pu.build()
+    pu.column_rank()
+    _check_contig(oracle, pu, 0, cb)
+    pu.close()
+
+
+def test_suspects_all_equals_the_per_contig_calls(gpu_ctx):
+    """hsgpu_suspects_all: every contig's list (and the depth numerators) in one call, ragged batch incl. an empty contig"""
+    batch = [cases.small_case(seed=21, length=9000, depth=40, mean_len=1500),
+             cases.small_case(seed=22, length=300, depth=0, mean_len=200),
+             cases.small_case(seed=23, length=20000, depth=25, mean_len=3000),
+             cases.small_case(seed=24, length=4097, depth=60, mean_len=900)]
+    pu = api.Pileup(gpu_ctx, api.PackedBatch(batch))
+    pu.build()
+    pu.column_rank()
+    pos, au, off, ds = pu.suspects_all()
+    ns, ds1 = pu.column_counts()
+    assert np.array_equal(np.diff(off), ns) and np.array_equal(ds, ds1) and off[0] == 0
+    assert int(ns.sum()) > 0
+    for ci in range(len(batch)):
+        p1, a1 = pu.suspects(ci)
+        assert np.array_equal(pos[off[ci]:off[ci + 1]], p1) and np.array_equal(au[off[ci]:off[ci + 1]], a1)
+    pu.close()

@@ -53,6 +53,28 @@ def test_pack_bases_and_parse_cigar():
     assert lib.hsgpu_parse_cigar(b"5Q", ops.ctypes.data, 16) == -3
 
 
+def test_pack_cigar8():
+    """the 8-bit CIGAR form: four op classes, ops longer than 63 split, N/P refused"""
+    lib = api.load()
+    ops = np.zeros(16, np.uint32)
+    n = lib.hsgpu_parse_cigar(b"12S130M2I1D5=63X0M7H", ops.ctypes.data, 16)
+    assert n == 8
+    out = np.zeros(32, np.uint8)
+    m = lib.hsgpu_pack_cigar8(ops.ctypes.data, n, out.ctypes.data, 32)
+    want = [(12, 3), (63, 0), (63, 0), (4, 0), (2, 1), (1, 2), (5, 0), (63, 0), (0, 0), (7, 3)]
+    assert m == len(want)
+    assert [(int(b) >> 2, int(b) & 3) for b in out[:m]] == want
+    assert lib.hsgpu_pack_cigar8(ops.ctypes.data, n, None, 0) == m          # counting only
+    assert lib.hsgpu_pack_cigar8(ops.ctypes.data, n, out.ctypes.data, 3) == -4  # capacity
+    n = lib.hsgpu_parse_cigar(b"5M3N5M", ops.ctypes.data, 16)
+    assert lib.hsgpu_pack_cigar8(ops.ctypes.data, n, out.ctypes.data, 32) == -3  # N has no 8-bit form
+    # numpy-side wrapper: offsets follow the splits
+    cig = np.array([(200 << 4) | 0, (3 << 4) | 1, (64 << 4) | 2, (10 << 4) | 0], np.uint32)
+    c8, off8 = api.cigar8(cig, np.array([0, 2, 2, 4], np.int64))
+    assert off8.tolist() == [0, 5, 5, 8]
+    assert [(int(b) >> 2, int(b) & 3) for b in c8] == [(63, 0), (63, 0), (63, 0), (11, 0), (3, 1), (63, 2), (1, 2), (10, 0)]
+
+
 def test_mean_distance_float_semantics(oracle):
     lib = api.load()
     for d, a in [(0, 0), (5, 100), (1234567, 17000000), (16777216, 2 ** 27), (20000000, 2 ** 28)]:
