@@ -43,8 +43,8 @@ def parse_args():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (testing only)")
     ap.add_argument("--cpu-sample-chunks", type=int, default=0, help="chunks in the CPU baseline sample (0 = auto)")
-    ap.add_argument("--e2e-lanes", type=int, default=3, help="hsgpu contexts (host threads) of the e2e path")
-    ap.add_argument("--e2e-groups", type=int, default=6, help="groups of contig chunks the e2e path cuts the batch into")
+    ap.add_argument("--e2e-lanes", type=int, default=2, help="hsgpu contexts (host threads) of the e2e path")
+    ap.add_argument("--e2e-groups", type=int, default=1, help="groups of contig chunks the e2e path cuts a step's batch into")
     ap.add_argument("--wall-chunks", type=int, default=0, help="chunks in the HS_call_variants wall-time stage (0 = all, -1 = skip)")
     return ap.parse_args()
 
@@ -455,17 +455,18 @@ def run_call_variants_wall(chunks, args):
 
 
 def run_e2e(chunks, local_rank, ctx, n_lanes, n_groups, steps, warmup, barrier):
-    """The way a caller drives the library from host buffers: the batch is cut into groups of contig chunks,
-    each group goes through one of `n_lanes` hsgpu contexts (one per host thread, as the header prescribes, like
-    the reference's OpenMP loop over contigs). The library lets one context upload at a time, so the kernels of
-    the group that has its data overlap the upload of the next group; CIGARs travel in the 8-bit form; every
-    group's results (suspect lists, depth numerators) come back through hsgpu_suspects_all. Inputs sit in pinned
+    """The way a caller drives the library from host buffers: every step's batch (optionally cut into `n_groups`
+    groups of contig chunks) goes through one of `n_lanes` hsgpu contexts (one per host thread, as the header
+    prescribes, like the reference's OpenMP loop over contigs), steps dealt to the lanes in turn. The library lets
+    one context upload at a time, so the kernels of the batch that has its data overlap the upload of the next
+    one (double buffering); CIGARs travel in the 8-bit form; every batch's results (suspect lists, depth
+    numerators) come back through hsgpu_suspects_all. Every step pays its own H2D and D2H; inputs sit in pinned
     host memory. Returns the device time of the slowest lane and the host wall clock over `steps` steps."""
     import threading
     import torch
     from hairsplitter_b200 import api
     n_groups = max(1, min(n_groups, len(chunks)))
-    n_lanes = max(1, min(n_lanes, n_groups))
+    n_lanes = max(1, n_lanes)
     groups = []
     keep = []
     for g in range(n_groups):
@@ -503,10 +504,14 @@ def run_e2e(chunks, local_rank, ctx, n_lanes, n_groups, steps, warmup, barrier):
         e2e_out[g] = pos.nbytes + au.nbytes + off.nbytes + ds.nbytes
         e2e_sus[g] = int(off[-1])
 
-    def e2e_step():
+    def e2e_steps(n_steps):
+        # work items = (step, group) in order, dealt round-robin to the lanes: with one group per step and two
+        # lanes this is plain double buffering -- the upload of step k+1 overlaps the kernels of step k
+        items = [(st, g) for st in range(n_steps) for g in range(n_groups)]
+
         def work(lane):
-            for g in range(lane, n_groups, n_lanes):
-                e2e_group(lane, g)
+            for i in range(lane, len(items), n_lanes):
+                e2e_group(lane, items[i][1])
         ts = [threading.Thread(target=work, args=(lane,)) for lane in range(1, n_lanes)]
         for t in ts:
             t.start()
@@ -515,17 +520,14 @@ def run_e2e(chunks, local_rank, ctx, n_lanes, n_groups, steps, warmup, barrier):
             t.join()
         return sum(e2e_out)
 
-    d2h_bytes = 0
-    for _ in range(max(1, min(warmup, 3))):
-        d2h_bytes = e2e_step()
+    d2h_bytes = e2e_steps(max(2, min(warmup, 3)))
     barrier()
     t_e2e = time.perf_counter()
     e0 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
     e1 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
     for ev, st_ in zip(e0, lane_streams):
         ev.record(st_)
-    for _ in range(steps):
-        d2h_bytes = e2e_step()
+    d2h_bytes = e2e_steps(steps)
     for ev, st_ in zip(e1, lane_streams):
         ev.record(st_)
     for c in lanes:
@@ -537,7 +539,7 @@ def run_e2e(chunks, local_rank, ctx, n_lanes, n_groups, steps, warmup, barrier):
     for c in lanes[1:]:
         c.close()
     if trace:  # the last step, times in ms from its first call
-        last = sorted(trace[-n_groups:], key=lambda r: r[2])
+        last = sorted(trace[-max(n_groups, 4):], key=lambda r: r[2])
         z = last[0][2]
         for r in last:
             print("  lane %d group %2d: create %.3f-%.3f build -%.3f rank -%.3f suspects_all -%.3f close -%.3f" %
@@ -744,9 +746,10 @@ def main():
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "host_wall_ms_per_step": t_e2e / max(args.steps, 1),
                     "h2d_copy_floor_ms": h2d_floor_ms, "h2d_gbs": h2d_bytes / (h2d_floor_ms * 1e-3) / 1e9,
-                    "path": f"{n_groups} groups of chunks over {n_lanes} hsgpu contexts (one host thread each): "
-                            "hsgpu_pileup_create(pinned host buffers, 8-bit CIGAR; one upload at a time) + build + "
-                            "column_rank + suspects_all"},
+                    "path": f"steps dealt in turn to {n_lanes} hsgpu contexts (one host thread each), {n_groups} group(s) of "
+                            "chunks per step: hsgpu_pileup_create(pinned host buffers, 8-bit CIGAR; one upload at a "
+                            "time, so the upload of step k+1 overlaps the kernels of step k) + build + column_rank + "
+                            "suspects_all; every step pays its own H2D and D2H"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "kernels": kernels,

@@ -46,10 +46,12 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
     const int64_t k0 = cigar_off[r], k1 = cigar_off[r + 1];
     long long sum = 0;
     long long first = k1, last = -1;  // first / last op that is an alignment position (M,=,X,I,D)
+    int clips = 0;
     for (int64_t k = k0 + lane; k < k1; k += 32) {
         const uint32_t op = __ldg(cigar + k);
         const int ty = (int)(op & 15);
         if (op_consumes_q(ty)) sum += op >> 4;
+        if ((ty == OP_S || ty == OP_H) && (op >> 4) > 0) clips = 1;
         if ((op_consumes_q(ty) || ty == OP_I) && (op >> 4) > 0) {
             if (k < first) first = k;
             last = k;
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
     }
     long long tlead = 0;
     int irregular = 0;
+    // the second pass places the clips; most reads have none
+    if (__any_sync(0xffffffffu, clips))
     for (int64_t k = k0 + lane; k < k1; k += 32) {
         const uint32_t op = __ldg(cigar + k);
         const int ty = (int)(op & 15);
@@ -788,35 +792,41 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
     HS_CUDA(ctx, hs_h2d(ctx, p->d_contig_word_off, in->contig_word_off, nc + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_contig_read_off, in->contig_read_off, nc + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_col_base, p->h_tables.data(), 4 * (nc + 1)));
-    // contig of every read and of every tile: looked up on the device (two sorted offset tables)
-    HS_KERNEL(ctx, "owner_fill_kernel", owner_fill_kernel<<<(unsigned)((nr + tiles + 255) / 256 + 1), 256, 0, ctx->stream>>>(
-        nc, nr, p->d_contig_read_off, p->d_read_contig, tiles, p->d_tile_base, p->d_tile_contig));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_bases, in->read_bases, read_words));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_word_off, in->read_word_off, nr + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_len, in->read_len, nr));
+    HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar_off, in->cigar_off, nr + 1));
+    HS_CUDA(ctx, hs_h2d(ctx, p->d_read_start, in->read_start, nr));
+    HS_CUDA(ctx, hs_h2d(ctx, p->d_read_strand, in->read_strand, nr));
     uint16_t* d_cigar16 = nullptr;
+    uint8_t* d_cigar8 = nullptr;
     if (in->cigar8) {
-        uint8_t* d_cigar8 = nullptr;
         HS_CUDA(ctx, hs_alloc(ctx, &d_cigar8, p->n_cigar));
         HS_CUDA(ctx, hs_h2d(ctx, d_cigar8, in->cigar8, p->n_cigar));
+    } else if (in->cigar16) {
+        HS_CUDA(ctx, hs_alloc(ctx, &d_cigar16, p->n_cigar));
+        HS_CUDA(ctx, hs_h2d(ctx, d_cigar16, in->cigar16, p->n_cigar));
+    } else {
+        HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar, in->cigar, p->n_cigar));
+    }
+    // contig of every read and of every tile: looked up on the device (two sorted offset tables)
+    HS_KERNEL(ctx, "owner_fill_kernel", owner_fill_kernel<<<(unsigned)((nr + tiles + 255) / 256 + 1), 256, 0, ctx->stream>>>(
+        nc, nr, p->d_contig_read_off, p->d_read_contig, tiles, p->d_tile_base, p->d_tile_contig));
+    if (d_cigar8) {
         if (p->n_cigar > 0)
             HS_KERNEL(ctx, "cigar8_expand_kernel", cigar8_expand_kernel<<<(unsigned)((p->n_cigar + 16 * 256 - 1) / (16 * 256)), 256, 0, ctx->stream>>>(
                 p->n_cigar, d_cigar8, p->d_cigar));
         hs_free(ctx, d_cigar8);
-    } else if (in->cigar16) {
-        HS_CUDA(ctx, hs_alloc(ctx, &d_cigar16, p->n_cigar));
-        HS_CUDA(ctx, hs_h2d(ctx, d_cigar16, in->cigar16, p->n_cigar));
+    } else if (d_cigar16) {
         if (p->n_cigar > 0)
             HS_KERNEL(ctx, "cigar_expand_kernel", cigar_expand_kernel<<<(unsigned)((p->n_cigar + 255) / 256), 256, 0, ctx->stream>>>(
                 p->n_cigar, d_cigar16, p->d_cigar));
         hs_free(ctx, d_cigar16);
-    } else {
-        HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar, in->cigar, p->n_cigar));
     }
-    HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar_off, in->cigar_off, nr + 1));
-    HS_CUDA(ctx, hs_h2d(ctx, p->d_read_start, in->read_start, nr));
-    HS_CUDA(ctx, hs_h2d(ctx, p->d_read_strand, in->read_strand, nr));
-    // the upload turn ends when the copies have landed (the caller's buffers are free again, too)
+    // The upload turn ends when the stream is idle: the copies have landed (the caller's buffers are free again) and
+    // the two small kernels behind them are done. Releasing the turn earlier, on an event behind the last copy, was
+    // measured slower and unstable (2.5-4.6 ms per e2e step against a steady 2.45 ms): the next context's upload
+    // then competes with this context's first kernels and its allocation-size round trip.
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = p;
     return HSGPU_OK;
