@@ -17,6 +17,7 @@
 
 #define CT_ROWS 256  // rows (reads) staged per batch
 #define CT_NPA 32    // active partitions staged per chunk
+#define CT_SSTRIDE (CT_ROWS + 4)  // row stride of the staged states: the 32 partitions of a chunk fall in different banks
 
 // computeChiSquare (:1135-1163) with the reference's exact mix of float and double arithmetic
 // (x86-64 SSE2, no FMA contraction): float margins and expected counts, squares and quotients in
@@ -46,7 +47,8 @@ __device__ __forceinline__ float hs_chi_square(int n00, int n01, int n10, int n1
 // secondFrequent of :832-844. `order` holds the codes (minus 33) in order of first appearance among the
 // partition's reads, hist their counts. The reference compares `char ref_base != unsigned char key`
 // (:838), which is always true for codes >= 128, so there the reference code itself competes.
-__device__ int hs_select_alt(const uint8_t* s_order, const uint16_t* s_hist, int stride, int tid, int m, int ref) {
+__device__ int hs_select_alt(const uint8_t* s_order, const uint16_t* s_hist, int stride, int tid, int m, int ref,
+                             const HsRankLut* __restrict__ lut) {
     const bool ref_excluded = ref < 128;
     int max2 = -1, alt = ' ', ties = 0;
     bool ref_seen = false;
@@ -59,14 +61,43 @@ __device__ int hs_select_alt(const uint8_t* s_order, const uint16_t* s_hist, int
         else if (cnt == max2) ties++;
     }
     if (ties <= 1) return alt;
-    // several codes share the maximum: the first one in the map's iteration order wins
+    // Several codes share the maximum: the first one in the map's iteration order wins. A flat robin-hood table
+    // keeps its entries sorted by home bucket (rank.cuh), so the tied key with the smallest home bucket in the
+    // table's final incarnation wins whenever no other tied key shares that bucket and the layout never forced
+    // an early growth (no entry 6 or more slots from home, as in hs_rank_hashbits). Otherwise: literal replay.
+    const int n = m + (ref_seen ? 0 : 1);  // content2[ref_base] creates the entry (:833)
+    if (lut && n <= 51) {
+        const int level = hs_rank_level(n);
+        const uint8_t* __restrict__ home = lut->home[level];
+        unsigned long long occ[4] = {0, 0, 0, 0};  // 4-bit occupancy counters of up to 64 buckets
+        int best = 1 << 30, nbest = 0;
+        for (int k = -1; k < m; k++) {
+            if (k < 0 && ref_seen) continue;
+            const int key = k < 0 ? ref : s_order[k * stride + tid] + HS_CODE0;
+            const int h = __ldg(home + key);
+            occ[h >> 4] += 1ull << (4 * (h & 15));
+            if (k < 0 || (ref_excluded && key == ref)) continue;
+            if ((int)s_hist[(key - HS_CODE0) * stride + tid] != max2) continue;
+            if (h < (best >> 8)) { best = (h << 8) | key; nbest = 1; }
+            else if (h == (best >> 8)) nbest++;
+        }
+        int next_free = 0, maxd = 0;
+        const int nb = 8 << level;
+        for (int b = 0; b < nb; b++) {
+            const int cnt = (int)((occ[b >> 4] >> (4 * (b & 15))) & 15ull);
+            if (next_free < b) next_free = b;
+            next_free += cnt;
+            if (cnt && next_free - 1 - b > maxd) maxd = next_free - 1 - b;
+        }
+        if (nbest == 1 && maxd < 6) return best & 0xff;
+    }
     HsRhTable t;
     hs_rh_new(t);
     for (int k = 0; k < m; k++) hs_rh_insert(t, (uint8_t)(s_order[k * stride + tid] + HS_CODE0));
-    if (!ref_seen) hs_rh_insert(t, (uint8_t)ref);  // content2[ref_base] creates the entry (:833)
+    if (!ref_seen) hs_rh_insert(t, (uint8_t)ref);
     uint8_t it[HS_RH_MAXKEYS];
-    const int n = hs_rh_iterate(t, it);
-    for (int i = 0; i < n; i++) {
+    const int nk = hs_rh_iterate(t, it);
+    for (int i = 0; i < nk; i++) {
         const int key = it[i];
         if (ref_excluded && key == ref) continue;
         if (key < HS_CODE0) continue;
@@ -89,6 +120,7 @@ struct TablesArgs {
     const int64_t* row_base;
     const uint8_t* codes;
     const uint8_t* k0;
+    const HsRankLut* lut;
     hsgpu_distance* out;
 };
 
@@ -171,7 +203,7 @@ __global__ void __launch_bounds__(128) partition_tables_kernel(TablesArgs a) {
                     }
                 }
             }
-            if (pass == 0 && valid && nb > 0) alt = hs_select_alt(s_order, s_hist, 128, tid, m, ref);
+            if (pass == 0 && valid && nb > 0) alt = hs_select_alt(s_order, s_hist, 128, tid, m, ref, a.lut);
         }
         if (valid) {
             hsgpu_distance d;
@@ -207,6 +239,10 @@ struct FilterArgs {
     const uint8_t* k0;
     const uint8_t* flags;
     const uint32_t* depth;
+    const uint32_t* counts;   // c0,c1,c2 per column (column ranking)
+    const uint8_t* pstate_t;  // [n_reads][npad]: the transpose of pstate, rows padded to 16 partitions
+    int npad;
+    const HsRankLut* lut;
     uint8_t* kept;  // [L]
 };
 
@@ -230,12 +266,13 @@ __global__ void __launch_bounds__(128) robust_filter_kernel(FilterArgs a) {
     uint4* s_tile = reinterpret_cast<uint4*>(smem);                                          // CT_ROWS*128
     uint16_t* s_hist = reinterpret_cast<uint16_t*>(smem + CT_ROWS * HS_TILE);                // [125][128]
     uint8_t* s_order = smem + CT_ROWS * HS_TILE + HS_NCODES * 128 * 2;                       // [125][128]
-    uint8_t* s_state = smem + CT_ROWS * HS_TILE + HS_NCODES * 128 * 3;                       // [CT_NPA][CT_ROWS]
-    int32_t* s_reads = reinterpret_cast<int32_t*>(s_state + CT_NPA * CT_ROWS);               // [CT_ROWS]
+    uint8_t* s_state = smem + CT_ROWS * HS_TILE + HS_NCODES * 128 * 3;                       // [CT_NPA][CT_SSTRIDE]
+    int32_t* s_reads = reinterpret_cast<int32_t*>(s_state + CT_NPA * CT_SSTRIDE);            // [CT_ROWS]
     __shared__ int s_cols[HS_TILE];
     __shared__ int s_parts[CT_NPA];
     __shared__ int s_ncols, s_nparts;
     __shared__ unsigned s_keep[HS_TILE];  // per column: 1 = kept
+    __shared__ unsigned s_pmask[4];       // partitions pb..pb+127 that hold one of the tile's reads
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int q0 = blockIdx.x * HS_TILE;
@@ -251,7 +288,12 @@ __global__ void __launch_bounds__(128) robust_filter_kernel(FilterArgs a) {
     {
         const int q = q0 + tid;
         const unsigned f = (q < a.L) ? a.flags[a.g0 + q] : 0u;
-        const bool act = (f & (HS_FLAG_INLIST | HS_FLAG_RESCUE)) != 0;
+        // Loop 4 keeps a column only if n10 + n00 > 4 (:756): reads that carry the alternative allele. No code but
+        // the column's own most frequent one (ref_base = k0) has more than c1 carriers, and when the reference's
+        // char/unsigned char quirk makes ref_base its own alternative the two counters stay 0 -- so a column with
+        // c1 <= 4 can only be kept by loop 3, i.e. if it is a suspect.
+        bool act = (f & HS_FLAG_INLIST) != 0;
+        if (!act && (f & HS_FLAG_RESCUE)) act = a.counts[3 * (a.g0 + q) + 1] > 4u;
         for (int w = 0; w < 4; w++) {
             if (wid == w) {
                 const unsigned mk = __ballot_sync(0xffffffffu, act);
@@ -274,16 +316,27 @@ __global__ void __launch_bounds__(128) robust_filter_kernel(FilterArgs a) {
     __syncthreads();
 
     for (int pb = 0; pb < a.n_parts; pb += 128) {
-        // which of partitions pb..pb+127 have one of the tile's reads?
-        bool present = false;
-        const int p = pb + tid;
-        if (p < a.n_parts) {
-            const uint8_t* __restrict__ ps = a.pstate + (int64_t)p * a.n_reads;
-            for (int i = 0; i < nlist && !present; i++) {
+        // which of partitions pb..pb+127 have one of the tile's reads? One 16-byte load covers 16 partitions of a
+        // read (pstate_t), every thread takes (read, vector) pairs, the answer is a 128-bit mask in shared memory
+        __syncthreads();
+        if (tid < 4) s_pmask[tid] = 0;
+        __syncthreads();
+        {
+            const int nvec = min(8, (a.npad - pb) >> 4);
+            for (int v = tid; v < nlist * nvec; v += 128) {
+                const int i = v / nvec, j = v - i * nvec;
                 const int32_t n = single ? s_reads[i] : (int32_t)(a.tile_reads[list_off + i] - a.read0);
-                present = (ps[n] & 3) != 0;
+                const uint4 x = __ldg(reinterpret_cast<const uint4*>(a.pstate_t + (int64_t)n * a.npad + pb + 16 * j));
+                const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+                unsigned bits = 0;
+#pragma unroll
+                for (int b = 0; b < 16; b++) bits |= (((w[b >> 2] >> (8 * (b & 3))) & 3u) ? 1u : 0u) << b;
+                if (bits) atomicOr(&s_pmask[j >> 1], bits << (16 * (j & 1)));
             }
         }
+        __syncthreads();
+        const int p = pb + tid;
+        const bool present = p < a.n_parts && ((s_pmask[tid >> 5] >> (tid & 31)) & 1u);
         // chunks of up to CT_NPA active partitions
         unsigned long long done_mask_lo = 0;  // unused; partitions are consumed in order below
         (void)done_mask_lo;
@@ -316,8 +369,10 @@ __global__ void __launch_bounds__(128) robust_filter_kernel(FilterArgs a) {
                 const int kk = valid ? item % npa : 0;
                 const int q = q0 + col;
                 const int ref = valid ? a.k0[a.g0 + q] : 0;
-                int m = 0, nb = 0, alt = ' ';
+                const unsigned f = valid ? a.flags[a.g0 + q] : 0u;
+                int m = 0, nb = 0, alt = ' ', nref = 0;
                 int n00 = 0, n01 = 0, n10 = 0, n11 = 0;
+                bool second = false;  // does this item need its 2x2 table?
                 for (int pass = 0; pass < 2; pass++) {
                     for (int b0 = 0; b0 < nlist; b0 += CT_ROWS) {
                         const int nrows = min(CT_ROWS, nlist - b0);
@@ -331,41 +386,64 @@ __global__ void __launch_bounds__(128) robust_filter_kernel(FilterArgs a) {
                             if (single) __syncthreads();
                             for (int v = tid; v < npa * nrows; v += 128) {
                                 const int k2 = v / nrows, row = v - k2 * nrows;
-                                s_state[k2 * CT_ROWS + row] = a.pstate[(int64_t)s_parts[k2] * a.n_reads + s_reads[row]];
+                                s_state[k2 * CT_SSTRIDE + row] = a.pstate[(int64_t)s_parts[k2] * a.n_reads + s_reads[row]];
                             }
                             __syncthreads();
                         }
                         if (valid) {
-                            const uint8_t* st_row = s_state + kk * CT_ROWS;
+                            const uint8_t* st_row = s_state + kk * CT_SSTRIDE;
                             if (pass == 0) {
-                                for (int row = 0; row < nrows; row++) {
-                                    const int code = s_bytes[row * HS_TILE + col];
-                                    if (code && (st_row[row] & 3)) {
-                                        const int idx = code - HS_CODE0;
-                                        const unsigned c = s_hist[idx * 128 + tid];
-                                        if (c == 0) s_order[(m++) * 128 + tid] = (uint8_t)idx;
-                                        s_hist[idx * 128 + tid] = (uint16_t)(c + 1);
-                                        nb++;
-                                    }
-                                }
-                            } else if (nb > 0) {
+                                // histogram of the codes among the partition's reads, first-seen order kept. The
+                                // column's own majority code (most of the rows) is counted in a register; the
+                                // rows it holds with state +1 / -1 are n11 / n01 of the table (:893-949).
                                 for (int row = 0; row < nrows; row++) {
                                     const int code = s_bytes[row * HS_TILE + col];
                                     const int sg = st_row[row] & 3;
-                                    if (code && (sg == 1 || sg == 2)) {
-                                        if (code == ref) { if (sg == 1) n11++; else n01++; }
-                                        else if (code == alt) { if (sg == 1) n10++; else n00++; }
+                                    if (code && sg) {
+                                        const int idx = code - HS_CODE0;
+                                        if (code == ref) {
+                                            if (nref == 0) s_order[(m++) * 128 + tid] = (uint8_t)idx;
+                                            nref++;
+                                            n11 += sg == 1;
+                                            n01 += sg == 2;
+                                        } else {
+                                            const unsigned c = s_hist[idx * 128 + tid];
+                                            if (c == 0) s_order[(m++) * 128 + tid] = (uint8_t)idx;
+                                            s_hist[idx * 128 + tid] = (uint16_t)(c + 1);
+                                        }
+                                        nb++;
+                                    }
+                                }
+                            } else if (second) {
+                                for (int row = 0; row < nrows; row++) {
+                                    const int code = s_bytes[row * HS_TILE + col];
+                                    const int sg = st_row[row] & 3;
+                                    if (code == alt && code != ref) {
+                                        n10 += sg == 1;
+                                        n00 += sg == 2;
                                     }
                                 }
                             }
                         }
                     }
-                    if (pass == 0 && valid && nb > 0) alt = hs_select_alt(s_order, s_hist, 128, tid, m, ref);
+                    if (pass == 0 && valid && nb > 0) {
+                        if (nref) s_hist[(ref - HS_CODE0) * 128 + tid] = (uint16_t)nref;
+                        // A column that is not a suspect is only kept through loop 4, which needs n10 + n00 > 4
+                        // (:756): at least 5 of the partition's reads on one code other than ref_base.
+                        // (codes >= 128 never count as ref_base in the reference's comparison, :838: no shortcut there)
+                        second = (f & HS_FLAG_INLIST) != 0 || ref >= 128;
+                        if (!second) {
+                            for (int k = 0; k < m && !second; k++) {
+                                const int idx = s_order[k * 128 + tid];
+                                second = idx + HS_CODE0 != ref && s_hist[idx * 128 + tid] > 4;
+                            }
+                        }
+                        if (second) alt = hs_select_alt(s_order, s_hist, 128, tid, m, ref, a.lut);
+                    }
                 }
                 if (valid) {
                     for (int k = 0; k < m; k++) s_hist[s_order[k * 128 + tid] * 128 + tid] = 0;
-                    if (nb > 0) {
-                        const unsigned f = a.flags[a.g0 + q];
+                    if (nb > 0 && second) {
                         const float chi = hs_chi_square(n00, n01, n10, n11);
                         bool keep = false;
                         // loop 3 (:721-738): suspects
@@ -438,8 +516,11 @@ __global__ void set_inlist_kernel(int n, const int32_t* __restrict__ pos, int64_
 }
 
 // dense partition-state matrix on the host: 0 absent/masked, 1 = +1, 2 = -1, 3 = 0, |4 solid
-static int build_pstate(hsgpu_ctx* ctx, const hsgpu_partitions* parts, int64_t n_reads, std::vector<uint8_t>& out) {
+// out_t (optional): the transpose [n_reads][npad], rows padded to npad partitions
+static int build_pstate(hsgpu_ctx* ctx, const hsgpu_partitions* parts, int64_t n_reads, std::vector<uint8_t>& out,
+                        std::vector<uint8_t>* out_t = nullptr, int npad = 0) {
     out.assign((size_t)parts->n_parts * (size_t)n_reads, 0);
+    if (out_t) out_t->assign((size_t)std::max<int64_t>(n_reads, 1) * (size_t)npad, 0);
     for (int p = 0; p < parts->n_parts; p++) {
         for (int64_t i = parts->part_off[p]; i < parts->part_off[p + 1]; i++) {
             const int32_t n = parts->read_idx[i];
@@ -453,13 +534,14 @@ static int build_pstate(hsgpu_ctx* ctx, const hsgpu_partitions* parts, int64_t n
             }
             if (v && parts->less && parts->more && parts->less[i] <= 1 && parts->more[i] >= 3) v |= 4;
             out[(size_t)p * n_reads + n] = v;
+            if (out_t) (*out_t)[(size_t)n * npad + p] = v;
         }
     }
     return HSGPU_OK;
 }
 
 static const int kTablesSmem = HS_NCODES * 128 * 3 + CT_ROWS * 5;
-static const int kFilterSmem = CT_ROWS * HS_TILE + HS_NCODES * 128 * 3 + CT_NPA * CT_ROWS + CT_ROWS * 4;
+static const int kFilterSmem = CT_ROWS * HS_TILE + HS_NCODES * 128 * 3 + CT_NPA * CT_SSTRIDE + CT_ROWS * 4;
 
 extern "C" {
 
@@ -507,6 +589,7 @@ int hsgpu_partition_tables(hsgpu_pileup* p, int32_t contig, const hsgpu_partitio
     a.row_base = p->d_row_base;
     a.codes = p->d_codes;
     a.k0 = p->d_k0;
+    a.lut = (const HsRankLut*)ctx->d_rank_lut;
     a.out = d_out;
     HS_KERNEL(ctx, "partition_tables_kernel", partition_tables_kernel<<<n_cols, 128, kTablesSmem, ctx->stream>>>(a));
     HS_CUDA(ctx, hs_d2h(ctx, out, d_out, n_out));
@@ -529,10 +612,13 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     if (parts->n_parts == 0 || L == 0) return HSGPU_OK;  // :640-642: no partition, nothing is kept
     for (int i = 0; i < n_suspects; i++)
         if (suspect_pos[i] < 0 || suspect_pos[i] >= L) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_robust_filter: position out of range");
-    std::vector<uint8_t> pst;
-    int rc = build_pstate(ctx, parts, R, pst);
+    // with the transpose, rows padded to 16 partitions (the kernel's presence scan reads 16 partitions of a read at once)
+    const int npad = (parts->n_parts + 15) & ~15;
+    std::vector<uint8_t> pst, pst_t;
+    int rc = build_pstate(ctx, parts, R, pst, &pst_t, npad);
     if (rc) return rc;
     uint8_t* d_pst = nullptr;
+    uint8_t* d_pst_t = nullptr;
     int32_t* d_pos = nullptr;
     uint8_t* d_kept = nullptr;
     int32_t* d_list = nullptr;
@@ -541,6 +627,8 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     HS_CUDA(ctx, hs_alloc(ctx, &d_kept, L));
     HS_CUDA(ctx, hs_alloc(ctx, &d_list, (int64_t)kept_capacity + 1));
     HS_CUDA(ctx, hs_h2d(ctx, d_pst, pst.data(), (int64_t)pst.size()));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_pst_t, (int64_t)pst_t.size()));
+    HS_CUDA(ctx, hs_h2d(ctx, d_pst_t, pst_t.data(), (int64_t)pst_t.size()));
     HS_CUDA(ctx, hs_h2d(ctx, d_pos, suspect_pos, n_suspects));
     const int64_t g0 = p->h_col_base[contig];
     if (n_suspects > 0) {
@@ -569,6 +657,10 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     a.k0 = p->d_k0;
     a.flags = p->d_flags;
     a.depth = p->d_depth;
+    a.counts = p->d_counts;
+    a.pstate_t = d_pst_t;
+    a.npad = npad;
+    a.lut = (const HsRankLut*)ctx->d_rank_lut;
     a.kept = d_kept;
     const unsigned ntile = (unsigned)((L + HS_TILE - 1) / HS_TILE);
     HS_KERNEL(ctx, "robust_filter_kernel", robust_filter_kernel<<<ntile, 128, kFilterSmem, ctx->stream>>>(a));
@@ -587,6 +679,7 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
         HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     hs_free(ctx, d_pst);
+    hs_free(ctx, d_pst_t);
     hs_free(ctx, d_pos);
     hs_free(ctx, d_kept);
     hs_free(ctx, d_list);
