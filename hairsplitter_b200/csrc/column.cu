@@ -652,11 +652,11 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
         HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // mean_error is caller memory
         hs_free(ctx, d_me);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // per device: function attributes belong to the device's context
+    if (!attr_set[ctx->device & 63]) {
         HS_CUDA(ctx, cudaFuncSetAttribute(column_rank_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           column_smem<uint16_t>()));
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     if (p->n_tiles > 0) {
         ColumnArgs a;

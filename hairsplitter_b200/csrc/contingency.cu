@@ -568,10 +568,10 @@ int hsgpu_partition_tables(hsgpu_pileup* p, int32_t contig, const hsgpu_partitio
     HS_CUDA(ctx, hs_alloc(ctx, &d_out, n_out));
     HS_CUDA(ctx, hs_h2d(ctx, d_pst, pst.data(), (int64_t)pst.size()));
     HS_CUDA(ctx, hs_h2d(ctx, d_pos, pos, n_cols));
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};  // per device: function attributes belong to the device's context
+    if (!attr[ctx->device & 63]) {
         HS_CUDA(ctx, cudaFuncSetAttribute(partition_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTablesSmem));
-        attr = true;
+        attr[ctx->device & 63] = true;
     }
     TablesArgs a;
     a.n_cols = n_cols;
@@ -634,10 +634,10 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     if (n_suspects > 0) {
         HS_KERNEL(ctx, "set_inlist_kernel", set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 1));
     }
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};  // per device: function attributes belong to the device's context
+    if (!attr[ctx->device & 63]) {
         HS_CUDA(ctx, cudaFuncSetAttribute(robust_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFilterSmem));
-        attr = true;
+        attr[ctx->device & 63] = true;
     }
     FilterArgs a;
     a.contig = contig;

@@ -697,10 +697,10 @@ int hsgpu_pairs_compute(hsgpu_pairs* h) {
         HS_CUDA(ctx, cudaMemsetAsync(h->d_diff, 0, out_bytes, ctx->stream));
     }
     if (h->n_work > 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[64] = {};  // per device: function attributes belong to the device's context
+        if (!attr_set[ctx->device & 63]) {
             HS_CUDA(ctx, cudaFuncSetAttribute(pair_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
-            attr_set = true;
+            attr_set[ctx->device & 63] = true;
         }
         const int grid = (int)std::min<int64_t>(h->n_work, ctx->sm_count);
         HS_KERNEL(ctx, "pair_umma_kernel", pair_umma_kernel<<<grid, PG_THREADS, PG_SMEM, ctx->stream>>>(
