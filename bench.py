@@ -560,7 +560,7 @@ def run_reference(args, rank, world):
         return
     from hairsplitter_b200 import synth
     cores = host_cores()
-    n_sample = args.cpu_sample_chunks or max(1, min(cores, 8))
+    n_sample = args.cpu_sample_chunks or max(1, min(cores, 17))  # one chunk per host thread, up to the whole workload
     chunks, info = synth.make_config(args.config, scale=args.scale, seed=args.config, n_chunks=n_sample)
     n_threads = min(cores, len(chunks))
     for _ in range(args.warmup if args.warmup < 1 else 1):  # one warm-up pass is enough for a CPU code path
@@ -757,7 +757,7 @@ def main():
         }
         if world == 1:
             cores = host_cores()
-            n_sample = args.cpu_sample_chunks or max(1, min(cores, 8, len(chunks)))
+            n_sample = args.cpu_sample_chunks or max(1, min(cores, len(chunks)))  # every host core gets a chunk
             sample = chunks[:n_sample]
             n_threads = min(cores, len(sample))
             rate, kind, dt = cpu_reference_rate(sample, n_threads)

@@ -696,7 +696,7 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
             HS_KERNEL(ctx, "column_rank_kernel<u16>", column_rank_kernel<uint16_t><<<(unsigned)p->n_tiles, HS_TILE, column_smem<uint16_t>(), ctx->stream>>>(a));
         uint32_t* lit_items = p->d_item_off + p->n_cols;
         HS_KERNEL(ctx, "column_rank_deferred_kernel",
-                  column_rank_deferred_kernel<false><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(a, nc, lit_items));
+                  column_rank_deferred_kernel<false><<<ctx->sm_count * 16, 128, 0, ctx->stream>>>(a, nc, lit_items));  // every resident slot: the items are long, divergent and few per thread
         HS_KERNEL(ctx, "column_rank_deferred_kernel<literal>",
                   column_rank_deferred_kernel<true><<<ctx->sm_count * 4, 128, 0, ctx->stream>>>(a, nc, lit_items));
         LiteralArgs la;

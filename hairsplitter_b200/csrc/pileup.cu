@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
     long long sum = 0;
     long long first = k1, last = -1;  // first / last op that is an alignment position (M,=,X,I,D)
     int clips = 0;
+#pragma unroll 8
     for (int64_t k = k0 + lane; k < k1; k += 32) {
         const uint32_t op = __ldg(cigar + k);
         const int ty = (int)(op & 15);
