@@ -338,8 +338,6 @@ __global__ void __launch_bounds__(128) robust_filter_kernel(FilterArgs a) {
         const int p = pb + tid;
         const bool present = p < a.n_parts && ((s_pmask[tid >> 5] >> (tid & 31)) & 1u);
         // chunks of up to CT_NPA active partitions
-        unsigned long long done_mask_lo = 0;  // unused; partitions are consumed in order below
-        (void)done_mask_lo;
         int consumed = 0;  // number of active partitions (in thread order) already processed
         for (;;) {
             __syncthreads();

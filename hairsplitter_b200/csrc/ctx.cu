@@ -87,7 +87,7 @@ int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
     HS_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
         char buf[256];
-        snprintf(buf, sizeof(buf), "libhsgpu: device %d (%s) is sm_%d%d; kernels are built for sm_100a only", device,
+        snprintf(buf, sizeof(buf), "libhsgpu: device %d (%.64s) is sm_%d%d; kernels are built for sm_100a only", device,
                  prop.name, prop.major, prop.minor);
         hs_set_error(nullptr, buf);
         return HSGPU_ERR_NO_DEVICE;

@@ -4,6 +4,7 @@
 // partition x column filtering (loops 3+4 of keep_only_robust_variants) run on the GPU through the
 // C ABI of libhsgpu (include/hsgpu.h). Contigs are sharded over the visible GPUs, heaviest first.
 #include <omp.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -11,6 +12,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <functional>
 #include <future>
 #include <numeric>
 #include <string>
@@ -86,8 +88,9 @@ static void fetch_columns(hsgpu_ctx* ctx, hsgpu_pileup* pu, int c, const std::ve
 }
 
 // one batch of contigs on one GPU
-static void process_batch(hsgpu_ctx* ctx, const Store& st, const std::string& reads_path, const std::vector<int>& batch,
-                          float auto_threshold, std::vector<ContigResult>& results) {
+// (get_ctx waits for the context that is being created in the background: the reads are loaded and packed first)
+static void process_batch(const std::function<hsgpu_ctx*()>& get_ctx, const Store& st, const std::string& reads_path,
+                          const std::vector<int>& batch, float auto_threshold, std::vector<ContigResult>& results) {
     const int nc = (int)batch.size();
     std::vector<int32_t> contig_len(nc), read_len, read_start;
     std::vector<int64_t> contig_word_off(nc + 1, 0), contig_read_off(nc + 1, 0), read_word_off(1, 0), cigar_off(1, 0);
@@ -162,8 +165,11 @@ static void process_batch(hsgpu_ctx* ctx, const Store& st, const std::string& re
     in.read_start = read_start.data();
     in.read_strand = read_strand.data();
     phase("  load+pack reads");
+    hsgpu_ctx* ctx = get_ctx();
+    phase("  wait for the CUDA context");
     hsgpu_pileup* pu = nullptr;
     GPU_CHECK(ctx, hsgpu_pileup_create(ctx, &in, &pu));
+    phase("    upload");
     GPU_CHECK(ctx, hsgpu_pileup_build(pu));                            // generate_msa
     GPU_CHECK(ctx, hsgpu_column_rank(pu, nullptr, auto_threshold));    // call_variants
     std::vector<int64_t> cells(nc), dist(nc), alen(nc), depth_sum(nc);
@@ -247,6 +253,7 @@ int main(int argc, char* argv[]) {
                      "<amplicon> <DEBUG> <file_out> <vcfFile> <automatic_snp_threshold>\n";
         return 0;
     }
+    const double t_main = omp_get_wtime();
     const std::string gfa_file = argv[1], reads_file = argv[2], sam_file = argv[3];
     const int num_threads = std::stoi(argv[4]);
     const std::string error_rate_out = argv[6];
@@ -271,11 +278,15 @@ int main(int argc, char* argv[]) {
     if (const char* e = std::getenv("HSGPU_DEVICE")) first_device = std::atoi(e);
     std::vector<std::future<hsgpu_ctx*>> contexts;
     for (int g = 0; g < n_gpus; g++)
-        contexts.push_back(std::async(std::launch::async, [=]() {
+        contexts.push_back(std::async(std::getenv("HS_CTX_FIRST") ? std::launch::deferred : std::launch::async, [=]() {
+            const double t0 = omp_get_wtime();
             hsgpu_ctx* ctx = nullptr;
             if (hsgpu_ctx_create(first_device + g, &ctx) != HSGPU_OK) return (hsgpu_ctx*)nullptr;
+            if (g_timing) fprintf(stderr, "[hs timing] (context %d created in %.3f s on its own thread)\n", g, omp_get_wtime() - t0);
             return ctx;
         }));
+    if (std::getenv("HS_CTX_FIRST"))  // experiment: create the contexts before anything else, one after the other
+        for (auto& f : contexts) f.wait();
     Store st;
     std::cout << " - Loading all reads from " << reads_file << " in memory\n";
     parse_reads(reads_file, st);
@@ -324,16 +335,21 @@ int main(int argc, char* argv[]) {
     for (int g = 0; g < n_gpus; g++) {
         phase("shard setup");
         omp_set_num_threads(std::max(1, num_threads / n_gpus));  // host threads of this shard's inner loops
-        hsgpu_ctx* ctx = contexts[g].get();
-        if (!ctx) {
-            std::cout << "ERROR: no usable GPU " << first_device + g << ": " << hsgpu_last_error(nullptr) << std::endl;
-            std::exit(1);  // there is no CPU fallback
-        }
+        hsgpu_ctx* ctx = nullptr;
+        const std::function<hsgpu_ctx*()> get_ctx = [&]() {
+            if (!ctx) {
+                ctx = contexts[g].get();
+                if (!ctx) {
+                    std::cout << "ERROR: no usable GPU " << first_device + g << ": " << hsgpu_last_error(nullptr) << std::endl;
+                    std::exit(1);  // there is no CPU fallback
+                }
+            }
+            return ctx;
+        };
         if (shard[g].empty()) {
-            hsgpu_ctx_destroy(ctx);
+            hsgpu_ctx_destroy(get_ctx());
             continue;
         }
-        phase("  ctx create");
         std::sort(shard[g].begin(), shard[g].end());
         std::vector<int> batch;
         double cells = 0;
@@ -341,12 +357,12 @@ int main(int argc, char* argv[]) {
             batch.push_back(shard[g][i]);
             cells += weight[shard[g][i]];
             if (cells >= batch_cells || i + 1 == shard[g].size()) {
-                process_batch(ctx, st, reads_file, batch, auto_threshold, results);
+                process_batch(get_ctx, st, reads_file, batch, auto_threshold, results);
                 batch.clear();
                 cells = 0;
             }
         }
-        hsgpu_ctx_destroy(ctx);
+        hsgpu_ctx_destroy(get_ctx());
     }
 
     phase("gpu shards total");
@@ -368,5 +384,13 @@ int main(int argc, char* argv[]) {
     error_file.close();
     write_outputs(st, variants, file_out, vcf_file);
     phase("write_outputs");
+    if (g_timing) fprintf(stderr, "[hs timing] %-28s %8.3f s\n", "main() so far", omp_get_wtime() - t_main);
+    // Every output file is written and closed. Leaving through exit() would now spend a few hundred milliseconds
+    // unwinding: the CUDA runtime's atexit handler tears the primary context down and the parsed reads (hundreds of
+    // megabytes of strings) are freed one by one. The operating system reclaims both at once.
+    std::cout.flush();
+    std::cerr.flush();
+    fflush(nullptr);
+    if (!std::getenv("HS_FULL_TEARDOWN")) _exit(0);
     return 0;
 }

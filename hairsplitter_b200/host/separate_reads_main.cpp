@@ -6,6 +6,7 @@
 // C ABI of libhsgpu (hsgpu_pairs_*, hsgpu_graph_*), all windows of all contigs of a shard in one batch. Contigs
 // are sharded over the visible GPUs (HSGPU_NGPUS, HSGPU_DEVICE), heaviest first.
 #include <omp.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -253,6 +254,12 @@ int main(int argc, char* argv[]) {
     st.ctxs.assign((size_t)st.n_gpus, nullptr);
     g_timing = std::getenv("HS_TIMING") != nullptr;
     const int rc = separate_reads_pipeline(argc, argv, gpu_prepare, gpu_stages, &st);
+    // The .gro file is written and closed (scoped streams in the pipeline). Skip the unwinding (CUDA context
+    // teardown in the runtime's atexit handler, freeing the parsed columns): the operating system reclaims both.
+    std::cout.flush();
+    std::cerr.flush();
+    fflush(nullptr);
+    if (!std::getenv("HS_FULL_TEARDOWN")) _exit(rc);
     for (hsgpu_ctx* c : st.ctxs)
         if (c) hsgpu_ctx_destroy(c);
     return rc;

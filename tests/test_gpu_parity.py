@@ -141,17 +141,18 @@ def test_many_partitions_tables(gpu_ctx, oracle):
     pu.close()
 
 
-@pytest.mark.parametrize("case", ["small", "medium", "hifi", "deep", "many_parts"])
+@pytest.mark.parametrize("case", ["small", "medium", "hifi", "deep", "many_parts", "over128_parts"])
 def test_robust_filter_matches_oracle(gpu_ctx, oracle, case):
     cb = {"small": lambda: cases.small_case(seed=91), "medium": lambda: cases.medium_case(seed=92),
           "hifi": lambda: cases.hifi_case(seed=93), "deep": lambda: cases.deep_case(seed=94),
-          "many_parts": lambda: cases.small_case(seed=95)}[case]()
+          "many_parts": lambda: cases.small_case(seed=95),
+          "over128_parts": lambda: cases.small_case(seed=96, length=4000, depth=40)}[case]()
     pk, pu = _build(gpu_ctx, [cb])
     o, oc, md = _check_contig(oracle, pu, 0, cb)
     rng = np.random.default_rng(7)
     parts = None
     from oracle import pyoracle
-    if pyoracle.ref_available() and case != "many_parts":
+    if pyoracle.ref_available() and case not in ("many_parts", "over128_parts"):
         R = pyoracle.RefCV(cb)
         rc = R.call_variants()
         assert np.array_equal(rc["suspects"]["pos"], oc["suspect_pos"])
@@ -159,7 +160,8 @@ def test_robust_filter_matches_oracle(gpu_ctx, oracle, case):
         kept = pu.robust_filter(0, parts, oc["suspect_pos"])
         assert np.array_equal(kept, filt["pos"])  # the reference's own snps_out
     if parts is None or len(parts) == 0:
-        parts = _random_partitions(rng, cb, o, 70 if case == "many_parts" else 12)
+        # over128_parts: the kernel takes partitions 128 at a time (presence masks, transposed state rows of 160)
+        parts = _random_partitions(rng, cb, o, {"many_parts": 70, "over128_parts": 150}.get(case, 12))
     want = oracle.robust_filter(o["col_off"], o["read_idx"], o["code"], oc["ref_base"], oc["second_base"], parts,
                                 oc["suspect_pos"])
     kept = pu.robust_filter(0, parts, oc["suspect_pos"])
@@ -275,4 +277,12 @@ def test_suspects_all_equals_the_per_contig_calls(gpu_ctx):
     for ci in range(len(batch)):
         p1, a1 = pu.suspects(ci)
         assert np.array_equal(pos[off[ci]:off[ci + 1]], p1) and np.array_equal(au[off[ci]:off[ci + 1]], a1)
+    # a buffer that is too small: HSGPU_ERR_CAPACITY, with the offsets filled in so the call can be retried
+    off2 = np.zeros(len(batch) + 1, np.int64)
+    small = np.zeros(1, np.int32)
+    rc = pu.lib.hsgpu_suspects_all(pu.h, 1, small.ctypes.data, None, off2.ctypes.data, None)
+    assert rc == -4 and np.array_equal(off2, off)
+    # only the counts
+    rc = pu.lib.hsgpu_suspects_all(pu.h, 0, None, None, off2.ctypes.data, None)
+    assert rc == 0 and np.array_equal(off2, off)
     pu.close()
