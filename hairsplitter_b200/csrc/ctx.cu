@@ -311,9 +311,8 @@ __global__ void scan_total_kernel(const int64_t* block_off, const int64_t* block
 }
 
 // Short inputs (every per-read / per-tile table of a batch of contig chunks): ONE launch of one CTA that walks
-// the array in pieces of 16384 with a running carry -- 1 driver call instead of the 13 of the recursive scan.
+// the array in pieces of 4096 with a running carry, the next piece in flight -- 1 driver call instead of the 13 of the recursive scan.
 #define SCAN_SINGLE_MAX (64 * 1024)
-#define SCAN_SINGLE_ITEMS 16
 template <typename TIn>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(const TIn* __restrict__ in, int64_t* __restrict__ out,
                                                                    int64_t n, int64_t* __restrict__ total) {
@@ -321,15 +320,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(const TIn* __
     __shared__ long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_carry = 0;
+    long long v[SCAN_ITEMS], nv[SCAN_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        const int64_t k = (int64_t)tid * SCAN_ITEMS + i;
+        v[i] = k < n ? (long long)in[k] : 0;
+    }
     __syncthreads();
-    for (int64_t base0 = 0; base0 < n; base0 += SCAN_THREADS * SCAN_SINGLE_ITEMS) {
-        const int64_t base = base0 + (int64_t)tid * SCAN_SINGLE_ITEMS;
-        long long v[SCAN_SINGLE_ITEMS];
+    for (int64_t base0 = 0; base0 < n; base0 += SCAN_BLOCK) {
+        const int64_t base = base0 + (int64_t)tid * SCAN_ITEMS;
+        // the next piece is requested before this one is scanned (out may alias in: it has not been written yet)
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            const int64_t k = base + SCAN_BLOCK + i;
+            nv[i] = k < n ? (long long)in[k] : 0;
+        }
         long long s = 0;
 #pragma unroll
-        for (int i = 0; i < SCAN_SINGLE_ITEMS; i++) v[i] = (base + i < n) ? (long long)in[base + i] : 0;
-#pragma unroll
-        for (int i = 0; i < SCAN_SINGLE_ITEMS; i++) s += v[i];
+        for (int i = 0; i < SCAN_ITEMS; i++) s += v[i];
         const long long incl = hs_warp_incl_scan64(s, lane);
         if (lane == 31) warp_tot[wid] = incl;
         const long long carry = s_carry;
@@ -343,9 +351,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(const TIn* __
         __syncthreads();
         long long run = carry + warp_tot[wid] + incl - s;
 #pragma unroll
-        for (int i = 0; i < SCAN_SINGLE_ITEMS; i++) {
+        for (int i = 0; i < SCAN_ITEMS; i++) {
             if (base + i < n) out[base + i] = run;
             run += v[i];
+            v[i] = nv[i];
         }
         __syncthreads();  // warp_tot and s_carry are rewritten by the next piece
     }

@@ -117,7 +117,8 @@ struct PileupArgs {
     int64_t* row_base;
     uint8_t* codes;
     unsigned long long* stats;
-    unsigned int* next_read;  // work counter of the persistent warps
+    unsigned int* next_read;  // work counters of the persistent warps, one per length class
+    int ops_long, ops_mid;    // CIGAR ops from which a read counts as long / medium
 };
 
 // ---- K3: the CIGAR walk. Persistent warps, one read at a time, one LANE per run of 30 positions. ----
@@ -287,11 +288,18 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 4) pileup_kernel(PileupArgs a) 
     unsigned int* __restrict__ sI = s_bits[wid][0];
     unsigned int* __restrict__ sD = s_bits[wid][1];
     uint8_t* __restrict__ buf = s_buf[wid];
+    // Longest reads first (three sweeps over the read list, each with its own counter): a warp walks its read
+    // alone, so a 60 kb read picked up late would run on long after every other warp has left.
+    for (int sweep = 0; sweep < 3; sweep++)
     for (;;) {
         unsigned int grab = 0;
-        if (lane == 0) grab = atomicAdd(a.next_read, 1u);
+        if (lane == 0) grab = atomicAdd(a.next_read + sweep, 1u);
         const int64_t r = __shfl_sync(0xffffffffu, grab, 0);
         if (r >= a.n_reads) break;  // whole warps leave together; only __syncwarp is used
+        {
+            const int n_ops = (int)(a.cigar_off[r + 1] - a.cigar_off[r]);
+            if ((n_ops >= a.ops_long ? 0 : (n_ops >= a.ops_mid ? 1 : 2)) != sweep) continue;
+        }
         const int start = a.read_start[r];
         const int64_t row_base = a.row_off[r] - (int64_t)(start & ~(HS_ALIGN - 1));
         if (lane == 0) a.row_base[r] = row_base;
@@ -770,7 +778,7 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
         A(d_contig_read_off, nc + 1); A(d_col_base, 4 * (nc + 1)); A(d_tile_contig, tiles);
         A(d_read_contig, nr); A(d_read_bases, read_words); A(d_read_word_off, nr + 1); A(d_read_len, nr);
         A(d_cigar, p->n_cigar); A(d_cigar_off, nr + 1); A(d_read_start, nr); A(d_read_strand, nr);
-        A(d_read_end, nr); A(d_read_tlead, nr); A(d_read_flags, nr); A(d_next_read, 1); A(d_row_alloc, nr + 1); A(d_row_base, nr); A(d_stats, 3 * nc);
+        A(d_read_end, nr); A(d_read_tlead, nr); A(d_read_flags, nr); A(d_next_read, 4); A(d_row_alloc, nr + 1); A(d_row_base, nr); A(d_stats, 3 * nc);
         A(d_tile_off, tiles + 1); A(d_super_off, supers + 1);
 #undef A
         HS_CUDA(ctx, cv.alloc(ctx, &p->d_create_block));
@@ -849,7 +857,7 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     int64_t* d_totals = nullptr;
     HS_CUDA(ctx, hs_alloc(ctx, &d_totals, 5));
     HS_CUDA(ctx, cudaMemsetAsync(d_totals, 0, 5 * sizeof(int64_t), ctx->stream));
-    HS_CUDA(ctx, cudaMemsetAsync(p->d_next_read, 0, sizeof(unsigned int), ctx->stream));
+    HS_CUDA(ctx, cudaMemsetAsync(p->d_next_read, 0, 4 * sizeof(unsigned int), ctx->stream));
     if (nr > 0) {
         HS_KERNEL(ctx, "span_kernel", span_kernel<<<rblocks, 256, 0, ctx->stream>>>(
             nr, p->d_cigar, p->d_cigar_off, p->d_read_start, p->d_read_contig, p->d_contig_len, p->d_read_end,
@@ -921,6 +929,11 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
         a.codes = p->d_codes;
         a.stats = p->d_stats;
         a.next_read = p->d_next_read;
+        {
+            const int64_t mean_ops = p->n_cigar / std::max<int64_t>(nr, 1);
+            a.ops_long = (int)std::min<int64_t>(2 * mean_ops + 1, 0x7fffffff);
+            a.ops_mid = (int)std::min<int64_t>(mean_ops + 1, 0x7fffffff);
+        }
         // persistent warps pull reads from a counter: read lengths vary by an order of magnitude
         static int ctas_per_sm = 0;
         if (!ctas_per_sm) {
