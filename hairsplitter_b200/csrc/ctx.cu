@@ -2,6 +2,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "rank.cuh"
 
@@ -108,12 +110,9 @@ int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     {
-        static HsRankLut lut;  // identical for every context
-        static bool have = false;
-        if (!have) {
-            hs_build_rank_lut(lut);
-            have = true;
-        }
+        static HsRankLut lut;  // identical for every context; contexts may be created from several threads at once
+        static std::once_flag lut_once;
+        std::call_once(lut_once, []() { hs_build_rank_lut(lut); });
         e = cudaMalloc(&ctx->d_rank_lut, sizeof(HsRankLut));
         if (e == cudaSuccess) e = cudaMemcpy(ctx->d_rank_lut, &lut, sizeof(HsRankLut), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {

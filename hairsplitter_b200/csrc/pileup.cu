@@ -720,17 +720,29 @@ void hsgpu_pileup_destroy(hsgpu_pileup* p) {
     delete p;
 }
 
+static int pileup_create_impl(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pileup* p);
+
 int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pileup** out) {
     if (!ctx || !in || !out) return HSGPU_ERR_ARG;
     *out = nullptr;
     if (in->n_contigs <= 0 || in->n_reads < 0) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pileup_create: empty batch");
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int32_t nc = in->n_contigs;
-    const int64_t nr = in->n_reads;
-    if (in->contig_read_off[0] != 0 || in->contig_read_off[nc] != nr)
+    if (in->contig_read_off[0] != 0 || in->contig_read_off[in->n_contigs] != in->n_reads)
         HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pileup_create: contig_read_off must span [0, n_reads]");
     hsgpu_pileup* p = new hsgpu_pileup();
     p->ctx = ctx;
+    const int rc = pileup_create_impl(ctx, in, p);
+    if (rc != HSGPU_OK) {  // whatever was allocated so far goes back to the pool
+        hsgpu_pileup_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return HSGPU_OK;
+}
+
+static int pileup_create_impl(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pileup* p) {
+    const int32_t nc = in->n_contigs;
+    const int64_t nr = in->n_reads;
     p->n_contigs = nc;
     p->n_reads = nr;
     p->h_contig_len.assign(in->contig_len, in->contig_len + nc);
@@ -742,10 +754,8 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
     int64_t cols = 0, tiles = 0, sus = 0, supers = 0;
     std::vector<int64_t> super_base((size_t)nc + 1);
     for (int c = 0; c < nc; c++) {
-        if (in->contig_len[c] < 0 || in->contig_read_off[c + 1] < in->contig_read_off[c]) {
-            delete p;
+        if (in->contig_len[c] < 0 || in->contig_read_off[c + 1] < in->contig_read_off[c])
             HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pileup_create: negative contig length or read range");
-        }
         p->h_col_base[c] = cols;
         p->h_tile_base[c] = tiles;
         p->h_suspect_base[c] = sus;
@@ -764,10 +774,8 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
     p->n_tiles = tiles;
     p->n_cigar = in->cigar_off[nr];
     for (int64_t r = 0; r < nr; r++) {
-        if (in->read_start[r] < 0 || in->read_len[r] < 0) {
-            delete p;
+        if (in->read_start[r] < 0 || in->read_len[r] < 0)
             HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pileup_create: negative read start or length");
-        }
     }
     const int64_t contig_words = in->contig_word_off[nc];
     const int64_t read_words = in->read_word_off[nr];
@@ -837,7 +845,6 @@ int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pile
     // measured slower and unstable (2.5-4.6 ms per e2e step against a steady 2.45 ms): the next context's upload
     // then competes with this context's first kernels and its allocation-size round trip.
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *out = p;
     return HSGPU_OK;
 }
 

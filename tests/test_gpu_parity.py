@@ -286,3 +286,21 @@ def test_suspects_all_equals_the_per_contig_calls(gpu_ctx):
     rc = pu.lib.hsgpu_suspects_all(pu.h, 0, None, None, off2.ctypes.data, None)
     assert rc == 0 and np.array_equal(off2, off)
     pu.close()
+
+
+def test_invalid_batch_is_refused_and_leaves_the_context_usable(gpu_ctx, oracle):
+    """hsgpu_pileup_create validates the batch (error code + message, nothing leaked) and the context keeps working"""
+    cb = cases.small_case(seed=97, length=2000, depth=10, mean_len=600)
+    pk = api.PackedBatch([cb])
+    bad = pk.read_start.copy()
+    bad[0] = -5
+    good, pk.read_start = pk.read_start, bad
+    with pytest.raises(api.HsgpuError) as e:
+        api.Pileup(gpu_ctx, pk)
+    assert "negative read start" in str(e.value)
+    pk.read_start = good
+    pu = api.Pileup(gpu_ctx, pk)
+    pu.build()
+    pu.column_rank()
+    _check_contig(oracle, pu, 0, cb)
+    pu.close()
