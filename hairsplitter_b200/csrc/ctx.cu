@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include <chrono>
 #include <mutex>
 
 #include "common.cuh"
@@ -72,11 +73,22 @@ const char* hsgpu_profile_report(hsgpu_ctx* ctx) {
     return ctx->prof_report.c_str();
 }
 
+// HSGPU_TIMING=1: where the time of hsgpu_ctx_create goes (almost all of it is the driver's)
+static void ctx_lap(const char* what, std::chrono::steady_clock::time_point& t0) {
+    static const bool on = getenv("HSGPU_TIMING") != nullptr;
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[hsgpu timing] ctx_create: %-34s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+}
+
 int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
     if (!out) return HSGPU_ERR_ARG;
     *out = nullptr;
+    auto lap = std::chrono::steady_clock::now();
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
+    ctx_lap("cudaGetDeviceCount (cuInit)", lap);
     if (e != cudaSuccess || n == 0) {
         hs_set_error(nullptr, "libhsgpu: no CUDA device available (this library has no CPU fallback)");
         return HSGPU_ERR_NO_DEVICE;
@@ -87,6 +99,7 @@ int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
     }
     cudaDeviceProp prop;
     HS_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    ctx_lap("cudaGetDeviceProperties", lap);
     if (prop.major != 10) {
         char buf[256];
         snprintf(buf, sizeof(buf), "libhsgpu: device %d (%.64s) is sm_%d%d; kernels are built for sm_100a only", device,
@@ -99,6 +112,7 @@ int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    ctx_lap("cudaSetDevice + stream (primary context)", lap);
     if (e != cudaSuccess) {
         delete ctx;
         return hs_cuda_fail(nullptr, e, "cudaStreamCreate", __FILE__, __LINE__);
@@ -113,6 +127,7 @@ int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
         static HsRankLut lut;  // identical for every context; contexts may be created from several threads at once
         static std::once_flag lut_once;
         std::call_once(lut_once, []() { hs_build_rank_lut(lut); });
+        ctx_lap("memory pool + rank table (host)", lap);
         e = cudaMalloc(&ctx->d_rank_lut, sizeof(HsRankLut));
         if (e == cudaSuccess) e = cudaMemcpy(ctx->d_rank_lut, &lut, sizeof(HsRankLut), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
@@ -121,12 +136,14 @@ int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
             return hs_cuda_fail(nullptr, e, "rank table upload", __FILE__, __LINE__);
         }
     }
+    ctx_lap("cudaMalloc + cudaMemcpy (rank table)", lap);
     e = cudaHostAlloc((void**)&ctx->h_scratch, 64, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->scratch_event, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         hsgpu_ctx_destroy(ctx);
         return hs_cuda_fail(nullptr, e, "pinned scratch", __FILE__, __LINE__);
     }
+    ctx_lap("cudaHostAlloc + event", lap);
     *out = ctx;
     return HSGPU_OK;
 }
