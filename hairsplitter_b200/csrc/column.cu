@@ -255,8 +255,12 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
             itotal += t;
         }
         if (tid == 0 && total > 0) {
-            s_base[0] = atomicAdd(a.counters + 0, (unsigned)total);
-            s_base[1] = atomicAdd(a.counters + 1, (unsigned)itotal);
+            // counters[0] (words) and counters[1] (items) are one aligned 64-bit word: a single atomic reserves both
+            // (every tile of the batch comes through here; the words stay far below 2^32, see arena_words)
+            const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(a.counters),
+                                                     (unsigned long long)(unsigned)total | ((unsigned long long)(unsigned)itotal << 32));
+            s_base[0] = (unsigned)old;
+            s_base[1] = (unsigned)(old >> 32);
         }
         __syncthreads();
         if (defer == 1) {

@@ -326,55 +326,42 @@ __global__ void scan_total_kernel(const int64_t* block_off, const int64_t* block
     *total = block_off[nb - 1] + block_sums[nb - 1];
 }
 
-// Short inputs (every per-read / per-tile table of a batch of contig chunks): ONE launch of one CTA that walks
-// the array in pieces of 4096 with a running carry, the next piece in flight -- 1 driver call instead of the 13 of the recursive scan.
+// Short inputs (every per-read / per-tile table of a batch of contig chunks): ONE launch of one CTA -- 1 driver call
+// instead of the 13 of the recursive scan. Each of the 32 warps owns a contiguous segment: it sums it (loads fully
+// pipelined, no barrier), the 32 totals are scanned once, then the warp walks its segment again 32 elements at a
+// time (warp scan + running carry, next row already requested). Two barriers in all; out may alias in.
 #define SCAN_SINGLE_MAX (64 * 1024)
 template <typename TIn>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(const TIn* __restrict__ in, int64_t* __restrict__ out,
-                                                                   int64_t n, int64_t* __restrict__ total) {
-    __shared__ long long warp_tot[32];
-    __shared__ long long s_carry;
+__global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(const TIn* in, int64_t* out, int64_t n,
+                                                                   int64_t* __restrict__ total) {
+    __shared__ long long s_tot[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    long long v[SCAN_ITEMS], nv[SCAN_ITEMS];
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        const int64_t k = (int64_t)tid * SCAN_ITEMS + i;
-        v[i] = k < n ? (long long)in[k] : 0;
+    const int64_t per = (((n + 31) / 32) + 31) & ~(int64_t)31;  // elements per warp, a multiple of 32
+    const int64_t b = (int64_t)wid * per;
+    const int64_t e = b + per < n ? b + per : n;
+    long long acc = 0;
+#pragma unroll 8
+    for (int64_t k = b + lane; k < e; k += 32) acc += (long long)in[k];
+    acc = hs_warp_sum64(acc);
+    if (lane == 0) s_tot[wid] = acc;
+    __syncthreads();
+    if (wid == 0) {
+        const long long w = s_tot[lane];
+        const long long wi = hs_warp_incl_scan64(w, lane);
+        s_tot[lane] = wi - w;
+        if (lane == 31 && total) *total = wi;
     }
     __syncthreads();
-    for (int64_t base0 = 0; base0 < n; base0 += SCAN_BLOCK) {
-        const int64_t base = base0 + (int64_t)tid * SCAN_ITEMS;
-        // the next piece is requested before this one is scanned (out may alias in: it has not been written yet)
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            const int64_t k = base + SCAN_BLOCK + i;
-            nv[i] = k < n ? (long long)in[k] : 0;
-        }
-        long long s = 0;
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) s += v[i];
-        const long long incl = hs_warp_incl_scan64(s, lane);
-        if (lane == 31) warp_tot[wid] = incl;
-        const long long carry = s_carry;
-        __syncthreads();
-        if (wid == 0) {
-            const long long w = warp_tot[lane];
-            const long long wi = hs_warp_incl_scan64(w, lane);
-            warp_tot[lane] = wi - w;
-            if (lane == 31) s_carry = carry + wi;
-        }
-        __syncthreads();
-        long long run = carry + warp_tot[wid] + incl - s;
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            if (base + i < n) out[base + i] = run;
-            run += v[i];
-            v[i] = nv[i];
-        }
-        __syncthreads();  // warp_tot and s_carry are rewritten by the next piece
+    long long carry = s_tot[wid];
+    long long v = (b + lane < e) ? (long long)in[b + lane] : 0;
+    for (int64_t k0 = b; k0 < e; k0 += 32) {
+        const int64_t k = k0 + lane;
+        const long long nv = (k + 32 < e) ? (long long)in[k + 32] : 0;  // the next row, before this one is overwritten
+        const long long incl = hs_warp_incl_scan64(v, lane);
+        if (k < e) out[k] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        v = nv;
     }
-    if (tid == 0 && total) *total = s_carry;
 }
 
 template <typename TIn>

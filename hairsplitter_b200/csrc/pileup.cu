@@ -40,22 +40,37 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
                                                    int32_t* __restrict__ read_end, int64_t* __restrict__ row_alloc,
                                                    int32_t* __restrict__ read_tlead, uint8_t* __restrict__ read_flags,
                                                    unsigned long long* __restrict__ totals) {
+    // the three totals are summed per CTA first: one global atomic per counter and CTA instead of one per read
+    // (30 000 atomics on the same address were what bounded this kernel)
+    __shared__ unsigned long long s_tot[3];
+    if (threadIdx.x < 3) s_tot[threadIdx.x] = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (r >= n_reads) return;
-    const int64_t k0 = cigar_off[r], k1 = cigar_off[r + 1];
+    const bool valid = r < n_reads;
+    const int64_t k0 = valid ? cigar_off[r] : 0, k1 = valid ? cigar_off[r + 1] : 0;
     long long sum = 0;
     long long first = k1, last = -1;  // first / last op that is an alignment position (M,=,X,I,D)
     int clips = 0;
-#pragma unroll 8
-    for (int64_t k = k0 + lane; k < k1; k += 32) {
-        const uint32_t op = __ldg(cigar + k);
-        const int ty = (int)(op & 15);
-        if (op_consumes_q(ty)) sum += op >> 4;
-        if ((ty == OP_S || ty == OP_H) && (op >> 4) > 0) clips = 1;
-        if ((op_consumes_q(ty) || ty == OP_I) && (op >> 4) > 0) {
-            if (k < first) first = k;
-            last = k;
+    // eight independent loads per lane in flight (the loop is otherwise bound by the latency of one load per trip)
+    for (int64_t kb = k0; kb < k1; kb += 8 * 32) {
+        uint32_t ops[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int64_t k = kb + 32 * j + lane;
+            ops[j] = k < k1 ? __ldg(cigar + k) : (uint32_t)OP_P;  // a zero-length pad op takes part in nothing
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int64_t k = kb + 32 * j + lane;
+            const uint32_t op = ops[j];
+            const int ty = (int)(op & 15);
+            if (op_consumes_q(ty)) sum += op >> 4;
+            if ((ty == OP_S || ty == OP_H) && (op >> 4) > 0) clips = 1;
+            if ((op_consumes_q(ty) || ty == OP_I) && (op >> 4) > 0) {
+                if (k < first) first = k;
+                last = k;
+            }
         }
     }
     sum = hs_warp_sum64(sum);
@@ -78,7 +93,7 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
     }
     tlead = hs_warp_sum64(tlead);
     irregular = __any_sync(0xffffffffu, irregular) || tlead > 0x3fffffff;
-    if (lane == 0) {
+    if (valid && lane == 0) {
         const int L = contig_len[read_contig[r]];
         const int start = read_start[r];
         long long end = start;
@@ -89,12 +104,15 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
         row_alloc[r] = alloc;
         read_tlead[r] = (int32_t)tlead;
         read_flags[r] = irregular ? HS_READ_IRREGULAR : 0;
-        if (irregular) atomicAdd(totals + 2, 1ull);
+        if (irregular) atomicAdd(&s_tot[2], 1ull);
         if (end > start) {  // exact sizes of the two index levels (tile_index_kernel), known before they are built
-            atomicAdd(totals + 1, (unsigned long long)((end - 1) / HS_TILE - start / HS_TILE + 1));
-            atomicAdd(totals + 4, (unsigned long long)((end - 1) / HS_SUPER_COLS - start / HS_SUPER_COLS + 1));
+            atomicAdd(&s_tot[0], (unsigned long long)((end - 1) / HS_TILE - start / HS_TILE + 1));
+            atomicAdd(&s_tot[1], (unsigned long long)((end - 1) / HS_SUPER_COLS - start / HS_SUPER_COLS + 1));
         }
     }
+    __syncthreads();
+    if (threadIdx.x < 3 && s_tot[threadIdx.x])
+        atomicAdd(totals + (threadIdx.x == 0 ? 1 : (threadIdx.x == 1 ? 4 : 2)), s_tot[threadIdx.x]);
 }
 
 struct PileupArgs {
@@ -612,14 +630,20 @@ __global__ void __launch_bounds__(256) tile_index_kernel(int64_t n_tiles, const 
                                                          int64_t* __restrict__ tile_cnt_or_off,
                                                          int32_t* __restrict__ tile_reads,
                                                          unsigned long long* __restrict__ max_count) {
+    __shared__ unsigned long long s_max;  // deepest tile of the CTA: one global atomicMax per CTA
+    if (!FILL) {
+        if (threadIdx.x == 0) s_max = 0;
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (tile >= n_tiles) return;
-    const int c = tile_contig[tile];
-    const int64_t lt = tile - tile_base[c];
+    const bool valid = tile < n_tiles;
+    if (FILL && !valid) return;
+    const int c = valid ? tile_contig[tile] : 0;
+    const int64_t lt = valid ? tile - tile_base[c] : 0;
     const int q0 = (int)lt * HS_TILE, q1 = q0 + HS_TILE;
     const int64_t su = super_base[c] + lt / HS_SUPER_TILES;
-    const int64_t l0 = super_off[su], l1 = super_off[su + 1];
+    const int64_t l0 = valid ? super_off[su] : 0, l1 = valid ? super_off[su + 1] : 0;
     int64_t out = FILL ? tile_cnt_or_off[tile] : 0;
     for (int64_t lb = l0; lb < l1; lb += 32) {
         const int64_t l = lb + lane;
@@ -634,9 +658,13 @@ __global__ void __launch_bounds__(256) tile_index_kernel(int64_t n_tiles, const 
         if (FILL && hit) tile_reads[out + __popc(m & ((1u << lane) - 1u))] = r;
         out += __popc(m);
     }
-    if (!FILL && lane == 0) {
-        tile_cnt_or_off[tile] = out;
-        if (max_count && out > 0) atomicMax(max_count, (unsigned long long)out);
+    if (!FILL) {
+        if (valid && lane == 0) {
+            tile_cnt_or_off[tile] = out;
+            if (out > 0) atomicMax(&s_max, (unsigned long long)out);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && max_count && s_max > 0) atomicMax(max_count, s_max);
     }
 }
 
