@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
             s_lut_words[i] = __ldg(reinterpret_cast<const uint32_t*>(a.lut) + i);
     }
     __syncthreads();
-    s_hist[tid] = 1;  // bin 0 ("no cell") never looks like a first sighting
+    s_hist[col] = 1;  // bin 0 ("no cell") never looks like a first sighting; set by the column's own thread (a tile
+                      // without reads has no barrier between here and the read of this bin below)
     int m = 0, rows_done = 0;
     H* const hcol = s_hist + col;
     const int crow = tid >> 3, cpart = tid & 7;  // this thread's copy slot in a batch: row, 16-byte part
