@@ -423,6 +423,8 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     HS_CUDA(ctx, hs_alloc(ctx, &d_to, n_pairs + 1));
     HS_CUDA(ctx, hs_alloc(ctx, &d_bmo, n_pairs + 1));
     HS_CUDA(ctx, hs_alloc(ctx, &d_res, n_pairs));
+    // phase A fills some of the fields; the whole struct travels to the host after it
+    HS_CUDA(ctx, cudaMemsetAsync(d_res, 0, sizeof(hsgpu_edlib_result) * (size_t)std::max(n_pairs, 1), ctx->stream));
     HS_CUDA(ctx, hs_alloc(ctx, &d_bm, bmw));
     HS_CUDA(ctx, hs_alloc(ctx, &d_counter, 2));
     HS_CUDA(ctx, hs_alloc(ctx, &d_peq, (int64_t)n_warps * 256 * 32));
@@ -470,6 +472,9 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     if (rc == HSGPU_OK) {
         HS_CUDA(ctx, hs_alloc(ctx, &d_ends, nloc));
         HS_CUDA(ctx, hs_alloc(ctx, &d_starts, nloc));
+        // pairs for which edlib reports no start locations (empty sequences) leave their slots untouched: -1
+        HS_CUDA(ctx, cudaMemsetAsync(d_ends, 0xff, sizeof(int32_t) * (size_t)std::max<int64_t>(nloc, 1), ctx->stream));
+        HS_CUDA(ctx, cudaMemsetAsync(d_starts, 0xff, sizeof(int32_t) * (size_t)std::max<int64_t>(nloc, 1), ctx->stream));
         HS_CUDA(ctx, hs_h2d(ctx, d_res, results, n_pairs));
         if (task == 2) {
             HS_CUDA(ctx, hs_alloc(ctx, &d_aln_tmp, tmpb));
