@@ -101,7 +101,10 @@ typedef struct {
     const uint8_t* cigar8;
 } hsgpu_pileup_input;
 
-/* copies the batch to the device (asynchronous on the context's stream) */
+/* copies the batch to the device and returns when the upload has landed (the caller's buffers are free again).
+ * Uploads take turns per device: while one context uploads, the kernels of the other contexts keep running, which
+ * is what overlaps transfer and compute when every host thread drives its own context. Pinned host buffers
+ * (hsgpu_host_alloc) reach the full link rate. On failure nothing is left allocated. */
 int hsgpu_pileup_create(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgpu_pileup** out);
 void hsgpu_pileup_destroy(hsgpu_pileup* p);
 
