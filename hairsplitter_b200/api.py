@@ -40,6 +40,19 @@ class PileupInput(C.Structure):
     ]
 
 
+class EdlibAlignConfig(C.Structure):
+    """layout of EdlibAlignConfig (reference src/edlib/include/edlib.h:100-106)"""
+    _fields_ = [("k", C.c_int), ("mode", C.c_int), ("task", C.c_int), ("additionalEqualities", C.c_void_p),
+                ("additionalEqualitiesLength", C.c_int)]
+
+
+class EdlibAlignResult(C.Structure):
+    """layout of EdlibAlignResult (reference src/edlib/include/edlib.h:213-262)"""
+    _fields_ = [("status", C.c_int), ("editDistance", C.c_int), ("endLocations", C.POINTER(C.c_int)),
+                ("startLocations", C.POINTER(C.c_int)), ("numLocations", C.c_int),
+                ("alignment", C.POINTER(C.c_ubyte)), ("alignmentLength", C.c_int), ("alphabetLength", C.c_int)]
+
+
 class Partitions(C.Structure):
     _fields_ = [
         ("n_parts", C.c_int32),
@@ -70,7 +83,7 @@ EXPORTS = [
     "hsgpu_column_counts", "hsgpu_suspects", "hsgpu_suspects_all", "hsgpu_column_summary", "hsgpu_partition_tables", "hsgpu_robust_filter",
     "hsgpu_read_pair_counts", "hsgpu_pairs_create", "hsgpu_pairs_compute", "hsgpu_pairs_fetch", "hsgpu_pairs_info",
     "hsgpu_pairs_destroy", "hsgpu_graph_create", "hsgpu_graph_build", "hsgpu_graph_adjacency", "hsgpu_graph_whispers",
-    "hsgpu_graph_destroy", "hsgpu_edlib_align_batch",
+    "hsgpu_graph_destroy", "hsgpu_edlib_align_batch", "hsgpu_edlibAlign", "hsgpu_edlibFreeAlignResult",
 ]
 PAIRS_DENSE, PAIRS_KEEP_ORDER, PAIRS_SIMT = 1, 2, 4
 
@@ -139,6 +152,10 @@ def load():
     L.hsgpu_graph_whispers.argtypes = [vp, i64, vp, vp, i32, vp, vp]
     L.hsgpu_graph_destroy.argtypes = [vp]
     L.hsgpu_graph_destroy.restype = None
+    L.hsgpu_edlibAlign.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, C.c_int, EdlibAlignConfig]
+    L.hsgpu_edlibAlign.restype = EdlibAlignResult
+    L.hsgpu_edlibFreeAlignResult.argtypes = [EdlibAlignResult]
+    L.hsgpu_edlibFreeAlignResult.restype = None
     L.hsgpu_edlib_align_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i64, vp, i64]
     for name in ("hsgpu_debug_rank_column", "hsgpu_debug_rh_order", "hsgpu_debug_sort_desc"):
         getattr(L, name).restype = C.c_int if name == "hsgpu_debug_rh_order" else None
@@ -394,6 +411,19 @@ class Context:
                                                     starts.ctypes.data, loc_cap, aln.ctypes.data, aln_cap),
                    "hsgpu_edlib_align_batch")
         return res, ends, starts, aln
+
+
+    def edlib_align(self, query: bytes, target: bytes, k=-1, mode=2, task=2):
+        """hsgpu_edlibAlign: one pair, edlib's own result struct; returned as the dict the oracle uses"""
+        cfg = EdlibAlignConfig(k, mode, task, None, 0)
+        r = self.lib.hsgpu_edlibAlign(self.h, query, len(query), target, len(target), cfg)
+        n = r.numLocations
+        out = dict(status=r.status, edit_distance=r.editDistance, alphabet_length=r.alphabetLength,
+                   end_locations=(np.array(r.endLocations[:n], np.int32) if r.endLocations else None),
+                   start_locations=(np.array(r.startLocations[:n], np.int32) if r.startLocations else None),
+                   alignment=(np.array(r.alignment[:r.alignmentLength], np.uint8) if r.alignment else None))
+        self.lib.hsgpu_edlibFreeAlignResult(r)
+        return out
 
 
 class Pairs:

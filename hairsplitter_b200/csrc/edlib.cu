@@ -19,6 +19,8 @@
 //   Pairs whose path falls in edlib's Hirschberg regime ((20*blocks+8)*columns >= 1 MiB, :1193-1195) get
 //   status 2 and no alignment: Hirschberg picks the split row by its own tie rule, not implemented here.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -517,4 +519,57 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     hs_free(ctx, d_starts); hs_free(ctx, d_aln_tmp); hs_free(ctx, d_tmpo); hs_free(ctx, d_trace); hs_free(ctx, d_aln);
     hs_free(ctx, d_scan);
     return rc;
+}
+
+extern "C" hsgpu_EdlibAlignResult hsgpu_edlibAlign(hsgpu_ctx* ctx, const char* query, int queryLength, const char* target,
+                                                   int targetLength, hsgpu_EdlibAlignConfig config) {
+    hsgpu_EdlibAlignResult out;
+    out.status = 1;  // EDLIB_STATUS_ERROR
+    out.editDistance = -1;
+    out.endLocations = out.startLocations = nullptr;
+    out.numLocations = 0;
+    out.alignment = nullptr;
+    out.alignmentLength = 0;
+    out.alphabetLength = 0;
+    if (!ctx || queryLength < 0 || targetLength < 0 || (!query && queryLength > 0) || (!target && targetLength > 0)) return out;
+    if (config.additionalEqualitiesLength > 0) {
+        hs_set_error(ctx, "hsgpu_edlibAlign: additional equalities are not supported");
+        return out;
+    }
+    const int64_t qo[2] = {0, queryLength}, to[2] = {0, targetLength};
+    const int64_t loc_cap = (int64_t)targetLength + 2, aln_cap = (int64_t)queryLength + targetLength + 8;
+    int32_t* ends = static_cast<int32_t*>(malloc(sizeof(int32_t) * (size_t)loc_cap));
+    int32_t* starts = static_cast<int32_t*>(malloc(sizeof(int32_t) * (size_t)loc_cap));
+    uint8_t* aln = static_cast<uint8_t*>(malloc((size_t)aln_cap));
+    hsgpu_edlib_result r;
+    memset(&r, 0, sizeof(r));
+    const int rc = (ends && starts && aln)
+                       ? hsgpu_edlib_align_batch(ctx, 1, query ? query : "", qo, target ? target : "", to, config.k, config.mode,
+                                                 config.task, &r, ends, starts, loc_cap, aln, aln_cap)
+                       : HSGPU_ERR_CUDA;
+    if (rc != HSGPU_OK) {
+        free(ends);
+        free(starts);
+        free(aln);
+        return out;
+    }
+    out.status = r.status;
+    out.editDistance = r.edit_distance;
+    out.numLocations = r.n_locations;
+    out.alphabetLength = r.alphabet_length;
+    if (r.n_locations > 0) out.endLocations = ends; else free(ends);
+    if (r.n_locations > 0 && r.has_start_locations) out.startLocations = starts; else free(starts);
+    if (r.alignment_length > 0) {
+        out.alignment = aln;
+        out.alignmentLength = r.alignment_length;
+    } else {
+        free(aln);
+    }
+    return out;
+}
+
+extern "C" void hsgpu_edlibFreeAlignResult(hsgpu_EdlibAlignResult result) {
+    free(result.endLocations);
+    free(result.startLocations);
+    free(result.alignment);
 }

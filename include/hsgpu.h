@@ -261,6 +261,37 @@ int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const char* queries
                             hsgpu_edlib_result* results, int32_t* end_locations, int32_t* start_locations,
                             int64_t loc_capacity, uint8_t* alignment, int64_t aln_capacity);
 
+/* Single-pair form with edlib's own calling convention, so that the four call sites of the reference
+ * (src/create_new_contigs.cpp:557-630, src/tools.cpp:508-536) change by one line:
+ *     EdlibAlignResult r = edlibAlign(q, ql, t, tl, cfg);   ->   hsgpu_edlibAlign(ctx, q, ql, t, tl, cfg);
+ * The two structs are layout-compatible with EdlibAlignConfig / EdlibAlignResult (src/edlib/include/edlib.h:
+ * 100-106, 213-262): a maintainer may pass edlib's own objects through a cast; edlibAlignmentToCigar works on the
+ * result unchanged. endLocations / startLocations / alignment are malloc'd by the library and released by
+ * hsgpu_edlibFreeAlignResult (or free()), NULL where edlib leaves them NULL (distance above k, DISTANCE task,
+ * empty sequence). status: 0 = EDLIB_STATUS_OK, 1 = EDLIB_STATUS_ERROR (also: additional equalities are not
+ * supported), 2 = distance and locations are exact but the path lies in edlib's Hirschberg regime and was not
+ * produced. One pair per call costs a kernel launch and a round trip: batch the pairs where the caller can. */
+typedef struct {
+    int k;
+    int mode; /* EdlibAlignMode: 0 NW, 1 SHW, 2 HW */
+    int task; /* EdlibAlignTask: 0 DISTANCE, 1 LOC, 2 PATH */
+    const void* additionalEqualities;
+    int additionalEqualitiesLength;
+} hsgpu_EdlibAlignConfig;
+typedef struct {
+    int status;
+    int editDistance;
+    int* endLocations;
+    int* startLocations;
+    int numLocations;
+    unsigned char* alignment;
+    int alignmentLength;
+    int alphabetLength;
+} hsgpu_EdlibAlignResult;
+hsgpu_EdlibAlignResult hsgpu_edlibAlign(hsgpu_ctx* ctx, const char* query, int queryLength, const char* target,
+                                        int targetLength, hsgpu_EdlibAlignConfig config);
+void hsgpu_edlibFreeAlignResult(hsgpu_EdlibAlignResult result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,3 +124,42 @@ def test_query_longer_than_limit_fails_loudly(gpu_ctx):
     from hairsplitter_b200 import api
     with pytest.raises(api.HsgpuError):
         gpu_ctx.edlib_align_batch([b"A" * 2049], [b"ACGT" * 10], k=-1, mode=0, task=0)
+
+
+def test_single_pair_shim_has_edlibs_result_semantics(gpu_ctx, oracle):
+    """hsgpu_edlibAlign: edlib's calling convention for one pair (the one-line change at the reference's call sites):
+    same fields, NULL pointers where edlib leaves them NULL, arrays released by hsgpu_edlibFreeAlignResult"""
+    from hairsplitter_b200 import api
+    from oracle import pyoracle
+    rng = np.random.default_rng(77)
+    ref = pyoracle.RefEdlib if pyoracle.RefEdlib.available() else None
+    cases_ = []
+    for it in range(24):
+        t = _rnd(rng, int(rng.choice([0, 1, 40, 300, 2300])))
+        qlen = int(rng.choice([0, 1, 20, 64, 150, 300]))
+        if len(t) > qlen > 0 and rng.random() < 0.7:
+            s0 = int(rng.integers(0, len(t) - qlen + 1))
+            q = _mutate(rng, t[s0:s0 + qlen], 0.1)
+        else:
+            q = _rnd(rng, qlen)
+        cases_.append((q, t))
+    for q, t in cases_:
+        for k, mode, task in ((-1, 2, 2), (3, 2, 2), (-1, 0, 1), (-1, 1, 0)):
+            got = gpu_ctx.edlib_align(q, t, k=k, mode=mode, task=task)
+            want = ref.align(q, t, k, mode, task) if ref is not None else oracle.edlib_align(q, t, k, mode, task)
+            ctx = (len(q), len(t), k, mode, task)
+            assert got["status"] == 0 and got["edit_distance"] == want["edit_distance"], ctx
+            assert got["alphabet_length"] == want["alphabet_length"], ctx
+            for key in ("end_locations", "start_locations"):
+                if want[key] is None or len(want[key]) == 0:
+                    assert got[key] is None, (key, ctx)
+                else:
+                    assert np.array_equal(got[key], want[key]), (key, ctx)
+            if task == 2 and want["edit_distance"] >= 0 and want.get("alignment") is not None and len(want["alignment"]):
+                assert np.array_equal(got["alignment"], want["alignment"]), ctx
+            elif task != 2 or want["edit_distance"] < 0:
+                assert got["alignment"] is None, ctx
+    # additional equalities are refused, not ignored
+    cfg = api.EdlibAlignConfig(-1, 2, 2, None, 1)
+    r = gpu_ctx.lib.hsgpu_edlibAlign(gpu_ctx.h, b"ACGT", 4, b"ACGT", 4, cfg)
+    assert r.status == 1 and not r.endLocations

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     lib = api.load()
     header = open(os.path.join(ROOT, "include", "hsgpu.h")).read()
-    declared = sorted(set(re.findall(r"\b(hsgpu_[a-z0-9_]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"\b(hsgpu_[A-Za-z0-9_]+)\s*\(", header)))
     assert len(declared) >= 25
     for name in declared:
         assert hasattr(lib, name), name
