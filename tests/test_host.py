@@ -157,3 +157,41 @@ def test_synthetic_generator_is_self_consistent():
             ln, op = ops >> 4, ops & 15
             assert int(ln[np.isin(op, [0, 1, 4, 5, 7, 8])].sum()) == int(rl[i])
             assert cb.start[i] + int(ln[np.isin(op, [0, 2, 7, 8])].sum()) <= cb.length
+
+
+def test_edlib_shim_structs_are_layout_compatible_with_edlib(tmp_path):
+    """hsgpu_EdlibAlignConfig / hsgpu_EdlibAlignResult claim the layout of edlib's structs (a maintainer may cast):
+    checked by the C compiler against the reference's own header, where the reference tree is present"""
+    import subprocess
+    ref_inc = "/root/reference/src/edlib/include"
+    if not os.path.exists(os.path.join(ref_inc, "edlib.h")):
+        pytest.skip("reference tree not present (GPU box)")
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include "edlib.h"
+#include "hsgpu.h"
+#define SAME(T, U, f) _Static_assert(offsetof(T, f) == offsetof(U, f) && sizeof(((T*)0)->f) == sizeof(((U*)0)->f), #f)
+_Static_assert(sizeof(EdlibAlignConfig) == sizeof(hsgpu_EdlibAlignConfig), "config size");
+_Static_assert(sizeof(EdlibAlignResult) == sizeof(hsgpu_EdlibAlignResult), "result size");
+SAME(EdlibAlignConfig, hsgpu_EdlibAlignConfig, k);
+SAME(EdlibAlignConfig, hsgpu_EdlibAlignConfig, mode);
+SAME(EdlibAlignConfig, hsgpu_EdlibAlignConfig, task);
+SAME(EdlibAlignConfig, hsgpu_EdlibAlignConfig, additionalEqualities);
+SAME(EdlibAlignConfig, hsgpu_EdlibAlignConfig, additionalEqualitiesLength);
+SAME(EdlibAlignResult, hsgpu_EdlibAlignResult, status);
+SAME(EdlibAlignResult, hsgpu_EdlibAlignResult, editDistance);
+SAME(EdlibAlignResult, hsgpu_EdlibAlignResult, endLocations);
+SAME(EdlibAlignResult, hsgpu_EdlibAlignResult, startLocations);
+SAME(EdlibAlignResult, hsgpu_EdlibAlignResult, numLocations);
+SAME(EdlibAlignResult, hsgpu_EdlibAlignResult, alignment);
+SAME(EdlibAlignResult, hsgpu_EdlibAlignResult, alignmentLength);
+SAME(EdlibAlignResult, hsgpu_EdlibAlignResult, alphabetLength);
+_Static_assert(EDLIB_MODE_NW == 0 && EDLIB_MODE_SHW == 1 && EDLIB_MODE_HW == 2, "modes");
+_Static_assert(EDLIB_TASK_DISTANCE == 0 && EDLIB_TASK_LOC == 1 && EDLIB_TASK_PATH == 2, "tasks");
+_Static_assert(EDLIB_STATUS_OK == 0 && EDLIB_STATUS_ERROR == 1, "status");
+int main(void) { return 0; }
+''')
+    r = subprocess.run(["/usr/bin/gcc", "-std=c11", "-I", ref_inc, "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                        "-o", str(tmp_path / "layout.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
