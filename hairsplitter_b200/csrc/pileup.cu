@@ -32,7 +32,6 @@ __device__ __forceinline__ bool op_consumes_t(int ty) {
 #define HS_READ_IRREGULAR 1
 #define HS_SUPER_TILES 4  // tiles per super-tile of the two-level tile index
 #define HS_SUPER_COLS (HS_SUPER_TILES * HS_TILE)
-template <bool VEC>
 __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32_t* __restrict__ cigar,
                                                    const int64_t* __restrict__ cigar_off,
                                                    const int32_t* __restrict__ read_start,
@@ -53,39 +52,6 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
     long long sum = 0;
     long long first = k1, last = -1;  // first / last op that is an alignment position (M,=,X,I,D)
     int clips = 0;
-    if (VEC) {
-    // 16-byte loads (four ops per lane and load, two loads per lane in flight): the loop is bound by load latency
-    const int64_t ka = k0 & ~(int64_t)3;  // the op array is 16-byte aligned
-    for (int64_t kb = ka; kb < k1; kb += 2 * 128) {
-        uint32_t ops[2][4];
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int64_t kv = kb + 128 * j + 4 * lane;
-            if (kv + 4 <= k1) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(cigar + kv));
-                ops[j][0] = v.x; ops[j][1] = v.y; ops[j][2] = v.z; ops[j][3] = v.w;
-            } else {  // the read's last, partial vector (nothing is read past its ops)
-#pragma unroll
-                for (int e = 0; e < 4; e++) ops[j][e] = kv + e < k1 ? __ldg(cigar + kv + e) : (uint32_t)OP_P;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int64_t k = kb + 128 * j + 4 * lane + e;
-                const uint32_t op = k >= k0 ? ops[j][e] : (uint32_t)OP_P;  // a zero-length pad op takes part in nothing
-                const int ty = (int)(op & 15);
-                if (op_consumes_q(ty)) sum += op >> 4;
-                if ((ty == OP_S || ty == OP_H) && (op >> 4) > 0) clips = 1;
-                if ((op_consumes_q(ty) || ty == OP_I) && (op >> 4) > 0) {
-                    if (k < first) first = k;
-                    last = k;
-                }
-            }
-        }
-    }
-    } else {
     // eight independent loads per lane in flight (the loop is otherwise bound by the latency of one load per trip)
     for (int64_t kb = k0; kb < k1; kb += 8 * 32) {
         uint32_t ops[8];
@@ -106,7 +72,6 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
                 last = k;
             }
         }
-    }
     }
     sum = hs_warp_sum64(sum);
 #pragma unroll
@@ -929,9 +894,7 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     HS_CUDA(ctx, cudaMemsetAsync(d_totals, 0, 5 * sizeof(int64_t), ctx->stream));
     HS_CUDA(ctx, cudaMemsetAsync(p->d_next_read, 0, 4 * sizeof(unsigned int), ctx->stream));
     if (nr > 0) {
-        // HSGPU_SPAN_VEC=1 selects the 16-byte-load variant of the op scan (experimental until measured on the GPU)
-        static const bool span_vec = getenv("HSGPU_SPAN_VEC") != nullptr;
-        HS_KERNEL(ctx, "span_kernel", (span_vec ? span_kernel<true> : span_kernel<false>)<<<rblocks, 256, 0, ctx->stream>>>(
+        HS_KERNEL(ctx, "span_kernel", span_kernel<<<rblocks, 256, 0, ctx->stream>>>(
             nr, p->d_cigar, p->d_cigar_off, p->d_read_start, p->d_read_contig, p->d_contig_len, p->d_read_end,
             p->d_row_alloc, p->d_read_tlead, p->d_read_flags, reinterpret_cast<unsigned long long*>(d_totals)));
     }
