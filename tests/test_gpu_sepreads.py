@@ -192,6 +192,26 @@ def test_two_gpus_give_the_same_gro(tmp_path):
     assert ref == ours
 
 
+@pytest.mark.parametrize("case", ["ont", "lowmem", "amplicon"])
+def test_gro_matches_golden(tmp_path, case):
+    """committed fixtures (tests/golden/make_golden_sr.py: the reference's .col and the RNG-pinned reference's .gro):
+    the GPU executable reproduces the .gro byte for byte without oracle/_ref at run time"""
+    import gzip
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_sr
+    _, err, low, rare, amp = make_golden_sr.CASES[case]
+    g = os.path.join(ROOT, "tests", "golden")
+    tmp = str(tmp_path)
+    col, out = os.path.join(tmp, case + ".col"), os.path.join(tmp, "ours.gro")
+    with open(col, "wb") as f:
+        f.write(gzip.open(os.path.join(g, f"sr_{case}.col.gz")).read())
+    want = gzip.open(os.path.join(g, f"sr_{case}.gro.gz")).read()
+    subprocess.run([OURS, col, "4", err, os.path.join(tmp, "no_ploidy"), low, rare, amp, out, "0"], check=True,
+                   stdout=subprocess.DEVNULL, env=dict(os.environ, HS_PIN_SEED=str(PIN_SEED)))
+    assert open(out, "rb").read() == want
+
+
 def test_unpinned_run_is_a_valid_clustering(tmp_path):
     """without HS_PIN_SEED the sweep orders are random (as in the reference): same windows and reads, labels may differ"""
     chunks = [cases.small_case(seed=102, length=40000, depth=70, mean_len=7000, error=0.06)]

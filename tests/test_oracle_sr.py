@@ -110,6 +110,32 @@ def test_host_pipeline_gro_identical_to_pinned_reference(tmp_path, case):
     assert ref.count(b"GROUP") >= 1
 
 
+def _golden(tmp, name):
+    """a committed .col of the reference's HS_call_variants and the pinned reference's .gro for it
+    (tests/golden/make_golden_sr.py); returns (path of the unpacked .col, .gro bytes, arguments)"""
+    import gzip
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_sr
+    _, err, low, rare, amp = make_golden_sr.CASES[name]
+    g = os.path.join(ROOT, "tests", "golden")
+    col = os.path.join(tmp, name + ".col")
+    with open(col, "wb") as f:
+        f.write(gzip.open(os.path.join(g, f"sr_{name}.col.gz")).read())
+    return col, gzip.open(os.path.join(g, f"sr_{name}.gro.gz")).read(), (err, low, rare, amp)
+
+
+@pytest.mark.parametrize("case", ["ont", "lowmem", "amplicon"])
+def test_host_pipeline_matches_golden_gro(tmp_path, case):
+    """the same comparison against committed fixtures: needs neither /root/reference nor oracle/_ref at run time"""
+    col, want, (err, low, rare, amp) = _golden(str(tmp_path), case)
+    out = os.path.join(str(tmp_path), "ours.gro")
+    subprocess.run([HOSTCHECK, col, "2", err, os.path.join(str(tmp_path), "no_ploidy"), low, rare, amp, out, "0"], check=True,
+                   stdout=subprocess.DEVNULL)
+    assert open(out, "rb").read() == want
+    assert want.count(b"GROUP") >= 1
+
+
 def test_usage_and_help_status(tmp_path):
     """hairsplitter.py probes the executable with --help and expects status 0 (hairsplitter.py:241-252)"""
     r = subprocess.run([HOSTCHECK, "--help"], stdout=subprocess.PIPE)
