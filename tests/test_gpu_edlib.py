@@ -163,3 +163,34 @@ def test_single_pair_shim_has_edlibs_result_semantics(gpu_ctx, oracle):
     cfg = api.EdlibAlignConfig(-1, 2, 2, None, 1)
     r = gpu_ctx.lib.hsgpu_edlibAlign(gpu_ctx.h, b"ACGT", 4, b"ACGT", 4, cfg)
     assert r.status == 1 and not r.endLocations
+
+
+def test_golden_vectors_of_the_vendored_edlib(gpu_ctx):
+    """committed vectors made from the reference's vendored edlib (tests/golden/make_golden_edlib.py): the batch
+    kernel reproduces distance, locations and path without oracle/_ref at run time"""
+    import gzip
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    vec = json.loads(gzip.open(os.path.join(root, "tests", "golden", "edlib_vectors.json.gz")).read())
+    groups = {}
+    for v in vec:
+        groups.setdefault((v["k"], v["mode"], v["task"]), []).append(v)
+    for (k, mode, task), vs in groups.items():
+        qs = [v["q"].encode("latin1") for v in vs]
+        ts = [v["t"].encode("latin1") for v in vs]
+        res, ends, starts, aln = gpu_ctx.edlib_align_batch(qs, ts, k=k, mode=mode, task=task)
+        for i, v in enumerate(vs):
+            r = res[i]
+            ctx = (i, len(qs[i]), len(ts[i]), k, mode, task)
+            assert int(r["edit_distance"]) == v["edit_distance"], ctx
+            assert int(r["alphabet_length"]) == v["alphabet_length"], ctx
+            lo, nl = int(r["loc_off"]), int(r["n_locations"])
+            assert ends[lo:lo + nl].tolist() == v["end_locations"], ctx
+            if v["start_locations"] is None:
+                assert int(r["has_start_locations"]) == 0, ctx
+            else:
+                assert starts[lo:lo + nl].tolist() == v["start_locations"], ctx
+            if task == 2 and v["alignment"] is not None and v["edit_distance"] >= 0 and int(r["status"]) == 0:
+                ao, al = int(r["aln_off"]), int(r["alignment_length"])
+                assert aln[ao:ao + al].tolist() == v["alignment"], ctx
