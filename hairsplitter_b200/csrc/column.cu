@@ -9,6 +9,8 @@
 // reference's robin_hood map and decides ties (rank.cuh).
 #include <algorithm>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "rank.cuh"
 
@@ -638,7 +640,7 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
         cv.add(&p->d_work, p->n_cols + 4);
         p->arena_words = (unsigned int)std::min<int64_t>(2 * p->n_cols + 1024, 0x7fffffff);
         cv.add(&p->d_arena, p->arena_words);
-        cv.add(&p->d_item_off, p->n_cols + p->n_cols / 2 + 512);  // items, then the literal list
+        cv.add(&p->d_item_off, 2 * p->n_cols + 512);  // items, then the literal list (at most one entry per item)
         cv.add(&p->d_tile_sus, p->n_tiles + 1);
         HS_CUDA(ctx, cv.alloc(ctx, &p->d_rank_block));
     }
@@ -657,7 +659,7 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
         HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // mean_error is caller memory
         hs_free(ctx, d_me);
     }
-    static bool attr_set[64] = {};  // per device: function attributes belong to the device's context
+    static std::atomic<bool> attr_set[64];  // per device: function attributes belong to the device's context
     if (!attr_set[ctx->device & 63]) {
         HS_CUDA(ctx, cudaFuncSetAttribute(column_rank_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           column_smem<uint16_t>()));

@@ -12,6 +12,8 @@
 //   pass 2  the 2x2 table n11/n01/n10/n00 (+ solid variants) over reads with state +-1.
 #include <vector>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "rank.cuh"
 
@@ -566,7 +568,7 @@ int hsgpu_partition_tables(hsgpu_pileup* p, int32_t contig, const hsgpu_partitio
     HS_CUDA(ctx, hs_alloc(ctx, &d_out, n_out));
     HS_CUDA(ctx, hs_h2d(ctx, d_pst, pst.data(), (int64_t)pst.size()));
     HS_CUDA(ctx, hs_h2d(ctx, d_pos, pos, n_cols));
-    static bool attr[64] = {};  // per device: function attributes belong to the device's context
+    static std::atomic<bool> attr[64];  // per device: function attributes belong to the device's context
     if (!attr[ctx->device & 63]) {
         HS_CUDA(ctx, cudaFuncSetAttribute(partition_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTablesSmem));
         attr[ctx->device & 63] = true;
@@ -632,7 +634,7 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     if (n_suspects > 0) {
         HS_KERNEL(ctx, "set_inlist_kernel", set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 1));
     }
-    static bool attr[64] = {};  // per device: function attributes belong to the device's context
+    static std::atomic<bool> attr[64];  // per device: function attributes belong to the device's context
     if (!attr[ctx->device & 63]) {
         HS_CUDA(ctx, cudaFuncSetAttribute(robust_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFilterSmem));
         attr[ctx->device & 63] = true;

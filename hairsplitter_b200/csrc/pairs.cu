@@ -25,6 +25,8 @@
 #include <numeric>
 #include <vector>
 
+#include <atomic>
+
 #include "common.cuh"
 
 #define PG_TILE 128                     // rows per tile (UMMA M, and N per operand half)
@@ -421,7 +423,8 @@ typedef CUresult (*PgEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int pg_make_tmap(hsgpu_ctx* ctx, CUtensorMap* tm, void* base, int64_t k_ld, int64_t rows) {
-    static PgEncodeTiled enc = nullptr;
+    static std::atomic<PgEncodeTiled> enc_cache{nullptr};  // the same pointer whoever stores it first
+    PgEncodeTiled enc = enc_cache.load();
     if (!enc) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qr;
@@ -429,6 +432,7 @@ static int pg_make_tmap(hsgpu_ctx* ctx, CUtensorMap* tm, void* base, int64_t k_l
         if (!fn || qr != cudaDriverEntryPointSuccess)
             HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu_pairs: the driver does not export cuTensorMapEncodeTiled");
         enc = (PgEncodeTiled)fn;
+        enc_cache.store(enc);
     }
     const cuuint64_t dims[2] = {(cuuint64_t)k_ld, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)k_ld};
@@ -697,7 +701,7 @@ int hsgpu_pairs_compute(hsgpu_pairs* h) {
         HS_CUDA(ctx, cudaMemsetAsync(h->d_diff, 0, out_bytes, ctx->stream));
     }
     if (h->n_work > 0) {
-        static bool attr_set[64] = {};  // per device: function attributes belong to the device's context
+        static std::atomic<bool> attr_set[64];  // per device: function attributes belong to the device's context
         if (!attr_set[ctx->device & 63]) {
             HS_CUDA(ctx, cudaFuncSetAttribute(pair_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
             attr_set[ctx->device & 63] = true;

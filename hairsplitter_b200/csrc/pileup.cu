@@ -13,6 +13,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <atomic>
+
 #include "common.cuh"
 
 static std::mutex g_upload_mutex[64];  // per device, see hsgpu_pileup_create
@@ -970,10 +972,12 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
             a.ops_mid = (int)std::min<int64_t>(mean_ops + 1, 0x7fffffff);
         }
         // persistent warps pull reads from a counter: read lengths vary by an order of magnitude
-        static int ctas_per_sm = 0;
+        static std::atomic<int> ctas_cache{0};  // a property of the kernel, the same on every sm_100 device
+        int ctas_per_sm = ctas_cache.load();
         if (!ctas_per_sm) {
             HS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pileup_kernel, 32 * PW_WARPS, 0));
             if (ctas_per_sm < 1) ctas_per_sm = 1;
+            ctas_cache.store(ctas_per_sm);
         }
         const unsigned pgrid = (unsigned)std::min<int64_t>(rblocks, (int64_t)ctx->sm_count * ctas_per_sm);
         HS_KERNEL(ctx, "pileup_kernel", pileup_kernel<<<pgrid, 32 * PW_WARPS, 0, ctx->stream>>>(a));
