@@ -221,17 +221,33 @@ __global__ void __launch_bounds__(128) partition_tables_kernel(TablesArgs a) {
     }
 }
 
-// ---- kernel B: loops 3 and 4 of keep_only_robust_variants over every column of a contig -----------
-// One CTA per 128-column tile. Work items are (active column, active partition) pairs: a column is
-// active when it is a suspect (loop 3) or passes the rescue pre-filter (loop 4); a partition is
-// active for the tile when at least one of the tile's reads is present in it.
+// ---- kernel B: loops 3 and 4 of keep_only_robust_variants for every contig of a pileup -------------
+// A column can only be kept if it is in snps_in (loop 3, :721-738) or passes the rescue pre-filter with at
+// least 5 carriers of its second allele (loop 4, :745-764; see filter_active_kernel) -- about 3 % of the
+// columns at 60x / 10 % error. Those ACTIVE columns are compacted first; then one WARP takes one active column:
+// its cells (read, code) are gathered once into shared memory, the partitions that hold one of its reads come
+// from one 128-bit presence row per read, and for every such partition the warp builds the reference's 2x2
+// table with ballots (the column's own majority code) and a small shared-memory histogram (everything else).
+// One launch covers all contigs of the batch; the work is proportional to the active columns, not to the tiles.
 #define HS_FLAG_INLIST 16
+#define RF_WARPS 8
+#define RF_CAP 192  // cells of a column staged per warp; deeper columns (amplicons) are re-gathered per partition
+
+struct FilterDesc {     // per contig
+    int64_t pst_off;    // byte offset of its [n_reads][npad] state rows in pst_t
+    int64_t pmask_off;  // word offset of its [n_reads][pwords] presence rows in pmask
+    int32_t n_parts, npad, pwords, pad_;
+};
 
 struct FilterArgs {
-    int contig;
-    int64_t tile0, read0, g0;
-    int L, n_reads, n_parts;
-    const uint8_t* pstate;
+    int n_contigs;
+    unsigned in_flag;  // the flag bit that marks snps_in: HS_FLAG_INLIST (caller's list) or HS_FLAG_SUSPECT (the pileup's own)
+    const FilterDesc* desc;
+    const uint8_t* pst_t;
+    const uint32_t* pmask;
+    const int64_t* col_base;
+    const int64_t* tile_base;
+    const int64_t* contig_read_off;
     const int64_t* tile_off;
     const int32_t* tile_reads;
     const int32_t* read_start;
@@ -241,251 +257,372 @@ struct FilterArgs {
     const uint8_t* k0;
     const uint8_t* flags;
     const uint32_t* depth;
-    const uint32_t* counts;   // c0,c1,c2 per column (column ranking)
-    const uint8_t* pstate_t;  // [n_reads][npad]: the transpose of pstate, rows padded to 16 partitions
-    int npad;
+    const uint32_t* counts;  // c0,c1,c2 per column (column ranking)
     const HsRankLut* lut;
-    uint8_t* kept;  // [L]
+    int64_t g_begin, g_end;  // global column range handled by this call
+    uint32_t* active;        // compacted global ids of the active columns
+    unsigned int* counters;  // [0] active columns, [1] work cursor of robust_filter_kernel, [2] kept columns (list reservation)
+    uint8_t* kept;           // [n_cols]
 };
 
-__device__ __forceinline__ void ct_stage_rows(uint4* s_tile, int32_t* s_reads, const FilterArgs& a, int64_t list_off,
-                                              int b0, int nrows, int q0, int tid) {
-    for (int v = tid; v < nrows * (HS_TILE / 16); v += 128) {
-        const int row = v >> 3, part = v & 7;
-        const int32_t r = __ldg(a.tile_reads + list_off + b0 + row);
-        const int s = __ldg(a.read_start + r) & ~(HS_ALIGN - 1);
-        const int e = (__ldg(a.read_end + r) + HS_ALIGN - 1) & ~(HS_ALIGN - 1);
-        const int qv = q0 + 16 * part;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (qv >= s && qv < e) val = __ldg(reinterpret_cast<const uint4*>(a.codes + __ldg(a.row_base + r) + qv));
-        s_tile[v] = val;
+__device__ __forceinline__ int rf_contig_of(const int64_t* __restrict__ col_base, int n_contigs, int64_t g) {
+    int lo = 0, hi = n_contigs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(col_base + mid) <= g) lo = mid; else hi = mid - 1;
     }
-    for (int i = tid; i < nrows; i += 128) s_reads[i] = (int32_t)(a.tile_reads[list_off + b0 + i] - a.read0);
+    return lo;
 }
 
-__global__ void __launch_bounds__(128) robust_filter_kernel(FilterArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint4* s_tile = reinterpret_cast<uint4*>(smem);                                          // CT_ROWS*128
-    uint16_t* s_hist = reinterpret_cast<uint16_t*>(smem + CT_ROWS * HS_TILE);                // [125][128]
-    uint8_t* s_order = smem + CT_ROWS * HS_TILE + HS_NCODES * 128 * 2;                       // [125][128]
-    uint8_t* s_state = smem + CT_ROWS * HS_TILE + HS_NCODES * 128 * 3;                       // [CT_NPA][CT_SSTRIDE]
-    int32_t* s_reads = reinterpret_cast<int32_t*>(s_state + CT_NPA * CT_SSTRIDE);            // [CT_ROWS]
-    __shared__ int s_cols[HS_TILE];
-    __shared__ int s_parts[CT_NPA];
-    __shared__ int s_ncols, s_nparts;
-    __shared__ unsigned s_keep[HS_TILE];  // per column: 1 = kept
-    __shared__ unsigned s_pmask[4];       // partitions pb..pb+127 that hold one of the tile's reads
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int q0 = blockIdx.x * HS_TILE;
-    const int64_t tile = a.tile0 + blockIdx.x;
-    const int64_t list_off = a.tile_off[tile];
-    const int nlist = (int)(a.tile_off[tile + 1] - list_off);
-    const unsigned char* s_bytes = reinterpret_cast<const unsigned char*>(s_tile);
-
-    // active columns, in order
-    if (tid == 0) s_ncols = 0;
-    s_keep[tid] = 0;
-    __syncthreads();
-    {
-        const int q = q0 + tid;
-        const unsigned f = (q < a.L) ? a.flags[a.g0 + q] : 0u;
-        // Loop 4 keeps a column only if n10 + n00 > 4 (:756): reads that carry the alternative allele. No code but
-        // the column's own most frequent one (ref_base = k0) has more than c1 carriers, and when the reference's
-        // char/unsigned char quirk makes ref_base its own alternative the two counters stay 0 -- so a column with
-        // c1 <= 4 can only be kept by loop 3, i.e. if it is a suspect.
-        bool act = (f & HS_FLAG_INLIST) != 0;
-        if (!act && (f & HS_FLAG_RESCUE)) act = a.counts[3 * (a.g0 + q) + 1] > 4u;
-        for (int w = 0; w < 4; w++) {
-            if (wid == w) {
-                const unsigned mk = __ballot_sync(0xffffffffu, act);
-                const int base = s_ncols;
-                if (act) s_cols[base + __popc(mk & ((1u << lane) - 1u))] = tid;
-                __syncwarp();
-                if (lane == 0) s_ncols = base + __popc(mk);
-            }
-            __syncthreads();
-        }
+// Loop 4 keeps a column only if n10 + n00 > 4 (:756): reads that carry the alternative allele. No code but the
+// column's own most frequent one (ref_base = k0) has more than c1 carriers, and when the reference's
+// char/unsigned char quirk makes ref_base its own alternative the two counters stay 0 -- so a column with c1 <= 4
+// can only be kept by loop 3, i.e. if it is in snps_in.
+__global__ void __launch_bounds__(256) filter_active_kernel(FilterArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = a.g_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool act = false;
+    if (g < a.g_end) {
+        const unsigned f = a.flags[g];
+        act = (f & a.in_flag) != 0;
+        if (!act && (f & HS_FLAG_RESCUE)) act = a.counts[3 * g + 1] > 4u;
+        if (act) act = a.desc[rf_contig_of(a.col_base, a.n_contigs, g)].n_parts > 0;  // :640-642: no partition, nothing kept
+        a.kept[g] = 0;
     }
-    const int ncols = s_ncols;
-    if (ncols == 0 || nlist == 0 || a.n_parts == 0) {
-        if (q0 + tid < a.L) a.kept[q0 + tid] = 0;
-        return;
+    const unsigned mk = __ballot_sync(0xffffffffu, act);
+    if (mk) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(a.counters, (unsigned)__popc(mk));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (act) a.active[base + __popc(mk & ((1u << lane) - 1u))] = (uint32_t)g;
     }
-    for (int i = tid; i < HS_NCODES * 128 * 2 / 4; i += 128) reinterpret_cast<uint32_t*>(s_hist)[i] = 0;
-    const bool single = nlist <= CT_ROWS;
-    if (single) ct_stage_rows(s_tile, s_reads, a, list_off, 0, nlist, q0, tid);
-    __syncthreads();
+}
 
-    for (int pb = 0; pb < a.n_parts; pb += 128) {
-        // which of partitions pb..pb+127 have one of the tile's reads? One 16-byte load covers 16 partitions of a
-        // read (pstate_t), every thread takes (read, vector) pairs, the answer is a 128-bit mask in shared memory
-        __syncthreads();
-        if (tid < 4) s_pmask[tid] = 0;
-        __syncthreads();
-        {
-            const int nvec = min(8, (a.npad - pb) >> 4);
-            for (int v = tid; v < nlist * nvec; v += 128) {
-                const int i = v / nvec, j = v - i * nvec;
-                const int32_t n = single ? s_reads[i] : (int32_t)(a.tile_reads[list_off + i] - a.read0);
-                const uint4 x = __ldg(reinterpret_cast<const uint4*>(a.pstate_t + (int64_t)n * a.npad + pb + 16 * j));
-                const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-                unsigned bits = 0;
-#pragma unroll
-                for (int b = 0; b < 16; b++) bits |= (((w[b >> 2] >> (8 * (b & 3))) & 3u) ? 1u : 0u) << b;
-                if (bits) atomicOr(&s_pmask[j >> 1], bits << (16 * (j & 1)));
-            }
+// alternative allele of a (column, partition) pair among tied codes: the reference iterates its robin_hood map
+// and keeps the first strict maximum (:832-844). `order` = the codes (minus 33) in order of first appearance among
+// the partition's reads, hist their counts (both in this warp's shared memory); see hs_select_alt.
+__device__ __noinline__ int rf_select_alt_tied(const uint8_t* order, const uint32_t* hist, int m, int ref, int max2,
+                                                const HsRankLut* __restrict__ lut) {
+    const bool ref_excluded = ref < 128;
+    bool ref_seen = false;
+    for (int k = 0; k < m; k++) ref_seen |= (order[k] + HS_CODE0 == ref);
+    const int n = m + (ref_seen ? 0 : 1);  // content2[ref_base] creates the entry (:833)
+    if (lut && n <= 51) {
+        const int level = hs_rank_level(n);
+        const uint8_t* __restrict__ home = lut->home[level];
+        unsigned long long occ[4] = {0, 0, 0, 0};  // 4-bit occupancy counters of up to 64 buckets
+        int best = 1 << 30, nbest = 0;
+        for (int k = -1; k < m; k++) {
+            if (k < 0 && ref_seen) continue;
+            const int key = k < 0 ? ref : order[k] + HS_CODE0;
+            const int h = __ldg(home + key);
+            occ[h >> 4] += 1ull << (4 * (h & 15));
+            if (k < 0 || (ref_excluded && key == ref)) continue;
+            if ((int)hist[key - HS_CODE0] != max2) continue;
+            if (h < (best >> 8)) { best = (h << 8) | key; nbest = 1; }
+            else if (h == (best >> 8)) nbest++;
         }
-        __syncthreads();
-        const int p = pb + tid;
-        const bool present = p < a.n_parts && ((s_pmask[tid >> 5] >> (tid & 31)) & 1u);
-        // chunks of up to CT_NPA active partitions
-        int consumed = 0;  // number of active partitions (in thread order) already processed
-        for (;;) {
-            __syncthreads();
-            if (tid == 0) s_nparts = 0;
-            __syncthreads();
-            // ordered compaction of the next CT_NPA active partitions
-            for (int w = 0; w < 4; w++) {
-                if (wid == w) {
-                    const unsigned mk = __ballot_sync(0xffffffffu, present);
-                    const int base = s_nparts;  // counts ALL active partitions seen so far in this sweep
-                    const int my = base + __popc(mk & ((1u << lane) - 1u));
-                    if (present && my >= consumed && my < consumed + CT_NPA) s_parts[my - consumed] = p;
+        int next_free = 0, maxd = 0;
+        const int nb = 8 << level;
+        for (int b = 0; b < nb; b++) {
+            const int cnt = (int)((occ[b >> 4] >> (4 * (b & 15))) & 15ull);
+            if (next_free < b) next_free = b;
+            next_free += cnt;
+            if (cnt && next_free - 1 - b > maxd) maxd = next_free - 1 - b;
+        }
+        if (nbest == 1 && maxd < 6) return best & 0xff;
+    }
+    HsRhTable t;
+    hs_rh_new(t);
+    for (int k = 0; k < m; k++) hs_rh_insert(t, (uint8_t)(order[k] + HS_CODE0));
+    if (!ref_seen) hs_rh_insert(t, (uint8_t)ref);
+    uint8_t it[HS_RH_MAXKEYS];
+    const int nk = hs_rh_iterate(t, it);
+    for (int i = 0; i < nk; i++) {
+        const int key = it[i];
+        if (ref_excluded && key == ref) continue;
+        if (key < HS_CODE0) continue;
+        if ((int)hist[key - HS_CODE0] == max2) return key;
+    }
+    return ' ';
+}
+
+__global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs a) {
+    __shared__ int32_t s_n_all[RF_WARPS][RF_CAP];
+    __shared__ uint8_t s_code_all[RF_WARPS][RF_CAP];
+    __shared__ uint8_t s_st_all[RF_WARPS][RF_CAP];
+    __shared__ uint32_t s_hist_all[RF_WARPS][HS_NCODES + 3];
+    __shared__ uint8_t s_touched_all[RF_WARPS][HS_NCODES + 3];
+    __shared__ int s_m_all[RF_WARPS];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int32_t* const s_n = s_n_all[wid];
+    uint8_t* const s_code = s_code_all[wid];
+    uint8_t* const s_st = s_st_all[wid];
+    uint32_t* const s_hist = s_hist_all[wid];
+    uint8_t* const s_touched = s_touched_all[wid];
+    int* const s_m = &s_m_all[wid];
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i = lane; i < HS_NCODES + 3; i += 32) s_hist[i] = 0;
+    if (lane == 0) *s_m = 0;
+    __syncwarp();
+    const unsigned n_active = a.counters[0];
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(a.counters + 1, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_active) break;
+        const int64_t g = a.active[item];
+        const int c = rf_contig_of(a.col_base, a.n_contigs, g);
+        const FilterDesc d = a.desc[c];
+        const int q = (int)(g - a.col_base[c]);
+        const int64_t read0 = a.contig_read_off[c];
+        const int64_t tile = a.tile_base[c] + q / HS_TILE;
+        const int64_t l0 = a.tile_off[tile], l1 = a.tile_off[tile + 1];
+        const int ref = a.k0[g];
+        const unsigned f = a.flags[g];
+        const bool inlist = (f & a.in_flag) != 0;
+        const uint8_t* __restrict__ pst = a.pst_t + d.pst_off;
+        const uint32_t* __restrict__ pm = a.pmask + d.pmask_off;
+        // ---- the column's cells, in ascending read order ----
+        int ncell = 0;
+        for (int64_t lb = l0; lb < l1; lb += 32) {
+            const int64_t l = lb + lane;
+            bool hit = false;
+            int32_t r = 0;
+            if (l < l1) {
+                r = __ldg(a.tile_reads + l);
+                hit = __ldg(a.read_start + r) <= q && q < __ldg(a.read_end + r);
+            }
+            const unsigned mk = __ballot_sync(0xffffffffu, hit);
+            const int o = ncell + __popc(mk & lt);
+            if (hit && o < RF_CAP) {
+                s_n[o] = (int32_t)(r - read0);
+                s_code[o] = __ldg(a.codes + __ldg(a.row_base + r) + q);
+            }
+            ncell += __popc(mk);
+        }
+        const bool staged = ncell <= RF_CAP;
+        __syncwarp();
+        // visits every cell of the column, 32 at a time: body(valid, code, n, slot) with slot = index in the staged
+        // arrays (or -1 when the column is too deep to be staged and is gathered again)
+        auto for_cells = [&](auto body) {
+            if (staged) {
+                for (int i0 = 0; i0 < ncell; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool v = i < ncell;
+                    body(v, v ? (int)s_code[i] : 0, v ? s_n[i] : 0, v ? i : -1);
+                }
+            } else {
+                for (int64_t lb = l0; lb < l1; lb += 32) {
+                    const int64_t l = lb + lane;
+                    bool hit = false;
+                    int32_t r = 0;
+                    int code = 0;
+                    if (l < l1) {
+                        r = __ldg(a.tile_reads + l);
+                        hit = __ldg(a.read_start + r) <= q && q < __ldg(a.read_end + r);
+                        if (hit) code = __ldg(a.codes + __ldg(a.row_base + r) + q);
+                    }
+                    body(hit, code, (int32_t)(r - read0), -1);
+                }
+            }
+        };
+        bool keep = false;
+        for (int pb = 0; pb < d.n_parts && !keep; pb += 128) {
+            // partitions pb..pb+127 that hold at least one of the column's reads
+            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+            for_cells([&](bool v, int, int32_t n, int) {
+                if (v) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(pm + (int64_t)n * d.pwords + (pb >> 5)));
+                    m0 |= x.x; m1 |= x.y; m2 |= x.z; m3 |= x.w;
+                }
+            });
+            uint32_t present[4] = {__reduce_or_sync(0xffffffffu, m0), __reduce_or_sync(0xffffffffu, m1),
+                                   __reduce_or_sync(0xffffffffu, m2), __reduce_or_sync(0xffffffffu, m3)};
+            for (int w = 0; w < 4 && !keep; w++) {
+                uint32_t bits = present[w];
+                while (bits && !keep) {
+                    const int p = pb + 32 * w + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    // ---- pass 1: the partition's reads on this column. The column's own majority code is counted
+                    // with ballots (its rows with state +1 / -1 are n11 / n01, :893-949), every other code goes
+                    // through the warp's histogram ----
+                    int nb = 0, nref = 0, n11 = 0, n01 = 0;
+                    for_cells([&](bool v, int code, int32_t n, int slot) {
+                        int sg = 0;
+                        if (v) {
+                            sg = __ldg(pst + (int64_t)n * d.npad + p) & 3;
+                            if (slot >= 0) s_st[slot] = (uint8_t)sg;
+                        }
+                        const bool act = v && sg != 0;
+                        const bool isref = act && code == ref;
+                        nb += __popc(__ballot_sync(0xffffffffu, act));
+                        nref += __popc(__ballot_sync(0xffffffffu, isref));
+                        n11 += __popc(__ballot_sync(0xffffffffu, isref && sg == 1));
+                        n01 += __popc(__ballot_sync(0xffffffffu, isref && sg == 2));
+                        if (act && !isref) {
+                            if (atomicAdd(&s_hist[code - HS_CODE0], 1u) == 0u) s_touched[atomicAdd(s_m, 1)] = (uint8_t)(code - HS_CODE0);
+                        }
+                    });
                     __syncwarp();
-                    if (lane == 0) s_nparts = base + __popc(mk);
-                }
-                __syncthreads();
-            }
-            const int total_active = s_nparts;
-            const int npa = min(CT_NPA, total_active - consumed);
-            if (npa <= 0) break;
-
-            const int nitems = ncols * npa;
-            for (int ib = 0; ib < nitems; ib += 128) {
-                const int item = ib + tid;
-                const bool valid = item < nitems;
-                const int col = valid ? s_cols[item / npa] : 0;
-                const int kk = valid ? item % npa : 0;
-                const int q = q0 + col;
-                const int ref = valid ? a.k0[a.g0 + q] : 0;
-                const unsigned f = valid ? a.flags[a.g0 + q] : 0u;
-                int m = 0, nb = 0, alt = ' ', nref = 0;
-                int n00 = 0, n01 = 0, n10 = 0, n11 = 0;
-                bool second = false;  // does this item need its 2x2 table?
-                for (int pass = 0; pass < 2; pass++) {
-                    for (int b0 = 0; b0 < nlist; b0 += CT_ROWS) {
-                        const int nrows = min(CT_ROWS, nlist - b0);
-                        if (!single) {
-                            __syncthreads();
-                            ct_stage_rows(s_tile, s_reads, a, list_off, b0, nrows, q0, tid);
-                            __syncthreads();
+                    const int m = *s_m;  // distinct codes other than ref_base
+                    if (nb > 0) {
+                        // A column outside snps_in is only kept through loop 4, which needs n10 + n00 > 4 (:756): at
+                        // least 5 of the partition's reads on one code other than ref_base (codes >= 128 never count
+                        // as ref_base in the reference's comparison, :838: no shortcut there)
+                        int maxc = -1;
+                        for (int k0 = 0; k0 < m; k0 += 32) {
+                            const int k = k0 + lane;
+                            const int cnt = k < m ? (int)s_hist[s_touched[k]] : -1;
+                            maxc = max(maxc, cnt);
                         }
-                        if (!single || (ib == 0 && pass == 0)) {
-                            // states of the chunk's partitions for the staged rows
-                            if (single) __syncthreads();
-                            for (int v = tid; v < npa * nrows; v += 128) {
-                                const int k2 = v / nrows, row = v - k2 * nrows;
-                                s_state[k2 * CT_SSTRIDE + row] = a.pstate[(int64_t)s_parts[k2] * a.n_reads + s_reads[row]];
+                        maxc = __reduce_max_sync(0xffffffffu, maxc);
+                        const bool second = inlist || ref >= 128 || maxc > 4;
+                        if (second) {
+                            // secondFrequent (:832-844): the most frequent code other than ref_base (ref_base itself
+                            // competes when it is >= 128)
+                            int max2 = maxc, alt = ' ';
+                            if (ref >= 128 && nref > 0 && nref >= max2) max2 = max(max2, nref);
+                            int ties = 0, cand = ' ';
+                            for (int k0 = 0; k0 < m; k0 += 32) {
+                                const int k = k0 + lane;
+                                const bool hitk = k < m && (int)s_hist[s_touched[k]] == max2;
+                                const unsigned mk = __ballot_sync(0xffffffffu, hitk);
+                                ties += __popc(mk);
+                                if (mk) {
+                                    const int src = __ffs(mk) - 1;
+                                    const int key = __shfl_sync(0xffffffffu, hitk ? (int)s_touched[k] + HS_CODE0 : 0, src);
+                                    cand = key;
+                                }
                             }
-                            __syncthreads();
-                        }
-                        if (valid) {
-                            const uint8_t* st_row = s_state + kk * CT_SSTRIDE;
-                            if (pass == 0) {
-                                // histogram of the codes among the partition's reads, first-seen order kept. The
-                                // column's own majority code (most of the rows) is counted in a register; the
-                                // rows it holds with state +1 / -1 are n11 / n01 of the table (:893-949).
-                                for (int row = 0; row < nrows; row++) {
-                                    const int code = s_bytes[row * HS_TILE + col];
-                                    const int sg = st_row[row] & 3;
-                                    if (code && sg) {
-                                        const int idx = code - HS_CODE0;
-                                        if (code == ref) {
-                                            if (nref == 0) s_order[(m++) * 128 + tid] = (uint8_t)idx;
-                                            nref++;
-                                            n11 += sg == 1;
-                                            n01 += sg == 2;
-                                        } else {
-                                            const unsigned c = s_hist[idx * 128 + tid];
-                                            if (c == 0) s_order[(m++) * 128 + tid] = (uint8_t)idx;
-                                            s_hist[idx * 128 + tid] = (uint16_t)(c + 1);
+                            if (ref >= 128 && nref > 0 && nref == max2) { ties++; cand = ref; }
+                            if (max2 < 0) {
+                                alt = ' ';  // no candidate at all (every read of the partition carries ref_base < 128)
+                            } else if (ties == 1) {
+                                alt = cand;
+                            } else {
+                                // several codes share the maximum: the map's iteration order decides. Lane 0 rebuilds
+                                // the order of first appearance and replays the reference (rare).
+                                int alt0 = ' ';
+                                if (staged) {
+                                    if (lane == 0) {
+                                        uint8_t order[HS_NCODES + 1];
+                                        int mo = 0;
+                                        bool ref_in = false;
+                                        if (nref > 0) s_hist[ref - HS_CODE0] = (uint32_t)nref;
+                                        for (int i = 0; i < ncell; i++) {
+                                            if (!s_st[i]) continue;
+                                            const int idx = s_code[i] - HS_CODE0;
+                                            bool seen = false;
+                                            for (int k = 0; k < mo; k++) seen |= order[k] == idx;
+                                            if (!seen) order[mo++] = (uint8_t)idx;
+                                            ref_in |= (idx + HS_CODE0 == ref);
                                         }
-                                        nb++;
+                                        alt0 = rf_select_alt_tied(order, s_hist, mo, ref, max2, a.lut);
+                                        if (nref > 0) s_hist[ref - HS_CODE0] = 0;
+                                    }
+                                } else {
+                                    // deep column: first appearances = lowest list position of every code
+                                    // (collected chunk by chunk in list order by the whole warp)
+                                    __shared__ uint8_t s_order_deep[RF_WARPS][HS_NCODES + 1];
+                                    uint8_t* order = s_order_deep[wid];
+                                    int mo = 0;
+                                    for_cells([&](bool v, int code, int32_t n, int) {
+                                        int sg = 0;
+                                        if (v) sg = __ldg(pst + (int64_t)n * d.npad + p) & 3;
+                                        unsigned todo = __ballot_sync(0xffffffffu, v && sg != 0);
+                                        while (todo) {  // in lane order = read order
+                                            const int src = __ffs(todo) - 1;
+                                            todo &= todo - 1;
+                                            const int idx = __shfl_sync(0xffffffffu, code, src) - HS_CODE0;
+                                            bool seen = false;
+                                            for (int k = lane; k < mo; k += 32) seen |= order[k] == idx;
+                                            if (!__any_sync(0xffffffffu, seen)) {
+                                                if (lane == 0) order[mo] = (uint8_t)idx;
+                                                mo++;
+                                                __syncwarp();
+                                            }
+                                        }
+                                    });
+                                    if (lane == 0) {
+                                        if (nref > 0) s_hist[ref - HS_CODE0] = (uint32_t)nref;
+                                        alt0 = rf_select_alt_tied(order, s_hist, mo, ref, max2, a.lut);
+                                        if (nref > 0) s_hist[ref - HS_CODE0] = 0;
                                     }
                                 }
-                            } else if (second) {
-                                for (int row = 0; row < nrows; row++) {
-                                    const int code = s_bytes[row * HS_TILE + col];
-                                    const int sg = st_row[row] & 3;
-                                    if (code == alt && code != ref) {
-                                        n10 += sg == 1;
-                                        n00 += sg == 2;
-                                    }
-                                }
+                                alt = __shfl_sync(0xffffffffu, alt0, 0);
+                            }
+                            // ---- pass 2: n10 / n00 ----
+                            int n10 = 0, n00 = 0;
+                            if (alt != ref) {
+                                for_cells([&](bool v, int code, int32_t n, int slot) {
+                                    int sg = 0;
+                                    if (v && code == alt) sg = slot >= 0 ? (int)s_st[slot] : (__ldg(pst + (int64_t)n * d.npad + p) & 3);
+                                    n10 += __popc(__ballot_sync(0xffffffffu, sg == 1));
+                                    n00 += __popc(__ballot_sync(0xffffffffu, sg == 2));
+                                });
+                            }
+                            // loop 3 (:721-738): columns of snps_in; loop 4 (:745-764): rescue of every other column (also
+                            // of suspects that failed loop 3). The chi-square is only evaluated where an integer
+                            // condition leaves the decision open.
+                            const bool c3 = inlist && (double)(n00 + n01 + n10 + n11) > __dmul_rn(0.5, (double)a.depth[g]);
+                            const bool c4 = (f & HS_FLAG_RESCUE) && n10 + n00 > 4 && n01 + n11 > 4;
+                            if (c3 || c4) {
+                                const float chi = hs_chi_square(n00, n01, n10, n11);
+                                if ((c3 && chi > 15.f) || (c4 && (double)chi > 20.0)) keep = true;
                             }
                         }
                     }
-                    if (pass == 0 && valid && nb > 0) {
-                        if (nref) s_hist[(ref - HS_CODE0) * 128 + tid] = (uint16_t)nref;
-                        // A column that is not a suspect is only kept through loop 4, which needs n10 + n00 > 4
-                        // (:756): at least 5 of the partition's reads on one code other than ref_base.
-                        // (codes >= 128 never count as ref_base in the reference's comparison, :838: no shortcut there)
-                        second = (f & HS_FLAG_INLIST) != 0 || ref >= 128;
-                        if (!second) {
-                            for (int k = 0; k < m && !second; k++) {
-                                const int idx = s_order[k * 128 + tid];
-                                second = idx + HS_CODE0 != ref && s_hist[idx * 128 + tid] > 4;
-                            }
-                        }
-                        if (second) alt = hs_select_alt(s_order, s_hist, 128, tid, m, ref, a.lut);
-                    }
-                }
-                if (valid) {
-                    for (int k = 0; k < m; k++) s_hist[s_order[k * 128 + tid] * 128 + tid] = 0;
-                    if (nb > 0 && second) {
-                        const float chi = hs_chi_square(n00, n01, n10, n11);
-                        bool keep = false;
-                        // loop 3 (:721-738): suspects
-                        if ((f & HS_FLAG_INLIST) &&
-                            (double)(n00 + n01 + n10 + n11) > __dmul_rn(0.5, (double)a.depth[a.g0 + q]) && chi > 15.f)
-                            keep = true;
-                        // loop 4 (:745-764): rescue of every other column (also suspects that failed loop 3)
-                        if ((f & HS_FLAG_RESCUE) && (double)chi > 20.0 && n10 + n00 > 4 && n01 + n11 > 4) keep = true;
-                        if (keep) s_keep[col] = 1;
-                    }
+                    // reset the histogram
+                    for (int k = lane; k < m; k += 32) s_hist[s_touched[k]] = 0;
+                    if (lane == 0) *s_m = 0;
+                    __syncwarp();
                 }
             }
-            consumed += npa;
-            if (consumed >= total_active) break;
         }
+        if (keep && lane == 0) a.kept[g] = 1;
     }
-    __syncthreads();
-    if (q0 + tid < a.L) a.kept[q0 + tid] = (uint8_t)s_keep[tid];
 }
 
-// ascending compaction of the kept columns: one CTA of 1024 threads; a round covers 16 columns per thread
-// (one 16-byte load of the flags), block-scans the per-thread counts and writes the positions in order
-__global__ void __launch_bounds__(1024) kept_scan_kernel(int L, const uint8_t* __restrict__ kept, int capacity,
-                                                         int32_t* __restrict__ out, int32_t* __restrict__ n_out) {
+// ascending compaction of the kept columns, one CTA of 1024 threads per contig: a first sweep counts, one atomic
+// reserves the contig's slice of the packed list (hdr[2c] = start, hdr[2c+1] = count), a second sweep writes the
+// positions in order. A round covers 16 columns per thread.
+__device__ __forceinline__ unsigned rf_kept_bits(const uint8_t* __restrict__ kept, int64_t g0, int L, int q0) {
+    unsigned bits = 0;
+    for (int j = 0; j < 16 && q0 + j < L; j++) bits |= (kept[g0 + q0 + j] ? 1u : 0u) << j;
+    return bits;
+}
+__global__ void __launch_bounds__(1024) kept_scan_kernel(int contig0, const int64_t* __restrict__ col_base,
+                                                         const int32_t* __restrict__ contig_len,
+                                                         const uint8_t* __restrict__ kept, unsigned int* __restrict__ total,
+                                                         int64_t capacity, int32_t* __restrict__ out, int64_t* __restrict__ hdr) {
     __shared__ int s_warp[32];
     __shared__ int s_total;
+    __shared__ unsigned s_start;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    int n = 0;  // kept columns before this round (same value in every thread)
+    const int c = contig0 + blockIdx.x;
+    const int L = contig_len[c];
+    const int64_t g0 = col_base[c];
+    int cnt_all = 0;
+    for (int r0 = 0; r0 < L; r0 += 1024 * 16) cnt_all += __popc(rf_kept_bits(kept, g0, L, r0 + 16 * tid));
+    cnt_all = hs_warp_incl_scan(cnt_all, lane);
+    if (lane == 31) s_warp[wid] = cnt_all;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < 32; w++) t += s_warp[w];
+        s_start = atomicAdd(total, (unsigned)t);
+        hdr[2 * blockIdx.x] = s_start;
+        hdr[2 * blockIdx.x + 1] = t;
+    }
+    __syncthreads();
+    int64_t n = s_start;  // list position of the next kept column (same value in every thread)
     for (int r0 = 0; r0 < L; r0 += 1024 * 16) {
         const int q0 = r0 + 16 * tid;
-        uint32_t w[4] = {0, 0, 0, 0};
-        if (q0 + 16 <= L) {  // d_kept is its own cudaMallocAsync block: 16-byte aligned
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(kept + q0));
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        } else {
-            for (int j = 0; q0 + j < L && j < 16; j++) w[j >> 2] |= (kept[q0 + j] ? 1u : 0u) << (8 * (j & 3));
-        }
-        unsigned bits = 0;  // bit j = column q0 + j is kept
-#pragma unroll
-        for (int j = 0; j < 16; j++) bits |= (((w[j >> 2] >> (8 * (j & 3))) & 0xffu) ? 1u : 0u) << j;
+        unsigned bits = rf_kept_bits(kept, g0, L, q0);
         const int cnt = __popc(bits);
         const int incl = hs_warp_incl_scan(cnt, lane);
+        __syncthreads();
         if (lane == 31) s_warp[wid] = incl;
         __syncthreads();
         if (wid == 0) {
@@ -494,7 +631,7 @@ __global__ void __launch_bounds__(1024) kept_scan_kernel(int L, const uint8_t* _
             if (lane == 31) s_total = wi;
         }
         __syncthreads();
-        int i = n + s_warp[wid] + incl - cnt;
+        int64_t i = n + s_warp[wid] + incl - cnt;
         while (bits) {
             const int j = __ffs(bits) - 1;
             bits &= bits - 1;
@@ -502,9 +639,7 @@ __global__ void __launch_bounds__(1024) kept_scan_kernel(int L, const uint8_t* _
             i++;
         }
         n += s_total;
-        __syncthreads();
     }
-    if (tid == 0) *n_out = n;
 }
 
 __global__ void set_inlist_kernel(int n, const int32_t* __restrict__ pos, int64_t g0, uint8_t* __restrict__ flags,
