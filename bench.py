@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """Benchmark of the hot path on B200 (contract: see the task statement / DESIGN.md section "Measurement").
 
-A step = one pass of the pileup path (generate_msa + call_variants counting/ranking, hot loops A+B of
-SURVEY.md section 8) over one batch of synthetic input: BASELINE.json configs[1], a 5 Mb bacterial genome
-cut into 17 contig chunks (<= 300 kb), 2 strains 1 % apart, ONT-like reads (10 kb mean, 10 % error), 60x.
+A step = one pass of the per-chunk call_variants path -- generate_msa, call_variants (allele counting / ranking)
+and loops 3+4 of keep_only_robust_variants, hot loops A+B+C of SURVEY.md section 8 -- over one batch of synthetic
+input: BASELINE.json configs[1] unless --config says otherwise (a 5 Mb bacterial genome cut into 17 contig chunks
+<= 300 kb, 2 strains 1 % apart, ONT-like reads 10 kb mean, 10 % error, 60x).
 Metric: pileup windows/s, window = 2000 columns x depth, value = columns / 2000 / s.
 
-  value   inputs resident in HBM, CUDA-event timed on the library's stream (hsgpu_pileup_build +
-          hsgpu_column_rank per step)
+  value   inputs resident in HBM (reads, CIGARs, final partitions), CUDA-event timed on the library's stream:
+          hsgpu_pileup_build + hsgpu_column_rank + hsgpu_robust_filter_all per step
   e2e     the same through the C ABI from pinned HOST buffers: hsgpu_pileup_create (H2D) + build + rank +
-          D2H of the per-contig results (suspect lists, counts), every step
+          hsgpu_partitions_set (H2D) + hsgpu_robust_filter_all + D2H of the per-contig results (suspect lists,
+          snps_out, counts), every step. The final partitions (loops 1-2, sequential host C++ in
+          hairsplitter_b200/host) are an input of the C ABI and are built once outside the timed region.
   roofline / kernels   per-kernel event timing (hsgpu_profile_enable) over a second pass of the same steps
-  cpu_baseline         the reference's own generate_msa + call_variants (oracle/_ref) or the C oracle
+  cpu_baseline         the reference's own generate_msa + call_variants + keep_only_robust_variants (oracle/_ref,
+                       all four loops) or, when the compiled reference did not travel, the C oracle
                        port, on the host cores, on a bounded sample of the same workload
 
 `--impl reference` times only the CPU reference arm and prints the same JSON shape.
@@ -45,6 +49,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-chunks", type=int, default=0, help="chunks in the CPU baseline sample (0 = auto)")
     ap.add_argument("--e2e-lanes", type=int, default=2, help="hsgpu contexts (host threads) of the e2e path")
     ap.add_argument("--e2e-groups", type=int, default=1, help="groups of contig chunks the e2e path cuts a step's batch into")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: ONE workload (same seed on every rank) dealt "
+                    "to the ranks by sharding.lpt_assign; value = all columns / max-over-ranks time")
+    ap.add_argument("--no-stages", action="store_true", help="skip the side stages (realign is always measured)")
     ap.add_argument("--wall-ref-runs", type=int, default=3, help="runs of the reference HS_call_variants (median reported)")
     ap.add_argument("--wall-chunks", type=int, default=0, help="chunks in the HS_call_variants wall-time stage (0 = all, -1 = skip)")
     return ap.parse_args()
@@ -106,9 +113,9 @@ def host_cores():
 
 
 def cpu_reference_rate(chunks, n_threads, repeat=1):
-    """generate_msa + call_variants of the reference (oracle/_ref) -- or the C oracle port when the
-    compiled reference did not travel -- over `chunks`, one chunk per thread at a time.
-    Returns (windows/s, kind, seconds)."""
+    """generate_msa + call_variants + keep_only_robust_variants of the reference (oracle/_ref) -- or the C oracle
+    port of the first two when the compiled reference did not travel -- over `chunks`, one chunk per thread at a
+    time. Returns (windows/s, kind, seconds)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle
     use_ref = pyoracle.ref_available()
@@ -127,6 +134,7 @@ def cpu_reference_rate(chunks, n_threads, repeat=1):
         def work(a):
             h = L.hsref_cv_create(a[0], a[1], a[2], a[3], a[4].ctypes.data, a[5].ctypes.data)  # generate_msa
             L.hsref_cv_call_variants(h, -1.0, 0.33)                                             # call_variants
+            L.hsref_cv_robust(h, -1.0)                                                          # keep_only_robust_variants
             L.hsref_cv_destroy(h)
     else:
         O = pyoracle.Oracle()
@@ -169,64 +177,104 @@ def make_realign_pairs(rng, contig, n_pairs, qlen=1536, slack=0.15, err=0.10):
     return [row.tobytes() for row in q], [row.tobytes() for row in t]
 
 
-def run_stages(ctx, stream, chunks, args, hbm_peak):
-    """realignment (edlib-compatible Myers kernel) and the partition x column contingency filter, each with
-    its own CPU baseline; both verified against the reference inside the run when oracle/_ref is present."""
+def load_peaks():
+    """MEASURED_PEAKS.json (driver-written: HBM, bf16) and profiles/peaks_int.json (scripts/peaks_int.py: INT32 pipes,
+    int8 tensor) -- measured denominators for every roofline fraction"""
+    peaks, ipeaks = {}, {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    try:
+        ipeaks = json.load(open(os.path.join(ROOT, "profiles", "peaks_int.json")))
+    except Exception:
+        pass
+    return peaks, ipeaks
+
+
+def run_realign(ctx, stream, chunks, args, verify):
+    """realignment (edlib-compatible Myers kernel): HW + PATH on the two shapes SURVEY.md 8d names -- 1536-base read
+    chunks on 1766-base windows, and the in-pipeline 300 x 2300 shape -- each with its CPU baseline and parity check
+    against the vendored edlib when `verify` (rank 0 of a 1-GPU run)."""
     import torch
     from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    cores = host_cores()
+    rng = np.random.default_rng(12345)
+    _, ipeaks = load_peaks()
+    out = {}
+    for tag, qlen, slack, n_full in (("chunk_1536x1766", 1536, 0.15, 20000), ("pipeline_300x2300", 300, 6.6667, 60000)):
+        n_pairs = max(64, int(n_full * min(1.0, args.scale * 4)))
+        qs, ts = make_realign_pairs(rng, chunks[0].contig, n_pairs, qlen=qlen, slack=slack)
+        cells = float(sum(len(q) * len(t) for q, t in zip(qs, ts)))
+        ctx.edlib_align_batch(qs[:256], ts[:256], k=-1, mode=2, task=2)  # warm-up (allocations, code load)
+        ctx.edlib_align_batch(qs, ts, k=-1, mode=2, task=2)
+        ctx.profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res, ends, starts, aln = ctx.edlib_align_batch(qs, ts, k=-1, mode=2, task=2)
+        e1.record(stream)
+        ctx.sync()
+        prof = ctx.profile_report()
+        ctx.profile(False)
+        ms_e2e = e0.elapsed_time(e1)
+        ms_kernel = sum(v[1] for kname, v in prof.items() if kname.startswith("edlib_"))
+        r = {
+            "shape": f"{n_pairs} pairs, query {qlen} x target {len(ts[0])}, HW + PATH (10% error)",
+            "kernel_gcups": cells / (ms_kernel * 1e-3) / 1e9, "e2e_gcups": cells / (ms_e2e * 1e-3) / 1e9,
+            "kernel_ms": ms_kernel, "e2e_ms": ms_e2e,
+            "kernels": {kname: {"launches": v[0], "ms": v[1]} for kname, v in prof.items()},
+        }
+        # useful logic work: one Myers column step of a 32-row word is ~19 32-bit logic/add operations (SURVEY.md 8d:
+        # 14-22 per word step, edlib.cpp:411-446); HW + PATH sweeps the matrix three times (end, start, path)
+        useful_ops = cells / 32.0 * 19.0 * 3.0
+        if ipeaks.get("int32_peak_tops"):
+            r["useful_int32_tops"] = useful_ops / (ms_kernel * 1e-3) / 1e12
+            r["frac_of_int32_peak"] = r["useful_int32_tops"] / ipeaks["int32_peak_tops"]
+            r["frac_of_alu_pipe_peak"] = r["useful_int32_tops"] / ipeaks["int32_alu_pipe_tops"]
+            r["int32_peak_source"] = "profiles/peaks_int.json (lop3+imad chains: both integer pipes; lop3 alone: ALU pipe)"
+        if verify:
+            n_cpu = min(n_pairs, 250 * cores)
+            t0 = time.perf_counter()
+            if pyoracle.RefEdlib.available():
+                kind = "reference"
+                with ThreadPoolExecutor(max_workers=cores) as ex:
+                    cpu = list(ex.map(lambda i: pyoracle.RefEdlib.align(qs[i], ts[i], -1, 2, 2), range(n_cpu)))
+            else:
+                kind = "port"
+                O = pyoracle.Oracle()
+                n_cpu = min(n_cpu, 8 * cores)
+                with ThreadPoolExecutor(max_workers=cores) as ex:
+                    cpu = list(ex.map(lambda i: O.edlib_align(qs[i], ts[i], -1, 2, 2), range(n_cpu)))
+            dt = time.perf_counter() - t0
+            for i in range(n_cpu):  # parity of the timed results
+                rr = res[i]
+                assert int(rr["edit_distance"]) == cpu[i]["edit_distance"]
+                lo, nl = int(rr["loc_off"]), int(rr["n_locations"])
+                assert np.array_equal(ends[lo:lo + nl], cpu[i]["end_locations"])
+                assert np.array_equal(starts[lo:lo + nl], cpu[i]["start_locations"])
+                ao, al = int(rr["aln_off"]), int(rr["alignment_length"])
+                assert np.array_equal(aln[ao:ao + al], cpu[i]["alignment"])
+            cpu_cells = float(sum(len(qs[i]) * len(ts[i]) for i in range(n_cpu)))
+            r["cpu_baseline"] = {"value": cpu_cells / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
+                                 "sample": f"first {n_cpu} pairs, edlibAlign HW+PATH, one pair per thread at a time",
+                                 "verified_pairs": n_cpu}
+        r["cells"] = cells
+        out[tag] = r
+    out["metric"] = "realign_gcups"
+    out["unit"] = "GCUPS (|query| x |target| cells per pair, full matrix, counted once)"
+    return out
+
+
+def run_stages(ctx, stream, chunks, args, hbm_peak):
+    """the partition x column contingency filter on one chunk against the reference's own snps_out, and the read x read
+    counts; both verified against the reference inside the run when oracle/_ref is present."""
+    import torch
     from hairsplitter_b200 import api
     from oracle import pyoracle
     out = {}
     cores = host_cores()
     rng = np.random.default_rng(12345)
-
-    # ---- realign: HW + PATH, 1536-base read chunks on 1766-base windows ----
-    n_pairs = max(64, int(20000 * min(1.0, args.scale * 4)))
-    qs, ts = make_realign_pairs(rng, chunks[0].contig, n_pairs)
-    cells = float(sum(len(q) * len(t) for q, t in zip(qs, ts)))
-    ctx.edlib_align_batch(qs[:256], ts[:256], k=-1, mode=2, task=2)  # warm-up (allocations, code load)
-    ctx.profile(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    res, ends, starts, aln = ctx.edlib_align_batch(qs, ts, k=-1, mode=2, task=2)
-    e1.record(stream)
-    ctx.sync()
-    prof = ctx.profile_report()
-    ctx.profile(False)
-    ms_e2e = e0.elapsed_time(e1)
-    ms_kernel = sum(v[1] for kname, v in prof.items() if kname.startswith("edlib_"))
-    n_cpu = min(n_pairs, 250 * cores)
-    t0 = time.perf_counter()
-    if pyoracle.RefEdlib.available():
-        kind = "reference"
-        with ThreadPoolExecutor(max_workers=cores) as ex:
-            cpu = list(ex.map(lambda i: pyoracle.RefEdlib.align(qs[i], ts[i], -1, 2, 2), range(n_cpu)))
-    else:
-        kind = "port"
-        O = pyoracle.Oracle()
-        n_cpu = min(n_cpu, 8 * cores)
-        with ThreadPoolExecutor(max_workers=cores) as ex:
-            cpu = list(ex.map(lambda i: O.edlib_align(qs[i], ts[i], -1, 2, 2), range(n_cpu)))
-    dt = time.perf_counter() - t0
-    for i in range(n_cpu):  # parity of the timed results
-        r = res[i]
-        assert int(r["edit_distance"]) == cpu[i]["edit_distance"]
-        lo, nl = int(r["loc_off"]), int(r["n_locations"])
-        assert np.array_equal(ends[lo:lo + nl], cpu[i]["end_locations"])
-        assert np.array_equal(starts[lo:lo + nl], cpu[i]["start_locations"])
-        ao, al = int(r["aln_off"]), int(r["alignment_length"])
-        assert np.array_equal(aln[ao:ao + al], cpu[i]["alignment"])
-    cpu_cells = float(sum(len(qs[i]) * len(ts[i]) for i in range(n_cpu)))
-    out["realign"] = {
-        "metric": "realign_gcups", "unit": "GCUPS (|query| x |target| cells per pair, full matrix, counted once)",
-        "shape": f"{n_pairs} pairs, query 1536 (read chunk, 10% error) x target 1766 (window + 15% slack), HW + PATH",
-        "kernel_gcups": cells / (ms_kernel * 1e-3) / 1e9, "e2e_gcups": cells / (ms_e2e * 1e-3) / 1e9,
-        "kernel_ms": ms_kernel, "e2e_ms": ms_e2e,
-        "kernels": {kname: {"launches": v[0], "ms": v[1]} for kname, v in prof.items()},
-        "cpu_baseline": {"value": cpu_cells / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
-                         "sample": f"first {n_cpu} pairs, edlibAlign HW+PATH, one pair per thread at a time",
-                         "verified_pairs": n_cpu},
-    }
 
     # ---- contingency: loops 3+4 of keep_only_robust_variants on one 300 kb chunk ----
     cb = chunks[0]
@@ -292,14 +340,15 @@ def run_stages(ctx, stream, chunks, args, hbm_peak):
         summ = pu.column_summary(ci)
         cols.append((cb.n_reads, off, idx, code, summ["ref_base"][pos], summ["second_base"][pos]))
     pu.close()
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    # int8 tensor peak: MEASURED_PEAKS.json has no int8 figure; the nominal dense int8 rate of the part is
-    # 4.5 POP/s = 2x bf16, so the measured-derived denominator is 2x the measured cuBLAS bf16 burst figure
-    int8_peak_tops = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+    peaks, ipeaks = load_peaks()
+    # int8 tensor peak: measured with cuBLASLt (torch._int_mm 8192^3) by scripts/peaks_int.py; only if that file is
+    # missing, 2 x the measured bf16 burst figure (nominal dense int8 is 2 x bf16)
+    if ipeaks.get("int8_peak_tops"):
+        int8_peak_tops = float(ipeaks["int8_peak_tops"])
+        int8_src = "measured: cuBLASLt int8 GEMM 8192^3 (profiles/peaks_int.json)"
+    else:
+        int8_peak_tops = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        int8_src = "assumed 2 x measured bf16 burst (profiles/peaks_int.json missing)"
     pairs = {}
     for tag, flags in (("band", 0), ("dense", api.PAIRS_DENSE)):
         P = api.Pairs(ctx, cols, flags)
@@ -351,7 +400,7 @@ def run_stages(ctx, stream, chunks, args, hbm_peak):
         "shape": f"{len(cols)} chunks, {sum(c[0] for c in cols)} reads, {n_snps} SNP columns, "
                  f"{sum(int(c[1][-1]) for c in cols)} cells",
         "int8_peak_tops": int8_peak_tops,
-        "int8_peak_source": "2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json); nominal dense int8 is 4500",
+        "int8_peak_source": int8_src,
         **pairs,
     }
     return out
@@ -466,14 +515,15 @@ def run_call_variants_wall(chunks, args):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
-def run_e2e(chunks, local_rank, ctx, n_lanes, n_groups, steps, warmup, barrier):
+def run_e2e(chunks, parts_per_contig, local_rank, ctx, n_lanes, n_groups, steps, warmup, barrier):
     """The way a caller drives the library from host buffers: every step's batch (optionally cut into `n_groups`
     groups of contig chunks) goes through one of `n_lanes` hsgpu contexts (one per host thread, as the header
     prescribes, like the reference's OpenMP loop over contigs), steps dealt to the lanes in turn. The library lets
     one context upload at a time, so the kernels of the batch that has its data overlap the upload of the next
-    one (double buffering); CIGARs travel in the 8-bit form; every batch's results (suspect lists, depth
-    numerators) come back through hsgpu_suspects_all. Every step pays its own H2D and D2H; inputs sit in pinned
-    host memory. Returns the device time of the slowest lane and the host wall clock over `steps` steps."""
+    one (double buffering); CIGARs travel in the 8-bit form; the final partitions go up through
+    hsgpu_partitions_set; every batch's results (snps_out, suspect lists, depth numerators) come back through
+    hsgpu_robust_filter_all and hsgpu_suspects_all. Every step pays its own H2D and D2H; read / CIGAR inputs sit
+    in pinned host memory. Returns the device time of the slowest lane and the host wall clock over `steps` steps."""
     import threading
     import torch
     from hairsplitter_b200 import api
@@ -481,7 +531,9 @@ def run_e2e(chunks, local_rank, ctx, n_lanes, n_groups, steps, warmup, barrier):
     n_lanes = max(1, n_lanes)
     groups = []
     keep = []
+    group_parts = []
     for g in range(n_groups):
+        group_parts.append(api.Pileup.prepare_partitions(parts_per_contig[g::n_groups]))
         pb = api.PackedBatch(chunks[g::n_groups]).use_cigar8()
         for name in ("contig_len", "contig_bases", "contig_word_off", "contig_read_off", "read_bases", "read_word_off",
                      "read_len", "cigar8", "cigar8_off", "read_start", "read_strand"):
@@ -492,7 +544,8 @@ def run_e2e(chunks, local_rank, ctx, n_lanes, n_groups, steps, warmup, barrier):
             keep.append(t)
             setattr(pb, name, arr)
         groups.append(pb)
-    h2d_bytes = sum(int(pb.input_bytes) for pb in groups)
+    h2d_bytes = sum(int(pb.input_bytes) for pb in groups) + sum(int(gp[2]) for gp in group_parts)
+    e2e_kept = [0] * n_groups
     lanes = [ctx] + [api.Context(local_rank) for _ in range(n_lanes - 1)]
     lane_streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local_rank)) for c in lanes]
     e2e_out = [0] * n_groups
@@ -508,13 +561,16 @@ def run_e2e(chunks, local_rank, ctx, n_lanes, n_groups, steps, warmup, barrier):
         t2 = time.perf_counter()
         p.column_rank()
         t3 = time.perf_counter()
+        p.partitions_set(prepared=group_parts[g])   # H2D of the final partitions
+        kept, koff = p.robust_filter_all(int(groups[g].contig_len.sum()))   # loops 3+4 + D2H of snps_out
         pos, au, off, ds = p.suspects_all()      # D2H of the call_variants results
         t4 = time.perf_counter()
         p.close()
         if trace is not None:
             trace.append((lane, g, t0, t1, t2, t3, t4, time.perf_counter()))
-        e2e_out[g] = pos.nbytes + au.nbytes + off.nbytes + ds.nbytes
+        e2e_out[g] = pos.nbytes + au.nbytes + off.nbytes + ds.nbytes + kept.nbytes + koff.nbytes
         e2e_sus[g] = int(off[-1])
+        e2e_kept[g] = int(koff[-1])
 
     def e2e_steps(n_steps):
         # work items = (step, group) in order, dealt round-robin to the lanes: with one group per step and two
@@ -557,7 +613,7 @@ def run_e2e(chunks, local_rank, ctx, n_lanes, n_groups, steps, warmup, barrier):
             print("  lane %d group %2d: create %.3f-%.3f build -%.3f rank -%.3f suspects_all -%.3f close -%.3f" %
                   ((r[0], r[1]) + tuple((x - z) * 1e3 for x in r[2:])), file=sys.stderr)
     return {"device_ms": e2e_ms, "wall_ms": t_e2e, "h2d_bytes": h2d_bytes, "d2h_bytes": d2h_bytes,
-            "suspects": sum(e2e_sus), "groups": n_groups, "lanes": n_lanes}
+            "suspects": sum(e2e_sus), "kept": sum(e2e_kept), "groups": n_groups, "lanes": n_lanes}
 
 
 def workload_description(info, chunks):
@@ -583,7 +639,7 @@ def run_reference(args, rank, world):
         cols += sum(c.length for c in chunks)
     value = cols / WINDOW / t_total
     sample = (f"{len(chunks)} of the workload's chunks ({sum(c.length for c in chunks)} columns, "
-              f"{sum(c.n_reads for c in chunks)} reads) per step, generate_msa + call_variants per chunk, "
+              f"{sum(c.n_reads for c in chunks)} reads) per step, generate_msa + call_variants + keep_only_robust_variants per chunk, "
               f"one chunk per thread")
     line = {
         "impl": "reference", "metric": "pileup_windows_per_s", "value": value, "unit": "windows/s", "n_gpus": args.gpus,
@@ -622,21 +678,49 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- workload: every rank gets its own genome of the configured shape (weak scaling) ----
+    # ---- workload ----
+    from hairsplitter_b200 import sharding
     t_gen = time.perf_counter()
-    chunks, info = synth.make_config(args.config, scale=args.scale, seed=args.config + 1000 * rank)
+    workers = max(1, host_cores() // max(world, 1))
+    lpt = None
+    if args.strong:
+        # ONE workload, the same on every rank, dealt out chunk by chunk: heaviest first onto the least loaded rank
+        all_chunks, info = synth.make_config(args.config, scale=args.scale, seed=args.config, workers=workers)
+        weights = [sharding.chunk_weight(c) for c in all_chunks]
+        bins = sharding.lpt_assign(weights, world)
+        loads = [sum(weights[i] for i in b) for b in bins]
+        lpt = {"chunks_total": len(all_chunks), "chunks_per_rank": [len(b) for b in bins],
+               "imbalance_max_over_mean": max(loads) / (sum(loads) / len(loads))}
+        chunks = [all_chunks[i] for i in bins[rank]]
+        del all_chunks
+    else:
+        # every rank gets its own genome of the configured shape (weak scaling)
+        chunks, info = synth.make_config(args.config, scale=args.scale, seed=args.config + 1000 * rank, workers=workers)
     packed = api.PackedBatch(chunks)
     t_gen = time.perf_counter() - t_gen
     n_cols = int(packed.contig_len.sum())
     ctx = api.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 
+    # ---- the final partitions of every chunk (loops 1-2 of keep_only_robust_variants: sequential host C++, an INPUT
+    # of the C ABI's filter stage): built once from a first build + rank, outside every timed region ----
+    pu = api.Pileup(ctx, packed)
+    pu.build()
+    pu.column_rank()
+    t_parts = time.perf_counter()
+    parts_per_contig = [pu.host_partitions(ci) for ci in range(len(chunks))]
+    t_parts = time.perf_counter() - t_parts
+    prepared = api.Pileup.prepare_partitions(parts_per_contig)
+    n_parts = sum(len(x) for x in parts_per_contig)
+    pu.partitions_set(prepared=prepared)
+    kept_cap = n_cols
+
     def step(pu):
-        pu.build()
-        pu.column_rank()
+        pu.build()                                 # generate_msa
+        pu.column_rank()                           # call_variants
+        return pu.robust_filter_all(kept_cap)      # loops 3+4 of keep_only_robust_variants -> snps_out
 
     # ---- value: inputs resident in HBM ----
-    pu = api.Pileup(ctx, packed)
     for _ in range(max(args.warmup, 0)):
         step(pu)
     ctx.sync()
@@ -647,7 +731,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
-        step(pu)
+        kept, kept_off = step(pu)
     ev1.record(stream)
     ctx.sync()
     barrier()
@@ -657,7 +741,8 @@ def main():
     cells, dist_sum, alen = pu.stats()
     n_sus, depth_sum = pu.column_counts()
     assert int(depth_sum.sum()) == int(cells.sum()), "depth numerator must equal the number of pileup cells"
-    assert int(n_sus.sum()) > 0
+    assert int(n_sus.sum()) > 0 or n_cols < 100000
+    n_kept = int(kept_off[-1])
 
     # ---- per-kernel timing over a second pass of the same steps ----
     ctx.profile(True)
@@ -666,19 +751,19 @@ def main():
     prof = ctx.profile_report()
     ctx.profile(False)
     n_cells = int(cells.sum())
-    tile_entries = None
+    finfo = pu.filter_info()
     alg_bytes = {
-        # 1 B code out + 2-bit read base in + 2-bit contig base in per cell, 4 B per CIGAR op, ~48 B metadata per read
-        "pileup_kernel": n_cells * 1.0 + packed.read_bases.nbytes + n_cells * 0.25 + packed.cigar.nbytes
+        # 1 B code out + 2-bit read base + 2-bit contig base per cell, ~0.1 B of CIGAR per cell (the ops
+        # as the byte-sized form the kernel reads), 48 B of metadata per read
+        "pileup_kernel": n_cells * 1.0 + packed.read_bases.nbytes + n_cells * 0.25 + float(pu.cigar_bytes())
         + packed.n_reads * 48,
         # 1 B code in per cell (+ tile padding not counted), 4 B per (tile, read) index entry, 19 B summary out per column
         "column_rank_kernel": n_cells * 1.0 + (n_cells / 128.0 + packed.n_reads) * 4 + n_cols * 19.0,
+        # the cells of the active columns: 1 B code + 2 B read index each, one state byte per cell and
+        # partition that holds the read, 1 B kept flag out per column
+        "robust_filter_kernel": finfo["active_cells"] * 3.0 + finfo["active_cells"] * finfo["parts_per_cell"] + n_cols * 1.0,
     }
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks, ipeaks = load_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     traffic = {}
@@ -697,43 +782,71 @@ def main():
     dom = kernels[0] if kernels else None
     roofline = None
     if dom and "achieved_gbs" in dom:
+        tr = traffic.get(dom["name"])
         roofline = {"kernel": dom["name"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": hbm_peak,
                     "unit": "GB/s", "frac": dom["achieved_gbs"] / hbm_peak, "peak_source": peak_src,
-                    "traffic": traffic.get(dom["name"]),
+                    "traffic": tr.get("bytes") if isinstance(tr, dict) else tr,
+                    "traffic_source": (tr.get("source") if isinstance(tr, dict) else
+                                       "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)") if tr else None,
                     "share_of_step": dom["ms_per_step"] / sum(k["ms_per_step"] for k in kernels),
                     "note": "per-launch duration from CUDA events on the launching stream, second pass of the same steps"}
     pu.close()
 
     # ---- e2e: host buffers -> C ABI -> host results, every step ----
-    e2e = run_e2e(chunks, local_rank, ctx, args.e2e_lanes, args.e2e_groups, args.steps, args.warmup, barrier)
-    assert e2e["suspects"] == int(n_sus.sum()), "the grouped e2e path must find the same suspect columns"
+    e2e = run_e2e(chunks, parts_per_contig, local_rank, ctx, args.e2e_lanes, args.e2e_groups, args.steps, args.warmup, barrier)
+    assert e2e["suspects"] == int(n_sus.sum()), "the e2e path must find the same suspect columns"
+    assert e2e["kept"] == n_kept, "the e2e path must keep the same columns"
     e2e_ms, t_e2e, h2d_bytes, d2h_bytes = e2e["device_ms"], e2e["wall_ms"], e2e["h2d_bytes"], e2e["d2h_bytes"]
     n_groups, n_lanes = e2e["groups"], e2e["lanes"]
-    # the floor of the e2e step on this box: the same bytes from pinned memory with nothing else going on
+    # the floor of the e2e step on this box: the same bytes from pinned memory -- first with every rank copying at
+    # the same moment (what the ranks of a multi-GPU run do to the host's memory system and PCIe uplinks), then alone
     src = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
     dst = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
     dst.copy_(src, non_blocking=True)
     torch.cuda.synchronize()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record()
-    for _ in range(3):
-        dst.copy_(src, non_blocking=True)
-    c1.record()
-    torch.cuda.synchronize()
-    h2d_floor_ms = c0.elapsed_time(c1) / 3
+
+    def copy_floor():
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        return c0.elapsed_time(c1) / 3
+
+    barrier()
+    h2d_floor_concurrent_ms = copy_floor()
+    barrier()
+    h2d_floor_ms = h2d_floor_concurrent_ms
+    if world > 1:
+        for turn in range(world):  # one rank at a time
+            if turn == rank:
+                h2d_floor_ms = copy_floor()
+            barrier()
     del src, dst
 
+    # ---- realignment: measured on every rank (BASELINE metric: realign GCUPS at 1/2/4/8 GPUs) ----
+    realign = run_realign(ctx, stream, chunks, args, verify=(rank == 0 and world == 1))
     # ---- the other stages of the hot path (reported beside the headline, rank 0 / 1 GPU only) ----
-    stages = {}
-    if rank == 0 and world == 1:
-        stages = run_stages(ctx, stream, chunks, args, hbm_peak)
+    stages = {"realign": realign}
+    if rank == 0 and world == 1 and not args.no_stages:
+        stages.update(run_stages(ctx, stream, chunks, args, hbm_peak))
         if args.wall_chunks >= 0:
+            args.links = info.get("links", [])
             stages["call_variants_wall"] = run_call_variants_wall(chunks, args)
 
     # ---- max over ranks of the time, sum over ranks of the columns (hairsplitter_b200/sharding.py) ----
-    from hairsplitter_b200 import sharding
     ms_total, total_cols = sharding.reduce_step(ms_total, float(n_cols), device="cuda")
     e2e_ms, _ = sharding.reduce_step(e2e_ms, 0.0, device="cuda")
+    h2d_floor_concurrent_ms, _ = sharding.reduce_step(h2d_floor_concurrent_ms, 0.0, device="cuda")
+    realign_line = {}
+    for tag in ("chunk_1536x1766", "pipeline_300x2300"):
+        k_ms, cells_all = sharding.reduce_step(realign[tag]["kernel_ms"], realign[tag]["cells"], device="cuda")
+        e_ms, _ = sharding.reduce_step(realign[tag]["e2e_ms"], 0.0, device="cuda")
+        realign_line[tag] = {"kernel_gcups": cells_all / (k_ms * 1e-3) / 1e9, "e2e_gcups": cells_all / (e_ms * 1e-3) / 1e9}
+        for key in ("frac_of_int32_peak", "frac_of_alu_pipe_peak"):
+            if key in realign[tag]:
+                realign_line[tag][key + "_rank0"] = realign[tag][key]
 
     if rank == 0:
         value = total_cols * args.steps / WINDOW / (ms_total * 1e-3)
@@ -741,30 +854,41 @@ def main():
         line = {
             "metric": "pileup_windows_per_s", "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
             "config": {
-                "workload": workload_description(info, chunks) if args.scale == 1.0 else f"configs[{args.config - 1}] scaled x{args.scale}",
+                "workload": workload_description(info, chunks) if args.scale == 1.0 else
+                            f"BASELINE configs[{args.config - 1}] scaled x{args.scale}: {info['description']}",
                 "window": "2000 columns x depth", "columns_per_gpu": n_cols, "reads_per_gpu": packed.n_reads,
-                "cells_per_gpu": n_cells, "step": "hsgpu_pileup_build + hsgpu_column_rank (generate_msa + call_variants)",
+                "cells_per_gpu": n_cells, "partitions_per_gpu": n_parts, "suspects_per_gpu": int(n_sus.sum()),
+                "snps_out_per_gpu": n_kept,
+                "step": "hsgpu_pileup_build + hsgpu_column_rank + hsgpu_robust_filter_all (generate_msa + call_variants "
+                        "+ loops 3-4 of keep_only_robust_variants on resident partitions)",
                 "l2": "inputs + pileup per step (%.0f MB) exceed the 126 MB L2; no explicit flush" %
                       ((packed.input_bytes + n_cells) / 1e6),
-                "sharding": "independent contig chunks per rank, no data-path collective",
-                "generation_s": round(t_gen, 1),
+                "sharding": ("one workload dealt to the ranks by longest-processing-time-first, no data-path collective"
+                             if args.strong else "independent contig chunks per rank, no data-path collective"),
+                "generation_s": round(t_gen, 1), "host_partitions_s": round(t_parts, 2),
             },
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "windows/s", "ms_per_step": e2e_ms / max(args.steps, 1),
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "host_wall_ms_per_step": t_e2e / max(args.steps, 1),
                     "h2d_copy_floor_ms": h2d_floor_ms, "h2d_gbs": h2d_bytes / (h2d_floor_ms * 1e-3) / 1e9,
+                    "h2d_copy_floor_all_ranks_at_once_ms": h2d_floor_concurrent_ms,
+                    "h2d_gbs_per_gpu_all_ranks_at_once": h2d_bytes / (h2d_floor_concurrent_ms * 1e-3) / 1e9,
                     "path": f"steps dealt in turn to {n_lanes} hsgpu contexts (one host thread each), {n_groups} group(s) of "
                             "chunks per step: hsgpu_pileup_create(pinned host buffers, 8-bit CIGAR; one upload at a "
                             "time, so the upload of step k+1 overlaps the kernels of step k) + build + column_rank + "
-                            "suspects_all; every step pays its own H2D and D2H"},
+                            "partitions_set + robust_filter_all + suspects_all; every step pays its own H2D and D2H"},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "realign_gcups": realign_line,
             "kernels": kernels,
             "stages": stages,
         }
+        if lpt is not None:
+            line["strong_scaling"] = lpt
         if world == 1:
             cores = host_cores()
             n_sample = args.cpu_sample_chunks or max(1, min(cores, len(chunks)))  # every host core gets a chunk
@@ -774,7 +898,7 @@ def main():
             line["cpu_baseline"] = {
                 "value": rate, "unit": "windows/s", "cores": n_threads, "kind": kind, "seconds": round(dt, 2),
                 "sample": f"first {len(sample)} chunks of the workload ({sum(c.length for c in sample)} columns), "
-                          f"generate_msa + call_variants, one chunk per thread",
+                          f"generate_msa + call_variants + keep_only_robust_variants, one chunk per thread",
             }
         print(json.dumps(line), flush=True)
     ctx.close()

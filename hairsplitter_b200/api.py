@@ -81,6 +81,7 @@ EXPORTS = [
     "hsgpu_pileup_create", "hsgpu_pileup_destroy", "hsgpu_pileup_build", "hsgpu_pileup_stats", "hsgpu_mean_distance",
     "hsgpu_pileup_read_ends", "hsgpu_pileup_export", "hsgpu_pileup_extract_columns", "hsgpu_column_rank",
     "hsgpu_column_counts", "hsgpu_suspects", "hsgpu_suspects_all", "hsgpu_column_summary", "hsgpu_partition_tables", "hsgpu_robust_filter",
+    "hsgpu_partitions_set", "hsgpu_robust_filter_all", "hsgpu_pileup_info",
     "hsgpu_read_pair_counts", "hsgpu_pairs_create", "hsgpu_pairs_compute", "hsgpu_pairs_fetch", "hsgpu_pairs_info",
     "hsgpu_pairs_destroy", "hsgpu_graph_create", "hsgpu_graph_build", "hsgpu_graph_adjacency", "hsgpu_graph_whispers",
     "hsgpu_graph_destroy", "hsgpu_edlib_align_batch", "hsgpu_edlibAlign", "hsgpu_edlibFreeAlignResult",
@@ -139,6 +140,9 @@ def load():
     L.hsgpu_column_summary.argtypes = [vp, i32, vp, vp, vp, vp]
     L.hsgpu_partition_tables.argtypes = [vp, i32, C.POINTER(Partitions), i32, vp, vp]
     L.hsgpu_robust_filter.argtypes = [vp, i32, C.POINTER(Partitions), i32, vp, i32, vp, vp]
+    L.hsgpu_pileup_info.argtypes = [vp, vp]
+    L.hsgpu_partitions_set.argtypes = [vp, vp]
+    L.hsgpu_robust_filter_all.argtypes = [vp, i64, vp, vp]
     L.hsgpu_read_pair_counts.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.hsgpu_pairs_create.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, C.POINTER(vp)]
     L.hsgpu_pairs_compute.argtypes = [vp]
@@ -329,6 +333,44 @@ def make_partitions(parts):
     s.more = mo.ctypes.data
     s.less = le.ctypes.data
     return s, (off, idx, st, mo, le)
+
+
+class HostLogic:
+    """libhshost.so: the sequential host side of keep_only_robust_variants (loops 1-2: greedy partition building
+    and merging, reference src/call_variants.cpp:590-708 + src/Partition.cpp), the C++ code HS_call_variants runs
+    between hsgpu_column_rank and hsgpu_robust_filter_all. Product code (hairsplitter_b200/host), not the oracle."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(_HERE, "libhshost.so"))
+            L.hshost_build_partitions.restype = C.c_void_p
+            L.hshost_build_partitions.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_float]
+            L.hshost_parts_count.argtypes = [C.c_void_p]
+            L.hshost_part_size.argtypes = [C.c_void_p, C.c_int]
+            L.hshost_part_get.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+            L.hshost_parts_free.argtypes = [C.c_void_p]
+            cls._lib = L
+        return cls._lib
+
+    @classmethod
+    def build_partitions(cls, pos, off, read_idx, code, ref_base, second_base, mean_error):
+        """suspect columns (CSR over columns) -> the final partitions as a list of dicts"""
+        L = cls.lib()
+        pos, off = _a(pos, np.int32), _a(off, np.int64)
+        read_idx, code = _a(read_idx, np.uint32), _a(code, np.uint8)
+        rb, sb = _a(ref_base, np.uint8), _a(second_base, np.uint8)
+        h = L.hshost_build_partitions(int(pos.size), off.ctypes.data, read_idx.ctypes.data, code.ctypes.data,
+                                      pos.ctypes.data, rb.ctypes.data, sb.ctypes.data, float(mean_error))
+        parts = []
+        for p in range(L.hshost_parts_count(h)):
+            n = L.hshost_part_size(h, p)
+            a = [np.zeros(n, np.int32), np.zeros(n, np.int16), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(2, np.int32)]
+            L.hshost_part_get(h, p, *[x.ctypes.data for x in a])
+            parts.append(dict(read_idx=a[0], state=a[1], more=a[2], less=a[3], left=int(a[4][0]), right=int(a[4][1])))
+        L.hshost_parts_free(h)
+        return parts
 
 
 class Context:
@@ -659,6 +701,67 @@ class Pileup:
                                                        out.ctypes.data), "hsgpu_partition_tables")
         del keep
         return out
+
+    def info(self):
+        v = np.zeros(8, np.int64)
+        self.ctx.check(self.lib.hsgpu_pileup_info(self.h, v.ctypes.data), "hsgpu_pileup_info")
+        return v
+
+    def cigar_bytes(self):
+        return int(self.info()[0])
+
+    def filter_info(self):
+        v = self.info()
+        return {"active_columns": int(v[4]), "active_cells": int(v[5]), "state_bytes": int(v[6]), "kept": int(v[7]),
+                "parts_per_cell": float(v[6]) / max(float(v[5]), 1.0)}
+
+    @staticmethod
+    def prepare_partitions(parts_per_contig):
+        """the hsgpu_partitions array of a batch (parts_per_contig[c] = list of partition dicts of contig c) as
+        (ctypes array, keep-alive arrays, bytes the arrays hold): build once, hand to partitions_set as often as needed"""
+        n = len(parts_per_contig)
+        arr = (Partitions * n)()
+        keep, nbytes = [], 0
+        for c, parts in enumerate(parts_per_contig):
+            s, k = make_partitions(parts)
+            arr[c] = s
+            keep.append(k)
+            nbytes += sum(int(x.nbytes) for x in k) if len(parts) else 0
+        return arr, keep, nbytes
+
+    def partitions_set(self, parts_per_contig=None, prepared=None):
+        """uploads the final partitions of every contig; they stay on the device with the pileup"""
+        if prepared is None:
+            prepared = self.prepare_partitions(parts_per_contig)
+        assert len(prepared[0]) == int(self.packed.contig_len.shape[0])
+        self.ctx.check(self.lib.hsgpu_partitions_set(self.h, C.cast(prepared[0], C.c_void_p)), "hsgpu_partitions_set")
+
+    def robust_filter_all(self, capacity=None):
+        """loops 3+4 of keep_only_robust_variants for every contig in one launch -> (kept positions, off[n_contigs+1]).
+        Without a capacity the call is made twice (sizes first)."""
+        n = int(self.packed.contig_len.shape[0])
+        off = np.zeros(n + 1, np.int64)
+        if capacity is None:
+            rc = self.lib.hsgpu_robust_filter_all(self.h, 0, None, off.ctypes.data)
+            if rc not in (0, -4):
+                self.ctx.check(rc, "hsgpu_robust_filter_all")
+            capacity = int(off[-1])
+            if capacity == 0:
+                return np.zeros(0, np.int32), off
+        kept = np.zeros(max(int(capacity), 1), np.int32)
+        self.ctx.check(self.lib.hsgpu_robust_filter_all(self.h, int(capacity), kept.ctypes.data, off.ctypes.data),
+                       "hsgpu_robust_filter_all")
+        return kept[: int(off[-1])], off
+
+    def host_partitions(self, contig):
+        """loops 1-2 of keep_only_robust_variants on the host (libhshost.so) for one contig of a ranked pileup: what
+        HS_call_variants does between hsgpu_column_rank and hsgpu_robust_filter_all"""
+        pos, _ = self.suspects(contig)
+        off, idx, code = self.extract_columns(contig, pos)
+        summ = self.column_summary(contig)
+        _, dist, alen = self.stats()
+        md = self.mean_distance(dist[contig], alen[contig])
+        return HostLogic.build_partitions(pos, off, idx, code, summ["ref_base"][pos], summ["second_base"][pos], md)
 
     def robust_filter(self, contig, parts, suspect_pos):
         suspect_pos = _a(suspect_pos, np.int32)

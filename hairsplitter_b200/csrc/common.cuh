@@ -187,7 +187,7 @@ struct hsgpu_pileup {
     uint32_t* d_read_bases = nullptr;
     int64_t* d_read_word_off = nullptr;
     int32_t* d_read_len = nullptr;
-    uint32_t* d_cigar = nullptr;
+    uint8_t* d_cigar = nullptr;   // one byte per op: len << 2 | kind (pileup.cu)
     int64_t* d_cigar_off = nullptr;
     int32_t* d_read_start = nullptr;
     uint8_t* d_read_strand = nullptr;
@@ -233,6 +233,19 @@ struct hsgpu_pileup {
     unsigned int arena_words = 0;
     int64_t* d_tile_sus = nullptr; // accepted suspects per tile, then its exclusive scan
     bool have_col_off = false;
+
+    // partitions of the batch (hsgpu_partitions_set) and the work arrays of the robust filter (contingency.cu)
+    void* d_filter_block = nullptr;
+    void* d_fdesc = nullptr;
+    uint8_t* d_pst_t = nullptr;
+    uint32_t* d_pmask = nullptr;
+    bool have_parts = false;
+    void* d_filter_work = nullptr;
+    uint32_t* d_factive = nullptr;
+    uint8_t* d_fkept = nullptr;
+    int32_t* d_fkept_list = nullptr;
+    unsigned int* d_fcounters = nullptr;
+    int64_t* d_fhdr = nullptr;
 };
 
 int hs_resolve_max_tile_reads(hsgpu_pileup* p);

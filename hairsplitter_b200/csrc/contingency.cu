@@ -10,6 +10,7 @@
 //   pass 1  histogram of the column's codes over the partition's reads -> alternative allele = most
 //           frequent code different from ref_base, ties broken by robin_hood iteration order (rank.cuh);
 //   pass 2  the 2x2 table n11/n01/n10/n00 (+ solid variants) over reads with state +-1.
+#include <cstring>
 #include <vector>
 
 #include <atomic>
@@ -261,7 +262,8 @@ struct FilterArgs {
     const HsRankLut* lut;
     int64_t g_begin, g_end;  // global column range handled by this call
     uint32_t* active;        // compacted global ids of the active columns
-    unsigned int* counters;  // [0] active columns, [1] work cursor of robust_filter_kernel, [2] kept columns (list reservation)
+    unsigned int* counters;  // [0] active columns, [1] work cursor of robust_filter_kernel, [2] kept columns (list
+                             // reservation), [4..5] / [6..7] 64-bit: cells of the active columns / state bytes read
     uint8_t* kept;           // [n_cols]
 };
 
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs
     __shared__ uint32_t s_hist_all[RF_WARPS][HS_NCODES + 3];
     __shared__ uint8_t s_touched_all[RF_WARPS][HS_NCODES + 3];
     __shared__ int s_m_all[RF_WARPS];
+    __shared__ uint8_t s_order_deep[RF_WARPS][HS_NCODES + 3];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int32_t* const s_n = s_n_all[wid];
     uint8_t* const s_code = s_code_all[wid];
@@ -428,6 +431,7 @@ __global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs
             }
         };
         bool keep = false;
+        int n_visited = 0;  // partitions whose states were read
         for (int pb = 0; pb < d.n_parts && !keep; pb += 128) {
             // partitions pb..pb+127 that hold at least one of the column's reads
             uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
@@ -444,6 +448,7 @@ __global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs
                 while (bits && !keep) {
                     const int p = pb + 32 * w + __ffs(bits) - 1;
                     bits &= bits - 1;
+                    n_visited++;
                     // ---- pass 1: the partition's reads on this column. The column's own majority code is counted
                     // with ballots (its rows with state +1 / -1 are n11 / n01, :893-949), every other code goes
                     // through the warp's histogram ----
@@ -508,7 +513,6 @@ __global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs
                                     if (lane == 0) {
                                         uint8_t order[HS_NCODES + 1];
                                         int mo = 0;
-                                        bool ref_in = false;
                                         if (nref > 0) s_hist[ref - HS_CODE0] = (uint32_t)nref;
                                         for (int i = 0; i < ncell; i++) {
                                             if (!s_st[i]) continue;
@@ -516,7 +520,6 @@ __global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs
                                             bool seen = false;
                                             for (int k = 0; k < mo; k++) seen |= order[k] == idx;
                                             if (!seen) order[mo++] = (uint8_t)idx;
-                                            ref_in |= (idx + HS_CODE0 == ref);
                                         }
                                         alt0 = rf_select_alt_tied(order, s_hist, mo, ref, max2, a.lut);
                                         if (nref > 0) s_hist[ref - HS_CODE0] = 0;
@@ -524,7 +527,6 @@ __global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs
                                 } else {
                                     // deep column: first appearances = lowest list position of every code
                                     // (collected chunk by chunk in list order by the whole warp)
-                                    __shared__ uint8_t s_order_deep[RF_WARPS][HS_NCODES + 1];
                                     uint8_t* order = s_order_deep[wid];
                                     int mo = 0;
                                     for_cells([&](bool v, int code, int32_t n, int) {
@@ -580,7 +582,11 @@ __global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs
                 }
             }
         }
-        if (keep && lane == 0) a.kept[g] = 1;
+        if (lane == 0) {
+            if (keep) a.kept[g] = 1;
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 4), (unsigned long long)ncell);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 6), (unsigned long long)ncell * (unsigned)n_visited);
+        }
     }
 }
 
@@ -676,7 +682,6 @@ static int build_pstate(hsgpu_ctx* ctx, const hsgpu_partitions* parts, int64_t n
 }
 
 static const int kTablesSmem = HS_NCODES * 128 * 3 + CT_ROWS * 5;
-static const int kFilterSmem = CT_ROWS * HS_TILE + HS_NCODES * 128 * 3 + CT_NPA * CT_SSTRIDE + CT_ROWS * 4;
 
 extern "C" {
 
@@ -735,54 +740,114 @@ int hsgpu_partition_tables(hsgpu_pileup* p, int32_t contig, const hsgpu_partitio
     return HSGPU_OK;
 }
 
-int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions* parts, int32_t n_suspects,
-                        const int32_t* suspect_pos, int32_t kept_capacity, int32_t* kept, int32_t* n_kept) {
-    if (!p || !parts || contig < 0 || contig >= p->n_contigs || n_suspects < 0 || !n_kept) return HSGPU_ERR_ARG;
-    hsgpu_ctx* ctx = p->ctx;
-    if (!p->ranked) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_robust_filter: call hsgpu_column_rank first");
-    HS_CUDA(ctx, cudaSetDevice(ctx->device));
-    *n_kept = 0;
-    const int64_t R = p->h_contig_read_off[contig + 1] - p->h_contig_read_off[contig];
-    const int64_t L = p->h_contig_len[contig];
-    if (parts->n_parts == 0 || L == 0) return HSGPU_OK;  // :640-642: no partition, nothing is kept
-    for (int i = 0; i < n_suspects; i++)
-        if (suspect_pos[i] < 0 || suspect_pos[i] >= L) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_robust_filter: position out of range");
-    // with the transpose, rows padded to 16 partitions (the kernel's presence scan reads 16 partitions of a read at once)
-    const int npad = (parts->n_parts + 15) & ~15;
-    std::vector<uint8_t> pst, pst_t;
-    int rc = build_pstate(ctx, parts, R, pst, &pst_t, npad);
-    if (rc) return rc;
-    uint8_t* d_pst = nullptr;
-    uint8_t* d_pst_t = nullptr;
-    int32_t* d_pos = nullptr;
-    uint8_t* d_kept = nullptr;
-    int32_t* d_list = nullptr;
-    HS_CUDA(ctx, hs_alloc(ctx, &d_pst, (int64_t)pst.size()));
-    HS_CUDA(ctx, hs_alloc(ctx, &d_pos, n_suspects));
-    HS_CUDA(ctx, hs_alloc(ctx, &d_kept, L));
-    HS_CUDA(ctx, hs_alloc(ctx, &d_list, (int64_t)kept_capacity + 1));
-    HS_CUDA(ctx, hs_h2d(ctx, d_pst, pst.data(), (int64_t)pst.size()));
-    HS_CUDA(ctx, hs_alloc(ctx, &d_pst_t, (int64_t)pst_t.size()));
-    HS_CUDA(ctx, hs_h2d(ctx, d_pst_t, pst_t.data(), (int64_t)pst_t.size()));
-    HS_CUDA(ctx, hs_h2d(ctx, d_pos, suspect_pos, n_suspects));
-    const int64_t g0 = p->h_col_base[contig];
-    if (n_suspects > 0) {
-        HS_KERNEL(ctx, "set_inlist_kernel", set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 1));
+// the partitions of one contig in the two forms robust_filter_kernel reads: state rows [n_reads][npad] (1 = +1,
+// 2 = -1, 3 = 0, 0 = absent or masked; |4 solid) and presence rows [n_reads][pwords] (bit p = the read is in
+// partition p with a state other than masked)
+static int build_filter_rows(hsgpu_ctx* ctx, const hsgpu_partitions* parts, int64_t n_reads, int npad, int pwords,
+                             uint8_t* pst_t, uint32_t* pmask) {
+    memset(pst_t, 0, (size_t)n_reads * (size_t)npad);
+    memset(pmask, 0, (size_t)n_reads * (size_t)pwords * sizeof(uint32_t));
+    for (int p = 0; p < parts->n_parts; p++) {
+        for (int64_t i = parts->part_off[p]; i < parts->part_off[p + 1]; i++) {
+            const int32_t n = parts->read_idx[i];
+            if (n < 0 || n >= n_reads) HS_FAIL(ctx, HSGPU_ERR_ARG, "partition read index out of range");
+            uint8_t v = 0;
+            switch (parts->state[i]) {
+                case 1: v = 1; break;
+                case -1: v = 2; break;
+                case 0: v = 3; break;
+                default: v = 0; break;  // -2: masked
+            }
+            if (v && parts->less && parts->more && parts->less[i] <= 1 && parts->more[i] >= 3) v |= 4;
+            pst_t[(size_t)n * npad + p] = v;
+            if (v) pmask[(size_t)n * pwords + (p >> 5)] |= 1u << (p & 31);
+        }
     }
-    static std::atomic<bool> attr[64];  // per device: function attributes belong to the device's context
-    if (!attr[ctx->device & 63]) {
-        HS_CUDA(ctx, cudaFuncSetAttribute(robust_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFilterSmem));
-        attr[ctx->device & 63] = true;
+    return HSGPU_OK;
+}
+
+static void filter_free(hsgpu_pileup* p) {
+    hs_free(p->ctx, p->d_filter_block);
+    p->have_parts = false;
+}
+
+// uploads the partitions of contigs [c0, c0 + n) (parts[i] belongs to contig c0 + i; every other contig of the
+// pileup gets none) and keeps them with the pileup
+static int filter_set(hsgpu_pileup* p, int c0, int n, const hsgpu_partitions* parts) {
+    hsgpu_ctx* ctx = p->ctx;
+    const int nc = p->n_contigs;
+    std::vector<FilterDesc> desc((size_t)nc);
+    int64_t pst_bytes = 0, pmask_words = 0;
+    for (int c = 0; c < nc; c++) {
+        FilterDesc& d = desc[c];
+        memset(&d, 0, sizeof(d));
+        const hsgpu_partitions* q = (c >= c0 && c < c0 + n) ? &parts[c - c0] : nullptr;
+        if (!q || q->n_parts <= 0) continue;
+        const int64_t R = p->h_contig_read_off[c + 1] - p->h_contig_read_off[c];
+        d.n_parts = q->n_parts;
+        d.npad = (q->n_parts + 15) & ~15;
+        d.pwords = ((q->n_parts + 127) / 128) * 4;
+        d.pst_off = pst_bytes;
+        d.pmask_off = pmask_words;
+        pst_bytes += ((R * d.npad + 15) & ~(int64_t)15);
+        pmask_words += R * d.pwords;
+    }
+    const size_t desc_bytes = sizeof(FilterDesc) * (size_t)nc;
+    const size_t desc_pad = (desc_bytes + 255) & ~(size_t)255, pst_pad = ((size_t)pst_bytes + 255) & ~(size_t)255;
+    const size_t total = desc_pad + pst_pad + (size_t)pmask_words * 4 + 256;
+    uint8_t* h = reinterpret_cast<uint8_t*>(hs_host_stage(ctx, total));
+    if (!h) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu: pinned staging allocation failed");
+    memcpy(h, desc.data(), desc_bytes);
+    int rc_all = HSGPU_OK;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = c0; c < c0 + n; c++) {
+        const FilterDesc& d = desc[c];
+        if (d.n_parts <= 0) continue;
+        const int64_t R = p->h_contig_read_off[c + 1] - p->h_contig_read_off[c];
+        const int rc = build_filter_rows(ctx, &parts[c - c0], R, d.npad, d.pwords, h + desc_pad + d.pst_off,
+                                         reinterpret_cast<uint32_t*>(h + desc_pad + pst_pad) + d.pmask_off);
+        if (rc) {
+#pragma omp critical
+            rc_all = rc;
+        }
+    }
+    if (rc_all) return rc_all;
+    filter_free(p);
+    HS_CUDA(ctx, cudaMallocAsync(&p->d_filter_block, total, ctx->stream));
+    HS_CUDA(ctx, cudaMemcpyAsync(p->d_filter_block, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging area is reused by the next call
+    p->d_fdesc = p->d_filter_block;
+    p->d_pst_t = reinterpret_cast<uint8_t*>(p->d_filter_block) + desc_pad;
+    p->d_pmask = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p->d_filter_block) + desc_pad + pst_pad);
+    p->have_parts = true;
+    return HSGPU_OK;
+}
+
+// loops 3+4 over contigs [c0, c0 + n): kept positions packed per contig, off[i] .. off[i+1] for contig c0 + i
+static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t capacity, int32_t* kept, int64_t* off) {
+    hsgpu_ctx* ctx = p->ctx;
+    const int64_t g_begin = p->h_col_base[c0], g_end = p->h_col_base[c0 + n];
+    const int64_t ncols = g_end - g_begin;
+    for (int i = 0; i <= n; i++) off[i] = 0;
+    if (ncols <= 0) return HSGPU_OK;
+    if (!p->d_filter_work) {  // active list, kept flags, kept list, counters: allocated once per pileup
+        HsCarve cv;
+        cv.add(&p->d_factive, p->n_cols);
+        cv.add(&p->d_fkept, p->n_cols);
+        cv.add(&p->d_fkept_list, p->n_cols);
+        cv.add(&p->d_fcounters, 8);
+        cv.add(&p->d_fhdr, 2 * (int64_t)p->n_contigs + 2);
+        HS_CUDA(ctx, cv.alloc(ctx, &p->d_filter_work));
     }
     FilterArgs a;
-    a.contig = contig;
-    a.tile0 = p->h_tile_base[contig];
-    a.read0 = p->h_contig_read_off[contig];
-    a.g0 = g0;
-    a.L = (int)L;
-    a.n_reads = (int)R;
-    a.n_parts = parts->n_parts;
-    a.pstate = d_pst;
+    a.n_contigs = p->n_contigs;
+    a.in_flag = in_flag;
+    a.desc = reinterpret_cast<const FilterDesc*>(p->d_fdesc);
+    a.pst_t = p->d_pst_t;
+    a.pmask = p->d_pmask;
+    a.col_base = p->d_col_base;
+    a.tile_base = p->d_tile_base;
+    a.contig_read_off = p->d_contig_read_off;
     a.tile_off = p->d_tile_off;
     a.tile_reads = p->d_tile_reads;
     a.read_start = p->d_read_start;
@@ -793,32 +858,112 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     a.flags = p->d_flags;
     a.depth = p->d_depth;
     a.counts = p->d_counts;
-    a.pstate_t = d_pst_t;
-    a.npad = npad;
     a.lut = (const HsRankLut*)ctx->d_rank_lut;
-    a.kept = d_kept;
-    const unsigned ntile = (unsigned)((L + HS_TILE - 1) / HS_TILE);
-    HS_KERNEL(ctx, "robust_filter_kernel", robust_filter_kernel<<<ntile, 128, kFilterSmem, ctx->stream>>>(a));
-    HS_KERNEL(ctx, "kept_scan_kernel", kept_scan_kernel<<<1, 1024, 0, ctx->stream>>>((int)L, d_kept, kept_capacity, d_list, d_list + kept_capacity));
-    if (n_suspects > 0) {
-        HS_KERNEL(ctx, "set_inlist_kernel", set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 0));
-    }
-    HS_CUDA(ctx, hs_d2h(ctx, n_kept, d_list + kept_capacity, 1));
+    a.g_begin = g_begin;
+    a.g_end = g_end;
+    a.active = p->d_factive;
+    a.counters = p->d_fcounters;
+    a.kept = p->d_fkept;
+    HS_CUDA(ctx, cudaMemsetAsync(p->d_fcounters, 0, 8 * sizeof(unsigned int), ctx->stream));
+    HS_KERNEL(ctx, "filter_active_kernel", filter_active_kernel<<<(unsigned)((ncols + 255) / 256), 256, 0, ctx->stream>>>(a));
+    // persistent warps pull active columns from a counter (their cost varies with depth and partition count)
+    HS_KERNEL(ctx, "robust_filter_kernel", robust_filter_kernel<<<ctx->sm_count * 8, 32 * RF_WARPS, 0, ctx->stream>>>(a));
+    HS_KERNEL(ctx, "kept_scan_kernel", kept_scan_kernel<<<n, 1024, 0, ctx->stream>>>(c0, p->d_col_base, p->d_contig_len, p->d_fkept,
+                                                                                     p->d_fcounters + 2, p->n_cols, p->d_fkept_list, p->d_fhdr));
+    int64_t* h_hdr = reinterpret_cast<int64_t*>(hs_host_stage(ctx, sizeof(int64_t) * (size_t)(2 * n)));
+    if (!h_hdr) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu: pinned staging allocation failed");
+    HS_CUDA(ctx, cudaMemcpyAsync(h_hdr, p->d_fhdr, sizeof(int64_t) * (size_t)(2 * n), cudaMemcpyDeviceToHost, ctx->stream));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    int rc2 = HSGPU_OK;
-    if (*n_kept > kept_capacity) {
-        hs_set_error(ctx, "hsgpu_robust_filter: kept_capacity too small");
-        rc2 = HSGPU_ERR_CAPACITY;
-    } else if (kept) {
-        HS_CUDA(ctx, hs_d2h(ctx, kept, d_list, *n_kept));
-        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int64_t> start((size_t)n), count((size_t)n);
+    int64_t total = 0;
+    for (int i = 0; i < n; i++) {
+        start[i] = h_hdr[2 * i];
+        count[i] = h_hdr[2 * i + 1];
+        off[i + 1] = off[i] + count[i];
+        total += count[i];
     }
-    hs_free(ctx, d_pst);
-    hs_free(ctx, d_pst_t);
+    if (total > capacity && kept) HS_FAIL(ctx, HSGPU_ERR_CAPACITY, "hsgpu_robust_filter: capacity too small");
+    if (total > 0 && kept) {
+        int32_t* h_list = reinterpret_cast<int32_t*>(hs_host_stage(ctx, sizeof(int32_t) * (size_t)total));
+        if (!h_list) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu: pinned staging allocation failed");
+        HS_CUDA(ctx, cudaMemcpyAsync(h_list, p->d_fkept_list, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n; i++)  // the contigs reserved their slices in the order their CTAs got there
+            memcpy(kept + off[i], h_list + start[i], sizeof(int32_t) * (size_t)count[i]);
+    }
+    return HSGPU_OK;
+}
+
+int hsgpu_pileup_info(hsgpu_pileup* p, int64_t* info) {
+    if (!p || !info) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = p->ctx;
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < 8; i++) info[i] = 0;
+    info[0] = p->n_cigar;
+    info[1] = p->built ? p->codes_bytes : 0;
+    info[2] = p->built ? p->tile_entries : 0;
+    info[3] = p->built ? p->n_irregular : 0;
+    if (p->d_filter_work) {
+        unsigned int c[8];
+        HS_CUDA(ctx, cudaMemcpyAsync(c, p->d_fcounters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        info[4] = c[0];
+        info[5] = (int64_t)c[4] | ((int64_t)c[5] << 32);
+        info[6] = (int64_t)c[6] | ((int64_t)c[7] << 32);
+        info[7] = c[2];
+    }
+    return HSGPU_OK;
+}
+
+int hsgpu_partitions_set(hsgpu_pileup* p, const hsgpu_partitions* parts) {
+    if (!p || !parts) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = p->ctx;
+    if (!p->built) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_partitions_set: call hsgpu_pileup_build first");
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return filter_set(p, 0, p->n_contigs, parts);
+}
+
+int hsgpu_robust_filter_all(hsgpu_pileup* p, int64_t capacity, int32_t* kept, int64_t* off) {
+    if (!p || !off) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = p->ctx;
+    if (!p->ranked) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_robust_filter_all: call hsgpu_column_rank first");
+    if (!p->have_parts) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_robust_filter_all: call hsgpu_partitions_set first");
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return filter_run(p, 0, p->n_contigs, HS_FLAG_SUSPECT, capacity, kept, off);
+}
+
+int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions* parts, int32_t n_suspects,
+                        const int32_t* suspect_pos, int32_t kept_capacity, int32_t* kept, int32_t* n_kept) {
+    if (!p || !parts || contig < 0 || contig >= p->n_contigs || n_suspects < 0 || !n_kept) return HSGPU_ERR_ARG;
+    hsgpu_ctx* ctx = p->ctx;
+    if (!p->ranked) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_robust_filter: call hsgpu_column_rank first");
+    HS_CUDA(ctx, cudaSetDevice(ctx->device));
+    *n_kept = 0;
+    const int64_t L = p->h_contig_len[contig];
+    if (parts->n_parts == 0 || L == 0) return HSGPU_OK;  // :640-642: no partition, nothing is kept
+    for (int i = 0; i < n_suspects; i++)
+        if (suspect_pos[i] < 0 || suspect_pos[i] >= L) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_robust_filter: position out of range");
+    int rc = filter_set(p, contig, 1, parts);
+    if (rc) return rc;
+    int32_t* d_pos = nullptr;
+    HS_CUDA(ctx, hs_alloc(ctx, &d_pos, n_suspects));
+    HS_CUDA(ctx, hs_h2d(ctx, d_pos, suspect_pos, n_suspects));
+    const int64_t g0 = p->h_col_base[contig];
+    if (n_suspects > 0)
+        HS_KERNEL(ctx, "set_inlist_kernel", set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 1));
+    int64_t off[2] = {0, 0};
+    std::vector<int32_t> tmp((size_t)std::max<int64_t>(L, 1));
+    rc = filter_run(p, contig, 1, HS_FLAG_INLIST, L, tmp.data(), off);
+    if (n_suspects > 0)
+        HS_KERNEL(ctx, "set_inlist_kernel", set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 0));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // suspect_pos is caller memory
     hs_free(ctx, d_pos);
-    hs_free(ctx, d_kept);
-    hs_free(ctx, d_list);
-    return rc2;
+    filter_free(p);  // these partitions were the caller's for this call only
+    if (rc) return rc;
+    *n_kept = (int32_t)off[1];
+    if (off[1] > kept_capacity) HS_FAIL(ctx, HSGPU_ERR_CAPACITY, "hsgpu_robust_filter: kept_capacity too small");
+    if (kept) memcpy(kept, tmp.data(), sizeof(int32_t) * (size_t)off[1]);
+    return HSGPU_OK;
 }
 
 }  // extern "C"

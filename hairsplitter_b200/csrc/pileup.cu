@@ -19,11 +19,24 @@
 
 static std::mutex g_upload_mutex[64];  // per device, see hsgpu_pileup_create
 
-enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };
+enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };  // BAM ops (host side)
 
-__device__ __forceinline__ bool op_consumes_q(int ty) { return ty == OP_M || ty == OP_EQ || ty == OP_X || ty == OP_D; }
-__device__ __forceinline__ bool op_consumes_t(int ty) {
-    return ty == OP_M || ty == OP_EQ || ty == OP_X || ty == OP_I || ty == OP_S || ty == OP_H;
+// ---- CIGAR on the device --------------------------------------------------------------------------
+// One byte per op: len << 2 | kind, len <= 63, kind 0 = M/=/X, 1 = I, 2 = D, 3 = S/H -- the four classes
+// generate_msa distinguishes (:226-342); N and P ops move neither cursor there and are dropped, longer ops are
+// split. This is hsgpu_pileup_input.cigar8 as the caller gives it; the u32 / u16 forms are converted on the host
+// (hs_cigar_to_bytes). Four ops sit in one 32-bit word, so lengths and kinds are handled four at a time.
+#define HS_READ_IRREGULAR 1
+#define HS_SUPER_TILES 4  // tiles per super-tile of the two-level tile index
+#define HS_SUPER_COLS (HS_SUPER_TILES * HS_TILE)
+
+// the aligned word holding cigar bytes [kb, kb+4) of a read whose ops are bytes [k0, k1): bytes outside are zeroed
+// (a zero byte is an M op of length 0: it takes part in nothing)
+__device__ __forceinline__ uint32_t cg_word(const uint8_t* __restrict__ cigar, int64_t kb, int64_t k0, int64_t k1) {
+    uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(cigar + kb));
+    if (kb < k0) w &= 0xffffffffu << (8 * (int)(k0 - kb));
+    if (kb + 4 > k1) w &= (k1 - kb <= 0) ? 0u : (0xffffffffu >> (8 * (int)(kb + 4 - k1)));
+    return w;
 }
 
 // ---- K1: contig span of every read (sum of M/=/X/D lengths, clipped at the contig end, :217) ----
@@ -31,10 +44,7 @@ __device__ __forceinline__ bool op_consumes_t(int ty) {
 // which is what SAM allows; its leading clip length is the read offset of the first aligned base
 // (S and H both advance the read cursor in the reference, :269-273). Anything else is IRREGULAR and
 // goes through pileup_generic_kernel.
-#define HS_READ_IRREGULAR 1
-#define HS_SUPER_TILES 4  // tiles per super-tile of the two-level tile index
-#define HS_SUPER_COLS (HS_SUPER_TILES * HS_TILE)
-__global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32_t* __restrict__ cigar,
+__global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint8_t* __restrict__ cigar,
                                                    const int64_t* __restrict__ cigar_off,
                                                    const int32_t* __restrict__ read_start,
                                                    const int32_t* __restrict__ read_contig,
@@ -43,7 +53,6 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
                                                    int32_t* __restrict__ read_tlead, uint8_t* __restrict__ read_flags,
                                                    unsigned long long* __restrict__ totals) {
     // the three totals are summed per CTA first: one global atomic per counter and CTA instead of one per read
-    // (30 000 atomics on the same address were what bounded this kernel)
     __shared__ unsigned long long s_tot[3];
     if (threadIdx.x < 3) s_tot[threadIdx.x] = 0;
     __syncthreads();
@@ -51,31 +60,36 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
     const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const bool valid = r < n_reads;
     const int64_t k0 = valid ? cigar_off[r] : 0, k1 = valid ? cigar_off[r + 1] : 0;
-    long long sum = 0;
-    long long first = k1, last = -1;  // first / last op that is an alignment position (M,=,X,I,D)
+    const int64_t kbase = k0 & ~(int64_t)3;
+    int sum = 0;
+    long long first = k1, last = -1;  // first / last op that holds alignment positions (M, I, D with a length)
     int clips = 0;
-    // eight independent loads per lane in flight (the loop is otherwise bound by the latency of one load per trip)
-    for (int64_t kb = k0; kb < k1; kb += 8 * 32) {
-        uint32_t ops[8];
+    // four independent loads per lane in flight
+    for (int64_t kb = kbase + 4 * lane; kb < k1; kb += 4 * 32 * 4) {
+        uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int64_t k = kb + 32 * j + lane;
-            ops[j] = k < k1 ? __ldg(cigar + k) : (uint32_t)OP_P;  // a zero-length pad op takes part in nothing
+        for (int j = 0; j < 4; j++) {
+            const int64_t k = kb + 128 * j;
+            w[j] = k < k1 ? cg_word(cigar, k, k0, k1) : 0u;
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int64_t k = kb + 32 * j + lane;
-            const uint32_t op = ops[j];
-            const int ty = (int)(op & 15);
-            if (op_consumes_q(ty)) sum += op >> 4;
-            if ((ty == OP_S || ty == OP_H) && (op >> 4) > 0) clips = 1;
-            if ((op_consumes_q(ty) || ty == OP_I) && (op >> 4) > 0) {
-                if (k < first) first = k;
-                last = k;
+        for (int j = 0; j < 4; j++) {
+            const int64_t k = kb + 128 * j;
+            const uint32_t lens = (w[j] >> 2) & 0x3f3f3f3fu;
+            const uint32_t b0 = w[j] & 0x01010101u, b1 = (w[j] >> 1) & 0x01010101u;
+            sum = (int)__dp4a(lens & ((b0 ^ 0x01010101u) * 255u), 0x01010101u, (unsigned int)sum);  // kinds 0 and 2 consume the contig
+            const uint32_t nz = ((lens + 0x3f3f3f3fu) >> 6) & 0x01010101u;       // len > 0
+            const uint32_t is_s = b0 & b1;
+            const uint32_t al = nz & ~is_s;
+            if (al) {
+                const long long f = k + ((__ffs(al) - 1) >> 3), l = k + ((31 - __clz(al)) >> 3);
+                if (f < first) first = f;
+                if (l > last) last = l;
             }
+            if (nz & is_s) clips = 1;
         }
     }
-    sum = hs_warp_sum64(sum);
+    long long sum64 = hs_warp_sum64((long long)sum);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
@@ -85,12 +99,16 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
     int irregular = 0;
     // the second pass places the clips; most reads have none
     if (__any_sync(0xffffffffu, clips))
-    for (int64_t k = k0 + lane; k < k1; k += 32) {
-        const uint32_t op = __ldg(cigar + k);
-        const int ty = (int)(op & 15);
-        if ((ty == OP_S || ty == OP_H) && (op >> 4) > 0) {
-            if (k < first) tlead += op >> 4;
-            else if (k < last) irregular = 1;
+    for (int64_t kb = kbase + 4 * lane; kb < k1; kb += 128) {
+        const uint32_t w = cg_word(cigar, kb, k0, k1);
+        if (((w & (w >> 1)) & 0x01010101u) == 0) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t b = (w >> (8 * j)) & 0xffu;
+            if ((b & 3u) == 3u && (b >> 2) > 0) {
+                if (kb + j < first) tlead += b >> 2;
+                else if (kb + j < last) irregular = 1;
+            }
         }
     }
     tlead = hs_warp_sum64(tlead);
@@ -99,7 +117,7 @@ __global__ void __launch_bounds__(256) span_kernel(int64_t n_reads, const uint32
         const int L = contig_len[read_contig[r]];
         const int start = read_start[r];
         long long end = start;
-        if (start < L) end = (start + sum < (long long)L) ? start + sum : L;
+        if (start < L) end = (start + sum64 < (long long)L) ? start + sum64 : L;
         read_end[r] = (int)end;
         long long alloc = 0;
         if (end > start) alloc = ((end + HS_ALIGN - 1) & ~(long long)(HS_ALIGN - 1)) - (start & ~(HS_ALIGN - 1));
@@ -126,7 +144,7 @@ struct PileupArgs {
     const uint32_t* read_bases;
     const int64_t* read_word_off;
     const int32_t* read_len;
-    const uint32_t* cigar;
+    const uint8_t* cigar;   // one byte per op (see above)
     const int64_t* cigar_off;
     const int32_t* read_start;
     const uint8_t* read_strand;
@@ -154,12 +172,12 @@ struct PileupArgs {
 // shared memory and leave for HBM as whole aligned 16-byte vectors: every row byte is written exactly
 // once, fully coalesced.
 #define PW_WARPS 8
-#define PW_OPL 6                  // CIGAR ops per lane and window
+#define PW_OPL 6                  // CIGAR ops per lane and window (byte-sized: four in one register, two in another)
 #define PW_NOPS (32 * PW_OPL)
 #define PW_P 30                   // positions per lane and window (+2 warm-up = 32 steps)
 #define PW_E (32 * PW_P)
 #define PW_BUF 1024               // staging row: a carried partial vector + one window of columns (<= 16 + 960 + 16)
-enum { PK_M = 0, PK_I = 1, PK_D = 2, PK_SKIP = 3, PK_NONE = 4 };
+enum { CG_M = 0, CG_I = 1, CG_D = 2, CG_S = 3 };  // kinds of the byte-sized CIGAR ops
 
 __device__ __forceinline__ uint32_t pw_word(const uint32_t* __restrict__ w, int i, int n) {
     return (i >= 0 && i < n) ? __ldg(w + i) : 0u;
@@ -189,18 +207,41 @@ __device__ __forceinline__ uint32_t pw_read_window(const uint32_t* __restrict__ 
     return x;
 }
 
-// set bits [a, b) of a warp-private bit array in shared memory
-__device__ __forceinline__ void pw_set_bits(unsigned int* __restrict__ bits, int a, int b) {
-    int w = a >> 5;
-    const int w1 = (b - 1) >> 5;
-    unsigned int m = 0xffffffffu << (a & 31);
-    const unsigned int mlast = 0xffffffffu >> (31 - ((b - 1) & 31));
-    while (w < w1) {
-        atomicOr(bits + w, m);
-        m = 0xffffffffu;
-        w++;
+// set bits [a, a + n) of a warp-private bit array in shared memory, 0 < n <= 63 (one CIGAR op). Insertions and
+// deletions are a few bases long: up to 32 bits take one atomic, two when the run crosses a word boundary.
+__device__ __forceinline__ void pw_set_bits(unsigned int* __restrict__ bits, int a, int n) {
+    for (;;) {
+        const int s = a & 31, n1 = min(n, 32);
+        unsigned int* const w = bits + (a >> 5);
+        const unsigned int m = n1 == 32 ? 0xffffffffu : ((1u << n1) - 1u);
+        atomicOr(w, m << s);
+        const unsigned int up = __funnelshift_l(m, 0u, s);  // the part that spills into the next word (0 when s == 0)
+        if (up) atomicOr(w + 1, up);
+        if (n <= 32) break;
+        a += 32;
+        n -= 32;
     }
-    atomicOr(bits + w, m & mlast);
+}
+
+// the PW_OPL ops [kop + PW_OPL*lane, ...) of a read: four in `lo`, two in the low half of `hi` (bytes past nops
+// read as zero: empty M ops)
+__device__ __forceinline__ void pw_load_ops(const uint8_t* __restrict__ cig, int kop, int nops, int lane, uint32_t& lo,
+                                            uint32_t& hi) {
+    const uint8_t* p = cig + kop + PW_OPL * lane;
+    const int sh = (int)(reinterpret_cast<uintptr_t>(p) & 3);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(p - sh);
+    const int nv = min(PW_OPL, nops - kop - PW_OPL * lane);  // valid bytes from p on
+    // three aligned words cover the six bytes; a word is read only if it holds a valid byte
+    const uint32_t w0 = nv > 0 ? __ldg(wp) : 0u;
+    const uint32_t w1 = nv + sh > 4 ? __ldg(wp + 1) : 0u;
+    const uint32_t w2 = nv + sh > 8 ? __ldg(wp + 2) : 0u;
+    lo = __funnelshift_r(w0, w1, 8 * sh);
+    hi = __funnelshift_r(w1, w2, 8 * sh) & 0xffffu;
+    if (nv < PW_OPL) {
+        if (nv <= 0) { lo = 0; hi = 0; }
+        else if (nv <= 4) { hi = 0; if (nv < 4) lo &= (1u << (8 * nv)) - 1u; }
+        else hi &= (1u << (8 * (nv - 4))) - 1u;
+    }
 }
 
 // One step of the FAST walk, as PTX so that it stays the 14 predicated instructions it is meant to be
@@ -334,7 +375,7 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 4) pileup_kernel(PileupArgs a) 
         const int strand = a.read_strand[r];
         const int end = a.read_end[r];
         uint8_t* __restrict__ row = a.codes + row_base;
-        const uint32_t* __restrict__ cig = a.cigar + a.cigar_off[r];
+        const uint8_t* __restrict__ cig = a.cigar + a.cigar_off[r];
         const int nops = (int)(a.cigar_off[r + 1] - a.cigar_off[r]);
         int kop = 0;                   // first op of the window
         int off0 = 0;                  // positions of op kop that earlier windows already consumed
@@ -345,29 +386,19 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 4) pileup_kernel(PileupArgs a) 
         unsigned int udist = 0, ualen = 0;  // per warp (same value in every lane)
         if (lane < HS_ALIGN) buf[lane] = 0;  // the pad in front of the first cell
         __syncwarp();
-        // the window's ops live in registers; the next window's are requested before the walk of this one
-        uint32_t opw[PW_OPL];
-#pragma unroll
-        for (int j = 0; j < PW_OPL; j++) {
-            const int k = kop + PW_OPL * lane + j;
-            opw[j] = (k < nops) ? __ldg(cig + k) : (uint32_t)OP_P;
-        }
+        // the window's ops live in two registers (six byte-sized ops per lane); the next window's are requested
+        // before the walk of this one
+        uint32_t oplo, ophi;
+        pw_load_ops(cig, kop, nops, lane, oplo, ophi);
         while (kop < nops && q0 < L) {
-            // ---- the window's ops: classify, scan the position counts -------------------------------
-            int klen[PW_OPL], kd[PW_OPL], e_in[PW_OPL];
-            int es = 0;
-#pragma unroll
-            for (int j = 0; j < PW_OPL; j++) {
-                const int ty = (int)(opw[j] & 15);
-                int ln = (int)(opw[j] >> 4);
-                if (j == 0 && lane == 0) ln -= off0;
-                // M,=,X -> PK_M; I -> PK_I; D -> PK_D; everything else takes no alignment position
-                const int kind = (ty < 8) ? (int)((0x04444210u >> (4 * ty)) & 15u) : (ty == OP_X ? PK_M : PK_NONE);
-                kd[j] = kind;
-                klen[j] = (kind != PK_NONE) ? min(ln, 1024) : 0;  // the window ends inside anything longer than PW_E
-                e_in[j] = es;
-                es += klen[j];
-            }
+            // ---- the window's ops, four at a time: lengths, kinds, positions taken (S/H take none) ------------
+            const uint32_t len_lo = (oplo >> 2) & 0x3f3f3f3fu, len_hi = (ophi >> 2) & 0x3f3f3f3fu;
+            const uint32_t s_lo = oplo & (oplo >> 1) & 0x01010101u, s_hi = ophi & (ophi >> 1) & 0x01010101u;
+            uint32_t pl_lo = len_lo & ~(s_lo * 255u), pl_hi = len_hi & ~(s_hi * 255u);
+            if (lane == 0) pl_lo -= min((uint32_t)off0, pl_lo & 0xffu);  // op kop was partly consumed by the last window
+            const int es_lo = (int)__dp4a(pl_lo, 0x01010101u, 0u), es = (int)__dp4a(pl_hi, 0x01010101u, (unsigned int)es_lo);
+            // exclusive prefix of the positions inside each word (byte k = positions of the bytes below k; <= 189)
+            const uint32_t pre_lo = pl_lo * 0x01010100u, pre_hi = pl_hi * 0x01010100u;
             const int ei = hs_warp_incl_scan(es, lane);
             const int ebase = ei - es;
             const int Etot = __shfl_sync(0xffffffffu, ei, 31);
@@ -377,10 +408,18 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 4) pileup_kernel(PileupArgs a) 
             int kop_next = kop + nload, off0_next = 0;
             if (Enew < Etot) {
                 int myslot = -1, myd = 0;
+                if (es > 0 && ebase <= Enew && Enew < ei) {  // exactly one lane: the op that holds position Enew
+                    const int rel = Enew - ebase;
+                    const bool hi = rel >= es_lo;
+                    const int rel2 = hi ? rel - es_lo : rel;
+                    const uint32_t pl = hi ? pl_hi : pl_lo, pre = hi ? pre_hi : pre_lo;
+                    int j = 0;
 #pragma unroll
-                for (int j = 0; j < PW_OPL; j++) {
-                    const int pa = ebase + e_in[j];
-                    if (klen[j] > 0 && pa <= Enew && Enew < pa + klen[j]) { myslot = PW_OPL * lane + j; myd = Enew - pa; }
+                    for (int k = 1; k < 4; k++)
+                        if ((int)((pre >> (8 * k)) & 0xffu) <= rel2 && ((pl >> (8 * k)) & 0xffu) > 0) j = k;
+                    // the last byte whose range starts at or before rel2 and is not empty holds it
+                    myslot = PW_OPL * lane + (hi ? 4 : 0) + j;
+                    myd = rel2 - (int)((pre >> (8 * j)) & 0xffu);
                 }
                 const unsigned int who = __ballot_sync(0xffffffffu, myslot >= 0);
                 const int src = __ffs(who) - 1;
@@ -389,11 +428,8 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 4) pileup_kernel(PileupArgs a) 
                 off0_next = (slot == 0 ? off0 : 0) + d;
                 kop_next = kop + slot;
             }
-#pragma unroll
-            for (int j = 0; j < PW_OPL; j++) {
-                const int k = kop_next + PW_OPL * lane + j;
-                opw[j] = (k < nops) ? __ldg(cig + k) : (uint32_t)OP_P;
-            }
+            const uint32_t cur_lo = oplo, cur_hi = ophi;
+            pw_load_ops(cig, kop_next, nops, lane, oplo, ophi);
             kop = kop_next;
             off0 = off0_next;
             if (Etot == 0) continue;  // nothing but clips / padding
@@ -403,11 +439,20 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 4) pileup_kernel(PileupArgs a) 
             sI[lane] = 0;
             sD[lane] = 0;
             __syncwarp();
+            if (ebase < Enew) {
+                // kind 1 = I, kind 2 = D: exactly one of the two low bits
+                const uint32_t id_lo = (cur_lo ^ (cur_lo >> 1)) & 0x01010101u, id_hi = (cur_hi ^ (cur_hi >> 1)) & 0x01010101u;
 #pragma unroll
-            for (int j = 0; j < PW_OPL; j++) {
-                if ((kd[j] == PK_I || kd[j] == PK_D) && klen[j] > 0) {
-                    const int pa = ebase + e_in[j], pb = min(pa + klen[j], Enew);
-                    if (pa < pb) pw_set_bits(kd[j] == PK_I ? sI : sD, pa + 2, pb + 2);
+                for (int j = 0; j < PW_OPL; j++) {
+                    const uint32_t idm = j < 4 ? id_lo : id_hi, pl = j < 4 ? pl_lo : pl_hi, pre = j < 4 ? pre_lo : pre_hi;
+                    const uint32_t cur = j < 4 ? cur_lo : cur_hi;
+                    const int sh = 8 * (j & 3);
+                    const int ln = (int)((pl >> sh) & 0xffu);
+                    if (((idm >> sh) & 1u) && ln > 0) {
+                        const int pa = ebase + (j < 4 ? 0 : es_lo) + (int)((pre >> sh) & 0xffu);
+                        const int n = min(ln, Enew - pa);
+                        if (n > 0) pw_set_bits(((cur >> sh) & 1u) ? sI : sD, pa + 2, n);
+                    }
                 }
             }
             __syncwarp();
@@ -506,10 +551,10 @@ __global__ void __launch_bounds__(256) pileup_generic_kernel(PileupArgs a) {
     unsigned int dist = 0, alen = 0;
     for (int64_t kb = k0; kb < k1 && q < L; kb += 32) {
         const int64_t k = kb + lane;
-        uint32_t op = (k < k1) ? __ldg(a.cigar + k) : (uint32_t)OP_P;
-        const int len = (int)(op >> 4), ty = (int)(op & 15);
-        const bool cq = op_consumes_q(ty), ct = op_consumes_t(ty);
-        const int qa = cq ? len : 0, ta = ct ? len : 0, ea = (cq || ct) ? len : 0;
+        const uint32_t op = (k < k1) ? (uint32_t)__ldg(a.cigar + k) : 0u;  // a zero byte: an M op without positions
+        const int len = (int)(op >> 2), ty = (int)(op & 3u);
+        const bool cq = ty == CG_M || ty == CG_D, ct = ty != CG_D;
+        const int qa = cq ? len : 0, ta = ct ? len : 0, ea = len;
         const int qi = hs_warp_incl_scan(qa, lane), ti = hs_warp_incl_scan(ta, lane), ei = hs_warp_incl_scan(ea, lane);
         s_q[wid][lane] = q + qi - qa;
         s_t[wid][lane] = t + ti - ta;
@@ -527,14 +572,14 @@ __global__ void __launch_bounds__(256) pileup_generic_kernel(PileupArgs a) {
             }
             const int off = e - s_e[wid][lo];
             const int oty = s_ty[wid][lo];
-            const bool ocq = op_consumes_q(oty), oct = op_consumes_t(oty);
+            const bool ocq = oty == CG_M || oty == CG_D, oct = oty != CG_D;
             const int qp = s_q[wid][lo] + (ocq ? off : 0);
             const int tp = s_t[wid][lo] + (oct ? off : 0);
             const bool active = (e < E) && (qp < L);
-            const bool push = active && (ocq || oty == OP_I);
+            const bool push = active && (ocq || oty == CG_I);
             int sym = 0;
             if (push) {
-                if (oty == OP_D) sym = 4;
+                if (oty == CG_D) sym = 4;
                 else if (tp < rlen) {  // a CIGAR longer than the read is malformed; the reference reads past the string
                     sym = strand ? hs_base2(rb, tp) : 3 - hs_base2(rb, (int64_t)rlen - 1 - tp);
                 }
@@ -552,9 +597,9 @@ __global__ void __launch_bounds__(256) pileup_generic_kernel(PileupArgs a) {
                 if (ocq) {
                     row[qp] = (uint8_t)(HS_CODE0 + 5 * prev2 + prev1 + 25 * sym);  // :238,287
                     alen++;
-                    if (oty == OP_D) dist++;
+                    if (oty == CG_D) dist++;
                     else if (sym != hs_base2(cb, qp)) dist++;  // :254-256
-                } else if (oty == OP_I) {
+                } else if (oty == CG_I) {
                     dist++;  // :337-338
                     alen++;
                 }
@@ -670,42 +715,6 @@ __global__ void __launch_bounds__(256) tile_index_kernel(int64_t n_tiles, const 
     }
 }
 
-__global__ void cigar_expand_kernel(int64_t n, const uint16_t* __restrict__ in, uint32_t* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const uint32_t v = in[i];
-        out[i] = ((v >> 4) << 4) | (v & 15u);  // same bit layout, wider length field
-    }
-}
-
-// 8-bit form (hsgpu_pack_cigar8): len<<2 | kind, kind 0 M, 1 I, 2 D, 3 S; sixteen ops per thread
-__global__ void cigar8_expand_kernel(int64_t n, const uint8_t* __restrict__ in, uint32_t* __restrict__ out) {
-    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (i0 >= n) return;
-    uint32_t w[4];
-    if (i0 + 16 <= n) {  // `in` is its own allocation: 16-byte aligned
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i0));
-        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-    } else {
-        w[0] = w[1] = w[2] = w[3] = 0;
-        for (int j = 0; i0 + j < n; j++) w[j >> 2] |= (uint32_t)in[i0 + j] << (8 * (j & 3));
-    }
-    uint32_t o[16];
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-        const uint32_t kind = b & 3u;
-        o[j] = ((b >> 2) << 4) | (kind == 3u ? (uint32_t)OP_S : kind);
-    }
-    if (i0 + 16 <= n) {  // out + i0 is 64-byte aligned
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            reinterpret_cast<uint4*>(out + i0)[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-    } else {
-        for (int j = 0; i0 + j < n; j++) out[i0 + j] = o[j];
-    }
-}
-
 // the contig every read / every tile belongs to: last c with off[c] <= i (empty contigs repeat an offset)
 __device__ __forceinline__ int hs_owner(const int64_t* __restrict__ off, int n, int64_t i) {
     int lo = 0, hi = n - 1;
@@ -724,6 +733,44 @@ __global__ void __launch_bounds__(256) owner_fill_kernel(int nc, int64_t n_reads
 }
 
 // ---- host side --------------------------------------------------------------------------------
+// u32 (BAM) or u16 ops -> the byte form the kernels read. N and P ops are dropped (generate_msa moves neither cursor
+// for them), ops longer than 63 are split, =/X become M and H becomes S. Reads in parallel: a counting pass, the
+// offsets, a filling pass.
+template <typename OP>
+static void hs_cigar_to_bytes(const OP* ops, const int64_t* off, int64_t n_reads, std::vector<int64_t>& out_off,
+                              std::vector<uint8_t>& out) {
+    static const int8_t kind_of[16] = {0, 1, 2, -1, 3, 3, -1, 0, 0, -1, -1, -1, -1, -1, -1, -1};
+    out_off.assign((size_t)n_reads + 1, 0);
+#pragma omp parallel for schedule(static, 256)
+    for (int64_t r = 0; r < n_reads; r++) {
+        int64_t n = 0;
+        for (int64_t k = off[r]; k < off[r + 1]; k++) {
+            const uint32_t op = (uint32_t)ops[k];
+            if (kind_of[op & 15u] < 0) continue;
+            const uint32_t len = op >> 4;
+            n += len <= 63u ? 1 : (len + 62u) / 63u;
+        }
+        out_off[r + 1] = n;
+    }
+    for (int64_t r = 0; r < n_reads; r++) out_off[r + 1] += out_off[r];
+    out.resize((size_t)out_off[n_reads] + 16);
+#pragma omp parallel for schedule(static, 256)
+    for (int64_t r = 0; r < n_reads; r++) {
+        uint8_t* w = out.data() + out_off[r];
+        for (int64_t k = off[r]; k < off[r + 1]; k++) {
+            const uint32_t op = (uint32_t)ops[k];
+            const int kind = kind_of[op & 15u];
+            if (kind < 0) continue;
+            uint32_t len = op >> 4;
+            do {
+                const uint32_t piece = len > 63u ? 63u : len;
+                *w++ = (uint8_t)((piece << 2) | (uint32_t)kind);
+                len -= piece;
+            } while (len > 0);
+        }
+    }
+}
+
 // hsgpu_pileup_build leaves the deepest tile's read count in flight (pinned scratch of the context + event)
 int hs_resolve_max_tile_reads(hsgpu_pileup* p) {
     hsgpu_ctx* ctx = p->ctx;
@@ -747,6 +794,8 @@ void hsgpu_pileup_destroy(hsgpu_pileup* p) {
     hs_free(ctx, p->d_tile_reads);
     if (ctx->scratch_owner == p) ctx->scratch_owner = nullptr;
     hs_free(ctx, p->d_col_off);
+    hs_free(ctx, p->d_filter_block);
+    hs_free(ctx, p->d_filter_work);
     delete p;
 }
 
@@ -802,7 +851,20 @@ static int pileup_create_impl(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgp
     p->n_super = supers;
     p->n_cols = cols;
     p->n_tiles = tiles;
-    p->n_cigar = in->cigar_off[nr];
+    // the CIGARs as bytes: the caller's cigar8 as it is, the wider forms converted here
+    std::vector<int64_t> cig_off_conv;
+    std::vector<uint8_t> cig_conv;
+    const uint8_t* h_cigar = in->cigar8;
+    const int64_t* h_cigar_off = in->cigar_off;
+    if (!h_cigar) {
+        if (in->cigar16) hs_cigar_to_bytes(in->cigar16, in->cigar_off, nr, cig_off_conv, cig_conv);
+        else if (in->cigar) hs_cigar_to_bytes(in->cigar, in->cigar_off, nr, cig_off_conv, cig_conv);
+        else if (in->cigar_off[nr] > 0) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pileup_create: no CIGAR array given");
+        else cig_off_conv.assign((size_t)nr + 1, 0), cig_conv.assign(16, 0);
+        h_cigar = cig_conv.data();
+        h_cigar_off = cig_off_conv.data();
+    }
+    p->n_cigar = h_cigar_off[nr];
     for (int64_t r = 0; r < nr; r++) {
         if (in->read_start[r] < 0 || in->read_len[r] < 0)
             HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pileup_create: negative read start or length");
@@ -815,7 +877,7 @@ static int pileup_create_impl(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgp
         A(d_contig_len, nc); A(d_contig_bases, contig_words); A(d_contig_word_off, nc + 1);
         A(d_contig_read_off, nc + 1); A(d_col_base, 4 * (nc + 1)); A(d_tile_contig, tiles);
         A(d_read_contig, nr); A(d_read_bases, read_words); A(d_read_word_off, nr + 1); A(d_read_len, nr);
-        A(d_cigar, p->n_cigar); A(d_cigar_off, nr + 1); A(d_read_start, nr); A(d_read_strand, nr);
+        A(d_cigar, p->n_cigar + 16); A(d_cigar_off, nr + 1); A(d_read_start, nr); A(d_read_strand, nr);
         A(d_read_end, nr); A(d_read_tlead, nr); A(d_read_flags, nr); A(d_next_read, 4); A(d_row_alloc, nr + 1); A(d_row_base, nr); A(d_stats, 3 * nc);
         A(d_tile_off, tiles + 1); A(d_super_off, supers + 1);
 #undef A
@@ -842,34 +904,13 @@ static int pileup_create_impl(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgp
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_bases, in->read_bases, read_words));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_word_off, in->read_word_off, nr + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_len, in->read_len, nr));
-    HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar_off, in->cigar_off, nr + 1));
+    HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar_off, h_cigar_off, nr + 1));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_start, in->read_start, nr));
     HS_CUDA(ctx, hs_h2d(ctx, p->d_read_strand, in->read_strand, nr));
-    uint16_t* d_cigar16 = nullptr;
-    uint8_t* d_cigar8 = nullptr;
-    if (in->cigar8) {
-        HS_CUDA(ctx, hs_alloc(ctx, &d_cigar8, p->n_cigar));
-        HS_CUDA(ctx, hs_h2d(ctx, d_cigar8, in->cigar8, p->n_cigar));
-    } else if (in->cigar16) {
-        HS_CUDA(ctx, hs_alloc(ctx, &d_cigar16, p->n_cigar));
-        HS_CUDA(ctx, hs_h2d(ctx, d_cigar16, in->cigar16, p->n_cigar));
-    } else {
-        HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar, in->cigar, p->n_cigar));
-    }
+    HS_CUDA(ctx, hs_h2d(ctx, p->d_cigar, h_cigar, p->n_cigar));
     // contig of every read and of every tile: looked up on the device (two sorted offset tables)
     HS_KERNEL(ctx, "owner_fill_kernel", owner_fill_kernel<<<(unsigned)((nr + tiles + 255) / 256 + 1), 256, 0, ctx->stream>>>(
         nc, nr, p->d_contig_read_off, p->d_read_contig, tiles, p->d_tile_base, p->d_tile_contig));
-    if (d_cigar8) {
-        if (p->n_cigar > 0)
-            HS_KERNEL(ctx, "cigar8_expand_kernel", cigar8_expand_kernel<<<(unsigned)((p->n_cigar + 16 * 256 - 1) / (16 * 256)), 256, 0, ctx->stream>>>(
-                p->n_cigar, d_cigar8, p->d_cigar));
-        hs_free(ctx, d_cigar8);
-    } else if (d_cigar16) {
-        if (p->n_cigar > 0)
-            HS_KERNEL(ctx, "cigar_expand_kernel", cigar_expand_kernel<<<(unsigned)((p->n_cigar + 255) / 256), 256, 0, ctx->stream>>>(
-                p->n_cigar, d_cigar16, p->d_cigar));
-        hs_free(ctx, d_cigar16);
-    }
     // The upload turn ends when the stream is idle: the copies have landed (the caller's buffers are free again) and
     // the two small kernels behind them are done. Releasing the turn earlier, on an event behind the last copy, was
     // measured slower and unstable (2.5-4.6 ms per e2e step against a steady 2.45 ms): the next context's upload

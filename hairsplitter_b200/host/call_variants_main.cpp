@@ -202,34 +202,42 @@ static void process_batch(const std::function<hsgpu_ctx*()>& get_ctx, const Stor
 #pragma omp parallel for schedule(dynamic, 1)
     for (int b = 0; b < nc; b++) build_partitions(suspects[b], mean_distance[b], parts[b]);
     phase("  build partitions");
-    // phase C: loops 3+4 on the device, then the merge with the automatic SNPs (main(), :1334-1352)
+    // phase C: loops 3+4 on the device -- the final partitions of every contig of the batch go up in one piece and
+    // one launch filters all contigs -- then the merge with the automatic SNPs (main(), :1334-1352)
+    std::vector<std::vector<int64_t>> part_off(nc);
+    std::vector<std::vector<int32_t>> p_idx(nc), p_more(nc), p_less(nc);
+    std::vector<std::vector<int16_t>> p_state(nc);
+    std::vector<hsgpu_partitions> hp(nc);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < nc; b++) {
+        part_off[b].assign(1, 0);
+        for (const Partition& p : parts[b]) {
+            p_idx[b].insert(p_idx[b].end(), p.readIdx.begin(), p.readIdx.end());
+            p_state[b].insert(p_state[b].end(), p.state.begin(), p.state.end());
+            p_more[b].insert(p_more[b].end(), p.more.begin(), p.more.end());
+            p_less[b].insert(p_less[b].end(), p.less.begin(), p.less.end());
+            part_off[b].push_back((int64_t)p_idx[b].size());
+        }
+        hp[b].n_parts = (int32_t)parts[b].size();
+        hp[b].part_off = part_off[b].data();
+        hp[b].read_idx = p_idx[b].data();
+        hp[b].state = p_state[b].data();
+        hp[b].more = p_more[b].data();
+        hp[b].less = p_less[b].data();
+    }
+    GPU_CHECK(ctx, hsgpu_partitions_set(pu, hp.data()));
+    std::vector<int64_t> kept_off(nc + 1, 0);
+    int64_t total_cols = 0;
+    for (int b = 0; b < nc; b++) total_cols += contig_len[b];
+    std::vector<int32_t> kept_all((size_t)std::max<int64_t>(total_cols, 1));
+    GPU_CHECK(ctx, hsgpu_robust_filter_all(pu, total_cols, kept_all.data(), kept_off.data()));
     for (int b = 0; b < nc; b++) {
         ContigResult& res = results[batch[b]];
         res.mean_distance = mean_distance[b];
         res.depth = (float)((double)depth_sum[b] / (size_t)contig_len[b]);
         std::vector<Column> filtered;
         if (!parts[b].empty()) {
-            std::vector<int64_t> part_off(1, 0);
-            std::vector<int32_t> idx, more, less;
-            std::vector<int16_t> state;
-            for (const Partition& p : parts[b]) {
-                idx.insert(idx.end(), p.readIdx.begin(), p.readIdx.end());
-                state.insert(state.end(), p.state.begin(), p.state.end());
-                more.insert(more.end(), p.more.begin(), p.more.end());
-                less.insert(less.end(), p.less.begin(), p.less.end());
-                part_off.push_back((int64_t)idx.size());
-            }
-            hsgpu_partitions hp;
-            hp.n_parts = (int32_t)parts[b].size();
-            hp.part_off = part_off.data();
-            hp.read_idx = idx.data();
-            hp.state = state.data();
-            hp.more = more.data();
-            hp.less = less.data();
-            std::vector<int32_t> kept((size_t)std::max(contig_len[b], 1));
-            int32_t n_kept = 0;
-            GPU_CHECK(ctx, hsgpu_robust_filter(pu, b, &hp, n_suspects[b], suspect_pos[b].data(), contig_len[b], kept.data(), &n_kept));
-            kept.resize(n_kept);
+            std::vector<int32_t> kept(kept_all.begin() + kept_off[b], kept_all.begin() + kept_off[b + 1]);
             fetch_columns(ctx, pu, b, kept, k0[b], k1[b], filtered);
         }
         size_t ia = 0, jf = 0;

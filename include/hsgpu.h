@@ -114,6 +114,10 @@ int hsgpu_pileup_build(hsgpu_pileup* p);
 /* per contig: total cells, and the integer sums behind generate_msa's return value
  * (totalDistance numerator, totalLengthOfAlignment without its initial 1). Any pointer may be NULL. */
 int hsgpu_pileup_stats(hsgpu_pileup* p, int64_t* n_cells, int64_t* distance_sum, int64_t* aligned_sum);
+/* sizes behind the roofline figures of bench.py. info[8]: [0] CIGAR bytes on the device (one byte per op), [1] pileup
+ * bytes, [2] (tile, read) index entries, [3] reads with clips inside the alignment; of the last hsgpu_robust_filter*
+ * call: [4] active columns, [5] their cells, [6] partition state bytes read, [7] columns kept */
+int hsgpu_pileup_info(hsgpu_pileup* p, int64_t* info);
 /* generate_msa's float return value from the two sums (float accumulator, :67-68,434) */
 float hsgpu_mean_distance(int64_t distance_sum, int64_t aligned_sum);
 /* positionOfReads[n].second of every read (:354), i.e. readLimits */
@@ -181,6 +185,16 @@ int hsgpu_partition_tables(hsgpu_pileup* p, int32_t contig, const hsgpu_partitio
  * *n_kept is always written. */
 int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions* parts, int32_t n_suspects,
                         const int32_t* suspect_pos, int32_t kept_capacity, int32_t* kept, int32_t* n_kept);
+
+/* Batch form of the same filter (what HS_call_variants' loop over contigs becomes on one GPU, src/call_variants.cpp:
+ * 1276-1330): hsgpu_partitions_set uploads the final partitions of EVERY contig of the pileup (parts[c] for contig c,
+ * n_parts may be 0) and keeps them with the pileup until it is called again; hsgpu_robust_filter_all then runs loops
+ * 3+4 for all contigs in one launch, with the pileup's own suspect columns (hsgpu_column_rank) as snps_in -- the way
+ * main() chains call_variants and keep_only_robust_variants (:1322-1327). Contig c's snps_out are
+ * kept[off[c] .. off[c+1]) (positions inside the contig, ascending); off has n_contigs+1 entries and is always written;
+ * kept may be NULL (counts only); HSGPU_ERR_CAPACITY when capacity < off[n_contigs]. */
+int hsgpu_partitions_set(hsgpu_pileup* p, const hsgpu_partitions* parts);
+int hsgpu_robust_filter_all(hsgpu_pileup* p, int64_t capacity, int32_t* kept, int64_t* off);
 
 /* ---- read x read counts: list_similarities_and_differences_between_reads3
  * (src/separate_reads.cpp:374-433) --------------------------------------------------------------

@@ -304,3 +304,52 @@ def test_invalid_batch_is_refused_and_leaves_the_context_usable(gpu_ctx, oracle)
     pu.column_rank()
     _check_contig(oracle, pu, 0, cb)
     pu.close()
+
+
+def test_robust_filter_all_contigs_in_one_launch(gpu_ctx, oracle):
+    """hsgpu_partitions_set + hsgpu_robust_filter_all: loops 3+4 of keep_only_robust_variants for a whole batch
+    (a deep amplicon-like contig, a contig without reads, one without partitions, > 128 partitions), snps_in =
+    the pileup's own suspect columns; against the oracle contig by contig, and against the reference's own
+    partitions / snps_out where the compiled reference travelled"""
+    from oracle import pyoracle
+    chunks = [cases.small_case(seed=191), cases.ragged_cases()[1], cases.medium_case(seed=192), cases.deep_case(seed=193),
+              cases.hifi_case(seed=194), cases.small_case(seed=195, length=4000, depth=40), cases.small_case(seed=196)]
+    pk, pu = _build(gpu_ctx, chunks)
+    rng = np.random.default_rng(8)
+    all_parts, want = [], []
+    for ci, cb in enumerate(chunks):
+        if cb.n_reads == 0:
+            all_parts.append([])
+            want.append(np.zeros(0, np.int32))
+            continue
+        o = oracle.pileup(cb)
+        _, dist, alen = pu.stats()
+        oc = oracle.call_variants(o["col_off"], o["code"], pu.mean_distance(dist[ci], alen[ci]))
+        parts = None
+        if ci == 6:
+            parts = []  # no partition: nothing is kept (:640-642)
+        elif ci == 5:
+            parts = _random_partitions(rng, cb, o, 150)
+        elif pyoracle.ref_available():
+            R = pyoracle.RefCV(cb)
+            R.call_variants()
+            parts, filt, _ = R.robust()
+            if len(parts):
+                want_ref = filt["pos"]
+        if parts is None or (len(parts) == 0 and ci not in (6,)):
+            parts = _random_partitions(rng, cb, o, 10)
+        all_parts.append(parts)
+        w = oracle.robust_filter(o["col_off"], o["read_idx"], o["code"], oc["ref_base"], oc["second_base"], parts,
+                                 oc["suspect_pos"]) if len(parts) else np.zeros(0, np.int32)
+        want.append(w)
+    pu.partitions_set(all_parts)
+    for _ in range(2):  # the call may be repeated on resident partitions
+        kept, off = pu.robust_filter_all()
+        assert off.shape[0] == len(chunks) + 1
+        for ci in range(len(chunks)):
+            assert np.array_equal(kept[off[ci]:off[ci + 1]], want[ci]), ci
+    assert sum(w.size for w in want) > 0
+    # the single-contig call gives the same list and leaves the batch's partitions replaced: set them again
+    one = pu.robust_filter(2, all_parts[2], pu.suspects(2)[0])
+    assert np.array_equal(one, want[2])
+    pu.close()
