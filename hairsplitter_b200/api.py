@@ -83,7 +83,7 @@ EXPORTS = [
     "hsgpu_column_counts", "hsgpu_suspects", "hsgpu_suspects_all", "hsgpu_column_summary", "hsgpu_partition_tables", "hsgpu_robust_filter",
     "hsgpu_partitions_set", "hsgpu_robust_filter_all", "hsgpu_pileup_info",
     "hsgpu_read_pair_counts", "hsgpu_pairs_create", "hsgpu_pairs_compute", "hsgpu_pairs_fetch", "hsgpu_pairs_info",
-    "hsgpu_pairs_destroy", "hsgpu_graph_create", "hsgpu_graph_build", "hsgpu_graph_adjacency", "hsgpu_graph_whispers",
+    "hsgpu_pairs_destroy", "hsgpu_graph_create", "hsgpu_graph_create_ex", "hsgpu_graph_build", "hsgpu_graph_adjacency", "hsgpu_graph_whispers",
     "hsgpu_graph_destroy", "hsgpu_edlib_align_batch", "hsgpu_edlibAlign", "hsgpu_edlibFreeAlignResult",
 ]
 PAIRS_DENSE, PAIRS_KEEP_ORDER, PAIRS_SIMT = 1, 2, 4
@@ -151,6 +151,7 @@ def load():
     L.hsgpu_pairs_destroy.argtypes = [vp]
     L.hsgpu_pairs_destroy.restype = None
     L.hsgpu_graph_create.argtypes = [vp, i32, vp, vp, vp, f32, C.POINTER(vp)]
+    L.hsgpu_graph_create_ex.argtypes = [vp, i32, vp, vp, vp, vp, f32, C.POINTER(vp)]
     L.hsgpu_graph_build.argtypes = [vp, vp]
     L.hsgpu_graph_adjacency.argtypes = [vp, vp, i64, vp, vp]
     L.hsgpu_graph_whispers.argtypes = [vp, i64, vp, vp, i32, vp, vp]
@@ -355,6 +356,25 @@ class HostLogic:
         return cls._lib
 
     @classmethod
+    def read_graph_low_memory(cls, col, masked, error_rate):
+        """create_read_graph_low_memory of the host path (hs_sepreads.cpp) -> (adj_off, adj, reads cover consecutive SNPs)"""
+        L = cls.lib()
+        n_reads, snp_off, idx, code, rb, sb = col
+        snp_off, idx, code = _a(snp_off, np.int64), _a(idx, np.uint32), _a(code, np.uint8)
+        rb, sb, masked = _a(rb, np.uint8), _a(sb, np.uint8), _a(masked, np.int32)
+        f = L.hshost_read_graph_low_memory
+        f.restype = C.c_int64
+        f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        adj_off = np.zeros(masked.size + 1, np.int64)
+        cons = C.c_int(0)
+        n = f(n_reads, snp_off.size - 1, snp_off.ctypes.data, idx.ctypes.data, code.ctypes.data, rb.ctypes.data, sb.ctypes.data,
+              masked.size, masked.ctypes.data, float(error_rate), adj_off.ctypes.data, None, C.byref(cons))
+        adj = np.zeros(max(int(n), 1), np.int32)
+        f(n_reads, snp_off.size - 1, snp_off.ctypes.data, idx.ctypes.data, code.ctypes.data, rb.ctypes.data, sb.ctypes.data,
+          masked.size, masked.ctypes.data, float(error_rate), adj_off.ctypes.data, adj.ctypes.data, C.byref(cons))
+        return adj_off, adj[:int(n)], bool(cons.value)
+
+    @classmethod
     def build_partitions(cls, pos, off, read_idx, code, ref_base, second_base, mean_error):
         """suspect columns (CSR over columns) -> the final partitions as a list of dicts"""
         L = cls.lib()
@@ -525,15 +545,19 @@ class Graph:
     """hsgpu_graph: read graphs (create_read_graph_matrix) and chinese-whispers runs of a batch of windows over the
     device-resident counts of a Pairs object. windows: list of (contig, ascending read indices spanning the window)."""
 
-    def __init__(self, pairs: Pairs, windows, error_rate):
+    def __init__(self, pairs: Pairs, windows, error_rate, low_memory=None):
+        """low_memory: optional per-window flags -- the neighbour choice of create_read_graph_low_memory"""
         self.ctx, self.lib, self.pairs = pairs.ctx, pairs.lib, pairs
         self.win_contig = _a([w[0] for w in windows], np.int32)
         self.win_off = np.zeros(len(windows) + 1, np.int64)
         self.win_off[1:] = np.cumsum([len(w[1]) for w in windows])
         self.win_reads = (np.concatenate([_a(w[1], np.int32) for w in windows]) if windows else np.zeros(0, np.int32))
         h = C.c_void_p()
-        self.ctx.check(self.lib.hsgpu_graph_create(pairs.h, len(windows), self.win_contig.ctypes.data, self.win_off.ctypes.data,
-                                                   self.win_reads.ctypes.data, float(error_rate), C.byref(h)), "hsgpu_graph_create")
+        self.win_low = None if low_memory is None else _a(low_memory, np.uint8)
+        self.ctx.check(self.lib.hsgpu_graph_create_ex(pairs.h, len(windows), self.win_contig.ctypes.data, self.win_off.ctypes.data,
+                                                      self.win_reads.ctypes.data,
+                                                      None if self.win_low is None else self.win_low.ctypes.data,
+                                                      float(error_rate), C.byref(h)), "hsgpu_graph_create_ex")
         self.h = h
         self.replayed = 0
 

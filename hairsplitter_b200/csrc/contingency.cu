@@ -349,14 +349,65 @@ __device__ __noinline__ int rf_select_alt_tied(const uint8_t* order, const uint3
     return ' ';
 }
 
-__global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs a) {
+// One chunk of 32 cells of a column. Staged columns read the warp's shared arrays; a column too deep to be staged
+// (amplicons) is gathered again from the pileup -- the rare path, kept out of line so that the kernel stays small
+// (an earlier build of this kernel was bound by instruction fetch).
+struct RfCell {
+    int code;   // 0 = no cell in this lane
+    int32_t n;  // read index inside the contig
+};
+__device__ __noinline__ RfCell rf_gather_cell(const FilterArgs& a, int q, int64_t lb, int64_t l1, int64_t read0, int lane) {
+    RfCell c;
+    c.code = 0;
+    c.n = 0;
+    const int64_t l = lb + lane;
+    if (l < l1) {
+        const int32_t r = __ldg(a.tile_reads + l);
+        if (__ldg(a.read_start + r) <= q && q < __ldg(a.read_end + r)) {
+            c.code = __ldg(a.codes + __ldg(a.row_base + r) + q);
+            c.n = (int32_t)(r - read0);
+        }
+    }
+    return c;
+}
+
+__device__ __noinline__ float rf_chi_square(int n00, int n01, int n10, int n11) { return hs_chi_square(n00, n01, n10, n11); }
+
+// Several codes share the maximum of a (column, partition) pair: the reference's map iteration order decides
+// (:832-844). The order of first appearance among the partition's reads is rebuilt by lane 0 (rare path).
+__device__ __noinline__ int rf_tied_alt(const FilterArgs& a, const uint8_t* pst_p, int npad, int q, int64_t l0, int64_t l1,
+                                         int64_t read0, bool staged, int ncell, const uint8_t* s_code, const uint8_t* s_st,
+                                         uint32_t* s_hist, int ref, int nref, int max2) {
+    uint8_t order[HS_NCODES + 1];
+    int mo = 0;
+    auto see = [&](int code) {
+        const int idx = code - HS_CODE0;
+        bool seen = false;
+        for (int k = 0; k < mo; k++) seen |= order[k] == idx;
+        if (!seen) order[mo++] = (uint8_t)idx;
+    };
+    if (staged) {
+        for (int i = 0; i < ncell; i++)
+            if (s_st[i]) see(s_code[i]);
+    } else {
+        for (int64_t l = l0; l < l1; l++) {
+            const int32_t r = a.tile_reads[l];
+            if (a.read_start[r] <= q && q < a.read_end[r] && (pst_p[(int64_t)(r - read0) * npad] & 3)) see(a.codes[a.row_base[r] + q]);
+        }
+    }
+    if (nref > 0) s_hist[ref - HS_CODE0] = (uint32_t)nref;
+    const int alt = rf_select_alt_tied(order, s_hist, mo, ref, max2, a.lut);
+    if (nref > 0) s_hist[ref - HS_CODE0] = 0;
+    return alt;
+}
+
+__global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterArgs a) {
     __shared__ int32_t s_n_all[RF_WARPS][RF_CAP];
     __shared__ uint8_t s_code_all[RF_WARPS][RF_CAP];
     __shared__ uint8_t s_st_all[RF_WARPS][RF_CAP];
     __shared__ uint32_t s_hist_all[RF_WARPS][HS_NCODES + 3];
     __shared__ uint8_t s_touched_all[RF_WARPS][HS_NCODES + 3];
     __shared__ int s_m_all[RF_WARPS];
-    __shared__ uint8_t s_order_deep[RF_WARPS][HS_NCODES + 3];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int32_t* const s_n = s_n_all[wid];
     uint8_t* const s_code = s_code_all[wid];
@@ -389,86 +440,80 @@ __global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs
         // ---- the column's cells, in ascending read order ----
         int ncell = 0;
         for (int64_t lb = l0; lb < l1; lb += 32) {
-            const int64_t l = lb + lane;
-            bool hit = false;
-            int32_t r = 0;
-            if (l < l1) {
-                r = __ldg(a.tile_reads + l);
-                hit = __ldg(a.read_start + r) <= q && q < __ldg(a.read_end + r);
-            }
-            const unsigned mk = __ballot_sync(0xffffffffu, hit);
+            const RfCell cl = rf_gather_cell(a, q, lb, l1, read0, lane);
+            const unsigned mk = __ballot_sync(0xffffffffu, cl.code != 0);
             const int o = ncell + __popc(mk & lt);
-            if (hit && o < RF_CAP) {
-                s_n[o] = (int32_t)(r - read0);
-                s_code[o] = __ldg(a.codes + __ldg(a.row_base + r) + q);
+            if (cl.code != 0 && o < RF_CAP) {
+                s_n[o] = cl.n;
+                s_code[o] = (uint8_t)cl.code;
             }
             ncell += __popc(mk);
         }
         const bool staged = ncell <= RF_CAP;
+        const int nchunk = staged ? (ncell + 31) >> 5 : (int)((l1 - l0 + 31) >> 5);
         __syncwarp();
-        // visits every cell of the column, 32 at a time: body(valid, code, n, slot) with slot = index in the staged
-        // arrays (or -1 when the column is too deep to be staged and is gathered again)
-        auto for_cells = [&](auto body) {
-            if (staged) {
-                for (int i0 = 0; i0 < ncell; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool v = i < ncell;
-                    body(v, v ? (int)s_code[i] : 0, v ? s_n[i] : 0, v ? i : -1);
-                }
-            } else {
-                for (int64_t lb = l0; lb < l1; lb += 32) {
-                    const int64_t l = lb + lane;
-                    bool hit = false;
-                    int32_t r = 0;
-                    int code = 0;
-                    if (l < l1) {
-                        r = __ldg(a.tile_reads + l);
-                        hit = __ldg(a.read_start + r) <= q && q < __ldg(a.read_end + r);
-                        if (hit) code = __ldg(a.codes + __ldg(a.row_base + r) + q);
-                    }
-                    body(hit, code, (int32_t)(r - read0), -1);
-                }
-            }
-        };
+        // chunk ch of the column: the lane's cell (code 0 = none) and its slot in the staged arrays (-1 = not staged)
+#define RF_CELL(ch, cl, slot)                                                                     \
+    RfCell cl;                                                                                     \
+    int slot = -1;                                                                                 \
+    if (staged) {                                                                                  \
+        slot = 32 * (ch) + lane;                                                                   \
+        const bool v_ = slot < ncell;                                                              \
+        cl.code = v_ ? (int)s_code[slot] : 0;                                                      \
+        cl.n = v_ ? s_n[slot] : 0;                                                                 \
+        if (!v_) slot = -1;                                                                        \
+    } else {                                                                                       \
+        cl = rf_gather_cell(a, q, l0 + 32 * (int64_t)(ch), l1, read0, lane);                        \
+    }
         bool keep = false;
         int n_visited = 0;  // partitions whose states were read
         for (int pb = 0; pb < d.n_parts && !keep; pb += 128) {
-            // partitions pb..pb+127 that hold at least one of the column's reads
-            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-            for_cells([&](bool v, int, int32_t n, int) {
-                if (v) {
-                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(pm + (int64_t)n * d.pwords + (pb >> 5)));
-                    m0 |= x.x; m1 |= x.y; m2 |= x.z; m3 |= x.w;
+            // partitions pb..pb+127 that hold at least one of the column's reads (one 128-bit presence row per read)
+            uint32_t present[4] = {0, 0, 0, 0};
+#pragma unroll 1
+            for (int ch = 0; ch < nchunk; ch++) {
+                RF_CELL(ch, cl, slot)
+                (void)slot;
+                if (cl.code != 0) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(pm + (int64_t)cl.n * d.pwords + (pb >> 5)));
+                    present[0] |= x.x; present[1] |= x.y; present[2] |= x.z; present[3] |= x.w;
                 }
-            });
-            uint32_t present[4] = {__reduce_or_sync(0xffffffffu, m0), __reduce_or_sync(0xffffffffu, m1),
-                                   __reduce_or_sync(0xffffffffu, m2), __reduce_or_sync(0xffffffffu, m3)};
+            }
+#pragma unroll
+            for (int w = 0; w < 4; w++) present[w] = __reduce_or_sync(0xffffffffu, present[w]);
+#pragma unroll 1
             for (int w = 0; w < 4 && !keep; w++) {
                 uint32_t bits = present[w];
+#pragma unroll 1
                 while (bits && !keep) {
                     const int p = pb + 32 * w + __ffs(bits) - 1;
                     bits &= bits - 1;
                     n_visited++;
+                    const uint8_t* __restrict__ pst_p = pst + p;
                     // ---- pass 1: the partition's reads on this column. The column's own majority code is counted
                     // with ballots (its rows with state +1 / -1 are n11 / n01, :893-949), every other code goes
                     // through the warp's histogram ----
                     int nb = 0, nref = 0, n11 = 0, n01 = 0;
-                    for_cells([&](bool v, int code, int32_t n, int slot) {
+#pragma unroll 1
+                    for (int ch = 0; ch < nchunk; ch++) {
+                        RF_CELL(ch, cl, slot)
                         int sg = 0;
-                        if (v) {
-                            sg = __ldg(pst + (int64_t)n * d.npad + p) & 3;
+                        if (cl.code != 0) {
+                            sg = __ldg(pst_p + (int64_t)cl.n * d.npad) & 3;
                             if (slot >= 0) s_st[slot] = (uint8_t)sg;
                         }
-                        const bool act = v && sg != 0;
-                        const bool isref = act && code == ref;
+                        const bool act = sg != 0;
+                        const bool isref = act && cl.code == ref;
                         nb += __popc(__ballot_sync(0xffffffffu, act));
-                        nref += __popc(__ballot_sync(0xffffffffu, isref));
+                        const unsigned mref = __ballot_sync(0xffffffffu, isref);
+                        nref += __popc(mref);
                         n11 += __popc(__ballot_sync(0xffffffffu, isref && sg == 1));
                         n01 += __popc(__ballot_sync(0xffffffffu, isref && sg == 2));
                         if (act && !isref) {
-                            if (atomicAdd(&s_hist[code - HS_CODE0], 1u) == 0u) s_touched[atomicAdd(s_m, 1)] = (uint8_t)(code - HS_CODE0);
+                            if (atomicAdd(&s_hist[cl.code - HS_CODE0], 1u) == 0u)
+                                s_touched[atomicAdd(s_m, 1)] = (uint8_t)(cl.code - HS_CODE0);
                         }
-                    });
+                    }
                     __syncwarp();
                     const int m = *s_m;  // distinct codes other than ref_base
                     if (nb > 0) {
@@ -476,93 +521,45 @@ __global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs
                         // least 5 of the partition's reads on one code other than ref_base (codes >= 128 never count
                         // as ref_base in the reference's comparison, :838: no shortcut there)
                         int maxc = -1;
-                        for (int k0 = 0; k0 < m; k0 += 32) {
-                            const int k = k0 + lane;
-                            const int cnt = k < m ? (int)s_hist[s_touched[k]] : -1;
-                            maxc = max(maxc, cnt);
-                        }
+                        for (int k = lane; k < m; k += 32) maxc = max(maxc, (int)s_hist[s_touched[k]]);
                         maxc = __reduce_max_sync(0xffffffffu, maxc);
-                        const bool second = inlist || ref >= 128 || maxc > 4;
-                        if (second) {
+                        if (inlist || ref >= 128 || maxc > 4) {
                             // secondFrequent (:832-844): the most frequent code other than ref_base (ref_base itself
                             // competes when it is >= 128)
                             int max2 = maxc, alt = ' ';
-                            if (ref >= 128 && nref > 0 && nref >= max2) max2 = max(max2, nref);
+                            const bool ref_competes = ref >= 128 && nref > 0;
+                            if (ref_competes && nref > max2) max2 = nref;
                             int ties = 0, cand = ' ';
                             for (int k0 = 0; k0 < m; k0 += 32) {
                                 const int k = k0 + lane;
                                 const bool hitk = k < m && (int)s_hist[s_touched[k]] == max2;
                                 const unsigned mk = __ballot_sync(0xffffffffu, hitk);
                                 ties += __popc(mk);
-                                if (mk) {
-                                    const int src = __ffs(mk) - 1;
-                                    const int key = __shfl_sync(0xffffffffu, hitk ? (int)s_touched[k] + HS_CODE0 : 0, src);
-                                    cand = key;
-                                }
+                                if (mk) cand = __shfl_sync(0xffffffffu, hitk ? (int)s_touched[k] + HS_CODE0 : 0, __ffs(mk) - 1);
                             }
-                            if (ref >= 128 && nref > 0 && nref == max2) { ties++; cand = ref; }
-                            if (max2 < 0) {
-                                alt = ' ';  // no candidate at all (every read of the partition carries ref_base < 128)
-                            } else if (ties == 1) {
-                                alt = cand;
-                            } else {
-                                // several codes share the maximum: the map's iteration order decides. Lane 0 rebuilds
-                                // the order of first appearance and replays the reference (rare).
-                                int alt0 = ' ';
-                                if (staged) {
-                                    if (lane == 0) {
-                                        uint8_t order[HS_NCODES + 1];
-                                        int mo = 0;
-                                        if (nref > 0) s_hist[ref - HS_CODE0] = (uint32_t)nref;
-                                        for (int i = 0; i < ncell; i++) {
-                                            if (!s_st[i]) continue;
-                                            const int idx = s_code[i] - HS_CODE0;
-                                            bool seen = false;
-                                            for (int k = 0; k < mo; k++) seen |= order[k] == idx;
-                                            if (!seen) order[mo++] = (uint8_t)idx;
-                                        }
-                                        alt0 = rf_select_alt_tied(order, s_hist, mo, ref, max2, a.lut);
-                                        if (nref > 0) s_hist[ref - HS_CODE0] = 0;
-                                    }
+                            if (ref_competes && nref == max2) { ties++; cand = ref; }
+                            if (max2 >= 0) {
+                                if (ties == 1) {
+                                    alt = cand;
                                 } else {
-                                    // deep column: first appearances = lowest list position of every code
-                                    // (collected chunk by chunk in list order by the whole warp)
-                                    uint8_t* order = s_order_deep[wid];
-                                    int mo = 0;
-                                    for_cells([&](bool v, int code, int32_t n, int) {
-                                        int sg = 0;
-                                        if (v) sg = __ldg(pst + (int64_t)n * d.npad + p) & 3;
-                                        unsigned todo = __ballot_sync(0xffffffffu, v && sg != 0);
-                                        while (todo) {  // in lane order = read order
-                                            const int src = __ffs(todo) - 1;
-                                            todo &= todo - 1;
-                                            const int idx = __shfl_sync(0xffffffffu, code, src) - HS_CODE0;
-                                            bool seen = false;
-                                            for (int k = lane; k < mo; k += 32) seen |= order[k] == idx;
-                                            if (!__any_sync(0xffffffffu, seen)) {
-                                                if (lane == 0) order[mo] = (uint8_t)idx;
-                                                mo++;
-                                                __syncwarp();
-                                            }
-                                        }
-                                    });
-                                    if (lane == 0) {
-                                        if (nref > 0) s_hist[ref - HS_CODE0] = (uint32_t)nref;
-                                        alt0 = rf_select_alt_tied(order, s_hist, mo, ref, max2, a.lut);
-                                        if (nref > 0) s_hist[ref - HS_CODE0] = 0;
-                                    }
+                                    int alt0 = ' ';
+                                    if (lane == 0)
+                                        alt0 = rf_tied_alt(a, pst_p, d.npad, q, l0, l1, read0, staged, ncell, s_code, s_st, s_hist, ref,
+                                                           nref, max2);
+                                    alt = __shfl_sync(0xffffffffu, alt0, 0);
                                 }
-                                alt = __shfl_sync(0xffffffffu, alt0, 0);
                             }
                             // ---- pass 2: n10 / n00 ----
                             int n10 = 0, n00 = 0;
-                            if (alt != ref) {
-                                for_cells([&](bool v, int code, int32_t n, int slot) {
+                            if (alt != ref && alt != ' ') {
+#pragma unroll 1
+                                for (int ch = 0; ch < nchunk; ch++) {
+                                    RF_CELL(ch, cl, slot)
                                     int sg = 0;
-                                    if (v && code == alt) sg = slot >= 0 ? (int)s_st[slot] : (__ldg(pst + (int64_t)n * d.npad + p) & 3);
+                                    if (cl.code == alt) sg = slot >= 0 ? (int)s_st[slot] : (__ldg(pst_p + (int64_t)cl.n * d.npad) & 3);
                                     n10 += __popc(__ballot_sync(0xffffffffu, sg == 1));
                                     n00 += __popc(__ballot_sync(0xffffffffu, sg == 2));
-                                });
+                                }
                             }
                             // loop 3 (:721-738): columns of snps_in; loop 4 (:745-764): rescue of every other column (also
                             // of suspects that failed loop 3). The chi-square is only evaluated where an integer
@@ -570,7 +567,7 @@ __global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs
                             const bool c3 = inlist && (double)(n00 + n01 + n10 + n11) > __dmul_rn(0.5, (double)a.depth[g]);
                             const bool c4 = (f & HS_FLAG_RESCUE) && n10 + n00 > 4 && n01 + n11 > 4;
                             if (c3 || c4) {
-                                const float chi = hs_chi_square(n00, n01, n10, n11);
+                                const float chi = rf_chi_square(n00, n01, n10, n11);
                                 if ((c3 && chi > 15.f) || (c4 && (double)chi > 20.0)) keep = true;
                             }
                         }
@@ -582,6 +579,7 @@ __global__ void __launch_bounds__(32 * RF_WARPS) robust_filter_kernel(FilterArgs
                 }
             }
         }
+#undef RF_CELL
         if (lane == 0) {
             if (keep) a.kept[g] = 1;
             atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 4), (unsigned long long)ncell);

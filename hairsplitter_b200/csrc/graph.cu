@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "pairs_view.cuh"
 
 #define GR_WARPS 8  // warps (= masked reads, runs) per CTA
 
@@ -49,9 +50,10 @@ struct hsgpu_graph {
     // device
     int32_t *d_win_contig = nullptr, *d_win_reads = nullptr, *d_read_win = nullptr;
     int64_t *d_win_off = nullptr, *d_sel_off = nullptr;
-    const int32_t** d_sim = nullptr;  // per contig: base of its n_pad x n_pad block
-    const int32_t** d_diff = nullptr;
-    int32_t *d_contig_n = nullptr, *d_contig_npad = nullptr;
+    HsPairView* d_views = nullptr;  // per contig: where its similarity / difference blocks are (pairs_view.cuh)
+    uint8_t* d_win_low = nullptr;   // per window: 1 = the distance rule of create_read_graph_low_memory
+    bool any_low = false;
+    int32_t* d_contig_n = nullptr;
     uint32_t* d_sel = nullptr;   // per window m rows of ceil(m/32) words: bit j of row i = read i selected j
     uint8_t* d_flag = nullptr;   // per masked read: the selection depends on the order of equal distances
     uint32_t* d_deg = nullptr;
@@ -59,38 +61,47 @@ struct hsgpu_graph {
     int32_t* d_adj = nullptr;      // neighbours as local indices, ascending
 };
 
-int hs_pairs_view(hsgpu_pairs* h, int32_t contig, hsgpu_ctx** ctx, const int32_t** sim, const int32_t** diff, int32_t* n,
-                  int32_t* n_pad);
+int hs_pairs_view(hsgpu_pairs* h, int32_t contig, hsgpu_ctx** ctx, HsPairView* view);
 int hs_pairs_contigs(hsgpu_pairs* h);
 
 // ---- distances of one masked read to the others of its window ----------------------------------------------
-// sd[j] = sims+diffs, dist[j] as the reference computes it (:752-766). Returns max_compat.
-__device__ __forceinline__ void gr_distances(const int32_t* __restrict__ row_s, const int32_t* __restrict__ row_d,
-                                             const int32_t* __restrict__ M, int m, int i, int lane, float* dist) {
+// dist[j] as the reference computes it: create_read_graph_matrix (:752-766) or, with `low`, the pairwise loop of
+// create_read_graph_low_memory (:583-628), which has no `sims > 0` guard (a pair without a common SNP gives
+// 1 - 0 / float(0) = NaN, a pair with differences only gets a distance too) and skips the reads that appear in no
+// SNP column. Returns true when a NaN survives the overlap filter: the neighbour choice then hangs on what
+// std::sort does with it, and the read is replayed on the host.
+__device__ __forceinline__ bool gr_distances(const HsPairView& v, const int32_t* __restrict__ M, int m, int i, int lane,
+                                             float* dist, bool low) {
     int max_compat = 0;
+    const int ri = M[i];
     for (int j = lane; j < m; j += 32) {
         float ds = 0.f;
         if (j != i) {
             const int r = M[j];
-            const int s = __ldg(row_s + r), d = __ldg(row_d + r);
-            if (s > 0) {
-                const float diff = (float)max(0, d - 1);                       // :754
-                ds = __fsub_rn(1.0f, __fdiv_rn(diff, (float)(s + d)));         // :755
+            int s, d;
+            hs_pair_get(v, ri, r, s, d);
+            if (low ? (__ldg(v.has_cells + r) != 0) : (s > 0)) {
+                const float diff = (float)max(0, d - 1);                       // :754 / :618
+                ds = __fsub_rn(1.0f, __fdiv_rn(diff, (float)(s + d)));         // :755 / :618
                 max_compat = max(max_compat, s);
             }
         }
         dist[j] = ds;
     }
     max_compat = __reduce_max_sync(0xffffffffu, max_compat);
-    const double lim = 0.7 * (double)max_compat;  // :763, double arithmetic
+    const double lim = 0.7 * (double)max_compat;  // :763 / :628, double arithmetic
+    bool nan = false;
     for (int j = lane; j < m; j += 32) {
         if (j != i) {
             const int r = M[j];
-            const int s = __ldg(row_s + r), d = __ldg(row_d + r);
+            int s, d;
+            hs_pair_get(v, ri, r, s, d);
             if ((double)(s + d) < lim) dist[j] = 0.f;
+            nan |= dist[j] != dist[j];
         }
     }
     __syncwarp();
+    return __any_sync(0xffffffffu, nan);
 }
 
 __device__ __forceinline__ int gr_warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
@@ -128,9 +139,8 @@ __global__ void __launch_bounds__(GR_WARPS * 32)
 read_graph_kernel(int64_t n_items, const int64_t* __restrict__ items, const int64_t* __restrict__ item_off,
                   const int32_t* __restrict__ read_win, const int64_t* __restrict__ win_off,
                   const int32_t* __restrict__ win_reads, const int32_t* __restrict__ win_contig,
-                  const int32_t* const* __restrict__ sim, const int32_t* const* __restrict__ diff,
-                  const int32_t* __restrict__ contig_n, const int32_t* __restrict__ contig_npad,
-                  const int64_t* __restrict__ sel_off, float error_rate, int max_m, uint32_t* __restrict__ sel,
+                  const HsPairView* __restrict__ views, const uint8_t* __restrict__ win_low,
+                  const int32_t* __restrict__ contig_n, const int64_t* __restrict__ sel_off, float error_rate, int max_m, uint32_t* __restrict__ sel,
                   uint8_t* __restrict__ flag, float* __restrict__ rows) {
     extern __shared__ float gr_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,10 +154,18 @@ read_graph_kernel(int64_t n_items, const int64_t* __restrict__ items, const int6
     const int32_t* M = win_reads + g0;
     const int c = win_contig[w];
     const int R = contig_n[c];
-    const int64_t ld = contig_npad[c];
-    const int32_t* row_s = sim[c] + (int64_t)M[i] * ld;
-    const int32_t* row_d = diff[c] + (int64_t)M[i] * ld;
-    gr_distances(row_s, row_d, M, m, i, lane, dist);
+    const HsPairView view = views[c];
+    const bool low = win_low != nullptr && win_low[w] != 0;
+    if (low && __ldg(view.has_cells + M[i]) == 0) {
+        // create_read_graph_low_memory skips a read that appears in no SNP column (mask_extend, :569-576)
+        if (MODE == 0) {
+            uint32_t* out0 = sel + sel_off[w] + (int64_t)i * ((m + 31) >> 5);
+            for (int k = lane; k < ((m + 31) >> 5); k += 32) out0[k] = 0;
+            if (lane == 0) flag[g] = 0;
+        }
+        return;
+    }
+    const bool has_nan = gr_distances(view, M, m, i, lane, dist, low);
     if (MODE == 1) {
         float* out = rows + item_off[item];
         for (int j = lane; j < m; j += 32) out[j] = dist[j];
@@ -183,7 +201,7 @@ read_graph_kernel(int64_t n_items, const int64_t* __restrict__ items, const int6
         }
     }
     // ---- selection (:808-817): entries >= above (or == 1) always link, the rest while fewer than 5 are linked ----
-    bool ambiguous = below < 0.f;  // zeros would qualify: order among all n_reads zeros matters -> host
+    bool ambiguous = below < 0.f || has_nan;  // zeros would qualify: order among all n_reads zeros matters -> host
     int n_a = 0, n_rest = 0;
     for (int j = lane; j < m; j += 32) {
         const float v = dist[j];
@@ -405,8 +423,8 @@ static void replay_selection(int R, int m, const int32_t* M, const float* dist, 
 static void graph_release(hsgpu_graph* g) {
     hsgpu_ctx* ctx = g->ctx;
     hs_free(ctx, g->d_win_contig); hs_free(ctx, g->d_win_reads); hs_free(ctx, g->d_read_win);
-    hs_free(ctx, g->d_win_off); hs_free(ctx, g->d_sel_off); hs_free(ctx, g->d_sim); hs_free(ctx, g->d_diff);
-    hs_free(ctx, g->d_contig_n); hs_free(ctx, g->d_contig_npad); hs_free(ctx, g->d_sel); hs_free(ctx, g->d_flag);
+    hs_free(ctx, g->d_win_off); hs_free(ctx, g->d_sel_off); hs_free(ctx, g->d_views); hs_free(ctx, g->d_win_low);
+    hs_free(ctx, g->d_contig_n); hs_free(ctx, g->d_sel); hs_free(ctx, g->d_flag);
     hs_free(ctx, g->d_deg); hs_free(ctx, g->d_adj_off); hs_free(ctx, g->d_adj);
 }
 
@@ -424,13 +442,17 @@ extern "C" {
 
 int hsgpu_graph_create(hsgpu_pairs* pairs, int32_t n_windows, const int32_t* win_contig, const int64_t* win_off,
                        const int32_t* win_reads, float error_rate, hsgpu_graph** out) {
+    return hsgpu_graph_create_ex(pairs, n_windows, win_contig, win_off, win_reads, nullptr, error_rate, out);
+}
+
+int hsgpu_graph_create_ex(hsgpu_pairs* pairs, int32_t n_windows, const int32_t* win_contig, const int64_t* win_off,
+                          const int32_t* win_reads, const uint8_t* win_low_memory, float error_rate, hsgpu_graph** out) {
     if (!pairs || !out || n_windows < 0 || (n_windows > 0 && (!win_contig || !win_off))) return HSGPU_ERR_ARG;
     hsgpu_ctx* ctx = nullptr;
     const int n_contigs = hs_pairs_contigs(pairs);
     {
-        const int32_t *s, *d;
-        int32_t n, np;
-        if (n_contigs <= 0 || hs_pairs_view(pairs, 0, &ctx, &s, &d, &n, &np) != HSGPU_OK) return HSGPU_ERR_ARG;
+        HsPairView v0;
+        if (n_contigs <= 0 || hs_pairs_view(pairs, 0, &ctx, &v0) != HSGPU_OK) return HSGPU_ERR_ARG;
     }
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     hsgpu_graph* g = new hsgpu_graph;
@@ -441,14 +463,15 @@ int hsgpu_graph_create(hsgpu_pairs* pairs, int32_t n_windows, const int32_t* win
     g->error_rate = error_rate;
     g->total_masked = n_windows ? win_off[n_windows] : 0;
     if (g->total_masked > 0 && !win_reads) { delete g; return HSGPU_ERR_ARG; }
-    std::vector<const int32_t*> sim(n_contigs), diff(n_contigs);
-    std::vector<int32_t> cn(n_contigs), cnp(n_contigs);
+    std::vector<HsPairView> views(n_contigs);
+    std::vector<int32_t> cn(n_contigs);
     for (int c = 0; c < n_contigs; c++) {
         hsgpu_ctx* cx;
-        if (hs_pairs_view(pairs, c, &cx, &sim[c], &diff[c], &cn[c], &cnp[c]) != HSGPU_OK) {
+        if (hs_pairs_view(pairs, c, &cx, &views[c]) != HSGPU_OK) {
             delete g;
             HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_graph_create: call hsgpu_pairs_compute first");
         }
+        cn[c] = views[c].n;
     }
     g->h_contig_n = cn;
     g->h_win_contig.assign(win_contig, win_contig + n_windows);
@@ -474,19 +497,24 @@ int hsgpu_graph_create(hsgpu_pairs* pairs, int32_t n_windows, const int32_t* win
         g->h_sel_off[w + 1] = g->h_sel_off[w] + m * ((m + 31) / 32);
     }
     g->sel_words = g->h_sel_off[n_windows];
-    if ((size_t)GR_WARPS * 2 * g->max_m * sizeof(int32_t) > 200 * 1024) {
+    // read_graph_kernel keeps one distance row per warp in shared memory (whispers_kernel: two label arrays, checked
+    // in hsgpu_graph_whispers)
+    if ((size_t)GR_WARPS * g->max_m * sizeof(float) > 200 * 1024) {
         delete g;
-        HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_graph_create: more than 3200 reads span one window (shared-memory label arrays)");
+        HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_graph_create: more than 6400 reads span one window");
     }
     GR_TRY(hs_alloc(ctx, &g->d_win_contig, n_windows));
     GR_TRY(hs_alloc(ctx, &g->d_win_off, n_windows + 1));
     GR_TRY(hs_alloc(ctx, &g->d_sel_off, n_windows + 1));
     GR_TRY(hs_alloc(ctx, &g->d_win_reads, g->total_masked));
     GR_TRY(hs_alloc(ctx, &g->d_read_win, g->total_masked));
-    GR_TRY(hs_alloc(ctx, &g->d_sim, n_contigs));
-    GR_TRY(hs_alloc(ctx, &g->d_diff, n_contigs));
+    GR_TRY(hs_alloc(ctx, &g->d_views, n_contigs));
     GR_TRY(hs_alloc(ctx, &g->d_contig_n, n_contigs));
-    GR_TRY(hs_alloc(ctx, &g->d_contig_npad, n_contigs));
+    if (win_low_memory) {
+        GR_TRY(hs_alloc(ctx, &g->d_win_low, n_windows));
+        GR_TRY(hs_h2d(ctx, g->d_win_low, win_low_memory, n_windows));
+        for (int w = 0; w < n_windows; w++) g->any_low = g->any_low || win_low_memory[w];
+    }
     GR_TRY(hs_alloc(ctx, &g->d_sel, g->sel_words));
     GR_TRY(hs_alloc(ctx, &g->d_flag, g->total_masked));
     GR_TRY(hs_alloc(ctx, &g->d_deg, g->total_masked));
@@ -496,10 +524,8 @@ int hsgpu_graph_create(hsgpu_pairs* pairs, int32_t n_windows, const int32_t* win
     GR_TRY(hs_h2d(ctx, g->d_sel_off, g->h_sel_off.data(), n_windows + 1));
     GR_TRY(hs_h2d(ctx, g->d_win_reads, g->h_win_reads.data(), g->total_masked));
     GR_TRY(hs_h2d(ctx, g->d_read_win, read_win.data(), g->total_masked));
-    GR_TRY(hs_h2d(ctx, g->d_sim, sim.data(), n_contigs));
-    GR_TRY(hs_h2d(ctx, g->d_diff, diff.data(), n_contigs));
+    GR_TRY(hs_h2d(ctx, g->d_views, views.data(), n_contigs));
     GR_TRY(hs_h2d(ctx, g->d_contig_n, cn.data(), n_contigs));
-    GR_TRY(hs_h2d(ctx, g->d_contig_npad, cnp.data(), n_contigs));
     GR_TRY(cudaStreamSynchronize(ctx->stream));  // the staging vectors go out of scope
     *out = g;
     return HSGPU_OK;
@@ -532,8 +558,8 @@ int hsgpu_graph_build(hsgpu_graph* g, int64_t* n_replayed) {
     }
     HS_KERNEL(ctx, "read_graph_kernel",
               read_graph_kernel<0><<<blocks, GR_WARPS * 32, smem, ctx->stream>>>(
-                  total, nullptr, nullptr, g->d_read_win, g->d_win_off, g->d_win_reads, g->d_win_contig, g->d_sim, g->d_diff,
-                  g->d_contig_n, g->d_contig_npad, g->d_sel_off, g->error_rate, g->max_m, g->d_sel, g->d_flag, nullptr));
+                  total, nullptr, nullptr, g->d_read_win, g->d_win_off, g->d_win_reads, g->d_win_contig, g->d_views, g->d_win_low,
+                  g->d_contig_n, g->d_sel_off, g->error_rate, g->max_m, g->d_sel, g->d_flag, nullptr));
     // reads whose selection hangs on std::sort's order of equal distances: replay the reference on the host
     std::vector<uint8_t> flag((size_t)total);
     HS_CUDA(ctx, hs_d2h(ctx, flag.data(), g->d_flag, total));
@@ -563,8 +589,8 @@ int hsgpu_graph_build(hsgpu_graph* g, int64_t* n_replayed) {
         HS_CUDA(ctx, hs_h2d(ctx, d_item_off, item_off.data(), ni));
         HS_KERNEL(ctx, "read_graph_rows_kernel",
                   read_graph_kernel<1><<<(unsigned)((ni + GR_WARPS - 1) / GR_WARPS), GR_WARPS * 32, smem, ctx->stream>>>(
-                      ni, d_items, d_item_off, g->d_read_win, g->d_win_off, g->d_win_reads, g->d_win_contig, g->d_sim,
-                      g->d_diff, g->d_contig_n, g->d_contig_npad, g->d_sel_off, g->error_rate, g->max_m, g->d_sel,
+                      ni, d_items, d_item_off, g->d_read_win, g->d_win_off, g->d_win_reads, g->d_win_contig, g->d_views,
+                      g->d_win_low, g->d_contig_n, g->d_sel_off, g->error_rate, g->max_m, g->d_sel,
                       g->d_flag, d_rows));
         std::vector<float> rows((size_t)n_floats);
         HS_CUDA(ctx, hs_d2h(ctx, rows.data(), d_rows, n_floats));
@@ -628,11 +654,16 @@ int hsgpu_graph_whispers(hsgpu_graph* g, int64_t n_runs, const int32_t* run_wind
     if (n_runs == 0) return HSGPU_OK;
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<int64_t> run_off((size_t)n_runs + 1, 0);
+    int32_t run_max_m = 1;  // the largest window a run works on sizes the shared-memory label arrays
     for (int64_t i = 0; i < n_runs; i++) {
         const int w = run_window[i];
         if (w < 0 || w >= g->n_windows) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_graph_whispers: bad window index");
         run_off[i + 1] = run_off[i] + (g->h_win_off[w + 1] - g->h_win_off[w]);
+        run_max_m = std::max<int32_t>(run_max_m, (int32_t)(g->h_win_off[w + 1] - g->h_win_off[w]));
     }
+    if ((size_t)GR_WARPS * 2 * run_max_m * sizeof(int32_t) > 200 * 1024)
+        HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_graph_whispers: a run works on a window of more than 3200 reads (shared-memory "
+                                      "label arrays); cluster such windows from hsgpu_graph_adjacency on the host");
     std::vector<int64_t> order_base((size_t)g->n_contigs + 1, 0);
     for (int c = 0; c < g->n_contigs; c++) order_base[c + 1] = order_base[c] + (int64_t)n_orders * g->h_contig_n[c];
     const int64_t n_lab = run_off[n_runs];
@@ -654,12 +685,12 @@ int hsgpu_graph_whispers(hsgpu_graph* g, int64_t n_runs, const int32_t* run_wind
     HS_KERNEL(ctx, "window_order_kernel",
               window_order_kernel<<<(unsigned)((n_items + GR_WARPS - 1) / GR_WARPS), GR_WARPS * 32, 0, ctx->stream>>>(
                   n_items, n_orders, g->d_win_off, g->d_win_reads, g->d_win_contig, g->d_contig_n, d_order_base, d_rank, d_order));
-    const size_t smem = (size_t)GR_WARPS * 2 * g->max_m * sizeof(int32_t);
+    const size_t smem = (size_t)GR_WARPS * 2 * run_max_m * sizeof(int32_t);
     if (smem > 48 * 1024)
         HS_CUDA(ctx, cudaFuncSetAttribute(whispers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HS_KERNEL(ctx, "whispers_kernel",
               whispers_kernel<<<(unsigned)((n_runs + GR_WARPS - 1) / GR_WARPS), GR_WARPS * 32, smem, ctx->stream>>>(
-                  n_runs, d_run_window, d_run_off, d_init, g->d_win_off, g->d_adj_off, g->d_adj, n_orders, d_order, g->max_m, d_out));
+                  n_runs, d_run_window, d_run_off, d_init, g->d_win_off, g->d_adj_off, g->d_adj, n_orders, d_order, run_max_m, d_out));
     HS_CUDA(ctx, hs_d2h(ctx, labels_out, d_out, n_lab));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     hs_free(ctx, d_run_window); hs_free(ctx, d_run_off); hs_free(ctx, d_init); hs_free(ctx, d_out);

@@ -15,10 +15,10 @@
 //            two M128 x N256 x K32 instructions per 32 SNPs: A_i x [A_j;R_j] lands on columns 0..255,
 //            R_i x [A_j;R_j] on columns 128..383, so the middle block accumulates both cross products;
 //   warps 2-5 epilogue: tcgen05.ld the three blocks, sim = 3*acc0 + acc2, diff = acc1, zero the
-//            diagonal, store tile (i,j) row-wise and, by symmetry, tile (j,i) column-wise (coalesced).
-// Reads are ordered by their first SNP before tiling (the output is written back through the
-// permutation), so tiles far from the diagonal share no SNP block and are never scheduled: the work is
-// the band of overlapping reads, not R^2 * S.
+//            diagonal, store the 128 x 128 block of the tile pair row-wise (16-byte stores).
+// Reads are ordered by their first SNP before tiling, so tiles far from the diagonal share no SNP block and
+// are never scheduled: work AND output are the band of overlapping reads, not R^2 (pairs_view.cuh): every
+// scheduled tile pair owns one block per matrix, a per-contig tile map finds it.
 #include <cuda.h>  // CUtensorMap and its enums only; the encoder is fetched from the driver at run time
 
 #include <algorithm>
@@ -28,6 +28,7 @@
 #include <atomic>
 
 #include "common.cuh"
+#include "pairs_view.cuh"
 
 #define PG_TILE 128                     // rows per tile (UMMA M, and N per operand half)
 #define PG_BK 128                       // SNPs (= bytes of K) per pipeline stage: one 128-byte swizzle row
@@ -45,31 +46,29 @@ struct PairWork {
 };
 
 struct PairContig {
-    int64_t row0;     // first row of the contig in the stacked operand matrices
-    int64_t out_off;  // element offset of the contig's n_pad x n_pad block in sim / diff
+    int64_t row0;      // first row of the contig in the stacked operand matrices
+    int64_t map_off;   // offset of the contig's nt x nt tile map
+    int64_t read0;     // first read of the contig in the per-read arrays (row_of, has_cells)
     int32_t n, n_pad;
-    int32_t identity;  // reads already in first-SNP order: rows map to themselves
-    int32_t pad;
 };
 
 struct hsgpu_pairs {
     hsgpu_ctx* ctx = nullptr;
     int32_t n_contigs = 0;
     int32_t flags = 0;
-    int64_t total_rows = 0, k_ld = 0, n_cells = 0, out_elems = 0, n_work = 0;
+    int64_t total_rows = 0, k_ld = 0, n_cells = 0, n_work = 0;
     int64_t kblocks_listed = 0, kblocks_dense = 0, tiles_dense = 0;
     std::vector<PairContig> h_contigs;
     uint8_t *d_A = nullptr, *d_R = nullptr;
     int32_t* d_rowmap = nullptr;   // stacked row -> read index in the contig (-1 = padding)
-    int32_t* d_rowof = nullptr;    // per contig-local read: stacked row (inverse map, for the one-hot scatter)
+    int32_t* d_rowof = nullptr;    // per read: stacked row (inverse map, for the one-hot scatter)
+    int32_t* d_rowloc = nullptr;   // per read: row inside its contig (what HsPairView.row_of points into)
+    uint8_t* d_has_cells = nullptr;  // per read: appears in at least one SNP column
     PairContig* d_contigs = nullptr;
     PairWork* d_work = nullptr;
-    int32_t *d_sim = nullptr, *d_diff = nullptr;    // results in the caller's read order (what fetch returns)
-    int32_t *d_psim = nullptr, *d_pdiff = nullptr;  // results in tile order; alias d_sim/d_diff when no contig was reordered
+    int32_t *d_sim = nullptr, *d_diff = nullptr;  // one 128 x 128 block per scheduled tile pair (work item)
+    int32_t* d_tilemap = nullptr;                 // per contig nt x nt: block of the tile pair (ti <= tj), -1 = none
     bool all_identity = true;
-    uint8_t* d_sched = nullptr;      // per contig nt x nt: 1 where the tile pair was scheduled
-    int64_t* d_sched_off = nullptr;
-    int32_t* d_row_contig = nullptr;  // stacked row -> contig
     int64_t* d_read_base = nullptr;
     int32_t* d_err = nullptr;
     // the SNP columns (inputs), kept until the operands are built
@@ -190,6 +189,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1)
 pair_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapR,
                  const PairWork* __restrict__ work, int n_work, const PairContig* __restrict__ contigs,
                  int32_t* __restrict__ sim, int32_t* __restrict__ diff, int32_t* __restrict__ err) {
+    // sim / diff: one 128 x 128 block per work item (pairs_view.cuh)
     extern __shared__ unsigned char pg_raw[];
     // 1024-byte alignment: the swizzle pattern is a function of the shared-memory address
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pg_raw) + 1023) & ~(uintptr_t)1023);
@@ -287,23 +287,20 @@ pair_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
         }
     } else {
         // ===== epilogue: 4 warps, warp (w % 4) owns TMEM lanes 32*(w % 4) .. +31 =====
-        // Output in tile (= first-SNP) order, n_pad x n_pad per contig: thread t owns row t of the tile, so tile
-        // (i,j) goes out as 16-byte pieces of its row and the mirror tile (j,i) as one column per store, the
-        // 32 lanes of a warp writing 32 consecutive ints.
+        // Output: the 128 x 128 block of work item w (pairs_view.cuh); thread t owns row t of the tile and stores
+        // it as 16-byte pieces. The mirror tile is not materialised: readers swap the indices.
         const int quarter = warp & 3;
         const int t = quarter * 32 + lane;  // row of the tile
         uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const PairWork wk = work[w];
-            const PairContig pc = contigs[wk.contig];
-            const int64_t ld = pc.n_pad;
             const int orow = wk.ti * PG_TILE + t;
             const int ocol0 = wk.tj * PG_TILE;
             mbar_wait(acc_full, acc_phase, err, 4);
             acc_phase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            int32_t* const sim_c = sim + pc.out_off;
-            int32_t* const diff_c = diff + pc.out_off;
+            int32_t* const sim_b = sim + (int64_t)w * HS_PV_BLOCK + t * PG_TILE;
+            int32_t* const diff_b = diff + (int64_t)w * HS_PV_BLOCK + t * PG_TILE;
             const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
             for (int cb = 0; cb < 4; cb++) {
@@ -324,20 +321,12 @@ pair_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                     v0[c] = dead ? 0u : 3u * v0[c] + v2[c];
                     v1[c] = dead ? 0u : v1[c];
                 }
-                int4* ps = reinterpret_cast<int4*>(sim_c + (int64_t)orow * ld + ocol0 + cb * 32);
-                int4* pd = reinterpret_cast<int4*>(diff_c + (int64_t)orow * ld + ocol0 + cb * 32);
+                int4* ps = reinterpret_cast<int4*>(sim_b + cb * 32);
+                int4* pd = reinterpret_cast<int4*>(diff_b + cb * 32);
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     ps[c] = make_int4((int)v0[4 * c], (int)v0[4 * c + 1], (int)v0[4 * c + 2], (int)v0[4 * c + 3]);
                     pd[c] = make_int4((int)v1[4 * c], (int)v1[4 * c + 1], (int)v1[4 * c + 2], (int)v1[4 * c + 3]);
-                }
-                if (wk.ti != wk.tj) {
-#pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const int64_t o = (int64_t)(ocol0 + cb * 32 + c) * ld + orow;
-                        sim_c[o] = (int)v0[c];
-                        diff_c[o] = (int)v1[c];
-                    }
                 }
             }
         }
@@ -351,70 +340,42 @@ pair_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     }
 }
 
-// Back to the caller's read order: out[r][k] = P[row(r)][row(k)] where the tile pair of (row(r), row(k)) was
-// scheduled, else 0. One CTA per output row; the source row of P is contiguous (n_pad ints), so the scattered
-// 4-byte reads stay inside a few KB that L1 holds, and every output row is written once, coalesced.
-__global__ void __launch_bounds__(256) pair_unpermute_kernel(const PairContig* __restrict__ contigs,
-                                                             const int32_t* __restrict__ row_contig,
-                                                             const int64_t* __restrict__ read_base,
-                                                             const int32_t* __restrict__ rowof,
-                                                             const uint8_t* __restrict__ sched,
-                                                             const int64_t* __restrict__ sched_off,
-                                                             const int32_t* __restrict__ psim, const int32_t* __restrict__ pdiff,
-                                                             int32_t* __restrict__ sim, int32_t* __restrict__ diff) {
-    const int64_t g = blockIdx.x;  // stacked row = (contig, read r in the caller's numbering)
-    const int c = row_contig[g];
-    const PairContig pc = contigs[c];
-    const int r = (int)(g - pc.row0);
-    if (r >= pc.n) return;
-    const int64_t rb0 = read_base[c];
-    const int ir = rowof[rb0 + r] - (int)pc.row0;
-    const int nt = pc.n_pad / PG_TILE;
-    const uint8_t* sc = sched + sched_off[c] + (int64_t)(ir / PG_TILE) * nt;
-    const int32_t* ps = psim + pc.out_off + (int64_t)ir * pc.n_pad;
-    const int32_t* pd = pdiff + pc.out_off + (int64_t)ir * pc.n_pad;
-    int32_t* os = sim + pc.out_off + (int64_t)r * pc.n_pad;
-    int32_t* od = diff + pc.out_off + (int64_t)r * pc.n_pad;
-    for (int k = threadIdx.x; k < pc.n_pad; k += blockDim.x) {
-        int vs = 0, vd = 0;
-        if (k < pc.n) {
-            const int ik = rowof[rb0 + k] - (int)pc.row0;
-            if (sc[ik / PG_TILE]) {
-                vs = ps[ik];
-                vd = pd[ik];
-            }
-        }
-        os[k] = vs;
-        od[k] = vd;
+// The dense n x n matrices of one contig in the caller's read order (hsgpu_pairs_fetch: tests and measurements).
+__global__ void __launch_bounds__(256) pair_dense_kernel(HsPairView v, int32_t* __restrict__ sim, int32_t* __restrict__ diff) {
+    const int r = blockIdx.x;
+    for (int k = threadIdx.x; k < v.n; k += blockDim.x) {
+        int s, d;
+        hs_pair_get(v, r, k, s, d);
+        sim[(int64_t)r * v.n + k] = s;
+        diff[(int64_t)r * v.n + k] = d;
     }
 }
 
-// Plain SIMT statement of the same contraction over the same operands (dp4a, one thread per output
-// element). Only reachable with HSGPU_PAIRS_SIMT: the A/B check of the tensor-core kernel in the tests.
-__global__ void __launch_bounds__(256) pair_simt_kernel(const PairContig* __restrict__ contigs, int contig, int64_t ld_k,
-                                                        const uint8_t* __restrict__ A, const uint8_t* __restrict__ R,
-                                                        const int32_t* __restrict__ rowmap, int32_t* __restrict__ sim,
-                                                        int32_t* __restrict__ diff) {
-    const PairContig pc = contigs[contig];
-    const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
-    if (i >= pc.n_pad || j >= pc.n_pad) return;
-    const int oi = rowmap[pc.row0 + i], oj = rowmap[pc.row0 + j];
-    if (oi < 0 || oj < 0) return;
-    const uint32_t* ai = reinterpret_cast<const uint32_t*>(A + (pc.row0 + i) * ld_k);
-    const uint32_t* ri = reinterpret_cast<const uint32_t*>(R + (pc.row0 + i) * ld_k);
-    const uint32_t* aj = reinterpret_cast<const uint32_t*>(A + (pc.row0 + j) * ld_k);
-    const uint32_t* rj = reinterpret_cast<const uint32_t*>(R + (pc.row0 + j) * ld_k);
-    unsigned aa = 0, rr = 0, x = 0;
-    for (int64_t k = 0; k < ld_k / 4; k++) {
-        const uint32_t a0 = ai[k], r0 = ri[k], a1 = aj[k], r1 = rj[k];
-        aa = __dp4a(a0, a1, aa);
-        rr = __dp4a(r0, r1, rr);
-        x = __dp4a(a0, r1, x);
-        x = __dp4a(r0, a1, x);
+// Plain SIMT statement of the same contraction over the same operands and the same work list (dp4a, one CTA per
+// tile pair). Only reachable with HSGPU_PAIRS_SIMT: the A/B check of the tensor-core kernel in the tests.
+__global__ void __launch_bounds__(256) pair_simt_kernel(const PairWork* __restrict__ work, const PairContig* __restrict__ contigs,
+                                                        int64_t ld_k, const uint8_t* __restrict__ A, const uint8_t* __restrict__ R,
+                                                        int32_t* __restrict__ sim, int32_t* __restrict__ diff) {
+    const PairWork wk = work[blockIdx.x];
+    const PairContig pc = contigs[wk.contig];
+    for (int e = threadIdx.x; e < HS_PV_BLOCK; e += blockDim.x) {
+        const int i = wk.ti * PG_TILE + (e >> 7), j = wk.tj * PG_TILE + (e & 127);
+        const uint32_t* ai = reinterpret_cast<const uint32_t*>(A + (pc.row0 + i) * ld_k);
+        const uint32_t* ri = reinterpret_cast<const uint32_t*>(R + (pc.row0 + i) * ld_k);
+        const uint32_t* aj = reinterpret_cast<const uint32_t*>(A + (pc.row0 + j) * ld_k);
+        const uint32_t* rj = reinterpret_cast<const uint32_t*>(R + (pc.row0 + j) * ld_k);
+        unsigned aa = 0, rr = 0, x = 0;
+        for (int64_t k = (int64_t)wk.kb0 * (PG_BK / 4); k < (int64_t)wk.kb1 * (PG_BK / 4); k++) {
+            const uint32_t a0 = ai[k], r0 = ri[k], a1 = aj[k], r1 = rj[k];
+            aa = __dp4a(a0, a1, aa);
+            rr = __dp4a(r0, r1, rr);
+            x = __dp4a(a0, r1, x);
+            x = __dp4a(r0, a1, x);
+        }
+        const bool dead = i == j;
+        sim[(int64_t)blockIdx.x * HS_PV_BLOCK + e] = dead ? 0 : (int)(3 * aa + rr);
+        diff[(int64_t)blockIdx.x * HS_PV_BLOCK + e] = dead ? 0 : (int)x;
     }
-    const bool dead = oi == oj;
-    sim[pc.out_off + (int64_t)oi * pc.n_pad + oj] = dead ? 0 : (int)(3 * aa + rr);
-    diff[pc.out_off + (int64_t)oi * pc.n_pad + oj] = dead ? 0 : (int)x;
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
@@ -455,10 +416,9 @@ void hsgpu_pairs_destroy(hsgpu_pairs* h) {
     hsgpu_ctx* ctx = h->ctx;
     cudaSetDevice(ctx->device);
     hs_free(ctx, h->d_A); hs_free(ctx, h->d_R); hs_free(ctx, h->d_rowmap); hs_free(ctx, h->d_rowof);
+    hs_free(ctx, h->d_rowloc); hs_free(ctx, h->d_has_cells);
     hs_free(ctx, h->d_contigs); hs_free(ctx, h->d_work);
-    if (h->d_psim != h->d_sim) { hs_free(ctx, h->d_psim); hs_free(ctx, h->d_pdiff); }
-    hs_free(ctx, h->d_sim); hs_free(ctx, h->d_diff);
-    hs_free(ctx, h->d_sched); hs_free(ctx, h->d_sched_off); hs_free(ctx, h->d_row_contig); hs_free(ctx, h->d_read_base);
+    hs_free(ctx, h->d_sim); hs_free(ctx, h->d_diff); hs_free(ctx, h->d_tilemap); hs_free(ctx, h->d_read_base);
     hs_free(ctx, h->d_err); hs_free(ctx, h->d_snp_off); hs_free(ctx, h->d_snp_base); hs_free(ctx, h->d_read_idx);
     hs_free(ctx, h->d_code); hs_free(ctx, h->d_rb); hs_free(ctx, h->d_sb); hs_free(ctx, h->d_snp_contig);
     cudaStreamSynchronize(ctx->stream);
@@ -485,15 +445,11 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
     h->n_cells = n_cells;
     h->h_contigs.resize(n_contigs);
     std::vector<int64_t> read_base(n_contigs + 1, 0);
-    int64_t max_snps = 0, rows = 0, out_elems = 0;
+    int64_t max_snps = 0, rows = 0, map_elems = 0;
     for (int c = 0; c < n_contigs; c++) {
         if (n_reads[c] < 0 || snp_base[c + 1] < snp_base[c]) {
             delete h;
             HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pairs_create: negative read or SNP count");
-        }
-        if (n_reads[c] > 46000) {
-            delete h;
-            HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_pairs_create: dense n x n output limited to 46000 reads per contig");
         }
         read_base[c + 1] = read_base[c] + n_reads[c];
         max_snps = std::max(max_snps, snp_base[c + 1] - snp_base[c]);
@@ -501,18 +457,17 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
         pc.n = n_reads[c];
         pc.n_pad = (n_reads[c] + PG_TILE - 1) / PG_TILE * PG_TILE;
         pc.row0 = rows;
-        pc.out_off = out_elems;
-        pc.identity = 1;
-        pc.pad = 0;
+        pc.map_off = map_elems;
+        pc.read0 = read_base[c];
         rows += pc.n_pad;
-        out_elems += (int64_t)pc.n_pad * pc.n_pad;
+        const int64_t nt = pc.n_pad / PG_TILE;
+        map_elems += nt * nt;
     }
     if (rows >= (int64_t)1 << 31) {
         delete h;
         HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_pairs_create: more than 2^31 operand rows in one batch");
     }
     h->total_rows = rows;
-    h->out_elems = out_elems;
     h->k_ld = std::max<int64_t>(PG_BK, (max_snps + PG_BK - 1) / PG_BK * PG_BK);
     const int64_t total_reads = read_base[n_contigs];
 
@@ -537,33 +492,28 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
             }
         }
     }
-    std::vector<int32_t> rowmap(rows, -1), rowof(std::max<int64_t>(total_reads, 1), 0);
+    std::vector<int32_t> rowmap(rows, -1), rowof(std::max<int64_t>(total_reads, 1), 0), rowloc(std::max<int64_t>(total_reads, 1), 0);
+    std::vector<uint8_t> has_cells(std::max<int64_t>(total_reads, 1), 0);
+    for (int64_t r = 0; r < total_reads; r++) has_cells[r] = last[r] >= 0;
     std::vector<PairWork> work;
-    std::vector<int32_t> row_contig(std::max<int64_t>(rows, 1), 0);
-    std::vector<int64_t> sched_off(n_contigs + 1, 0);
-    for (int c = 0; c < n_contigs; c++) {
-        const int64_t nt = h->h_contigs[c].n_pad / PG_TILE;
-        sched_off[c + 1] = sched_off[c] + nt * nt;
-    }
-    std::vector<uint8_t> sched(std::max<int64_t>(sched_off[n_contigs], 1), 0);
     int64_t kb_listed = 0, kb_dense = 0, tiles_dense = 0;
     for (int c = 0; c < n_contigs; c++) {
         PairContig& pc = h->h_contigs[c];
         const int64_t rb0 = read_base[c];
-        std::fill(row_contig.begin() + pc.row0, row_contig.begin() + pc.row0 + pc.n_pad, c);
         std::vector<int32_t> order(pc.n);
         std::iota(order.begin(), order.end(), 0);
         if (!keep_order) {
             std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return first[rb0 + a] < first[rb0 + b]; });
             for (int32_t r = 0; r < pc.n; r++)
                 if (order[r] != r) {
-                    pc.identity = 0;
+                    h->all_identity = false;
                     break;
                 }
         }
         for (int32_t r = 0; r < pc.n; r++) {
             rowmap[pc.row0 + r] = order[r];
             rowof[rb0 + order[r]] = (int32_t)(pc.row0 + r);
+            rowloc[rb0 + order[r]] = r;
         }
         const int nt = pc.n_pad / PG_TILE;
         const int nkb = (int)((snp_base[c + 1] - snp_base[c] + PG_BK - 1) / PG_BK);
@@ -582,7 +532,6 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
                 int k1 = dense ? nkb : std::min(khi[i], khi[j]);
                 if (k0 >= k1) continue;
                 work.push_back(PairWork{c, i, j, k0, k1});
-                sched[sched_off[c] + (int64_t)i * nt + j] = sched[sched_off[c] + (int64_t)j * nt + i] = 1;
                 kb_listed += k1 - k0;
             }
     }
@@ -592,7 +541,16 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
     h->kblocks_listed = kb_listed;
     h->kblocks_dense = kb_dense;
     h->tiles_dense = tiles_dense;
-    for (const PairContig& pc : h->h_contigs) h->all_identity = h->all_identity && pc.identity;
+    if ((int64_t)work.size() >= (int64_t)1 << 31) {
+        delete h;
+        HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_pairs_create: more than 2^31 tile pairs in one batch");
+    }
+    // the block of every scheduled tile pair = its place in the (sorted) work list
+    std::vector<int32_t> tilemap((size_t)std::max<int64_t>(map_elems, 1), -1);
+    for (size_t w = 0; w < work.size(); w++) {
+        const PairContig& pc = h->h_contigs[work[w].contig];
+        tilemap[(size_t)(pc.map_off + (int64_t)work[w].ti * (pc.n_pad / PG_TILE) + work[w].tj)] = (int32_t)w;
+    }
 
 #define PG_TRY(call)                                                               \
     do {                                                                           \
@@ -608,22 +566,15 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
     PG_TRY(hs_alloc(ctx, &h->d_rowof, total_reads));
     PG_TRY(hs_alloc(ctx, &h->d_contigs, n_contigs));
     PG_TRY(hs_alloc(ctx, &h->d_work, h->n_work));
-    PG_TRY(hs_alloc(ctx, &h->d_sim, out_elems));
-    PG_TRY(hs_alloc(ctx, &h->d_diff, out_elems));
-    if (h->all_identity) {
-        h->d_psim = h->d_sim;
-        h->d_pdiff = h->d_diff;
-    } else {
-        PG_TRY(hs_alloc(ctx, &h->d_psim, out_elems));
-        PG_TRY(hs_alloc(ctx, &h->d_pdiff, out_elems));
-    }
-    PG_TRY(hs_alloc(ctx, &h->d_sched, (int64_t)sched.size()));
-    PG_TRY(hs_alloc(ctx, &h->d_sched_off, n_contigs + 1));
-    PG_TRY(hs_alloc(ctx, &h->d_row_contig, (int64_t)row_contig.size()));
+    PG_TRY(hs_alloc(ctx, &h->d_sim, h->n_work * HS_PV_BLOCK));
+    PG_TRY(hs_alloc(ctx, &h->d_diff, h->n_work * HS_PV_BLOCK));
+    PG_TRY(hs_alloc(ctx, &h->d_tilemap, (int64_t)tilemap.size()));
+    PG_TRY(hs_alloc(ctx, &h->d_rowloc, total_reads));
+    PG_TRY(hs_alloc(ctx, &h->d_has_cells, total_reads));
     PG_TRY(hs_alloc(ctx, &h->d_read_base, n_contigs + 1));
-    PG_TRY(hs_h2d(ctx, h->d_sched, sched.data(), (int64_t)sched.size()));
-    PG_TRY(hs_h2d(ctx, h->d_sched_off, sched_off.data(), n_contigs + 1));
-    PG_TRY(hs_h2d(ctx, h->d_row_contig, row_contig.data(), (int64_t)row_contig.size()));
+    PG_TRY(hs_h2d(ctx, h->d_tilemap, tilemap.data(), (int64_t)tilemap.size()));
+    PG_TRY(hs_h2d(ctx, h->d_rowloc, rowloc.data(), total_reads));
+    PG_TRY(hs_h2d(ctx, h->d_has_cells, has_cells.data(), total_reads));
     PG_TRY(hs_h2d(ctx, h->d_read_base, read_base.data(), n_contigs + 1));
     PG_TRY(hs_alloc(ctx, &h->d_err, 1));
     PG_TRY(hs_alloc(ctx, &h->d_snp_off, total_snps + 1));
@@ -676,46 +627,39 @@ int hsgpu_pairs_compute(hsgpu_pairs* h) {
     hsgpu_ctx* ctx = h->ctx;
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     h->computed = false;
-    if (h->out_elems == 0) {
+    if (h->n_work == 0) {
         h->computed = true;
         return HSGPU_OK;
     }
-    const size_t out_bytes = (size_t)h->out_elems * sizeof(int32_t);
     if (h->flags & HSGPU_PAIRS_SIMT) {
-        HS_CUDA(ctx, cudaMemsetAsync(h->d_sim, 0, out_bytes, ctx->stream));
-        HS_CUDA(ctx, cudaMemsetAsync(h->d_diff, 0, out_bytes, ctx->stream));
-        for (int c = 0; c < h->n_contigs; c++) {
-            const int np = h->h_contigs[c].n_pad;
-            if (np == 0) continue;
-            dim3 grid(np / 16, np / 16), block(16, 16);
-            HS_KERNEL(ctx, "pair_simt_kernel", pair_simt_kernel<<<grid, block, 0, ctx->stream>>>(h->d_contigs, c, h->k_ld, h->d_A, h->d_R,
-                                                                                                h->d_rowmap, h->d_sim, h->d_diff));
-        }
+        HS_KERNEL(ctx, "pair_simt_kernel", pair_simt_kernel<<<(unsigned)h->n_work, 256, 0, ctx->stream>>>(
+            h->d_work, h->d_contigs, h->k_ld, h->d_A, h->d_R, h->d_sim, h->d_diff));
         h->computed = true;
         return HSGPU_OK;
     }
-    if (h->all_identity && !(h->flags & HSGPU_PAIRS_DENSE)) {
-        // tile order is the caller's order: the kernel writes the result in place, and tile pairs that are
-        // not scheduled share no SNP block, so their counts are zero
-        HS_CUDA(ctx, cudaMemsetAsync(h->d_sim, 0, out_bytes, ctx->stream));
-        HS_CUDA(ctx, cudaMemsetAsync(h->d_diff, 0, out_bytes, ctx->stream));
+    static std::atomic<bool> attr_set[64];  // per device: function attributes belong to the device's context
+    if (!attr_set[ctx->device & 63]) {
+        HS_CUDA(ctx, cudaFuncSetAttribute(pair_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
+        attr_set[ctx->device & 63] = true;
     }
-    if (h->n_work > 0) {
-        static std::atomic<bool> attr_set[64];  // per device: function attributes belong to the device's context
-        if (!attr_set[ctx->device & 63]) {
-            HS_CUDA(ctx, cudaFuncSetAttribute(pair_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM));
-            attr_set[ctx->device & 63] = true;
-        }
-        const int grid = (int)std::min<int64_t>(h->n_work, ctx->sm_count);
-        HS_KERNEL(ctx, "pair_umma_kernel", pair_umma_kernel<<<grid, PG_THREADS, PG_SMEM, ctx->stream>>>(
-            h->tmapA, h->tmapR, h->d_work, (int)h->n_work, h->d_contigs, h->d_psim, h->d_pdiff, h->d_err));
-    }
-    if (!h->all_identity)
-        HS_KERNEL(ctx, "pair_unpermute_kernel", pair_unpermute_kernel<<<(unsigned)h->total_rows, 256, 0, ctx->stream>>>(
-            h->d_contigs, h->d_row_contig, h->d_read_base, h->d_rowof, h->d_sched, h->d_sched_off, h->d_psim, h->d_pdiff,
-            h->d_sim, h->d_diff));
+    const int grid = (int)std::min<int64_t>(h->n_work, ctx->sm_count);
+    HS_KERNEL(ctx, "pair_umma_kernel", pair_umma_kernel<<<grid, PG_THREADS, PG_SMEM, ctx->stream>>>(
+        h->tmapA, h->tmapR, h->d_work, (int)h->n_work, h->d_contigs, h->d_sim, h->d_diff, h->d_err));
     h->computed = true;
     return HSGPU_OK;
+}
+
+static HsPairView pg_view(const hsgpu_pairs* h, int contig) {
+    const PairContig& pc = h->h_contigs[contig];
+    HsPairView v;
+    v.row_of = h->d_rowloc + pc.read0;
+    v.tilemap = h->d_tilemap + pc.map_off;
+    v.sim = h->d_sim;
+    v.diff = h->d_diff;
+    v.has_cells = h->d_has_cells + pc.read0;
+    v.nt = pc.n_pad / PG_TILE;
+    v.n = pc.n;
+    return v;
 }
 
 int hsgpu_pairs_fetch(hsgpu_pairs* h, int32_t contig, int32_t* sim, int32_t* diff) {
@@ -724,14 +668,23 @@ int hsgpu_pairs_fetch(hsgpu_pairs* h, int32_t contig, int32_t* sim, int32_t* dif
     if (!h->computed) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_pairs_fetch: call hsgpu_pairs_compute first");
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     const PairContig& pc = h->h_contigs[contig];
-    if (pc.n > 0) {
-        const size_t w = (size_t)pc.n * sizeof(int32_t), sp = (size_t)pc.n_pad * sizeof(int32_t);
-        if (sim) HS_CUDA(ctx, cudaMemcpy2DAsync(sim, w, h->d_sim + pc.out_off, sp, w, pc.n, cudaMemcpyDeviceToHost, ctx->stream));
-        if (diff) HS_CUDA(ctx, cudaMemcpy2DAsync(diff, w, h->d_diff + pc.out_off, sp, w, pc.n, cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t *d_s = nullptr, *d_d = nullptr;
+    if (pc.n > 0 && (sim || diff)) {
+        // the dense n x n form exists only here, for the caller who asks for it (the later stages of the library read
+        // the blocks): it is built on the device and copied out
+        if (pc.n > 46000) HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_pairs_fetch: dense n x n output limited to 46000 reads per contig");
+        const int64_t nn = (int64_t)pc.n * pc.n;
+        HS_CUDA(ctx, hs_alloc(ctx, &d_s, nn));
+        HS_CUDA(ctx, hs_alloc(ctx, &d_d, nn));
+        HS_KERNEL(ctx, "pair_dense_kernel", pair_dense_kernel<<<pc.n, 256, 0, ctx->stream>>>(pg_view(h, contig), d_s, d_d));
+        if (sim) HS_CUDA(ctx, hs_d2h(ctx, sim, d_s, nn));
+        if (diff) HS_CUDA(ctx, hs_d2h(ctx, diff, d_d, nn));
     }
     int32_t err = 0;
     HS_CUDA(ctx, hs_d2h(ctx, &err, h->d_err, 1));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    hs_free(ctx, d_s);
+    hs_free(ctx, d_d);
     if (err) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu_pairs: the tensor-core kernel timed out on a barrier");
     return HSGPU_OK;
 }
@@ -744,7 +697,7 @@ int hsgpu_pairs_info(hsgpu_pairs* h, int64_t* info) {
     info[3] = h->kblocks_dense;   // the same for the full upper triangles over all SNPs
     info[4] = h->total_rows;
     info[5] = h->k_ld;
-    info[6] = h->out_elems;
+    info[6] = h->n_work * HS_PV_BLOCK;  // elements stored per matrix: one block per scheduled tile pair
     info[7] = h->all_identity ? 1 : 0;
     return HSGPU_OK;
 }
@@ -768,15 +721,10 @@ int hsgpu_read_pair_counts(hsgpu_ctx* ctx, int32_t n_reads, int32_t n_snps, cons
 
 // internal view for the read-graph stage (graph.cu): the device-resident result blocks of one contig
 int hs_pairs_contigs(hsgpu_pairs* h) { return h ? h->n_contigs : 0; }
-int hs_pairs_view(hsgpu_pairs* h, int32_t contig, hsgpu_ctx** ctx, const int32_t** sim, const int32_t** diff, int32_t* n,
-                  int32_t* n_pad) {
+int hs_pairs_view(hsgpu_pairs* h, int32_t contig, hsgpu_ctx** ctx, HsPairView* view) {
     if (!h || contig < 0 || contig >= h->n_contigs) return HSGPU_ERR_ARG;
     *ctx = h->ctx;
     if (!h->computed) return HSGPU_ERR_STATE;
-    const PairContig& pc = h->h_contigs[contig];
-    *sim = h->d_sim + pc.out_off;
-    *diff = h->d_diff + pc.out_off;
-    *n = pc.n;
-    *n_pad = pc.n_pad;
+    *view = pg_view(h, contig);
     return HSGPU_OK;
 }

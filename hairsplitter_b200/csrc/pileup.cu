@@ -179,48 +179,53 @@ struct PileupArgs {
 #define PW_BUF 1024               // staging row: a carried partial vector + one window of columns (<= 16 + 960 + 16)
 enum { CG_M = 0, CG_I = 1, CG_D = 2, CG_S = 3 };  // kinds of the byte-sized CIGAR ops
 
+// CHECKED = false: the caller knows that every word touched lies inside the sequence (windows away from the ends
+// of the read and of the contig: all but the first and last window of a read)
+template <bool CHECKED>
 __device__ __forceinline__ uint32_t pw_word(const uint32_t* __restrict__ w, int i, int n) {
+    if (!CHECKED) return __ldg(w + i);
     return (i >= 0 && i < n) ? __ldg(w + i) : 0u;
 }
 // sixteen 2-bit symbols starting at base i (i may be negative or run past the end: zeros)
+template <bool CHECKED>
 __device__ __forceinline__ uint32_t pw_window(const uint32_t* __restrict__ w, int nw, int i) {
     const int wi = i >> 4;
-    return __funnelshift_r(pw_word(w, wi, nw), pw_word(w, wi + 1, nw), (i & 15) * 2);
+    return __funnelshift_r(pw_word<CHECKED>(w, wi, nw), pw_word<CHECKED>(w, wi + 1, nw), (i & 15) * 2);
 }
 // the 16 read symbols of alignment read offsets tp .. tp+15 (reverse strand: complement, read backwards)
+template <bool CHECKED>
 __device__ __forceinline__ uint32_t pw_read_window(const uint32_t* __restrict__ rb, int nw, int rlen, int tp, int strand) {
     uint32_t x;
     int nvalid;
     if (strand) {
-        x = pw_window(rb, nw, tp);
+        x = pw_window<CHECKED>(rb, nw, tp);
         nvalid = rlen - tp;
     } else {
         const int j = rlen - 1 - tp;  // first base wanted; the window is bases j-15 .. j, reversed
-        x = pw_window(rb, nw, j - 15);
+        x = pw_window<CHECKED>(rb, nw, j - 15);
         x = __brev(x);
         x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
         x = ~x;
         nvalid = j + 1;
     }
     // a CIGAR longer than the read is malformed (the reference reads past the string); those symbols are 0
-    if (nvalid < 16) x = (nvalid <= 0) ? 0u : (x & ((1u << (2 * nvalid)) - 1u));
+    if (CHECKED && nvalid < 16) x = (nvalid <= 0) ? 0u : (x & ((1u << (2 * nvalid)) - 1u));
     return x;
 }
 
-// set bits [a, a + n) of a warp-private bit array in shared memory, 0 < n <= 63 (one CIGAR op). Insertions and
-// deletions are a few bases long: up to 32 bits take one atomic, two when the run crosses a word boundary.
+// set bits [a, a + n) of a warp-private bit array in shared memory, 0 < n <= 63 (one CIGAR op): at most three words.
+// Straight-line code on purpose: a loop around the atomics makes the compiler insert YIELDs and a non-reconvergent
+// barrier, and the warp then walks the rest of the window in two halves (measured: 16 active lanes per instruction).
 __device__ __forceinline__ void pw_set_bits(unsigned int* __restrict__ bits, int a, int n) {
-    for (;;) {
-        const int s = a & 31, n1 = min(n, 32);
-        unsigned int* const w = bits + (a >> 5);
-        const unsigned int m = n1 == 32 ? 0xffffffffu : ((1u << n1) - 1u);
-        atomicOr(w, m << s);
-        const unsigned int up = __funnelshift_l(m, 0u, s);  // the part that spills into the next word (0 when s == 0)
-        if (up) atomicOr(w + 1, up);
-        if (n <= 32) break;
-        a += 32;
-        n -= 32;
-    }
+    const int s = a & 31;
+    unsigned int* const w = bits + (a >> 5);
+    const unsigned long long m = (1ull << n) - 1ull;  // n <= 63
+    const unsigned long long lo = m << s;             // bits 0..63 of the shifted run
+    const unsigned int w2 = s ? (unsigned int)(m >> (64 - s)) : 0u;  // bits 64.. (s + n <= 94)
+    atomicOr(w, (unsigned int)lo);
+    const unsigned int w1 = (unsigned int)(lo >> 32);
+    if (w1) atomicOr(w + 1, w1);
+    if (w2) atomicOr(w + 2, w2);
 }
 
 // the PW_OPL ops [kop + PW_OPL*lane, ...) of a read: four in `lo`, two in the low half of `hi` (bytes past nops
@@ -276,14 +281,15 @@ __device__ __forceinline__ void pw_load_ops(const uint8_t* __restrict__ cig, int
 
 // the 32 steps of one lane of a FAST window (a full window that cannot reach the contig end: every lane
 // emits exactly PW_P positions, nothing is predicated on counts or on the column)
+template <bool CHECKED>
 __device__ __forceinline__ void pw_walk_fast(const uint32_t mI, const uint32_t mD, const int lane, const int carry_ctx,
                                              const int carry_p1x, const uint32_t* __restrict__ rb, const int nrw,
                                              const int rlen, const int strand, int tp, const uint32_t* __restrict__ cb,
                                              const int ncw, const int q, unsigned int qa, int& ctx_out, int& p1x_out,
                                              unsigned int& dist) {
     int ctx = 0, p1x = 0;  // rebuilt by the two warm-up steps
-    uint32_t rw = pw_read_window(rb, nrw, rlen, tp, strand);
-    uint32_t cw = pw_window(cb, ncw, q);
+    uint32_t rw = pw_read_window<CHECKED>(rb, nrw, rlen, tp, strand);
+    uint32_t cw = pw_window<CHECKED>(cb, ncw, q);
     PW_WARM(0x1); PW_WARM(0x2);
     if (lane == 0) {  // lane 0 warmed up on two virtual positions: its context is the carry
         ctx = carry_ctx;
@@ -293,8 +299,8 @@ __device__ __forceinline__ void pw_walk_fast(const uint32_t mI, const uint32_t m
     PW_STEP(0x100); PW_STEP(0x200); PW_STEP(0x400); PW_STEP(0x800); PW_STEP(0x1000); PW_STEP(0x2000);
     PW_STEP(0x4000); PW_STEP(0x8000);
     const int lowI = __popc(mI & 0xffffu), lowD = __popc(mD & 0xffffu);
-    rw = pw_read_window(rb, nrw, rlen, tp + 16 - lowD, strand);
-    cw = pw_window(cb, ncw, q + 16 - lowI);
+    rw = pw_read_window<CHECKED>(rb, nrw, rlen, tp + 16 - lowD, strand);
+    cw = pw_window<CHECKED>(cb, ncw, q + 16 - lowI);
     PW_STEP(0x10000); PW_STEP(0x20000); PW_STEP(0x40000); PW_STEP(0x80000); PW_STEP(0x100000); PW_STEP(0x200000);
     PW_STEP(0x400000); PW_STEP(0x800000); PW_STEP(0x1000000); PW_STEP(0x2000000); PW_STEP(0x4000000);
     PW_STEP(0x8000000); PW_STEP(0x10000000); PW_STEP(0x20000000); PW_STEP(0x40000000); PW_STEP(0x80000000);
@@ -312,8 +318,8 @@ __device__ __forceinline__ void pw_walk_slow(const uint32_t mI, const uint32_t m
     int ctx = 0, p1x = 0;
 #pragma unroll 1
     for (int blk = 0; blk < 2; blk++) {
-        uint32_t rw = pw_read_window(rb, nrw, rlen, tp, strand);
-        uint32_t cw = pw_window(cb, ncw, q);
+        uint32_t rw = pw_read_window<true>(rb, nrw, rlen, tp, strand);
+        uint32_t cw = pw_window<true>(cb, ncw, q);
 #pragma unroll 4
         for (int uu = 0; uu < 16; uu++) {
             const int u = 16 * blk + uu;
@@ -476,14 +482,19 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 4) pileup_kernel(PileupArgs a) 
             int ctx, p1x;
             if (full && qend <= L) {
                 const unsigned int qa = (unsigned int)__cvta_generic_to_shared(buf) + (unsigned int)(q - bufbase);
-                pw_walk_fast(mI, mD, lane, carry_ctx, carry_p1x, rb, nrw, rlen, strand, tp, cb, ncw, q, qa, ctx, p1x, dist);
+                // every window of 16 symbols the lanes fetch stays inside the read and the contig (64 bases of margin:
+                // a fetch reaches at most 47 bases past the position it is made for)
+                const bool inside = q0 >= 64 && qend + 64 < L && t0 >= 64 && t0 + Enew + 64 < rlen;
+                if (inside) pw_walk_fast<false>(mI, mD, lane, carry_ctx, carry_p1x, rb, nrw, rlen, strand, tp, cb, ncw, q, qa, ctx, p1x, dist);
+                else pw_walk_fast<true>(mI, mD, lane, carry_ctx, carry_p1x, rb, nrw, rlen, strand, tp, cb, ncw, q, qa, ctx, p1x, dist);
                 ualen += Enew;
                 udist += totI;  // deletions count in the walk ('-' never equals the contig base)
             } else {
                 pw_walk_slow(mI, mD, cnt, lane, carry_ctx, carry_p1x, rb, nrw, rlen, strand, tp, cb, ncw, q, L,
                              buf - bufbase, ctx, p1x, dist, alen);
             }
-            const int last = (Enew - 1) / P;  // the lane that pushed the window's last symbol
+            // the lane that pushed the window's last symbol: (Enew - 1) / P without the division
+            const int last = full ? (PW_E - 1) / PW_P : 31 - __clz(__ballot_sync(0xffffffffu, cnt > 0));
             carry_ctx = __shfl_sync(0xffffffffu, ctx, last);
             carry_p1x = __shfl_sync(0xffffffffu, p1x, last);
             q0 = qend;

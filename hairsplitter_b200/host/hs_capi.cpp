@@ -4,6 +4,7 @@
 
 #include "hs_io.h"
 #include "hs_partition.h"
+#include "hs_sepreads.h"
 
 using namespace hs;
 
@@ -41,6 +42,43 @@ void hshost_part_get(void* h, int p, int32_t* read_idx, int16_t* state, int32_t*
     left_right[1] = pt.pos_right;
 }
 void hshost_parts_free(void* h) { delete (PartSet*)h; }
+
+// create_read_graph_low_memory of the host path on flat SNP columns: CSR over the masked reads, local indices;
+// also reports whether the device path may replace it (every read on consecutive SNP columns)
+int64_t hshost_read_graph_low_memory(int n_reads, int n_snps, const int64_t* snp_off, const uint32_t* idx, const uint8_t* code,
+                                     const uint8_t* rb, const uint8_t* sb, int m, const int32_t* masked, float error_rate,
+                                     int64_t* adj_off, int32_t* adj, int* consecutive) {
+    ColContig c;
+    c.read_lines.resize((size_t)n_reads);
+    c.snps.resize((size_t)n_snps);
+    for (int s = 0; s < n_snps; s++) {
+        Column& col = c.snps[s];
+        col.pos = s;
+        col.ref_base = rb[s];
+        col.second_base = sb[s];
+        col.readIdxs.assign(idx + snp_off[s], idx + snp_off[s + 1]);
+        col.content.assign(code + snp_off[s], code + snp_off[s + 1]);
+    }
+    if (consecutive) *consecutive = low_memory_counts_are_contig_counts(c) ? 1 : 0;
+    std::vector<char> mask((size_t)n_reads, 0);
+    std::vector<int> local((size_t)n_reads, -1);
+    for (int i = 0; i < m; i++) {
+        mask[masked[i]] = 1;
+        local[masked[i]] = i;
+    }
+    ReadGraph g;
+    create_read_graph_low_memory(c.snps, mask, g, error_rate);
+    int64_t n = 0;
+    for (int i = 0; i < m; i++) {
+        adj_off[i] = n;
+        for (int e = g.off[masked[i]]; e < g.off[masked[i] + 1]; e++) {
+            if (adj) adj[n] = local[g.nbr[e]];
+            n++;
+        }
+    }
+    adj_off[m] = n;
+    return n;
+}
 
 float hshost_chi_square(int n00, int n01, int n10, int n11) {
     Distance d;

@@ -95,7 +95,8 @@ std::vector<int> merge_haplotypes_to_fit_within_limit(int max_haplotypes, const 
 // per-contig state of the pipeline
 struct ContigJob {
     int n = 0;             // index in contigs
-    bool low_now = false;  // coverage > 1000 or -l: neighbour-list path on the host
+    bool low_now = false;  // coverage > 1000 or -l: the neighbour-list path (create_read_graph_low_memory)
+    bool device_lists = false;  // low_now: the stage provider built the neighbour lists (graphs[w], list mode)
     std::vector<Window> windows;
     // per window with SNPs: the read graph and the clusterings started from its SNPs (filled by the stage provider
     // for the high-memory contigs)
@@ -113,6 +114,14 @@ typedef void (*SepStages)(void* user, const std::vector<ColContig>& contigs, std
 
 // main() of HS_separate_reads (src/separate_reads.cpp:1398-1790) behind the stage provider. `prepare` runs
 // concurrently with the .col parser (the product creates its GPU contexts there) and returns non-zero on failure.
-int separate_reads_pipeline(int argc, char* argv[], int (*prepare)(void* user), SepStages stages, void* user);
+// `low_stages` (may be null): the same provider interface for the low-memory contigs whose reads all cover runs of
+// consecutive SNP columns (see low_memory_counts_are_contig_counts): it fills job.graphs[w] with the neighbour lists of
+// create_read_graph_low_memory and sets job.device_lists; the clusterings of those contigs stay on the host.
+int separate_reads_pipeline(int argc, char* argv[], int (*prepare)(void* user), SepStages stages, void* user,
+                            SepStages low_stages = nullptr);
+
+// create_read_graph_low_memory addresses a read's alleles by offset from its first SNP (:597-605). When every read
+// appears in a run of consecutive SNP columns that is the contig-wide similarity / difference count of the pair.
+bool low_memory_counts_are_contig_counts(const ColContig& c);
 
 }  // namespace hs

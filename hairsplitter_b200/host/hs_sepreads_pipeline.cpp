@@ -28,7 +28,23 @@ static const char* kUsage =
     "Usage: ./separate_reads <columns> <num_threads> <error_rate> <ploidy_of_contigs> <low_memory> "
     "<rarest-strain-abundance> <amplicon> <outfile> <DEBUG>";
 
-int separate_reads_pipeline(int argc, char* argv[], int (*prepare)(void* user), SepStages stages, void* user) {
+bool low_memory_counts_are_contig_counts(const ColContig& c) {
+    const size_t R = c.read_lines.size();
+    std::vector<int> first(R, -1), last(R, -1), count(R, 0);
+    for (size_t s = 0; s < c.snps.size(); s++)
+        for (int r : c.snps[s].readIdxs) {
+            if (r < 0 || (size_t)r >= R) return false;
+            if (first[r] < 0) first[r] = (int)s;
+            last[r] = (int)s;
+            count[r]++;
+        }
+    for (size_t r = 0; r < R; r++)
+        if (count[r] > 0 && count[r] != last[r] - first[r] + 1) return false;
+    return true;
+}
+
+int separate_reads_pipeline(int argc, char* argv[], int (*prepare)(void* user), SepStages stages, void* user,
+                            SepStages low_stages) {
     if (argc != 10) {
         if (argc == 2 && (argv[1] == std::string("-h") || argv[1] == std::string("--help"))) {
             std::cout << kUsage << std::endl;
@@ -127,6 +143,19 @@ int separate_reads_pipeline(int argc, char* argv[], int (*prepare)(void* user), 
     int64_t stats[4] = {0, 0, 0, 0};
     if (!high.empty()) stages(user, contigs, high, error_rate, master, stats);
     phase("graph + clustering stages");
+    // ---- the neighbour lists of the low-memory contigs (create_read_graph_low_memory) through the provider, where
+    // its pair counts are the reference's (HS_LOWMEM_HOST=1 keeps every such contig on the host loop) ----
+    if (low_stages && !std::getenv("HS_LOWMEM_HOST")) {
+        std::vector<ContigJob*> low;
+        for (size_t n = 0; n < contigs.size(); n++) {
+            if (contigs[n].snps.empty() || !jobs[n].low_now) continue;
+            size_t max_m = 0;
+            for (const Window& w : jobs[n].windows) max_m = std::max(max_m, w.masked.size());
+            if (max_m <= 6400 && low_memory_counts_are_contig_counts(contigs[n])) low.push_back(&jobs[n]);
+        }
+        if (!low.empty()) low_stages(user, contigs, low, error_rate, master, stats);
+        phase("low-memory read graphs");
+    }
 
     // ---- low-memory contigs: neighbour lists and clusterings on the host (:1636-1645,1660-1700) ----
     struct Item { int n, w; };
@@ -150,7 +179,8 @@ int separate_reads_pipeline(int argc, char* argv[], int (*prepare)(void* user), 
             for (int r : win.masked) mask[r] = 1;
             ReadGraph lists;  // neighbor_list_low_memory_strengthened
             if (job.low_now) {
-                create_read_graph_low_memory(c.snps, mask, lists, error_rate);
+                if (job.device_lists) lists = std::move(job.graphs[wi]);
+                else create_read_graph_low_memory(c.snps, mask, lists, error_rate);
                 auto& lc = job.local_clusters[wi];
                 lc.clear();
                 for (int s : win.restart_snps) {

@@ -3,8 +3,10 @@
 // post-processing of each window (finalize_clustering) run on the host; the read x read agreement counts
 // (list_similarities_and_differences_between_reads3), the read graph of every window (create_read_graph_matrix)
 // and the chinese-whispers runs started from every SNP (chinese_whispers_high_memory) run on the GPU through the
-// C ABI of libhsgpu (hsgpu_pairs_*, hsgpu_graph_*), all windows of all contigs of a shard in one batch. Contigs
-// are sharded over the visible GPUs (HSGPU_NGPUS, HSGPU_DEVICE), heaviest first.
+// C ABI of libhsgpu (hsgpu_pairs_*, hsgpu_graph_*), all windows of all contigs of a shard in one batch. The
+// neighbour lists of the low-memory path (create_read_graph_low_memory: -l, amplicons, > 1000x) come from the same
+// counts on the GPU; those contigs are clustered on the host like in the reference. Contigs are sharded over the
+// visible GPUs (HSGPU_NGPUS, HSGPU_DEVICE), heaviest first.
 #include <omp.h>
 #include <unistd.h>
 
@@ -43,7 +45,13 @@ static void phase(const char* name) {
         }                                                                                           \
     } while (0)
 
-// one GPU's share: read x read counts, read graphs and SNP-started clusterings of `jobs` (all high-memory contigs)
+// windows above this size are clustered on the host from the device-built graph (hsgpu_graph_whispers keeps two label
+// arrays per run in shared memory)
+static const size_t kMaxWhispersWindow = 3200;
+
+// one GPU's share: read x read counts, read graphs and SNP-started clusterings of `jobs`. High-memory contigs get
+// create_read_graph_matrix + the clustering runs; low-memory contigs (job->low_now) get the neighbour lists of
+// create_read_graph_low_memory and are clustered by the caller.
 static void gpu_shard(hsgpu_ctx* ctx, const std::vector<ColContig>& contigs, std::vector<ContigJob*>& jobs, float error_rate,
                       Shuffler& sh, int64_t* stats) {
     if (jobs.empty()) return;
@@ -91,11 +99,13 @@ static void gpu_shard(hsgpu_ctx* ctx, const std::vector<ColContig>& contigs, std
     std::vector<int32_t> win_contig, win_reads;
     std::vector<int64_t> win_off(1, 0);
     std::vector<std::pair<int, int>> win_ref;  // (job, window index)
+    std::vector<uint8_t> win_low;
     for (int j = 0; j < nc; j++) {
         for (size_t w = 0; w < jobs[j]->windows.size(); w++) {
             const Window& win = jobs[j]->windows[w];
             if (!win.has_snps) continue;
             win_contig.push_back(j);
+            win_low.push_back(jobs[j]->low_now ? 1 : 0);
             win_reads.insert(win_reads.end(), win.masked.begin(), win.masked.end());
             win_off.push_back((int64_t)win_reads.size());
             win_ref.emplace_back(j, (int)w);
@@ -103,7 +113,8 @@ static void gpu_shard(hsgpu_ctx* ctx, const std::vector<ColContig>& contigs, std
     }
     const int n_windows = (int)win_contig.size();
     hsgpu_graph* graph = nullptr;
-    GPU_CHECK(ctx, hsgpu_graph_create(pairs, n_windows, win_contig.data(), win_off.data(), win_reads.data(), error_rate, &graph));
+    GPU_CHECK(ctx, hsgpu_graph_create_ex(pairs, n_windows, win_contig.data(), win_off.data(), win_reads.data(), win_low.data(),
+                                         error_rate, &graph));
     int64_t replayed = 0;
     GPU_CHECK(ctx, hsgpu_graph_build(graph, &replayed));
     std::vector<int64_t> adj_off((size_t)win_off.back() + 1, 0);
@@ -115,8 +126,12 @@ static void gpu_shard(hsgpu_ctx* ctx, const std::vector<ColContig>& contigs, std
 
     // ---- clustering runs: one per (window, restart SNP) ----
     std::vector<int64_t> run_base((size_t)n_windows + 1, 0);  // first run of each window
+    auto on_device = [&](int w) {  // does the device cluster this window?
+        return !win_low[w] && (size_t)(win_off[w + 1] - win_off[w]) <= kMaxWhispersWindow;
+    };
     for (int w = 0; w < n_windows; w++)
-        run_base[w + 1] = run_base[w] + (int64_t)jobs[win_ref[w].first]->windows[win_ref[w].second].restart_snps.size();
+        run_base[w + 1] = run_base[w] +
+                          (on_device(w) ? (int64_t)jobs[win_ref[w].first]->windows[win_ref[w].second].restart_snps.size() : 0);
     const int64_t n_runs = run_base[n_windows];
     std::vector<int32_t> run_window((size_t)n_runs);
     std::vector<int64_t> run_off((size_t)n_runs + 1, 0);
@@ -132,6 +147,7 @@ static void gpu_shard(hsgpu_ctx* ctx, const std::vector<ColContig>& contigs, std
         std::vector<char> mask;
 #pragma omp for schedule(dynamic, 8)
         for (int w = 0; w < n_windows; w++) {
+            if (!on_device(w)) continue;
             const ContigJob& job = *jobs[win_ref[w].first];
             const Window& win = job.windows[win_ref[w].second];
             const ColContig& c = contigs[job.n];
@@ -181,14 +197,33 @@ static void gpu_shard(hsgpu_ctx* ctx, const std::vector<ColContig>& contigs, std
             int o = g.off[win.masked[i]];
             for (int64_t e = adj_off[win_off[w] + i]; e < adj_off[win_off[w] + i + 1]; e++) g.nbr[o++] = win.masked[adj[e]];
         }
+        if (win_low[w]) {  // neighbour lists of create_read_graph_low_memory: the caller clusters
+            g.list_mode = true;
+            continue;
+        }
         auto& lc = job.local_clusters[wi];
         lc.assign(win.restart_snps.size(), std::vector<int>());
+        if (!on_device(w)) {
+            // a window too large for the clustering kernel: chinese_whispers_high_memory on the host, on the graph the
+            // device built (each thread shuffles with its own generator, like the per-window loop of the pipeline)
+            Shuffler local_sh;
+            std::vector<char> mask((size_t)R, 0);
+            std::vector<int> start;
+            for (int r : win.masked) mask[r] = 1;
+            for (size_t k = 0; k < win.restart_snps.size(); k++) {
+                snp_start_labels(contigs[job.n].snps[win.restart_snps[k]], mask, start);
+                lc[k] = chinese_whispers(g, start, mask, local_sh);
+            }
+            continue;
+        }
         for (size_t k = 0; k < win.restart_snps.size(); k++) {
             lc[k].assign((size_t)R, -2);
             const int32_t* src = labels.data() + run_off[run_base[w] + (int64_t)k];
             for (int i = 0; i < m; i++) lc[k][win.masked[i]] = src[i] >= 0 ? win.masked[src[i]] : src[i];
         }
     }
+    for (int j = 0; j < nc; j++)
+        if (jobs[j]->low_now) jobs[j]->device_lists = true;
     stats[0] += n_windows;
     stats[1] += n_runs;
     stats[2] += win_off.back();
@@ -237,9 +272,14 @@ static void gpu_stages(void* user, const std::vector<ColContig>& contigs, std::v
             std::vector<ContigJob*> batch;
             double bytes = 0;
             while (i < shard[g].size()) {
-                const double r = (double)((contigs[shard[g][i]->n].read_lines.size() + 127) / 128 * 128);
-                if (!batch.empty() && bytes + r * r * 16 > 12e9) break;
-                bytes += r * r * 16;
+                // upper bound of what a contig keeps on the device: the count blocks of every tile pair (8 bytes per
+                // read pair; the band of overlapping reads in practice) and the one-hot operands (2 bytes per read
+                // and SNP of the widest contig, bounded here by its own SNP count)
+                const ColContig& cc = contigs[shard[g][i]->n];
+                const double r = (double)((cc.read_lines.size() + 127) / 128 * 128);
+                const double need = r * r * 8 + r * 2.0 * (double)((cc.snps.size() + 127) / 128 * 128);
+                if (!batch.empty() && bytes + need > 24e9) break;
+                bytes += need;
                 batch.push_back(shard[g][i++]);
             }
             gpu_shard(st.ctxs[g], contigs, batch, error_rate, sh, stats);
@@ -253,7 +293,7 @@ int main(int argc, char* argv[]) {
     if (const char* e = std::getenv("HSGPU_DEVICE")) st.first_device = std::atoi(e);
     st.ctxs.assign((size_t)st.n_gpus, nullptr);
     g_timing = std::getenv("HS_TIMING") != nullptr;
-    const int rc = separate_reads_pipeline(argc, argv, gpu_prepare, gpu_stages, &st);
+    const int rc = separate_reads_pipeline(argc, argv, gpu_prepare, gpu_stages, &st, gpu_stages);
     // The .gro file is written and closed (scoped streams in the pipeline). Skip the unwinding (CUDA context
     // teardown in the runtime's atexit handler, freeing the parsed columns): the operating system reclaims both.
     std::cout.flush();

@@ -200,7 +200,10 @@ int hsgpu_robust_filter_all(hsgpu_pileup* p, int64_t capacity, int32_t* kept, in
  * (src/separate_reads.cpp:374-433) --------------------------------------------------------------
  * SNP columns of one contig as parsed from the .col file (parse_column_file, :46-190): CSR over SNPs
  * with neighbour indices and codes, plus ref_base/second_base per SNP. sim/diff are dense
- * n_reads x n_reads int32 (row-major): similarity = 3*A*At + R*Rt, difference = A*Rt + R*At, zero diagonal. */
+ * n_reads x n_reads int32 (row-major): similarity = 3*A*At + R*Rt, difference = A*Rt + R*At, zero diagonal.
+ * The dense form exists for the caller only (at most 46000 reads, HSGPU_ERR_LIMIT beyond): on the device the counts
+ * are kept as 128 x 128 blocks over the band of reads that share SNPs, which is what hsgpu_graph_* read, so a
+ * contig's memory follows its read overlaps, not n_reads^2. */
 int hsgpu_read_pair_counts(hsgpu_ctx* ctx, int32_t n_reads, int32_t n_snps, const int64_t* snp_off,
                            const uint32_t* read_idx, const uint8_t* code, const uint8_t* ref_base,
                            const uint8_t* second_base, int32_t* sim, int32_t* diff);
@@ -238,6 +241,16 @@ void hsgpu_pairs_destroy(hsgpu_pairs* h);
 typedef struct hsgpu_graph hsgpu_graph;
 int hsgpu_graph_create(hsgpu_pairs* pairs, int32_t n_windows, const int32_t* win_contig, const int64_t* win_off,
                        const int32_t* win_reads, float error_rate, hsgpu_graph** out);
+/* The same with a per-window switch (win_low_memory[w] != 0, array may be NULL): the window's neighbour choice follows
+ * create_read_graph_low_memory (src/separate_reads.cpp:538-693, what the reference runs with -l, for amplicons and
+ * above 1000x) instead of create_read_graph_matrix: no `similarity > 0` guard on the distance, reads that appear in
+ * no SNP column are skipped. The counts are the same contig-wide similarity / difference counts of `pairs`; the
+ * reference's pairwise loop indexes a read's alleles by offset from its first SNP (:597-605), which gives those
+ * counts whenever every read covers a run of consecutive SNP columns -- the caller checks that (HS_separate_reads
+ * does, and falls back on its host loop otherwise). Limits: at most 6400 reads per window here, 3200 for
+ * hsgpu_graph_whispers (HSGPU_ERR_LIMIT beyond). */
+int hsgpu_graph_create_ex(hsgpu_pairs* pairs, int32_t n_windows, const int32_t* win_contig, const int64_t* win_off,
+                          const int32_t* win_reads, const uint8_t* win_low_memory, float error_rate, hsgpu_graph** out);
 /* builds the adjacency of every window. n_replayed (may be NULL) receives the number of reads whose neighbour
  * choice depended on std::sort's order of equal distances and was replayed with the reference's sort. */
 int hsgpu_graph_build(hsgpu_graph* g, int64_t* n_replayed);

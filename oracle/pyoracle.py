@@ -344,6 +344,23 @@ class RefSR:
         return adj_off, adj[:int(n)]
 
     @classmethod
+    def read_graph_low_memory(cls, col, masked, error_rate):
+        """the reference's create_read_graph_low_memory on SNP columns -> (adj_off, adj) over the masked reads"""
+        n_reads, snp_off, idx, code, rb, sb = col
+        snp_off, idx, code = _arr(snp_off, np.int64), _arr(idx, np.uint32), _arr(code, np.uint8)
+        rb, sb, masked = _arr(rb, np.uint8), _arr(sb, np.uint8), _arr(masked, np.int32)
+        f = cls.lib().hsref_read_graph_low_memory
+        f.restype = C.c_int64
+        f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+        adj_off = np.zeros(masked.size + 1, np.int64)
+        n = f(n_reads, snp_off.size - 1, snp_off.ctypes.data, idx.ctypes.data, code.ctypes.data, rb.ctypes.data, sb.ctypes.data,
+              masked.size, masked.ctypes.data, float(error_rate), adj_off.ctypes.data, None)
+        adj = np.zeros(max(int(n), 1), np.int32)
+        f(n_reads, snp_off.size - 1, snp_off.ctypes.data, idx.ctypes.data, code.ctypes.data, rb.ctypes.data, sb.ctypes.data,
+          masked.size, masked.ctypes.data, float(error_rate), adj_off.ctypes.data, adj.ctypes.data)
+        return adj_off, adj[:int(n)]
+
+    @classmethod
     def chinese_whispers(cls, n_reads, masked, adj_off, adj, init_reads):
         """chinese_whispers_high_memory (src/cluster_graph.cpp:240-310), random_device pinned; labels as read indices"""
         masked = np.ascontiguousarray(masked, np.int32)

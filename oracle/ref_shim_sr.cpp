@@ -7,6 +7,7 @@
 //   list_similarities_and_differences_between_reads3   src/separate_reads.cpp:374  (Eigen sparse products)
 //   list_similarities_and_differences_between_reads2   src/separate_reads.cpp:323  (its dense restatement)
 //   create_read_graph_matrix                           src/separate_reads.cpp:706
+//   create_read_graph_low_memory                       src/separate_reads.cpp:538  (the -l / amplicon / > 1000x path)
 //   chinese_whispers_high_memory                       src/cluster_graph.cpp:240  (std::random_device pinned by
 //                                                      ref_pin_rng.cpp, linked into this library with -Bsymbolic)
 #include <cstdint>
@@ -15,6 +16,10 @@
 
 #include "cluster_graph.h"
 #include "separate_reads.h"
+
+// the definition in src/separate_reads.cpp:538-544 (the header declares another parameter type for the lists)
+void create_read_graph_low_memory(std::vector<Column>& snps, std::vector<bool>& mask, int chunk, int sizeOfWindow,
+                                  std::vector<std::vector<int>>& neighbor_list_low_memory, float& errorRate);
 
 static std::vector<Column> make_columns(int n_snps, const int64_t* snp_off, const uint32_t* idx, const uint8_t* code,
                                         const uint8_t* rb, const uint8_t* sb) {
@@ -71,6 +76,32 @@ int64_t hsref_read_graph(int n_reads, int n_snps, const int64_t* snp_off, const 
         for (Eigen::SparseMatrix<int>::InnerIterator it(adjacency, masked[i]); it; ++it) {
             if (it.value() == 0) continue;
             if (adj) adj[n] = local[it.row()];
+            n++;
+        }
+    }
+    adj_off[m] = n;
+    return n;
+}
+
+// create_read_graph_low_memory over the SNP columns of a contig: the sorted neighbour lists of the masked reads, as
+// a CSR over the masked reads with local indices (same output form as hsref_read_graph)
+int64_t hsref_read_graph_low_memory(int n_reads, int n_snps, const int64_t* snp_off, const uint32_t* idx, const uint8_t* code,
+                                    const uint8_t* rb, const uint8_t* sb, int m, const int32_t* masked, float error_rate,
+                                    int64_t* adj_off, int32_t* adj) {
+    std::vector<Column> snps = make_columns(n_snps, snp_off, idx, code, rb, sb);
+    std::vector<bool> mask(n_reads, false);
+    std::vector<int> local(n_reads, -1);
+    for (int i = 0; i < m; i++) {
+        mask[masked[i]] = true;
+        local[masked[i]] = i;
+    }
+    std::vector<std::vector<int>> lists(n_reads);
+    create_read_graph_low_memory(snps, mask, 0, 2000, lists, error_rate);
+    int64_t n = 0;
+    for (int i = 0; i < m; i++) {
+        adj_off[i] = n;
+        for (int r : lists[masked[i]]) {
+            if (adj) adj[n] = local[r];
             n++;
         }
     }

@@ -238,3 +238,85 @@ def test_usage_and_help_status():
     assert r.returncode == 0 and b"Usage" in r.stdout
     r = subprocess.run([OURS], stdout=subprocess.PIPE)
     assert r.returncode == 1
+
+
+def _lowmem_check(ctx, col, masked_list, err):
+    """device neighbour lists (hsgpu_graph_create_ex, low-memory windows) against the host path's
+    create_read_graph_low_memory (hairsplitter_b200/host) and, when it travelled, the reference's own function"""
+    from oracle import pyoracle
+    pairs = api.Pairs(ctx, [col])
+    pairs.compute()
+    g = api.Graph(pairs, [(0, m) for m in masked_list], err, low_memory=[1] * len(masked_list))
+    g.build()
+    adj_off, adj = g.adjacency()
+    base = 0
+    for masked in masked_list:
+        h_off, h_adj, consecutive = api.HostLogic.read_graph_low_memory(col, masked, err)
+        assert consecutive
+        m = masked.size
+        assert np.array_equal(adj_off[base:base + m + 1] - adj_off[base], h_off)
+        assert np.array_equal(adj[adj_off[base]:adj_off[base + m]], h_adj)
+        if pyoracle.RefSR.available():
+            r_off, r_adj = pyoracle.RefSR.read_graph_low_memory(col, masked, err)
+            assert np.array_equal(h_off, r_off) and np.array_equal(h_adj, r_adj)
+        base += m
+    n_links, replayed = adj.size, g.replayed
+    g.close()
+    pairs.close()
+    return n_links, replayed
+
+
+def test_low_memory_read_graph_on_the_device(ctx, oracle):
+    """a15: create_read_graph_low_memory (src/separate_reads.cpp:538-693) from the tensor-core pair counts: windows of
+    an ONT contig, an amplicon-like column set (every read on every SNP, coarse distances: ties and NaN distances of
+    pairs without a common SNP are replayed with the reference's sort), reads without any SNP cell"""
+    cb = cases.small_case(seed=291, length=20000, depth=50, mean_len=5000, error=0.06)
+    col, pos = cases.snp_columns(oracle, cb, 0.06)
+    wins = [m for m, _ in cases.windows_of(col, pos)]
+    links, _ = _lowmem_check(ctx, col, wins, 0.06)
+    assert links > 0
+    rng = np.random.default_rng(23)
+    total_replayed = 0
+    for n_reads, n_snps, err in [(60, 8, 0.1), (200, 5, 0.2), (33, 4, 0.3), (300, 8, 0.1)]:
+        c = cases.coarse_columns(rng, n_reads, n_snps)
+        masked = np.sort(rng.choice(n_reads, size=n_reads - 3, replace=False)).astype(np.int32)
+        _, rep = _lowmem_check(ctx, c, [masked, masked[: n_reads // 2]], err)
+        total_replayed += rep
+    # reads 0..4 appear in no SNP column (mask_extend drops them), reads 5..9 only on the first SNP
+    n_reads, n_snps = 50, 6
+    c = list(cases.coarse_columns(rng, n_reads, n_snps))
+    off, idx, code = c[1], c[2], c[3]
+    keep = np.ones(idx.size, bool)
+    for s in range(n_snps):
+        seg = slice(int(off[s]), int(off[s + 1]))
+        keep[seg] &= idx[seg] >= 5
+        if s > 0:
+            keep[seg] &= idx[seg] >= 10
+    new_off = np.zeros(n_snps + 1, np.int64)
+    for s in range(n_snps):
+        new_off[s + 1] = new_off[s] + int(keep[int(off[s]):int(off[s + 1])].sum())
+    c = (n_reads, new_off, idx[keep], code[keep], c[4], c[5])
+    _lowmem_check(ctx, c, [np.arange(n_reads, dtype=np.int32), np.arange(0, n_reads, 2, dtype=np.int32)], 0.1)
+
+
+def test_low_memory_executable_device_and_host_lists_agree(tmp_path):
+    """HS_separate_reads -l on the low-memory golden: device neighbour lists (default) and HS_LOWMEM_HOST=1 give the
+    same .gro, which is the RNG-pinned reference's"""
+    import gzip
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_sr
+    _, err, low, rare, amp = make_golden_sr.CASES["lowmem"]
+    assert low == "1"
+    gold = os.path.join(ROOT, "tests", "golden")
+    col = os.path.join(str(tmp_path), "in.col")
+    with gzip.open(os.path.join(gold, "sr_lowmem.col.gz"), "rb") as f, open(col, "wb") as o:
+        o.write(f.read())
+    want = gzip.open(os.path.join(gold, "sr_lowmem.gro.gz"), "rb").read()
+    for tag, extra in (("dev", {}), ("host", {"HS_LOWMEM_HOST": "1"})):
+        gro = os.path.join(str(tmp_path), tag + ".gro")
+        env = dict(os.environ, HS_PIN_SEED=str(PIN_SEED), HS_TIMING="1", **extra)
+        r = subprocess.run([OURS, col, "4", err, os.path.join(str(tmp_path), "nop"), low, rare, amp, gro, "0"], check=True,
+                           env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        assert open(gro, "rb").read() == want, tag
+        assert ("low-memory read graphs" in r.stderr.decode()) == (tag == "dev")
