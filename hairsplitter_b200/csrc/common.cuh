@@ -237,12 +237,11 @@ struct hsgpu_pileup {
     // partitions of the batch (hsgpu_partitions_set) and the work arrays of the robust filter (contingency.cu)
     void* d_filter_block = nullptr;
     void* d_fdesc = nullptr;
-    uint8_t* d_pst_t = nullptr;
-    uint32_t* d_pmask = nullptr;
+    uint32_t* d_frows = nullptr;  // 2-bit partition states per read (contingency.cu)
     bool have_parts = false;
     void* d_filter_work = nullptr;
     uint32_t* d_factive = nullptr;
-    uint8_t* d_fkept = nullptr;
+    uint32_t* d_fkept = nullptr;  // bitmap of the kept columns
     int32_t* d_fkept_list = nullptr;
     unsigned int* d_fcounters = nullptr;
     int64_t* d_fhdr = nullptr;

@@ -232,20 +232,22 @@ __global__ void __launch_bounds__(128) partition_tables_kernel(TablesArgs a) {
 // One launch covers all contigs of the batch; the work is proportional to the active columns, not to the tiles.
 #define HS_FLAG_INLIST 16
 #define RF_WARPS 8
-#define RF_CAP 192  // cells of a column staged per warp; deeper columns (amplicons) are re-gathered per partition
+#define RF_CAP 128  // cells of a column staged per warp; deeper columns (amplicons) are re-gathered per partition
 
+// Partition states on the device: per read one row of 2-bit states, 128 partitions (8 words) per block: 0 = the read
+// is not in the partition (or masked), 1 = +1, 2 = -1, 3 = 0. A column's cells load their row of the current block
+// once (32 bytes per read) into shared memory; which partitions hold one of the column's reads, and every state the
+// table passes need, come from there.
 struct FilterDesc {     // per contig
-    int64_t pst_off;    // byte offset of its [n_reads][npad] state rows in pst_t
-    int64_t pmask_off;  // word offset of its [n_reads][pwords] presence rows in pmask
-    int32_t n_parts, npad, pwords, pad_;
+    int64_t row_off;    // word offset of its [n_reads][pwords] state rows
+    int32_t n_parts, pwords;  // pwords = 8 * ceil(n_parts / 128)
 };
 
 struct FilterArgs {
     int n_contigs;
     unsigned in_flag;  // the flag bit that marks snps_in: HS_FLAG_INLIST (caller's list) or HS_FLAG_SUSPECT (the pileup's own)
     const FilterDesc* desc;
-    const uint8_t* pst_t;
-    const uint32_t* pmask;
+    const uint32_t* rows;    // 2-bit partition states, all contigs
     const int64_t* col_base;
     const int64_t* tile_base;
     const int64_t* contig_read_off;
@@ -256,6 +258,7 @@ struct FilterArgs {
     const int64_t* row_base;
     const uint8_t* codes;
     const uint8_t* k0;
+    const uint8_t* k1;
     const uint8_t* flags;
     const uint32_t* depth;
     const uint32_t* counts;  // c0,c1,c2 per column (column ranking)
@@ -264,7 +267,7 @@ struct FilterArgs {
     uint32_t* active;        // compacted global ids of the active columns
     unsigned int* counters;  // [0] active columns, [1] work cursor of robust_filter_kernel, [2] kept columns (list
                              // reservation), [4..5] / [6..7] 64-bit: cells of the active columns / state bytes read
-    uint8_t* kept;           // [n_cols]
+    uint32_t* kept;          // bitmap over the columns of the batch (bit g & 31 of word g >> 5), zeroed by the caller
 };
 
 __device__ __forceinline__ int rf_contig_of(const int64_t* __restrict__ col_base, int n_contigs, int64_t g) {
@@ -282,21 +285,27 @@ __device__ __forceinline__ int rf_contig_of(const int64_t* __restrict__ col_base
 // can only be kept by loop 3, i.e. if it is in snps_in.
 __global__ void __launch_bounds__(256) filter_active_kernel(FilterArgs a) {
     const int lane = threadIdx.x & 31;
-    const int64_t g = a.g_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool act = false;
-    if (g < a.g_end) {
-        const unsigned f = a.flags[g];
-        act = (f & a.in_flag) != 0;
-        if (!act && (f & HS_FLAG_RESCUE)) act = a.counts[3 * g + 1] > 4u;
-        if (act) act = a.desc[rf_contig_of(a.col_base, a.n_contigs, g)].n_parts > 0;  // :640-642: no partition, nothing kept
-        a.kept[g] = 0;
-    }
-    const unsigned mk = __ballot_sync(0xffffffffu, act);
-    if (mk) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(a.counters, (unsigned)__popc(mk));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (act) a.active[base + __popc(mk & ((1u << lane) - 1u))] = (uint32_t)g;
+    // four columns per thread: one 4-byte load of the flags (the flag array starts 256-byte aligned)
+    const int64_t g4 = (a.g_begin & ~(int64_t)3) + 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    uint32_t f4 = 0;
+    if (g4 < a.g_end) f4 = __ldg(reinterpret_cast<const uint32_t*>(a.flags + g4));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t g = g4 + k;
+        const unsigned f = (f4 >> (8 * k)) & 0xffu;
+        bool act = false;
+        if (g >= a.g_begin && g < a.g_end && (f & (a.in_flag | HS_FLAG_RESCUE))) {
+            act = (f & a.in_flag) != 0;
+            if (!act) act = a.counts[3 * g + 1] > 4u;
+            if (act) act = a.desc[rf_contig_of(a.col_base, a.n_contigs, g)].n_parts > 0;  // :640-642: no partition, nothing kept
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, act);
+        if (mk) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(a.counters, (unsigned)__popc(mk));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (act) a.active[base + __popc(mk & ((1u << lane) - 1u))] = (uint32_t)g;
+        }
     }
 }
 
@@ -375,25 +384,19 @@ __device__ __noinline__ float rf_chi_square(int n00, int n01, int n10, int n11) 
 
 // Several codes share the maximum of a (column, partition) pair: the reference's map iteration order decides
 // (:832-844). The order of first appearance among the partition's reads is rebuilt by lane 0 (rare path).
-__device__ __noinline__ int rf_tied_alt(const FilterArgs& a, const uint8_t* pst_p, int npad, int q, int64_t l0, int64_t l1,
-                                         int64_t read0, bool staged, int ncell, const uint8_t* s_code, const uint8_t* s_st,
-                                         uint32_t* s_hist, int ref, int nref, int max2) {
+__device__ __noinline__ int rf_tied_alt(const FilterArgs& a, const uint32_t* rows_c, int pwords, int p, int q, int64_t l0, int64_t l1,
+                                         int64_t read0, uint32_t* s_hist, int ref, int nref, int max2) {
     uint8_t order[HS_NCODES + 1];
     int mo = 0;
-    auto see = [&](int code) {
-        const int idx = code - HS_CODE0;
+    for (int64_t l = l0; l < l1; l++) {
+        const int32_t r = a.tile_reads[l];
+        if (!(a.read_start[r] <= q && q < a.read_end[r])) continue;
+        const uint32_t w = rows_c[(int64_t)(r - read0) * pwords + (p >> 4)];
+        if (((w >> (2 * (p & 15))) & 3u) == 0) continue;
+        const int idx = a.codes[a.row_base[r] + q] - HS_CODE0;
         bool seen = false;
         for (int k = 0; k < mo; k++) seen |= order[k] == idx;
         if (!seen) order[mo++] = (uint8_t)idx;
-    };
-    if (staged) {
-        for (int i = 0; i < ncell; i++)
-            if (s_st[i]) see(s_code[i]);
-    } else {
-        for (int64_t l = l0; l < l1; l++) {
-            const int32_t r = a.tile_reads[l];
-            if (a.read_start[r] <= q && q < a.read_end[r] && (pst_p[(int64_t)(r - read0) * npad] & 3)) see(a.codes[a.row_base[r] + q]);
-        }
     }
     if (nref > 0) s_hist[ref - HS_CODE0] = (uint32_t)nref;
     const int alt = rf_select_alt_tied(order, s_hist, mo, ref, max2, a.lut);
@@ -404,14 +407,14 @@ __device__ __noinline__ int rf_tied_alt(const FilterArgs& a, const uint8_t* pst_
 __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterArgs a) {
     __shared__ int32_t s_n_all[RF_WARPS][RF_CAP];
     __shared__ uint8_t s_code_all[RF_WARPS][RF_CAP];
-    __shared__ uint8_t s_st_all[RF_WARPS][RF_CAP];
+    __shared__ __align__(16) uint32_t s_row_all[RF_WARPS][RF_CAP * 9];  // 8 state words per cell, rows padded to 9 words
     __shared__ uint32_t s_hist_all[RF_WARPS][HS_NCODES + 3];
     __shared__ uint8_t s_touched_all[RF_WARPS][HS_NCODES + 3];
     __shared__ int s_m_all[RF_WARPS];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int32_t* const s_n = s_n_all[wid];
     uint8_t* const s_code = s_code_all[wid];
-    uint8_t* const s_st = s_st_all[wid];
+    uint32_t* const s_row = s_row_all[wid];
     uint32_t* const s_hist = s_hist_all[wid];
     uint8_t* const s_touched = s_touched_all[wid];
     int* const s_m = &s_m_all[wid];
@@ -435,8 +438,14 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterA
         const int ref = a.k0[g];
         const unsigned f = a.flags[g];
         const bool inlist = (f & a.in_flag) != 0;
-        const uint8_t* __restrict__ pst = a.pst_t + d.pst_off;
-        const uint32_t* __restrict__ pm = a.pmask + d.pmask_off;
+        const uint32_t* __restrict__ rows_c = a.rows + d.row_off;
+        // A column outside snps_in is only kept through loop 4, which needs n10 + n00 > 4 (:756): at least 5 of a
+        // partition's reads on one code other than ref_base. When the column's third most frequent code has at most 4
+        // carriers in all (c2 <= 4), only its second code k1 can get there, and it then is the strict maximum of the
+        // partition: no histogram, one pass of ballots per partition. (Codes >= 128 never count as ref_base in the
+        // reference's comparison, :838: those columns take the general path.)
+        const bool single = !inlist && ref < 128 && a.counts[3 * g + 2] <= 4u;
+        const int k1 = a.k1[g];
         // ---- the column's cells, in ascending read order ----
         int ncell = 0;
         for (int64_t lb = l0; lb < l1; lb += 32) {
@@ -465,65 +474,89 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterA
     } else {                                                                                       \
         cl = rf_gather_cell(a, q, l0 + 32 * (int64_t)(ch), l1, read0, lane);                        \
     }
+        // state of the lane's cell in partition pb + pl (pl < 128) of the current block
+#define RF_STATE(cl, slot, pl)                                                                     \
+    ((cl).code == 0 ? 0                                                                            \
+                    : (int)((((slot) >= 0 ? s_row[(slot) * 9 + ((pl) >> 4)]                          \
+                                          : __ldg(rows_c + (int64_t)(cl).n * d.pwords + (pb >> 4) + ((pl) >> 4))) >> (2 * ((pl) & 15))) & 3u))
         bool keep = false;
         int n_visited = 0;  // partitions whose states were read
         for (int pb = 0; pb < d.n_parts && !keep; pb += 128) {
-            // partitions pb..pb+127 that hold at least one of the column's reads (one 128-bit presence row per read)
-            uint32_t present[4] = {0, 0, 0, 0};
+            // the cells' state rows of this block of 128 partitions; which partitions hold one of the column's reads
+            uint32_t nz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
             for (int ch = 0; ch < nchunk; ch++) {
                 RF_CELL(ch, cl, slot)
-                (void)slot;
                 if (cl.code != 0) {
-                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(pm + (int64_t)cl.n * d.pwords + (pb >> 5)));
-                    present[0] |= x.x; present[1] |= x.y; present[2] |= x.z; present[3] |= x.w;
+                    const uint4* src = reinterpret_cast<const uint4*>(rows_c + (int64_t)cl.n * d.pwords + (pb >> 4));
+                    const uint4 x = __ldg(src), y = __ldg(src + 1);
+                    const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        nz[k] |= w[k];
+                        if (slot >= 0) s_row[slot * 9 + k] = w[k];
+                    }
                 }
             }
 #pragma unroll
-            for (int w = 0; w < 4; w++) present[w] = __reduce_or_sync(0xffffffffu, present[w]);
+            for (int k = 0; k < 8; k++) {
+                nz[k] = __reduce_or_sync(0xffffffffu, nz[k]);
+                nz[k] = (nz[k] | (nz[k] >> 1)) & 0x55555555u;  // bit 2j = partition 16k + j holds a read of the column
+            }
+            __syncwarp();
 #pragma unroll 1
-            for (int w = 0; w < 4 && !keep; w++) {
-                uint32_t bits = present[w];
+            for (int k = 0; k < 8 && !keep; k++) {
+                uint32_t bits = nz[k];
 #pragma unroll 1
                 while (bits && !keep) {
-                    const int p = pb + 32 * w + __ffs(bits) - 1;
+                    const int pl = 16 * k + ((__ffs(bits) - 1) >> 1);
                     bits &= bits - 1;
                     n_visited++;
-                    const uint8_t* __restrict__ pst_p = pst + p;
-                    // ---- pass 1: the partition's reads on this column. The column's own majority code is counted
-                    // with ballots (its rows with state +1 / -1 are n11 / n01, :893-949), every other code goes
-                    // through the warp's histogram ----
-                    int nb = 0, nref = 0, n11 = 0, n01 = 0;
+                    int n00 = 0, n01 = 0, n10 = 0, n11 = 0;
+                    bool table = false;
+                    if (single) {
+                        int cnt1 = 0;
 #pragma unroll 1
-                    for (int ch = 0; ch < nchunk; ch++) {
-                        RF_CELL(ch, cl, slot)
-                        int sg = 0;
-                        if (cl.code != 0) {
-                            sg = __ldg(pst_p + (int64_t)cl.n * d.npad) & 3;
-                            if (slot >= 0) s_st[slot] = (uint8_t)sg;
+                        for (int ch = 0; ch < nchunk; ch++) {
+                            RF_CELL(ch, cl, slot)
+                            const int sg = RF_STATE(cl, slot, pl);
+                            const unsigned b1 = __ballot_sync(0xffffffffu, sg == 1), b2 = __ballot_sync(0xffffffffu, sg == 2);
+                            const unsigned b3 = __ballot_sync(0xffffffffu, sg == 3);
+                            const unsigned bref = __ballot_sync(0xffffffffu, cl.code == ref);
+                            const unsigned balt = __ballot_sync(0xffffffffu, cl.code == k1);
+                            n11 += __popc(b1 & bref);
+                            n01 += __popc(b2 & bref);
+                            n10 += __popc(b1 & balt);
+                            n00 += __popc(b2 & balt);
+                            cnt1 += __popc((b1 | b2 | b3) & balt);
                         }
-                        const bool act = sg != 0;
-                        const bool isref = act && cl.code == ref;
-                        nb += __popc(__ballot_sync(0xffffffffu, act));
-                        const unsigned mref = __ballot_sync(0xffffffffu, isref);
-                        nref += __popc(mref);
-                        n11 += __popc(__ballot_sync(0xffffffffu, isref && sg == 1));
-                        n01 += __popc(__ballot_sync(0xffffffffu, isref && sg == 2));
-                        if (act && !isref) {
-                            if (atomicAdd(&s_hist[cl.code - HS_CODE0], 1u) == 0u)
-                                s_touched[atomicAdd(s_m, 1)] = (uint8_t)(cl.code - HS_CODE0);
+                        table = cnt1 > 4;
+                    } else {
+                        // ---- pass 1: the partition's reads on this column. The column's own majority code is counted
+                        // with ballots (its rows with state +1 / -1 are n11 / n01, :893-949), every other code goes
+                        // through the warp's histogram ----
+                        int nb = 0, nref = 0;
+#pragma unroll 1
+                        for (int ch = 0; ch < nchunk; ch++) {
+                            RF_CELL(ch, cl, slot)
+                            const int sg = RF_STATE(cl, slot, pl);
+                            const bool act = sg != 0;
+                            const bool isref = act && cl.code == ref;
+                            nb += __popc(__ballot_sync(0xffffffffu, act));
+                            nref += __popc(__ballot_sync(0xffffffffu, isref));
+                            n11 += __popc(__ballot_sync(0xffffffffu, isref && sg == 1));
+                            n01 += __popc(__ballot_sync(0xffffffffu, isref && sg == 2));
+                            if (act && !isref) {
+                                if (atomicAdd(&s_hist[cl.code - HS_CODE0], 1u) == 0u)
+                                    s_touched[atomicAdd(s_m, 1)] = (uint8_t)(cl.code - HS_CODE0);
+                            }
                         }
-                    }
-                    __syncwarp();
-                    const int m = *s_m;  // distinct codes other than ref_base
-                    if (nb > 0) {
-                        // A column outside snps_in is only kept through loop 4, which needs n10 + n00 > 4 (:756): at
-                        // least 5 of the partition's reads on one code other than ref_base (codes >= 128 never count
-                        // as ref_base in the reference's comparison, :838: no shortcut there)
+                        __syncwarp();
+                        const int m = *s_m;  // distinct codes other than ref_base
                         int maxc = -1;
-                        for (int k = lane; k < m; k += 32) maxc = max(maxc, (int)s_hist[s_touched[k]]);
+                        for (int k2 = lane; k2 < m; k2 += 32) maxc = max(maxc, (int)s_hist[s_touched[k2]]);
                         maxc = __reduce_max_sync(0xffffffffu, maxc);
-                        if (inlist || ref >= 128 || maxc > 4) {
+                        if (nb > 0 && (inlist || ref >= 128 || maxc > 4)) {
                             // secondFrequent (:832-844): the most frequent code other than ref_base (ref_base itself
                             // competes when it is >= 128)
                             int max2 = maxc, alt = ' ';
@@ -531,11 +564,11 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterA
                             if (ref_competes && nref > max2) max2 = nref;
                             int ties = 0, cand = ' ';
                             for (int k0 = 0; k0 < m; k0 += 32) {
-                                const int k = k0 + lane;
-                                const bool hitk = k < m && (int)s_hist[s_touched[k]] == max2;
+                                const int k2 = k0 + lane;
+                                const bool hitk = k2 < m && (int)s_hist[s_touched[k2]] == max2;
                                 const unsigned mk = __ballot_sync(0xffffffffu, hitk);
                                 ties += __popc(mk);
-                                if (mk) cand = __shfl_sync(0xffffffffu, hitk ? (int)s_touched[k] + HS_CODE0 : 0, __ffs(mk) - 1);
+                                if (mk) cand = __shfl_sync(0xffffffffu, hitk ? (int)s_touched[k2] + HS_CODE0 : 0, __ffs(mk) - 1);
                             }
                             if (ref_competes && nref == max2) { ties++; cand = ref; }
                             if (max2 >= 0) {
@@ -543,62 +576,68 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterA
                                     alt = cand;
                                 } else {
                                     int alt0 = ' ';
-                                    if (lane == 0)
-                                        alt0 = rf_tied_alt(a, pst_p, d.npad, q, l0, l1, read0, staged, ncell, s_code, s_st, s_hist, ref,
-                                                           nref, max2);
+                                    if (lane == 0) alt0 = rf_tied_alt(a, rows_c, d.pwords, pb + pl, q, l0, l1, read0, s_hist, ref, nref, max2);
                                     alt = __shfl_sync(0xffffffffu, alt0, 0);
                                 }
                             }
                             // ---- pass 2: n10 / n00 ----
-                            int n10 = 0, n00 = 0;
                             if (alt != ref && alt != ' ') {
 #pragma unroll 1
                                 for (int ch = 0; ch < nchunk; ch++) {
                                     RF_CELL(ch, cl, slot)
-                                    int sg = 0;
-                                    if (cl.code == alt) sg = slot >= 0 ? (int)s_st[slot] : (__ldg(pst_p + (int64_t)cl.n * d.npad) & 3);
+                                    const int sg = cl.code == alt ? RF_STATE(cl, slot, pl) : 0;
                                     n10 += __popc(__ballot_sync(0xffffffffu, sg == 1));
                                     n00 += __popc(__ballot_sync(0xffffffffu, sg == 2));
                                 }
                             }
-                            // loop 3 (:721-738): columns of snps_in; loop 4 (:745-764): rescue of every other column (also
-                            // of suspects that failed loop 3). The chi-square is only evaluated where an integer
-                            // condition leaves the decision open.
-                            const bool c3 = inlist && (double)(n00 + n01 + n10 + n11) > __dmul_rn(0.5, (double)a.depth[g]);
-                            const bool c4 = (f & HS_FLAG_RESCUE) && n10 + n00 > 4 && n01 + n11 > 4;
-                            if (c3 || c4) {
-                                const float chi = rf_chi_square(n00, n01, n10, n11);
-                                if ((c3 && chi > 15.f) || (c4 && (double)chi > 20.0)) keep = true;
-                            }
+                            table = true;
+                        }
+                        // reset the histogram
+                        for (int k2 = lane; k2 < m; k2 += 32) s_hist[s_touched[k2]] = 0;
+                        if (lane == 0) *s_m = 0;
+                        __syncwarp();
+                    }
+                    if (table) {
+                        // loop 3 (:721-738): columns of snps_in; loop 4 (:745-764): rescue of every other column (also
+                        // of suspects that failed loop 3). The chi-square is only evaluated where an integer
+                        // condition leaves the decision open.
+                        const bool c3 = inlist && (double)(n00 + n01 + n10 + n11) > __dmul_rn(0.5, (double)a.depth[g]);
+                        const bool c4 = (f & HS_FLAG_RESCUE) && n10 + n00 > 4 && n01 + n11 > 4;
+                        if (c3 || c4) {
+                            const float chi = rf_chi_square(n00, n01, n10, n11);
+                            if ((c3 && chi > 15.f) || (c4 && (double)chi > 20.0)) keep = true;
                         }
                     }
-                    // reset the histogram
-                    for (int k = lane; k < m; k += 32) s_hist[s_touched[k]] = 0;
-                    if (lane == 0) *s_m = 0;
-                    __syncwarp();
                 }
             }
+            __syncwarp();
         }
 #undef RF_CELL
+#undef RF_STATE
         if (lane == 0) {
-            if (keep) a.kept[g] = 1;
+            if (keep) atomicOr(a.kept + (g >> 5), 1u << (g & 31));
             atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 4), (unsigned long long)ncell);
             atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 6), (unsigned long long)ncell * (unsigned)n_visited);
         }
     }
 }
 
-// ascending compaction of the kept columns, one CTA of 1024 threads per contig: a first sweep counts, one atomic
-// reserves the contig's slice of the packed list (hdr[2c] = start, hdr[2c+1] = count), a second sweep writes the
-// positions in order. A round covers 16 columns per thread.
-__device__ __forceinline__ unsigned rf_kept_bits(const uint8_t* __restrict__ kept, int64_t g0, int L, int q0) {
-    unsigned bits = 0;
-    for (int j = 0; j < 16 && q0 + j < L; j++) bits |= (kept[g0 + q0 + j] ? 1u : 0u) << j;
+// ascending compaction of the kept columns, one CTA of 1024 threads per contig over the kept bitmap: a first sweep
+// counts, one atomic reserves the contig's slice of the packed list (hdr[2c] = start, hdr[2c+1] = count), a second
+// sweep writes the positions in order. A round covers 32 columns per thread.
+__device__ __forceinline__ unsigned rf_kept_bits(const uint32_t* __restrict__ kept, int64_t g0, int L, int q0) {
+    if (q0 >= L) return 0u;
+    const int64_t g = g0 + q0;
+    const int sh = (int)(g & 31);
+    const uint32_t lo = __ldg(kept + (g >> 5));
+    const uint32_t hi = sh ? __ldg(kept + (g >> 5) + 1) : 0u;  // the bitmap has a spare word at its end
+    unsigned bits = __funnelshift_r(lo, hi, sh);
+    if (L - q0 < 32) bits &= (1u << (L - q0)) - 1u;
     return bits;
 }
 __global__ void __launch_bounds__(1024) kept_scan_kernel(int contig0, const int64_t* __restrict__ col_base,
                                                          const int32_t* __restrict__ contig_len,
-                                                         const uint8_t* __restrict__ kept, unsigned int* __restrict__ total,
+                                                         const uint32_t* __restrict__ kept, unsigned int* __restrict__ total,
                                                          int64_t capacity, int32_t* __restrict__ out, int64_t* __restrict__ hdr) {
     __shared__ int s_warp[32];
     __shared__ int s_total;
@@ -608,7 +647,7 @@ __global__ void __launch_bounds__(1024) kept_scan_kernel(int contig0, const int6
     const int L = contig_len[c];
     const int64_t g0 = col_base[c];
     int cnt_all = 0;
-    for (int r0 = 0; r0 < L; r0 += 1024 * 16) cnt_all += __popc(rf_kept_bits(kept, g0, L, r0 + 16 * tid));
+    for (int r0 = 0; r0 < L; r0 += 1024 * 32) cnt_all += __popc(rf_kept_bits(kept, g0, L, r0 + 32 * tid));
     cnt_all = hs_warp_incl_scan(cnt_all, lane);
     if (lane == 31) s_warp[wid] = cnt_all;
     __syncthreads();
@@ -621,8 +660,8 @@ __global__ void __launch_bounds__(1024) kept_scan_kernel(int contig0, const int6
     }
     __syncthreads();
     int64_t n = s_start;  // list position of the next kept column (same value in every thread)
-    for (int r0 = 0; r0 < L; r0 += 1024 * 16) {
-        const int q0 = r0 + 16 * tid;
+    for (int r0 = 0; r0 < L; r0 += 1024 * 32) {
+        const int q0 = r0 + 32 * tid;
         unsigned bits = rf_kept_bits(kept, g0, L, q0);
         const int cnt = __popc(bits);
         const int incl = hs_warp_incl_scan(cnt, lane);
@@ -738,27 +777,23 @@ int hsgpu_partition_tables(hsgpu_pileup* p, int32_t contig, const hsgpu_partitio
     return HSGPU_OK;
 }
 
-// the partitions of one contig in the two forms robust_filter_kernel reads: state rows [n_reads][npad] (1 = +1,
-// 2 = -1, 3 = 0, 0 = absent or masked; |4 solid) and presence rows [n_reads][pwords] (bit p = the read is in
-// partition p with a state other than masked)
-static int build_filter_rows(hsgpu_ctx* ctx, const hsgpu_partitions* parts, int64_t n_reads, int npad, int pwords,
-                             uint8_t* pst_t, uint32_t* pmask) {
-    memset(pst_t, 0, (size_t)n_reads * (size_t)npad);
-    memset(pmask, 0, (size_t)n_reads * (size_t)pwords * sizeof(uint32_t));
+// the partitions of one contig as robust_filter_kernel reads them: per read one row of 2-bit states, 16 partitions
+// per word, pwords words (1 = +1, 2 = -1, 3 = 0, 0 = absent or masked)
+static int build_filter_rows(hsgpu_ctx* ctx, const hsgpu_partitions* parts, int64_t n_reads, int pwords, uint32_t* rows) {
+    memset(rows, 0, (size_t)n_reads * (size_t)pwords * sizeof(uint32_t));
     for (int p = 0; p < parts->n_parts; p++) {
         for (int64_t i = parts->part_off[p]; i < parts->part_off[p + 1]; i++) {
             const int32_t n = parts->read_idx[i];
             if (n < 0 || n >= n_reads) HS_FAIL(ctx, HSGPU_ERR_ARG, "partition read index out of range");
-            uint8_t v = 0;
+            uint32_t v = 0;
             switch (parts->state[i]) {
                 case 1: v = 1; break;
                 case -1: v = 2; break;
                 case 0: v = 3; break;
                 default: v = 0; break;  // -2: masked
             }
-            if (v && parts->less && parts->more && parts->less[i] <= 1 && parts->more[i] >= 3) v |= 4;
-            pst_t[(size_t)n * npad + p] = v;
-            if (v) pmask[(size_t)n * pwords + (p >> 5)] |= 1u << (p & 31);
+            uint32_t& w = rows[(size_t)n * pwords + (p >> 4)];
+            w = (w & ~(3u << (2 * (p & 15)))) | (v << (2 * (p & 15)));  // a read listed twice: the last entry counts
         }
     }
     return HSGPU_OK;
@@ -775,7 +810,7 @@ static int filter_set(hsgpu_pileup* p, int c0, int n, const hsgpu_partitions* pa
     hsgpu_ctx* ctx = p->ctx;
     const int nc = p->n_contigs;
     std::vector<FilterDesc> desc((size_t)nc);
-    int64_t pst_bytes = 0, pmask_words = 0;
+    int64_t row_words = 0;
     for (int c = 0; c < nc; c++) {
         FilterDesc& d = desc[c];
         memset(&d, 0, sizeof(d));
@@ -783,16 +818,13 @@ static int filter_set(hsgpu_pileup* p, int c0, int n, const hsgpu_partitions* pa
         if (!q || q->n_parts <= 0) continue;
         const int64_t R = p->h_contig_read_off[c + 1] - p->h_contig_read_off[c];
         d.n_parts = q->n_parts;
-        d.npad = (q->n_parts + 15) & ~15;
-        d.pwords = ((q->n_parts + 127) / 128) * 4;
-        d.pst_off = pst_bytes;
-        d.pmask_off = pmask_words;
-        pst_bytes += ((R * d.npad + 15) & ~(int64_t)15);
-        pmask_words += R * d.pwords;
+        d.pwords = ((q->n_parts + 127) / 128) * 8;
+        d.row_off = row_words;
+        row_words += R * d.pwords;
     }
     const size_t desc_bytes = sizeof(FilterDesc) * (size_t)nc;
-    const size_t desc_pad = (desc_bytes + 255) & ~(size_t)255, pst_pad = ((size_t)pst_bytes + 255) & ~(size_t)255;
-    const size_t total = desc_pad + pst_pad + (size_t)pmask_words * 4 + 256;
+    const size_t desc_pad = (desc_bytes + 255) & ~(size_t)255;
+    const size_t total = desc_pad + (size_t)row_words * 4 + 256;
     uint8_t* h = reinterpret_cast<uint8_t*>(hs_host_stage(ctx, total));
     if (!h) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu: pinned staging allocation failed");
     memcpy(h, desc.data(), desc_bytes);
@@ -802,8 +834,7 @@ static int filter_set(hsgpu_pileup* p, int c0, int n, const hsgpu_partitions* pa
         const FilterDesc& d = desc[c];
         if (d.n_parts <= 0) continue;
         const int64_t R = p->h_contig_read_off[c + 1] - p->h_contig_read_off[c];
-        const int rc = build_filter_rows(ctx, &parts[c - c0], R, d.npad, d.pwords, h + desc_pad + d.pst_off,
-                                         reinterpret_cast<uint32_t*>(h + desc_pad + pst_pad) + d.pmask_off);
+        const int rc = build_filter_rows(ctx, &parts[c - c0], R, d.pwords, reinterpret_cast<uint32_t*>(h + desc_pad) + d.row_off);
         if (rc) {
 #pragma omp critical
             rc_all = rc;
@@ -815,8 +846,7 @@ static int filter_set(hsgpu_pileup* p, int c0, int n, const hsgpu_partitions* pa
     HS_CUDA(ctx, cudaMemcpyAsync(p->d_filter_block, h, total, cudaMemcpyHostToDevice, ctx->stream));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging area is reused by the next call
     p->d_fdesc = p->d_filter_block;
-    p->d_pst_t = reinterpret_cast<uint8_t*>(p->d_filter_block) + desc_pad;
-    p->d_pmask = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p->d_filter_block) + desc_pad + pst_pad);
+    p->d_frows = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p->d_filter_block) + desc_pad);
     p->have_parts = true;
     return HSGPU_OK;
 }
@@ -831,7 +861,7 @@ static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t 
     if (!p->d_filter_work) {  // active list, kept flags, kept list, counters: allocated once per pileup
         HsCarve cv;
         cv.add(&p->d_factive, p->n_cols);
-        cv.add(&p->d_fkept, p->n_cols);
+        cv.add(&p->d_fkept, p->n_cols / 32 + 2);
         cv.add(&p->d_fkept_list, p->n_cols);
         cv.add(&p->d_fcounters, 8);
         cv.add(&p->d_fhdr, 2 * (int64_t)p->n_contigs + 2);
@@ -841,8 +871,7 @@ static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t 
     a.n_contigs = p->n_contigs;
     a.in_flag = in_flag;
     a.desc = reinterpret_cast<const FilterDesc*>(p->d_fdesc);
-    a.pst_t = p->d_pst_t;
-    a.pmask = p->d_pmask;
+    a.rows = p->d_frows;
     a.col_base = p->d_col_base;
     a.tile_base = p->d_tile_base;
     a.contig_read_off = p->d_contig_read_off;
@@ -853,6 +882,7 @@ static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t 
     a.row_base = p->d_row_base;
     a.codes = p->d_codes;
     a.k0 = p->d_k0;
+    a.k1 = p->d_k1;
     a.flags = p->d_flags;
     a.depth = p->d_depth;
     a.counts = p->d_counts;
@@ -863,7 +893,8 @@ static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t 
     a.counters = p->d_fcounters;
     a.kept = p->d_fkept;
     HS_CUDA(ctx, cudaMemsetAsync(p->d_fcounters, 0, 8 * sizeof(unsigned int), ctx->stream));
-    HS_KERNEL(ctx, "filter_active_kernel", filter_active_kernel<<<(unsigned)((ncols + 255) / 256), 256, 0, ctx->stream>>>(a));
+    HS_CUDA(ctx, cudaMemsetAsync(p->d_fkept + (g_begin >> 5), 0, sizeof(uint32_t) * (size_t)((g_end >> 5) - (g_begin >> 5) + 2), ctx->stream));
+    HS_KERNEL(ctx, "filter_active_kernel", filter_active_kernel<<<(unsigned)((ncols + 3 + 4 * 256 - 1) / (4 * 256) + 1), 256, 0, ctx->stream>>>(a));
     // persistent warps pull active columns from a counter (their cost varies with depth and partition count)
     HS_KERNEL(ctx, "robust_filter_kernel", robust_filter_kernel<<<ctx->sm_count * 8, 32 * RF_WARPS, 0, ctx->stream>>>(a));
     HS_KERNEL(ctx, "kept_scan_kernel", kept_scan_kernel<<<n, 1024, 0, ctx->stream>>>(c0, p->d_col_base, p->d_contig_len, p->d_fkept,
