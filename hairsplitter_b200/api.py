@@ -84,9 +84,29 @@ EXPORTS = [
     "hsgpu_partitions_set", "hsgpu_robust_filter_all", "hsgpu_pileup_info",
     "hsgpu_read_pair_counts", "hsgpu_pairs_create", "hsgpu_pairs_compute", "hsgpu_pairs_fetch", "hsgpu_pairs_info",
     "hsgpu_pairs_destroy", "hsgpu_graph_create", "hsgpu_graph_create_ex", "hsgpu_graph_build", "hsgpu_graph_adjacency", "hsgpu_graph_whispers",
-    "hsgpu_graph_destroy", "hsgpu_edlib_align_batch", "hsgpu_edlibAlign", "hsgpu_edlibFreeAlignResult",
+    "hsgpu_graph_destroy", "hsgpu_edlib_align_batch", "hsgpu_edlibAlign", "hsgpu_edlibFreeAlignResult", "hsgpu_clip_reads",
 ]
 PAIRS_DENSE, PAIRS_KEEP_ORDER, PAIRS_SIMT = 1, 2, 4
+CLIP_DTYPE = np.dtype([(k, np.int32) for k in ("status", "read_start", "read_end", "cigar_start", "cigar_end", "op_first",
+                                                "op_first_skip", "op_last", "op_last_take")])
+
+
+def clipped_cigar(ops, clip) -> str:
+    """the clipped CIGAR string of one hsgpu_clip result (what convert_cigar2 gives the reference, create_new_contigs.cpp:461)"""
+    runs = []
+    for k in range(int(clip["op_first"]), min(int(clip["op_last"]) + 1, len(ops))):
+        n, ty = int(ops[k]) >> 4, int(ops[k]) & 15
+        if k == int(clip["op_last"]):
+            n = int(clip["op_last_take"])
+        if k == int(clip["op_first"]):
+            n -= int(clip["op_first_skip"])
+        if n <= 0:
+            continue
+        if runs and runs[-1][1] == ty:
+            runs[-1][0] += n
+        else:
+            runs.append([n, ty])
+    return "".join(f"{n}{'MIDNSHP=X'[ty]}" for n, ty in runs)
 
 
 def load():
@@ -451,6 +471,20 @@ class Context:
                                                    second_base.ctypes.data, sim.ctypes.data, diff.ctypes.data),
                    "hsgpu_read_pair_counts")
         return sim, diff
+
+    # -- read clipping (modify_GFA) ------------------------------------------------------------
+    def clip_reads(self, cigar, cigar_off, pos_2_1, item_read, left, right):
+        """hsgpu_clip_reads -> structured array (status, read_start, read_end, cigar_start, cigar_end, op_first,
+        op_first_skip, op_last, op_last_take) per item"""
+        cigar, cigar_off = _a(cigar, np.uint32), _a(cigar_off, np.int64)
+        pos_2_1, item_read = _a(pos_2_1, np.int32), _a(item_read, np.int64)
+        left, right = _a(left, np.int32), _a(right, np.int32)
+        out = np.zeros(item_read.size, dtype=CLIP_DTYPE)
+        f = self.lib.hsgpu_clip_reads
+        f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.check(f(self.h, pos_2_1.size, cigar.ctypes.data, cigar_off.ctypes.data, pos_2_1.ctypes.data, item_read.size,
+                     item_read.ctypes.data, left.ctypes.data, right.ctypes.data, out.ctypes.data), "hsgpu_clip_reads")
+        return out
 
     # -- edlib ---------------------------------------------------------------------------------
     def edlib_align_batch(self, queries, targets, k=-1, mode=2, task=2):

@@ -268,6 +268,30 @@ int hsgpu_graph_whispers(hsgpu_graph* g, int64_t n_runs, const int32_t* run_wind
                          int32_t n_orders, const int32_t* order_rank, int32_t* labels_out);
 void hsgpu_graph_destroy(hsgpu_graph* g);
 
+/* ---- read clipping / window extraction of modify_GFA (src/create_new_contigs.cpp:383-447) ----------------------
+ * For every window (interval) of a contig and every read with a cluster in it, the reference walks the read's
+ * expanded CIGAR from its first character to find the part of the read (posOnReadStart/End) and of the CIGAR
+ * (posOnCIGARStart/End) lying on [leftToPolish, rightToPolish] of the contig, then hands
+ * seq.substr(read_start, read_end - read_start) and convert_cigar2(cigar.substr(cigar_start, cigar_end - cigar_start))
+ * to the polisher (:449-461). hsgpu_clip_reads does the walks of a batch of (read, interval) items on the GPU.
+ * CIGARs are BAM ops (len << 4 | index in "MIDNSHP=X") of n_reads alignments, concatenated, read r = ops
+ * [cigar_off[r], cigar_off[r+1]); pos_2_1[r] = Overlap.position_2_1. Item i clips read item_read[i] to
+ * [left_to_polish[i], right_to_polish[i]]. status -2 = the reference sets interval.second[r] = -2 ("within a
+ * deletion", :442-447) and skips the read; the other fields are then unspecified. The clipped CIGAR is returned as a
+ * range of the read's ops: op_first without its first op_first_skip characters, the ops up to op_last (exclusive),
+ * and the first op_last_take characters of op_last (op_last may equal the number of ops, with op_last_take 0);
+ * adjacent ops of the same letter merge into one, as convert_cigar2 does. */
+typedef struct {
+    int32_t status;
+    int32_t read_start, read_end;
+    int32_t cigar_start, cigar_end;
+    int32_t op_first, op_first_skip;
+    int32_t op_last, op_last_take;
+} hsgpu_clip;
+int hsgpu_clip_reads(hsgpu_ctx* ctx, int64_t n_reads, const uint32_t* cigar, const int64_t* cigar_off,
+                     const int32_t* pos_2_1, int64_t n_items, const int64_t* item_read, const int32_t* left_to_polish,
+                     const int32_t* right_to_polish, hsgpu_clip* out);
+
 /* ---- realignment: edlibAlign (src/edlib/include/edlib.h:146-271, src/edlib/src/edlib.cpp:142-297)
  * Batch of (query, target) pairs, results with edlib's exact field semantics. Modes/tasks use edlib's
  * numeric values: mode 0 NW, 1 SHW, 2 HW; task 0 DISTANCE, 1 LOC, 2 PATH. */

@@ -574,3 +574,61 @@ void hso_read_pair_counts(int32_t n_reads, int32_t n_snps, const int64_t* snp_of
         }
     }
 }
+
+/* ---- read clipping: the CIGAR walk of modify_GFA (src/create_new_contigs.cpp:392-447) -------------------------------
+ * One character of the expanded CIGAR at a time, as the reference does it. Only 'M', 'D' and 'I' move a cursor
+ * (:426-435); 'S' / 'H' advance the read cursor until the start has been found and end the walk afterwards
+ * (:407-415); every other letter ('=', 'X', 'N', 'P') is looked at by the two position tests and moves nothing. */
+int32_t hso_clip_read(const uint32_t* ops, int64_t n_ops, int32_t pos_2_1, int32_t left_to_polish, int32_t right_to_polish,
+                      int32_t* out) {
+    static const char letters[] = "MIDNSHP=X";
+    int posOnRead = 0, posOnCIGAR = 0;
+    int posOnInterval = pos_2_1;
+    int posOnReadStart = -1, posOnReadEnd = -1, posOnCIGARStart = -1, posOnCIGAREnd = -1;
+    int done = 0;
+    for (int64_t k = 0; k < n_ops && !done; k++) {
+        const char c = letters[ops[k] & 15u];
+        const uint32_t n = ops[k] >> 4;
+        for (uint32_t i = 0; i < n; i++) {
+            posOnCIGAR++;
+            if (c == 'S' || c == 'H') {
+                if (posOnReadStart != -1) {
+                    posOnReadEnd = posOnRead;
+                    posOnCIGAREnd = posOnCIGAR - 1;
+                    done = 1;
+                    break;
+                }
+                posOnRead++;
+                continue;
+            }
+            if (posOnReadStart == -1 && posOnInterval >= left_to_polish) {
+                posOnReadStart = posOnRead;
+                posOnCIGARStart = posOnCIGAR - 1;
+            }
+            if (posOnReadEnd == -1 && posOnInterval == right_to_polish) {
+                posOnReadEnd = posOnRead;
+                posOnCIGAREnd = posOnCIGAR - 1;
+                done = 1;
+                break;
+            }
+            if (c == 'M') {
+                posOnRead++;
+                posOnInterval++;
+            } else if (c == 'D') {
+                posOnInterval++;
+            } else if (c == 'I') {
+                posOnRead++;
+            }
+        }
+    }
+    if (posOnReadEnd == -1) {
+        posOnReadEnd = posOnRead;
+        posOnCIGAREnd = posOnCIGAR;
+    }
+    out[0] = posOnReadStart;
+    out[1] = posOnReadEnd;
+    out[2] = posOnCIGARStart;
+    out[3] = posOnCIGAREnd;
+    if (posOnReadStart > posOnReadEnd || posOnReadStart == -1) return -2;
+    return 0;
+}

@@ -85,6 +85,13 @@ void hso_read_pair_counts(int32_t n_reads, int32_t n_snps, const int64_t* snp_of
                           const uint8_t* code, const uint8_t* ref_base, const uint8_t* second_base,
                           int32_t* sim, int32_t* diff);
 
+/* Read clipping of modify_GFA (src/create_new_contigs.cpp:392-447): the part of a read and of its expanded CIGAR
+ * that lies on the contig interval [left_to_polish, right_to_polish]. ops = BAM-encoded CIGAR (len << 4 | index in
+ * "MIDNSHP=X"), pos_2_1 = Overlap.position_2_1. out = {posOnReadStart, posOnReadEnd, posOnCIGARStart, posOnCIGAREnd}.
+ * Returns 0, or -2 when the reference marks the read "within a deletion" (interval.second[r] = -2). */
+int32_t hso_clip_read(const uint32_t* ops, int64_t n_ops, int32_t pos_2_1, int32_t left_to_polish, int32_t right_to_polish,
+                      int32_t* out);
+
 /* edlibAlign (src/edlib/src/edlib.cpp:142-297) restated as a full dynamic program (hs_oracle_edlib.c).
  * mode 0 NW / 1 SHW / 2 HW, task 0 DISTANCE / 1 LOC / 2 PATH, k < 0 = unbounded. Output arrays must hold
  * n+1 locations and m+n alignment bytes. Returns 0, or 2 when the path lies in edlib's Hirschberg regime

@@ -225,6 +225,16 @@ class Oracle:
           seeds.ctypes.data, out.ctypes.data)
         return out
 
+    def clip_read(self, ops, pos_2_1, left, right):
+        """the CIGAR walk of modify_GFA's read clipping -> (status, [posOnReadStart, posOnReadEnd, posOnCIGARStart, posOnCIGAREnd])"""
+        ops = _arr(ops, np.uint32)
+        out = np.zeros(4, np.int32)
+        f = self.lib.hso_clip_read
+        f.restype = C.c_int32
+        f.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        st = f(ops.ctypes.data, ops.size, int(pos_2_1), int(left), int(right), out.ctypes.data)
+        return int(st), out
+
     def edlib_align(self, query: bytes, target: bytes, k=-1, mode=2, task=2):
         m, n = len(query), len(target)
         ed = np.zeros(1, np.int32)
@@ -373,6 +383,37 @@ class RefSR:
 
 
 PIN_SEED = 20260117  # oracle/ref_pin_rng.cpp
+
+
+class RefClip:
+    """oracle/_ref/libhsref_clip.so: the reference's own read-clipping loop body (cut out of its source at build time)"""
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(HERE, "_ref", "libhsref_clip.so"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(HERE, "_ref", "libhsref_clip.so"))
+            L.hsref_clip_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+            L.hsref_clip_cigar.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
+            cls._lib = L
+        return cls._lib
+
+    @classmethod
+    def clip_read(cls, cigar: str, pos_2_1, left, right):
+        out = np.zeros(4, np.int32)
+        st = cls.lib().hsref_clip_read(cigar.encode(), int(pos_2_1), int(left), int(right), out.ctypes.data)
+        return int(st), out
+
+    @classmethod
+    def clip_cigar(cls, cigar: str, a, b) -> str:
+        buf = C.create_string_buffer(2 * len(cigar) + 64)
+        n = cls.lib().hsref_clip_cigar(cigar.encode(), int(a), int(b), buf, len(buf))
+        assert n >= 0
+        return buf.value.decode()
 
 
 def ref_available() -> bool:
