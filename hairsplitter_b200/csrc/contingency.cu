@@ -10,6 +10,7 @@
 //   pass 1  histogram of the column's codes over the partition's reads -> alternative allele = most
 //           frequent code different from ref_base, ties broken by robin_hood iteration order (rank.cuh);
 //   pass 2  the 2x2 table n11/n01/n10/n00 (+ solid variants) over reads with state +-1.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -265,8 +266,9 @@ struct FilterArgs {
     const HsRankLut* lut;
     int64_t g_begin, g_end;  // global column range handled by this call
     uint32_t* active;        // compacted global ids of the active columns
-    unsigned int* counters;  // [0] active columns, [1] work cursor of robust_filter_kernel, [2] kept columns (list
-                             // reservation), [4..5] / [6..7] 64-bit: cells of the active columns / state bytes read
+    unsigned int* counters;  // [0] active columns of ordinary depth (front of `active`), [1] their work cursor, [2] kept
+                             // columns (list reservation), [3] deep active columns (back of `active`), [5] their work
+                             // cursor, [8..9] / [10..11] 64-bit: cells of the active columns / states read
     uint32_t* kept;          // bitmap over the columns of the batch (bit g & 31 of word g >> 5), zeroed by the caller
 };
 
@@ -299,12 +301,25 @@ __global__ void __launch_bounds__(256) filter_active_kernel(FilterArgs a) {
             if (!act) act = a.counts[3 * g + 1] > 4u;
             if (act) act = a.desc[rf_contig_of(a.col_base, a.n_contigs, g)].n_parts > 0;  // :640-642: no partition, nothing kept
         }
-        const unsigned mk = __ballot_sync(0xffffffffu, act);
+        // columns of tiles with more than RF_CAP reads go to the back of the list (robust_filter_kernel<true>)
+        bool deep = false;
+        if (act) {
+            const int c = rf_contig_of(a.col_base, a.n_contigs, g);
+            const int64_t tile = a.tile_base[c] + (g - a.col_base[c]) / HS_TILE;
+            deep = a.tile_off[tile + 1] - a.tile_off[tile] > RF_CAP;
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, act && !deep), md = __ballot_sync(0xffffffffu, act && deep);
         if (mk) {
             unsigned base = 0;
             if (lane == 0) base = atomicAdd(a.counters, (unsigned)__popc(mk));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (act) a.active[base + __popc(mk & ((1u << lane) - 1u))] = (uint32_t)g;
+            if (act && !deep) a.active[base + __popc(mk & ((1u << lane) - 1u))] = (uint32_t)g;
+        }
+        if (md) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(a.counters + 3, (unsigned)__popc(md));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (act && deep) a.active[(a.g_end - a.g_begin) - 1 - (base + __popc(md & ((1u << lane) - 1u)))] = (uint32_t)g;
         }
     }
 }
@@ -358,14 +373,12 @@ __device__ __noinline__ int rf_select_alt_tied(const uint8_t* order, const uint3
     return ' ';
 }
 
-// One chunk of 32 cells of a column. Staged columns read the warp's shared arrays; a column too deep to be staged
-// (amplicons) is gathered again from the pileup -- the rare path, kept out of line so that the kernel stays small
-// (an earlier build of this kernel was bound by instruction fetch).
+// The lane's cell of chunk `lb` of a column's tile list (code 0 = the read does not cover the column)
 struct RfCell {
-    int code;   // 0 = no cell in this lane
+    int code;
     int32_t n;  // read index inside the contig
 };
-__device__ __noinline__ RfCell rf_gather_cell(const FilterArgs& a, int q, int64_t lb, int64_t l1, int64_t read0, int lane) {
+__device__ __forceinline__ RfCell rf_gather_cell(const FilterArgs& a, int q, int64_t lb, int64_t l1, int64_t read0, int lane) {
     RfCell c;
     c.code = 0;
     c.n = 0;
@@ -383,20 +396,31 @@ __device__ __noinline__ RfCell rf_gather_cell(const FilterArgs& a, int q, int64_
 __device__ __noinline__ float rf_chi_square(int n00, int n01, int n10, int n11) { return hs_chi_square(n00, n01, n10, n11); }
 
 // Several codes share the maximum of a (column, partition) pair: the reference's map iteration order decides
-// (:832-844). The order of first appearance among the partition's reads is rebuilt by lane 0 (rare path).
+// (:832-844). Lane 0 rebuilds the order of first appearance among the partition's reads -- from the staged cells and
+// state rows (s_code, s_row: word kw of every row, shift sh), or from the pileup for a column too deep to stage.
 __device__ __noinline__ int rf_tied_alt(const FilterArgs& a, const uint32_t* rows_c, int pwords, int p, int q, int64_t l0, int64_t l1,
-                                         int64_t read0, uint32_t* s_hist, int ref, int nref, int max2) {
+                                         int64_t read0, const uint8_t* s_code, const uint32_t* s_row, int ncell_staged,
+                                         uint32_t* s_hist, int ref, int nref, int max2) {
     uint8_t order[HS_NCODES + 1];
     int mo = 0;
-    for (int64_t l = l0; l < l1; l++) {
-        const int32_t r = a.tile_reads[l];
-        if (!(a.read_start[r] <= q && q < a.read_end[r])) continue;
-        const uint32_t w = rows_c[(int64_t)(r - read0) * pwords + (p >> 4)];
-        if (((w >> (2 * (p & 15))) & 3u) == 0) continue;
-        const int idx = a.codes[a.row_base[r] + q] - HS_CODE0;
+    auto see = [&](int code) {
+        const int idx = code - HS_CODE0;
         bool seen = false;
         for (int k = 0; k < mo; k++) seen |= order[k] == idx;
         if (!seen) order[mo++] = (uint8_t)idx;
+    };
+    const int kw = (p & 127) >> 4, sh = 2 * (p & 15);
+    if (ncell_staged >= 0) {
+        for (int i = 0; i < ncell_staged; i++)
+            if ((s_row[i * 9 + kw] >> sh) & 3u) see(s_code[i]);
+    } else {
+        for (int64_t l = l0; l < l1; l++) {
+            const int32_t r = a.tile_reads[l];
+            if (!(a.read_start[r] <= q && q < a.read_end[r])) continue;
+            const uint32_t w = rows_c[(int64_t)(r - read0) * pwords + (p >> 4)];
+            if (((w >> sh) & 3u) == 0) continue;
+            see(a.codes[a.row_base[r] + q]);
+        }
     }
     if (nref > 0) s_hist[ref - HS_CODE0] = (uint32_t)nref;
     const int alt = rf_select_alt_tied(order, s_hist, mo, ref, max2, a.lut);
@@ -404,15 +428,18 @@ __device__ __noinline__ int rf_tied_alt(const FilterArgs& a, const uint32_t* row
     return alt;
 }
 
-__global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterArgs a) {
-    __shared__ int32_t s_n_all[RF_WARPS][RF_CAP];
-    __shared__ uint8_t s_code_all[RF_WARPS][RF_CAP];
-    __shared__ __align__(16) uint32_t s_row_all[RF_WARPS][RF_CAP * 9];  // 8 state words per cell, rows padded to 9 words
+// DEEP = false: columns whose tile has at most RF_CAP reads (every ordinary depth): the cells' codes sit in four
+// registers per lane, their state rows in shared memory, and the chunk loops are unrolled. DEEP = true: amplicon-deep
+// columns, gathered again from the pileup for every partition. The two kinds come as the front and the back of the
+// active list (filter_active_kernel).
+template <bool DEEP, int MINB>
+__global__ void __launch_bounds__(32 * RF_WARPS, MINB) robust_filter_kernel(FilterArgs a) {
+    __shared__ uint8_t s_code_all[RF_WARPS][DEEP ? 4 : RF_CAP];
+    __shared__ __align__(16) uint32_t s_row_all[RF_WARPS][DEEP ? 4 : RF_CAP * 9];  // 8 state words per cell, rows padded to 9 words
     __shared__ uint32_t s_hist_all[RF_WARPS][HS_NCODES + 3];
     __shared__ uint8_t s_touched_all[RF_WARPS][HS_NCODES + 3];
     __shared__ int s_m_all[RF_WARPS];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int32_t* const s_n = s_n_all[wid];
     uint8_t* const s_code = s_code_all[wid];
     uint32_t* const s_row = s_row_all[wid];
     uint32_t* const s_hist = s_hist_all[wid];
@@ -422,13 +449,14 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterA
     for (int i = lane; i < HS_NCODES + 3; i += 32) s_hist[i] = 0;
     if (lane == 0) *s_m = 0;
     __syncwarp();
-    const unsigned n_active = a.counters[0];
+    const unsigned n_items = DEEP ? a.counters[3] : a.counters[0];
+    const int64_t n_cols_all = a.g_end - a.g_begin;
     for (;;) {
         unsigned item = 0;
-        if (lane == 0) item = atomicAdd(a.counters + 1, 1u);
+        if (lane == 0) item = atomicAdd(a.counters + (DEEP ? 5 : 1), 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= n_active) break;
-        const int64_t g = a.active[item];
+        if (item >= n_items) break;
+        const int64_t g = DEEP ? a.active[n_cols_all - 1 - item] : a.active[item];
         const int c = rf_contig_of(a.col_base, a.n_contigs, g);
         const FilterDesc d = a.desc[c];
         const int q = (int)(g - a.col_base[c]);
@@ -446,55 +474,79 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterA
         // reference's comparison, :838: those columns take the general path.)
         const bool single = !inlist && ref < 128 && a.counts[3 * g + 2] <= 4u;
         const int k1 = a.k1[g];
-        // ---- the column's cells, in ascending read order ----
+        // ---- the column's cells, in ascending read order: compacted, slot 32 * ch + lane (not DEEP) ----
+        constexpr int NCH = DEEP ? 1 : RF_CAP / 32;
+        int code4[NCH];
+        int32_t n4[NCH];
         int ncell = 0;
-        for (int64_t lb = l0; lb < l1; lb += 32) {
-            const RfCell cl = rf_gather_cell(a, q, lb, l1, read0, lane);
-            const unsigned mk = __ballot_sync(0xffffffffu, cl.code != 0);
-            const int o = ncell + __popc(mk & lt);
-            if (cl.code != 0 && o < RF_CAP) {
-                s_n[o] = cl.n;
-                s_code[o] = (uint8_t)cl.code;
+        if (!DEEP) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) { code4[ch] = 0; n4[ch] = 0; }
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+                if (l0 + 32 * ch < l1) {
+                    const RfCell cl = rf_gather_cell(a, q, l0 + 32 * ch, l1, read0, lane);
+                    const unsigned mk = __ballot_sync(0xffffffffu, cl.code != 0);
+                    const int o = ncell + __popc(mk & lt);
+                    // compaction through shuffles would need a variable source lane per slot: two staging bytes instead
+                    if (cl.code != 0) {
+                        s_code[o] = (uint8_t)cl.code;
+                        s_row[o * 9 + 8] = (uint32_t)cl.n;  // the pad word of the row carries the read index until staged
+                    }
+                    ncell += __popc(mk);
+                }
             }
-            ncell += __popc(mk);
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+                const int slot = 32 * ch + lane;
+                if (slot < ncell) {
+                    code4[ch] = s_code[slot];
+                    n4[ch] = (int32_t)s_row[slot * 9 + 8];
+                }
+            }
         }
-        const bool staged = ncell <= RF_CAP;
-        const int nchunk = staged ? (ncell + 31) >> 5 : (int)((l1 - l0 + 31) >> 5);
-        __syncwarp();
-        // chunk ch of the column: the lane's cell (code 0 = none) and its slot in the staged arrays (-1 = not staged)
-#define RF_CELL(ch, cl, slot)                                                                     \
-    RfCell cl;                                                                                     \
-    int slot = -1;                                                                                 \
-    if (staged) {                                                                                  \
-        slot = 32 * (ch) + lane;                                                                   \
-        const bool v_ = slot < ncell;                                                              \
-        cl.code = v_ ? (int)s_code[slot] : 0;                                                      \
-        cl.n = v_ ? s_n[slot] : 0;                                                                 \
-        if (!v_) slot = -1;                                                                        \
-    } else {                                                                                       \
-        cl = rf_gather_cell(a, q, l0 + 32 * (int64_t)(ch), l1, read0, lane);                        \
-    }
-        // state of the lane's cell in partition pb + pl (pl < 128) of the current block
-#define RF_STATE(cl, slot, pl)                                                                     \
-    ((cl).code == 0 ? 0                                                                            \
-                    : (int)((((slot) >= 0 ? s_row[(slot) * 9 + ((pl) >> 4)]                          \
-                                          : __ldg(rows_c + (int64_t)(cl).n * d.pwords + (pb >> 4) + ((pl) >> 4))) >> (2 * ((pl) & 15))) & 3u))
+        const int nchunk = DEEP ? (int)((l1 - l0 + 31) >> 5) : (ncell + 31) >> 5;
+        // ballots of the two codes the single-candidate path looks at (one per chunk, constant over the partitions)
+        unsigned refm[NCH], altm[NCH];
+        if (!DEEP) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+                refm[ch] = __ballot_sync(0xffffffffu, code4[ch] == ref);
+                altm[ch] = __ballot_sync(0xffffffffu, code4[ch] != 0 && code4[ch] == k1);
+            }
+        }
         bool keep = false;
         int n_visited = 0;  // partitions whose states were read
         for (int pb = 0; pb < d.n_parts && !keep; pb += 128) {
             // the cells' state rows of this block of 128 partitions; which partitions hold one of the column's reads
             uint32_t nz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 1
-            for (int ch = 0; ch < nchunk; ch++) {
-                RF_CELL(ch, cl, slot)
-                if (cl.code != 0) {
-                    const uint4* src = reinterpret_cast<const uint4*>(rows_c + (int64_t)cl.n * d.pwords + (pb >> 4));
-                    const uint4 x = __ldg(src), y = __ldg(src + 1);
-                    const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+            if (!DEEP) {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        nz[k] |= w[k];
-                        if (slot >= 0) s_row[slot * 9 + k] = w[k];
+                for (int ch = 0; ch < NCH; ch++) {
+                    if (code4[ch] != 0) {
+                        const int slot = 32 * ch + lane;
+                        const uint4* src = reinterpret_cast<const uint4*>(rows_c + (int64_t)n4[ch] * d.pwords + (pb >> 4));
+                        const uint4 x = __ldg(src), y = __ldg(src + 1);
+                        const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            nz[k] |= w[k];
+                            s_row[slot * 9 + k] = w[k];
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int ch = 0; ch < nchunk; ch++) {
+                    const RfCell cl = rf_gather_cell(a, q, l0 + 32 * (int64_t)ch, l1, read0, lane);
+                    if (ch == 0) ncell = 0;
+                    ncell += __popc(__ballot_sync(0xffffffffu, cl.code != 0));
+                    if (cl.code != 0) {
+                        const uint4* src = reinterpret_cast<const uint4*>(rows_c + (int64_t)cl.n * d.pwords + (pb >> 4));
+                        const uint4 x = __ldg(src), y = __ldg(src + 1);
+                        nz[0] |= x.x; nz[1] |= x.y; nz[2] |= x.z; nz[3] |= x.w;
+                        nz[4] |= y.x; nz[5] |= y.y; nz[6] |= y.z; nz[7] |= y.w;
                     }
                 }
             }
@@ -507,28 +559,67 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterA
 #pragma unroll 1
             for (int k = 0; k < 8 && !keep; k++) {
                 uint32_t bits = nz[k];
+                if (!bits) continue;
+                // word k of the cells' state rows: the states of partitions 16k .. 16k+15 of this block
+                uint32_t wr[NCH];
+                if (!DEEP) {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ch++) wr[ch] = code4[ch] != 0 ? s_row[(32 * ch + lane) * 9 + k] : 0u;
+                }
 #pragma unroll 1
                 while (bits && !keep) {
                     const int pl = 16 * k + ((__ffs(bits) - 1) >> 1);
+                    const int sh = 2 * (pl & 15);
                     bits &= bits - 1;
                     n_visited++;
+                    // the lane's cell of chunk ch and its state in this partition
+#define RF_EACH_CHUNK(...)                                                                           \
+    if (!DEEP) {                                                                                      \
+        _Pragma("unroll") for (int ch = 0; ch < NCH; ch++) {                                          \
+            if (32 * ch < ncell) {                                                                    \
+                const int code = code4[ch];                                                           \
+                const int sg = (int)((wr[ch] >> sh) & 3u);                                            \
+                __VA_ARGS__                                                                           \
+            }                                                                                         \
+        }                                                                                             \
+    } else {                                                                                          \
+        _Pragma("unroll 1") for (int ch = 0; ch < nchunk; ch++) {                                     \
+            const RfCell cl_ = rf_gather_cell(a, q, l0 + 32 * (int64_t)ch, l1, read0, lane);           \
+            const int code = cl_.code;                                                                \
+            const int sg = code == 0 ? 0 : (int)((__ldg(rows_c + (int64_t)cl_.n * d.pwords + ((pb + pl) >> 4)) >> sh) & 3u); \
+            __VA_ARGS__                                                                               \
+        }                                                                                             \
+    }
                     int n00 = 0, n01 = 0, n10 = 0, n11 = 0;
                     bool table = false;
                     if (single) {
                         int cnt1 = 0;
-#pragma unroll 1
-                        for (int ch = 0; ch < nchunk; ch++) {
-                            RF_CELL(ch, cl, slot)
-                            const int sg = RF_STATE(cl, slot, pl);
-                            const unsigned b1 = __ballot_sync(0xffffffffu, sg == 1), b2 = __ballot_sync(0xffffffffu, sg == 2);
-                            const unsigned b3 = __ballot_sync(0xffffffffu, sg == 3);
-                            const unsigned bref = __ballot_sync(0xffffffffu, cl.code == ref);
-                            const unsigned balt = __ballot_sync(0xffffffffu, cl.code == k1);
-                            n11 += __popc(b1 & bref);
-                            n01 += __popc(b2 & bref);
-                            n10 += __popc(b1 & balt);
-                            n00 += __popc(b2 & balt);
-                            cnt1 += __popc((b1 | b2 | b3) & balt);
+                        if (!DEEP) {
+#pragma unroll
+                            for (int ch = 0; ch < NCH; ch++) {
+                                if (32 * ch < ncell) {
+                                    const int sg = (int)((wr[ch] >> sh) & 3u);
+                                    const unsigned b1 = __ballot_sync(0xffffffffu, sg == 1), b2 = __ballot_sync(0xffffffffu, sg == 2);
+                                    const unsigned b3 = __ballot_sync(0xffffffffu, sg == 3);
+                                    n11 += __popc(b1 & refm[ch]);
+                                    n01 += __popc(b2 & refm[ch]);
+                                    n10 += __popc(b1 & altm[ch]);
+                                    n00 += __popc(b2 & altm[ch]);
+                                    cnt1 += __popc((b1 | b2 | b3) & altm[ch]);
+                                }
+                            }
+                        } else {
+                            RF_EACH_CHUNK({
+                                const unsigned b1 = __ballot_sync(0xffffffffu, sg == 1), b2 = __ballot_sync(0xffffffffu, sg == 2);
+                                const unsigned b3 = __ballot_sync(0xffffffffu, sg == 3);
+                                const unsigned bref = __ballot_sync(0xffffffffu, code == ref);
+                                const unsigned balt = __ballot_sync(0xffffffffu, code != 0 && code == k1);
+                                n11 += __popc(b1 & bref);
+                                n01 += __popc(b2 & bref);
+                                n10 += __popc(b1 & balt);
+                                n00 += __popc(b2 & balt);
+                                cnt1 += __popc((b1 | b2 | b3) & balt);
+                            })
                         }
                         table = cnt1 > 4;
                     } else {
@@ -536,21 +627,17 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterA
                         // with ballots (its rows with state +1 / -1 are n11 / n01, :893-949), every other code goes
                         // through the warp's histogram ----
                         int nb = 0, nref = 0;
-#pragma unroll 1
-                        for (int ch = 0; ch < nchunk; ch++) {
-                            RF_CELL(ch, cl, slot)
-                            const int sg = RF_STATE(cl, slot, pl);
+                        RF_EACH_CHUNK({
                             const bool act = sg != 0;
-                            const bool isref = act && cl.code == ref;
+                            const bool isref = act && code == ref;
                             nb += __popc(__ballot_sync(0xffffffffu, act));
                             nref += __popc(__ballot_sync(0xffffffffu, isref));
                             n11 += __popc(__ballot_sync(0xffffffffu, isref && sg == 1));
                             n01 += __popc(__ballot_sync(0xffffffffu, isref && sg == 2));
                             if (act && !isref) {
-                                if (atomicAdd(&s_hist[cl.code - HS_CODE0], 1u) == 0u)
-                                    s_touched[atomicAdd(s_m, 1)] = (uint8_t)(cl.code - HS_CODE0);
+                                if (atomicAdd(&s_hist[code - HS_CODE0], 1u) == 0u) s_touched[atomicAdd(s_m, 1)] = (uint8_t)(code - HS_CODE0);
                             }
-                        }
+                        })
                         __syncwarp();
                         const int m = *s_m;  // distinct codes other than ref_base
                         int maxc = -1;
@@ -576,19 +663,19 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterA
                                     alt = cand;
                                 } else {
                                     int alt0 = ' ';
-                                    if (lane == 0) alt0 = rf_tied_alt(a, rows_c, d.pwords, pb + pl, q, l0, l1, read0, s_hist, ref, nref, max2);
+                                    if (lane == 0)
+                                        alt0 = rf_tied_alt(a, rows_c, d.pwords, pb + pl, q, l0, l1, read0, s_code, s_row, DEEP ? -1 : ncell,
+                                                           s_hist, ref, nref, max2);
                                     alt = __shfl_sync(0xffffffffu, alt0, 0);
                                 }
                             }
                             // ---- pass 2: n10 / n00 ----
                             if (alt != ref && alt != ' ') {
-#pragma unroll 1
-                                for (int ch = 0; ch < nchunk; ch++) {
-                                    RF_CELL(ch, cl, slot)
-                                    const int sg = cl.code == alt ? RF_STATE(cl, slot, pl) : 0;
-                                    n10 += __popc(__ballot_sync(0xffffffffu, sg == 1));
-                                    n00 += __popc(__ballot_sync(0xffffffffu, sg == 2));
-                                }
+                                RF_EACH_CHUNK({
+                                    const int s2 = code == alt ? sg : 0;
+                                    n10 += __popc(__ballot_sync(0xffffffffu, s2 == 1));
+                                    n00 += __popc(__ballot_sync(0xffffffffu, s2 == 2));
+                                })
                             }
                             table = true;
                         }
@@ -597,6 +684,7 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterA
                         if (lane == 0) *s_m = 0;
                         __syncwarp();
                     }
+#undef RF_EACH_CHUNK
                     if (table) {
                         // loop 3 (:721-738): columns of snps_in; loop 4 (:745-764): rescue of every other column (also
                         // of suspects that failed loop 3). The chi-square is only evaluated where an integer
@@ -612,12 +700,10 @@ __global__ void __launch_bounds__(32 * RF_WARPS, 4) robust_filter_kernel(FilterA
             }
             __syncwarp();
         }
-#undef RF_CELL
-#undef RF_STATE
         if (lane == 0) {
             if (keep) atomicOr(a.kept + (g >> 5), 1u << (g & 31));
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 4), (unsigned long long)ncell);
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 6), (unsigned long long)ncell * (unsigned)n_visited);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 8), (unsigned long long)ncell);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 10), (unsigned long long)ncell * (unsigned)n_visited);
         }
     }
 }
@@ -863,7 +949,7 @@ static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t 
         cv.add(&p->d_factive, p->n_cols);
         cv.add(&p->d_fkept, p->n_cols / 32 + 2);
         cv.add(&p->d_fkept_list, p->n_cols);
-        cv.add(&p->d_fcounters, 8);
+        cv.add(&p->d_fcounters, 12);
         cv.add(&p->d_fhdr, 2 * (int64_t)p->n_contigs + 2);
         HS_CUDA(ctx, cv.alloc(ctx, &p->d_filter_work));
     }
@@ -892,11 +978,23 @@ static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t 
     a.active = p->d_factive;
     a.counters = p->d_fcounters;
     a.kept = p->d_fkept;
-    HS_CUDA(ctx, cudaMemsetAsync(p->d_fcounters, 0, 8 * sizeof(unsigned int), ctx->stream));
+    HS_CUDA(ctx, cudaMemsetAsync(p->d_fcounters, 0, 12 * sizeof(unsigned int), ctx->stream));
     HS_CUDA(ctx, cudaMemsetAsync(p->d_fkept + (g_begin >> 5), 0, sizeof(uint32_t) * (size_t)((g_end >> 5) - (g_begin >> 5) + 2), ctx->stream));
     HS_KERNEL(ctx, "filter_active_kernel", filter_active_kernel<<<(unsigned)((ncols + 3 + 4 * 256 - 1) / (4 * 256) + 1), 256, 0, ctx->stream>>>(a));
     // persistent warps pull active columns from a counter (their cost varies with depth and partition count)
-    HS_KERNEL(ctx, "robust_filter_kernel", robust_filter_kernel<<<ctx->sm_count * 8, 32 * RF_WARPS, 0, ctx->stream>>>(a));
+    // HSGPU_FILTER_OCC=3: the build with 3 CTAs per SM (more registers, no spills) instead of 4, for A/B measurements
+    static const bool occ3 = getenv("HSGPU_FILTER_OCC") && atoi(getenv("HSGPU_FILTER_OCC")) == 3;
+    if (occ3)
+        HS_KERNEL(ctx, "robust_filter_kernel", robust_filter_kernel<false, 3><<<ctx->sm_count * 3, 32 * RF_WARPS, 0, ctx->stream>>>(a));
+    else
+        HS_KERNEL(ctx, "robust_filter_kernel", robust_filter_kernel<false, 4><<<ctx->sm_count * 4, 32 * RF_WARPS, 0, ctx->stream>>>(a));
+    // amplicon-deep columns (tiles with more than RF_CAP reads): only when the batch has such a tile
+    {
+        const int rc_max = hs_resolve_max_tile_reads(p);
+        if (rc_max) return rc_max;
+    }
+    if (p->max_tile_reads > RF_CAP)
+        HS_KERNEL(ctx, "robust_filter_kernel<deep>", robust_filter_kernel<true, 4><<<ctx->sm_count * 4, 32 * RF_WARPS, 0, ctx->stream>>>(a));
     HS_KERNEL(ctx, "kept_scan_kernel", kept_scan_kernel<<<n, 1024, 0, ctx->stream>>>(c0, p->d_col_base, p->d_contig_len, p->d_fkept,
                                                                                      p->d_fcounters + 2, p->n_cols, p->d_fkept_list, p->d_fhdr));
     int64_t* h_hdr = reinterpret_cast<int64_t*>(hs_host_stage(ctx, sizeof(int64_t) * (size_t)(2 * n)));
@@ -933,12 +1031,12 @@ int hsgpu_pileup_info(hsgpu_pileup* p, int64_t* info) {
     info[2] = p->built ? p->tile_entries : 0;
     info[3] = p->built ? p->n_irregular : 0;
     if (p->d_filter_work) {
-        unsigned int c[8];
+        unsigned int c[12];
         HS_CUDA(ctx, cudaMemcpyAsync(c, p->d_fcounters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
         HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        info[4] = c[0];
-        info[5] = (int64_t)c[4] | ((int64_t)c[5] << 32);
-        info[6] = (int64_t)c[6] | ((int64_t)c[7] << 32);
+        info[4] = (int64_t)c[0] + c[3];
+        info[5] = (int64_t)c[8] | ((int64_t)c[9] << 32);
+        info[6] = (int64_t)c[10] | ((int64_t)c[11] << 32);
         info[7] = c[2];
     }
     return HSGPU_OK;

@@ -17,6 +17,12 @@
 #include <sstream>
 #include <stdexcept>
 
+#include <fcntl.h>
+#include <omp.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 namespace hs {
 
 // ---- .col parser (src/separate_reads.cpp:46-190) ---------------------------------------------------------------
@@ -26,7 +32,7 @@ namespace {
 struct Fields {
     const char* p;
     const char* end;
-    explicit Fields(const std::string& s) : p(s.data()), end(s.data() + s.size()) {}
+    Fields(const char* b, const char* e) : p(b), end(e) {}
     bool next(const char*& b, const char*& e) {
         while (p < end && std::isspace((unsigned char)*p)) p++;
         if (p >= end) return false;
@@ -43,41 +49,57 @@ struct Fields {
 
 int stoi_or_throw(const std::string& s) { return std::stoi(s); }
 
-}  // namespace
+// a token of 1..9 decimal digits (what the writer emits): parsed in place; anything else goes through the
+// library call the reference uses (std::stoi / atoi semantics on signs, blanks, junk, overflow)
+inline bool small_uint(const char* b, const char* e, int& v) {
+    const size_t n = (size_t)(e - b);
+    if (n == 0 || n > 9) return false;
+    int x = 0;
+    for (const char* q = b; q < e; q++) {
+        const unsigned d = (unsigned)(*q - '0');
+        if (d > 9) return false;
+        x = x * 10 + (int)d;
+    }
+    v = x;
+    return true;
+}
 
-void parse_column_file(const std::string& path, std::vector<ColContig>& contigs, int max_coverage,
-                       float rarest_strain_abundance) {
-    std::ifstream in(path);
-    std::string line;
-    bool numbers = false, first_snp_line = true;
-    std::vector<int> read_idxs;
-    std::vector<int> codes;
-    while (std::getline(in, line)) {
-        Fields f(line);
-        const char *b, *e;
-        if (!f.next(b, e)) continue;
-        const size_t tl = (size_t)(e - b);
-        if (tl == 6 && !std::memcmp(b, "CONTIG", 6)) {
-            contigs.emplace_back();
-            ColContig& c = contigs.back();
-            c.line = line;
+// the lines of one CONTIG block [b, e) (its CONTIG line first); same line-by-line behaviour as the sequential
+// loop of parse_column_file (:62-186)
+void parse_col_block(const char* b, const char* e, bool numbers, int max_coverage, float rarest_strain_abundance, ColContig& c) {
+    std::vector<int> read_idxs, codes;
+    bool have_contig = false;
+    for (const char* ls = b; ls < e;) {
+        const char* le = (const char*)std::memchr(ls, '\n', (size_t)(e - ls));
+        if (!le) le = e;
+        Fields f(ls, le);
+        const char *tb, *te;
+        const char* line_b = ls;
+        const char* line_e = le;
+        ls = le + 1;
+        if (!f.next(tb, te)) continue;
+        const size_t tl = (size_t)(te - tb);
+        if (tl == 6 && !std::memcmp(tb, "CONTIG", 6)) {
+            have_contig = true;
+            c.line.assign(line_b, line_e);
             f.next_string();  // name
             c.length = std::atoi(f.next_string().c_str());
             const std::string cov = f.next_string();
             c.coverage = cov.empty() ? 0.0 : std::strtod(cov.c_str(), nullptr);
-        } else if (tl == 4 && !std::memcmp(b, "SNPS", 4)) {
-            if (contigs.empty()) continue;  // the reference would index snps[-1]
-            const std::string pos = f.next_string(), ref_s = f.next_string(), sec_s = f.next_string();
-            if (first_snp_line && !ref_s.empty() && !std::isalpha((unsigned char)ref_s[0]) && ref_s[0] != '-') numbers = true;
+        } else if (tl == 4 && !std::memcmp(tb, "SNPS", 4)) {
+            if (!have_contig) continue;  // the reference would index snps[-1]
+            const char *pb = nullptr, *pe = nullptr, *rb_ = nullptr, *re_ = nullptr, *sb_ = nullptr, *se_ = nullptr;
+            const bool hp = f.next(pb, pe), hr = f.next(rb_, re_), hs = f.next(sb_, se_);
+            const std::string pos = hp ? std::string(pb, pe) : std::string();
             uint8_t ref_base, second_base;
             if (numbers) {
-                ref_base = (uint8_t)(char)stoi_or_throw(ref_s);
-                second_base = (uint8_t)(char)stoi_or_throw(sec_s);
+                int v;
+                ref_base = (hr && small_uint(rb_, re_, v)) ? (uint8_t)(char)v : (uint8_t)(char)stoi_or_throw(hr ? std::string(rb_, re_) : std::string());
+                second_base = (hs && small_uint(sb_, se_, v)) ? (uint8_t)(char)v : (uint8_t)(char)stoi_or_throw(hs ? std::string(sb_, se_) : std::string());
             } else {
-                ref_base = (uint8_t)ref_s[0];
-                second_base = (uint8_t)sec_s[0];
+                ref_base = (uint8_t)(hr ? *rb_ : 0);
+                second_base = (uint8_t)(hs ? *sb_ : 0);
             }
-            first_snp_line = false;
             const char *ib = nullptr, *ie = nullptr, *cb = nullptr, *ce = nullptr;
             const bool have_idx = f.next(ib, ie);
             const bool have_content = f.next(cb, ce);
@@ -88,7 +110,9 @@ void parse_column_file(const std::string& path, std::vector<ColContig>& contigs,
                 for (const char* q = cb; q < ce; q++) {
                     if (*q != ',') continue;
                     if (numbers) {
-                        codes.push_back((int)(uint8_t)stoi_or_throw(std::string(t0, q)));
+                        int v;
+                        if (!small_uint(t0, q, v)) v = stoi_or_throw(std::string(t0, q));
+                        codes.push_back((int)(uint8_t)v);
                     } else {
                         for (const char* z = t0; z < q; z++) codes.push_back((int)(uint8_t)*z);
                     }
@@ -105,14 +129,19 @@ void parse_column_file(const std::string& path, std::vector<ColContig>& contigs,
                 const char* t0 = ib;
                 for (const char* q = ib; q < ie; q++) {
                     if (*q != ',') continue;
-                    read_idxs.push_back(std::atoi(std::string(t0, q).c_str()));
+                    int v;
+                    if (!small_uint(t0, q, v)) v = std::atoi(std::string(t0, q).c_str());
+                    read_idxs.push_back(v);
                     t0 = q + 1;
                 }
             }
             Column snp;
-            snp.pos = std::atoi(pos.c_str());
+            int pv;
+            snp.pos = small_uint(pos.data(), pos.data() + pos.size(), pv) ? pv : std::atoi(pos.c_str());
             snp.ref_base = ref_base;
             snp.second_base = second_base;
+            snp.content.reserve(codes.size());
+            snp.readIdxs.reserve(codes.size());
             int cov_maj = 0, cov_sec = 0, cov = 0;
             for (size_t n = 0; n < codes.size(); n++) {
                 const int idx = n < read_idxs.size() ? read_idxs[n] : 0;
@@ -124,11 +153,10 @@ void parse_column_file(const std::string& path, std::vector<ColContig>& contigs,
                 }
                 if (codes[n] != ' ' && idx >= 0) cov++;
             }
-            if ((float)cov_sec >= rarest_strain_abundance * (float)(cov_maj + cov_sec)) contigs.back().snps.push_back(std::move(snp));
-        } else if (tl == 4 && !std::memcmp(b, "READ", 4)) {
-            if (contigs.empty()) continue;
-            ColContig& c = contigs.back();
-            c.read_lines.push_back(line);
+            if ((float)cov_sec >= rarest_strain_abundance * (float)(cov_maj + cov_sec)) c.snps.push_back(std::move(snp));
+        } else if (tl == 4 && !std::memcmp(tb, "READ", 4)) {
+            if (!have_contig) continue;
+            c.read_lines.emplace_back(line_b, line_e);
             f.next_string();  // name
             f.next_string();  // start on the read
             f.next_string();  // end on the read
@@ -137,11 +165,87 @@ void parse_column_file(const std::string& path, std::vector<ColContig>& contigs,
                 c.limits.emplace_back(std::stoi(start_contig), std::stoi(end_contig));
             } catch (const std::invalid_argument&) {
                 std::cout << "error in parsing read limits" << std::endl;
-                std::cout << "line : " << line << std::endl;
+                std::cout << "line : " << std::string(line_b, line_e) << std::endl;
                 std::exit(1);
             }
         }
     }
+}
+
+}  // namespace
+
+// The reference reads the file line by line into one growing structure (:62-186). Here the file is mapped once, cut at
+// its CONTIG lines and the blocks are parsed in parallel: a CONTIG block only depends on the letters-or-numbers switch,
+// which the first SNPS line of the file sets (:93-103).
+void parse_column_file(const std::string& path, std::vector<ColContig>& contigs, int max_coverage,
+                       float rarest_strain_abundance) {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return;  // an unreadable file leaves no contigs, like the reference's failed ifstream
+    struct stat sb;
+    if (::fstat(fd, &sb) != 0 || sb.st_size == 0) {
+        ::close(fd);
+        return;
+    }
+    const size_t size = (size_t)sb.st_size;
+    void* map = ::mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (map == MAP_FAILED) {
+        std::cout << "ERROR: cannot map " << path << std::endl;
+        std::exit(1);
+    }
+    ::madvise(map, size, MADV_SEQUENTIAL);
+    const char* base = (const char*)map;
+    const char* end = base + size;
+    // block starts: lines whose first field is CONTIG. Found in parallel over slices of the file.
+    std::vector<const char*> starts;
+    {
+        const int nt = std::max(1, omp_get_max_threads());
+        std::vector<std::vector<const char*>> found((size_t)nt);
+#pragma omp parallel for schedule(static, 1)
+        for (int t = 0; t < nt; t++) {
+            const char* lo = base + size * (size_t)t / (size_t)nt;
+            const char* hi = base + size * (size_t)(t + 1) / (size_t)nt;
+            if (t > 0) {  // first line that starts inside the slice
+                const char* nl = (const char*)std::memchr(lo - 1, '\n', (size_t)(end - (lo - 1)));
+                lo = nl ? nl + 1 : end;
+            }
+            for (const char* ls = lo; ls < hi;) {
+                const char* le = (const char*)std::memchr(ls, '\n', (size_t)(end - ls));
+                if (!le) le = end;
+                Fields f(ls, le);
+                const char *tb, *te;
+                if (f.next(tb, te) && te - tb == 6 && !std::memcmp(tb, "CONTIG", 6)) found[t].push_back(ls);
+                ls = le + 1;
+            }
+        }
+        for (const auto& v : found) starts.insert(starts.end(), v.begin(), v.end());
+    }
+    if (starts.empty()) {
+        ::munmap(map, size);
+        return;
+    }
+    // letters or numbers: decided by the first SNPS line that follows a CONTIG line (:93-103)
+    bool numbers = false;
+    for (const char* ls = starts[0]; ls < end;) {
+        const char* le = (const char*)std::memchr(ls, '\n', (size_t)(end - ls));
+        if (!le) le = end;
+        Fields f(ls, le);
+        const char *tb, *te;
+        if (f.next(tb, te) && te - tb == 4 && !std::memcmp(tb, "SNPS", 4)) {
+            f.next_string();
+            const std::string ref_s = f.next_string();
+            numbers = !ref_s.empty() && !std::isalpha((unsigned char)ref_s[0]) && ref_s[0] != '-';
+            break;
+        }
+        ls = le + 1;
+    }
+    const size_t first = contigs.size();
+    contigs.resize(first + starts.size());
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t b = 0; b < starts.size(); b++)
+        parse_col_block(starts[b], b + 1 < starts.size() ? starts[b + 1] : end, numbers, max_coverage, rarest_strain_abundance,
+                        contigs[first + b]);
+    ::munmap(map, size);
 }
 
 // ---- shuffled sweep orders ----------------------------------------------------------------------------------------

@@ -9,5 +9,5 @@ tail -2 gpurun_out/${T}_smoke.log
 timeout 900 python bench.py --steps 10 --warmup 3 --no-stages > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?"
 tail -5 gpurun_out/${T}_bench.err
 python scripts/show_bench.py gpurun_out/${T}_bench.json 2>&1 | head -40
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"column_rank|robust_filter_kernel" -c 5 -o gpurun_out/${T}_prof -f python bench.py --steps 1 --warmup 1 --no-stages --wall-chunks -1 > gpurun_out/${T}_ncu.log 2>&1; echo "ncu rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"robust_filter_kernel" -c 1 -o gpurun_out/${T}_prof -f python bench.py --steps 1 --warmup 1 --no-stages --wall-chunks -1 > gpurun_out/${T}_ncu.log 2>&1; echo "ncu rc=$?"
 true
