@@ -78,7 +78,7 @@ __device__ __forceinline__ void write_column(const ColumnArgs& a, int64_t g, int
     a.counts[3 * g + 2] = c2;
     const bool cbd = central_base_differs(k0, k1);
     unsigned f = 0;
-    if (cbd) f |= HS_FLAG_RESCUE;
+    if (cbd) f |= HS_FLAG_RESCUE | (c1 > 4u ? HS_FLAG_ACTIVE : 0u);
     if ((int)c1 > mr && ((int)c1 > (int)c2 * 5 || mr == 2) && cbd) {
         f |= HS_FLAG_CANDIDATE;
         if ((float)(int)c1 > __fmul_rn(a.auto_threshold, (float)(int)c0)) f |= HS_FLAG_AUTO;  // :531

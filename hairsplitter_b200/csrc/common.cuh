@@ -254,3 +254,5 @@ int hs_resolve_max_tile_reads(hsgpu_pileup* p);
 #define HS_FLAG_AUTO 2       // c1 > u*c0 (:531)
 #define HS_FLAG_RESCUE 4     // rescue pre-filter of loop 4 (:751-752)
 #define HS_FLAG_SUSPECT 8    // candidate that also passed the spacing rule (:529)
+#define HS_FLAG_INLIST 16    // member of the caller's snps_in of hsgpu_robust_filter (set and cleared by that call)
+#define HS_FLAG_ACTIVE 32    // rescue candidate whose second code has more than 4 carriers: loop 4 can keep it (:745-764)

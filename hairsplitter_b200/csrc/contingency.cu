@@ -231,7 +231,6 @@ __global__ void __launch_bounds__(128) partition_tables_kernel(TablesArgs a) {
 // from one 128-bit presence row per read, and for every such partition the warp builds the reference's 2x2
 // table with ballots (the column's own majority code) and a small shared-memory histogram (everything else).
 // One launch covers all contigs of the batch; the work is proportional to the active columns, not to the tiles.
-#define HS_FLAG_INLIST 16
 #define RF_WARPS 8
 #define RF_CAP 128  // cells of a column staged per warp; deeper columns (amplicons) are re-gathered per partition
 
@@ -296,11 +295,8 @@ __global__ void __launch_bounds__(256) filter_active_kernel(FilterArgs a) {
         const int64_t g = g4 + k;
         const unsigned f = (f4 >> (8 * k)) & 0xffu;
         bool act = false;
-        if (g >= a.g_begin && g < a.g_end && (f & (a.in_flag | HS_FLAG_RESCUE))) {
-            act = (f & a.in_flag) != 0;
-            if (!act) act = a.counts[3 * g + 1] > 4u;
-            if (act) act = a.desc[rf_contig_of(a.col_base, a.n_contigs, g)].n_parts > 0;  // :640-642: no partition, nothing kept
-        }
+        if (g >= a.g_begin && g < a.g_end && (f & (a.in_flag | HS_FLAG_ACTIVE)))  // ACTIVE: rescue column with c1 > 4 (write_column)
+            act = a.desc[rf_contig_of(a.col_base, a.n_contigs, g)].n_parts > 0;  // :640-642: no partition, nothing kept
         // columns of tiles with more than RF_CAP reads go to the back of the list (robust_filter_kernel<true>)
         bool deep = false;
         if (act) {

@@ -89,7 +89,7 @@ static void fetch_columns(hsgpu_ctx* ctx, hsgpu_pileup* pu, int c, const std::ve
 
 // one batch of contigs on one GPU
 // (get_ctx waits for the context that is being created in the background: the reads are loaded and packed first)
-static void process_batch(const std::function<hsgpu_ctx*()>& get_ctx, const Store& st, const std::string& reads_path,
+static void process_batch(const std::function<hsgpu_ctx*()>& get_ctx, const Store& st, const MappedFile& reads_map,
                           const std::vector<int>& batch, float auto_threshold, std::vector<ContigResult>& results) {
     const int nc = (int)batch.size();
     std::vector<int32_t> contig_len(nc), read_len, read_start;
@@ -98,17 +98,16 @@ static void process_batch(const std::function<hsgpu_ctx*()>& get_ctx, const Stor
     std::vector<uint16_t> cigar;
     std::vector<uint8_t> read_strand;
     {
-        // the reads of every contig: sequence lines and CIGAR ops, contigs in parallel (each thread its own
-        // file handle), then one pass for the offsets, then the 2-bit packing in parallel again
-        std::vector<std::vector<std::string>> seqs(nc);
+        // the reads of every contig: views of their sequence lines in the mapped reads file (no copies) and CIGAR ops,
+        // contigs in parallel, then one pass for the offsets, then the 2-bit packing straight from the mapping
+        std::vector<std::vector<std::pair<const char*, size_t>>> seqs(nc);
         std::vector<std::vector<std::vector<uint16_t>>> ops(nc);
 #pragma omp parallel
         {
-            std::ifstream reads_file(reads_path);
 #pragma omp for schedule(dynamic, 1)
             for (int b = 0; b < nc; b++) {
                 const SeqRec& contig = st.seqs[st.contigs[batch[b]]];
-                load_read_sequences(reads_file, st, st.contigs[batch[b]], seqs[b]);
+                view_read_sequences(reads_map, st, st.contigs[batch[b]], seqs[b]);
                 ops[b].resize(contig.alns.size());
                 std::vector<uint32_t> wide;
                 for (size_t n = 0; n < contig.alns.size(); n++) {
@@ -124,8 +123,8 @@ static void process_batch(const std::function<hsgpu_ctx*()>& get_ctx, const Stor
             contig_word_off[b + 1] = contig_word_off[b] + ((int64_t)contig.sequence.size() + 15) / 16;
             for (size_t n = 0; n < contig.alns.size(); n++) {
                 const Alignment& a = st.alns[contig.alns[n]];
-                read_word_off.push_back(read_word_off.back() + ((int64_t)seqs[b][n].size() + 15) / 16);
-                read_len.push_back((int32_t)seqs[b][n].size());
+                read_word_off.push_back(read_word_off.back() + ((int64_t)seqs[b][n].second + 15) / 16);
+                read_len.push_back((int32_t)seqs[b][n].second);
                 cigar_off.push_back(cigar_off.back() + (int64_t)ops[b][n].size());
                 read_start.push_back(a.pos_2_1);
                 read_strand.push_back(a.strand ? 1 : 0);
@@ -141,7 +140,7 @@ static void process_batch(const std::function<hsgpu_ctx*()>& get_ctx, const Stor
             hsgpu_pack_bases_ascii(contig.sequence.data(), (int64_t)contig.sequence.size(), contig_bases.data() + contig_word_off[b]);
             for (size_t n = 0; n < contig.alns.size(); n++) {
                 const int64_t r = contig_read_off[b] + (int64_t)n;
-                hsgpu_pack_bases_ascii(seqs[b][n].data(), (int64_t)seqs[b][n].size(), read_bases.data() + read_word_off[r]);
+                hsgpu_pack_bases_ascii(seqs[b][n].first, (int64_t)seqs[b][n].second, read_bases.data() + read_word_off[r]);
                 std::copy(ops[b][n].begin(), ops[b][n].end(), cigar.begin() + cigar_off[r]);
             }
         }
@@ -298,6 +297,11 @@ int main(int argc, char* argv[]) {
     Store st;
     std::cout << " - Loading all reads from " << reads_file << " in memory\n";
     parse_reads(reads_file, st);
+    MappedFile reads_map;  // the sequences are packed straight from this mapping (process_batch)
+    if (!reads_map.open(reads_file)) {
+        std::cout << "problem reading files in index_reads, while trying to read " << reads_file << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
     phase("parse_reads");
     std::cout << " - Loading all contigs from " << gfa_file << " in memory\n";
     parse_assembly(gfa_file, st);
@@ -365,7 +369,7 @@ int main(int argc, char* argv[]) {
             batch.push_back(shard[g][i]);
             cells += weight[shard[g][i]];
             if (cells >= batch_cells || i + 1 == shard[g].size()) {
-                process_batch(get_ctx, st, reads_file, batch, auto_threshold, results);
+                process_batch(get_ctx, st, reads_map, batch, auto_threshold, results);
                 batch.clear();
                 cells = 0;
             }

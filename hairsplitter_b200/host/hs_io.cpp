@@ -1,5 +1,11 @@
 #include "hs_io.h"
 
+#include <fcntl.h>
+#include <omp.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -235,29 +241,73 @@ void parse_sam_line(const char* p, const char* end, const Store& st, bool amplic
 }
 }  // namespace
 
+bool MappedFile::open(const string& path) {
+    close();
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat sb;
+    if (::fstat(fd, &sb) != 0) {
+        ::close(fd);
+        return false;
+    }
+    size = (size_t)sb.st_size;
+    if (size > 0) {
+        void* m = ::mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) {
+            ::close(fd);
+            size = 0;
+            return false;
+        }
+        ::madvise(m, size, MADV_WILLNEED);
+        data = (const char*)m;
+    }
+    ::close(fd);
+    return true;
+}
+
+void MappedFile::close() {
+    if (data) ::munmap((void*)data, size);
+    data = nullptr;
+    size = 0;
+}
+
 void parse_sam(const string& path, Store& st, bool amplicon) {
-    std::ifstream in(path, std::ios::binary);
-    if (!in) {
+    MappedFile text;
+    if (!text.open(path)) {
         std::cout << "problem reading SAM file " << path << std::endl;
         throw std::invalid_argument("Input file '" + path + "' could not be read");
     }
-    string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
-    in.close();
-    // line starts
+    // line starts: found in parallel over slices of the mapping, concatenated in file order
     std::vector<size_t> starts;
-    for (size_t p = 0; p < text.size();) {
-        starts.push_back(p);
-        const void* nl = memchr(text.data() + p, '\n', text.size() - p);
-        p = nl ? (size_t)((const char*)nl - text.data()) + 1 : text.size();
+    {
+        const int nt = std::max(1, omp_get_max_threads());
+        std::vector<std::vector<size_t>> found((size_t)nt);
+#pragma omp parallel for schedule(static, 1)
+        for (int t = 0; t < nt; t++) {
+            size_t lo = text.size * (size_t)t / (size_t)nt, hi = text.size * (size_t)(t + 1) / (size_t)nt;
+            if (t > 0 && lo > 0) {  // first line that starts inside the slice
+                const void* nl = memchr(text.data + lo - 1, '\n', text.size - (lo - 1));
+                lo = nl ? (size_t)((const char*)nl - text.data) + 1 : text.size;
+            }
+            for (size_t p = lo; p < hi;) {
+                found[t].push_back(p);
+                const void* nl = memchr(text.data + p, '\n', text.size - p);
+                p = nl ? (size_t)((const char*)nl - text.data) + 1 : text.size;
+            }
+        }
+        size_t total = 0;
+        for (const auto& v : found) total += v.size();
+        starts.reserve(total + 1);
+        for (const auto& v : found) starts.insert(starts.end(), v.begin(), v.end());
     }
     const size_t n_lines = starts.size();
-    starts.push_back(text.size() + 1);  // as if the last line ended with a newline
+    starts.push_back(text.size + 1);  // as if the last line ended with a newline
     std::vector<SamRecord> recs(n_lines);
     std::vector<char> is_record(n_lines, 0);
 #pragma omp parallel for schedule(dynamic, 256)
     for (size_t i = 0; i < n_lines; i++) {
-        const char* p = text.data() + starts[i];
-        const char* end = text.data() + std::min(starts[i + 1] - 1, text.size());  // the newline (or the end)
+        const char* p = text.data + starts[i];
+        const char* end = text.data + std::min(starts[i + 1] - 1, text.size);  // the newline (or the end)
         if (p < end && *p == '@') continue;
         is_record[i] = 1;
         parse_sam_line(p, end, st, amplicon, recs[i]);
@@ -306,37 +356,96 @@ void load_read_sequences(std::ifstream& reads_file, const Store& st, int64_t con
     }
 }
 
+void view_read_sequences(const MappedFile& reads, const Store& st, int64_t contig,
+                         std::vector<std::pair<const char*, size_t>>& out) {
+    out.clear();
+    for (int64_t id : st.seqs[contig].alns) {
+        const Alignment& a = st.alns[id];
+        const int64_t read = (a.read != contig) ? a.read : a.contig;
+        // what seekg(file_pos) + getline returns: the bytes up to the next newline (or the end of the file)
+        const size_t at = (size_t)st.seqs[read].file_pos;
+        size_t len = 0;
+        if (at < reads.size) {
+            const void* nl = memchr(reads.data + at, '\n', reads.size - at);
+            len = nl ? (size_t)((const char*)nl - (reads.data + at)) : reads.size - at;
+        }
+        out.emplace_back(reads.data + std::min(at, reads.size), len);
+    }
+}
+
 // src/call_variants.cpp:1174-1213. Alleles are written as decimal integers, lists end with a comma, every
 // contig block ends with an empty line; the .vcf is reopened, which drops the header written earlier.
+// The text of every contig block is formatted in parallel (one buffer per contig), then written in the iteration
+// order of the container, like the reference's sequential loop.
+static inline void append_uint(string& s, unsigned v) {
+    char buf[12];
+    int n = 0;
+    do {
+        buf[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) s += buf[--n];
+}
+
 void write_outputs(const Store& st, const std::unordered_map<int, std::vector<Column>>& variants,
                    const string& col_file, const string& vcf_file) {
-    std::ofstream out(col_file);
-    std::ofstream vcf(vcf_file);
-    string idxs, bases;
-    for (const auto& kv : variants) {
-        const SeqRec& contig = st.seqs[kv.first];
-        out << "CONTIG\t" << contig.name << "\t" << contig.sequence.size() << "\t" << contig.depth << "\n";
+    std::vector<const std::pair<const int, std::vector<Column>>*> order;
+    for (const auto& kv : variants) order.push_back(&kv);
+    std::vector<string> col_text(order.size()), vcf_text(order.size());
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t i = 0; i < order.size(); i++) {
+        const SeqRec& contig = st.seqs[order[i]->first];
+        string& o = col_text[i];
+        string& v = vcf_text[i];
+        {
+            std::ostringstream head;  // the depth is a float printed with the stream's default formatting
+            head << "CONTIG\t" << contig.name << "\t" << contig.sequence.size() << "\t" << contig.depth << "\n";
+            o += head.str();
+        }
         for (int64_t id : contig.alns) {
             const Alignment& a = st.alns[id];
-            out << "READ\t" << st.seqs[a.read].name << "\t" << a.pos_1_1 << "\t" << a.pos_1_2 << "\t" << a.pos_2_1 << "\t"
-                << a.pos_2_2 << "\t" << a.strand << "\n";
+            std::ostringstream line;
+            line << "READ\t" << st.seqs[a.read].name << "\t" << a.pos_1_1 << "\t" << a.pos_1_2 << "\t" << a.pos_2_1 << "\t"
+                 << a.pos_2_2 << "\t" << a.strand << "\n";
+            o += line.str();
         }
-        for (const Column& c : kv.second) {
-            out << "SNPS\t" << c.pos << "\t" << (int)c.ref_base << "\t" << (int)c.second_base << "\t";
-            idxs.clear();
-            bases.clear();
+        for (const Column& c : order[i]->second) {
+            o += "SNPS\t";
+            o += std::to_string(c.pos);
+            o += '\t';
+            append_uint(o, (unsigned)(int)c.ref_base);
+            o += '\t';
+            append_uint(o, (unsigned)(int)c.second_base);
+            o += '\t';
             for (size_t r = 0; r < c.readIdxs.size(); r++) {
-                idxs += std::to_string(c.readIdxs[r]);
-                idxs += ',';
-                bases += std::to_string((int)c.content[r]);
-                bases += ',';
+                append_uint(o, (unsigned)c.readIdxs[r]);
+                o += ',';
             }
-            out << idxs << "\t" << bases << "\n";
-            vcf << contig.name << "\t" << c.pos << "\t.\t" << "ACGT-"[(c.ref_base - '!') % 5] << "\t"
-                << "ACGT-"[(c.second_base - '!') % 5] << "\t.\t.\tDP=" << c.readIdxs.size() << "\n";
+            o += '\t';
+            for (size_t r = 0; r < c.content.size() && r < c.readIdxs.size(); r++) {
+                append_uint(o, (unsigned)(int)c.content[r]);
+                o += ',';
+            }
+            o += '\n';
+            v += contig.name;
+            v += '\t';
+            v += std::to_string(c.pos);
+            v += "\t.\t";
+            v += "ACGT-"[(c.ref_base - '!') % 5];
+            v += '\t';
+            v += "ACGT-"[(c.second_base - '!') % 5];
+            v += "\t.\t.\tDP=";
+            v += std::to_string(c.readIdxs.size());
+            v += '\n';
         }
-        out << std::endl;
-        vcf << std::endl;
+        o += '\n';
+        v += '\n';
+    }
+    std::ofstream out(col_file, std::ios::binary);
+    std::ofstream vcf(vcf_file, std::ios::binary);
+    for (size_t i = 0; i < order.size(); i++) {
+        out.write(col_text[i].data(), (std::streamsize)col_text[i].size());
+        vcf.write(vcf_text[i].data(), (std::streamsize)vcf_text[i].size());
     }
 }
 

@@ -11,6 +11,16 @@
 
 namespace hs {
 
+// a whole file mapped read-only (ingestion through one mmap instead of seekg/getline per read,
+// src/input_output.cpp:546-569; the SAM text is parsed in place)
+struct MappedFile {
+    const char* data = nullptr;
+    size_t size = 0;
+    bool open(const std::string& path);  // false when the file cannot be opened; an empty file maps to size 0
+    void close();
+    ~MappedFile() { close(); }
+};
+
 void parse_reads(const std::string& path, Store& st);
 void parse_assembly(const std::string& path, Store& st);
 void parse_sam(const std::string& path, Store& st, bool amplicon);
@@ -19,6 +29,9 @@ void parse_sam(const std::string& path, Store& st, bool amplicon);
 void cigar_ops(const std::string& cigar, std::vector<uint32_t>& ops);
 // the sequence lines of the reads aligned on `contig`, in neighbour order (parse_reads_on_contig)
 void load_read_sequences(std::ifstream& reads_file, const Store& st, int64_t contig, std::vector<std::string>& out);
+// the same lines as views into the mapped reads file (no copies): (pointer, length) per aligned read
+void view_read_sequences(const MappedFile& reads, const Store& st, int64_t contig,
+                         std::vector<std::pair<const char*, size_t>>& out);
 // .col and .vcf, contigs in the iteration order of the reference's own container
 void write_outputs(const Store& st, const std::unordered_map<int, std::vector<Column>>& variants,
                    const std::string& col_file, const std::string& vcf_file);

@@ -205,7 +205,7 @@ void parse_column_file(const std::string& path, std::vector<ColContig>& contigs,
         for (int t = 0; t < nt; t++) {
             const char* lo = base + size * (size_t)t / (size_t)nt;
             const char* hi = base + size * (size_t)(t + 1) / (size_t)nt;
-            if (t > 0) {  // first line that starts inside the slice
+            if (t > 0 && lo > base) {  // first line that starts inside the slice
                 const char* nl = (const char*)std::memchr(lo - 1, '\n', (size_t)(end - (lo - 1)));
                 lo = nl ? nl + 1 : end;
             }
