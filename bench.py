@@ -779,7 +779,25 @@ def main():
             k["achieved_gbs"] = alg_bytes[name] / (ms / n * 1e-3) / 1e9
             k["frac_of_hbm_peak"] = k["achieved_gbs"] / hbm_peak
         kernels.append(k)
+    # the robust filter runs as two launches of one template (ordinary tiles, then tiles deeper than its shared-memory
+    # stage); the active cells are counted over both, so the pair is one roofline entry
+    fam = [k for k in kernels if k["name"].startswith("robust_filter_kernel")]
+    if len(fam) == 2:
+        ms_f = sum(k["ms_per_step"] for k in fam)
+        both = {"name": "robust_filter_kernel", "ms_per_step": ms_f, "launches_per_step": 2.0,
+                "alg_bytes_per_launch": alg_bytes["robust_filter_kernel"],
+                "achieved_gbs": alg_bytes["robust_filter_kernel"] / (ms_f * 1e-3) / 1e9}
+        for k in fam:
+            for key in ("alg_bytes_per_launch", "achieved_gbs", "frac_of_hbm_peak"):
+                k.pop(key, None)
+            k["note"] = "bytes are counted over both launches of the template: see roofline"
+    else:
+        both = None
     dom = kernels[0] if kernels else None
+    if both and dom and (dom in fam or both["ms_per_step"] > dom["ms_per_step"]):
+        dom = both
+    if dom and "achieved_gbs" not in dom:  # a helper kernel on top (tiny workloads): the largest kernel with a byte model
+        dom = next((k for k in kernels if "achieved_gbs" in k), None)
     roofline = None
     if dom and "achieved_gbs" in dom:
         tr = traffic.get(dom["name"])

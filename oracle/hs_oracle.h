@@ -94,8 +94,8 @@ int32_t hso_clip_read(const uint32_t* ops, int64_t n_ops, int32_t pos_2_1, int32
 
 /* edlibAlign (src/edlib/src/edlib.cpp:142-297) restated as a full dynamic program (hs_oracle_edlib.c).
  * mode 0 NW / 1 SHW / 2 HW, task 0 DISTANCE / 1 LOC / 2 PATH, k < 0 = unbounded. Output arrays must hold
- * n+1 locations and m+n alignment bytes. Returns 0, or 2 when the path lies in edlib's Hirschberg regime
- * (alignment then not produced; everything else is still filled). */
+ * n+1 locations and m+n alignment bytes. Returns edlib's status (0; 1 when its Hirschberg recursion finds no split row).
+ * Paths at or above edlib's 1 MiB switch follow obtainAlignmentHirschberg's split rule (:1236-1401). */
 int32_t hso_edlib_align(const char* query, int32_t m, const char* target, int32_t n, int32_t k, int32_t mode,
                         int32_t task, int32_t* edit_distance, int32_t* alphabet_length, int32_t* n_locations,
                         int32_t* end_locations, int32_t* start_locations, int32_t* alignment_length,

@@ -17,8 +17,14 @@
  *     start = e - p; for e == -1 start = 0. NW/SHW: 0.
  *   - path (:265-283, obtainAlignmentTraceback :947-1146): NW alignment of the query against
  *     target[start0..end0], traced back from the bottom-right cell with priority up (1 = insertion)
- *     > left (2 = deletion) > diagonal (0 match / 3 mismatch), then reversed. Only valid below edlib's
- *     1 MiB switch to Hirschberg (:1193-1195), which has its own tie rule; above it status = 2 here.
+ *     > left (2 = deletion) > diagonal (0 match / 3 mismatch), then reversed -- below edlib's 1 MiB switch
+ *     (:1193-1195). At or above it obtainAlignmentHirschberg (:1236-1401): the target is halved, the score columns of
+ *     the left half and of the reversed right half are compared, the FIRST query row (ascending) whose two scores
+ *     add up to the distance is the split row (:1312-1323), then the row "-1" boundary, then the last row
+ *     (:1325-1343); both parts recurse through obtainAlignment with their own scores and their own 1 MiB test.
+ *     edlib computes the columns inside its Ukkonen band; every cell on an optimal path lies inside both bands, so
+ *     the full-matrix columns used here give the same split (pinned against the vendored edlib by
+ *     tests/test_oracle_edlib.py on random pairs in that regime).
  *   - empty query or target: the special case of :162-180.
  */
 #include <stdlib.h>
@@ -67,6 +73,78 @@ static int semiglobal_positions(const int* row, int m, int n, int k, int clamp_k
     }
     *best_out = best;
     return np;
+}
+
+/* last column of the NW matrix: out[i] = D[i][n], i = 0..m (rev: both sequences read backwards) */
+static void nw_last_column(const unsigned char* q, int m, const unsigned char* t, int n, int rev, int* out) {
+    int* prev = (int*)malloc(sizeof(int) * (size_t)(m + 1));
+    int* cur = (int*)malloc(sizeof(int) * (size_t)(m + 1));
+    for (int i = 0; i <= m; i++) prev[i] = i;
+    for (int j = 1; j <= n; j++) {
+        unsigned char tc = rev ? t[n - j] : t[j - 1];
+        cur[0] = j;
+        for (int i = 1; i <= m; i++) {
+            unsigned char qc = rev ? q[m - i] : q[i - 1];
+            cur[i] = imin(prev[i - 1] + (qc != tc), imin(cur[i - 1], prev[i]) + 1);
+        }
+        int* tmp = prev; prev = cur; cur = tmp;
+    }
+    memcpy(out, prev, sizeof(int) * (size_t)(m + 1));
+    free(prev);
+    free(cur);
+}
+
+/* obtainAlignment (:1168-1230): NW path of q against t with known score `best`; ops appended in order at out.
+ * Returns 0, or 1 when no split row exists (edlib's EDLIB_STATUS_ERROR). */
+static int nw_path(const unsigned char* q, int m, const unsigned char* t, int n, int best, uint8_t* out, int* len_out) {
+    if (m == 0 || n == 0) { /* :1173-1180 */
+        for (int i = 0; i < m + n; i++) out[i] = m == 0 ? 2 : 1;
+        *len_out = m + n;
+        return 0;
+    }
+    const long long blocks = (m + 63) / 64;
+    if ((2ll * 8 + 4) * blocks * n + 2ll * 4 * n < 1024 * 1024) { /* traceback (:947-1146) */
+        int* D = (int*)malloc(sizeof(int) * (size_t)(m + 1) * (size_t)(n + 1));
+#define DD(i, j) D[(size_t)(i) * (n + 1) + (j)]
+        for (int j = 0; j <= n; j++) DD(0, j) = j;
+        for (int i = 1; i <= m; i++) {
+            DD(i, 0) = i;
+            for (int j = 1; j <= n; j++)
+                DD(i, j) = imin(DD(i - 1, j - 1) + (q[i - 1] != t[j - 1]), imin(DD(i - 1, j), DD(i, j - 1)) + 1);
+        }
+        int i = m, j = n, len = 0;
+        while (i > 0 || j > 0) {
+            if (i > 0 && DD(i - 1, j) + 1 == DD(i, j)) { out[len++] = 1; i--; }
+            else if (j > 0 && DD(i, j - 1) + 1 == DD(i, j)) { out[len++] = 2; j--; }
+            else { out[len++] = DD(i - 1, j - 1) == DD(i, j) ? 0 : 3; i--; j--; }
+        }
+        for (int a = 0, b = len - 1; a < b; a++, b--) { uint8_t x = out[a]; out[a] = out[b]; out[b] = x; }
+        *len_out = len;
+        free(D);
+#undef DD
+        return 0;
+    }
+    /* Hirschberg (:1236-1401) */
+    const int left_w = n / 2, right_w = n - left_w;
+    int* L = (int*)malloc(sizeof(int) * (size_t)(m + 1));
+    int* R = (int*)malloc(sizeof(int) * (size_t)(m + 1));
+    nw_last_column(q, m, t, left_w, 0, L);            /* L[i] = D[i][left_w]: scoresLeft[r] = L[r + 1] */
+    nw_last_column(q, m, t + left_w, right_w, 1, R);  /* R[i] = reversed D[i][right_w]: scoresRight[r] = R[m - r] */
+    int row = -2, left_score = -1, right_score = -1;
+    for (int r = 0; r <= m - 2; r++) { /* :1312-1323 */
+        if (L[r + 1] + R[m - (r + 1)] == best) { row = r; left_score = L[r + 1]; right_score = R[m - (r + 1)]; break; }
+    }
+    if (row == -2 && left_w + R[m] == best) { row = -1; left_score = left_w; right_score = R[m]; }           /* :1325-1333 */
+    if (row == -2 && L[m] + right_w == best) { row = m - 1; left_score = L[m]; right_score = right_w; }       /* :1334-1343 */
+    free(L);
+    free(R);
+    if (row == -2) { *len_out = 0; return 1; }
+    const int ul_h = row + 1;
+    int l1 = 0, l2 = 0;
+    int rc = nw_path(q, ul_h, t, left_w, left_score, out, &l1);
+    if (!rc) rc = nw_path(q + ul_h, m - ul_h, t + left_w, right_w, right_score, out + l1, &l2);
+    *len_out = l1 + l2;
+    return rc;
 }
 
 int32_t hso_edlib_align(const char* query, int32_t m, const char* target, int32_t n, int32_t k, int32_t mode,
@@ -127,35 +205,10 @@ int32_t hso_edlib_align(const char* query, int32_t m, const char* target, int32_
     int status = 0;
     if (task == 2) {
         const int s0 = start_locations[0], e0 = end_locations[0];
-        const unsigned char* at = t + s0;
         const int an = e0 - s0 + 1;
-        if (an <= 0) { /* obtainAlignment special case (:1173-1180) with an empty target */
-            for (int i = 0; i < m; i++) alignment[i] = 1;
-            *alignment_length = m;
-        } else {
-            const long long blocks = (m + 63) / 64;
-            if ((2ll * 8 + 4) * blocks * an + 2ll * 4 * an >= 1024 * 1024) status = 2; /* Hirschberg regime */
-            else {
-                int* D = (int*)malloc(sizeof(int) * (size_t)(m + 1) * (size_t)(an + 1));
-#define DD(i, j) D[(size_t)(i) * (an + 1) + (j)]
-                for (int j = 0; j <= an; j++) DD(0, j) = j;
-                for (int i = 1; i <= m; i++) {
-                    DD(i, 0) = i;
-                    for (int j = 1; j <= an; j++)
-                        DD(i, j) = imin(DD(i - 1, j - 1) + (q[i - 1] != at[j - 1]), imin(DD(i - 1, j), DD(i, j - 1)) + 1);
-                }
-                int i = m, j = an, len = 0;
-                while (i > 0 || j > 0) {
-                    if (i > 0 && DD(i - 1, j) + 1 == DD(i, j)) { alignment[len++] = 1; i--; }
-                    else if (j > 0 && DD(i, j - 1) + 1 == DD(i, j)) { alignment[len++] = 2; j--; }
-                    else { alignment[len++] = DD(i - 1, j - 1) == DD(i, j) ? 0 : 3; i--; j--; }
-                }
-                for (int a = 0, b = len - 1; a < b; a++, b--) { uint8_t x = alignment[a]; alignment[a] = alignment[b]; alignment[b] = x; }
-                *alignment_length = len;
-                free(D);
-#undef DD
-            }
-        }
+        int len = 0;
+        status = nw_path(q, m, t + s0, an < 0 ? 0 : an, best, alignment, &len);
+        *alignment_length = len;
     }
     free(row);
     free(pos);
