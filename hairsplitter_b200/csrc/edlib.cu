@@ -16,8 +16,15 @@
 //     "horizontal delta is +1" per cell, so the NW pass stores the two bit-vectors Pv and Ph per
 //     (block, column), 2 bits per cell, in a per-warp scratch slab laid out [block][column] so that the
 //     walk loads 32 consecutive columns of the block it is in with one coalesced request.
-//   Pairs whose path falls in edlib's Hirschberg regime ((20*blocks+8)*columns >= 1 MiB, :1193-1195) get
-//   status 2 and no alignment: Hirschberg picks the split row by its own tie rule, not implemented here.
+//   * paths at or above edlib's 1 MiB switch ((20*blocks+8)*columns >= 1 MiB, :1193-1195) follow
+//     obtainAlignmentHirschberg (:1236-1401): the target is halved, the last score column of the left half and of the
+//     reversed right half are rebuilt from the final Pv/Mv bit-vectors of each block, the first query row (ascending)
+//     where the two add up to the distance is the split, both parts go back on a per-warp stack (right part first,
+//     because the ops are produced back to front) until a part passes the 1 MiB test and is traced back as above.
+// Queries longer than 2048 (more than one block per lane) are swept in strips of 32 blocks: the horizontal deltas that
+// leave the bottom row of a strip are kept per column (one byte) and enter the next strip as its top row.
+// The batch kernels come in two instantiations: the ordinary one (queries up to 2048, paths below the switch; the
+// throughput path), and the LONG one that runs over a list of the remaining pairs -- launched only when there are any.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -26,7 +33,9 @@
 #include "common.cuh"
 
 #define ED_WARPS 4          // warps (pairs in flight) per CTA
-#define ED_MAXBLOCKS 32     // one 64-row block per lane -> queries up to 2048
+#define ED_MAXBLOCKS 32     // one 64-row block per lane -> queries up to 2048 in one strip
+#define ED_MAX_QUERY (1 << 20)
+#define ED_STACK 40         // Hirschberg parts waiting per warp (the target halves at every level)
 #define ED_SMEM_SYMS 8      // alphabets up to this size keep Peq in shared memory
 #define ED_TRACE_BYTES (52429ll * 16)  // per-warp traceback slab: blocks*columns < 2^20/20 entries of 16 B
 
@@ -47,12 +56,26 @@ struct EdArgs {
     uint64_t* peq_big;            // per resident warp: 256 * 32 words, for alphabets > ED_SMEM_SYMS
     uint8_t* trace;               // per resident warp: ED_TRACE_BYTES
     unsigned int* counter;        // dynamic pair scheduler
+    // LONG instantiations only
+    const int32_t* list;          // pairs to work on
+    int n_list;
+    uint8_t* hbuf;                // per warp: 2 * hbuf_stride bytes (horizontal deltas between strips, ping-pong)
+    int64_t hbuf_stride;
+    ulonglong2* colv;             // per warp: 2 * col_stride final (Pv, Mv) per block: left half, reversed right half
+    int* colpre;                  // per warp: 2 * (col_stride + 1) prefix sums of the blocks' vertical deltas
+    int64_t col_stride;
 };
 
 struct WarpCtx {
     uint64_t* peq;        // [sym][32]
     const uint8_t* lut;   // byte -> symbol
     int lane;
+    // strip mode (MULTI passes build Peq themselves, 32 blocks at a time)
+    const uint8_t* q;
+    bool qrev;
+    int n_sym;
+    uint8_t* hbuf;
+    int64_t hbuf_stride;
 };
 
 // symbol table of a pair: lut[byte] = rank of the byte among the bytes present (any consistent numbering
@@ -82,11 +105,11 @@ __device__ int build_alphabet(const uint8_t* q, int m, const uint8_t* t, int n, 
 
 // Peq[sym][block]: bit i of block b set iff query row 64*b+i carries sym (buildPeq :357-385; padding rows
 // stay 0 -- they never influence the real rows because carries only travel towards higher rows)
-__device__ void build_peq(const WarpCtx& w, const uint8_t* q, int m, int nb, int n_sym, bool reversed) {
+__device__ void build_peq(const WarpCtx& w, const uint8_t* q, int m, int nb, int n_sym, bool reversed, int row0 = 0) {
     for (int i = w.lane; i < n_sym * 32; i += 32) w.peq[i] = 0ull;
     __syncwarp();
     if (w.lane < nb) {
-        const int r0 = w.lane * 64;
+        const int r0 = row0 + w.lane * 64;
         const int r1 = min(m, r0 + 64);
         for (int r = r0; r < r1; r++) {
             const int c = reversed ? q[m - 1 - r] : q[r];
@@ -96,7 +119,7 @@ __device__ void build_peq(const WarpCtx& w, const uint8_t* q, int m, int nb, int
     __syncwarp();
 }
 
-enum { PASS_SEMIGLOBAL = 0, PASS_NW_SCORE = 1, PASS_REV_SHW = 2, PASS_NW_STORE = 3 };
+enum { PASS_SEMIGLOBAL = 0, PASS_NW_SCORE = 1, PASS_REV_SHW = 2, PASS_NW_STORE = 3, PASS_NW_COLUMN = 4 };
 
 struct PassOut {
     int best;       // minimum bottom-row score (semi-global) / D[m][n] (NW)
@@ -107,11 +130,13 @@ struct PassOut {
 
 // One sweep over the columns. tget(c) = target symbol index source: forward t[c], or t[rev_end - c].
 // start_hin: +1 when the top row is penalised (NW, SHW), 0 for HW. consider_j0: position -1 competes.
-template <int KIND>
-__device__ PassOut dp_pass(const WarpCtx& w, int m, int nb, const uint8_t* t, int n, int rev_end, int start_hin,
-                           bool consider_j0, unsigned int* bitmask, ulonglong2* trace) {
+// MULTI: any query length, in strips of 32 blocks (w.q / w.qrev / w.n_sym / w.hbuf set by the caller);
+// otherwise the caller has built Peq for the at most 32 blocks. PASS_NW_COLUMN leaves the vertical deltas of the last
+// column in colv[block] = (Pv, Mv).
+template <int KIND, bool MULTI>
+__device__ PassOut dp_pass(const WarpCtx& w, int m, int nb_total, const uint8_t* t, int n, int rev_end, int start_hin,
+                           bool consider_j0, unsigned int* bitmask, ulonglong2* trace, ulonglong2* colv = nullptr) {
     const int lane = w.lane;
-    uint64_t Pv = ~0ull, Mv = 0ull;
     const int lb = (m - 1) & 63;
     int score = m;  // D[m][0]
     PassOut o;
@@ -120,61 +145,85 @@ __device__ PassOut dp_pass(const WarpCtx& w, int m, int nb, const uint8_t* t, in
     o.last_j = 0;
     o.count = consider_j0 ? 1 : 0;
     unsigned int bits = consider_j0 ? 1u : 0u;  // bit (j & 31) of the word being assembled
-    int packed = 0;
-    int tchunk = 0;
-    const int steps = n + nb - 1;
-    for (int s = 0; s < steps; s++) {
-        if ((s & 31) == 0) {
-            const int idx = s + lane;
-            tchunk = 0;
-            if (idx < n) tchunk = w.lut[rev_end >= 0 ? t[rev_end - idx] : t[idx]];
+    const int n_strips = MULTI ? (nb_total + 31) >> 5 : 1;
+    for (int st = 0; st < n_strips; st++) {
+        const int nb = MULTI ? min(32, nb_total - st * 32) : nb_total;
+        const bool last = !MULTI || st == n_strips - 1;
+        const uint8_t* hsrc = nullptr;
+        uint8_t* hdst = nullptr;
+        if (MULTI) {
+            build_peq(w, w.q, m, nb, w.n_sym, w.qrev, st * 64 * 32);
+            hsrc = w.hbuf + (size_t)(st & 1) * w.hbuf_stride;
+            hdst = w.hbuf + (size_t)((st + 1) & 1) * w.hbuf_stride;
         }
-        const int sym0 = __shfl_sync(0xffffffffu, tchunk, s & 31);
-        const int pk = __shfl_up_sync(0xffffffffu, packed, 1);
-        const int sym = lane == 0 ? sym0 : (pk >> 2);
-        const int hin = lane == 0 ? start_hin : ((pk & 3) - 1);
-        const int c = s - lane;
-        if (lane < nb && c >= 0 && c < n) {
-            uint64_t Eq = w.peq[sym * 32 + lane];
-            const uint64_t hneg = hin < 0 ? 1ull : 0ull, hpos = hin > 0 ? 1ull : 0ull;
-            const uint64_t Xv = Eq | Mv;
-            Eq |= hneg;
-            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-            uint64_t Ph = Mv | ~(Xh | Pv);
-            uint64_t Mh = Pv & Xh;
-            const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
-            packed = (sym << 2) | (hout + 1);
-            if (lane == nb - 1) {
-                score += (int)((Ph >> lb) & 1ull) - (int)((Mh >> lb) & 1ull);
-                const int j = c + 1;
-                if (KIND == PASS_SEMIGLOBAL) {
-                    if ((j & 31) == 0) bits = 0;
-                    if (score < o.best) { o.best = score; o.first_j = j; o.count = 0; }
-                    if (score == o.best) { o.count++; o.last_j = j; bits |= 1u << (j & 31); }
-                    if ((j & 31) == 31 || j == n) bitmask[j >> 5] = bits;
-                } else if (KIND == PASS_REV_SHW) {
-                    if (score < o.best) { o.best = score; o.first_j = j; }
-                    if (score == o.best) o.last_j = j;
-                } else {
-                    o.best = score;  // NW: value after the last column is D[m][n]
-                }
+        uint64_t Pv = ~0ull, Mv = 0ull;
+        int packed = 0;
+        int tchunk = 0, hchunk = 0;
+        const int steps = n + nb - 1;
+        for (int s = 0; s < steps; s++) {
+            if ((s & 31) == 0) {
+                const int idx = s + lane;
+                tchunk = 0;
+                if (idx < n) tchunk = w.lut[rev_end >= 0 ? t[rev_end - idx] : t[idx]];
+                if (MULTI && st > 0) hchunk = idx < n ? hsrc[idx] : 1;
             }
-            const uint64_t Phs = (Ph << 1) | hpos;
-            const uint64_t Mhs = (Mh << 1) | hneg;
-            Pv = Mhs | ~(Xv | Phs);
-            Mv = Phs & Xv;
-            if (KIND == PASS_NW_STORE) trace[(size_t)lane * n + c] = make_ulonglong2(Pv, Ph);
+            const int sym0 = __shfl_sync(0xffffffffu, tchunk, s & 31);
+            int hin0 = start_hin;
+            if (MULTI && st > 0) hin0 = __shfl_sync(0xffffffffu, hchunk, s & 31) - 1;
+            const int pk = __shfl_up_sync(0xffffffffu, packed, 1);
+            const int sym = lane == 0 ? sym0 : (pk >> 2);
+            const int hin = lane == 0 ? hin0 : ((pk & 3) - 1);
+            const int c = s - lane;
+            if (lane < nb && c >= 0 && c < n) {
+                uint64_t Eq = w.peq[sym * 32 + lane];
+                const uint64_t hneg = hin < 0 ? 1ull : 0ull, hpos = hin > 0 ? 1ull : 0ull;
+                const uint64_t Xv = Eq | Mv;
+                Eq |= hneg;
+                const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                uint64_t Ph = Mv | ~(Xh | Pv);
+                uint64_t Mh = Pv & Xh;
+                const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+                packed = (sym << 2) | (hout + 1);
+                if (lane == nb - 1) {
+                    if (!last) {
+                        hdst[c] = (uint8_t)(hout + 1);
+                    } else {
+                        score += (int)((Ph >> lb) & 1ull) - (int)((Mh >> lb) & 1ull);
+                        const int j = c + 1;
+                        if (KIND == PASS_SEMIGLOBAL) {
+                            if ((j & 31) == 0) bits = 0;
+                            if (score < o.best) { o.best = score; o.first_j = j; o.count = 0; }
+                            if (score == o.best) { o.count++; o.last_j = j; bits |= 1u << (j & 31); }
+                            if ((j & 31) == 31 || j == n) bitmask[j >> 5] = bits;
+                        } else if (KIND == PASS_REV_SHW) {
+                            if (score < o.best) { o.best = score; o.first_j = j; }
+                            if (score == o.best) o.last_j = j;
+                        } else {
+                            o.best = score;  // NW: value after the last column is D[m][n]
+                        }
+                    }
+                }
+                const uint64_t Phs = (Ph << 1) | hpos;
+                const uint64_t Mhs = (Mh << 1) | hneg;
+                Pv = Mhs | ~(Xv | Phs);
+                Mv = Phs & Xv;
+                if (KIND == PASS_NW_STORE) trace[(size_t)(st * 32 + lane) * n + c] = make_ulonglong2(Pv, Ph);
+            }
         }
+        if (KIND == PASS_NW_COLUMN && lane < nb) colv[st * 32 + lane] = make_ulonglong2(Pv, Mv);
+        if (MULTI) __syncwarp();
     }
-    // results live in lane nb-1
-    o.best = __shfl_sync(0xffffffffu, o.best, nb - 1);
-    o.first_j = __shfl_sync(0xffffffffu, o.first_j, nb - 1);
-    o.last_j = __shfl_sync(0xffffffffu, o.last_j, nb - 1);
-    o.count = __shfl_sync(0xffffffffu, o.count, nb - 1);
+    // results live in the lane of the last block
+    const int rl = (nb_total - 1) & 31;
+    o.best = __shfl_sync(0xffffffffu, o.best, rl);
+    o.first_j = __shfl_sync(0xffffffffu, o.first_j, rl);
+    o.last_j = __shfl_sync(0xffffffffu, o.last_j, rl);
+    o.count = __shfl_sync(0xffffffffu, o.count, rl);
     return o;
 }
 
 // ---- phase A: distance + end positions ------------------------------------------------------------
+template <bool LONG>
 __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_kernel(EdArgs a) {
     __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32];
     __shared__ uint8_t s_lut[ED_WARPS][256];
@@ -183,15 +232,21 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_kernel(EdArgs a) 
     WarpCtx w;
     w.lane = lane;
     w.lut = s_lut[wid];
+    w.qrev = false;
+    w.hbuf = LONG ? a.hbuf + (size_t)gw * 2 * a.hbuf_stride : nullptr;
+    w.hbuf_stride = a.hbuf_stride;
+    const int n_work = LONG ? a.n_list : a.n_pairs;
     for (;;) {
         int pair = 0;
         if (lane == 0) pair = (int)atomicAdd(a.counter, 1u);
         pair = __shfl_sync(0xffffffffu, pair, 0);
-        if (pair >= a.n_pairs) break;
-        const uint8_t* q = a.q + a.q_off[pair];
-        const uint8_t* t = a.t + a.t_off[pair];
+        if (pair >= n_work) break;
+        if (LONG) pair = a.list[pair];
         const int m = (int)(a.q_off[pair + 1] - a.q_off[pair]);
         const int n = (int)(a.t_off[pair + 1] - a.t_off[pair]);
+        if (!LONG && m > 64 * ED_MAXBLOCKS) continue;  // left to the LONG launch
+        const uint8_t* q = a.q + a.q_off[pair];
+        const uint8_t* t = a.t + a.t_off[pair];
         unsigned int* bm = a.bitmask + a.bm_off[pair];
         __syncwarp();
         const int n_sym = build_alphabet(q, m, t, n, s_lut[wid], lane);
@@ -218,13 +273,15 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_kernel(EdArgs a) 
         }
         const int nb = (m + 63) >> 6;
         w.peq = n_sym <= ED_SMEM_SYMS ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32;
-        build_peq(w, q, m, nb, n_sym, false);
+        w.q = q;
+        w.n_sym = n_sym;
+        if (!LONG) build_peq(w, q, m, nb, n_sym, false);
         const bool unbounded = a.k < 0;
         if (a.mode == 0) {
             int kk = unbounded ? 0x3fffffff : a.k;
             if (!(kk < abs(n - m))) {  // :741-744
                 kk = min(kk, max(m, n));
-                const PassOut o = dp_pass<PASS_NW_SCORE>(w, m, nb, t, n, -1, 1, false, nullptr, nullptr);
+                const PassOut o = dp_pass<PASS_NW_SCORE, LONG>(w, m, nb, t, n, -1, 1, false, nullptr, nullptr);
                 if (o.best <= kk) {
                     r.edit_distance = o.best;
                     r.n_locations = 1;
@@ -233,7 +290,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_kernel(EdArgs a) 
             }
         } else {
             const bool j0 = (m & 63) != 0;  // W > 0
-            const PassOut o = dp_pass<PASS_SEMIGLOBAL>(w, m, nb, t, n, -1, a.mode == 2 ? 0 : 1, j0, bm, nullptr);
+            const PassOut o = dp_pass<PASS_SEMIGLOBAL, LONG>(w, m, nb, t, n, -1, a.mode == 2 ? 0 : 1, j0, bm, nullptr);
             int kk = unbounded ? 0x3fffffff : a.k;
             if (a.mode == 2) kk = min(kk, m);  // :565-567
             if (o.best <= kk) {
@@ -295,25 +352,158 @@ __device__ int traceback(const ulonglong2* trace, const uint8_t* q, int m, const
     return len;
 }
 
+// score of row i in a last column kept as per-block (Pv, Mv) with the blocks' prefix sums: D[i][.] = top + the
+// vertical deltas of rows 0..i-1
+__device__ __forceinline__ int column_score(const ulonglong2* col, const int* pre, int top, int i) {
+    const int b = i >> 6, k = i & 63;
+    int v = top + pre[b];
+    if (k) {
+        const ulonglong2 c = col[b];
+        const uint64_t mask = (1ull << k) - 1ull;
+        v += __popcll(c.x & mask) - __popcll(c.y & mask);
+    }
+    return v;
+}
+
+__device__ void column_prefix(const ulonglong2* col, int* pre, int nb, int lane) {
+    int carry = 0;
+    for (int b0 = 0; b0 < nb; b0 += 32) {
+        const int b = b0 + lane;
+        int v = 0;
+        if (b < nb) {
+            const ulonglong2 c = col[b];
+            v = __popcll(c.x) - __popcll(c.y);
+        }
+        const int inc = hs_warp_incl_scan(v, lane);
+        if (b < nb) pre[b + 1] = carry + inc;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) pre[0] = 0;
+    __syncwarp();
+}
+
+struct HbPart {
+    int q0, m, t0, n, score;
+};
+
+// obtainAlignment (:1168-1230) for the NW problem q[0..m) x t[0..n) with distance `best`: ops in reverse order at
+// out, returns their number or -1 (no split row / stack exhausted: edlib's EDLIB_STATUS_ERROR)
+__device__ int path_any_size(WarpCtx& w, const EdArgs& a, int gw, const uint8_t* q, int m, const uint8_t* t, int n, int best,
+                             int n_sym, uint8_t* out, HbPart* stack) {
+    const int lane = w.lane;
+    ulonglong2* trace = reinterpret_cast<ulonglong2*>(a.trace + (size_t)gw * ED_TRACE_BYTES);
+    ulonglong2* colL = a.colv + (size_t)gw * 2 * a.col_stride;
+    ulonglong2* colR = colL + a.col_stride;
+    int* preL = a.colpre + (size_t)gw * 2 * (a.col_stride + 1);
+    int* preR = preL + a.col_stride + 1;
+    int sp = 0, len = 0;
+    if (lane == 0) stack[0] = HbPart{0, m, 0, n, best};
+    sp = 1;
+    __syncwarp();
+    w.n_sym = n_sym;
+    while (sp > 0) {
+        const HbPart p = stack[--sp];
+        __syncwarp();
+        const uint8_t* pq = q + p.q0;
+        const uint8_t* pt = t + p.t0;
+        if (p.m == 0 || p.n == 0) {  // :1173-1180
+            const uint8_t op = p.m == 0 ? 2 : 1;
+            for (int i = lane; i < p.m + p.n; i += 32) out[len + i] = op;
+            len += p.m + p.n;
+            continue;
+        }
+        const int nb = (p.m + 63) >> 6;
+        if ((2ll * 8 + 4) * nb * p.n + 8ll * p.n < 1024 * 1024) {  // traceback (:1193-1195)
+            w.q = pq;
+            w.qrev = false;
+            dp_pass<PASS_NW_STORE, true>(w, p.m, nb, pt, p.n, -1, 1, false, nullptr, trace);
+            __syncwarp();
+            len += traceback(trace, pq, p.m, pt, p.n, out + len, lane);
+            __syncwarp();
+            continue;
+        }
+        // Hirschberg (:1236-1401)
+        const int left_w = p.n / 2, right_w = p.n - left_w;
+        w.q = pq;
+        w.qrev = false;
+        dp_pass<PASS_NW_COLUMN, true>(w, p.m, nb, pt, left_w, -1, 1, false, nullptr, nullptr, colL);
+        w.qrev = true;
+        dp_pass<PASS_NW_COLUMN, true>(w, p.m, nb, pt + left_w, right_w, right_w - 1, 1, false, nullptr, nullptr, colR);
+        __syncwarp();
+        column_prefix(colL, preL, nb, lane);
+        column_prefix(colR, preR, nb, lane);
+        // first i = row + 1 in 1..m-1 with D_left[i][left_w] + D_right_reversed[m - i][right_w] == score (:1312-1323)
+        int split = -1, ls = 0, rs = 0;
+        for (int i0 = 1; i0 < p.m && split < 0; i0 += 32) {
+            const int i = i0 + lane;
+            int l = 0, r = 0;
+            bool hit = false;
+            if (i < p.m) {
+                l = column_score(colL, preL, left_w, i);
+                r = column_score(colR, preR, right_w, p.m - i);
+                hit = l + r == p.score;
+            }
+            const unsigned int who = __ballot_sync(0xffffffffu, hit);
+            if (who) {
+                const int src = __ffs(who) - 1;
+                split = i0 + src;
+                ls = __shfl_sync(0xffffffffu, l, src);
+                rs = __shfl_sync(0xffffffffu, r, src);
+            }
+        }
+        if (split < 0) {
+            const int r_all = column_score(colR, preR, right_w, p.m);
+            const int l_all = column_score(colL, preL, left_w, p.m);
+            if (left_w + r_all == p.score) {  // the whole query goes right (:1325-1333)
+                split = 0;
+                ls = left_w;
+                rs = r_all;
+            } else if (l_all + right_w == p.score) {  // the whole query goes left (:1334-1343)
+                split = p.m;
+                ls = l_all;
+                rs = right_w;
+            }
+        }
+        if (split < 0 || sp + 2 > ED_STACK) return -1;
+        __syncwarp();
+        if (lane == 0) {  // the right part is popped first: ops come out back to front
+            stack[sp] = HbPart{p.q0, split, p.t0, left_w, ls};
+            stack[sp + 1] = HbPart{p.q0 + split, p.m - split, p.t0 + left_w, right_w, rs};
+        }
+        sp += 2;
+        __syncwarp();
+    }
+    return len;
+}
+
+template <bool LONG>
 __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_kernel(EdArgs a) {
     __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32];
     __shared__ uint8_t s_lut[ED_WARPS][256];
+    __shared__ HbPart s_stack[LONG ? ED_WARPS : 1][LONG ? ED_STACK : 1];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gw = blockIdx.x * ED_WARPS + wid;
     WarpCtx w;
     w.lane = lane;
     w.lut = s_lut[wid];
+    w.qrev = false;
+    w.hbuf = LONG ? a.hbuf + (size_t)gw * 2 * a.hbuf_stride : nullptr;
+    w.hbuf_stride = a.hbuf_stride;
+    const int n_work = LONG ? a.n_list : a.n_pairs;
     for (;;) {
         int pair = 0;
         if (lane == 0) pair = (int)atomicAdd(a.counter, 1u);
         pair = __shfl_sync(0xffffffffu, pair, 0);
-        if (pair >= a.n_pairs) break;
-        hsgpu_edlib_result r = a.res[pair];
-        if (r.edit_distance < 0) continue;
-        const uint8_t* q = a.q + a.q_off[pair];
-        const uint8_t* t = a.t + a.t_off[pair];
+        if (pair >= n_work) break;
+        if (LONG) pair = a.list[pair];
         const int m = (int)(a.q_off[pair + 1] - a.q_off[pair]);
         const int n = (int)(a.t_off[pair + 1] - a.t_off[pair]);
+        if (!LONG && m > 64 * ED_MAXBLOCKS) continue;
+        hsgpu_edlib_result r = a.res[pair];
+        if (r.edit_distance < 0) continue;
+        r.status = 0;
+        const uint8_t* q = a.q + a.q_off[pair];
+        const uint8_t* t = a.t + a.t_off[pair];
         const unsigned int* bm = a.bitmask + a.bm_off[pair];
         int32_t* ends = a.ends + r.loc_off;
         int32_t* starts = a.starts + r.loc_off;
@@ -339,18 +529,22 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_kernel(EdArgs a) 
         const int nb = (m + 63) >> 6;
         const int n_sym = build_alphabet(q, m, t, n, s_lut[wid], lane);
         w.peq = n_sym <= ED_SMEM_SYMS ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32;
+        w.q = q;
+        w.n_sym = n_sym;
         if (a.mode == 2) {
-            build_peq(w, q, m, nb, n_sym, true);
+            if (!LONG) build_peq(w, q, m, nb, n_sym, true);
+            w.qrev = true;
             const bool j0c = (m & 63) != 0;
             for (int l = 0; l < r.n_locations; l++) {
                 const int e = ends[l];
                 int st = 0;
                 if (e >= 0) {
-                    const PassOut o = dp_pass<PASS_REV_SHW>(w, m, nb, t, e + 1, e, 1, j0c, nullptr, nullptr);
+                    const PassOut o = dp_pass<PASS_REV_SHW, LONG>(w, m, nb, t, e + 1, e, 1, j0c, nullptr, nullptr);
                     st = e - (o.last_j - 1);  // :254-256 last position
                 }
                 if (lane == 0) starts[l] = st;
             }
+            w.qrev = false;
         } else {
             for (int l = lane; l < r.n_locations; l += 32) starts[l] = 0;
         }
@@ -362,12 +556,16 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_kernel(EdArgs a) 
             if (an <= 0) {  // obtainAlignment's empty-target case (:1173-1180)
                 for (int i = lane; i < m; i += 32) out[i] = 1;
                 r.alignment_length = m;
+            } else if (LONG) {
+                const int len = path_any_size(w, a, gw, q, m, t + s0, an, r.edit_distance, n_sym, out, s_stack[wid]);
+                if (len < 0) r.status = 1;
+                else r.alignment_length = len;
             } else if ((2ll * 8 + 4) * nb * an + 8ll * an >= 1024 * 1024) {
-                r.status = 2;  // Hirschberg regime
+                r.status = 2;  // Hirschberg regime: redone by the LONG launch
             } else {
                 build_peq(w, q, m, nb, n_sym, false);
                 ulonglong2* trace = reinterpret_cast<ulonglong2*>(a.trace + (size_t)gw * ED_TRACE_BYTES);
-                dp_pass<PASS_NW_STORE>(w, m, nb, t + s0, an, -1, 1, false, nullptr, trace);
+                dp_pass<PASS_NW_STORE, false>(w, m, nb, t + s0, an, -1, 1, false, nullptr, trace);
                 __syncwarp();
                 r.alignment_length = traceback(trace, q, m, t + s0, an, out, lane);
             }
@@ -397,12 +595,14 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     if (n_pairs == 0) return HSGPU_OK;
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<int64_t> bm_off((size_t)n_pairs + 1), tmp_off((size_t)n_pairs + 1);
+    std::vector<int32_t> long_list;  // queries of more than one strip: both phases run in their LONG instantiation
     int64_t bmw = 0, tmpb = 0;
     for (int i = 0; i < n_pairs; i++) {
         const int64_t m = query_off[i + 1] - query_off[i], n = target_off[i + 1] - target_off[i];
         if (m < 0 || n < 0) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_edlib_align_batch: offsets must be non-decreasing");
-        if (m > 64 * ED_MAXBLOCKS)
-            HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_edlib_align_batch: queries longer than 2048 are not supported yet");
+        if (m > ED_MAX_QUERY || n > (1 << 30))
+            HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_edlib_align_batch: query longer than 2^20 or target longer than 2^30");
+        if (m > 64 * ED_MAXBLOCKS) long_list.push_back(i);
         bm_off[i] = bmw;
         tmp_off[i] = tmpb;
         bmw += (n + 1 + 31) / 32 + 1;
@@ -428,7 +628,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     // phase A fills some of the fields; the whole struct travels to the host after it
     HS_CUDA(ctx, cudaMemsetAsync(d_res, 0, sizeof(hsgpu_edlib_result) * (size_t)std::max(n_pairs, 1), ctx->stream));
     HS_CUDA(ctx, hs_alloc(ctx, &d_bm, bmw));
-    HS_CUDA(ctx, hs_alloc(ctx, &d_counter, 2));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_counter, 4));
     HS_CUDA(ctx, hs_alloc(ctx, &d_peq, (int64_t)n_warps * 256 * 32));
     HS_CUDA(ctx, hs_h2d(ctx, d_q, (const uint8_t*)queries, qbytes));
     HS_CUDA(ctx, hs_h2d(ctx, d_t, (const uint8_t*)targets, tbytes));
@@ -436,7 +636,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     HS_CUDA(ctx, hs_h2d(ctx, d_to, target_off, n_pairs + 1));
     HS_CUDA(ctx, hs_h2d(ctx, d_bmo, bm_off.data(), n_pairs + 1));
     HS_CUDA(ctx, cudaMemsetAsync(d_bm, 0, sizeof(unsigned int) * bmw, ctx->stream));
-    HS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned int), ctx->stream));
+    HS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 4 * sizeof(unsigned int), ctx->stream));
     EdArgs a;
     a.n_pairs = n_pairs;
     a.q = d_q;
@@ -456,7 +656,49 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     a.peq_big = d_peq;
     a.trace = nullptr;
     a.counter = d_counter;
-    HS_KERNEL(ctx, "edlib_phase_a_kernel", edlib_phase_a_kernel<<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
+    a.list = nullptr;
+    a.n_list = 0;
+    a.hbuf = nullptr;
+    a.hbuf_stride = 0;
+    a.colv = nullptr;
+    a.colpre = nullptr;
+    a.col_stride = 0;
+    HS_KERNEL(ctx, "edlib_phase_a_kernel", edlib_phase_a_kernel<false><<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
+    // scratch of the LONG launches, sized for the pairs of the list at hand
+    int32_t* d_list = nullptr;
+    uint8_t* d_hbuf = nullptr;
+    ulonglong2* d_colv = nullptr;
+    int* d_colpre = nullptr;
+    auto long_setup = [&](const std::vector<int32_t>& list, bool with_columns, int* grid_long) -> cudaError_t {
+        hs_free(ctx, d_list); hs_free(ctx, d_hbuf); hs_free(ctx, d_colv); hs_free(ctx, d_colpre);
+        d_list = nullptr; d_hbuf = nullptr; d_colv = nullptr; d_colpre = nullptr;
+        int64_t max_n = 1, max_nb = 1;
+        for (int32_t i : list) {
+            max_n = std::max<int64_t>(max_n, target_off[i + 1] - target_off[i] + 1);
+            max_nb = std::max<int64_t>(max_nb, (query_off[i + 1] - query_off[i] + 63) / 64);
+        }
+        *grid_long = (int)std::min<int64_t>(grid, ((int64_t)list.size() + ED_WARPS - 1) / ED_WARPS);
+        const int64_t nw = (int64_t)*grid_long * ED_WARPS;
+        a.hbuf_stride = (max_n + 15) & ~15ll;
+        a.col_stride = max_nb;
+        cudaError_t e = hs_alloc(ctx, &d_list, (int64_t)list.size());
+        if (e == cudaSuccess) e = hs_alloc(ctx, &d_hbuf, nw * 2 * a.hbuf_stride);
+        if (e == cudaSuccess && with_columns) e = hs_alloc(ctx, &d_colv, nw * 2 * a.col_stride);
+        if (e == cudaSuccess && with_columns) e = hs_alloc(ctx, &d_colpre, nw * 2 * (a.col_stride + 1));
+        if (e == cudaSuccess) e = hs_h2d(ctx, d_list, list.data(), (int64_t)list.size());
+        a.list = d_list;
+        a.n_list = (int)list.size();
+        a.hbuf = d_hbuf;
+        a.colv = d_colv;
+        a.colpre = d_colpre;
+        return e;
+    };
+    if (!long_list.empty()) {
+        int grid_long = 0;
+        HS_CUDA(ctx, long_setup(long_list, false, &grid_long));
+        a.counter = d_counter + 2;
+        HS_KERNEL(ctx, "edlib_phase_a_kernel<long>", edlib_phase_a_kernel<true><<<grid_long, ED_WARPS * 32, 0, ctx->stream>>>(a));
+    }
     // sizes -> offsets on the host (n_pairs structs; the location lists are usually 1-3 entries each)
     HS_CUDA(ctx, hs_d2h(ctx, results, d_res, n_pairs));
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -490,8 +732,23 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
         a.aln_tmp_off = d_tmpo;
         a.trace = d_trace;
         a.counter = d_counter + 1;
-        HS_KERNEL(ctx, "edlib_phase_b_kernel", edlib_phase_b_kernel<<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
+        HS_KERNEL(ctx, "edlib_phase_b_kernel", edlib_phase_b_kernel<false><<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
         HS_CUDA(ctx, hs_d2h(ctx, results, d_res, n_pairs));
+        if (task == 2 || !long_list.empty()) {
+            // the LONG launch: long queries, and the pairs whose path turned out to lie at or above edlib's 1 MiB switch
+            HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            std::vector<int32_t> list = long_list;
+            for (int i = 0; i < n_pairs; i++)
+                if (results[i].status == 2) list.push_back(i);
+            if (!list.empty()) {
+                int grid_long = 0;
+                HS_CUDA(ctx, long_setup(list, task == 2, &grid_long));
+                a.counter = d_counter + 3;
+                HS_KERNEL(ctx, "edlib_phase_b_kernel<long>",
+                          edlib_phase_b_kernel<true><<<grid_long, ED_WARPS * 32, 0, ctx->stream>>>(a));
+                HS_CUDA(ctx, hs_d2h(ctx, results, d_res, n_pairs));
+            }
+        }
         HS_CUDA(ctx, hs_d2h(ctx, end_locations, d_ends, nloc));
         if (task >= 1) HS_CUDA(ctx, hs_d2h(ctx, start_locations, d_starts, nloc));
         HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -517,7 +774,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     hs_free(ctx, d_q); hs_free(ctx, d_t); hs_free(ctx, d_qo); hs_free(ctx, d_to); hs_free(ctx, d_bmo);
     hs_free(ctx, d_res); hs_free(ctx, d_bm); hs_free(ctx, d_counter); hs_free(ctx, d_peq); hs_free(ctx, d_ends);
     hs_free(ctx, d_starts); hs_free(ctx, d_aln_tmp); hs_free(ctx, d_tmpo); hs_free(ctx, d_trace); hs_free(ctx, d_aln);
-    hs_free(ctx, d_scan);
+    hs_free(ctx, d_scan); hs_free(ctx, d_list); hs_free(ctx, d_hbuf); hs_free(ctx, d_colv); hs_free(ctx, d_colpre);
     return rc;
 }
 

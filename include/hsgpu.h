@@ -294,10 +294,13 @@ int hsgpu_clip_reads(hsgpu_ctx* ctx, int64_t n_reads, const uint32_t* cigar, con
 
 /* ---- realignment: edlibAlign (src/edlib/include/edlib.h:146-271, src/edlib/src/edlib.cpp:142-297)
  * Batch of (query, target) pairs, results with edlib's exact field semantics. Modes/tasks use edlib's
- * numeric values: mode 0 NW, 1 SHW, 2 HW; task 0 DISTANCE, 1 LOC, 2 PATH. */
+ * numeric values: mode 0 NW, 1 SHW, 2 HW; task 0 DISTANCE, 1 LOC, 2 PATH. Queries up to 2^20, targets up to 2^30.
+ * Paths at or above edlib's 1 MiB switch ((20*ceil(q/64)+8)*columns >= 1 MiB, edlib.cpp:1193-1195) are split the
+ * way obtainAlignmentHirschberg (edlib.cpp:1236-1401) splits them, so the ops are edlib's there too. Pairs with
+ * queries of at most 2048 whose path lies below the switch take the throughput kernels; the others are redone by a
+ * second, slower launch over just those pairs. */
 typedef struct {
-    int32_t status;               /* 0 = EDLIB_STATUS_OK; 2 = OK but the path lies in edlib's Hirschberg regime
-                                     ((20*ceil(q/64)+8)*columns >= 1 MiB, edlib.cpp:1193-1195) and was not produced */
+    int32_t status;               /* edlib's: 0 = EDLIB_STATUS_OK, 1 = EDLIB_STATUS_ERROR */
     int32_t edit_distance;        /* -1 if larger than k */
     int32_t n_locations;
     int32_t alignment_length;
@@ -320,8 +323,7 @@ int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const char* queries
  * result unchanged. endLocations / startLocations / alignment are malloc'd by the library and released by
  * hsgpu_edlibFreeAlignResult (or free()), NULL where edlib leaves them NULL (distance above k, DISTANCE task,
  * empty sequence). status: 0 = EDLIB_STATUS_OK, 1 = EDLIB_STATUS_ERROR (also: additional equalities are not
- * supported), 2 = distance and locations are exact but the path lies in edlib's Hirschberg regime and was not
- * produced. One pair per call costs a kernel launch and a round trip: batch the pairs where the caller can. */
+ * supported). One pair per call costs a kernel launch and a round trip: batch the pairs where the caller can. */
 typedef struct {
     int k;
     int mode; /* EdlibAlignMode: 0 NW, 1 SHW, 2 HW */

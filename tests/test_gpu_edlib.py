@@ -110,20 +110,67 @@ def test_benchmark_shape_read_chunk_on_window(gpu_ctx, oracle):
     _check_batch(gpu_ctx, oracle, qs, ts, -1, 0, 2, use_ref=True)
 
 
-def test_hirschberg_regime_is_flagged_not_faked(gpu_ctx, oracle):
-    rng = np.random.default_rng(9)
-    t = _rnd(rng, 2600)
-    q = _mutate(rng, t[:2040], 0.02)[:2048]
-    res, ends, starts, aln = gpu_ctx.edlib_align_batch([q], [t], k=-1, mode=0, task=2)
-    want = oracle.edlib_align(q, t, -1, 0, 2)
-    assert int(res[0]["edit_distance"]) == want["edit_distance"]
-    assert want["status"] == 2 and int(res[0]["status"]) == 2 and int(res[0]["alignment_length"]) == 0
+def _check_vectors(gpu_ctx, vec):
+    groups = {}
+    for v in vec:
+        groups.setdefault((v["k"], v["mode"], v["task"]), []).append(v)
+    for (k, mode, task), vs in groups.items():
+        qs = [v["q"].encode("latin1") for v in vs]
+        ts = [v["t"].encode("latin1") for v in vs]
+        res, ends, starts, aln = gpu_ctx.edlib_align_batch(qs, ts, k=k, mode=mode, task=task)
+        for i, v in enumerate(vs):
+            r = res[i]
+            ctx = (i, len(qs[i]), len(ts[i]), k, mode, task)
+            assert int(r["status"]) == v["status"], ctx
+            assert int(r["edit_distance"]) == v["edit_distance"], ctx
+            assert int(r["alphabet_length"]) == v["alphabet_length"], ctx
+            lo, nl = int(r["loc_off"]), int(r["n_locations"])
+            assert ends[lo:lo + nl].tolist() == v["end_locations"], ctx
+            if v["start_locations"] is None:
+                assert int(r["has_start_locations"]) == 0, ctx
+            else:
+                assert starts[lo:lo + nl].tolist() == v["start_locations"], ctx
+            if task == 2 and v["alignment"] is not None and v["edit_distance"] >= 0:
+                ao, al = int(r["aln_off"]), int(r["alignment_length"])
+                assert aln[ao:ao + al].tolist() == list(v["alignment"]), ctx
+
+
+def test_long_queries_and_hirschberg_golden_vectors(gpu_ctx):
+    """queries of more than 2048 rows (strips of 32 blocks) and paths at or above edlib's 1 MiB switch
+    (obtainAlignmentHirschberg, src/edlib/src/edlib.cpp:1236-1401) against vectors of the vendored edlib"""
+    from test_oracle_edlib import golden_vectors_long
+    _check_vectors(gpu_ctx, golden_vectors_long())
+
+
+def test_long_and_short_pairs_in_one_batch(gpu_ctx, oracle):
+    """one batch holding ordinary pairs, pairs in the Hirschberg regime and queries of several strips: the LONG launch
+    redoes only its own pairs"""
+    rng = np.random.default_rng(21)
+    qs, ts = [], []
+    for i in range(24):
+        if i % 6 == 0:
+            t = _rnd(rng, 3000)
+            q = _mutate(rng, t[200:2800], 0.08)            # long query, Hirschberg
+        elif i % 6 == 1:
+            t = _rnd(rng, 2600)
+            q = _mutate(rng, t[:2000], 0.05)[:2048]        # one strip, Hirschberg
+        elif i % 6 == 2:
+            t = _rnd(rng, 200)
+            q = _rnd(rng, 2300)                            # long query, traceback
+        else:
+            t = _rnd(rng, 900)
+            q = _mutate(rng, t[300:600], 0.1)
+        qs.append(q)
+        ts.append(t)
+    for mode in (0, 2):
+        _check_batch(gpu_ctx, oracle, qs, ts, -1, mode, 2, use_ref=True)
+    _check_batch(gpu_ctx, oracle, qs, ts, -1, 1, 1, use_ref=True)
 
 
 def test_query_longer_than_limit_fails_loudly(gpu_ctx):
     from hairsplitter_b200 import api
     with pytest.raises(api.HsgpuError):
-        gpu_ctx.edlib_align_batch([b"A" * 2049], [b"ACGT" * 10], k=-1, mode=0, task=0)
+        gpu_ctx.edlib_align_batch([b"A" * ((1 << 20) + 1)], [b"ACGT" * 10], k=-1, mode=0, task=0)
 
 
 def test_single_pair_shim_has_edlibs_result_semantics(gpu_ctx, oracle):
@@ -173,24 +220,4 @@ def test_golden_vectors_of_the_vendored_edlib(gpu_ctx):
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     vec = json.loads(gzip.open(os.path.join(root, "tests", "golden", "edlib_vectors.json.gz")).read())
-    groups = {}
-    for v in vec:
-        groups.setdefault((v["k"], v["mode"], v["task"]), []).append(v)
-    for (k, mode, task), vs in groups.items():
-        qs = [v["q"].encode("latin1") for v in vs]
-        ts = [v["t"].encode("latin1") for v in vs]
-        res, ends, starts, aln = gpu_ctx.edlib_align_batch(qs, ts, k=k, mode=mode, task=task)
-        for i, v in enumerate(vs):
-            r = res[i]
-            ctx = (i, len(qs[i]), len(ts[i]), k, mode, task)
-            assert int(r["edit_distance"]) == v["edit_distance"], ctx
-            assert int(r["alphabet_length"]) == v["alphabet_length"], ctx
-            lo, nl = int(r["loc_off"]), int(r["n_locations"])
-            assert ends[lo:lo + nl].tolist() == v["end_locations"], ctx
-            if v["start_locations"] is None:
-                assert int(r["has_start_locations"]) == 0, ctx
-            else:
-                assert starts[lo:lo + nl].tolist() == v["start_locations"], ctx
-            if task == 2 and v["alignment"] is not None and v["edit_distance"] >= 0 and int(r["status"]) == 0:
-                ao, al = int(r["aln_off"]), int(r["alignment_length"])
-                assert aln[ao:ao + al].tolist() == v["alignment"], ctx
+    _check_vectors(gpu_ctx, vec)
