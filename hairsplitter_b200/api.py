@@ -496,15 +496,23 @@ class Context:
         np.cumsum([len(t) for t in targets], out=to[1:])
         qb = np.frombuffer(b"".join(queries) or b"\0", dtype=np.uint8)
         tb = np.frombuffer(b"".join(targets) or b"\0", dtype=np.uint8)
-        res = np.zeros(n, dtype=EDLIB_RESULT_DTYPE)
-        loc_cap = int(to[-1]) + n + 8
-        aln_cap = int(qo[-1] + to[-1]) + 8
-        ends = np.zeros(loc_cap, dtype=np.int32)
-        starts = np.zeros(loc_cap, dtype=np.int32)
-        aln = np.zeros(aln_cap, dtype=np.uint8)
+        return self.edlib_align_batch_arrays(qb, qo, tb, to, k=k, mode=mode, task=task)
+
+    def edlib_align_batch_arrays(self, qb, qo, tb, to, k=-1, mode=2, task=2, out=None):
+        """hsgpu_edlib_align_batch on concatenated sequences (uint8) and their int64 offsets -- the C ABI's own
+        arguments; `out` = (results, ends, starts, alignment) buffers to fill (numpy arrays, e.g. views of pinned
+        memory), allocated here when None."""
+        n = len(qo) - 1
+        if out is None:
+            res = np.zeros(n, dtype=EDLIB_RESULT_DTYPE)
+            ends = np.zeros(int(to[-1]) + n + 8, dtype=np.int32)
+            starts = np.zeros(int(to[-1]) + n + 8, dtype=np.int32)
+            aln = np.zeros(int(qo[-1] + to[-1]) + 8, dtype=np.uint8)
+        else:
+            res, ends, starts, aln = out
         self.check(self.lib.hsgpu_edlib_align_batch(self.h, n, qb.ctypes.data, qo.ctypes.data, tb.ctypes.data,
                                                     to.ctypes.data, k, mode, task, res.ctypes.data, ends.ctypes.data,
-                                                    starts.ctypes.data, loc_cap, aln.ctypes.data, aln_cap),
+                                                    starts.ctypes.data, len(ends), aln.ctypes.data, len(aln)),
                    "hsgpu_edlib_align_batch")
         return res, ends, starts, aln
 

@@ -36,6 +36,9 @@
 #define ED_MAXBLOCKS 32     // one 64-row block per lane -> queries up to 2048 in one strip
 #define ED_MAX_QUERY (1 << 20)
 #define ED_STACK 40         // Hirschberg parts waiting per warp (the target halves at every level)
+#define ED_PACK_MAXBLOCKS 16  // queries up to 1024 share a warp with others of the same block count
+#define ED_PACK_MAXLOC 4      // ... as long as they have few end locations (the start-location sweeps run in step)
+enum { ED_ROUTE_ORDINARY = 0, ED_ROUTE_PACKED = 1, ED_ROUTE_LONG = 2, ED_ROUTE_NONE = 3 };
 #define ED_SMEM_SYMS 8      // alphabets up to this size keep Peq in shared memory
 #define ED_TRACE_BYTES (52429ll * 16)  // per-warp traceback slab: blocks*columns < 2^20/20 entries of 16 B
 
@@ -56,6 +59,13 @@ struct EdArgs {
     uint64_t* peq_big;            // per resident warp: 256 * 32 words, for alphabets > ED_SMEM_SYMS
     uint8_t* trace;               // per resident warp: ED_TRACE_BYTES
     unsigned int* counter;        // dynamic pair scheduler
+    const uint8_t* route;         // per pair: which launch works on it (ED_ROUTE_*)
+    // packed launches only: several short queries share a warp
+    const int32_t* alpha_len;     // per pair alphabet size (edlib_alphabet_kernel)
+    const unsigned int* batch_alpha;  // 256-bit set of the bytes present anywhere in the batch
+    const int32_t* plist;         // pairs in task order
+    const int32_t* tasks;         // per task: first index into plist, (blocks << 8) | pairs
+    int n_tasks;
     // LONG instantiations only
     const int32_t* list;          // pairs to work on
     int n_list;
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_kernel(EdArgs a) 
         if (LONG) pair = a.list[pair];
         const int m = (int)(a.q_off[pair + 1] - a.q_off[pair]);
         const int n = (int)(a.t_off[pair + 1] - a.t_off[pair]);
-        if (!LONG && m > 64 * ED_MAXBLOCKS) continue;  // left to the LONG launch
+        if (!LONG && a.route[pair] != ED_ROUTE_ORDINARY) continue;  // left to the packed / LONG launches
         const uint8_t* q = a.q + a.q_off[pair];
         const uint8_t* t = a.t + a.t_off[pair];
         unsigned int* bm = a.bitmask + a.bm_off[pair];
@@ -350,6 +360,366 @@ __device__ int traceback(const ulonglong2* trace, const uint8_t* q, int m, const
     }
     if (lane < (len & 31)) out[(len & ~31) + lane] = (uint8_t)pend;
     return len;
+}
+
+// ---- packed form: floor(32 / blocks) pairs of the same block count per warp -----------------------------
+// The in-pipeline realignment is a <= 300-base query against a ~2.3 kb window (reference src/create_new_contigs.cpp:
+// 557-630): 5 blocks, so one pair per warp leaves 27 lanes idle. Here lane = (group, block): each group of `nb` lanes
+// runs its own pair's wavefront, all groups in step. One symbol table serves the whole batch (the numbering of the
+// symbols never shows in edlib's results; the per-pair alphabet size comes from edlib_alphabet_kernel).
+struct PackLane {
+    int nb, bl, ghead;  // blocks per pair, this lane's block, first lane of its group
+    bool active;
+};
+
+__global__ void __launch_bounds__(256) edlib_alphabet_kernel(int n_pairs, const uint8_t* __restrict__ q,
+                                                             const int64_t* __restrict__ q_off, const uint8_t* __restrict__ t,
+                                                             const int64_t* __restrict__ t_off, int32_t* __restrict__ alpha_len,
+                                                             unsigned int* __restrict__ batch_alpha) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    unsigned int all[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int pair = gw; pair < n_pairs; pair += nw) {
+        unsigned int present[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int64_t q0 = q_off[pair], q1 = q_off[pair + 1], t0 = t_off[pair], t1 = t_off[pair + 1];
+        for (int64_t i = q0 + lane; i < q1; i += 32) { const int c = q[i]; present[c >> 5] |= 1u << (c & 31); }
+        for (int64_t i = t0 + lane; i < t1; i += 32) { const int c = t[i]; present[c >> 5] |= 1u << (c & 31); }
+        int total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const unsigned int v = __reduce_or_sync(0xffffffffu, present[w]);
+            total += __popc(v);
+            all[w] |= v;
+        }
+        if (lane == 0) alpha_len[pair] = total;
+    }
+    if (lane < 8) {
+        unsigned int v = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) if (w == lane) v = all[w];
+        if (v) atomicOr(batch_alpha + lane, v);
+    }
+}
+
+// lut over the batch's bytes (same numbering rule as build_alphabet); returns the number of symbols
+__device__ int build_batch_lut(const unsigned int* batch_alpha, uint8_t* lut, int lane) {
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const unsigned int v = batch_alpha[w];
+        lut[w * 32 + lane] = (uint8_t)(base + __popc(v & ((1u << lane) - 1u)));
+        base += __popc(v);
+    }
+    __syncwarp();
+    return base;
+}
+
+// every lane fills the Peq column of its own (pair, block)
+__device__ void build_peq_packed(uint64_t* peq, const uint8_t* lut, int lane, const PackLane& g, const uint8_t* q, int m,
+                                 int n_sym, bool reversed) {
+    for (int sym = 0; sym < n_sym; sym++) peq[sym * 32 + lane] = 0ull;
+    if (g.active) {
+        const int r0 = g.bl * 64;
+        const int r1 = min(m, r0 + 64);
+        for (int r = r0; r < r1; r++) {
+            const int c = reversed ? q[m - 1 - r] : q[r];
+            peq[lut[c] * 32 + lane] |= 1ull << (r - r0);
+        }
+    }
+    __syncwarp();
+}
+
+// dp_pass with per-lane pair parameters; n_max = the longest target of the warp's groups. The result is valid in the
+// lanes of the group it belongs to.
+template <int KIND>
+__device__ PassOut dp_pass_packed(const uint64_t* peq, const uint8_t* lut, int lane, const PackLane& g, int m,
+                                  const uint8_t* t, int n, int n_max, int rev_end, int start_hin, bool consider_j0,
+                                  unsigned int* bitmask, ulonglong2* trace) {
+    uint64_t Pv = ~0ull, Mv = 0ull;
+    const int lb = (m - 1) & 63;
+    const int nb = g.nb;
+    int score = m;
+    PassOut o;
+    o.best = consider_j0 ? m : 0x3fffffff;
+    o.first_j = 0;
+    o.last_j = 0;
+    o.count = consider_j0 ? 1 : 0;
+    unsigned int bits = consider_j0 ? 1u : 0u;
+    int packed = 0;
+    // target symbols: nb at a time per group (lane bl holds symbol chunk*nb + bl), fetched one chunk ahead
+    int tchunk = 0, tnext = 0;
+    if (g.active && g.bl < n) tchunk = lut[rev_end >= 0 ? t[rev_end - g.bl] : t[g.bl]];
+    if (g.active && nb + g.bl < n) tnext = lut[rev_end >= 0 ? t[rev_end - nb - g.bl] : t[nb + g.bl]];
+    int sc = 0;
+    const int steps = n_max + nb - 1;
+    for (int s = 0; s < steps; s++) {
+        const int sym0 = __shfl_sync(0xffffffffu, tchunk, g.ghead + sc);
+        const int pk = __shfl_up_sync(0xffffffffu, packed, 1);
+        const int sym = g.bl == 0 ? sym0 : (pk >> 2);
+        const int hin = g.bl == 0 ? start_hin : ((pk & 3) - 1);
+        const int c = s - g.bl;
+        if (g.active && c >= 0 && c < n) {
+            uint64_t Eq = peq[sym * 32 + lane];
+            const uint64_t hneg = hin < 0 ? 1ull : 0ull, hpos = hin > 0 ? 1ull : 0ull;
+            const uint64_t Xv = Eq | Mv;
+            Eq |= hneg;
+            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            uint64_t Ph = Mv | ~(Xh | Pv);
+            uint64_t Mh = Pv & Xh;
+            const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+            packed = (sym << 2) | (hout + 1);
+            if (g.bl == nb - 1) {
+                score += (int)((Ph >> lb) & 1ull) - (int)((Mh >> lb) & 1ull);
+                const int j = c + 1;
+                if (KIND == PASS_SEMIGLOBAL) {
+                    if ((j & 31) == 0) bits = 0;
+                    if (score < o.best) { o.best = score; o.first_j = j; o.count = 0; }
+                    if (score == o.best) { o.count++; o.last_j = j; bits |= 1u << (j & 31); }
+                    if ((j & 31) == 31 || j == n) bitmask[j >> 5] = bits;
+                } else if (KIND == PASS_REV_SHW) {
+                    if (score < o.best) { o.best = score; o.first_j = j; }
+                    if (score == o.best) o.last_j = j;
+                } else {
+                    o.best = score;
+                }
+            }
+            const uint64_t Phs = (Ph << 1) | hpos;
+            const uint64_t Mhs = (Mh << 1) | hneg;
+            Pv = Mhs | ~(Xv | Phs);
+            Mv = Phs & Xv;
+            if (KIND == PASS_NW_STORE) trace[(size_t)g.bl * n + c] = make_ulonglong2(Pv, Ph);
+        }
+        if (++sc == nb) {
+            sc = 0;
+            tchunk = tnext;
+            const int idx = s + 1 + nb + g.bl;
+            tnext = 0;
+            if (g.active && idx < n) tnext = lut[rev_end >= 0 ? t[rev_end - idx] : t[idx]];
+        }
+    }
+    const int rl = g.ghead + nb - 1;
+    o.best = __shfl_sync(0xffffffffu, o.best, rl);
+    o.first_j = __shfl_sync(0xffffffffu, o.first_j, rl);
+    o.last_j = __shfl_sync(0xffffffffu, o.last_j, rl);
+    o.count = __shfl_sync(0xffffffffu, o.count, rl);
+    return o;
+}
+
+// the groups of a warp walk their paths in step (same rules as traceback above; the window is nb columns wide)
+__device__ int traceback_packed(const ulonglong2* trace, const uint8_t* q, int m, const uint8_t* t, int n, uint8_t* out,
+                                const PackLane& g) {
+    const int nb = g.nb;
+    int i = g.active ? m : 0, j = g.active ? n : 0, len = 0, fl = 0;
+    unsigned int pend = 0;  // op of output position len - fl + bl
+    int win_block = -1, win_j0 = -1;
+    uint64_t wPv = 0, wPh = 0;
+    while (__any_sync(0xffffffffu, i > 0 && j > 0)) {
+        const bool go = i > 0 && j > 0;
+        if (go) {
+            const int b = (i - 1) >> 6;
+            if (b != win_block || j > win_j0 || j <= win_j0 - nb) {
+                win_block = b;
+                win_j0 = j;
+                const int jj = j - g.bl;  // lane bl of the group holds column j0 - bl
+                ulonglong2 v = make_ulonglong2(0ull, 0ull);
+                if (jj >= 1) v = trace[(size_t)b * n + (jj - 1)];
+                wPv = v.x;
+                wPh = v.y;
+            }
+        }
+        const int src = g.ghead + (go ? win_j0 - j : 0);
+        const uint64_t pv = shfl64(wPv, src), ph = shfl64(wPh, src);
+        if (go) {
+            const int bit = (i - 1) & 63;
+            int op;
+            if ((pv >> bit) & 1ull) op = 1;
+            else if ((ph >> bit) & 1ull) op = 2;
+            else op = (q[i - 1] == t[j - 1]) ? 0 : 3;
+            i -= op != 2;
+            j -= op != 1;
+            if (fl == g.bl) pend = (unsigned)op;
+            len++;
+            if (++fl == nb) {
+                fl = 0;
+                out[len - nb + g.bl] = (uint8_t)pend;
+            }
+        }
+    }
+    if (g.active) {
+        if (g.bl < fl) out[len - fl + g.bl] = (uint8_t)pend;
+        const int rest = i > 0 ? i : j;
+        const uint8_t rest_op = i > 0 ? 1 : 2;
+        for (int x = g.bl; x < rest; x += nb) out[len + x] = rest_op;
+        len += rest;
+    }
+    return len;
+}
+
+__device__ __forceinline__ PackLane pack_lane(int lane, int nb, int cnt) {
+    PackLane g;
+    g.nb = nb;
+    const int grp = lane / nb;
+    g.bl = lane - grp * nb;
+    g.ghead = grp * nb;
+    g.active = grp < cnt;
+    return g;
+}
+
+__global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_packed_kernel(EdArgs a) {
+    __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32];
+    __shared__ uint8_t s_lut[ED_WARPS][256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gw = blockIdx.x * ED_WARPS + wid;
+    const uint8_t* lut = s_lut[wid];
+    const int n_sym = build_batch_lut(a.batch_alpha, s_lut[wid], lane);
+    uint64_t* peq = n_sym <= ED_SMEM_SYMS ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32;
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = (int)atomicAdd(a.counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= a.n_tasks) break;
+        const int first = a.tasks[2 * task], nbc = a.tasks[2 * task + 1];
+        const PackLane g = pack_lane(lane, nbc >> 8, nbc & 255);
+        const int grp = lane / g.nb;
+        const int pair = g.active ? a.plist[first + grp] : 0;
+        const uint8_t* q = a.q + a.q_off[pair];
+        const uint8_t* t = a.t + a.t_off[pair];
+        const int m = g.active ? (int)(a.q_off[pair + 1] - a.q_off[pair]) : 1;
+        const int n = g.active ? (int)(a.t_off[pair + 1] - a.t_off[pair]) : 0;
+        unsigned int* bm = a.bitmask + a.bm_off[pair];
+        __syncwarp();
+        build_peq_packed(peq, lut, lane, g, q, m, n_sym, false);
+        hsgpu_edlib_result r;
+        r.status = 0;
+        r.edit_distance = -1;
+        r.n_locations = 0;
+        r.alignment_length = 0;
+        r.alphabet_length = g.active ? a.alpha_len[pair] : 0;
+        r.has_start_locations = 0;
+        r.loc_off = 0;
+        r.aln_off = 0;
+        const bool unbounded = a.k < 0;
+        int kk = unbounded ? 0x3fffffff : a.k;
+        if (a.mode == 0) {
+            const bool run = g.active && !(kk < abs(n - m));  // :741-744
+            kk = min(kk, max(m, n));
+            const int n_max = __reduce_max_sync(0xffffffffu, run ? n : 0);
+            PackLane gr = g;
+            gr.active = run;
+            const PassOut o = dp_pass_packed<PASS_NW_SCORE>(peq, lut, lane, gr, m, t, n, n_max, -1, 1, false, nullptr, nullptr);
+            if (run && o.best <= kk) {
+                r.edit_distance = o.best;
+                r.n_locations = 1;
+                if (g.bl == 0) bm[n >> 5] = 1u << (n & 31);
+            }
+        } else {
+            const bool j0 = (m & 63) != 0;  // W > 0
+            const int n_max = __reduce_max_sync(0xffffffffu, n);
+            const PassOut o = dp_pass_packed<PASS_SEMIGLOBAL>(peq, lut, lane, g, m, t, n, n_max, -1, a.mode == 2 ? 0 : 1, j0,
+                                                              bm, nullptr);
+            if (a.mode == 2) kk = min(kk, m);  // :565-567
+            if (o.best <= kk) {
+                r.edit_distance = o.best;
+                r.n_locations = o.count;
+                r.loc_off = o.first_j;
+            }
+        }
+        if (g.active && g.bl == 0) a.res[pair] = r;
+    }
+}
+
+__global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdArgs a) {
+    __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32];
+    __shared__ uint8_t s_lut[ED_WARPS][256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gw = blockIdx.x * ED_WARPS + wid;
+    const uint8_t* lut = s_lut[wid];
+    const int n_sym = build_batch_lut(a.batch_alpha, s_lut[wid], lane);
+    uint64_t* peq = n_sym <= ED_SMEM_SYMS ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32;
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = (int)atomicAdd(a.counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= a.n_tasks) break;
+        const int first = a.tasks[2 * task], nbc = a.tasks[2 * task + 1];
+        const PackLane g = pack_lane(lane, nbc >> 8, nbc & 255);
+        const int grp = lane / g.nb;
+        const int pair = g.active ? a.plist[first + grp] : 0;
+        hsgpu_edlib_result r = a.res[pair];
+        const uint8_t* q = a.q + a.q_off[pair];
+        const uint8_t* t = a.t + a.t_off[pair];
+        const int m = g.active ? (int)(a.q_off[pair + 1] - a.q_off[pair]) : 1;
+        const int n = g.active ? (int)(a.t_off[pair + 1] - a.t_off[pair]) : 0;
+        const unsigned int* bm = a.bitmask + a.bm_off[pair];
+        int32_t* ends = a.ends + r.loc_off;
+        int32_t* starts = a.starts + r.loc_off;
+        const int n_loc = g.active ? r.n_locations : 0;
+        __syncwarp();
+        if (g.active && g.bl == 0) {  // end locations: set bits j >= first_j, position = j - 1
+            const int first_j = r.aln_off < 0 ? 0 : (int)r.aln_off;
+            int found = 0;
+            for (int j0 = first_j & ~31; j0 <= n && found < n_loc; j0 += 32) {
+                unsigned int word = bm[j0 >> 5];
+                if (j0 < first_j) word &= ~((1u << (first_j - j0)) - 1u);
+                while (word && found < n_loc) {
+                    const int bpos = __ffs(word) - 1;
+                    word &= word - 1;
+                    ends[found++] = j0 + bpos - 1;
+                }
+            }
+        }
+        __syncwarp();
+        if (a.task == 0) continue;
+        r.has_start_locations = 1;
+        if (a.mode == 2) {
+            build_peq_packed(peq, lut, lane, g, q, m, n_sym, true);
+            const bool j0c = (m & 63) != 0;
+            const int loc_max = __reduce_max_sync(0xffffffffu, n_loc);
+            for (int l = 0; l < loc_max; l++) {
+                const int e = l < n_loc ? ends[l] : -1;
+                PackLane gr = g;
+                gr.active = g.active && e >= 0;
+                const int n_max = __reduce_max_sync(0xffffffffu, gr.active ? e + 1 : 0);
+                const PassOut o = dp_pass_packed<PASS_REV_SHW>(peq, lut, lane, gr, m, t, e + 1, n_max, e, 1, j0c, nullptr, nullptr);
+                if (g.bl == 0 && l < n_loc) starts[l] = e >= 0 ? e - (o.last_j - 1) : 0;  // :254-256 last position
+            }
+        } else if (g.active) {
+            for (int l = g.bl; l < n_loc; l += g.nb) starts[l] = 0;
+        }
+        __syncwarp();
+        if (a.task == 2) {
+            const int s0 = g.active ? starts[0] : 0, e0 = g.active ? ends[0] : -1;
+            const int an = e0 - s0 + 1;
+            uint8_t* out = a.aln_tmp + a.aln_tmp_off[pair];
+            // the groups share the warp's traceback slab
+            const bool walk = g.active && an > 0;
+            const long long need = walk ? (long long)g.nb * an : 0;  // entries of 16 bytes
+            const long long mine = g.bl == 0 ? need : 0;
+            long long incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
+            }
+            const long long base = __shfl_sync(0xffffffffu, incl - mine, g.ghead);
+            PackLane gw_ = g;
+            gw_.active = walk && (base + need) * 16 <= ED_TRACE_BYTES;
+            if (walk && !gw_.active) r.status = 1;  // cannot happen: the host routes by the same bound
+            ulonglong2* trace = reinterpret_cast<ulonglong2*>(a.trace + (size_t)gw * ED_TRACE_BYTES) + base;
+            if (g.active && an <= 0) {  // obtainAlignment's empty-target case (:1173-1180)
+                for (int i = g.bl; i < m; i += g.nb) out[i] = 1;
+                r.alignment_length = m;
+            }
+            build_peq_packed(peq, lut, lane, g, q, m, n_sym, false);
+            const int n_max = __reduce_max_sync(0xffffffffu, gw_.active ? an : 0);
+            dp_pass_packed<PASS_NW_STORE>(peq, lut, lane, gw_, m, t + s0, an, n_max, -1, 1, false, nullptr, trace);
+            __syncwarp();
+            const int len = traceback_packed(trace, q, m, t + s0, an, out, gw_);
+            if (gw_.active) r.alignment_length = len;
+            __syncwarp();
+        }
+        if (g.active && g.bl == 0) a.res[pair] = r;
+    }
 }
 
 // score of row i in a last column kept as per-block (Pv, Mv) with the blocks' prefix sums: D[i][.] = top + the
@@ -498,7 +868,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_kernel(EdArgs a) 
         if (LONG) pair = a.list[pair];
         const int m = (int)(a.q_off[pair + 1] - a.q_off[pair]);
         const int n = (int)(a.t_off[pair + 1] - a.t_off[pair]);
-        if (!LONG && m > 64 * ED_MAXBLOCKS) continue;
+        if (!LONG && a.route[pair] != ED_ROUTE_ORDINARY) continue;
         hsgpu_edlib_result r = a.res[pair];
         if (r.edit_distance < 0) continue;
         r.status = 0;
@@ -596,13 +966,25 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<int64_t> bm_off((size_t)n_pairs + 1), tmp_off((size_t)n_pairs + 1);
     std::vector<int32_t> long_list;  // queries of more than one strip: both phases run in their LONG instantiation
+    std::vector<uint8_t> route((size_t)n_pairs);
+    static const bool pack = !getenv("HSGPU_EDLIB_PACK") || atoi(getenv("HSGPU_EDLIB_PACK")) != 0;
+    int64_t n_packed = 0, n_ordinary = 0;
     int64_t bmw = 0, tmpb = 0;
     for (int i = 0; i < n_pairs; i++) {
         const int64_t m = query_off[i + 1] - query_off[i], n = target_off[i + 1] - target_off[i];
         if (m < 0 || n < 0) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_edlib_align_batch: offsets must be non-decreasing");
         if (m > ED_MAX_QUERY || n > (1 << 30))
             HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_edlib_align_batch: query longer than 2^20 or target longer than 2^30");
-        if (m > 64 * ED_MAXBLOCKS) long_list.push_back(i);
+        if (m > 64 * ED_MAXBLOCKS) {
+            long_list.push_back(i);
+            route[i] = ED_ROUTE_LONG;
+        } else if (pack && m >= 1 && m <= 64 * ED_PACK_MAXBLOCKS && n >= 1) {
+            route[i] = ED_ROUTE_PACKED;
+            n_packed++;
+        } else {
+            route[i] = ED_ROUTE_ORDINARY;
+            n_ordinary++;
+        }
         bm_off[i] = bmw;
         tmp_off[i] = tmpb;
         bmw += (n + 1 + 31) / 32 + 1;
@@ -628,7 +1010,48 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     // phase A fills some of the fields; the whole struct travels to the host after it
     HS_CUDA(ctx, cudaMemsetAsync(d_res, 0, sizeof(hsgpu_edlib_result) * (size_t)std::max(n_pairs, 1), ctx->stream));
     HS_CUDA(ctx, hs_alloc(ctx, &d_bm, bmw));
-    HS_CUDA(ctx, hs_alloc(ctx, &d_counter, 4));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_counter, 8));
+    uint8_t* d_route = nullptr;
+    int32_t *d_alpha_len = nullptr, *d_plist = nullptr, *d_tasks = nullptr;
+    unsigned int* d_batch_alpha = nullptr;
+    HS_CUDA(ctx, hs_alloc(ctx, &d_route, n_pairs));
+    HS_CUDA(ctx, hs_h2d(ctx, d_route, route.data(), n_pairs));
+    EdArgs a;
+    // tasks of the packed launches: pairs of one block count, floor(32 / blocks) to a warp
+    std::vector<int32_t> plist, tasks;
+    auto build_tasks = [&](int* grid_packed) -> cudaError_t {
+        int64_t cnt[ED_PACK_MAXBLOCKS + 2] = {0};
+        for (int i = 0; i < n_pairs; i++)
+            if (route[i] == ED_ROUTE_PACKED) cnt[(query_off[i + 1] - query_off[i] + 63) / 64 + 1]++;
+        for (int c = 1; c <= ED_PACK_MAXBLOCKS + 1; c++) cnt[c] += cnt[c - 1];
+        const int64_t total = cnt[ED_PACK_MAXBLOCKS + 1];
+        plist.assign((size_t)total, 0);
+        tasks.clear();
+        for (int c = 1; c <= ED_PACK_MAXBLOCKS; c++) {
+            const int per = 32 / c;
+            for (int64_t f = cnt[c]; f < cnt[c + 1]; f += per) {
+                tasks.push_back((int32_t)f);
+                tasks.push_back((c << 8) | (int32_t)std::min<int64_t>(per, cnt[c + 1] - f));
+            }
+        }
+        int64_t fill[ED_PACK_MAXBLOCKS + 2];
+        memcpy(fill, cnt, sizeof(fill));
+        for (int i = 0; i < n_pairs; i++)
+            if (route[i] == ED_ROUTE_PACKED) plist[(size_t)fill[(query_off[i + 1] - query_off[i] + 63) / 64]++] = i;
+        a.n_tasks = (int)(tasks.size() / 2);
+        *grid_packed = (int)std::min<int64_t>(grid, (a.n_tasks + ED_WARPS - 1) / ED_WARPS);
+        if (total == 0) return cudaSuccess;
+        cudaError_t e = hs_h2d(ctx, d_plist, plist.data(), total);
+        if (e == cudaSuccess) e = hs_h2d(ctx, d_tasks, tasks.data(), (int64_t)tasks.size());
+        return e;
+    };
+    if (n_packed > 0) {
+        HS_CUDA(ctx, hs_alloc(ctx, &d_alpha_len, n_pairs));
+        HS_CUDA(ctx, hs_alloc(ctx, &d_plist, n_packed));
+        HS_CUDA(ctx, hs_alloc(ctx, &d_tasks, 2 * n_packed));
+        HS_CUDA(ctx, hs_alloc(ctx, &d_batch_alpha, 8));
+        HS_CUDA(ctx, cudaMemsetAsync(d_batch_alpha, 0, 8 * sizeof(unsigned int), ctx->stream));
+    }
     HS_CUDA(ctx, hs_alloc(ctx, &d_peq, (int64_t)n_warps * 256 * 32));
     HS_CUDA(ctx, hs_h2d(ctx, d_q, (const uint8_t*)queries, qbytes));
     HS_CUDA(ctx, hs_h2d(ctx, d_t, (const uint8_t*)targets, tbytes));
@@ -636,8 +1059,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     HS_CUDA(ctx, hs_h2d(ctx, d_to, target_off, n_pairs + 1));
     HS_CUDA(ctx, hs_h2d(ctx, d_bmo, bm_off.data(), n_pairs + 1));
     HS_CUDA(ctx, cudaMemsetAsync(d_bm, 0, sizeof(unsigned int) * bmw, ctx->stream));
-    HS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 4 * sizeof(unsigned int), ctx->stream));
-    EdArgs a;
+    HS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 8 * sizeof(unsigned int), ctx->stream));
     a.n_pairs = n_pairs;
     a.q = d_q;
     a.q_off = d_qo;
@@ -663,7 +1085,24 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     a.colv = nullptr;
     a.colpre = nullptr;
     a.col_stride = 0;
-    HS_KERNEL(ctx, "edlib_phase_a_kernel", edlib_phase_a_kernel<false><<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
+    a.route = d_route;
+    a.alpha_len = d_alpha_len;
+    a.batch_alpha = d_batch_alpha;
+    a.plist = d_plist;
+    a.tasks = d_tasks;
+    a.n_tasks = 0;
+    if (n_ordinary > 0)
+        HS_KERNEL(ctx, "edlib_phase_a_kernel", edlib_phase_a_kernel<false><<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
+    if (n_packed > 0) {
+        int grid_packed = 0;
+        HS_KERNEL(ctx, "edlib_alphabet_kernel",
+                  edlib_alphabet_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(n_pairs, d_q, d_qo, d_t, d_to, d_alpha_len,
+                                                                                  d_batch_alpha));
+        HS_CUDA(ctx, build_tasks(&grid_packed));
+        a.counter = d_counter + 4;
+        HS_KERNEL(ctx, "edlib_phase_a_kernel<packed>",
+                  edlib_phase_a_packed_kernel<<<grid_packed, ED_WARPS * 32, 0, ctx->stream>>>(a));
+    }
     // scratch of the LONG launches, sized for the pairs of the list at hand
     int32_t* d_list = nullptr;
     uint8_t* d_hbuf = nullptr;
@@ -731,8 +1170,35 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
         a.aln_tmp = d_aln_tmp;
         a.aln_tmp_off = d_tmpo;
         a.trace = d_trace;
+        // who does phase B: the packed launch keeps the pairs whose few locations and short path fit its shared slab
+        n_ordinary = 0;
+        n_packed = 0;
+        for (int i = 0; i < n_pairs; i++) {
+            if (route[i] == ED_ROUTE_LONG) continue;
+            const bool was_packed = route[i] == ED_ROUTE_PACKED;
+            route[i] = ED_ROUTE_ORDINARY;
+            if (results[i].edit_distance < 0) {
+                route[i] = ED_ROUTE_NONE;
+                continue;
+            }
+            if (was_packed && results[i].n_locations <= ED_PACK_MAXLOC) {
+                const int64_t m = query_off[i + 1] - query_off[i], n = target_off[i + 1] - target_off[i];
+                const int64_t nb = (m + 63) / 64, bound = std::min<int64_t>(n, m + results[i].edit_distance);
+                if (task < 2 || nb * bound * 16 * (32 / nb) <= ED_TRACE_BYTES) route[i] = ED_ROUTE_PACKED;
+            }
+            if (route[i] == ED_ROUTE_PACKED) n_packed++; else n_ordinary++;
+        }
+        HS_CUDA(ctx, hs_h2d(ctx, d_route, route.data(), n_pairs));
         a.counter = d_counter + 1;
-        HS_KERNEL(ctx, "edlib_phase_b_kernel", edlib_phase_b_kernel<false><<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
+        if (n_ordinary > 0)
+            HS_KERNEL(ctx, "edlib_phase_b_kernel", edlib_phase_b_kernel<false><<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
+        if (n_packed > 0) {
+            int grid_packed = 0;
+            HS_CUDA(ctx, build_tasks(&grid_packed));
+            a.counter = d_counter + 5;
+            HS_KERNEL(ctx, "edlib_phase_b_kernel<packed>",
+                      edlib_phase_b_packed_kernel<<<grid_packed, ED_WARPS * 32, 0, ctx->stream>>>(a));
+        }
         HS_CUDA(ctx, hs_d2h(ctx, results, d_res, n_pairs));
         if (task == 2 || !long_list.empty()) {
             // the LONG launch: long queries, and the pairs whose path turned out to lie at or above edlib's 1 MiB switch
@@ -774,6 +1240,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     hs_free(ctx, d_q); hs_free(ctx, d_t); hs_free(ctx, d_qo); hs_free(ctx, d_to); hs_free(ctx, d_bmo);
     hs_free(ctx, d_res); hs_free(ctx, d_bm); hs_free(ctx, d_counter); hs_free(ctx, d_peq); hs_free(ctx, d_ends);
     hs_free(ctx, d_starts); hs_free(ctx, d_aln_tmp); hs_free(ctx, d_tmpo); hs_free(ctx, d_trace); hs_free(ctx, d_aln);
+    hs_free(ctx, d_route); hs_free(ctx, d_alpha_len); hs_free(ctx, d_plist); hs_free(ctx, d_tasks); hs_free(ctx, d_batch_alpha);
     hs_free(ctx, d_scan); hs_free(ctx, d_list); hs_free(ctx, d_hbuf); hs_free(ctx, d_colv); hs_free(ctx, d_colpre);
     return rc;
 }
