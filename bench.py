@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--e2e-groups", type=int, default=1, help="groups of contig chunks the e2e path cuts a step's batch into")
     ap.add_argument("--strong", action="store_true", help="strong scaling: ONE workload (same seed on every rank) dealt "
                     "to the ranks by sharding.lpt_assign; value = all columns / max-over-ranks time")
+    ap.add_argument("--only-realign", action="store_true", help="development: run the realign stage alone and print it")
     ap.add_argument("--no-stages", action="store_true", help="skip the side stages (realign is always measured)")
     ap.add_argument("--wall-ref-runs", type=int, default=3, help="runs of the reference HS_call_variants (median reported)")
     ap.add_argument("--wall-chunks", type=int, default=0, help="chunks in the HS_call_variants wall-time stage (0 = all, -1 = skip)")
@@ -730,6 +731,11 @@ def main():
     n_cols = int(packed.contig_len.sum())
     ctx = api.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    if args.only_realign:
+        realign = run_realign(ctx, stream, chunks, args, verify=(rank == 0 and world == 1))
+        if rank == 0:
+            print(json.dumps({"only_realign": True, "bpl": os.environ.get("HSGPU_EDLIB_BPL"), "realign": realign}))
+        return
 
     # ---- the final partitions of every chunk (loops 1-2 of keep_only_robust_variants: sequential host C++, an INPUT
     # of the C ABI's filter stage): built once from a first build + rank, outside every timed region ----

@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -36,8 +37,10 @@
 #define ED_MAXBLOCKS 32     // one 64-row block per lane -> queries up to 2048 in one strip
 #define ED_MAX_QUERY (1 << 20)
 #define ED_STACK 40         // Hirschberg parts waiting per warp (the target halves at every level)
-#define ED_PACK_MAXBLOCKS 16  // queries up to 1024 share a warp with others of the same block count
-#define ED_PACK_MAXLOC 4      // ... as long as they have few end locations (the start-location sweeps run in step)
+#define ED_PACK_MAXBLOCKS 32  // queries up to 2048 share a warp with others of the same block count
+#define ED_PACK_MAXBPL 4      // blocks of 64 rows stacked in one lane
+#define ED_PACK_MAXLOC 15     // ... as long as they have few end locations (the start-location sweeps run in step;
+                              // phase B groups pairs of equal location count)
 enum { ED_ROUTE_ORDINARY = 0, ED_ROUTE_PACKED = 1, ED_ROUTE_LONG = 2, ED_ROUTE_NONE = 3 };
 #define ED_SMEM_SYMS 8      // alphabets up to this size keep Peq in shared memory
 #define ED_TRACE_BYTES (52429ll * 16)  // per-warp traceback slab: blocks*columns < 2^20/20 entries of 16 B
@@ -66,6 +69,8 @@ struct EdArgs {
     const int32_t* plist;         // pairs in task order
     const int32_t* tasks;         // per task: first index into plist, (blocks << 8) | pairs
     int n_tasks;
+    uint8_t* ptrace;              // per resident warp of the packed phase B: ptrace_stride bytes shared by its groups
+    int64_t ptrace_stride;
     // LONG instantiations only
     const int32_t* list;          // pairs to work on
     int n_list;
@@ -362,13 +367,21 @@ __device__ int traceback(const ulonglong2* trace, const uint8_t* q, int m, const
     return len;
 }
 
-// ---- packed form: floor(32 / blocks) pairs of the same block count per warp -----------------------------
+// ---- packed form: several pairs per warp, several blocks per lane ------------------------------------------
 // The in-pipeline realignment is a <= 300-base query against a ~2.3 kb window (reference src/create_new_contigs.cpp:
-// 557-630): 5 blocks, so one pair per warp leaves 27 lanes idle. Here lane = (group, block): each group of `nb` lanes
-// runs its own pair's wavefront, all groups in step. One symbol table serves the whole batch (the numbering of the
-// symbols never shows in edlib's results; the per-pair alphabet size comes from edlib_alphabet_kernel).
+// 557-630): 5 blocks, so one pair per warp leaves 27 lanes idle; the 1536-base chunks of the benchmark shape fill 24.
+// Here a pair of `nb` blocks takes gl = ceil(nb / BPL) lanes (BPL = 1..4 blocks of 64 rows per lane, stacked: the
+// horizontal delta between the blocks of a lane stays in a register) and a warp runs floor(32 / gl) pairs of the same
+// block count, all groups in step: 1536 bases = 24 blocks = 8 lanes x 3 blocks, four pairs per warp, no idle lane,
+// one shuffle per three block steps. One symbol table serves the whole batch (the numbering of the symbols never
+// shows in edlib's results; the per-pair alphabet size comes from edlib_alphabet_kernel).
+// Traceback vectors are kept only where the path can be: a cell (row i, column j) of an alignment of distance d has
+// |i - j| <= d, so block b (rows 64b+1..64b+64) needs columns 64b-d .. 64b+63+d (0-based) -- band_w = min(n, 64 + 2d)
+// columns per block starting at band_first, instead of all n.
+__device__ __forceinline__ int band_first(int b, int d, int band_w, int n) { return min(max(64 * b - d, 0), n - band_w); }
+
 struct PackLane {
-    int nb, bl, ghead;  // blocks per pair, this lane's block, first lane of its group
+    int nb, gl, bl, ghead;  // blocks per pair, lanes per pair, this lane's place in its group, first lane of the group
     bool active;
 };
 
@@ -414,16 +427,20 @@ __device__ int build_batch_lut(const unsigned int* batch_alpha, uint8_t* lut, in
     return base;
 }
 
-// every lane fills the Peq column of its own (pair, block)
+// Peq of the packed kernels: [sym][k][lane], k = the lane's k-th block; every lane fills its own entries
+template <int BPL>
 __device__ void build_peq_packed(uint64_t* peq, const uint8_t* lut, int lane, const PackLane& g, const uint8_t* q, int m,
                                  int n_sym, bool reversed) {
-    for (int sym = 0; sym < n_sym; sym++) peq[sym * 32 + lane] = 0ull;
+    for (int i = 0; i < n_sym * BPL; i++) peq[i * 32 + lane] = 0ull;
     if (g.active) {
-        const int r0 = g.bl * 64;
-        const int r1 = min(m, r0 + 64);
-        for (int r = r0; r < r1; r++) {
-            const int c = reversed ? q[m - 1 - r] : q[r];
-            peq[lut[c] * 32 + lane] |= 1ull << (r - r0);
+#pragma unroll
+        for (int k = 0; k < BPL; k++) {
+            const int r0 = (g.bl * BPL + k) * 64;
+            const int r1 = min(m, r0 + 64);
+            for (int r = r0; r < r1; r++) {
+                const int c = reversed ? q[m - 1 - r] : q[r];
+                peq[(lut[c] * BPL + k) * 32 + lane] |= 1ull << (r - r0);
+            }
         }
     }
     __syncwarp();
@@ -431,13 +448,21 @@ __device__ void build_peq_packed(uint64_t* peq, const uint8_t* lut, int lane, co
 
 // dp_pass with per-lane pair parameters; n_max = the longest target of the warp's groups. The result is valid in the
 // lanes of the group it belongs to.
-template <int KIND>
+template <int KIND, int BPL>
 __device__ PassOut dp_pass_packed(const uint64_t* peq, const uint8_t* lut, int lane, const PackLane& g, int m,
                                   const uint8_t* t, int n, int n_max, int rev_end, int start_hin, bool consider_j0,
-                                  unsigned int* bitmask, ulonglong2* trace) {
-    uint64_t Pv = ~0ull, Mv = 0ull;
+                                  unsigned int* bitmask, ulonglong2* trace, int band_d = 0, int band_w = 0) {
+    uint64_t Pv[BPL], Mv[BPL];
+    int band_lo[BPL];  // PASS_NW_STORE: first column kept of each block (band_first)
+#pragma unroll
+    for (int k = 0; k < BPL; k++) {
+        Pv[k] = ~0ull;
+        Mv[k] = 0ull;
+        band_lo[k] = band_first(g.bl * BPL + k, band_d, band_w, n);
+    }
     const int lb = (m - 1) & 63;
-    const int nb = g.nb;
+    const int gl = g.gl;
+    const int k_last = (g.nb - 1) - (gl - 1) * BPL;  // the block of the bottom row inside the group's last lane
     int score = m;
     PassOut o;
     o.best = consider_j0 ? m : 0x3fffffff;
@@ -446,30 +471,41 @@ __device__ PassOut dp_pass_packed(const uint64_t* peq, const uint8_t* lut, int l
     o.count = consider_j0 ? 1 : 0;
     unsigned int bits = consider_j0 ? 1u : 0u;
     int packed = 0;
-    // target symbols: nb at a time per group (lane bl holds symbol chunk*nb + bl), fetched one chunk ahead
+    // target symbols: gl at a time per group (lane bl holds symbol chunk*gl + bl), fetched one chunk ahead
     int tchunk = 0, tnext = 0;
     if (g.active && g.bl < n) tchunk = lut[rev_end >= 0 ? t[rev_end - g.bl] : t[g.bl]];
-    if (g.active && nb + g.bl < n) tnext = lut[rev_end >= 0 ? t[rev_end - nb - g.bl] : t[nb + g.bl]];
+    if (g.active && gl + g.bl < n) tnext = lut[rev_end >= 0 ? t[rev_end - gl - g.bl] : t[gl + g.bl]];
     int sc = 0;
-    const int steps = n_max + nb - 1;
+    const int steps = n_max + gl - 1;
     for (int s = 0; s < steps; s++) {
         const int sym0 = __shfl_sync(0xffffffffu, tchunk, g.ghead + sc);
         const int pk = __shfl_up_sync(0xffffffffu, packed, 1);
         const int sym = g.bl == 0 ? sym0 : (pk >> 2);
-        const int hin = g.bl == 0 ? start_hin : ((pk & 3) - 1);
+        int hin = g.bl == 0 ? start_hin : ((pk & 3) - 1);
         const int c = s - g.bl;
         if (g.active && c >= 0 && c < n) {
-            uint64_t Eq = peq[sym * 32 + lane];
-            const uint64_t hneg = hin < 0 ? 1ull : 0ull, hpos = hin > 0 ? 1ull : 0ull;
-            const uint64_t Xv = Eq | Mv;
-            Eq |= hneg;
-            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-            uint64_t Ph = Mv | ~(Xh | Pv);
-            uint64_t Mh = Pv & Xh;
-            const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
-            packed = (sym << 2) | (hout + 1);
-            if (g.bl == nb - 1) {
-                score += (int)((Ph >> lb) & 1ull) - (int)((Mh >> lb) & 1ull);
+            uint64_t phs = 0, mhs = 0;  // Ph / Mh of the block that holds the bottom row
+#pragma unroll
+            for (int k = 0; k < BPL; k++) {
+                uint64_t Eq = peq[(sym * BPL + k) * 32 + lane];
+                const uint64_t hneg = hin < 0 ? 1ull : 0ull, hpos = hin > 0 ? 1ull : 0ull;
+                const uint64_t Xv = Eq | Mv[k];
+                Eq |= hneg;
+                const uint64_t Xh = (((Eq & Pv[k]) + Pv[k]) ^ Pv[k]) | Eq;
+                uint64_t Ph = Mv[k] | ~(Xh | Pv[k]);
+                uint64_t Mh = Pv[k] & Xh;
+                hin = (int)(Ph >> 63) - (int)(Mh >> 63);
+                if (k == k_last) { phs = Ph; mhs = Mh; }
+                const uint64_t Phs = (Ph << 1) | hpos;
+                const uint64_t Mhs = (Mh << 1) | hneg;
+                Pv[k] = Mhs | ~(Xv | Phs);
+                Mv[k] = Phs & Xv;
+                if (KIND == PASS_NW_STORE && g.bl * BPL + k < g.nb && (unsigned)(c - band_lo[k]) < (unsigned)band_w)
+                    trace[(size_t)(g.bl * BPL + k) * band_w + (c - band_lo[k])] = make_ulonglong2(Pv[k], Ph);
+            }
+            packed = (sym << 2) | (hin + 1);
+            if (g.bl == gl - 1) {
+                score += (int)((phs >> lb) & 1ull) - (int)((mhs >> lb) & 1ull);
                 const int j = c + 1;
                 if (KIND == PASS_SEMIGLOBAL) {
                     if ((j & 31) == 0) bits = 0;
@@ -483,21 +519,16 @@ __device__ PassOut dp_pass_packed(const uint64_t* peq, const uint8_t* lut, int l
                     o.best = score;
                 }
             }
-            const uint64_t Phs = (Ph << 1) | hpos;
-            const uint64_t Mhs = (Mh << 1) | hneg;
-            Pv = Mhs | ~(Xv | Phs);
-            Mv = Phs & Xv;
-            if (KIND == PASS_NW_STORE) trace[(size_t)g.bl * n + c] = make_ulonglong2(Pv, Ph);
         }
-        if (++sc == nb) {
+        if (++sc == gl) {
             sc = 0;
             tchunk = tnext;
-            const int idx = s + 1 + nb + g.bl;
+            const int idx = s + 1 + gl + g.bl;
             tnext = 0;
             if (g.active && idx < n) tnext = lut[rev_end >= 0 ? t[rev_end - idx] : t[idx]];
         }
     }
-    const int rl = g.ghead + nb - 1;
+    const int rl = g.ghead + gl - 1;
     o.best = __shfl_sync(0xffffffffu, o.best, rl);
     o.first_j = __shfl_sync(0xffffffffu, o.first_j, rl);
     o.last_j = __shfl_sync(0xffffffffu, o.last_j, rl);
@@ -505,10 +536,10 @@ __device__ PassOut dp_pass_packed(const uint64_t* peq, const uint8_t* lut, int l
     return o;
 }
 
-// the groups of a warp walk their paths in step (same rules as traceback above; the window is nb columns wide)
+// the groups of a warp walk their paths in step (same rules as traceback above; the window is gl columns wide)
 __device__ int traceback_packed(const ulonglong2* trace, const uint8_t* q, int m, const uint8_t* t, int n, uint8_t* out,
-                                const PackLane& g) {
-    const int nb = g.nb;
+                                const PackLane& g, int band_d, int band_w) {
+    const int gl = g.gl;
     int i = g.active ? m : 0, j = g.active ? n : 0, len = 0, fl = 0;
     unsigned int pend = 0;  // op of output position len - fl + bl
     int win_block = -1, win_j0 = -1;
@@ -517,12 +548,12 @@ __device__ int traceback_packed(const ulonglong2* trace, const uint8_t* q, int m
         const bool go = i > 0 && j > 0;
         if (go) {
             const int b = (i - 1) >> 6;
-            if (b != win_block || j > win_j0 || j <= win_j0 - nb) {
+            if (b != win_block || j > win_j0 || j <= win_j0 - gl) {
                 win_block = b;
                 win_j0 = j;
-                const int jj = j - g.bl;  // lane bl of the group holds column j0 - bl
+                const int x = j - g.bl - 1 - band_first(b, band_d, band_w, n);  // lane bl of the group holds column j0 - bl
                 ulonglong2 v = make_ulonglong2(0ull, 0ull);
-                if (jj >= 1) v = trace[(size_t)b * n + (jj - 1)];
+                if ((unsigned)x < (unsigned)band_w) v = trace[(size_t)b * band_w + x];  // columns off the band are never walked
                 wPv = v.x;
                 wPh = v.y;
             }
@@ -539,9 +570,9 @@ __device__ int traceback_packed(const ulonglong2* trace, const uint8_t* q, int m
             j -= op != 1;
             if (fl == g.bl) pend = (unsigned)op;
             len++;
-            if (++fl == nb) {
+            if (++fl == gl) {
                 fl = 0;
-                out[len - nb + g.bl] = (uint8_t)pend;
+                out[len - gl + g.bl] = (uint8_t)pend;
             }
         }
     }
@@ -549,38 +580,41 @@ __device__ int traceback_packed(const ulonglong2* trace, const uint8_t* q, int m
         if (g.bl < fl) out[len - fl + g.bl] = (uint8_t)pend;
         const int rest = i > 0 ? i : j;
         const uint8_t rest_op = i > 0 ? 1 : 2;
-        for (int x = g.bl; x < rest; x += nb) out[len + x] = rest_op;
+        for (int x = g.bl; x < rest; x += gl) out[len + x] = rest_op;
         len += rest;
     }
     return len;
 }
 
+template <int BPL>
 __device__ __forceinline__ PackLane pack_lane(int lane, int nb, int cnt) {
     PackLane g;
     g.nb = nb;
-    const int grp = lane / nb;
-    g.bl = lane - grp * nb;
-    g.ghead = grp * nb;
+    g.gl = (nb + BPL - 1) / BPL;
+    const int grp = lane / g.gl;
+    g.bl = lane - grp * g.gl;
+    g.ghead = grp * g.gl;
     g.active = grp < cnt;
     return g;
 }
 
+template <int BPL>
 __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_packed_kernel(EdArgs a) {
-    __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32];
+    __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32 * BPL];
     __shared__ uint8_t s_lut[ED_WARPS][256];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gw = blockIdx.x * ED_WARPS + wid;
     const uint8_t* lut = s_lut[wid];
     const int n_sym = build_batch_lut(a.batch_alpha, s_lut[wid], lane);
-    uint64_t* peq = n_sym <= ED_SMEM_SYMS ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32;
+    uint64_t* peq = n_sym <= ED_SMEM_SYMS ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32 * ED_PACK_MAXBPL;
     for (;;) {
         int task = 0;
         if (lane == 0) task = (int)atomicAdd(a.counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= a.n_tasks) break;
         const int first = a.tasks[2 * task], nbc = a.tasks[2 * task + 1];
-        const PackLane g = pack_lane(lane, nbc >> 8, nbc & 255);
-        const int grp = lane / g.nb;
+        const PackLane g = pack_lane<BPL>(lane, nbc >> 8, nbc & 255);
+        const int grp = lane / g.gl;
         const int pair = g.active ? a.plist[first + grp] : 0;
         const uint8_t* q = a.q + a.q_off[pair];
         const uint8_t* t = a.t + a.t_off[pair];
@@ -588,7 +622,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_packed_kernel(EdA
         const int n = g.active ? (int)(a.t_off[pair + 1] - a.t_off[pair]) : 0;
         unsigned int* bm = a.bitmask + a.bm_off[pair];
         __syncwarp();
-        build_peq_packed(peq, lut, lane, g, q, m, n_sym, false);
+        build_peq_packed<BPL>(peq, lut, lane, g, q, m, n_sym, false);
         hsgpu_edlib_result r;
         r.status = 0;
         r.edit_distance = -1;
@@ -606,7 +640,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_packed_kernel(EdA
             const int n_max = __reduce_max_sync(0xffffffffu, run ? n : 0);
             PackLane gr = g;
             gr.active = run;
-            const PassOut o = dp_pass_packed<PASS_NW_SCORE>(peq, lut, lane, gr, m, t, n, n_max, -1, 1, false, nullptr, nullptr);
+            const PassOut o = dp_pass_packed<PASS_NW_SCORE, BPL>(peq, lut, lane, gr, m, t, n, n_max, -1, 1, false, nullptr, nullptr);
             if (run && o.best <= kk) {
                 r.edit_distance = o.best;
                 r.n_locations = 1;
@@ -615,8 +649,8 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_packed_kernel(EdA
         } else {
             const bool j0 = (m & 63) != 0;  // W > 0
             const int n_max = __reduce_max_sync(0xffffffffu, n);
-            const PassOut o = dp_pass_packed<PASS_SEMIGLOBAL>(peq, lut, lane, g, m, t, n, n_max, -1, a.mode == 2 ? 0 : 1, j0,
-                                                              bm, nullptr);
+            const PassOut o = dp_pass_packed<PASS_SEMIGLOBAL, BPL>(peq, lut, lane, g, m, t, n, n_max, -1, a.mode == 2 ? 0 : 1, j0,
+                                                                   bm, nullptr);
             if (a.mode == 2) kk = min(kk, m);  // :565-567
             if (o.best <= kk) {
                 r.edit_distance = o.best;
@@ -628,22 +662,23 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_packed_kernel(EdA
     }
 }
 
+template <int BPL>
 __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdArgs a) {
-    __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32];
+    __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32 * BPL];
     __shared__ uint8_t s_lut[ED_WARPS][256];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gw = blockIdx.x * ED_WARPS + wid;
     const uint8_t* lut = s_lut[wid];
     const int n_sym = build_batch_lut(a.batch_alpha, s_lut[wid], lane);
-    uint64_t* peq = n_sym <= ED_SMEM_SYMS ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32;
+    uint64_t* peq = n_sym <= ED_SMEM_SYMS ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32 * ED_PACK_MAXBPL;
     for (;;) {
         int task = 0;
         if (lane == 0) task = (int)atomicAdd(a.counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= a.n_tasks) break;
         const int first = a.tasks[2 * task], nbc = a.tasks[2 * task + 1];
-        const PackLane g = pack_lane(lane, nbc >> 8, nbc & 255);
-        const int grp = lane / g.nb;
+        const PackLane g = pack_lane<BPL>(lane, nbc >> 8, nbc & 255);
+        const int grp = lane / g.gl;
         const int pair = g.active ? a.plist[first + grp] : 0;
         hsgpu_edlib_result r = a.res[pair];
         const uint8_t* q = a.q + a.q_off[pair];
@@ -672,19 +707,21 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdA
         if (a.task == 0) continue;
         r.has_start_locations = 1;
         if (a.mode == 2) {
-            build_peq_packed(peq, lut, lane, g, q, m, n_sym, true);
+            build_peq_packed<BPL>(peq, lut, lane, g, q, m, n_sym, true);
             const bool j0c = (m & 63) != 0;
             const int loc_max = __reduce_max_sync(0xffffffffu, n_loc);
             for (int l = 0; l < loc_max; l++) {
                 const int e = l < n_loc ? ends[l] : -1;
                 PackLane gr = g;
                 gr.active = g.active && e >= 0;
-                const int n_max = __reduce_max_sync(0xffffffffu, gr.active ? e + 1 : 0);
-                const PassOut o = dp_pass_packed<PASS_REV_SHW>(peq, lut, lane, gr, m, t, e + 1, n_max, e, 1, j0c, nullptr, nullptr);
+                // an alignment of distance d takes at most m + d target symbols: no later column can reach d again
+                const int nrev = min(e + 1, m + r.edit_distance);
+                const int n_max = __reduce_max_sync(0xffffffffu, gr.active ? nrev : 0);
+                const PassOut o = dp_pass_packed<PASS_REV_SHW, BPL>(peq, lut, lane, gr, m, t, nrev, n_max, e, 1, j0c, nullptr, nullptr);
                 if (g.bl == 0 && l < n_loc) starts[l] = e >= 0 ? e - (o.last_j - 1) : 0;  // :254-256 last position
             }
         } else if (g.active) {
-            for (int l = g.bl; l < n_loc; l += g.nb) starts[l] = 0;
+            for (int l = g.bl; l < n_loc; l += g.gl) starts[l] = 0;
         }
         __syncwarp();
         if (a.task == 2) {
@@ -693,7 +730,8 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdA
             uint8_t* out = a.aln_tmp + a.aln_tmp_off[pair];
             // the groups share the warp's traceback slab
             const bool walk = g.active && an > 0;
-            const long long need = walk ? (long long)g.nb * an : 0;  // entries of 16 bytes
+            const int band_d = r.edit_distance, band_w = min(an, 64 + 2 * band_d);
+            const long long need = walk ? (long long)g.nb * band_w : 0;  // entries of 16 bytes
             const long long mine = g.bl == 0 ? need : 0;
             long long incl = mine;
 #pragma unroll
@@ -702,20 +740,21 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdA
                 if (lane >= d) incl += up;
             }
             const long long base = __shfl_sync(0xffffffffu, incl - mine, g.ghead);
-            PackLane gw_ = g;
-            gw_.active = walk && (base + need) * 16 <= ED_TRACE_BYTES;
-            if (walk && !gw_.active) r.status = 1;  // cannot happen: the host routes by the same bound
-            ulonglong2* trace = reinterpret_cast<ulonglong2*>(a.trace + (size_t)gw * ED_TRACE_BYTES) + base;
+            PackLane gt = g;
+            gt.active = walk && (base + need) * 16 <= a.ptrace_stride;
+            if (walk && !gt.active) r.status = 1;  // cannot happen: the host sizes the slab by an upper bound of the same sum
+            ulonglong2* trace = reinterpret_cast<ulonglong2*>(a.ptrace + (size_t)gw * a.ptrace_stride) + base;
             if (g.active && an <= 0) {  // obtainAlignment's empty-target case (:1173-1180)
-                for (int i = g.bl; i < m; i += g.nb) out[i] = 1;
+                for (int i = g.bl; i < m; i += g.gl) out[i] = 1;
                 r.alignment_length = m;
             }
-            build_peq_packed(peq, lut, lane, g, q, m, n_sym, false);
-            const int n_max = __reduce_max_sync(0xffffffffu, gw_.active ? an : 0);
-            dp_pass_packed<PASS_NW_STORE>(peq, lut, lane, gw_, m, t + s0, an, n_max, -1, 1, false, nullptr, trace);
+            build_peq_packed<BPL>(peq, lut, lane, g, q, m, n_sym, false);
+            const int n_max = __reduce_max_sync(0xffffffffu, gt.active ? an : 0);
+            dp_pass_packed<PASS_NW_STORE, BPL>(peq, lut, lane, gt, m, t + s0, an, n_max, -1, 1, false, nullptr, trace, band_d,
+                                               band_w);
             __syncwarp();
-            const int len = traceback_packed(trace, q, m, t + s0, an, out, gw_);
-            if (gw_.active) r.alignment_length = len;
+            const int len = traceback_packed(trace, q, m, t + s0, an, out, gt, band_d, band_w);
+            if (gt.active) r.alignment_length = len;
             __syncwarp();
         }
         if (g.active && g.bl == 0) a.res[pair] = r;
@@ -909,7 +948,9 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_kernel(EdArgs a) 
                 const int e = ends[l];
                 int st = 0;
                 if (e >= 0) {
-                    const PassOut o = dp_pass<PASS_REV_SHW, LONG>(w, m, nb, t, e + 1, e, 1, j0c, nullptr, nullptr);
+                    // an alignment of distance d takes at most m + d target symbols: no later column can reach d again
+                    const PassOut o = dp_pass<PASS_REV_SHW, LONG>(w, m, nb, t, min(e + 1, m + r.edit_distance), e, 1, j0c,
+                                                                  nullptr, nullptr);
                     st = e - (o.last_j - 1);  // :254-256 last position
                 }
                 if (lane == 0) starts[l] = st;
@@ -995,7 +1036,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     const int64_t qbytes = query_off[n_pairs], tbytes = target_off[n_pairs];
     const int grid = ctx->sm_count * 4;
     const int n_warps = grid * ED_WARPS;
-    uint8_t *d_q = nullptr, *d_t = nullptr, *d_aln_tmp = nullptr, *d_trace = nullptr, *d_aln = nullptr;
+    uint8_t *d_q = nullptr, *d_t = nullptr, *d_aln_tmp = nullptr, *d_trace = nullptr, *d_aln = nullptr, *d_ptrace = nullptr;
     int64_t *d_qo = nullptr, *d_to = nullptr, *d_bmo = nullptr, *d_tmpo = nullptr, *d_scan = nullptr;
     hsgpu_edlib_result* d_res = nullptr;
     unsigned int *d_bm = nullptr, *d_counter = nullptr;
@@ -1010,36 +1051,75 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     // phase A fills some of the fields; the whole struct travels to the host after it
     HS_CUDA(ctx, cudaMemsetAsync(d_res, 0, sizeof(hsgpu_edlib_result) * (size_t)std::max(n_pairs, 1), ctx->stream));
     HS_CUDA(ctx, hs_alloc(ctx, &d_bm, bmw));
-    HS_CUDA(ctx, hs_alloc(ctx, &d_counter, 8));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_counter, 32));
     uint8_t* d_route = nullptr;
     int32_t *d_alpha_len = nullptr, *d_plist = nullptr, *d_tasks = nullptr;
     unsigned int* d_batch_alpha = nullptr;
     HS_CUDA(ctx, hs_alloc(ctx, &d_route, n_pairs));
     HS_CUDA(ctx, hs_h2d(ctx, d_route, route.data(), n_pairs));
     EdArgs a;
-    // tasks of the packed launches: pairs of one block count, floor(32 / blocks) to a warp
+    // tasks of the packed launches: pairs of one block count, floor(32 / lanes per pair) to a warp. Blocks per lane:
+    // what a block step costs (core work per block + the per-step overhead of a lane, shared by the warp's pairs)
+    static int bpl_of[ED_PACK_MAXBLOCKS + 1];
+    static std::once_flag bpl_once;
+    std::call_once(bpl_once, [] {
+        const int forced = getenv("HSGPU_EDLIB_BPL") ? atoi(getenv("HSGPU_EDLIB_BPL")) : 0;
+        for (int nb = 1; nb <= ED_PACK_MAXBLOCKS; nb++) {
+            double best = 1e30;
+            for (int b = 1; b <= ED_PACK_MAXBPL; b++) {
+                const int gl = (nb + b - 1) / b;
+                const double cost = (34.0 * b + 28.0) / (32 / gl);
+                if (cost < best - 1e-9) { best = cost; bpl_of[nb] = b; }
+            }
+            if (forced >= 1 && forced <= ED_PACK_MAXBPL) bpl_of[nb] = forced;
+        }
+    });
     std::vector<int32_t> plist, tasks;
-    auto build_tasks = [&](int* grid_packed) -> cudaError_t {
-        int64_t cnt[ED_PACK_MAXBLOCKS + 2] = {0};
+    int task_first[ED_PACK_MAXBPL + 2];  // tasks of BPL = b: [task_first[b], task_first[b + 1])
+    int64_t ptrace_stride = 0;
+    // key of a pair: (blocks per lane, blocks, end locations) -- counting sort, then tasks of equal block count
+    auto build_tasks = [&](bool phase_b) -> cudaError_t {
+        const int NL = ED_PACK_MAXLOC + 1, NB = ED_PACK_MAXBLOCKS + 1;
+        const int NK = (ED_PACK_MAXBPL + 1) * NB * NL;
+        std::vector<int64_t> cnt((size_t)NK + 1, 0);
+        auto key = [&](int i) {
+            const int nb = (int)((query_off[i + 1] - query_off[i] + 63) / 64);
+            return (bpl_of[nb] * NB + nb) * NL + (phase_b ? results[i].n_locations : 0);
+        };
         for (int i = 0; i < n_pairs; i++)
-            if (route[i] == ED_ROUTE_PACKED) cnt[(query_off[i + 1] - query_off[i] + 63) / 64 + 1]++;
-        for (int c = 1; c <= ED_PACK_MAXBLOCKS + 1; c++) cnt[c] += cnt[c - 1];
-        const int64_t total = cnt[ED_PACK_MAXBLOCKS + 1];
+            if (route[i] == ED_ROUTE_PACKED) cnt[(size_t)key(i) + 1]++;
+        for (int c = 1; c <= NK; c++) cnt[c] += cnt[c - 1];
+        const int64_t total = cnt[NK];
         plist.assign((size_t)total, 0);
+        std::vector<int64_t> fill(cnt);
+        for (int i = 0; i < n_pairs; i++)
+            if (route[i] == ED_ROUTE_PACKED) plist[(size_t)fill[(size_t)key(i)]++] = i;
         tasks.clear();
-        for (int c = 1; c <= ED_PACK_MAXBLOCKS; c++) {
-            const int per = 32 / c;
-            for (int64_t f = cnt[c]; f < cnt[c + 1]; f += per) {
-                tasks.push_back((int32_t)f);
-                tasks.push_back((c << 8) | (int32_t)std::min<int64_t>(per, cnt[c + 1] - f));
+        ptrace_stride = 0;
+        for (int b = 1; b <= ED_PACK_MAXBPL; b++) {
+            task_first[b] = (int)(tasks.size() / 2);
+            for (int nb = 1; nb <= ED_PACK_MAXBLOCKS; nb++) {
+                const int per = 32 / ((nb + b - 1) / b);
+                const int64_t lo = cnt[(size_t)(b * NB + nb) * NL], hi = cnt[(size_t)(b * NB + nb + 1) * NL];
+                for (int64_t f = lo; f < hi; f += per) {
+                    const int n_in = (int)std::min<int64_t>(per, hi - f);
+                    tasks.push_back((int32_t)f);
+                    tasks.push_back((nb << 8) | n_in);
+                    if (phase_b && task == 2) {  // the task's groups share one traceback slab
+                        int64_t need = 0;
+                        for (int x = 0; x < n_in; x++) {
+                            const int i = plist[(size_t)(f + x)];
+                            const int64_t m = query_off[i + 1] - query_off[i], n = target_off[i + 1] - target_off[i];
+                            const int64_t d = results[i].edit_distance;  // band of the path: see band_first
+                            need += nb * std::min<int64_t>(std::min<int64_t>(n, m + d), 64 + 2 * d) * 16;
+                        }
+                        ptrace_stride = std::max(ptrace_stride, need);
+                    }
+                }
             }
         }
-        int64_t fill[ED_PACK_MAXBLOCKS + 2];
-        memcpy(fill, cnt, sizeof(fill));
-        for (int i = 0; i < n_pairs; i++)
-            if (route[i] == ED_ROUTE_PACKED) plist[(size_t)fill[(query_off[i + 1] - query_off[i] + 63) / 64]++] = i;
-        a.n_tasks = (int)(tasks.size() / 2);
-        *grid_packed = (int)std::min<int64_t>(grid, (a.n_tasks + ED_WARPS - 1) / ED_WARPS);
+        task_first[ED_PACK_MAXBPL + 1] = (int)(tasks.size() / 2);
+        ptrace_stride = (ptrace_stride + 255) & ~255ll;
         if (total == 0) return cudaSuccess;
         cudaError_t e = hs_h2d(ctx, d_plist, plist.data(), total);
         if (e == cudaSuccess) e = hs_h2d(ctx, d_tasks, tasks.data(), (int64_t)tasks.size());
@@ -1052,14 +1132,14 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
         HS_CUDA(ctx, hs_alloc(ctx, &d_batch_alpha, 8));
         HS_CUDA(ctx, cudaMemsetAsync(d_batch_alpha, 0, 8 * sizeof(unsigned int), ctx->stream));
     }
-    HS_CUDA(ctx, hs_alloc(ctx, &d_peq, (int64_t)n_warps * 256 * 32));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_peq, (int64_t)n_warps * 256 * 32 * ED_PACK_MAXBPL));
     HS_CUDA(ctx, hs_h2d(ctx, d_q, (const uint8_t*)queries, qbytes));
     HS_CUDA(ctx, hs_h2d(ctx, d_t, (const uint8_t*)targets, tbytes));
     HS_CUDA(ctx, hs_h2d(ctx, d_qo, query_off, n_pairs + 1));
     HS_CUDA(ctx, hs_h2d(ctx, d_to, target_off, n_pairs + 1));
     HS_CUDA(ctx, hs_h2d(ctx, d_bmo, bm_off.data(), n_pairs + 1));
     HS_CUDA(ctx, cudaMemsetAsync(d_bm, 0, sizeof(unsigned int) * bmw, ctx->stream));
-    HS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 8 * sizeof(unsigned int), ctx->stream));
+    HS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 32 * sizeof(unsigned int), ctx->stream));
     a.n_pairs = n_pairs;
     a.q = d_q;
     a.q_off = d_qo;
@@ -1091,17 +1171,26 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     a.plist = d_plist;
     a.tasks = d_tasks;
     a.n_tasks = 0;
+    a.ptrace = nullptr;
+    a.ptrace_stride = 0;
     if (n_ordinary > 0)
         HS_KERNEL(ctx, "edlib_phase_a_kernel", edlib_phase_a_kernel<false><<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
     if (n_packed > 0) {
-        int grid_packed = 0;
         HS_KERNEL(ctx, "edlib_alphabet_kernel",
                   edlib_alphabet_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(n_pairs, d_q, d_qo, d_t, d_to, d_alpha_len,
                                                                                   d_batch_alpha));
-        HS_CUDA(ctx, build_tasks(&grid_packed));
-        a.counter = d_counter + 4;
-        HS_KERNEL(ctx, "edlib_phase_a_kernel<packed>",
-                  edlib_phase_a_packed_kernel<<<grid_packed, ED_WARPS * 32, 0, ctx->stream>>>(a));
+        HS_CUDA(ctx, build_tasks(false));
+        for (int b = 1; b <= ED_PACK_MAXBPL; b++) {
+            a.tasks = d_tasks + 2 * task_first[b];
+            a.n_tasks = task_first[b + 1] - task_first[b];
+            if (a.n_tasks == 0) continue;
+            a.counter = d_counter + 8 + b;
+            const int gp = (int)std::min<int64_t>(grid, (a.n_tasks + ED_WARPS - 1) / ED_WARPS);
+            if (b == 1) HS_KERNEL(ctx, "edlib_phase_a_kernel<packed,1>", edlib_phase_a_packed_kernel<1><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
+            if (b == 2) HS_KERNEL(ctx, "edlib_phase_a_kernel<packed,2>", edlib_phase_a_packed_kernel<2><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
+            if (b == 3) HS_KERNEL(ctx, "edlib_phase_a_kernel<packed,3>", edlib_phase_a_packed_kernel<3><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
+            if (b == 4) HS_KERNEL(ctx, "edlib_phase_a_kernel<packed,4>", edlib_phase_a_packed_kernel<4><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
+        }
     }
     // scratch of the LONG launches, sized for the pairs of the list at hand
     int32_t* d_list = nullptr;
@@ -1162,7 +1251,6 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
         if (task == 2) {
             HS_CUDA(ctx, hs_alloc(ctx, &d_aln_tmp, tmpb));
             HS_CUDA(ctx, hs_alloc(ctx, &d_tmpo, n_pairs + 1));
-            HS_CUDA(ctx, hs_alloc(ctx, &d_trace, (int64_t)n_warps * ED_TRACE_BYTES));
             HS_CUDA(ctx, hs_h2d(ctx, d_tmpo, tmp_off.data(), n_pairs + 1));
         }
         a.ends = d_ends;
@@ -1182,22 +1270,39 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
                 continue;
             }
             if (was_packed && results[i].n_locations <= ED_PACK_MAXLOC) {
+                // the path must lie below edlib's 1 MiB switch whatever the start location turns out to be
                 const int64_t m = query_off[i + 1] - query_off[i], n = target_off[i + 1] - target_off[i];
                 const int64_t nb = (m + 63) / 64, bound = std::min<int64_t>(n, m + results[i].edit_distance);
-                if (task < 2 || nb * bound * 16 * (32 / nb) <= ED_TRACE_BYTES) route[i] = ED_ROUTE_PACKED;
+                if (task < 2 || (2 * 8 + 4) * nb * bound + 8 * bound < 1024 * 1024) route[i] = ED_ROUTE_PACKED;
             }
             if (route[i] == ED_ROUTE_PACKED) n_packed++; else n_ordinary++;
         }
         HS_CUDA(ctx, hs_h2d(ctx, d_route, route.data(), n_pairs));
         a.counter = d_counter + 1;
-        if (n_ordinary > 0)
+        if (n_ordinary > 0) {
+            if (task == 2) HS_CUDA(ctx, hs_alloc(ctx, &d_trace, (int64_t)n_warps * ED_TRACE_BYTES));
+            a.trace = d_trace;
             HS_KERNEL(ctx, "edlib_phase_b_kernel", edlib_phase_b_kernel<false><<<grid, ED_WARPS * 32, 0, ctx->stream>>>(a));
+        }
         if (n_packed > 0) {
-            int grid_packed = 0;
-            HS_CUDA(ctx, build_tasks(&grid_packed));
-            a.counter = d_counter + 5;
-            HS_KERNEL(ctx, "edlib_phase_b_kernel<packed>",
-                      edlib_phase_b_packed_kernel<<<grid_packed, ED_WARPS * 32, 0, ctx->stream>>>(a));
+            HS_CUDA(ctx, build_tasks(true));
+            // one traceback slab per resident warp, shared by the warp's pairs; at most 16 GB of them
+            const int64_t max_warps = std::max<int64_t>(ED_WARPS, (16ll << 30) / std::max<int64_t>(ptrace_stride, 1));
+            const int grid_cap = (int)std::min<int64_t>(grid, max_warps / ED_WARPS);
+            if (task == 2) HS_CUDA(ctx, hs_alloc(ctx, &d_ptrace, (int64_t)grid_cap * ED_WARPS * ptrace_stride));
+            a.ptrace = d_ptrace;
+            a.ptrace_stride = ptrace_stride;
+            for (int b = 1; b <= ED_PACK_MAXBPL; b++) {
+                a.tasks = d_tasks + 2 * task_first[b];
+                a.n_tasks = task_first[b + 1] - task_first[b];
+                if (a.n_tasks == 0) continue;
+                a.counter = d_counter + 16 + b;
+                const int gp = (int)std::min<int64_t>(grid_cap, (a.n_tasks + ED_WARPS - 1) / ED_WARPS);
+                if (b == 1) HS_KERNEL(ctx, "edlib_phase_b_kernel<packed,1>", edlib_phase_b_packed_kernel<1><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
+                if (b == 2) HS_KERNEL(ctx, "edlib_phase_b_kernel<packed,2>", edlib_phase_b_packed_kernel<2><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
+                if (b == 3) HS_KERNEL(ctx, "edlib_phase_b_kernel<packed,3>", edlib_phase_b_packed_kernel<3><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
+                if (b == 4) HS_KERNEL(ctx, "edlib_phase_b_kernel<packed,4>", edlib_phase_b_packed_kernel<4><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
+            }
         }
         HS_CUDA(ctx, hs_d2h(ctx, results, d_res, n_pairs));
         if (task == 2 || !long_list.empty()) {
@@ -1209,6 +1314,8 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
             if (!list.empty()) {
                 int grid_long = 0;
                 HS_CUDA(ctx, long_setup(list, task == 2, &grid_long));
+                if (task == 2 && !d_trace) HS_CUDA(ctx, hs_alloc(ctx, &d_trace, (int64_t)n_warps * ED_TRACE_BYTES));
+                a.trace = d_trace;
                 a.counter = d_counter + 3;
                 HS_KERNEL(ctx, "edlib_phase_b_kernel<long>",
                           edlib_phase_b_kernel<true><<<grid_long, ED_WARPS * 32, 0, ctx->stream>>>(a));
@@ -1240,7 +1347,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     hs_free(ctx, d_q); hs_free(ctx, d_t); hs_free(ctx, d_qo); hs_free(ctx, d_to); hs_free(ctx, d_bmo);
     hs_free(ctx, d_res); hs_free(ctx, d_bm); hs_free(ctx, d_counter); hs_free(ctx, d_peq); hs_free(ctx, d_ends);
     hs_free(ctx, d_starts); hs_free(ctx, d_aln_tmp); hs_free(ctx, d_tmpo); hs_free(ctx, d_trace); hs_free(ctx, d_aln);
-    hs_free(ctx, d_route); hs_free(ctx, d_alpha_len); hs_free(ctx, d_plist); hs_free(ctx, d_tasks); hs_free(ctx, d_batch_alpha);
+    hs_free(ctx, d_ptrace); hs_free(ctx, d_route); hs_free(ctx, d_alpha_len); hs_free(ctx, d_plist); hs_free(ctx, d_tasks); hs_free(ctx, d_batch_alpha);
     hs_free(ctx, d_scan); hs_free(ctx, d_list); hs_free(ctx, d_hbuf); hs_free(ctx, d_colv); hs_free(ctx, d_colpre);
     return rc;
 }

@@ -73,6 +73,7 @@ int separate_reads_pipeline(int argc, char* argv[], int (*prepare)(void* user), 
 
     std::vector<ColContig> contigs;
     int prepare_rc = 0;
+    omp_set_max_active_levels(2);  // the parser's own loops run as a team inside its section
 #pragma omp parallel sections num_threads(2)
     {
 #pragma omp section
