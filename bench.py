@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (testing only)")
     ap.add_argument("--cpu-sample-chunks", type=int, default=0, help="chunks in the CPU baseline sample (0 = auto)")
-    ap.add_argument("--e2e-lanes", type=int, default=2, help="hsgpu contexts (host threads) of the e2e path")
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="hsgpu contexts (host threads) of the e2e path")
     ap.add_argument("--e2e-groups", type=int, default=1, help="groups of contig chunks the e2e path cuts a step's batch into")
     ap.add_argument("--strong", action="store_true", help="strong scaling: ONE workload (same seed on every rank) dealt "
                     "to the ranks by sharding.lpt_assign; value = all columns / max-over-ranks time")
@@ -592,12 +592,14 @@ def run_e2e(chunks, parts_per_contig, local_rank, ctx, n_lanes, n_groups, steps,
         p.column_rank()
         t3 = time.perf_counter()
         p.partitions_set(prepared=group_parts[g])   # H2D of the final partitions
+        t3a = time.perf_counter()
         kept, koff = p.robust_filter_all(int(groups[g].contig_len.sum()))   # loops 3+4 + D2H of snps_out
+        t3b = time.perf_counter()
         pos, au, off, ds = p.suspects_all()      # D2H of the call_variants results
         t4 = time.perf_counter()
         p.close()
         if trace is not None:
-            trace.append((lane, g, t0, t1, t2, t3, t4, time.perf_counter()))
+            trace.append((lane, g, t0, t1, t2, t3, t3a, t3b, t4, time.perf_counter()))
         e2e_out[g] = pos.nbytes + au.nbytes + off.nbytes + ds.nbytes + kept.nbytes + koff.nbytes
         e2e_sus[g] = int(off[-1])
         e2e_kept[g] = int(koff[-1])
@@ -637,10 +639,10 @@ def run_e2e(chunks, parts_per_contig, local_rank, ctx, n_lanes, n_groups, steps,
     for c in lanes[1:]:
         c.close()
     if trace:  # the last step, times in ms from its first call
-        last = sorted(trace[-max(n_groups, 4):], key=lambda r: r[2])
+        last = sorted(trace[-max(n_groups, 9):], key=lambda r: r[2])
         z = last[0][2]
         for r in last:
-            print("  lane %d group %2d: create %.3f-%.3f build -%.3f rank -%.3f suspects_all -%.3f close -%.3f" %
+            print("  lane %d group %2d: create %.3f-%.3f build -%.3f rank -%.3f partitions_set -%.3f filter_all -%.3f suspects_all -%.3f close -%.3f" %
                   ((r[0], r[1]) + tuple((x - z) * 1e3 for x in r[2:])), file=sys.stderr)
     return {"device_ms": e2e_ms, "wall_ms": t_e2e, "h2d_bytes": h2d_bytes, "d2h_bytes": d2h_bytes,
             "suspects": sum(e2e_sus), "kept": sum(e2e_kept), "groups": n_groups, "lanes": n_lanes}

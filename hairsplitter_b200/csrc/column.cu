@@ -428,21 +428,29 @@ __device__ __forceinline__ bool is_candidate(const uint8_t* __restrict__ flags, 
     return q > 0 && (flags[g0 + q] & HS_FLAG_CANDIDATE);
 }
 
-__global__ void __launch_bounds__(HS_TILE) suspect_mark_kernel(const int32_t* __restrict__ tile_contig,
-                                                               const int64_t* __restrict__ tile_base,
-                                                               const int64_t* __restrict__ col_base,
-                                                               const int32_t* __restrict__ contig_len,
-                                                               uint8_t* __restrict__ flags) {
-    const int64_t tile = blockIdx.x;
+// SUS_TILES tiles per CTA (a CTA per tile is bound by the CTA launch rate: 39 000 tiny CTAs per step on config 2).
+// The head thread of a segment also counts the accepted columns per tile (they may lie in later tiles).
+#define SUS_TILES 8
+__global__ void __launch_bounds__(HS_TILE * SUS_TILES) suspect_mark_kernel(int64_t n_tiles, const int32_t* __restrict__ tile_contig,
+                                                                           const int64_t* __restrict__ tile_base,
+                                                                           const int64_t* __restrict__ col_base,
+                                                                           const int32_t* __restrict__ contig_len,
+                                                                           uint8_t* __restrict__ flags,
+                                                                           unsigned long long* __restrict__ tile_cnt) {
+    const int64_t tile = (int64_t)blockIdx.x * SUS_TILES + (threadIdx.x / HS_TILE);
+    if (tile >= n_tiles) return;
     const int c = tile_contig[tile];
     const int L = contig_len[c];
     const int64_t g0 = col_base[c];
-    const int q = (int)(tile - tile_base[c]) * HS_TILE + threadIdx.x;
+    const int64_t t0 = tile_base[c];
+    const int q = (int)(tile - t0) * HS_TILE + (threadIdx.x % HS_TILE);
     if (q >= L || !is_candidate(flags, g0, q)) return;
     for (int d = 1; d <= 5; d++)
         if (q - d > 0 && (flags[g0 + q - d] & HS_FLAG_CANDIDATE)) return;  // not a segment head
     flags[g0 + q] |= HS_FLAG_SUSPECT;
     int last = q, pc = q, p = q;
+    int64_t cur_tile = tile;
+    unsigned cur_n = 1;
     for (;;) {
         p++;
         if (p >= L || p - pc > 5) break;
@@ -450,50 +458,58 @@ __global__ void __launch_bounds__(HS_TILE) suspect_mark_kernel(const int32_t* __
             if (p - last > 5) {
                 flags[g0 + p] |= HS_FLAG_SUSPECT;
                 last = p;
+                const int64_t tl = t0 + p / HS_TILE;
+                if (tl != cur_tile) {
+                    atomicAdd(tile_cnt + cur_tile, (unsigned long long)cur_n);
+                    cur_tile = tl;
+                    cur_n = 0;
+                }
+                cur_n++;
             }
             pc = p;
         }
     }
+    atomicAdd(tile_cnt + cur_tile, (unsigned long long)cur_n);
 }
 
-// ordered compaction of the accepted columns: count per tile, scan, fill
-template <bool FILL>
-__global__ void __launch_bounds__(HS_TILE) suspect_compact_kernel(const int32_t* __restrict__ tile_contig,
-                                                                  const int64_t* __restrict__ tile_base,
-                                                                  const int64_t* __restrict__ col_base,
-                                                                  const int32_t* __restrict__ contig_len,
-                                                                  const int64_t* __restrict__ suspect_base,
-                                                                  const uint8_t* __restrict__ flags,
-                                                                  int64_t* __restrict__ tile_cnt_or_off,
-                                                                  int32_t* __restrict__ suspect_pos,
-                                                                  uint8_t* __restrict__ suspect_auto) {
-    __shared__ int s_warp[4];
+// ordered compaction of the accepted columns from the scanned per-tile counts; the first tile of a contig also
+// writes the contig's total
+__global__ void __launch_bounds__(HS_TILE * SUS_TILES) suspect_fill_kernel(int64_t n_tiles, const int32_t* __restrict__ tile_contig,
+                                                                           const int64_t* __restrict__ tile_base,
+                                                                           const int64_t* __restrict__ col_base,
+                                                                           const int32_t* __restrict__ contig_len,
+                                                                           const int64_t* __restrict__ suspect_base,
+                                                                           const uint8_t* __restrict__ flags,
+                                                                           const int64_t* __restrict__ tile_off,
+                                                                           int32_t* __restrict__ suspect_pos,
+                                                                           uint8_t* __restrict__ suspect_auto,
+                                                                           int32_t* __restrict__ n_suspects) {
+    __shared__ int s_warp[SUS_TILES * 4];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int64_t tile = blockIdx.x;
-    const int c = tile_contig[tile];
-    const int L = contig_len[c];
-    const int64_t g0 = col_base[c];
-    const int q = (int)(tile - tile_base[c]) * HS_TILE + tid;
-    const unsigned f = (q < L) ? flags[g0 + q] : 0u;
+    const int64_t tile = (int64_t)blockIdx.x * SUS_TILES + (tid / HS_TILE);
+    const bool live = tile < n_tiles;
+    int c = 0, L = 0, q = 0;
+    int64_t g0 = 0;
+    if (live) {
+        c = tile_contig[tile];
+        L = contig_len[c];
+        g0 = col_base[c];
+        q = (int)(tile - tile_base[c]) * HS_TILE + (tid % HS_TILE);
+    }
+    const unsigned f = (live && q < L) ? flags[g0 + q] : 0u;
     const bool acc = (f & HS_FLAG_SUSPECT) != 0;
     const unsigned m = __ballot_sync(0xffffffffu, acc);
     if (lane == 0) s_warp[wid] = __popc(m);
     __syncthreads();
-    if (!FILL) {
-        if (tid == 0) tile_cnt_or_off[tile] = s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
-    } else if (acc) {
+    if (acc) {
         int before = __popc(m & ((1u << lane) - 1u));
-        for (int w = 0; w < wid; w++) before += s_warp[w];
-        const int64_t i = suspect_base[c] + (tile_cnt_or_off[tile] - tile_cnt_or_off[tile_base[c]]) + before;
+        for (int w = wid & ~3; w < wid; w++) before += s_warp[w];
+        const int64_t i = suspect_base[c] + (tile_off[tile] - tile_off[tile_base[c]]) + before;
         suspect_pos[i] = q;
         suspect_auto[i] = (f & HS_FLAG_AUTO) ? 1 : 0;
     }
-}
-
-__global__ void suspect_count_kernel(int n_contigs, const int64_t* __restrict__ tile_base,
-                                     const int64_t* __restrict__ tile_sus_off, int32_t* __restrict__ n_suspects) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n_contigs) n_suspects[c] = (int32_t)(tile_sus_off[tile_base[c + 1]] - tile_sus_off[tile_base[c]]);
+    if (live && (tid % HS_TILE) == 0 && tile == tile_base[c])
+        n_suspects[c] = (int32_t)(tile_off[tile_base[c + 1]] - tile_off[tile]);
 }
 
 // all suspect lists of a batch, packed contig after contig (hsgpu_suspects_all). One CTA per contig; hdr =
@@ -723,18 +739,17 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
                   column_rank_literal_kernel<<<ctx->sm_count * 2, 128, 0, ctx->stream>>>(la));
     }
     if (p->n_tiles > 0) {
-        HS_KERNEL(ctx, "suspect_mark_kernel", suspect_mark_kernel<<<(unsigned)p->n_tiles, HS_TILE, 0, ctx->stream>>>(
-            p->d_tile_contig, p->d_tile_base, p->d_col_base, p->d_contig_len, p->d_flags));
-        HS_KERNEL(ctx, "suspect_compact_kernel<0>", suspect_compact_kernel<false><<<(unsigned)p->n_tiles, HS_TILE, 0, ctx->stream>>>(
-            p->d_tile_contig, p->d_tile_base, p->d_col_base, p->d_contig_len, p->d_suspect_base, p->d_flags,
-            p->d_tile_sus, nullptr, nullptr));
+        const unsigned sus_grid = (unsigned)((p->n_tiles + SUS_TILES - 1) / SUS_TILES);
+        HS_CUDA(ctx, cudaMemsetAsync(p->d_tile_sus, 0, sizeof(int64_t) * (size_t)(p->n_tiles + 1), ctx->stream));
+        HS_CUDA(ctx, cudaMemsetAsync(p->d_n_suspects, 0, sizeof(int32_t) * nc, ctx->stream));  // contigs without tiles
+        HS_KERNEL(ctx, "suspect_mark_kernel", suspect_mark_kernel<<<sus_grid, HS_TILE * SUS_TILES, 0, ctx->stream>>>(
+            p->n_tiles, p->d_tile_contig, p->d_tile_base, p->d_col_base, p->d_contig_len, p->d_flags,
+            reinterpret_cast<unsigned long long*>(p->d_tile_sus)));
         int rc = hs_exclusive_scan_i64(ctx, p->d_tile_sus, p->d_tile_sus, p->n_tiles, p->d_tile_sus + p->n_tiles);
         if (rc) return rc;
-        HS_KERNEL(ctx, "suspect_compact_kernel<1>", suspect_compact_kernel<true><<<(unsigned)p->n_tiles, HS_TILE, 0, ctx->stream>>>(
-            p->d_tile_contig, p->d_tile_base, p->d_col_base, p->d_contig_len, p->d_suspect_base, p->d_flags,
-            p->d_tile_sus, p->d_suspect_pos, p->d_suspect_auto));
-        HS_KERNEL(ctx, "suspect_count_kernel", suspect_count_kernel<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(
-            nc, p->d_tile_base, p->d_tile_sus, p->d_n_suspects));
+        HS_KERNEL(ctx, "suspect_fill_kernel", suspect_fill_kernel<<<sus_grid, HS_TILE * SUS_TILES, 0, ctx->stream>>>(
+            p->n_tiles, p->d_tile_contig, p->d_tile_base, p->d_col_base, p->d_contig_len, p->d_suspect_base, p->d_flags,
+            p->d_tile_sus, p->d_suspect_pos, p->d_suspect_auto, p->d_n_suspects));
     } else {
         HS_CUDA(ctx, cudaMemsetAsync(p->d_n_suspects, 0, sizeof(int32_t) * nc, ctx->stream));
     }

@@ -96,6 +96,18 @@ struct HsCarve {
         if (n <= 0) n = 1;
         pieces.push_back({reinterpret_cast<void**>(slot), ((size_t)n * sizeof(T) + 255) & ~(size_t)255});
     }
+    size_t total() const {
+        size_t t = 0;
+        for (const Piece& q : pieces) t += q.bytes;
+        return t ? t : 256;
+    }
+    void place(void* base) {  // the pieces inside a block the caller owns (256-byte aligned)
+        size_t off = 0;
+        for (const Piece& q : pieces) {
+            *q.slot = static_cast<char*>(base) + off;
+            off += q.bytes;
+        }
+    }
     cudaError_t alloc(hsgpu_ctx* ctx, void** base) {
         size_t total = 0;
         for (const Piece& q : pieces) total += q.bytes;

@@ -16,6 +16,8 @@
 
 #include <atomic>
 
+#include <chrono>
+
 #include "common.cuh"
 #include "rank.cuh"
 
@@ -285,38 +287,52 @@ __device__ __forceinline__ int rf_contig_of(const int64_t* __restrict__ col_base
 // char/unsigned char quirk makes ref_base its own alternative the two counters stay 0 -- so a column with c1 <= 4
 // can only be kept by loop 3, i.e. if it is in snps_in.
 __global__ void __launch_bounds__(256) filter_active_kernel(FilterArgs a) {
-    const int lane = threadIdx.x & 31;
+    __shared__ unsigned s_cnt[2][8], s_base[2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // four columns per thread: one 4-byte load of the flags (the flag array starts 256-byte aligned)
     const int64_t g4 = (a.g_begin & ~(int64_t)3) + 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     uint32_t f4 = 0;
     if (g4 < a.g_end) f4 = __ldg(reinterpret_cast<const uint32_t*>(a.flags + g4));
+    unsigned front = 0, back = 0;  // bit k: column g4 + k goes to the front / the back of the list
+    if (f4 & (0x01010101u * (a.in_flag | HS_FLAG_ACTIVE))) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t g = g4 + k;
+            const unsigned f = (f4 >> (8 * k)) & 0xffu;
+            if (g >= a.g_begin && g < a.g_end && (f & (a.in_flag | HS_FLAG_ACTIVE))) {  // ACTIVE: rescue column with c1 > 4 (write_column)
+                const int c = rf_contig_of(a.col_base, a.n_contigs, g);
+                if (a.desc[c].n_parts > 0) {  // :640-642: no partition, nothing kept
+                    // columns of tiles with more than RF_CAP reads go to the back of the list (robust_filter_kernel<true>)
+                    const int64_t tile = a.tile_base[c] + (g - a.col_base[c]) / HS_TILE;
+                    if (a.tile_off[tile + 1] - a.tile_off[tile] > RF_CAP) back |= 1u << k;
+                    else front |= 1u << k;
+                }
+            }
+        }
+    }
+    // one reservation per CTA and list (the list order is free)
+    const unsigned nf = __popc(front), nk = __popc(back);
+    const unsigned inc_f = hs_warp_incl_scan((int)nf, lane), inc_b = hs_warp_incl_scan((int)nk, lane);
+    if (lane == 31) {
+        s_cnt[0][wid] = inc_f;
+        s_cnt[1][wid] = inc_b;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        unsigned tot = 0;
+        for (int w = 0; w < 8; w++) {
+            const unsigned v = s_cnt[threadIdx.x][w];
+            s_cnt[threadIdx.x][w] = tot;
+            tot += v;
+        }
+        s_base[threadIdx.x] = tot ? atomicAdd(a.counters + 3 * threadIdx.x, tot) : 0u;
+    }
+    __syncthreads();
+    unsigned of = s_base[0] + s_cnt[0][wid] + inc_f - nf, ob = s_base[1] + s_cnt[1][wid] + inc_b - nk;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int64_t g = g4 + k;
-        const unsigned f = (f4 >> (8 * k)) & 0xffu;
-        bool act = false;
-        if (g >= a.g_begin && g < a.g_end && (f & (a.in_flag | HS_FLAG_ACTIVE)))  // ACTIVE: rescue column with c1 > 4 (write_column)
-            act = a.desc[rf_contig_of(a.col_base, a.n_contigs, g)].n_parts > 0;  // :640-642: no partition, nothing kept
-        // columns of tiles with more than RF_CAP reads go to the back of the list (robust_filter_kernel<true>)
-        bool deep = false;
-        if (act) {
-            const int c = rf_contig_of(a.col_base, a.n_contigs, g);
-            const int64_t tile = a.tile_base[c] + (g - a.col_base[c]) / HS_TILE;
-            deep = a.tile_off[tile + 1] - a.tile_off[tile] > RF_CAP;
-        }
-        const unsigned mk = __ballot_sync(0xffffffffu, act && !deep), md = __ballot_sync(0xffffffffu, act && deep);
-        if (mk) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(a.counters, (unsigned)__popc(mk));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (act && !deep) a.active[base + __popc(mk & ((1u << lane) - 1u))] = (uint32_t)g;
-        }
-        if (md) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(a.counters + 3, (unsigned)__popc(md));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (act && deep) a.active[(a.g_end - a.g_begin) - 1 - (base + __popc(md & ((1u << lane) - 1u)))] = (uint32_t)g;
-        }
+        if (front & (1u << k)) a.active[of++] = (uint32_t)(g4 + k);
+        if (back & (1u << k)) a.active[(a.g_end - a.g_begin) - 1 - (ob++)] = (uint32_t)(g4 + k);
     }
 }
 
@@ -859,26 +875,31 @@ int hsgpu_partition_tables(hsgpu_pileup* p, int32_t contig, const hsgpu_partitio
     return HSGPU_OK;
 }
 
-// the partitions of one contig as robust_filter_kernel reads them: per read one row of 2-bit states, 16 partitions
-// per word, pwords words (1 = +1, 2 = -1, 3 = 0, 0 = absent or masked)
-static int build_filter_rows(hsgpu_ctx* ctx, const hsgpu_partitions* parts, int64_t n_reads, int pwords, uint32_t* rows) {
-    memset(rows, 0, (size_t)n_reads * (size_t)pwords * sizeof(uint32_t));
-    for (int p = 0; p < parts->n_parts; p++) {
-        for (int64_t i = parts->part_off[p]; i < parts->part_off[p + 1]; i++) {
-            const int32_t n = parts->read_idx[i];
-            if (n < 0 || n >= n_reads) HS_FAIL(ctx, HSGPU_ERR_ARG, "partition read index out of range");
-            uint32_t v = 0;
-            switch (parts->state[i]) {
-                case 1: v = 1; break;
-                case -1: v = 2; break;
-                case 0: v = 3; break;
-                default: v = 0; break;  // -2: masked
-            }
-            uint32_t& w = rows[(size_t)n * pwords + (p >> 4)];
-            w = (w & ~(3u << (2 * (p & 15)))) | (v << (2 * (p & 15)));  // a read listed twice: the last entry counts
-        }
+// the partitions as robust_filter_kernel reads them: per read one row of 2-bit states, 16 partitions per word,
+// pwords words (1 = +1, 2 = -1, 3 = 0, 0 = absent or masked). The rows are scattered on the device from the
+// partitions' entry lists: one thread per partition walks its entries in order (a read listed twice: the last entry
+// counts), fields of different partitions in one word meet through atomics.
+struct FilterPart {
+    int32_t contig, local;  // the contig of a partition, its index inside the contig
+};
+
+__global__ void __launch_bounds__(128) filter_rows_kernel(int64_t n_parts_all, const FilterPart* __restrict__ meta,
+                                                          const int64_t* __restrict__ ent_off,
+                                                          const int32_t* __restrict__ read_idx,
+                                                          const uint8_t* __restrict__ state2, const FilterDesc* __restrict__ desc,
+                                                          uint32_t* __restrict__ rows) {
+    const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= n_parts_all) return;
+    const FilterPart pm = meta[gp];
+    const FilterDesc d = desc[pm.contig];
+    uint32_t* const base = rows + d.row_off + (pm.local >> 4);
+    const int sh = 2 * (pm.local & 15);
+    const int64_t e1 = ent_off[gp + 1];
+    for (int64_t i = ent_off[gp]; i < e1; i++) {
+        uint32_t* const w = base + (int64_t)read_idx[i] * d.pwords;
+        atomicAnd(w, ~(3u << sh));
+        atomicOr(w, (uint32_t)state2[i] << sh);
     }
-    return HSGPU_OK;
 }
 
 static void filter_free(hsgpu_pileup* p) {
@@ -904,31 +925,86 @@ static int filter_set(hsgpu_pileup* p, int c0, int n, const hsgpu_partitions* pa
         d.row_off = row_words;
         row_words += R * d.pwords;
     }
-    const size_t desc_bytes = sizeof(FilterDesc) * (size_t)nc;
-    const size_t desc_pad = (desc_bytes + 255) & ~(size_t)255;
-    const size_t total = desc_pad + (size_t)row_words * 4 + 256;
-    uint8_t* h = reinterpret_cast<uint8_t*>(hs_host_stage(ctx, total));
-    if (!h) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu: pinned staging allocation failed");
-    memcpy(h, desc.data(), desc_bytes);
-    int rc_all = HSGPU_OK;
-#pragma omp parallel for schedule(dynamic, 1)
+    // staged for one upload: descriptors, per-partition (contig, index), entry offsets, read indices, 2-bit states
+    int64_t n_parts_all = 0, n_ent = 0;
     for (int c = c0; c < c0 + n; c++) {
-        const FilterDesc& d = desc[c];
-        if (d.n_parts <= 0) continue;
-        const int64_t R = p->h_contig_read_off[c + 1] - p->h_contig_read_off[c];
-        const int rc = build_filter_rows(ctx, &parts[c - c0], R, d.pwords, reinterpret_cast<uint32_t*>(h + desc_pad) + d.row_off);
-        if (rc) {
-#pragma omp critical
-            rc_all = rc;
-        }
+        if (desc[c].n_parts <= 0) continue;
+        const hsgpu_partitions& q = parts[c - c0];
+        n_parts_all += q.n_parts;
+        n_ent += q.part_off[q.n_parts] - q.part_off[0];
     }
-    if (rc_all) return rc_all;
+    static const bool timing = getenv("HSGPU_TIMING") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    HsCarve hv;  // used for its offsets only: the pieces are cut out of the pinned staging block and of one device block
+    FilterDesc* o_desc;
+    FilterPart* o_meta;
+    int64_t* o_off;
+    int32_t* o_idx;
+    uint8_t* o_st;
+    hv.add(&o_desc, nc);
+    hv.add(&o_meta, n_parts_all);
+    hv.add(&o_off, n_parts_all + 1);
+    hv.add(&o_idx, n_ent);
+    hv.add(&o_st, n_ent);
+    const size_t in_bytes = hv.total();
+    uint8_t* h = reinterpret_cast<uint8_t*>(hs_host_stage(ctx, in_bytes));
+    if (!h) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu: pinned staging allocation failed");
+    hv.place(h);
+    memcpy(o_desc, desc.data(), sizeof(FilterDesc) * (size_t)nc);
+    int64_t gp = 0, ge = 0;
+    for (int c = c0; c < c0 + n; c++) {
+        if (desc[c].n_parts <= 0) continue;
+        const hsgpu_partitions& q = parts[c - c0];
+        const int64_t R = p->h_contig_read_off[c + 1] - p->h_contig_read_off[c];
+        const int64_t e0 = q.part_off[0];
+        for (int k = 0; k < q.n_parts; k++) {
+            o_meta[gp + k].contig = c;
+            o_meta[gp + k].local = k;
+            o_off[gp + k] = ge + (q.part_off[k] - e0);
+        }
+        const int64_t ne = q.part_off[q.n_parts] - e0;
+        const int32_t* ri = q.read_idx + e0;
+        const int16_t* st = q.state + e0;
+        int32_t bad = 0;
+        for (int64_t i = 0; i < ne; i++) {
+            const int32_t r = ri[i];
+            bad |= (r < 0) | (r >= R);
+            o_idx[ge + i] = r;
+            const int v = st[i];
+            o_st[ge + i] = (uint8_t)(v == 1 ? 1 : v == -1 ? 2 : v == 0 ? 3 : 0);  // -2: masked
+        }
+        if (bad) HS_FAIL(ctx, HSGPU_ERR_ARG, "partition read index out of range");
+        gp += q.n_parts;
+        ge += ne;
+    }
+    o_off[gp] = ge;
+    const auto t_staged = std::chrono::steady_clock::now();
     filter_free(p);
+    const size_t in_pad = (in_bytes + 255) & ~(size_t)255;
+    const size_t total = in_pad + (size_t)row_words * 4 + 256;
     HS_CUDA(ctx, cudaMallocAsync(&p->d_filter_block, total, ctx->stream));
-    HS_CUDA(ctx, cudaMemcpyAsync(p->d_filter_block, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* const dev = reinterpret_cast<uint8_t*>(p->d_filter_block);
+    HS_CUDA(ctx, cudaMemcpyAsync(dev, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(ctx, cudaMemsetAsync(dev + in_pad, 0, (size_t)row_words * 4 + 256, ctx->stream));
+    p->d_fdesc = dev + ((uint8_t*)o_desc - h);
+    p->d_frows = reinterpret_cast<uint32_t*>(dev + in_pad);
+    if (n_parts_all > 0)
+        HS_KERNEL(ctx, "filter_rows_kernel",
+                  filter_rows_kernel<<<(unsigned)((n_parts_all + 127) / 128), 128, 0, ctx->stream>>>(
+                      n_parts_all, reinterpret_cast<const FilterPart*>(dev + ((uint8_t*)o_meta - h)),
+                      reinterpret_cast<const int64_t*>(dev + ((uint8_t*)o_off - h)),
+                      reinterpret_cast<const int32_t*>(dev + ((uint8_t*)o_idx - h)), dev + ((uint8_t*)o_st - h),
+                      reinterpret_cast<const FilterDesc*>(p->d_fdesc), p->d_frows));
+    const auto t_queued = std::chrono::steady_clock::now();
     HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging area is reused by the next call
-    p->d_fdesc = p->d_filter_block;
-    p->d_frows = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p->d_filter_block) + desc_pad);
+    if (timing) {
+        const auto t_end = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) {
+            return std::chrono::duration<double, std::milli>(y - x).count();
+        };
+        fprintf(stderr, "[hsgpu timing] partitions_set: %lld partitions, %lld entries: stage %.3f ms, queue %.3f ms, sync %.3f ms\n",
+                (long long)n_parts_all, (long long)n_ent, ms(t_begin, t_staged), ms(t_staged, t_queued), ms(t_queued, t_end));
+    }
     p->have_parts = true;
     return HSGPU_OK;
 }

@@ -448,7 +448,15 @@ __device__ void build_peq_packed(uint64_t* peq, const uint8_t* lut, int lane, co
 
 // dp_pass with per-lane pair parameters; n_max = the longest target of the warp's groups. The result is valid in the
 // lanes of the group it belongs to.
-template <int KIND, int BPL>
+// store of a traceback entry under a predicate, without a branch (the band test differs from block to block)
+__device__ __forceinline__ void st_if(bool on, ulonglong2* p, uint64_t x, uint64_t y) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.global.v2.u64 [%1], {%2, %3}; }" ::"r"((unsigned)on), "l"(p),
+                 "l"(x), "l"(y)
+                 : "memory");
+}
+
+// KL = the block of the bottom row inside the group's last lane, (nb - 1) % BPL: the same for every pair of a launch
+template <int KIND, int BPL, int KL>
 __device__ PassOut dp_pass_packed(const uint64_t* peq, const uint8_t* lut, int lane, const PackLane& g, int m,
                                   const uint8_t* t, int n, int n_max, int rev_end, int start_hin, bool consider_j0,
                                   unsigned int* bitmask, ulonglong2* trace, int band_d = 0, int band_w = 0) {
@@ -459,10 +467,10 @@ __device__ PassOut dp_pass_packed(const uint64_t* peq, const uint8_t* lut, int l
         Pv[k] = ~0ull;
         Mv[k] = 0ull;
         band_lo[k] = band_first(g.bl * BPL + k, band_d, band_w, n);
+        if (g.bl * BPL + k >= g.nb) band_lo[k] = 0x40000000;  // padding block: never stored
     }
     const int lb = (m - 1) & 63;
     const int gl = g.gl;
-    const int k_last = (g.nb - 1) - (gl - 1) * BPL;  // the block of the bottom row inside the group's last lane
     int score = m;
     PassOut o;
     o.best = consider_j0 ? m : 0x3fffffff;
@@ -470,7 +478,8 @@ __device__ PassOut dp_pass_packed(const uint64_t* peq, const uint8_t* lut, int l
     o.last_j = 0;
     o.count = consider_j0 ? 1 : 0;
     unsigned int bits = consider_j0 ? 1u : 0u;
-    int packed = 0;
+    unsigned int packed = 0;  // symbol << 2 | (horizontal delta leaving the lane is +1) << 1 | (... is -1)
+    const unsigned int head_carry = start_hin > 0 ? 2u : 0u;
     // target symbols: gl at a time per group (lane bl holds symbol chunk*gl + bl), fetched one chunk ahead
     int tchunk = 0, tnext = 0;
     if (g.active && g.bl < n) tchunk = lut[rev_end >= 0 ? t[rev_end - g.bl] : t[g.bl]];
@@ -478,32 +487,35 @@ __device__ PassOut dp_pass_packed(const uint64_t* peq, const uint8_t* lut, int l
     int sc = 0;
     const int steps = n_max + gl - 1;
     for (int s = 0; s < steps; s++) {
-        const int sym0 = __shfl_sync(0xffffffffu, tchunk, g.ghead + sc);
-        const int pk = __shfl_up_sync(0xffffffffu, packed, 1);
-        const int sym = g.bl == 0 ? sym0 : (pk >> 2);
-        int hin = g.bl == 0 ? start_hin : ((pk & 3) - 1);
+        const unsigned int sym0 = (unsigned)__shfl_sync(0xffffffffu, tchunk, g.ghead + sc);
+        unsigned int pk = __shfl_up_sync(0xffffffffu, packed, 1);
+        if (g.bl == 0) pk = (sym0 << 2) | head_carry;
+        const unsigned int sym = pk >> 2;
+        uint64_t hneg = pk & 1u, hpos = (pk >> 1) & 1u;
         const int c = s - g.bl;
         if (g.active && c >= 0 && c < n) {
             uint64_t phs = 0, mhs = 0;  // Ph / Mh of the block that holds the bottom row
 #pragma unroll
             for (int k = 0; k < BPL; k++) {
                 uint64_t Eq = peq[(sym * BPL + k) * 32 + lane];
-                const uint64_t hneg = hin < 0 ? 1ull : 0ull, hpos = hin > 0 ? 1ull : 0ull;
                 const uint64_t Xv = Eq | Mv[k];
                 Eq |= hneg;
                 const uint64_t Xh = (((Eq & Pv[k]) + Pv[k]) ^ Pv[k]) | Eq;
-                uint64_t Ph = Mv[k] | ~(Xh | Pv[k]);
-                uint64_t Mh = Pv[k] & Xh;
-                hin = (int)(Ph >> 63) - (int)(Mh >> 63);
-                if (k == k_last) { phs = Ph; mhs = Mh; }
+                const uint64_t Ph = Mv[k] | ~(Xh | Pv[k]);
+                const uint64_t Mh = Pv[k] & Xh;
+                if (k == KL) { phs = Ph; mhs = Mh; }
                 const uint64_t Phs = (Ph << 1) | hpos;
                 const uint64_t Mhs = (Mh << 1) | hneg;
+                hpos = Ph >> 63;
+                hneg = Mh >> 63;
                 Pv[k] = Mhs | ~(Xv | Phs);
                 Mv[k] = Phs & Xv;
-                if (KIND == PASS_NW_STORE && g.bl * BPL + k < g.nb && (unsigned)(c - band_lo[k]) < (unsigned)band_w)
-                    trace[(size_t)(g.bl * BPL + k) * band_w + (c - band_lo[k])] = make_ulonglong2(Pv[k], Ph);
+                if (KIND == PASS_NW_STORE) {
+                    const int x = c - band_lo[k];
+                    st_if((unsigned)x < (unsigned)band_w, trace + (size_t)(g.bl * BPL + k) * band_w + x, Pv[k], Ph);
+                }
             }
-            packed = (sym << 2) | (hin + 1);
+            packed = (sym << 2) | ((unsigned)hpos << 1) | (unsigned)hneg;
             if (g.bl == gl - 1) {
                 score += (int)((phs >> lb) & 1ull) - (int)((mhs >> lb) & 1ull);
                 const int j = c + 1;
@@ -598,7 +610,7 @@ __device__ __forceinline__ PackLane pack_lane(int lane, int nb, int cnt) {
     return g;
 }
 
-template <int BPL>
+template <int BPL, int KL>
 __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_packed_kernel(EdArgs a) {
     __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32 * BPL];
     __shared__ uint8_t s_lut[ED_WARPS][256];
@@ -640,7 +652,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_packed_kernel(EdA
             const int n_max = __reduce_max_sync(0xffffffffu, run ? n : 0);
             PackLane gr = g;
             gr.active = run;
-            const PassOut o = dp_pass_packed<PASS_NW_SCORE, BPL>(peq, lut, lane, gr, m, t, n, n_max, -1, 1, false, nullptr, nullptr);
+            const PassOut o = dp_pass_packed<PASS_NW_SCORE, BPL, KL>(peq, lut, lane, gr, m, t, n, n_max, -1, 1, false, nullptr, nullptr);
             if (run && o.best <= kk) {
                 r.edit_distance = o.best;
                 r.n_locations = 1;
@@ -649,7 +661,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_packed_kernel(EdA
         } else {
             const bool j0 = (m & 63) != 0;  // W > 0
             const int n_max = __reduce_max_sync(0xffffffffu, n);
-            const PassOut o = dp_pass_packed<PASS_SEMIGLOBAL, BPL>(peq, lut, lane, g, m, t, n, n_max, -1, a.mode == 2 ? 0 : 1, j0,
+            const PassOut o = dp_pass_packed<PASS_SEMIGLOBAL, BPL, KL>(peq, lut, lane, g, m, t, n, n_max, -1, a.mode == 2 ? 0 : 1, j0,
                                                                    bm, nullptr);
             if (a.mode == 2) kk = min(kk, m);  // :565-567
             if (o.best <= kk) {
@@ -662,7 +674,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_packed_kernel(EdA
     }
 }
 
-template <int BPL>
+template <int BPL, int KL>
 __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdArgs a) {
     __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32 * BPL];
     __shared__ uint8_t s_lut[ED_WARPS][256];
@@ -717,7 +729,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdA
                 // an alignment of distance d takes at most m + d target symbols: no later column can reach d again
                 const int nrev = min(e + 1, m + r.edit_distance);
                 const int n_max = __reduce_max_sync(0xffffffffu, gr.active ? nrev : 0);
-                const PassOut o = dp_pass_packed<PASS_REV_SHW, BPL>(peq, lut, lane, gr, m, t, nrev, n_max, e, 1, j0c, nullptr, nullptr);
+                const PassOut o = dp_pass_packed<PASS_REV_SHW, BPL, KL>(peq, lut, lane, gr, m, t, nrev, n_max, e, 1, j0c, nullptr, nullptr);
                 if (g.bl == 0 && l < n_loc) starts[l] = e >= 0 ? e - (o.last_j - 1) : 0;  // :254-256 last position
             }
         } else if (g.active) {
@@ -750,7 +762,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdA
             }
             build_peq_packed<BPL>(peq, lut, lane, g, q, m, n_sym, false);
             const int n_max = __reduce_max_sync(0xffffffffu, gt.active ? an : 0);
-            dp_pass_packed<PASS_NW_STORE, BPL>(peq, lut, lane, gt, m, t + s0, an, n_max, -1, 1, false, nullptr, trace, band_d,
+            dp_pass_packed<PASS_NW_STORE, BPL, KL>(peq, lut, lane, gt, m, t + s0, an, n_max, -1, 1, false, nullptr, trace, band_d,
                                                band_w);
             __syncwarp();
             const int len = traceback_packed(trace, q, m, t + s0, an, out, gt, band_d, band_w);
@@ -1034,7 +1046,8 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     bm_off[n_pairs] = bmw;
     tmp_off[n_pairs] = tmpb;
     const int64_t qbytes = query_off[n_pairs], tbytes = target_off[n_pairs];
-    const int grid = ctx->sm_count * 4;
+    static const int ctas_per_sm = getenv("HSGPU_EDLIB_CTAS") ? std::max(1, atoi(getenv("HSGPU_EDLIB_CTAS"))) : 5;
+    const int grid = ctx->sm_count * ctas_per_sm;
     const int n_warps = grid * ED_WARPS;
     uint8_t *d_q = nullptr, *d_t = nullptr, *d_aln_tmp = nullptr, *d_trace = nullptr, *d_aln = nullptr, *d_ptrace = nullptr;
     int64_t *d_qo = nullptr, *d_to = nullptr, *d_bmo = nullptr, *d_tmpo = nullptr, *d_scan = nullptr;
@@ -1075,16 +1088,19 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
         }
     });
     std::vector<int32_t> plist, tasks;
-    int task_first[ED_PACK_MAXBPL + 2];  // tasks of BPL = b: [task_first[b], task_first[b + 1])
+    // a launch = one (blocks per lane, block of the bottom row in the last lane) class: 1 + 2 + 3 + 4 of them
+    constexpr int NCLS = ED_PACK_MAXBPL * (ED_PACK_MAXBPL + 1) / 2;
+    auto cls_of = [](int nb) { const int b = bpl_of[nb]; return b * (b - 1) / 2 + (nb - 1) % b; };
+    int task_first[NCLS + 1];  // tasks of class c: [task_first[c], task_first[c + 1])
     int64_t ptrace_stride = 0;
-    // key of a pair: (blocks per lane, blocks, end locations) -- counting sort, then tasks of equal block count
+    // key of a pair: (class, blocks, end locations) -- counting sort, then tasks of equal block count
     auto build_tasks = [&](bool phase_b) -> cudaError_t {
         const int NL = ED_PACK_MAXLOC + 1, NB = ED_PACK_MAXBLOCKS + 1;
-        const int NK = (ED_PACK_MAXBPL + 1) * NB * NL;
+        const int NK = NCLS * NB * NL;
         std::vector<int64_t> cnt((size_t)NK + 1, 0);
         auto key = [&](int i) {
             const int nb = (int)((query_off[i + 1] - query_off[i] + 63) / 64);
-            return (bpl_of[nb] * NB + nb) * NL + (phase_b ? results[i].n_locations : 0);
+            return (cls_of(nb) * NB + nb) * NL + (phase_b ? results[i].n_locations : 0);
         };
         for (int i = 0; i < n_pairs; i++)
             if (route[i] == ED_ROUTE_PACKED) cnt[(size_t)key(i) + 1]++;
@@ -1096,11 +1112,13 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
             if (route[i] == ED_ROUTE_PACKED) plist[(size_t)fill[(size_t)key(i)]++] = i;
         tasks.clear();
         ptrace_stride = 0;
-        for (int b = 1; b <= ED_PACK_MAXBPL; b++) {
-            task_first[b] = (int)(tasks.size() / 2);
+        for (int c = 0; c < NCLS; c++) {
+            task_first[c] = (int)(tasks.size() / 2);
             for (int nb = 1; nb <= ED_PACK_MAXBLOCKS; nb++) {
+                if (cls_of(nb) != c) continue;
+                const int b = bpl_of[nb];
                 const int per = 32 / ((nb + b - 1) / b);
-                const int64_t lo = cnt[(size_t)(b * NB + nb) * NL], hi = cnt[(size_t)(b * NB + nb + 1) * NL];
+                const int64_t lo = cnt[(size_t)(c * NB + nb) * NL], hi = cnt[(size_t)(c * NB + nb + 1) * NL];
                 for (int64_t f = lo; f < hi; f += per) {
                     const int n_in = (int)std::min<int64_t>(per, hi - f);
                     tasks.push_back((int32_t)f);
@@ -1118,13 +1136,34 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
                 }
             }
         }
-        task_first[ED_PACK_MAXBPL + 1] = (int)(tasks.size() / 2);
+        task_first[NCLS] = (int)(tasks.size() / 2);
         ptrace_stride = (ptrace_stride + 255) & ~255ll;
         if (total == 0) return cudaSuccess;
         cudaError_t e = hs_h2d(ctx, d_plist, plist.data(), total);
         if (e == cudaSuccess) e = hs_h2d(ctx, d_tasks, tasks.data(), (int64_t)tasks.size());
         return e;
     };
+    typedef void (*PackedKernel)(EdArgs);
+    static const PackedKernel phase_a_packed[NCLS] = {
+        edlib_phase_a_packed_kernel<1, 0>, edlib_phase_a_packed_kernel<2, 0>, edlib_phase_a_packed_kernel<2, 1>,
+        edlib_phase_a_packed_kernel<3, 0>, edlib_phase_a_packed_kernel<3, 1>, edlib_phase_a_packed_kernel<3, 2>,
+        edlib_phase_a_packed_kernel<4, 0>, edlib_phase_a_packed_kernel<4, 1>, edlib_phase_a_packed_kernel<4, 2>,
+        edlib_phase_a_packed_kernel<4, 3>};
+    static const PackedKernel phase_b_packed[NCLS] = {
+        edlib_phase_b_packed_kernel<1, 0>, edlib_phase_b_packed_kernel<2, 0>, edlib_phase_b_packed_kernel<2, 1>,
+        edlib_phase_b_packed_kernel<3, 0>, edlib_phase_b_packed_kernel<3, 1>, edlib_phase_b_packed_kernel<3, 2>,
+        edlib_phase_b_packed_kernel<4, 0>, edlib_phase_b_packed_kernel<4, 1>, edlib_phase_b_packed_kernel<4, 2>,
+        edlib_phase_b_packed_kernel<4, 3>};
+    static const char* const phase_a_names[NCLS] = {
+        "edlib_phase_a_kernel<packed,1,0>", "edlib_phase_a_kernel<packed,2,0>", "edlib_phase_a_kernel<packed,2,1>",
+        "edlib_phase_a_kernel<packed,3,0>", "edlib_phase_a_kernel<packed,3,1>", "edlib_phase_a_kernel<packed,3,2>",
+        "edlib_phase_a_kernel<packed,4,0>", "edlib_phase_a_kernel<packed,4,1>", "edlib_phase_a_kernel<packed,4,2>",
+        "edlib_phase_a_kernel<packed,4,3>"};
+    static const char* const phase_b_names[NCLS] = {
+        "edlib_phase_b_kernel<packed,1,0>", "edlib_phase_b_kernel<packed,2,0>", "edlib_phase_b_kernel<packed,2,1>",
+        "edlib_phase_b_kernel<packed,3,0>", "edlib_phase_b_kernel<packed,3,1>", "edlib_phase_b_kernel<packed,3,2>",
+        "edlib_phase_b_kernel<packed,4,0>", "edlib_phase_b_kernel<packed,4,1>", "edlib_phase_b_kernel<packed,4,2>",
+        "edlib_phase_b_kernel<packed,4,3>"};
     if (n_packed > 0) {
         HS_CUDA(ctx, hs_alloc(ctx, &d_alpha_len, n_pairs));
         HS_CUDA(ctx, hs_alloc(ctx, &d_plist, n_packed));
@@ -1180,16 +1219,13 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
                   edlib_alphabet_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(n_pairs, d_q, d_qo, d_t, d_to, d_alpha_len,
                                                                                   d_batch_alpha));
         HS_CUDA(ctx, build_tasks(false));
-        for (int b = 1; b <= ED_PACK_MAXBPL; b++) {
-            a.tasks = d_tasks + 2 * task_first[b];
-            a.n_tasks = task_first[b + 1] - task_first[b];
+        for (int c = 0; c < NCLS; c++) {
+            a.tasks = d_tasks + 2 * task_first[c];
+            a.n_tasks = task_first[c + 1] - task_first[c];
             if (a.n_tasks == 0) continue;
-            a.counter = d_counter + 8 + b;
+            a.counter = d_counter + 8 + c;
             const int gp = (int)std::min<int64_t>(grid, (a.n_tasks + ED_WARPS - 1) / ED_WARPS);
-            if (b == 1) HS_KERNEL(ctx, "edlib_phase_a_kernel<packed,1>", edlib_phase_a_packed_kernel<1><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
-            if (b == 2) HS_KERNEL(ctx, "edlib_phase_a_kernel<packed,2>", edlib_phase_a_packed_kernel<2><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
-            if (b == 3) HS_KERNEL(ctx, "edlib_phase_a_kernel<packed,3>", edlib_phase_a_packed_kernel<3><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
-            if (b == 4) HS_KERNEL(ctx, "edlib_phase_a_kernel<packed,4>", edlib_phase_a_packed_kernel<4><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
+            HS_KERNEL(ctx, phase_a_names[c], phase_a_packed[c]<<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
         }
     }
     // scratch of the LONG launches, sized for the pairs of the list at hand
@@ -1292,16 +1328,13 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
             if (task == 2) HS_CUDA(ctx, hs_alloc(ctx, &d_ptrace, (int64_t)grid_cap * ED_WARPS * ptrace_stride));
             a.ptrace = d_ptrace;
             a.ptrace_stride = ptrace_stride;
-            for (int b = 1; b <= ED_PACK_MAXBPL; b++) {
-                a.tasks = d_tasks + 2 * task_first[b];
-                a.n_tasks = task_first[b + 1] - task_first[b];
+            for (int c = 0; c < NCLS; c++) {
+                a.tasks = d_tasks + 2 * task_first[c];
+                a.n_tasks = task_first[c + 1] - task_first[c];
                 if (a.n_tasks == 0) continue;
-                a.counter = d_counter + 16 + b;
+                a.counter = d_counter + 20 + c;
                 const int gp = (int)std::min<int64_t>(grid_cap, (a.n_tasks + ED_WARPS - 1) / ED_WARPS);
-                if (b == 1) HS_KERNEL(ctx, "edlib_phase_b_kernel<packed,1>", edlib_phase_b_packed_kernel<1><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
-                if (b == 2) HS_KERNEL(ctx, "edlib_phase_b_kernel<packed,2>", edlib_phase_b_packed_kernel<2><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
-                if (b == 3) HS_KERNEL(ctx, "edlib_phase_b_kernel<packed,3>", edlib_phase_b_packed_kernel<3><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
-                if (b == 4) HS_KERNEL(ctx, "edlib_phase_b_kernel<packed,4>", edlib_phase_b_packed_kernel<4><<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
+                HS_KERNEL(ctx, phase_b_names[c], phase_b_packed[c]<<<gp, ED_WARPS * 32, 0, ctx->stream>>>(a));
             }
         }
         HS_CUDA(ctx, hs_d2h(ctx, results, d_res, n_pairs));
