@@ -36,7 +36,17 @@ struct hsgpu_ctx {
     // growable pinned staging area for results that are read back in one piece (hs_host_stage)
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
+    // every context allocates from its own stream-ordered pool: what a context frees is what its next batch takes,
+    // whatever the other contexts of the device are doing (with the device's shared default pool, contexts on
+    // different streams kept making the pool grow -- physical allocations under the driver's global lock, 10-20 ms
+    // stalls of every thread)
+    cudaMemPool_t pool = nullptr;
 };
+
+static inline cudaError_t hs_malloc_async(hsgpu_ctx* ctx, void** p, size_t bytes) {
+    if (ctx->pool) return cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream);
+    return cudaMallocAsync(p, bytes, ctx->stream);
+}
 
 // pinned staging area of at least `bytes` (contents are not kept when it grows); null on failure
 void* hs_host_stage(hsgpu_ctx* ctx, size_t bytes);
@@ -79,7 +89,7 @@ int hs_cuda_fail(hsgpu_ctx* ctx, cudaError_t e, const char* what, const char* fi
 template <typename T>
 static inline cudaError_t hs_alloc(hsgpu_ctx* ctx, T** p, int64_t n) {
     if (n <= 0) n = 1;
-    return cudaMallocAsync((void**)p, (size_t)n * sizeof(T), ctx->stream);
+    return hs_malloc_async(ctx, (void**)p, (size_t)n * sizeof(T));
 }
 template <typename T>
 static inline void hs_free(hsgpu_ctx* ctx, T*& p) {
@@ -111,7 +121,7 @@ struct HsCarve {
     cudaError_t alloc(hsgpu_ctx* ctx, void** base) {
         size_t total = 0;
         for (const Piece& q : pieces) total += q.bytes;
-        cudaError_t e = cudaMallocAsync(base, total ? total : 256, ctx->stream);
+        cudaError_t e = hs_malloc_async(ctx, base, total ? total : 256);
         if (e != cudaSuccess) return e;
         size_t off = 0;
         for (const Piece& q : pieces) {

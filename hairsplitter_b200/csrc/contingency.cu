@@ -982,7 +982,7 @@ static int filter_set(hsgpu_pileup* p, int c0, int n, const hsgpu_partitions* pa
     filter_free(p);
     const size_t in_pad = (in_bytes + 255) & ~(size_t)255;
     const size_t total = in_pad + (size_t)row_words * 4 + 256;
-    HS_CUDA(ctx, cudaMallocAsync(&p->d_filter_block, total, ctx->stream));
+    HS_CUDA(ctx, hs_malloc_async(ctx, &p->d_filter_block, total));
     uint8_t* const dev = reinterpret_cast<uint8_t*>(p->d_filter_block);
     HS_CUDA(ctx, cudaMemcpyAsync(dev, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     HS_CUDA(ctx, cudaMemsetAsync(dev + in_pad, 0, (size_t)row_words * 4 + 256, ctx->stream));

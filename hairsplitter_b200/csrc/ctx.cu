@@ -117,11 +117,26 @@ int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
         delete ctx;
         return hs_cuda_fail(nullptr, e, "cudaStreamCreate", __FILE__, __LINE__);
     }
-    // keep freed blocks in the stream-ordered pool instead of returning them to the driver
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    // the context's own stream-ordered pool; freed blocks stay in it instead of going back to the driver
+    // (HSGPU_SHARED_POOL=1: the device's default pool, for A/B measurements)
+    {
         uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        static const bool shared_pool = getenv("HSGPU_SHARED_POOL") && atoi(getenv("HSGPU_SHARED_POOL")) != 0;
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (!shared_pool && cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
+            cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        } else {
+            ctx->pool = nullptr;
+            cudaGetLastError();
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
     }
     {
         static HsRankLut lut;  // identical for every context; contexts may be created from several threads at once
@@ -157,6 +172,7 @@ void hsgpu_ctx_destroy(hsgpu_ctx* ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaStreamDestroy(ctx->stream);
     if (ctx->d_rank_lut) cudaFree(ctx->d_rank_lut);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
 
