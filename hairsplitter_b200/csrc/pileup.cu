@@ -157,6 +157,7 @@ struct PileupArgs {
     unsigned long long* stats;
     unsigned int* next_read;  // work counters of the persistent warps, one per length class
     int ops_long, ops_mid;    // CIGAR ops from which a read counts as long / medium
+    int k_one, k_four;        // 1 and 4, unknown to the assembler: see PW_STEP
 };
 
 // ---- K3: the CIGAR walk. Persistent warps, one read at a time, one LANE per run of 30 positions. ----
@@ -213,6 +214,32 @@ __device__ __forceinline__ uint32_t pw_read_window(const uint32_t* __restrict__ 
     return x;
 }
 
+// The same windows with symbol 0 in the TOP two bits, for the fast walk: taking a symbol is a shift by 30, moving on
+// is a multiplication by 4 -- IMAD on the FMA pipe instead of SHF on the ALU pipe, which bounds the kernel.
+__device__ __forceinline__ uint32_t pw_rev2(uint32_t x) {
+    x = __brev(x);
+    return ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+}
+template <bool CHECKED>
+__device__ __forceinline__ uint32_t pw_window_top(const uint32_t* __restrict__ w, int nw, int i) {
+    return pw_rev2(pw_window<CHECKED>(w, nw, i));
+}
+template <bool CHECKED>
+__device__ __forceinline__ uint32_t pw_read_window_top(const uint32_t* __restrict__ rb, int nw, int rlen, int tp, int strand) {
+    uint32_t x;
+    int nvalid;
+    if (strand) {
+        x = pw_rev2(pw_window<CHECKED>(rb, nw, tp));
+        nvalid = rlen - tp;
+    } else {
+        const int j = rlen - 1 - tp;  // bases j-15 .. j: the last one is the first symbol, and already on top
+        x = ~pw_window<CHECKED>(rb, nw, j - 15);
+        nvalid = j + 1;
+    }
+    if (CHECKED && nvalid < 16) x = (nvalid <= 0) ? 0u : (x & ~((1u << (32 - 2 * nvalid)) - 1u));
+    return x;
+}
+
 // set bits [a, a + n) of a warp-private bit array in shared memory, 0 < n <= 63 (one CIGAR op): at most three words.
 // Straight-line code on purpose: a loop around the atomics makes the compiler insert YIELDs and a non-reconvergent
 // barrier, and the warp then walks the rest of the window in two halves (measured: 16 active lanes per instruction).
@@ -255,27 +282,32 @@ __device__ __forceinline__ void pw_load_ops(const uint8_t* __restrict__ cig, int
 //   sym   = '-' for a deletion, else the next read symbol;  code = ctx + 25*sym, ctx = '!' + 5*b(-2) + b(-1)  (:238,287)
 //   a mismatch is counted for M and D positions ('-' never matches, :254-256,305); insertions are counted from the mask
 //   p1x   = 5*b(-1) + '!' of the next step
+// The kernel is bound by the ALU pipe (LOP3 / SHF / ISETP / SEL / IADD: 64 lanes per clock and SM), not by issue
+// slots, while the FMA pipe is almost idle. The windows keep their next symbol on top, so that advancing is a
+// multiplication by 4; the +1 of the staging address and of the mismatch count are multiply-adds by 1. %8 = 1 and
+// %9 = 4 come from the kernel parameters so that the assembler cannot turn them back into adds and shifts:
+// 6 ALU + 7 FMA + 1 LSU instructions per step instead of 10 + 3 + 1.
 #define PW_STEP_HEAD(BIT)                                   \
     "and.b32 t, %6, " #BIT ";\n\t"                          \
     "setp.ne.u32 pI, t, 0;\n\t"                             \
     "and.b32 t, %7, " #BIT ";\n\t"                          \
     "setp.ne.u32 pD, t, 0;\n\t"                             \
-    "and.b32 b, %0, 3;\n\t"                                 \
+    "shr.u32 b, %0, 30;\n\t"                                \
     "selp.b32 sym, 4, b, pD;\n\t"
 #define PW_STEP_EMIT                                        \
-    "and.b32 c, %1, 3;\n\t"                                 \
+    "shr.u32 c, %1, 30;\n\t"                                \
     "mad.lo.s32 code, sym, 25, %3;\n\t"                     \
     "@!pI st.shared.u8 [%2], code;\n\t"                     \
     "setp.ne.and.s32 pm, sym, c, !pI;\n\t"                  \
-    "@pm add.s32 %5, %5, 1;\n\t"
+    "@pm mad.lo.s32 %5, %8, %8, %5;\n\t"
 #define PW_STEP_TAIL                                        \
-    "@!pD shr.u32 %0, %0, 2;\n\t"                           \
-    "@!pI shr.u32 %1, %1, 2;\n\t"                           \
-    "@!pI add.s32 %2, %2, 1;\n\t"                           \
+    "@!pD mul.lo.u32 %0, %0, %9;\n\t"                       \
+    "@!pI mul.lo.u32 %1, %1, %9;\n\t"                       \
+    "@!pI mad.lo.s32 %2, %8, %8, %2;\n\t"                   \
     "add.s32 %3, %4, sym;\n\t"                              \
     "mad.lo.s32 %4, sym, 5, 33;\n\t"
 #define PW_STEP_REGS "{\n\t.reg .pred pI, pD, pm;\n\t.reg .b32 t, b, c, sym, code;\n\t"
-#define PW_STEP_OPS : "+r"(rw), "+r"(cw), "+r"(qa), "+r"(ctx), "+r"(p1x), "+r"(dist) : "r"(mI), "r"(mD)
+#define PW_STEP_OPS : "+r"(rw), "+r"(cw), "+r"(qa), "+r"(ctx), "+r"(p1x), "+r"(dist) : "r"(mI), "r"(mD), "r"(k_one), "r"(k_four)
 #define PW_WARM(BIT) asm volatile(PW_STEP_REGS PW_STEP_HEAD(BIT) PW_STEP_TAIL "}" PW_STEP_OPS)
 #define PW_STEP(BIT) asm volatile(PW_STEP_REGS PW_STEP_HEAD(BIT) PW_STEP_EMIT PW_STEP_TAIL "}" PW_STEP_OPS)
 
@@ -286,10 +318,10 @@ __device__ __forceinline__ void pw_walk_fast(const uint32_t mI, const uint32_t m
                                              const int carry_p1x, const uint32_t* __restrict__ rb, const int nrw,
                                              const int rlen, const int strand, int tp, const uint32_t* __restrict__ cb,
                                              const int ncw, const int q, unsigned int qa, int& ctx_out, int& p1x_out,
-                                             unsigned int& dist) {
+                                             unsigned int& dist, const int k_one, const int k_four) {
     int ctx = 0, p1x = 0;  // rebuilt by the two warm-up steps
-    uint32_t rw = pw_read_window<CHECKED>(rb, nrw, rlen, tp, strand);
-    uint32_t cw = pw_window<CHECKED>(cb, ncw, q);
+    uint32_t rw = pw_read_window_top<CHECKED>(rb, nrw, rlen, tp, strand);
+    uint32_t cw = pw_window_top<CHECKED>(cb, ncw, q);
     PW_WARM(0x1); PW_WARM(0x2);
     if (lane == 0) {  // lane 0 warmed up on two virtual positions: its context is the carry
         ctx = carry_ctx;
@@ -299,8 +331,8 @@ __device__ __forceinline__ void pw_walk_fast(const uint32_t mI, const uint32_t m
     PW_STEP(0x100); PW_STEP(0x200); PW_STEP(0x400); PW_STEP(0x800); PW_STEP(0x1000); PW_STEP(0x2000);
     PW_STEP(0x4000); PW_STEP(0x8000);
     const int lowI = __popc(mI & 0xffffu), lowD = __popc(mD & 0xffffu);
-    rw = pw_read_window<CHECKED>(rb, nrw, rlen, tp + 16 - lowD, strand);
-    cw = pw_window<CHECKED>(cb, ncw, q + 16 - lowI);
+    rw = pw_read_window_top<CHECKED>(rb, nrw, rlen, tp + 16 - lowD, strand);
+    cw = pw_window_top<CHECKED>(cb, ncw, q + 16 - lowI);
     PW_STEP(0x10000); PW_STEP(0x20000); PW_STEP(0x40000); PW_STEP(0x80000); PW_STEP(0x100000); PW_STEP(0x200000);
     PW_STEP(0x400000); PW_STEP(0x800000); PW_STEP(0x1000000); PW_STEP(0x2000000); PW_STEP(0x4000000);
     PW_STEP(0x8000000); PW_STEP(0x10000000); PW_STEP(0x20000000); PW_STEP(0x40000000); PW_STEP(0x80000000);
@@ -485,8 +517,8 @@ __global__ void __launch_bounds__(32 * PW_WARPS, 4) pileup_kernel(PileupArgs a) 
                 // every window of 16 symbols the lanes fetch stays inside the read and the contig (64 bases of margin:
                 // a fetch reaches at most 47 bases past the position it is made for)
                 const bool inside = q0 >= 64 && qend + 64 < L && t0 >= 64 && t0 + Enew + 64 < rlen;
-                if (inside) pw_walk_fast<false>(mI, mD, lane, carry_ctx, carry_p1x, rb, nrw, rlen, strand, tp, cb, ncw, q, qa, ctx, p1x, dist);
-                else pw_walk_fast<true>(mI, mD, lane, carry_ctx, carry_p1x, rb, nrw, rlen, strand, tp, cb, ncw, q, qa, ctx, p1x, dist);
+                if (inside) pw_walk_fast<false>(mI, mD, lane, carry_ctx, carry_p1x, rb, nrw, rlen, strand, tp, cb, ncw, q, qa, ctx, p1x, dist, a.k_one, a.k_four);
+                else pw_walk_fast<true>(mI, mD, lane, carry_ctx, carry_p1x, rb, nrw, rlen, strand, tp, cb, ncw, q, qa, ctx, p1x, dist, a.k_one, a.k_four);
                 ualen += Enew;
                 udist += totI;  // deletions count in the walk ('-' never equals the contig base)
             } else {
@@ -1022,6 +1054,8 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
             const int64_t mean_ops = p->n_cigar / std::max<int64_t>(nr, 1);
             a.ops_long = (int)std::min<int64_t>(2 * mean_ops + 1, 0x7fffffff);
             a.ops_mid = (int)std::min<int64_t>(mean_ops + 1, 0x7fffffff);
+            a.k_one = 1;
+            a.k_four = 4;
         }
         // persistent warps pull reads from a counter: read lengths vary by an order of magnitude
         static std::atomic<int> ctas_cache{0};  // a property of the kernel, the same on every sm_100 device
