@@ -266,6 +266,7 @@ struct hsgpu_pileup {
     uint32_t* d_fkept = nullptr;  // bitmap of the kept columns
     int32_t* d_fkept_list = nullptr;
     unsigned int* d_fcounters = nullptr;
+    uint32_t* d_foverflow = nullptr;  // columns handed from robust_filter_lanes_kernel to robust_filter_kernel
     int64_t* d_fhdr = nullptr;
 };
 

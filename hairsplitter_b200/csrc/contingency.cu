@@ -271,6 +271,8 @@ struct FilterArgs {
                              // columns (list reservation), [3] deep active columns (back of `active`), [5] their work
                              // cursor, [8..9] / [10..11] 64-bit: cells of the active columns / states read
     uint32_t* kept;          // bitmap over the columns of the batch (bit g & 31 of word g >> 5), zeroed by the caller
+    uint32_t* overflow;      // columns robust_filter_lanes_kernel hands to robust_filter_kernel ([6] their number, [7] cursor)
+    int from_overflow;       // robust_filter_kernel<false>: 1 = work off the overflow list instead of the front of `active`
 };
 
 __device__ __forceinline__ int rf_contig_of(const int64_t* __restrict__ col_base, int n_contigs, int64_t g) {
@@ -461,14 +463,14 @@ __global__ void __launch_bounds__(32 * RF_WARPS, MINB) robust_filter_kernel(Filt
     for (int i = lane; i < HS_NCODES + 3; i += 32) s_hist[i] = 0;
     if (lane == 0) *s_m = 0;
     __syncwarp();
-    const unsigned n_items = DEEP ? a.counters[3] : a.counters[0];
+    const unsigned n_items = DEEP ? a.counters[3] : (a.from_overflow ? a.counters[6] : a.counters[0]);
     const int64_t n_cols_all = a.g_end - a.g_begin;
     for (;;) {
         unsigned item = 0;
-        if (lane == 0) item = atomicAdd(a.counters + (DEEP ? 5 : 1), 1u);
+        if (lane == 0) item = atomicAdd(a.counters + (DEEP ? 5 : (a.from_overflow ? 7 : 1)), 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        const int64_t g = DEEP ? a.active[n_cols_all - 1 - item] : a.active[item];
+        const int64_t g = DEEP ? a.active[n_cols_all - 1 - item] : (a.from_overflow ? a.overflow[item] : a.active[item]);
         const int c = rf_contig_of(a.col_base, a.n_contigs, g);
         const FilterDesc d = a.desc[c];
         const int q = (int)(g - a.col_base[c]);
@@ -711,6 +713,359 @@ __global__ void __launch_bounds__(32 * RF_WARPS, MINB) robust_filter_kernel(Filt
                 }
             }
             __syncwarp();
+        }
+        if (lane == 0) {
+            if (keep) atomicOr(a.kept + (g >> 5), 1u << (g & 31));
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 8), (unsigned long long)ncell);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 10), (unsigned long long)ncell * (unsigned)n_visited);
+        }
+    }
+}
+
+// ---- loops 3+4, one LANE per partition (robust_filter_lanes_kernel) -------------------------------------------------
+// The kernel above takes the partitions of a column one after the other with the column's reads on the lanes; most
+// of its time went into the pairs where several codes tie for the alternative allele (a partition whose reads carry
+// ref_base plus a few different singletons is the common case of a suspect column), which one lane settled alone.
+// Here a warp still owns a column, but the lanes are the PARTITIONS that hold one of the column's reads: the column's
+// cells are grouped by code once (distinct codes in order of first appearance, at most RL_MAXC), every lane runs over
+// the cells of a code and counts its partition's states in one packed register (a byte per state), and the
+// per-partition decisions -- most frequent other code, ties by the bucket-table rule, 2x2 table, chi-square -- are
+// taken by all lanes at once. Columns with more distinct codes than RL_MAXC go to an overflow list that the kernel
+// above works off afterwards.
+#define RL_WARPS 4
+#define RL_MAXC 32
+
+// the alternative allele among tied codes, for this lane's partition: rf_select_alt_tied's bucket-table rule on the
+// column's code list and the lane's counts (s_acc column); returns the index of the code in the list, -1 for none,
+// -2 when the rule cannot decide (the literal replay needs the order of first appearance: rl_tied_slow)
+__device__ __noinline__ int rl_tied_fast(const uint8_t* s_clist, const uint32_t* s_acc_lane, int M, int jref, int ref, int nref,
+                                         int max2, int n_keys, const HsRankLut* __restrict__ lut) {
+    if (!lut || n_keys > 51) return -2;
+    const bool ref_excluded = ref < 128;
+    const int level = hs_rank_level(n_keys);
+    const uint8_t* __restrict__ home = lut->home[level];
+    unsigned long long occ0 = 0, occ1 = 0, occ2 = 0, occ3 = 0;  // 4-bit occupancy counters of up to 64 buckets
+    int best = 1 << 30, nbest = 0;
+    auto put = [&](int h) {
+        const unsigned long long one = 1ull << (4 * (h & 15));
+        const int w = h >> 4;
+        if (w == 0) occ0 += one; else if (w == 1) occ1 += one; else if (w == 2) occ2 += one; else occ3 += one;
+    };
+    if (jref < 0) put(__ldg(home + ref));  // content2[ref_base] creates the entry (:833)
+    for (int j = 0; j < M; j++) {
+        const uint32_t acc = s_acc_lane[j * 32];
+        const int any = (int)((acc >> 8) & 255u) + (int)((acc >> 16) & 255u) + (int)(acc >> 24);
+        const bool is_ref = j == jref;
+        if (!is_ref && any == 0) continue;  // not a key of this partition's map
+        const int h = __ldg(home + s_clist[j]);
+        put(h);
+        if (is_ref && (nref == 0 || ref_excluded)) continue;
+        if ((is_ref ? nref : any) != max2) continue;
+        if (h < (best >> 8)) { best = (h << 8) | j; nbest = 1; }
+        else if (h == (best >> 8)) nbest++;
+    }
+    int next_free = 0, maxd = 0;
+    const int nb = 8 << level;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        if (16 * w < nb) {
+            const unsigned long long o = w == 0 ? occ0 : (w == 1 ? occ1 : (w == 2 ? occ2 : occ3));
+#pragma unroll
+            for (int bb = 0; bb < 16; bb++) {
+                const int b = 16 * w + bb;
+                if (b < nb) {
+                    const int cnt = (int)((o >> (4 * bb)) & 15ull);
+                    if (next_free < b) next_free = b;
+                    next_free += cnt;
+                    if (cnt && next_free - 1 - b > maxd) maxd = next_free - 1 - b;
+                }
+            }
+        }
+    }
+    if (nbest == 1 && maxd < 6) return best & 0xff;
+    return -2;
+}
+
+// the literal replay for this lane's partition: order of first appearance among the partition's reads from the staged
+// cells (slot order = read order), counts from the lane's s_acc column; returns the code or ' '
+__device__ __noinline__ int rl_tied_slow(const uint8_t* s_code, const uint32_t* s_row, int ncell, int kw, int sh,
+                                         const uint8_t* s_clist, const uint32_t* s_acc_lane, int M, int ref, int nref, int max2) {
+    uint8_t order[HS_NCODES + 1];
+    uint32_t hist[HS_NCODES + 3];
+    for (int i = 0; i < HS_NCODES + 3; i++) hist[i] = 0;
+    int mo = 0;
+    for (int i = 0; i < ncell; i++) {
+        if (((s_row[i * 9 + kw] >> sh) & 3u) == 0) continue;
+        const int idx = s_code[i] - HS_CODE0;
+        bool seen = false;
+        for (int k = 0; k < mo; k++) seen |= order[k] == idx;
+        if (!seen) order[mo++] = (uint8_t)idx;
+    }
+    for (int j = 0; j < M; j++) {
+        const uint32_t acc = s_acc_lane[j * 32];
+        hist[s_clist[j] - HS_CODE0] = ((acc >> 8) & 255u) + ((acc >> 16) & 255u) + (acc >> 24);
+    }
+    (void)nref;  // the count of ref_base is part of the histogram already
+    return rf_select_alt_tied(order, hist, mo, ref, max2, nullptr);
+}
+
+__global__ void __launch_bounds__(32 * RL_WARPS) robust_filter_lanes_kernel(FilterArgs a) {
+    __shared__ uint8_t s_code_all[RL_WARPS][RF_CAP];
+    __shared__ uint16_t s_sorted_all[RL_WARPS][RF_CAP];  // word offsets of the cells' state rows, grouped by code
+    __shared__ uint32_t s_map_all[RL_WARPS][32];         // byte per code: its index in the column's list
+    __shared__ uint32_t s_cnt_all[RL_WARPS][RL_MAXC + 4];
+    __shared__ uint8_t s_clist_all[RL_WARPS][RL_MAXC];
+    __shared__ uint8_t s_cstart_all[RL_WARPS][RL_MAXC + 4];
+    __shared__ uint8_t s_plist_all[RL_WARPS][128];
+    __shared__ __align__(16) uint32_t s_row_all[RL_WARPS][RF_CAP * 9];  // 8 state words per cell, rows padded to 9 words
+    __shared__ uint32_t s_acc_all[RL_WARPS][RL_MAXC * 32];
+    // the run of ref_base cells (most of a column) is counted for four partitions at a time: s_lut[t - 1][x] has a 1 in
+    // byte i when field i of the eight state bits x equals t; s_ref = the three byte-packed counts per lane
+    __shared__ uint32_t s_lut[3 * 256];
+    __shared__ uint32_t s_ref_all[RL_WARPS][3 * 32];
+    for (int i = threadIdx.x; i < 3 * 256; i += 32 * RL_WARPS) {
+        const unsigned x = i & 255u, t = i / 256 + 1;
+        uint32_t v = 0;
+        for (int k = 0; k < 4; k++) v |= (uint32_t)(((x >> (2 * k)) & 3u) == t) << (8 * k);
+        s_lut[i] = v;
+    }
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* const s_ref = s_ref_all[wid];
+    uint8_t* const s_code = s_code_all[wid];
+    uint16_t* const s_sorted = s_sorted_all[wid];
+    uint32_t* const s_map = s_map_all[wid];
+    uint32_t* const s_cnt32 = s_cnt_all[wid];
+    uint8_t* const s_clist = s_clist_all[wid];
+    uint8_t* const s_cstart = s_cstart_all[wid];
+    uint8_t* const s_plist = s_plist_all[wid];
+    uint32_t* const s_row = s_row_all[wid];
+    uint32_t* const s_acc = s_acc_all[wid];
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned n_items = a.counters[0];
+    constexpr int NCH = RF_CAP / 32;
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(a.counters + 1, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int64_t g = a.active[item];
+        const int c = rf_contig_of(a.col_base, a.n_contigs, g);
+        const FilterDesc d = a.desc[c];
+        const int q = (int)(g - a.col_base[c]);
+        const int64_t read0 = a.contig_read_off[c];
+        const int64_t tile = a.tile_base[c] + q / HS_TILE;
+        const int64_t l0 = a.tile_off[tile], l1 = a.tile_off[tile + 1];
+        const int ref = a.k0[g];
+        const unsigned f = a.flags[g];
+        const bool inlist = (f & a.in_flag) != 0;
+        const uint32_t* __restrict__ rows_c = a.rows + d.row_off;
+        __syncwarp();
+        // ---- the column's cells, in ascending read order: compacted, slot 32 * ch + lane ----
+        int code4[NCH];
+        int32_t n4[NCH];
+        int ncell = 0;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) { code4[ch] = 0; n4[ch] = 0; }
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) {
+            if (l0 + 32 * ch < l1) {
+                const RfCell cl = rf_gather_cell(a, q, l0 + 32 * ch, l1, read0, lane);
+                const unsigned mk = __ballot_sync(0xffffffffu, cl.code != 0);
+                const int o = ncell + __popc(mk & lt);
+                if (cl.code != 0) {
+                    s_code[o] = (uint8_t)cl.code;
+                    s_row[o * 9 + 8] = (uint32_t)cl.n;  // the pad word of the row carries the read index until staged
+                }
+                ncell += __popc(mk);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) {
+            const int slot = 32 * ch + lane;
+            if (slot < ncell) {
+                code4[ch] = s_code[slot];
+                n4[ch] = (int32_t)s_row[slot * 9 + 8];
+            }
+        }
+        // ---- the column's distinct codes (any order: the tie rules do not depend on it) and the cells grouped by
+        // code: s_map[code] = index in the list, claimed chunk by chunk by the first lane of every group of equal
+        // codes; then a counting sort of the cell slots by that index ----
+        s_map[lane] = 0xffffffffu;  // 128 bytes: codes - HS_CODE0 < 128
+        for (int i = lane; i < RL_MAXC + 4; i += 32) s_cnt32[i] = 0u;
+        __syncwarp();
+        int M = 0, jref = -1;
+        int cidx4[NCH];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) {
+            cidx4[ch] = 0;
+            if (32 * ch < ncell) {
+                const bool valid = code4[ch] != 0;
+                const unsigned peers = __match_any_sync(0xffffffffu, code4[ch]);
+                uint8_t* const slot_of = reinterpret_cast<uint8_t*>(s_map) + (valid ? code4[ch] - HS_CODE0 : 0);
+                const bool isnew = valid && (__ffs(peers) - 1 == lane) && *slot_of == 0xff;
+                const unsigned nm = __ballot_sync(0xffffffffu, isnew);
+                if (isnew) {
+                    const int j = M + __popc(nm & lt);
+                    *slot_of = (uint8_t)min(j, 0xfe);
+                    if (j < RL_MAXC) s_clist[j] = (uint8_t)code4[ch];
+                }
+                M += __popc(nm);
+                __syncwarp();
+            }
+        }
+        if (M > RL_MAXC) {  // more distinct codes than the lanes keep counts for: the general kernel takes the column
+            if (lane == 0) a.overflow[atomicAdd(a.counters + 6, 1u)] = (uint32_t)g;
+            continue;
+        }
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++) {
+            if (code4[ch] != 0) {
+                cidx4[ch] = reinterpret_cast<const uint8_t*>(s_map)[code4[ch] - HS_CODE0];
+                atomicAdd(&s_cnt32[cidx4[ch]], 1u);
+            }
+        }
+        __syncwarp();
+        {
+            const int cnt = lane < M ? (int)s_cnt32[lane] : 0;
+            const int incl = hs_warp_incl_scan(cnt, lane);
+            if (lane < M) {
+                s_cstart[lane] = (uint8_t)(incl - cnt);
+                s_cnt32[lane] = (uint32_t)(incl - cnt);  // becomes the fill cursor of the code
+                if (s_clist[lane] == ref) jref = lane;
+            }
+            if (lane == M - 1 || (M == 0 && lane == 0)) s_cstart[M] = (uint8_t)(M ? incl : 0);
+            jref = __reduce_max_sync(0xffffffffu, jref);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++)
+            if (code4[ch] != 0) s_sorted[atomicAdd(&s_cnt32[cidx4[ch]], 1u)] = (uint16_t)((32 * ch + lane) * 9);
+        __syncwarp();
+        bool keep = false;
+        int n_visited = 0;
+        for (int pb = 0; pb < d.n_parts && !keep; pb += 128) {
+            // the cells' state rows of this block of 128 partitions; which partitions hold one of the column's reads
+            uint32_t nz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+                if (code4[ch] != 0) {
+                    const int slot = 32 * ch + lane;
+                    const uint4* src = reinterpret_cast<const uint4*>(rows_c + (int64_t)n4[ch] * d.pwords + (pb >> 4));
+                    const uint4 x = __ldg(src), y = __ldg(src + 1);
+                    const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        nz[k] |= w[k];
+                        s_row[slot * 9 + k] = w[k];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                nz[k] = __reduce_or_sync(0xffffffffu, nz[k]);
+                nz[k] = (nz[k] | (nz[k] >> 1)) & 0x55555555u;  // bit 2j = partition 16k + j holds a read of the column
+            }
+            // the list of those partitions, ascending
+            int n_present = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t wz = lane < 16 ? nz[2 * r] : nz[2 * r + 1];
+                const bool pres = (wz >> (2 * (lane & 15))) & 1u;
+                const unsigned mk = __ballot_sync(0xffffffffu, pres);
+                if (pres) s_plist[n_present + __popc(mk & lt)] = (uint8_t)(32 * r + lane);
+                n_present += __popc(mk);
+            }
+            __syncwarp();
+            n_visited += n_present;
+            if (jref >= 0) {  // lane = (state word, byte of it): partitions 16 * (lane >> 2) + 4 * (lane & 3) .. + 3
+                const int kwq = lane >> 2, shq = 8 * (lane & 3);
+                const int x1 = s_cstart[jref + 1];
+                uint32_t r1 = 0, r2 = 0, r3 = 0;
+#pragma unroll 4
+                for (int x = s_cstart[jref]; x < x1; x++) {
+                    const uint32_t xx = (s_row[(int)s_sorted[x] + kwq] >> shq) & 255u;
+                    r1 += s_lut[xx];
+                    r2 += s_lut[256 + xx];
+                    r3 += s_lut[512 + xx];
+                }
+                s_ref[lane] = r1;
+                s_ref[32 + lane] = r2;
+                s_ref[64 + lane] = r3;
+                __syncwarp();
+            }
+            for (int g0 = 0; g0 < n_present && !keep; g0 += 32) {
+                const bool has = g0 + lane < n_present;
+                const int pl = has ? s_plist[g0 + lane] : 0;
+                const int kw = pl >> 4, sh = 2 * (pl & 15);
+                // counts of this lane's partition per code: byte 1 = state +1, byte 2 = state -1, byte 3 = state 0
+                int nb = 0, nref = 0, n11 = 0, n01 = 0, maxc = -1, ndist = 0, ties = 0, jbest = -1;
+#pragma unroll 1
+                for (int j = 0; j < M; j++) {
+                    const int x1 = s_cstart[j + 1];
+                    uint32_t acc = 0;
+                    if (j == jref) {
+                        const int rl = pl >> 2, rs = 8 * (pl & 3);
+                        acc = (((s_ref[rl] >> rs) & 255u) << 8) | (((s_ref[32 + rl] >> rs) & 255u) << 16) |
+                              (((s_ref[64 + rl] >> rs) & 255u) << 24);
+                    } else {
+#pragma unroll 4
+                        for (int x = s_cstart[j]; x < x1; x++) {
+                            const uint32_t t = (s_row[(int)s_sorted[x] + kw] >> sh) & 3u;
+                            acc += 1u << (8 * t);
+                        }
+                    }
+                    s_acc[j * 32 + lane] = acc;
+                    const int b1 = (int)((acc >> 8) & 255u), b2 = (int)((acc >> 16) & 255u);
+                    const int any = b1 + b2 + (int)(acc >> 24);
+                    nb += any;
+                    if (j == jref) {
+                        nref = any;
+                        n11 = b1;
+                        n01 = b2;
+                    } else if (any > 0) {
+                        ndist++;
+                        if (any > maxc) { maxc = any; ties = 1; jbest = j; }
+                        else if (any == maxc) ties++;
+                    }
+                }
+                bool keep_l = false;
+                if (has && nb > 0 && (inlist || ref >= 128 || maxc > 4)) {
+                    // secondFrequent (:832-844): the most frequent code other than ref_base (ref_base itself competes
+                    // when it is >= 128)
+                    int max2 = maxc, jalt = jbest;
+                    if (ref >= 128 && nref > 0) {
+                        if (nref > max2) { max2 = nref; ties = 1; jalt = jref; }
+                        else if (nref == max2) ties++;
+                    }
+                    if (max2 < 0) jalt = -1;
+                    if (max2 >= 0 && ties > 1) {
+                        jalt = rl_tied_fast(s_clist, s_acc + lane, M, jref, ref, nref, max2, ndist + 1, a.lut);
+                        if (jalt == -2) {
+                            const int alt = rl_tied_slow(s_code, s_row, ncell, kw, sh, s_clist, s_acc + lane, M, ref, nref, max2);
+                            jalt = -1;
+                            for (int j = 0; j < M; j++) if (s_clist[j] == alt) jalt = j;
+                        }
+                    }
+                    int n10 = 0, n00 = 0;
+                    if (jalt >= 0 && jalt != jref) {
+                        const uint32_t acc = s_acc[jalt * 32 + lane];
+                        n10 = (int)((acc >> 8) & 255u);
+                        n00 = (int)((acc >> 16) & 255u);
+                    }
+                    // loop 3 (:721-738): columns of snps_in; loop 4 (:745-764): rescue of every other column (also of
+                    // suspects that failed loop 3)
+                    const bool c3 = inlist && (double)(n00 + n01 + n10 + n11) > __dmul_rn(0.5, (double)a.depth[g]);
+                    const bool c4 = (f & HS_FLAG_RESCUE) && n10 + n00 > 4 && n01 + n11 > 4;
+                    if (c3 || c4) {
+                        const float chi = rf_chi_square(n00, n01, n10, n11);
+                        keep_l = (c3 && chi > 15.f) || (c4 && (double)chi > 20.0);
+                    }
+                }
+                keep = __any_sync(0xffffffffu, keep_l);
+            }
         }
         if (lane == 0) {
             if (keep) atomicOr(a.kept + (g >> 5), 1u << (g & 31));
@@ -1022,6 +1377,7 @@ static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t 
         cv.add(&p->d_fkept, p->n_cols / 32 + 2);
         cv.add(&p->d_fkept_list, p->n_cols);
         cv.add(&p->d_fcounters, 12);
+        cv.add(&p->d_foverflow, p->n_cols);
         cv.add(&p->d_fhdr, 2 * (int64_t)p->n_contigs + 2);
         HS_CUDA(ctx, cv.alloc(ctx, &p->d_filter_work));
     }
@@ -1055,11 +1411,20 @@ static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t 
     HS_KERNEL(ctx, "filter_active_kernel", filter_active_kernel<<<(unsigned)((ncols + 3 + 4 * 256 - 1) / (4 * 256) + 1), 256, 0, ctx->stream>>>(a));
     // persistent warps pull active columns from a counter (their cost varies with depth and partition count)
     // HSGPU_FILTER_OCC=3: the build with 3 CTAs per SM (more registers, no spills) instead of 4, for A/B measurements
-    static const bool occ3 = getenv("HSGPU_FILTER_OCC") && atoi(getenv("HSGPU_FILTER_OCC")) == 3;
-    if (occ3)
-        HS_KERNEL(ctx, "robust_filter_kernel", robust_filter_kernel<false, 3><<<ctx->sm_count * 3, 32 * RF_WARPS, 0, ctx->stream>>>(a));
-    else
+    // HSGPU_FILTER_LANES=0: the lane-per-read kernel for every column, for A/B measurements
+    static const bool by_lanes = !getenv("HSGPU_FILTER_LANES") || atoi(getenv("HSGPU_FILTER_LANES")) != 0;
+    static const int lanes_ctas = getenv("HSGPU_FILTER_CTAS") ? std::max(1, atoi(getenv("HSGPU_FILTER_CTAS"))) : 5;
+    a.overflow = p->d_foverflow;
+    a.from_overflow = 0;
+    if (by_lanes) {
+        HS_KERNEL(ctx, "robust_filter_lanes_kernel",
+                  robust_filter_lanes_kernel<<<ctx->sm_count * lanes_ctas, 32 * RL_WARPS, 0, ctx->stream>>>(a));
+        a.from_overflow = 1;  // columns with more distinct codes than the lanes keep counts for (rare)
+        HS_KERNEL(ctx, "robust_filter_kernel<overflow>", robust_filter_kernel<false, 4><<<ctx->sm_count, 32 * RF_WARPS, 0, ctx->stream>>>(a));
+        a.from_overflow = 0;
+    } else {
         HS_KERNEL(ctx, "robust_filter_kernel", robust_filter_kernel<false, 4><<<ctx->sm_count * 4, 32 * RF_WARPS, 0, ctx->stream>>>(a));
+    }
     // amplicon-deep columns (tiles with more than RF_CAP reads): only when the batch has such a tile
     {
         const int rc_max = hs_resolve_max_tile_reads(p);
