@@ -752,10 +752,18 @@ def main():
     pu.partitions_set(prepared=prepared)
     kept_cap = n_cols
 
+    step_trace = [] if os.environ.get("HS_STEP_TRACE") else None
+
     def step(pu):
+        t0 = time.perf_counter()
         pu.build()                                 # generate_msa
+        t1 = time.perf_counter()
         pu.column_rank()                           # call_variants
-        return pu.robust_filter_all(kept_cap)      # loops 3+4 of keep_only_robust_variants -> snps_out
+        t2 = time.perf_counter()
+        out = pu.robust_filter_all(kept_cap)       # loops 3+4 of keep_only_robust_variants -> snps_out
+        if step_trace is not None:
+            step_trace.append((t1 - t0, t2 - t1, time.perf_counter() - t2))
+        return out
 
     # ---- value: inputs resident in HBM ----
     for _ in range(max(args.warmup, 0)):
@@ -772,6 +780,9 @@ def main():
     ev1.record(stream)
     ctx.sync()
     barrier()
+    if step_trace:
+        for tr in step_trace[-args.steps:]:
+            print("  step host ms: build %.2f rank %.2f filter_all %.2f" % tuple(x * 1e3 for x in tr), file=sys.stderr)
     clk = clocks.stop()
     launches = ctx.launches() - l0
     ms_total = ev0.elapsed_time(ev1)

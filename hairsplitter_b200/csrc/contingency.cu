@@ -819,19 +819,7 @@ __global__ void __launch_bounds__(32 * RL_WARPS) robust_filter_lanes_kernel(Filt
     __shared__ uint8_t s_plist_all[RL_WARPS][128];
     __shared__ __align__(16) uint32_t s_row_all[RL_WARPS][RF_CAP * 9];  // 8 state words per cell, rows padded to 9 words
     __shared__ uint32_t s_acc_all[RL_WARPS][RL_MAXC * 32];
-    // the run of ref_base cells (most of a column) is counted for four partitions at a time: s_lut[t - 1][x] has a 1 in
-    // byte i when field i of the eight state bits x equals t; s_ref = the three byte-packed counts per lane
-    __shared__ uint32_t s_lut[3 * 256];
-    __shared__ uint32_t s_ref_all[RL_WARPS][3 * 32];
-    for (int i = threadIdx.x; i < 3 * 256; i += 32 * RL_WARPS) {
-        const unsigned x = i & 255u, t = i / 256 + 1;
-        uint32_t v = 0;
-        for (int k = 0; k < 4; k++) v |= (uint32_t)(((x >> (2 * k)) & 3u) == t) << (8 * k);
-        s_lut[i] = v;
-    }
-    __syncthreads();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* const s_ref = s_ref_all[wid];
     uint8_t* const s_code = s_code_all[wid];
     uint16_t* const s_sorted = s_sorted_all[wid];
     uint32_t* const s_map = s_map_all[wid];
@@ -980,22 +968,6 @@ __global__ void __launch_bounds__(32 * RL_WARPS) robust_filter_lanes_kernel(Filt
             }
             __syncwarp();
             n_visited += n_present;
-            if (jref >= 0) {  // lane = (state word, byte of it): partitions 16 * (lane >> 2) + 4 * (lane & 3) .. + 3
-                const int kwq = lane >> 2, shq = 8 * (lane & 3);
-                const int x1 = s_cstart[jref + 1];
-                uint32_t r1 = 0, r2 = 0, r3 = 0;
-#pragma unroll 4
-                for (int x = s_cstart[jref]; x < x1; x++) {
-                    const uint32_t xx = (s_row[(int)s_sorted[x] + kwq] >> shq) & 255u;
-                    r1 += s_lut[xx];
-                    r2 += s_lut[256 + xx];
-                    r3 += s_lut[512 + xx];
-                }
-                s_ref[lane] = r1;
-                s_ref[32 + lane] = r2;
-                s_ref[64 + lane] = r3;
-                __syncwarp();
-            }
             for (int g0 = 0; g0 < n_present && !keep; g0 += 32) {
                 const bool has = g0 + lane < n_present;
                 const int pl = has ? s_plist[g0 + lane] : 0;
@@ -1006,16 +978,10 @@ __global__ void __launch_bounds__(32 * RL_WARPS) robust_filter_lanes_kernel(Filt
                 for (int j = 0; j < M; j++) {
                     const int x1 = s_cstart[j + 1];
                     uint32_t acc = 0;
-                    if (j == jref) {
-                        const int rl = pl >> 2, rs = 8 * (pl & 3);
-                        acc = (((s_ref[rl] >> rs) & 255u) << 8) | (((s_ref[32 + rl] >> rs) & 255u) << 16) |
-                              (((s_ref[64 + rl] >> rs) & 255u) << 24);
-                    } else {
 #pragma unroll 4
-                        for (int x = s_cstart[j]; x < x1; x++) {
-                            const uint32_t t = (s_row[(int)s_sorted[x] + kw] >> sh) & 3u;
-                            acc += 1u << (8 * t);
-                        }
+                    for (int x = s_cstart[j]; x < x1; x++) {
+                        const uint32_t t = (s_row[(int)s_sorted[x] + kw] >> sh) & 3u;
+                        acc += 1u << (8 * t);
                     }
                     s_acc[j * 32 + lane] = acc;
                     const int b1 = (int)((acc >> 8) & 255u), b2 = (int)((acc >> 16) & 255u);

@@ -141,18 +141,21 @@ def test_many_partitions_tables(gpu_ctx, oracle):
     pu.close()
 
 
-@pytest.mark.parametrize("case", ["small", "medium", "hifi", "deep", "many_parts", "over128_parts"])
+@pytest.mark.parametrize("case", ["small", "medium", "hifi", "deep", "many_parts", "over128_parts", "noisy"])
 def test_robust_filter_matches_oracle(gpu_ctx, oracle, case):
     cb = {"small": lambda: cases.small_case(seed=91), "medium": lambda: cases.medium_case(seed=92),
           "hifi": lambda: cases.hifi_case(seed=93), "deep": lambda: cases.deep_case(seed=94),
           "many_parts": lambda: cases.small_case(seed=95),
-          "over128_parts": lambda: cases.small_case(seed=96, length=4000, depth=40)}[case]()
+          "over128_parts": lambda: cases.small_case(seed=96, length=4000, depth=40),
+          # 35 % error at depth ~100: a fifth of the columns have more than 32 distinct codes (up to 45), which the
+          # lane-per-partition kernel hands over to the lane-per-read kernel
+          "noisy": lambda: cases.small_case(seed=97, length=3000, depth=110, mean_len=1500, error=0.35)}[case]()
     pk, pu = _build(gpu_ctx, [cb])
     o, oc, md = _check_contig(oracle, pu, 0, cb)
     rng = np.random.default_rng(7)
     parts = None
     from oracle import pyoracle
-    if pyoracle.ref_available() and case not in ("many_parts", "over128_parts"):
+    if pyoracle.ref_available() and case not in ("many_parts", "over128_parts", "noisy"):
         R = pyoracle.RefCV(cb)
         rc = R.call_variants()
         assert np.array_equal(rc["suspects"]["pos"], oc["suspect_pos"])
@@ -161,7 +164,7 @@ def test_robust_filter_matches_oracle(gpu_ctx, oracle, case):
         assert np.array_equal(kept, filt["pos"])  # the reference's own snps_out
     if parts is None or len(parts) == 0:
         # over128_parts: the kernel takes partitions 128 at a time (presence masks, transposed state rows of 160)
-        parts = _random_partitions(rng, cb, o, {"many_parts": 70, "over128_parts": 150}.get(case, 12))
+        parts = _random_partitions(rng, cb, o, {"many_parts": 70, "over128_parts": 150, "noisy": 40}.get(case, 12))
     want = oracle.robust_filter(o["col_off"], o["read_idx"], o["code"], oc["ref_base"], oc["second_base"], parts,
                                 oc["suspect_pos"])
     kept = pu.robust_filter(0, parts, oc["suspect_pos"])
