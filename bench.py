@@ -811,6 +811,8 @@ def main():
         # partition that holds the read, 1 B kept flag out per column
         "robust_filter_kernel": finfo["active_cells"] * 3.0 + finfo["active_cells"] * finfo["parts_per_cell"] + n_cols * 1.0,
     }
+    # the same bytes whichever kernel instance does the ordinary depths (one lane per partition by default)
+    alg_bytes["robust_filter_lanes_kernel"] = alg_bytes["robust_filter_kernel"]
     peaks, ipeaks = load_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
@@ -829,10 +831,10 @@ def main():
         kernels.append(k)
     # the robust filter runs as two launches of one template (ordinary tiles, then tiles deeper than its shared-memory
     # stage); the active cells are counted over both, so the pair is one roofline entry
-    fam = [k for k in kernels if k["name"].startswith("robust_filter_kernel")]
+    fam = [k for k in kernels if k["name"].startswith("robust_filter_") and "overflow" not in k["name"]]
     if len(fam) == 2:
         ms_f = sum(k["ms_per_step"] for k in fam)
-        both = {"name": "robust_filter_kernel", "ms_per_step": ms_f, "launches_per_step": 2.0,
+        both = {"name": fam[0]["name"].split("<")[0] + " + " + fam[1]["name"], "ms_per_step": ms_f, "launches_per_step": 2.0,
                 "alg_bytes_per_launch": alg_bytes["robust_filter_kernel"],
                 "achieved_gbs": alg_bytes["robust_filter_kernel"] / (ms_f * 1e-3) / 1e9}
         for k in fam:
@@ -854,8 +856,15 @@ def main():
                     "traffic": tr.get("bytes") if isinstance(tr, dict) else tr,
                     "traffic_source": (tr.get("source") if isinstance(tr, dict) else
                                        "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)") if tr else None,
-                    "share_of_step": dom["ms_per_step"] / sum(k["ms_per_step"] for k in kernels),
+                    "share_of_step": dom["ms_per_step"] / sum(k["ms_per_step"] for k in kernels if k is not both),
                     "note": "per-launch duration from CUDA events on the launching stream, second pass of the same steps"}
+    if roofline and roofline["kernel"].startswith("robust_filter"):
+        # not a streaming kernel: its work is one 2-bit state per (active cell, partition that holds a read of the column)
+        pairs = float(finfo["state_bytes"])
+        roofline["work"] = {"cell_partition_pairs_per_launch": pairs,
+                            "pairs_per_s": pairs / (dom["ms_per_step"] * 1e-3),
+                            "note": "latency / issue bound (ncu: profiles/r02w_ncu_filter_lanes.txt); the HBM fraction is "
+                                    "reported because the contract asks for it"}
     pu.close()
 
     # ---- e2e: host buffers -> C ABI -> host results, every step ----

@@ -212,7 +212,7 @@ extern "C" int hsgpu_clip_reads(hsgpu_ctx* ctx, int64_t n_reads, const uint32_t*
     ctx->launches++;
     e = cudaGetLastError();
     if (e == cudaSuccess) e = hs_d2h(ctx, out, d_out, n_items);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = hs_stream_sync(ctx);
     hs_free(ctx, block);
     if (e != cudaSuccess) return hs_cuda_fail(ctx, e, "hsgpu_clip_reads", __FILE__, __LINE__);
     return HSGPU_OK;

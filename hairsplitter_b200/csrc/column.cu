@@ -672,7 +672,7 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
     HS_CUDA(ctx, cudaMemsetAsync(p->d_min_reads + nc, 0, sizeof(int32_t), ctx->stream));
     HS_KERNEL(ctx, "min_reads_kernel", min_reads_kernel<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(nc, p->d_stats, d_me, p->d_min_reads));
     if (mean_error) {
-        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // mean_error is caller memory
+        HS_CUDA(ctx, hs_stream_sync(ctx));  // mean_error is caller memory
         hs_free(ctx, d_me);
     }
     static std::atomic<bool> attr_set[64];  // per device: function attributes belong to the device's context
@@ -766,7 +766,7 @@ int hsgpu_column_counts(hsgpu_pileup* p, int32_t* n_suspects, int64_t* depth_sum
     HS_CUDA(ctx, hs_d2h(ctx, &err, p->d_min_reads + p->n_contigs, 1));
     if (n_suspects) HS_CUDA(ctx, hs_d2h(ctx, n_suspects, p->d_n_suspects, p->n_contigs));
     if (depth_sum) HS_CUDA(ctx, hs_d2h(ctx, (unsigned long long*)depth_sum, p->d_depth_sum, p->n_contigs));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     if (err) HS_FAIL(ctx, HSGPU_ERR_LIMIT, "hsgpu_column_rank: more than 65000 reads over one 128-column tile");
     return HSGPU_OK;
 }
@@ -778,11 +778,11 @@ int hsgpu_suspects(hsgpu_pileup* p, int32_t contig, int32_t capacity, int32_t* p
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     int32_t n = 0;
     HS_CUDA(ctx, hs_d2h(ctx, &n, p->d_n_suspects + contig, 1));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     if (n > capacity) HS_FAIL(ctx, HSGPU_ERR_CAPACITY, "hsgpu_suspects: capacity too small");
     if (pos) HS_CUDA(ctx, hs_d2h(ctx, pos, p->d_suspect_pos + p->h_suspect_base[contig], n));
     if (is_automatic) HS_CUDA(ctx, hs_d2h(ctx, is_automatic, p->d_suspect_auto + p->h_suspect_base[contig], n));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     return HSGPU_OK;
 }
 
@@ -807,7 +807,7 @@ int hsgpu_suspects_all(hsgpu_pileup* p, int64_t capacity, int32_t* pos, uint8_t*
     int64_t* h_hdr = reinterpret_cast<int64_t*>(hs_host_stage(ctx, hdr_bytes));
     if (!h_hdr) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu_suspects_all: pinned staging allocation failed");
     HS_CUDA(ctx, cudaMemcpyAsync(h_hdr, d_hdr, hdr_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     const int64_t err = h_hdr[0];
     std::copy(h_hdr + 1, h_hdr + nc + 2, off);
     if (depth_sum) std::copy(h_hdr + nc + 2, h_hdr + 2 * nc + 2, depth_sum);
@@ -826,7 +826,7 @@ int hsgpu_suspects_all(hsgpu_pileup* p, int64_t capacity, int32_t* pos, uint8_t*
         if (!h) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu_suspects_all: pinned staging allocation failed");
         if (pos) HS_CUDA(ctx, cudaMemcpyAsync(h, d_pos, pos_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (is_automatic) HS_CUDA(ctx, cudaMemcpyAsync(h + pos_bytes, d_auto, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
-        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        HS_CUDA(ctx, hs_stream_sync(ctx));
         if (pos) memcpy(pos, h, pos_bytes);
         if (is_automatic) memcpy(is_automatic, h + pos_bytes, (size_t)total);
     }
@@ -847,7 +847,7 @@ int hsgpu_column_summary(hsgpu_pileup* p, int32_t contig, uint8_t* ref_base, uin
     if (second_base) HS_CUDA(ctx, hs_d2h(ctx, second_base, p->d_k1 + g0, L));
     if (counts) HS_CUDA(ctx, hs_d2h(ctx, counts, p->d_counts + 3 * g0, 3 * L));
     if (depth) HS_CUDA(ctx, hs_d2h(ctx, depth, p->d_depth + g0, L));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     return HSGPU_OK;
 }
 
@@ -871,7 +871,7 @@ int hsgpu_pileup_export(hsgpu_pileup* p, int32_t contig, int64_t cell_capacity, 
     if (rc) return rc;
     const int64_t g0 = p->h_col_base[contig], L = p->h_contig_len[contig];
     HS_CUDA(ctx, hs_d2h(ctx, col_off, p->d_col_off + g0, L + 1));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     const int64_t first = col_off[0];
     for (int64_t i = 0; i <= L; i++) col_off[i] -= first;
     const int64_t n = col_off[L];
@@ -891,7 +891,7 @@ int hsgpu_pileup_export(hsgpu_pileup* p, int32_t contig, int64_t cell_capacity, 
                                                                p->d_row_base, p->d_codes, p->d_col_off, d_idx, d_code));
     HS_CUDA(ctx, hs_d2h(ctx, read_idx, d_idx, n));
     HS_CUDA(ctx, hs_d2h(ctx, code, d_code, n));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     hs_free(ctx, d_idx);
     hs_free(ctx, d_code);
     return HSGPU_OK;
@@ -916,7 +916,7 @@ int hsgpu_pileup_extract_columns(hsgpu_pileup* p, int32_t contig, int32_t n_cols
     HS_KERNEL(ctx, "gather_depth_kernel", gather_depth_kernel<<<(n_cols + 255) / 256, 256, 0, ctx->stream>>>(n_cols, d_pos, p->h_col_base[contig], p->d_depth,
                                                                        d_off));
     HS_CUDA(ctx, hs_d2h(ctx, off + 1, d_off, n_cols));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     for (int i = 0; i < n_cols; i++) off[i + 1] += off[i];  // depths -> offsets (n_cols is small)
     const int64_t n = off[n_cols];
     int rc = HSGPU_OK;
@@ -937,11 +937,11 @@ int hsgpu_pileup_extract_columns(hsgpu_pileup* p, int32_t contig, int32_t n_cols
                                                                   p->d_row_base, p->d_codes, d_off, d_idx, d_code));
         HS_CUDA(ctx, hs_d2h(ctx, read_idx, d_idx, n));
         HS_CUDA(ctx, hs_d2h(ctx, code, d_code, n));
-        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        HS_CUDA(ctx, hs_stream_sync(ctx));
         hs_free(ctx, d_idx);
         hs_free(ctx, d_code);
     }
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     hs_free(ctx, d_pos);
     hs_free(ctx, d_off);
     return rc;

@@ -41,7 +41,18 @@ struct hsgpu_ctx {
     // different streams kept making the pool grow -- physical allocations under the driver's global lock, 10-20 ms
     // stalls of every thread)
     cudaMemPool_t pool = nullptr;
+    // how the host waits for the stream: spinning (the driver's default, lowest latency) or sleeping on an event
+    // created with cudaEventBlockingSync (HSGPU_WAIT=block: several contexts per core, e.g. 8 ranks x 3 host threads
+    // on a 16-core box, where spinning waiters take the cores from the threads that have work)
+    cudaEvent_t wait_event = nullptr;
 };
+
+static inline cudaError_t hs_stream_sync(hsgpu_ctx* ctx) {
+    if (!ctx->wait_event) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->wait_event, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->wait_event);
+}
 
 static inline cudaError_t hs_malloc_async(hsgpu_ctx* ctx, void** p, size_t bytes) {
     if (ctx->pool) return cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream);

@@ -1189,7 +1189,7 @@ int hsgpu_partition_tables(hsgpu_pileup* p, int32_t contig, const hsgpu_partitio
     a.out = d_out;
     HS_KERNEL(ctx, "partition_tables_kernel", partition_tables_kernel<<<n_cols, 128, kTablesSmem, ctx->stream>>>(a));
     HS_CUDA(ctx, hs_d2h(ctx, out, d_out, n_out));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     hs_free(ctx, d_pst);
     hs_free(ctx, d_pos);
     hs_free(ctx, d_out);
@@ -1317,7 +1317,7 @@ static int filter_set(hsgpu_pileup* p, int c0, int n, const hsgpu_partitions* pa
                       reinterpret_cast<const int32_t*>(dev + ((uint8_t*)o_idx - h)), dev + ((uint8_t*)o_st - h),
                       reinterpret_cast<const FilterDesc*>(p->d_fdesc), p->d_frows));
     const auto t_queued = std::chrono::steady_clock::now();
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging area is reused by the next call
+    HS_CUDA(ctx, hs_stream_sync(ctx));  // the staging area is reused by the next call
     if (timing) {
         const auto t_end = std::chrono::steady_clock::now();
         auto ms = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) {
@@ -1403,7 +1403,7 @@ static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t 
     int64_t* h_hdr = reinterpret_cast<int64_t*>(hs_host_stage(ctx, sizeof(int64_t) * (size_t)(2 * n)));
     if (!h_hdr) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu: pinned staging allocation failed");
     HS_CUDA(ctx, cudaMemcpyAsync(h_hdr, p->d_fhdr, sizeof(int64_t) * (size_t)(2 * n), cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     std::vector<int64_t> start((size_t)n), count((size_t)n);
     int64_t total = 0;
     for (int i = 0; i < n; i++) {
@@ -1417,7 +1417,7 @@ static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t 
         int32_t* h_list = reinterpret_cast<int32_t*>(hs_host_stage(ctx, sizeof(int32_t) * (size_t)total));
         if (!h_list) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu: pinned staging allocation failed");
         HS_CUDA(ctx, cudaMemcpyAsync(h_list, p->d_fkept_list, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
-        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        HS_CUDA(ctx, hs_stream_sync(ctx));
         for (int i = 0; i < n; i++)  // the contigs reserved their slices in the order their CTAs got there
             memcpy(kept + off[i], h_list + start[i], sizeof(int32_t) * (size_t)count[i]);
     }
@@ -1436,7 +1436,7 @@ int hsgpu_pileup_info(hsgpu_pileup* p, int64_t* info) {
     if (p->d_filter_work) {
         unsigned int c[12];
         HS_CUDA(ctx, cudaMemcpyAsync(c, p->d_fcounters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
-        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        HS_CUDA(ctx, hs_stream_sync(ctx));
         info[4] = (int64_t)c[0] + c[3];
         info[5] = (int64_t)c[8] | ((int64_t)c[9] << 32);
         info[6] = (int64_t)c[10] | ((int64_t)c[11] << 32);
@@ -1486,7 +1486,7 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     rc = filter_run(p, contig, 1, HS_FLAG_INLIST, L, tmp.data(), off);
     if (n_suspects > 0)
         HS_KERNEL(ctx, "set_inlist_kernel", set_inlist_kernel<<<(n_suspects + 255) / 256, 256, 0, ctx->stream>>>(n_suspects, d_pos, g0, p->d_flags, 0));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // suspect_pos is caller memory
+    HS_CUDA(ctx, hs_stream_sync(ctx));  // suspect_pos is caller memory
     hs_free(ctx, d_pos);
     filter_free(p);  // these partitions were the caller's for this call only
     if (rc) return rc;

@@ -158,6 +158,15 @@ int hsgpu_ctx_create(int device, hsgpu_ctx** out) {
         hsgpu_ctx_destroy(ctx);
         return hs_cuda_fail(nullptr, e, "pinned scratch", __FILE__, __LINE__);
     }
+    {
+        const char* w = getenv("HSGPU_WAIT");
+        if (w && !strcmp(w, "block")) {
+            if (cudaEventCreateWithFlags(&ctx->wait_event, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
+                ctx->wait_event = nullptr;
+                cudaGetLastError();
+            }
+        }
+    }
     ctx_lap("cudaHostAlloc + event", lap);
     *out = ctx;
     return HSGPU_OK;
@@ -168,6 +177,7 @@ void hsgpu_ctx_destroy(hsgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
+    if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaStreamDestroy(ctx->stream);
@@ -180,7 +190,7 @@ const char* hsgpu_last_error(hsgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g
 
 int hsgpu_sync(hsgpu_ctx* ctx) {
     if (!ctx) return HSGPU_ERR_ARG;
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     return HSGPU_OK;
 }
 

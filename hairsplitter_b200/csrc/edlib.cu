@@ -1265,7 +1265,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     }
     // sizes -> offsets on the host (n_pairs structs; the location lists are usually 1-3 entries each)
     HS_CUDA(ctx, hs_d2h(ctx, results, d_res, n_pairs));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     int64_t nloc = 0;
     for (int i = 0; i < n_pairs; i++) {
         results[i].aln_off = results[i].loc_off;  // first_j parked by phase A
@@ -1340,7 +1340,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
         HS_CUDA(ctx, hs_d2h(ctx, results, d_res, n_pairs));
         if (task == 2 || !long_list.empty()) {
             // the LONG launch: long queries, and the pairs whose path turned out to lie at or above edlib's 1 MiB switch
-            HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            HS_CUDA(ctx, hs_stream_sync(ctx));
             std::vector<int32_t> list = long_list;
             for (int i = 0; i < n_pairs; i++)
                 if (results[i].status == 2) list.push_back(i);
@@ -1357,7 +1357,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
         }
         HS_CUDA(ctx, hs_d2h(ctx, end_locations, d_ends, nloc));
         if (task >= 1) HS_CUDA(ctx, hs_d2h(ctx, start_locations, d_starts, nloc));
-        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        HS_CUDA(ctx, hs_stream_sync(ctx));
         int64_t naln = 0;
         for (int i = 0; i < n_pairs; i++) {
             results[i].aln_off = naln;
@@ -1373,7 +1373,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
                 HS_KERNEL(ctx, "edlib_gather_kernel",
                           edlib_gather_kernel<<<n_pairs, 128, 0, ctx->stream>>>(n_pairs, d_res, d_aln_tmp, d_tmpo, d_aln));
                 HS_CUDA(ctx, hs_d2h(ctx, alignment, d_aln, naln));
-                HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                HS_CUDA(ctx, hs_stream_sync(ctx));
             }
         }
     }

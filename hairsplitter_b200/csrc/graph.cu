@@ -526,7 +526,7 @@ int hsgpu_graph_create_ex(hsgpu_pairs* pairs, int32_t n_windows, const int32_t* 
     GR_TRY(hs_h2d(ctx, g->d_read_win, read_win.data(), g->total_masked));
     GR_TRY(hs_h2d(ctx, g->d_views, views.data(), n_contigs));
     GR_TRY(hs_h2d(ctx, g->d_contig_n, cn.data(), n_contigs));
-    GR_TRY(cudaStreamSynchronize(ctx->stream));  // the staging vectors go out of scope
+    GR_TRY(hs_stream_sync(ctx));  // the staging vectors go out of scope
     *out = g;
     return HSGPU_OK;
 }
@@ -563,7 +563,7 @@ int hsgpu_graph_build(hsgpu_graph* g, int64_t* n_replayed) {
     // reads whose selection hangs on std::sort's order of equal distances: replay the reference on the host
     std::vector<uint8_t> flag((size_t)total);
     HS_CUDA(ctx, hs_d2h(ctx, flag.data(), g->d_flag, total));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     std::vector<int64_t> items, item_off;
     int64_t n_floats = 0;
     {
@@ -594,11 +594,11 @@ int hsgpu_graph_build(hsgpu_graph* g, int64_t* n_replayed) {
                       g->d_flag, d_rows));
         std::vector<float> rows((size_t)n_floats);
         HS_CUDA(ctx, hs_d2h(ctx, rows.data(), d_rows, n_floats));
-        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        HS_CUDA(ctx, hs_stream_sync(ctx));
         // patch the selection rows of the replayed reads in a host copy of the bit matrices
         std::vector<uint32_t> sel((size_t)g->sel_words);
         HS_CUDA(ctx, hs_d2h(ctx, sel.data(), g->d_sel, g->sel_words));
-        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        HS_CUDA(ctx, hs_stream_sync(ctx));
 #pragma omp parallel for schedule(dynamic, 16)
         for (int64_t t = 0; t < ni; t++) {
             const int64_t gi = items[t];
@@ -609,7 +609,7 @@ int hsgpu_graph_build(hsgpu_graph* g, int64_t* n_replayed) {
                              g->error_rate, sel.data() + g->h_sel_off[w] + (gi - g0) * ((m + 31) / 32));
         }
         HS_CUDA(ctx, hs_h2d(ctx, g->d_sel, sel.data(), g->sel_words));
-        HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        HS_CUDA(ctx, hs_stream_sync(ctx));
         hs_free(ctx, d_items); hs_free(ctx, d_item_off); hs_free(ctx, d_rows);
     }
     HS_KERNEL(ctx, "graph_degree_kernel",
@@ -621,7 +621,7 @@ int hsgpu_graph_build(hsgpu_graph* g, int64_t* n_replayed) {
     if (rc) return rc;
     HS_CUDA(ctx, cudaMemcpyAsync(g->d_adj_off + total, d_total, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
     HS_CUDA(ctx, hs_d2h(ctx, &g->n_adj, d_total, 1));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     hs_free(ctx, d_total);
     hs_free(ctx, g->d_adj);
     HS_CUDA(ctx, hs_alloc(ctx, &g->d_adj, g->n_adj));
@@ -641,7 +641,7 @@ int hsgpu_graph_adjacency(hsgpu_graph* g, int64_t* adj_off, int64_t capacity, in
     if (adj_off) HS_CUDA(ctx, hs_d2h(ctx, adj_off, g->d_adj_off, g->total_masked + 1));
     const bool fits = capacity >= g->n_adj;
     if (adj && fits) HS_CUDA(ctx, hs_d2h(ctx, adj, g->d_adj, g->n_adj));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     return (adj && !fits) ? HSGPU_ERR_CAPACITY : HSGPU_OK;
 }
 
@@ -692,7 +692,7 @@ int hsgpu_graph_whispers(hsgpu_graph* g, int64_t n_runs, const int32_t* run_wind
               whispers_kernel<<<(unsigned)((n_runs + GR_WARPS - 1) / GR_WARPS), GR_WARPS * 32, smem, ctx->stream>>>(
                   n_runs, d_run_window, d_run_off, d_init, g->d_win_off, g->d_adj_off, g->d_adj, n_orders, d_order, run_max_m, d_out));
     HS_CUDA(ctx, hs_d2h(ctx, labels_out, d_out, n_lab));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     hs_free(ctx, d_run_window); hs_free(ctx, d_run_off); hs_free(ctx, d_init); hs_free(ctx, d_out);
     hs_free(ctx, d_rank); hs_free(ctx, d_order_base); hs_free(ctx, d_order);
     return HSGPU_OK;

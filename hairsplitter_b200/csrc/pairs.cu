@@ -421,7 +421,7 @@ void hsgpu_pairs_destroy(hsgpu_pairs* h) {
     hs_free(ctx, h->d_sim); hs_free(ctx, h->d_diff); hs_free(ctx, h->d_tilemap); hs_free(ctx, h->d_read_base);
     hs_free(ctx, h->d_err); hs_free(ctx, h->d_snp_off); hs_free(ctx, h->d_snp_base); hs_free(ctx, h->d_read_idx);
     hs_free(ctx, h->d_code); hs_free(ctx, h->d_rb); hs_free(ctx, h->d_sb); hs_free(ctx, h->d_snp_contig);
-    cudaStreamSynchronize(ctx->stream);
+    hs_stream_sync(ctx);
     delete h;
 }
 
@@ -608,7 +608,7 @@ int hsgpu_pairs_create(hsgpu_ctx* ctx, int32_t n_contigs, const int32_t* n_reads
         PG_TRY(cudaGetLastError());
     }
     // host vectors above are pageable: the copies must have left them before we return
-    PG_TRY(cudaStreamSynchronize(ctx->stream));
+    PG_TRY(hs_stream_sync(ctx));
 #undef PG_TRY
     if (rows > 0) {
         int rc = pg_make_tmap(ctx, &h->tmapA, h->d_A, h->k_ld, rows);
@@ -682,7 +682,7 @@ int hsgpu_pairs_fetch(hsgpu_pairs* h, int32_t contig, int32_t* sim, int32_t* dif
     }
     int32_t err = 0;
     HS_CUDA(ctx, hs_d2h(ctx, &err, h->d_err, 1));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     hs_free(ctx, d_s);
     hs_free(ctx, d_d);
     if (err) HS_FAIL(ctx, HSGPU_ERR_CUDA, "hsgpu_pairs: the tensor-core kernel timed out on a barrier");

@@ -958,7 +958,7 @@ static int pileup_create_impl(hsgpu_ctx* ctx, const hsgpu_pileup_input* in, hsgp
     // the two small kernels behind them are done. Releasing the turn earlier, on an event behind the last copy, was
     // measured slower and unstable (2.5-4.6 ms per e2e step against a steady 2.45 ms): the next context's upload
     // then competes with this context's first kernels and its allocation-size round trip.
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     return HSGPU_OK;
 }
 
@@ -988,7 +988,7 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     if (rc) return rc;
     int64_t totals[5] = {0, 0, 0, 0, 0};
     HS_CUDA(ctx, hs_d2h(ctx, totals, d_totals, 5));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the only host round trip of the build: the allocation sizes
+    HS_CUDA(ctx, hs_stream_sync(ctx));  // the only host round trip of the build: the allocation sizes
     p->codes_bytes = totals[0];
     p->tile_entries = totals[1];
     p->n_irregular = totals[2];
@@ -1081,7 +1081,7 @@ int hsgpu_pileup_stats(hsgpu_pileup* p, int64_t* n_cells, int64_t* distance_sum,
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     static_assert(sizeof(unsigned long long) == sizeof(int64_t), "");
     HS_CUDA(ctx, hs_d2h(ctx, (unsigned long long*)p->h_stats.data(), p->d_stats, 3 * p->n_contigs));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     for (int c = 0; c < p->n_contigs; c++) {
         if (distance_sum) distance_sum[c] = p->h_stats[3 * c + 0];
         if (aligned_sum) aligned_sum[c] = p->h_stats[3 * c + 1];
@@ -1104,7 +1104,7 @@ int hsgpu_pileup_read_ends(hsgpu_pileup* p, int32_t* read_end) {
     if (!p->built) HS_FAIL(ctx, HSGPU_ERR_STATE, "hsgpu_pileup_read_ends: call hsgpu_pileup_build first");
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     HS_CUDA(ctx, hs_d2h(ctx, read_end, p->d_read_end, p->n_reads));
-    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, hs_stream_sync(ctx));
     return HSGPU_OK;
 }
 
