@@ -548,6 +548,142 @@ __device__ PassOut dp_pass_packed(const uint64_t* peq, const uint8_t* lut, int l
     return o;
 }
 
+// ---- banded sweeps of phase B -------------------------------------------------------------------------------------
+// Once the distance d is known, only cells with |row - column| <= d can lie on a path of that distance (the cells
+// whose value is at most d, and they keep their exact values when everything outside is taken as too large: Ukkonen).
+// Group i of a pair = its blocks i*BPL .. i*BPL + BPL - 1; it needs the columns 64*BPL*i - d .. 64*BPL*(i+1) - 1 + d and
+// meets column c at step c + i, like in the full sweep. A pair therefore never has more than a few groups at work, and
+// gl lanes take its groups in turn: lane r does groups r, r + gl, r + 2 gl, ... (gl is chosen so that group i + gl
+// starts after group i has ended). A group that starts takes the column to its left as all +1 below the bottom score
+// of the group above, which it picked up from the ring one step earlier; where the group above has already ended, the
+// delta coming in from above is +1 (edlib does the same when its band moves, edlib.cpp:781-860). Every lane fetches its
+// own target symbols. Peq sits in shared memory per pair as [symbol][block].
+#define ED_BAND_PEQ_WORDS 1024  // per warp: pairs x symbols x blocks
+
+template <bool REV>
+__device__ void build_peq_band(uint64_t* peq_pair, const uint8_t* lut, const PackLane& g, const uint8_t* q, int m, int n_sym) {
+    if (g.active) {
+        for (int i = g.bl; i < n_sym * g.nb; i += g.gl) peq_pair[i] = 0ull;
+    }
+    __syncwarp();
+    if (g.active) {
+        for (int b = g.bl; b < g.nb; b += g.gl) {
+            const int r0 = 64 * b, r1 = min(m, r0 + 64);
+            for (int r = r0; r < r1; r++) {
+                const int c = REV ? q[m - 1 - r] : q[r];
+                peq_pair[lut[c] * g.nb + b] |= 1ull << (r - r0);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int KIND, int BPL, int KL>
+__device__ PassOut dp_pass_band(const uint64_t* peq_pair, const uint8_t* lut, const PackLane& g, int m, const uint8_t* t,
+                                int n, int n_max, int rev_end, bool consider_j0, int d, ulonglong2* trace, int band_w) {
+    const int nb = g.nb, gl = g.gl;
+    const int n_grp = (nb + BPL - 1) / BPL;
+    const int i_last = n_grp - 1;
+    const int lb = (m - 1) & 63;
+    const int prev_lane = g.ghead + (g.bl + gl - 1) % gl;
+    uint64_t Pv[BPL], Mv[BPL];
+    int band_lo[BPL];
+    int i_cur = g.bl, lo = 0, hi = -1;
+    int top = 0;      // score of the row above the group at column lo - 1
+    int bs = 0;       // score of the group's bottom row (of row m for the last group) at the column just done
+    int sym_next = 0;
+    bool alive = g.active && i_cur < n_grp;
+    PassOut o;
+    o.best = consider_j0 ? m : 0x3fffffff;
+    o.first_j = 0;
+    o.last_j = 0;
+    o.count = consider_j0 ? 1 : 0;
+    auto fetch = [&](int c) -> int { return c < n ? (int)lut[rev_end >= 0 ? t[rev_end - c] : t[c]] : 0; };
+    auto enter = [&](int i) {
+#pragma unroll
+        for (int k = 0; k < BPL; k++) {
+            Pv[k] = ~0ull;
+            Mv[k] = 0ull;
+            band_lo[k] = KIND == PASS_NW_STORE ? band_first(i * BPL + k, d, band_w, n) : 0;
+            if (i * BPL + k >= nb) band_lo[k] = 0x40000000;  // padding block: never stored
+        }
+        lo = max(0, 64 * BPL * i - d);
+        hi = min(n - 1, 64 * BPL * (i + 1) - 1 + d);
+        if (lo == 0) {  // the group starts at the matrix's left edge: D[r][0] = r
+            top = 64 * BPL * i;
+            sym_next = fetch(0);
+        }
+    };
+    if (alive) enter(i_cur);
+    unsigned int packed = 0;  // (bottom score << 2) | (horizontal delta leaving the group is +1) << 1 | (... is -1)
+    const int steps = n_max + n_grp - 1;
+    for (int s = 0; s < steps; s++) {
+        const unsigned int pk = __shfl_sync(0xffffffffu, packed, prev_lane);
+        if (alive && s - i_cur > hi) {  // this group is done: the lane's next one
+            i_cur += gl;
+            alive = i_cur < n_grp;
+            if (alive) enter(i_cur);
+        }
+        const int c = s - i_cur;
+        if (alive && lo > 0 && c == lo - 1) {  // one step before the group starts: what the group above had at column lo - 1
+            top = (int)(pk >> 2);
+            sym_next = fetch(lo);
+        }
+        if (alive && c >= lo && c <= hi) {
+            if (c == lo) bs = top + (i_cur == i_last ? 64 * KL + lb + 1 : 64 * BPL);
+            const int sym = sym_next;
+            sym_next = fetch(c + 1);
+            // the delta coming in from above: the group above at this column, if it still has it
+            uint64_t hneg = 0, hpos = 1;
+            if (i_cur > 0 && c <= 64 * BPL * i_cur - 1 + d) {
+                hneg = pk & 1u;
+                hpos = (pk >> 1) & 1u;
+            }
+            uint64_t phs = 0, mhs = 0;
+            const uint64_t* pq = peq_pair + sym * nb + i_cur * BPL;
+#pragma unroll
+            for (int k = 0; k < BPL; k++) {
+                uint64_t Eq = i_cur * BPL + k < nb ? pq[k] : 0ull;
+                const uint64_t Xv = Eq | Mv[k];
+                Eq |= hneg;
+                const uint64_t Xh = (((Eq & Pv[k]) + Pv[k]) ^ Pv[k]) | Eq;
+                const uint64_t Ph = Mv[k] | ~(Xh | Pv[k]);
+                const uint64_t Mh = Pv[k] & Xh;
+                if (k == KL) { phs = Ph; mhs = Mh; }
+                const uint64_t Phs = (Ph << 1) | hpos;
+                const uint64_t Mhs = (Mh << 1) | hneg;
+                hpos = Ph >> 63;
+                hneg = Mh >> 63;
+                Pv[k] = Mhs | ~(Xv | Phs);
+                Mv[k] = Phs & Xv;
+                if (KIND == PASS_NW_STORE) {
+                    const int x = c - band_lo[k];
+                    st_if((unsigned)x < (unsigned)band_w, trace + (size_t)(i_cur * BPL + k) * band_w + x, Pv[k], Ph);
+                }
+            }
+            if (i_cur == i_last) {
+                bs += (int)((phs >> lb) & 1ull) - (int)((mhs >> lb) & 1ull);
+                if (KIND == PASS_REV_SHW) {
+                    const int j = c + 1;
+                    if (bs < o.best) { o.best = bs; o.first_j = j; }
+                    if (bs == o.best) o.last_j = j;
+                } else {
+                    o.best = bs;
+                }
+            } else {
+                bs += (int)hpos - (int)hneg;
+            }
+            packed = ((unsigned)bs << 2) | ((unsigned)hpos << 1) | (unsigned)hneg;
+        }
+    }
+    const int rl = g.ghead + i_last % gl;  // the lane that did the last group
+    o.best = __shfl_sync(0xffffffffu, o.best, rl);
+    o.first_j = __shfl_sync(0xffffffffu, o.first_j, rl);
+    o.last_j = __shfl_sync(0xffffffffu, o.last_j, rl);
+    o.count = __shfl_sync(0xffffffffu, o.count, rl);
+    return o;
+}
+
 // the groups of a warp walk their paths in step (same rules as traceback above; the window is gl columns wide)
 __device__ int traceback_packed(const ulonglong2* trace, const uint8_t* q, int m, const uint8_t* t, int n, uint8_t* out,
                                 const PackLane& g, int band_d, int band_w) {
@@ -599,10 +735,10 @@ __device__ int traceback_packed(const ulonglong2* trace, const uint8_t* q, int m
 }
 
 template <int BPL>
-__device__ __forceinline__ PackLane pack_lane(int lane, int nb, int cnt) {
+__device__ __forceinline__ PackLane pack_lane(int lane, int nb, int cnt, int band_lanes = 0) {
     PackLane g;
     g.nb = nb;
-    g.gl = (nb + BPL - 1) / BPL;
+    g.gl = band_lanes ? band_lanes : (nb + BPL - 1) / BPL;
     const int grp = lane / g.gl;
     g.bl = lane - grp * g.gl;
     g.ghead = grp * g.gl;
@@ -674,23 +810,25 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_a_packed_kernel(EdA
     }
 }
 
-template <int BPL, int KL>
+// BAND: the two sweeps run inside the band of the known distance (dp_pass_band); the task word carries the lanes per pair
+template <int BPL, int KL, bool BAND>
 __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdArgs a) {
-    __shared__ uint64_t s_peq[ED_WARPS][ED_SMEM_SYMS * 32 * BPL];
+    __shared__ uint64_t s_peq[ED_WARPS][BAND ? ED_BAND_PEQ_WORDS : ED_SMEM_SYMS * 32 * BPL];
     __shared__ uint8_t s_lut[ED_WARPS][256];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gw = blockIdx.x * ED_WARPS + wid;
     const uint8_t* lut = s_lut[wid];
     const int n_sym = build_batch_lut(a.batch_alpha, s_lut[wid], lane);
-    uint64_t* peq = n_sym <= ED_SMEM_SYMS ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32 * ED_PACK_MAXBPL;
+    uint64_t* peq = (BAND || n_sym <= ED_SMEM_SYMS) ? s_peq[wid] : a.peq_big + (size_t)gw * 256 * 32 * ED_PACK_MAXBPL;
     for (;;) {
         int task = 0;
         if (lane == 0) task = (int)atomicAdd(a.counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= a.n_tasks) break;
         const int first = a.tasks[2 * task], nbc = a.tasks[2 * task + 1];
-        const PackLane g = pack_lane<BPL>(lane, nbc >> 8, nbc & 255);
+        const PackLane g = pack_lane<BPL>(lane, (nbc >> 8) & 255, nbc & 255, BAND ? (nbc >> 16) : 0);
         const int grp = lane / g.gl;
+        uint64_t* const peq_pair = peq + (BAND ? grp * n_sym * g.nb : 0);  // BAND: this pair's [symbol][block]
         const int pair = g.active ? a.plist[first + grp] : 0;
         hsgpu_edlib_result r = a.res[pair];
         const uint8_t* q = a.q + a.q_off[pair];
@@ -719,7 +857,8 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdA
         if (a.task == 0) continue;
         r.has_start_locations = 1;
         if (a.mode == 2) {
-            build_peq_packed<BPL>(peq, lut, lane, g, q, m, n_sym, true);
+            if (BAND) build_peq_band<true>(peq_pair, lut, g, q, m, n_sym);
+            else build_peq_packed<BPL>(peq, lut, lane, g, q, m, n_sym, true);
             const bool j0c = (m & 63) != 0;
             const int loc_max = __reduce_max_sync(0xffffffffu, n_loc);
             for (int l = 0; l < loc_max; l++) {
@@ -729,7 +868,10 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdA
                 // an alignment of distance d takes at most m + d target symbols: no later column can reach d again
                 const int nrev = min(e + 1, m + r.edit_distance);
                 const int n_max = __reduce_max_sync(0xffffffffu, gr.active ? nrev : 0);
-                const PassOut o = dp_pass_packed<PASS_REV_SHW, BPL, KL>(peq, lut, lane, gr, m, t, nrev, n_max, e, 1, j0c, nullptr, nullptr);
+                const PassOut o = BAND ? dp_pass_band<PASS_REV_SHW, BPL, KL>(peq_pair, lut, gr, m, t, nrev, n_max, e, j0c,
+                                                                              r.edit_distance, nullptr, 0)
+                                       : dp_pass_packed<PASS_REV_SHW, BPL, KL>(peq, lut, lane, gr, m, t, nrev, n_max, e, 1, j0c,
+                                                                                nullptr, nullptr);
                 if (g.bl == 0 && l < n_loc) starts[l] = e >= 0 ? e - (o.last_j - 1) : 0;  // :254-256 last position
             }
         } else if (g.active) {
@@ -760,10 +902,15 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edlib_phase_b_packed_kernel(EdA
                 for (int i = g.bl; i < m; i += g.gl) out[i] = 1;
                 r.alignment_length = m;
             }
-            build_peq_packed<BPL>(peq, lut, lane, g, q, m, n_sym, false);
             const int n_max = __reduce_max_sync(0xffffffffu, gt.active ? an : 0);
-            dp_pass_packed<PASS_NW_STORE, BPL, KL>(peq, lut, lane, gt, m, t + s0, an, n_max, -1, 1, false, nullptr, trace, band_d,
-                                               band_w);
+            if (BAND) {
+                build_peq_band<false>(peq_pair, lut, g, q, m, n_sym);
+                dp_pass_band<PASS_NW_STORE, BPL, KL>(peq_pair, lut, gt, m, t + s0, an, n_max, -1, false, band_d, trace, band_w);
+            } else {
+                build_peq_packed<BPL>(peq, lut, lane, g, q, m, n_sym, false);
+                dp_pass_packed<PASS_NW_STORE, BPL, KL>(peq, lut, lane, gt, m, t + s0, an, n_max, -1, 1, false, nullptr, trace,
+                                                       band_d, band_w);
+            }
             __syncwarp();
             const int len = traceback_packed(trace, q, m, t + s0, an, out, gt, band_d, band_w);
             if (gt.active) r.alignment_length = len;
@@ -1064,7 +1211,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     // phase A fills some of the fields; the whole struct travels to the host after it
     HS_CUDA(ctx, cudaMemsetAsync(d_res, 0, sizeof(hsgpu_edlib_result) * (size_t)std::max(n_pairs, 1), ctx->stream));
     HS_CUDA(ctx, hs_alloc(ctx, &d_bm, bmw));
-    HS_CUDA(ctx, hs_alloc(ctx, &d_counter, 32));
+    HS_CUDA(ctx, hs_alloc(ctx, &d_counter, 48));
     uint8_t* d_route = nullptr;
     int32_t *d_alpha_len = nullptr, *d_plist = nullptr, *d_tasks = nullptr;
     unsigned int* d_batch_alpha = nullptr;
@@ -1090,53 +1237,81 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     std::vector<int32_t> plist, tasks;
     // a launch = one (blocks per lane, block of the bottom row in the last lane) class: 1 + 2 + 3 + 4 of them
     constexpr int NCLS = ED_PACK_MAXBPL * (ED_PACK_MAXBPL + 1) / 2;
-    auto cls_of = [](int nb) { const int b = bpl_of[nb]; return b * (b - 1) / 2 + (nb - 1) % b; };
-    int task_first[NCLS + 1];  // tasks of class c: [task_first[c], task_first[c + 1])
+    // phase B may run its two sweeps inside the band of the known distance: a plan per pair = (banded?, blocks per
+    // lane, lanes per pair); launches are per (banded?, blocks per lane, bottom-row block) class
+    static const bool band_on = getenv("HSGPU_EDLIB_BAND") && atoi(getenv("HSGPU_EDLIB_BAND")) != 0;  // off until validated on the GPU
+    int n_sym_batch = 256;  // symbols of the batch (known after phase A): bounds the banded kernels' Peq in shared memory
+    struct Plan { int cls, nb, gl, per; };  // class index (0 .. 2 NCLS - 1), blocks, lanes per pair (0 = all groups), pairs per task
+    auto plan_of = [&](int i, bool phase_b) -> Plan {
+        const int nb = (int)((query_off[i + 1] - query_off[i] + 63) / 64);
+        const int bu = bpl_of[nb];
+        Plan pl{bu * (bu - 1) / 2 + (nb - 1) % bu, nb, 0, 32 / ((nb + bu - 1) / bu)};
+        if (!phase_b || !band_on || (mode != 2 && task != 2)) return pl;
+        double best = (34.0 * bu + 28.0) / pl.per;
+        const int64_t d = results[i].edit_distance;
+        for (int b = 1; b <= ED_PACK_MAXBPL; b++) {
+            const int n_grp = (nb + b - 1) / b;
+            int gl = 2;
+            while (gl <= 8 && 64ll * b * (gl - 1) + gl < 2 * d + 4) gl++;  // group i + gl starts after group i has ended
+            if (gl > 8 || gl >= n_grp) continue;
+            const int per = std::min(32 / gl, ED_BAND_PEQ_WORDS / std::max(1, n_sym_batch * nb));
+            if (per < 1) continue;
+            const double cost = (34.0 * b + 44.0) / per;
+            if (cost < best - 1e-9) {
+                best = cost;
+                pl = Plan{NCLS + b * (b - 1) / 2 + (nb - 1) % b, nb, gl, per};
+            }
+        }
+        return pl;
+    };
+    int task_first[2 * NCLS + 1];  // tasks of class c: [task_first[c], task_first[c + 1])
     int64_t ptrace_stride = 0;
-    // key of a pair: (class, blocks, end locations) -- counting sort, then tasks of equal block count
+    // key of a pair: (class, blocks, lanes per pair, end locations) -- counting sort, then tasks of equal shape
     auto build_tasks = [&](bool phase_b) -> cudaError_t {
-        const int NL = ED_PACK_MAXLOC + 1, NB = ED_PACK_MAXBLOCKS + 1;
-        const int NK = NCLS * NB * NL;
+        const int NL = ED_PACK_MAXLOC + 1, NB = ED_PACK_MAXBLOCKS + 1, NG = 9;
+        const int NK = 2 * NCLS * NB * NG * NL;
         std::vector<int64_t> cnt((size_t)NK + 1, 0);
-        auto key = [&](int i) {
-            const int nb = (int)((query_off[i + 1] - query_off[i] + 63) / 64);
-            return (cls_of(nb) * NB + nb) * NL + (phase_b ? results[i].n_locations : 0);
-        };
-        for (int i = 0; i < n_pairs; i++)
-            if (route[i] == ED_ROUTE_PACKED) cnt[(size_t)key(i) + 1]++;
+        std::vector<int32_t> keys((size_t)n_pairs, -1);
+        for (int i = 0; i < n_pairs; i++) {
+            if (route[i] != ED_ROUTE_PACKED) continue;
+            const Plan pl = plan_of(i, phase_b);
+            keys[i] = (((pl.cls * NB + pl.nb) * NG + pl.gl) * NL) + (phase_b ? results[i].n_locations : 0);
+            cnt[(size_t)keys[i] + 1]++;
+        }
         for (int c = 1; c <= NK; c++) cnt[c] += cnt[c - 1];
         const int64_t total = cnt[NK];
         plist.assign((size_t)total, 0);
         std::vector<int64_t> fill(cnt);
         for (int i = 0; i < n_pairs; i++)
-            if (route[i] == ED_ROUTE_PACKED) plist[(size_t)fill[(size_t)key(i)]++] = i;
+            if (keys[i] >= 0) plist[(size_t)fill[(size_t)keys[i]]++] = i;
         tasks.clear();
         ptrace_stride = 0;
-        for (int c = 0; c < NCLS; c++) {
+        for (int c = 0; c < 2 * NCLS; c++) {
             task_first[c] = (int)(tasks.size() / 2);
             for (int nb = 1; nb <= ED_PACK_MAXBLOCKS; nb++) {
-                if (cls_of(nb) != c) continue;
-                const int b = bpl_of[nb];
-                const int per = 32 / ((nb + b - 1) / b);
-                const int64_t lo = cnt[(size_t)(c * NB + nb) * NL], hi = cnt[(size_t)(c * NB + nb + 1) * NL];
-                for (int64_t f = lo; f < hi; f += per) {
-                    const int n_in = (int)std::min<int64_t>(per, hi - f);
-                    tasks.push_back((int32_t)f);
-                    tasks.push_back((nb << 8) | n_in);
-                    if (phase_b && task == 2) {  // the task's groups share one traceback slab
-                        int64_t need = 0;
-                        for (int x = 0; x < n_in; x++) {
-                            const int i = plist[(size_t)(f + x)];
-                            const int64_t m = query_off[i + 1] - query_off[i], n = target_off[i + 1] - target_off[i];
-                            const int64_t d = results[i].edit_distance;  // band of the path: see band_first
-                            need += nb * std::min<int64_t>(std::min<int64_t>(n, m + d), 64 + 2 * d) * 16;
+                for (int gl = 0; gl < NG; gl++) {
+                    const int64_t lo = cnt[(size_t)((c * NB + nb) * NG + gl) * NL], hi = cnt[(size_t)((c * NB + nb) * NG + gl + 1) * NL];
+                    if (lo == hi) continue;
+                    const int per = plan_of(plist[(size_t)lo], phase_b).per;  // the same for every pair of the bucket but for d: take the first
+                    for (int64_t f = lo; f < hi; f += per) {
+                        const int n_in = (int)std::min<int64_t>(per, hi - f);
+                        tasks.push_back((int32_t)f);
+                        tasks.push_back((gl << 16) | (nb << 8) | n_in);
+                        if (phase_b && task == 2) {  // the task's groups share one traceback slab
+                            int64_t need = 0;
+                            for (int x = 0; x < n_in; x++) {
+                                const int i = plist[(size_t)(f + x)];
+                                const int64_t m = query_off[i + 1] - query_off[i], n = target_off[i + 1] - target_off[i];
+                                const int64_t d = results[i].edit_distance;  // band of the path: see band_first
+                                need += nb * std::min<int64_t>(std::min<int64_t>(n, m + d), 64 + 2 * d) * 16;
+                            }
+                            ptrace_stride = std::max(ptrace_stride, need);
                         }
-                        ptrace_stride = std::max(ptrace_stride, need);
                     }
                 }
             }
         }
-        task_first[NCLS] = (int)(tasks.size() / 2);
+        task_first[2 * NCLS] = (int)(tasks.size() / 2);
         ptrace_stride = (ptrace_stride + 255) & ~255ll;
         if (total == 0) return cudaSuccess;
         cudaError_t e = hs_h2d(ctx, d_plist, plist.data(), total);
@@ -1149,21 +1324,29 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
         edlib_phase_a_packed_kernel<3, 0>, edlib_phase_a_packed_kernel<3, 1>, edlib_phase_a_packed_kernel<3, 2>,
         edlib_phase_a_packed_kernel<4, 0>, edlib_phase_a_packed_kernel<4, 1>, edlib_phase_a_packed_kernel<4, 2>,
         edlib_phase_a_packed_kernel<4, 3>};
-    static const PackedKernel phase_b_packed[NCLS] = {
-        edlib_phase_b_packed_kernel<1, 0>, edlib_phase_b_packed_kernel<2, 0>, edlib_phase_b_packed_kernel<2, 1>,
-        edlib_phase_b_packed_kernel<3, 0>, edlib_phase_b_packed_kernel<3, 1>, edlib_phase_b_packed_kernel<3, 2>,
-        edlib_phase_b_packed_kernel<4, 0>, edlib_phase_b_packed_kernel<4, 1>, edlib_phase_b_packed_kernel<4, 2>,
-        edlib_phase_b_packed_kernel<4, 3>};
+    static const PackedKernel phase_b_packed[2 * NCLS] = {
+        edlib_phase_b_packed_kernel<1, 0, false>, edlib_phase_b_packed_kernel<2, 0, false>, edlib_phase_b_packed_kernel<2, 1, false>,
+        edlib_phase_b_packed_kernel<3, 0, false>, edlib_phase_b_packed_kernel<3, 1, false>, edlib_phase_b_packed_kernel<3, 2, false>,
+        edlib_phase_b_packed_kernel<4, 0, false>, edlib_phase_b_packed_kernel<4, 1, false>, edlib_phase_b_packed_kernel<4, 2, false>,
+        edlib_phase_b_packed_kernel<4, 3, false>,
+        edlib_phase_b_packed_kernel<1, 0, true>, edlib_phase_b_packed_kernel<2, 0, true>, edlib_phase_b_packed_kernel<2, 1, true>,
+        edlib_phase_b_packed_kernel<3, 0, true>, edlib_phase_b_packed_kernel<3, 1, true>, edlib_phase_b_packed_kernel<3, 2, true>,
+        edlib_phase_b_packed_kernel<4, 0, true>, edlib_phase_b_packed_kernel<4, 1, true>, edlib_phase_b_packed_kernel<4, 2, true>,
+        edlib_phase_b_packed_kernel<4, 3, true>};
     static const char* const phase_a_names[NCLS] = {
         "edlib_phase_a_kernel<packed,1,0>", "edlib_phase_a_kernel<packed,2,0>", "edlib_phase_a_kernel<packed,2,1>",
         "edlib_phase_a_kernel<packed,3,0>", "edlib_phase_a_kernel<packed,3,1>", "edlib_phase_a_kernel<packed,3,2>",
         "edlib_phase_a_kernel<packed,4,0>", "edlib_phase_a_kernel<packed,4,1>", "edlib_phase_a_kernel<packed,4,2>",
         "edlib_phase_a_kernel<packed,4,3>"};
-    static const char* const phase_b_names[NCLS] = {
+    static const char* const phase_b_names[2 * NCLS] = {
         "edlib_phase_b_kernel<packed,1,0>", "edlib_phase_b_kernel<packed,2,0>", "edlib_phase_b_kernel<packed,2,1>",
         "edlib_phase_b_kernel<packed,3,0>", "edlib_phase_b_kernel<packed,3,1>", "edlib_phase_b_kernel<packed,3,2>",
         "edlib_phase_b_kernel<packed,4,0>", "edlib_phase_b_kernel<packed,4,1>", "edlib_phase_b_kernel<packed,4,2>",
-        "edlib_phase_b_kernel<packed,4,3>"};
+        "edlib_phase_b_kernel<packed,4,3>",
+        "edlib_phase_b_kernel<band,1,0>", "edlib_phase_b_kernel<band,2,0>", "edlib_phase_b_kernel<band,2,1>",
+        "edlib_phase_b_kernel<band,3,0>", "edlib_phase_b_kernel<band,3,1>", "edlib_phase_b_kernel<band,3,2>",
+        "edlib_phase_b_kernel<band,4,0>", "edlib_phase_b_kernel<band,4,1>", "edlib_phase_b_kernel<band,4,2>",
+        "edlib_phase_b_kernel<band,4,3>"};
     if (n_packed > 0) {
         HS_CUDA(ctx, hs_alloc(ctx, &d_alpha_len, n_pairs));
         HS_CUDA(ctx, hs_alloc(ctx, &d_plist, n_packed));
@@ -1178,7 +1361,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     HS_CUDA(ctx, hs_h2d(ctx, d_to, target_off, n_pairs + 1));
     HS_CUDA(ctx, hs_h2d(ctx, d_bmo, bm_off.data(), n_pairs + 1));
     HS_CUDA(ctx, cudaMemsetAsync(d_bm, 0, sizeof(unsigned int) * bmw, ctx->stream));
-    HS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 32 * sizeof(unsigned int), ctx->stream));
+    HS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 48 * sizeof(unsigned int), ctx->stream));
     a.n_pairs = n_pairs;
     a.q = d_q;
     a.q_off = d_qo;
@@ -1265,7 +1448,13 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     }
     // sizes -> offsets on the host (n_pairs structs; the location lists are usually 1-3 entries each)
     HS_CUDA(ctx, hs_d2h(ctx, results, d_res, n_pairs));
+    unsigned int h_alpha[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (d_batch_alpha) HS_CUDA(ctx, hs_d2h(ctx, h_alpha, d_batch_alpha, 8));
     HS_CUDA(ctx, hs_stream_sync(ctx));
+    if (d_batch_alpha) {
+        n_sym_batch = 0;
+        for (int w = 0; w < 8; w++) n_sym_batch += __builtin_popcount(h_alpha[w]);
+    }
     int64_t nloc = 0;
     for (int i = 0; i < n_pairs; i++) {
         results[i].aln_off = results[i].loc_off;  // first_j parked by phase A
@@ -1328,7 +1517,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
             if (task == 2) HS_CUDA(ctx, hs_alloc(ctx, &d_ptrace, (int64_t)grid_cap * ED_WARPS * ptrace_stride));
             a.ptrace = d_ptrace;
             a.ptrace_stride = ptrace_stride;
-            for (int c = 0; c < NCLS; c++) {
+            for (int c = 0; c < 2 * NCLS; c++) {
                 a.tasks = d_tasks + 2 * task_first[c];
                 a.n_tasks = task_first[c + 1] - task_first[c];
                 if (a.n_tasks == 0) continue;
