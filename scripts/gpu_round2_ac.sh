@@ -2,7 +2,7 @@
 # banded phase-B sweeps: edlib tests, realign stage with the band on and off
 T=${1:-r02ac}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_edlib.py -m gpu -x -q > gpurun_out/${T}_edlib_tests.log 2>&1; echo "edlib pytest rc=$?"; tail -12 gpurun_out/${T}_edlib_tests.log
+HSGPU_EDLIB_BAND=1 timeout 900 python -m pytest tests/test_gpu_edlib.py -m gpu -x -q > gpurun_out/${T}_edlib_tests.log 2>&1; echo "edlib pytest rc=$?"; tail -12 gpurun_out/${T}_edlib_tests.log
 for b in 1 0; do
   HSGPU_EDLIB_BAND=$b timeout 600 python bench.py --only-realign > gpurun_out/${T}_realign_band$b.json 2> gpurun_out/${T}_realign_band$b.err; echo "band $b rc=$?"
   tail -2 gpurun_out/${T}_realign_band$b.err
