@@ -113,7 +113,7 @@ struct SmemAcc {
 #define CR_U8_MAX 240
 template <typename H>
 constexpr int column_smem() {
-    return 2 * CR_ROWS * HS_TILE + CR_BINS * HS_TILE * (int)sizeof(H) + CR_ORD * HS_TILE + CR_META * 8 + CR_META;
+    return 2 * CR_ROWS * HS_TILE + CR_BINS * HS_TILE * (int)sizeof(H) + (CR_ORD + 1) * HS_TILE + CR_META * 8 + CR_META;
 }
 
 __device__ __forceinline__ void cr_cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
     unsigned char* s_rows = smem;                                                        // 2 x 16 x 128 B
     H* s_hist = reinterpret_cast<H*>(smem + 2 * CR_ROWS * HS_TILE);                      // [126][128]
     uint8_t* s_order = smem + 2 * CR_ROWS * HS_TILE + CR_BINS * HS_TILE * (int)sizeof(H);  // [32][128] u8
-    const uint8_t** s_ptr = reinterpret_cast<const uint8_t**>(s_order + CR_ORD * HS_TILE);  // [128]
+    const uint8_t** s_ptr = reinterpret_cast<const uint8_t**>(s_order + (CR_ORD + 1) * HS_TILE);  // [128]; s_order has a spare row
     uint8_t* s_vmask = reinterpret_cast<uint8_t*>(s_ptr + CR_META);                      // [128]
     __shared__ unsigned long long s_depth;
     __shared__ __align__(16) uint32_t s_lut_words[HS_RANK_LUT_FAST_BYTES / 4];  // the part of HsRankLut hs_rank_fast reads
@@ -207,10 +207,12 @@ __global__ void __launch_bounds__(HS_TILE) column_rank_kernel(ColumnArgs a) {
             for (int row = 0; row < CR_ROWS; row++) {
                 const int bin = max(code[row], 32) - 32;
                 const unsigned int cnt = hcol[bin * HS_TILE];
-                if (cnt == 0) {
-                    if (m < CR_ORD) s_order[m * HS_TILE + col] = (uint8_t)code[row];
-                    m++;
-                }
+                // first-seen order without a branch (a first sighting somewhere in the warp is the normal case, and the
+                // divergent path cost every row its issue slots): the code always goes to slot m, which only becomes
+                // valid when m moves on -- later rows overwrite the open slot until the next first sighting fills it.
+                // Slot CR_ORD is the spare row for columns that have run out of slots (they are re-read anyway).
+                s_order[min(m, CR_ORD) * HS_TILE + col] = (uint8_t)code[row];
+                m += cnt == 0;
                 hcol[bin * HS_TILE] = (H)(cnt + 1);
             }
         }
