@@ -343,7 +343,7 @@ def run_stages(ctx, stream, chunks, args, hbm_peak):
     if filt is not None:
         assert np.array_equal(kept, filt["pos"]), "snps_out differs from the reference"
     cells0, _, _ = pu.stats()
-    kms = prof.get("robust_filter_kernel", (0, 0.0))[1]
+    kms = sum(v[1] for kname, v in prof.items() if kname.startswith("robust_filter_"))  # lanes kernel + overflow / deep
     out["contingency"] = {
         "metric": "robust_filter (loops 3+4 of keep_only_robust_variants) on one chunk",
         "shape": f"{cb.length} columns, {cb.n_reads} reads, {len(parts)} partitions, {pos.size} suspects -> {kept.size} kept",

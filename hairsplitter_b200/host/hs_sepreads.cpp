@@ -33,11 +33,13 @@ struct Fields {
     const char* p;
     const char* end;
     Fields(const char* b, const char* e) : p(b), end(e) {}
+    // the classic locale's whitespace (what `iss >>` skips), inline: std::isspace is a library call per character
+    static bool blank(char c) { return c == ' ' || (unsigned char)(c - 9) < 5; }
     bool next(const char*& b, const char*& e) {
-        while (p < end && std::isspace((unsigned char)*p)) p++;
+        while (p < end && blank(*p)) p++;
         if (p >= end) return false;
         b = p;
-        while (p < end && !std::isspace((unsigned char)*p)) p++;
+        while (p < end && !blank(*p)) p++;
         e = p;
         return true;
     }
