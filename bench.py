@@ -47,7 +47,9 @@ def parse_args():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (testing only)")
     ap.add_argument("--cpu-sample-chunks", type=int, default=0, help="chunks in the CPU baseline sample (0 = auto)")
-    ap.add_argument("--e2e-lanes", type=int, default=3, help="hsgpu contexts (host threads) of the e2e path")
+    ap.add_argument("--e2e-lanes", type=int, default=0, help="hsgpu contexts (host threads) of the e2e path; 0 = by the "
+                    "host cores per rank: 4 on a box of its own (measured: 2 / 3 / 4 lanes = 5.0 / 3.2 / 2.8 ms per step), fewer "
+                    "when several ranks share the host")
     ap.add_argument("--e2e-groups", type=int, default=1, help="groups of contig chunks the e2e path cuts a step's batch into")
     ap.add_argument("--strong", action="store_true", help="strong scaling: ONE workload (same seed on every rank) dealt "
                     "to the ranks by sharding.lpt_assign; value = all columns / max-over-ranks time")
@@ -583,6 +585,23 @@ def run_e2e(chunks, parts_per_contig, local_rank, ctx, n_lanes, n_groups, steps,
 
     trace = [] if os.environ.get("HS_E2E_TRACE") else None
 
+    # result buffers of every lane, kept from step to step (pinned): a caller in a loop does not allocate per batch,
+    # and large numpy arrays allocated and freed per call mean an mmap / munmap pair each -- with several threads in
+    # the driver at the same time that showed up as stalls of every lane
+    def pinned_array(n, dtype):
+        tns = torch.empty(max(int(n), 1) * np.dtype(dtype).itemsize, dtype=torch.uint8, pin_memory=True)
+        keep.append(tns)
+        return tns.numpy().view(dtype)
+    nc_max = max(int(pb.contig_len.shape[0]) for pb in groups)
+    cols_max = max(int(pb.contig_len.astype(np.int64).sum()) for pb in groups)
+    lane_out = []
+    for _ in range(n_lanes):
+        lane_out.append({
+            "kept": (pinned_array(cols_max // 4 + 1024, np.int32), pinned_array(nc_max + 1, np.int64)),
+            "sus": (pinned_array(cols_max // 6 + 2 * nc_max, np.int32), pinned_array(cols_max // 6 + 2 * nc_max, np.uint8),
+                    pinned_array(nc_max + 1, np.int64), pinned_array(nc_max, np.int64)),
+        })
+
     def e2e_group(lane, g):
         t0 = time.perf_counter()
         p = api.Pileup(lanes[lane], groups[g])   # H2D of the group
@@ -593,9 +612,12 @@ def run_e2e(chunks, parts_per_contig, local_rank, ctx, n_lanes, n_groups, steps,
         t3 = time.perf_counter()
         p.partitions_set(prepared=group_parts[g])   # H2D of the final partitions
         t3a = time.perf_counter()
-        kept, koff = p.robust_filter_all(int(groups[g].contig_len.sum()))   # loops 3+4 + D2H of snps_out
+        nc_g = int(groups[g].contig_len.shape[0])
+        kept, koff = p.robust_filter_all(out=lane_out[lane]["kept"])   # loops 3+4 + D2H of snps_out
+        koff = koff[: nc_g + 1]
         t3b = time.perf_counter()
-        pos, au, off, ds = p.suspects_all()      # D2H of the call_variants results
+        pos, au, off, ds = p.suspects_all(out=lane_out[lane]["sus"])   # D2H of the call_variants results
+        off, ds = off[: nc_g + 1], ds[:nc_g]
         t4 = time.perf_counter()
         p.close()
         if trace is not None:
@@ -620,7 +642,9 @@ def run_e2e(chunks, parts_per_contig, local_rank, ctx, n_lanes, n_groups, steps,
             t.join()
         return sum(e2e_out)
 
-    d2h_bytes = e2e_steps(max(2, min(warmup, 3)))
+    # every lane runs at least two untimed steps: its context's memory pool and staging buffers reach their size there
+    # (a lane that met its first batch inside the timed region paid the physical allocations of its pool: 10-100 ms)
+    d2h_bytes = e2e_steps(max(warmup, 2 * n_lanes))
     barrier()
     t_e2e = time.perf_counter()
     e0 = [torch.cuda.Event(enable_timing=True) for _ in lanes]
@@ -868,7 +892,8 @@ def main():
     pu.close()
 
     # ---- e2e: host buffers -> C ABI -> host results, every step ----
-    e2e = run_e2e(chunks, parts_per_contig, local_rank, ctx, args.e2e_lanes, args.e2e_groups, args.steps, args.warmup, barrier)
+    e2e_lanes = args.e2e_lanes if args.e2e_lanes > 0 else max(2, min(4, host_cores() // max(world, 1) - 1))
+    e2e = run_e2e(chunks, parts_per_contig, local_rank, ctx, e2e_lanes, args.e2e_groups, args.steps, args.warmup, barrier)
     assert e2e["suspects"] == int(n_sus.sum()), "the e2e path must find the same suspect columns"
     assert e2e["kept"] == n_kept, "the e2e path must keep the same columns"
     e2e_ms, t_e2e, h2d_bytes, d2h_bytes = e2e["device_ms"], e2e["wall_ms"], e2e["h2d_bytes"], e2e["d2h_bytes"]

@@ -708,14 +708,19 @@ class Pileup:
         n = int(ns[contig])
         return pos[:n], au[:n]
 
-    def suspects_all(self, want_depth=True):
-        """every contig's suspect list in one call: (pos, is_automatic, off[n_contigs+1], depth_sum)"""
+    def suspects_all(self, want_depth=True, out=None):
+        """every contig's suspect list in one call: (pos, is_automatic, off[n_contigs+1], depth_sum); `out` = buffers
+        of a caller that keeps them from call to call (pos int32, is_automatic uint8, off int64, depth_sum int64)"""
         nc = self.packed.n_contigs
-        cap = int(self.packed.contig_len.astype(np.int64).sum()) // 6 + 2 * nc
-        pos = np.empty(cap, np.int32)
-        au = np.empty(cap, np.uint8)
-        off = np.zeros(nc + 1, np.int64)
-        ds = np.zeros(nc, np.int64)
+        if out is not None:
+            pos, au, off, ds = out
+            cap = min(len(pos), len(au))
+        else:
+            cap = int(self.packed.contig_len.astype(np.int64).sum()) // 6 + 2 * nc
+            pos = np.empty(cap, np.int32)
+            au = np.empty(cap, np.uint8)
+            off = np.zeros(nc + 1, np.int64)
+            ds = np.zeros(nc, np.int64)
         self.ctx.check(self.lib.hsgpu_suspects_all(self.h, cap, pos.ctypes.data, au.ctypes.data, off.ctypes.data,
                                                    ds.ctypes.data if want_depth else None), "hsgpu_suspects_all")
         n = int(off[nc])
@@ -802,10 +807,16 @@ class Pileup:
         assert len(prepared[0]) == int(self.packed.contig_len.shape[0])
         self.ctx.check(self.lib.hsgpu_partitions_set(self.h, C.cast(prepared[0], C.c_void_p)), "hsgpu_partitions_set")
 
-    def robust_filter_all(self, capacity=None):
+    def robust_filter_all(self, capacity=None, out=None):
         """loops 3+4 of keep_only_robust_variants for every contig in one launch -> (kept positions, off[n_contigs+1]).
-        Without a capacity the call is made twice (sizes first)."""
+        Without a capacity the call is made twice (sizes first). `out` = (kept int32, off int64) buffers of a caller
+        that keeps them from call to call."""
         n = int(self.packed.contig_len.shape[0])
+        if out is not None:
+            kept, off = out
+            self.ctx.check(self.lib.hsgpu_robust_filter_all(self.h, len(kept), kept.ctypes.data, off.ctypes.data),
+                           "hsgpu_robust_filter_all")
+            return kept[: int(off[n])], off
         off = np.zeros(n + 1, np.int64)
         if capacity is None:
             rc = self.lib.hsgpu_robust_filter_all(self.h, 0, None, off.ctypes.data)

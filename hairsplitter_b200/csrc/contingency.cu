@@ -730,10 +730,15 @@ __global__ void __launch_bounds__(32 * RF_WARPS, MINB) robust_filter_kernel(Filt
 // cells are grouped by code once (distinct codes in order of first appearance, at most RL_MAXC), every lane runs over
 // the cells of a code and counts its partition's states in one packed register (a byte per state), and the
 // per-partition decisions -- most frequent other code, ties by the bucket-table rule, 2x2 table, chi-square -- are
-// taken by all lanes at once. Columns with more distinct codes than RL_MAXC go to an overflow list that the kernel
+// taken by all lanes at once. Columns with more distinct codes than RL_MAXC (24) go to an overflow list that the kernel
 // above works off afterwards.
 #define RL_WARPS 4
-#define RL_MAXC 32
+#ifndef RL_MAXC
+#define RL_MAXC 24  // measured: 16 sends too many columns to the overflow kernel (config 3: +16 ms), 32 costs a CTA per SM
+#endif
+#ifndef RL_MINB
+#define RL_MINB 6
+#endif
 
 // the alternative allele among tied codes, for this lane's partition: rf_select_alt_tied's bucket-table rule on the
 // column's code list and the lane's counts (s_acc column); returns the index of the code in the list, -1 for none,
@@ -809,7 +814,7 @@ __device__ __noinline__ int rl_tied_slow(const uint8_t* s_code, const uint32_t* 
     return rf_select_alt_tied(order, hist, mo, ref, max2, nullptr);
 }
 
-__global__ void __launch_bounds__(32 * RL_WARPS) robust_filter_lanes_kernel(FilterArgs a) {
+__global__ void __launch_bounds__(32 * RL_WARPS, RL_MINB) robust_filter_lanes_kernel(FilterArgs a) {
     __shared__ uint8_t s_code_all[RL_WARPS][RF_CAP];
     __shared__ uint16_t s_sorted_all[RL_WARPS][RF_CAP];  // word offsets of the cells' state rows, grouped by code
     __shared__ uint32_t s_map_all[RL_WARPS][32];         // byte per code: its index in the column's list
@@ -1379,7 +1384,7 @@ static int filter_run(hsgpu_pileup* p, int c0, int n, unsigned in_flag, int64_t 
     // HSGPU_FILTER_OCC=3: the build with 3 CTAs per SM (more registers, no spills) instead of 4, for A/B measurements
     // HSGPU_FILTER_LANES=0: the lane-per-read kernel for every column, for A/B measurements
     static const bool by_lanes = !getenv("HSGPU_FILTER_LANES") || atoi(getenv("HSGPU_FILTER_LANES")) != 0;
-    static const int lanes_ctas = getenv("HSGPU_FILTER_CTAS") ? std::max(1, atoi(getenv("HSGPU_FILTER_CTAS"))) : 5;
+    static const int lanes_ctas = getenv("HSGPU_FILTER_CTAS") ? std::max(1, atoi(getenv("HSGPU_FILTER_CTAS"))) : RL_MINB;
     a.overflow = p->d_foverflow;
     a.from_overflow = 0;
     if (by_lanes) {

@@ -147,7 +147,7 @@ def test_robust_filter_matches_oracle(gpu_ctx, oracle, case):
           "hifi": lambda: cases.hifi_case(seed=93), "deep": lambda: cases.deep_case(seed=94),
           "many_parts": lambda: cases.small_case(seed=95),
           "over128_parts": lambda: cases.small_case(seed=96, length=4000, depth=40),
-          # 35 % error at depth ~100: a fifth of the columns have more than 32 distinct codes (up to 45), which the
+          # 35 % error at depth ~100: a fifth of the columns have more than 24 distinct codes (up to 45), which the
           # lane-per-partition kernel hands over to the lane-per-read kernel
           "noisy": lambda: cases.small_case(seed=97, length=3000, depth=110, mean_len=1500, error=0.35)}[case]()
     pk, pu = _build(gpu_ctx, [cb])
