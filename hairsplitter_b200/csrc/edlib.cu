@@ -591,14 +591,21 @@ __device__ PassOut dp_pass_band(const uint64_t* peq_pair, const uint8_t* lut, co
     int i_cur = g.bl, lo = 0, hi = -1;
     int top = 0;      // score of the row above the group at column lo - 1
     int bs = 0;       // score of the group's bottom row (of row m for the last group) at the column just done
-    int sym_next = 0;
+    unsigned int symq = 0, symq_next = 0;  // the next four target symbols (a byte each) and the four after them
+    int symq_left = 0;
     bool alive = g.active && i_cur < n_grp;
     PassOut o;
     o.best = consider_j0 ? m : 0x3fffffff;
     o.first_j = 0;
     o.last_j = 0;
     o.count = consider_j0 ? 1 : 0;
-    auto fetch = [&](int c) -> int { return c < n ? (int)lut[rev_end >= 0 ? t[rev_end - c] : t[c]] : 0; };
+    auto fetch = [&](int c) -> unsigned int { return c < n ? (unsigned int)lut[rev_end >= 0 ? t[rev_end - c] : t[c]] : 0u; };
+    auto fetch4 = [&](int c) -> unsigned int { return fetch(c) | (fetch(c + 1) << 8) | (fetch(c + 2) << 16) | (fetch(c + 3) << 24); };
+    auto prime = [&](int c) {  // the group starts at column c
+        symq = fetch4(c);
+        symq_next = fetch4(c + 4);
+        symq_left = 4;
+    };
     auto enter = [&](int i) {
 #pragma unroll
         for (int k = 0; k < BPL; k++) {
@@ -611,7 +618,7 @@ __device__ PassOut dp_pass_band(const uint64_t* peq_pair, const uint8_t* lut, co
         hi = min(n - 1, 64 * BPL * (i + 1) - 1 + d);
         if (lo == 0) {  // the group starts at the matrix's left edge: D[r][0] = r
             top = 64 * BPL * i;
-            sym_next = fetch(0);
+            prime(0);
         }
     };
     if (alive) enter(i_cur);
@@ -627,12 +634,17 @@ __device__ PassOut dp_pass_band(const uint64_t* peq_pair, const uint8_t* lut, co
         const int c = s - i_cur;
         if (alive && lo > 0 && c == lo - 1) {  // one step before the group starts: what the group above had at column lo - 1
             top = (int)(pk >> 2);
-            sym_next = fetch(lo);
+            prime(lo);
         }
         if (alive && c >= lo && c <= hi) {
             if (c == lo) bs = top + (i_cur == i_last ? 64 * KL + lb + 1 : 64 * BPL);
-            const int sym = sym_next;
-            sym_next = fetch(c + 1);
+            const int sym = (int)(symq & 255u);
+            symq >>= 8;
+            if (--symq_left == 0) {  // the loads of the refill are four steps ahead of their first use
+                symq = symq_next;
+                symq_next = fetch4(c + 5);
+                symq_left = 4;
+            }
             // the delta coming in from above: the group above at this column, if it still has it
             uint64_t hneg = 0, hpos = 1;
             if (i_cur > 0 && c <= 64 * BPL * i_cur - 1 + d) {
@@ -1249,7 +1261,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
         if (!phase_b || !band_on || (mode != 2 && task != 2)) return pl;
         double best = (34.0 * bu + 28.0) / pl.per;
         const int64_t d = results[i].edit_distance;
-        for (int b = 1; b <= ED_PACK_MAXBPL; b++) {
+        for (int b = bu; b <= bu; b++) {  // the same blocks per lane as the full sweeps (one class per batch shape)
             const int n_grp = (nb + b - 1) / b;
             int gl = 2;
             while (gl <= 8 && 64ll * b * (gl - 1) + gl < 2 * d + 4) gl++;  // group i + gl starts after group i has ended
