@@ -379,14 +379,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(const TIn* in
     }
     __syncthreads();
     long long carry = s_tot[wid];
-    long long v = (b + lane < e) ? (long long)in[b + lane] : 0;
-    for (int64_t k0 = b; k0 < e; k0 += 32) {
-        const int64_t k = k0 + lane;
-        const long long nv = (k + 32 < e) ? (long long)in[k + 32] : 0;  // the next row, before this one is overwritten
-        const long long incl = hs_warp_incl_scan64(v, lane);
-        if (k < e) out[k] = carry + incl - v;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
-        v = nv;
+    // eight rows in flight: the loop is a chain of global-load latencies otherwise (one CTA, nothing else to run)
+    constexpr int RB = 8;
+    for (int64_t k0 = b; k0 < e; k0 += 32 * RB) {
+        long long v[RB];
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const int64_t k = k0 + 32 * r + lane;
+            v[r] = k < e ? (long long)in[k] : 0;  // all read before any of these rows is written (out may alias in)
+        }
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const int64_t k = k0 + 32 * r + lane;
+            const long long incl = hs_warp_incl_scan64(v[r], lane);
+            if (k < e) out[k] = carry + incl - v[r];
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
 }
 
