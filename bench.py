@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrinks the genome (testing only)")
     ap.add_argument("--cpu-sample-chunks", type=int, default=0, help="chunks in the CPU baseline sample (0 = auto)")
     ap.add_argument("--e2e-lanes", type=int, default=0, help="hsgpu contexts (host threads) of the e2e path; 0 = by the "
-                    "host cores per rank: 4 on a box of its own (measured: 2 / 3 / 4 lanes = 5.0 / 3.2 / 2.8 ms per step), fewer "
+                    "host cores per rank: 5 on a box of its own (measured: 3 / 4 / 5 / 6 lanes = 3.2 / 2.8 / 2.6 / 3.1 ms per step), fewer "
                     "when several ranks share the host")
     ap.add_argument("--e2e-groups", type=int, default=1, help="groups of contig chunks the e2e path cuts a step's batch into")
     ap.add_argument("--strong", action="store_true", help="strong scaling: ONE workload (same seed on every rank) dealt "
@@ -892,7 +892,7 @@ def main():
     pu.close()
 
     # ---- e2e: host buffers -> C ABI -> host results, every step ----
-    e2e_lanes = args.e2e_lanes if args.e2e_lanes > 0 else max(2, min(4, host_cores() // max(world, 1) - 1))
+    e2e_lanes = args.e2e_lanes if args.e2e_lanes > 0 else max(2, min(5, host_cores() // max(world, 1) - 1))
     e2e = run_e2e(chunks, parts_per_contig, local_rank, ctx, e2e_lanes, args.e2e_groups, args.steps, args.warmup, barrier)
     assert e2e["suspects"] == int(n_sus.sum()), "the e2e path must find the same suspect columns"
     assert e2e["kept"] == n_kept, "the e2e path must keep the same columns"
