@@ -113,3 +113,116 @@ int hshost_parse_dump(const char* gfa, const char* reads, const char* sam, int a
 }
 
 }  // extern "C"
+
+// ---- .col sidecar (hs_colbin.h) ----------------------------------------------------------------------------------
+#include <chrono>
+#include <sstream>
+
+#include "hs_colbin.h"
+
+namespace {
+uint64_t mix(uint64_t h, const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; i++) {
+        h ^= b[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+}  // namespace
+
+extern "C" {
+
+// Everything parse_column_file leaves behind, folded into one number, plus counts: out = {digest, contigs, snps,
+// cells, route (1 = the sidecar was used)}. route_wanted: 0 = text only, 1 = sidecar only (fails with -1 if there is no
+// usable one), 2 = what HS_separate_reads does. Returns the seconds the parse took, < 0 on failure.
+double hshost_col_digest(const char* col_path, int max_coverage, float rarest, int route_wanted, uint64_t* out) {
+    std::vector<ColContig> contigs;
+    const auto t0 = std::chrono::steady_clock::now();
+    int route = 0;
+    if (route_wanted == 0) parse_column_text(col_path, contigs, max_coverage, rarest);
+    else if (read_col_sidecar(col_path, contigs, max_coverage, rarest)) route = 1;
+    else if (route_wanted == 1) return -1.0;
+    else parse_column_text(col_path, contigs, max_coverage, rarest);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    uint64_t h = 1469598103934665603ull, n_snps = 0, n_cells = 0;
+    for (const ColContig& c : contigs) {
+        h = mix(h, c.line.data(), c.line.size());
+        h = mix(h, &c.length, sizeof(c.length));
+        h = mix(h, &c.coverage, sizeof(c.coverage));
+        const uint64_t nr = c.read_lines.size(), nl = c.limits.size(), ns = c.snps.size();
+        h = mix(h, &nr, 8);
+        h = mix(h, &nl, 8);
+        h = mix(h, &ns, 8);
+        for (const std::string& r : c.read_lines) h = mix(h, r.data(), r.size() + 1);
+        for (const auto& l : c.limits) {
+            h = mix(h, &l.first, sizeof(int));
+            h = mix(h, &l.second, sizeof(int));
+        }
+        for (const Column& s : c.snps) {
+            const uint64_t m = s.readIdxs.size(), k = s.content.size();
+            h = mix(h, &s.pos, sizeof(int));
+            h = mix(h, &s.ref_base, 1);
+            h = mix(h, &s.second_base, 1);
+            h = mix(h, &m, 8);
+            h = mix(h, &k, 8);
+            h = mix(h, s.readIdxs.data(), 4 * m);
+            h = mix(h, s.content.data(), k);
+            n_cells += k;
+        }
+        n_snps += ns;
+    }
+    out[0] = h;
+    out[1] = contigs.size();
+    out[2] = n_snps;
+    out[3] = n_cells;
+    out[4] = (uint64_t)route;
+    return dt;
+}
+
+// a .col text (any writer's) through write_outputs again: col_out must reproduce it block for block, and the sidecar
+// write_outputs leaves next to col_out must parse to the same structures as the text
+int hshost_rewrite_col(const char* col_in, const char* col_out, const char* vcf_out) {
+    try {
+        std::vector<ColContig> contigs;
+        parse_column_text(col_in, contigs, 2147483647, 0.0f);
+        Store st;
+        std::unordered_map<int, std::vector<Column>> variants;
+        for (ColContig& c : contigs) {
+            std::istringstream cl(c.line);
+            std::string tag, name, len, cov;
+            cl >> tag >> name >> len >> cov;
+            SeqRec contig;
+            contig.name = name;
+            contig.sequence.assign((size_t)c.length, 'A');
+            contig.depth = std::strtof(cov.c_str(), nullptr);
+            const int64_t ci = (int64_t)st.seqs.size();
+            st.seqs.push_back(std::move(contig));
+            st.contigs.push_back(ci);
+            for (const std::string& rl : c.read_lines) {
+                std::istringstream is(rl);
+                std::string rname;
+                Alignment a;
+                int strand = 0;
+                is >> tag >> rname >> a.pos_1_1 >> a.pos_1_2 >> a.pos_2_1 >> a.pos_2_2 >> strand;
+                a.strand = strand != 0;
+                a.contig = ci;
+                a.read = (int64_t)st.seqs.size();
+                SeqRec read;
+                read.name = rname;
+                st.seqs.push_back(std::move(read));
+                st.seqs[ci].alns.push_back((int64_t)st.alns.size());
+                st.alns.push_back(std::move(a));
+            }
+            variants[(int)ci] = std::move(c.snps);
+        }
+        write_outputs(st, variants, col_out, vcf_out);
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+
+int hshost_col_sidecar_enabled() { return col_sidecar_enabled() ? 1 : 0; }
+
+}  // extern "C"

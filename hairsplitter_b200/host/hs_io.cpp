@@ -1,5 +1,7 @@
 #include "hs_io.h"
 
+#include "hs_colbin.h"
+
 #include <fcntl.h>
 #include <omp.h>
 #include <sys/mman.h>
@@ -392,6 +394,7 @@ void write_outputs(const Store& st, const std::unordered_map<int, std::vector<Co
     std::vector<const std::pair<const int, std::vector<Column>>*> order;
     for (const auto& kv : variants) order.push_back(&kv);
     std::vector<string> col_text(order.size()), vcf_text(order.size());
+    std::vector<size_t> head_bytes(order.size(), 0);  // CONTIG + READ lines of the block: the sidecar keeps them as text
 #pragma omp parallel for schedule(dynamic, 1)
     for (size_t i = 0; i < order.size(); i++) {
         const SeqRec& contig = st.seqs[order[i]->first];
@@ -409,6 +412,7 @@ void write_outputs(const Store& st, const std::unordered_map<int, std::vector<Co
                  << a.pos_2_2 << "\t" << a.strand << "\n";
             o += line.str();
         }
+        head_bytes[i] = o.size();
         for (const Column& c : order[i]->second) {
             o += "SNPS\t";
             o += std::to_string(c.pos);
@@ -447,6 +451,14 @@ void write_outputs(const Store& st, const std::unordered_map<int, std::vector<Co
         out.write(col_text[i].data(), (std::streamsize)col_text[i].size());
         vcf.write(vcf_text[i].data(), (std::streamsize)vcf_text[i].size());
     }
+    out.close();
+    // the same content once more as flat arrays, for HS_separate_reads (hs_colbin.h)
+    std::vector<ColSidecarBlock> blocks(order.size());
+    for (size_t i = 0; i < order.size(); i++) {
+        blocks[i].head.assign(col_text[i], 0, head_bytes[i]);
+        blocks[i].snps = &order[i]->second;
+    }
+    write_col_sidecar(col_file, blocks);
 }
 
 }  // namespace hs

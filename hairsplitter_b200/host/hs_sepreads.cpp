@@ -5,6 +5,8 @@
 // sequence of operations, so the result is the same by construction.
 #include "hs_sepreads.h"
 
+#include "hs_colbin.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -176,10 +178,22 @@ void parse_col_block(const char* b, const char* e, bool numbers, int max_coverag
 
 }  // namespace
 
+void parse_col_head(const char* b, const char* e, ColContig& c) { parse_col_block(b, e, true, 0, 0.0f, c); }
+
 // The reference reads the file line by line into one growing structure (:62-186). Here the file is mapped once, cut at
 // its CONTIG lines and the blocks are parsed in parallel: a CONTIG block only depends on the letters-or-numbers switch,
 // which the first SNPS line of the file sets (:93-103).
 void parse_column_file(const std::string& path, std::vector<ColContig>& contigs, int max_coverage,
+                       float rarest_strain_abundance) {
+    // the writer's binary sidecar, when it belongs to this very file (hs_colbin.h): same structures, no text to tokenise
+    if (read_col_sidecar(path, contigs, max_coverage, rarest_strain_abundance)) {
+        if (std::getenv("HS_TIMING")) fprintf(stderr, "[hs timing] (.col read from its binary sidecar)\n");
+        return;
+    }
+    parse_column_text(path, contigs, max_coverage, rarest_strain_abundance);
+}
+
+void parse_column_text(const std::string& path, std::vector<ColContig>& contigs, int max_coverage,
                        float rarest_strain_abundance) {
     const int fd = ::open(path.c_str(), O_RDONLY);
     if (fd < 0) return;  // an unreadable file leaves no contigs, like the reference's failed ifstream

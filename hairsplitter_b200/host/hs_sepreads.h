@@ -29,6 +29,9 @@ struct ColContig {
 // uninitialised int when rarest_strain_abundance != 0 (:1420-1426), which behaves as "no limit".
 void parse_column_file(const std::string& path, std::vector<ColContig>& contigs, int max_coverage,
                        float rarest_strain_abundance);
+// the text route alone (parse_column_file first tries the writer's binary sidecar, hs_colbin.h)
+void parse_column_text(const std::string& path, std::vector<ColContig>& contigs, int max_coverage,
+                       float rarest_strain_abundance);
 
 // Where the seeds of the per-sweep shuffles come from (cluster_graph.cpp:255-258,429-432: a fresh
 // std::random_device-seeded mt19937 per sweep). HS_PIN_SEED=<n> in the environment replaces random_device by the

@@ -320,3 +320,33 @@ def test_low_memory_executable_device_and_host_lists_agree(tmp_path):
                            env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
         assert open(gro, "rb").read() == want, tag
         assert ("low-memory read graphs" in r.stderr.decode()) == (tag == "dev")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SR), reason="oracle/_ref not built")
+def test_both_executables_chained_through_the_sidecar(tmp_path):
+    """f2: our HS_call_variants leaves <col>.hsb next to the .col; our HS_separate_reads reads it instead of the text.
+    The .gro must be the pinned reference's on the same .col, with the sidecar, without it (HS_SIDECAR=0), and with the
+    rarest-strain filter of parse_column_file (src/separate_reads.cpp:167) applied to the arrays."""
+    ours_cv = os.path.join(ROOT, "hairsplitter_b200", "bin", "HS_call_variants")
+    chunks = [cases.small_case(seed=104, length=30000, depth=50, mean_len=5000, error=0.06),
+              cases.small_case(seed=101, length=60000, depth=60, mean_len=9000, error=0.10, n_strains=2)]
+    for i, c in enumerate(chunks):
+        c.name = f"ctg{i}"
+    tmp = str(tmp_path)
+    gfa, reads, sam = synth.write_files(chunks, os.path.join(tmp, "in"))
+    col = os.path.join(tmp, "ours.col")
+    subprocess.run([ours_cv, gfa, reads, sam, "4", tmp, os.path.join(tmp, "err"), "0", "0", col, os.path.join(tmp, "ours.vcf"), "0.33"],
+                   check=True, stdout=subprocess.DEVNULL)
+    assert os.path.getsize(col + ".hsb") > 1000
+    for rare in ("0", "0.2"):
+        ref = os.path.join(tmp, f"ref_{rare}.gro")
+        subprocess.run([REF_SR, col, "1", "0.06", "none", "0", rare, "0", ref, "0"], check=True, stdout=subprocess.DEVNULL)
+        want = open(ref, "rb").read()
+        assert want.count(b"GROUP") > 5
+        for tag, extra in (("sidecar", {}), ("text", {"HS_SIDECAR": "0"})):
+            gro = os.path.join(tmp, f"{tag}_{rare}.gro")
+            env = dict(os.environ, HS_PIN_SEED=str(PIN_SEED), HS_TIMING="1", **extra)
+            r = subprocess.run([OURS, col, "4", "0.06", "none", "0", rare, "0", gro, "0"], check=True, env=env,
+                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+            assert ("binary sidecar" in r.stderr.decode()) == (tag == "sidecar")
+            assert open(gro, "rb").read() == want, (tag, rare)
