@@ -666,6 +666,8 @@ int hsgpu_column_rank(hsgpu_pileup* p, const float* mean_error, float automatic_
     p->have_col_off = false;
     p->auto_threshold = automatic_snp_threshold;
     float* d_me = nullptr;
+    HsTemps temps(ctx);
+    temps.own(d_me);
     if (mean_error) {
         HS_CUDA(ctx, hs_alloc(ctx, &d_me, nc));
         HS_CUDA(ctx, hs_h2d(ctx, d_me, mean_error, nc));
@@ -799,6 +801,8 @@ int hsgpu_suspects_all(hsgpu_pileup* p, int64_t capacity, int32_t* pos, uint8_t*
     int32_t* d_pos = nullptr;
     uint8_t* d_auto = nullptr;
     int64_t* d_hdr = nullptr;
+    HsTemps temps(ctx);
+    temps.own(d_pos, d_auto, d_hdr);
     HS_CUDA(ctx, hs_alloc(ctx, &d_pos, cap_all));
     HS_CUDA(ctx, hs_alloc(ctx, &d_auto, cap_all));
     HS_CUDA(ctx, hs_alloc(ctx, &d_hdr, 2 * nc + 2));
@@ -884,6 +888,8 @@ int hsgpu_pileup_export(hsgpu_pileup* p, int32_t contig, int64_t cell_capacity, 
     if (n == 0) return HSGPU_OK;
     uint32_t* d_idx = nullptr;
     uint8_t* d_code = nullptr;
+    HsTemps temps(ctx);
+    temps.own(d_idx, d_code);
     HS_CUDA(ctx, hs_alloc(ctx, &d_idx, n));
     HS_CUDA(ctx, hs_alloc(ctx, &d_code, n));
     const int64_t ntile = (L + HS_TILE - 1) / HS_TILE;
@@ -912,6 +918,8 @@ int hsgpu_pileup_extract_columns(hsgpu_pileup* p, int32_t contig, int32_t n_cols
         if (pos[i] < 0 || pos[i] >= L) HS_FAIL(ctx, HSGPU_ERR_ARG, "hsgpu_pileup_extract_columns: position out of range");
     int32_t* d_pos = nullptr;
     int64_t* d_off = nullptr;
+    HsTemps temps(ctx);
+    temps.own(d_pos, d_off);
     HS_CUDA(ctx, hs_alloc(ctx, &d_pos, n_cols));
     HS_CUDA(ctx, hs_alloc(ctx, &d_off, n_cols + 1));
     HS_CUDA(ctx, hs_h2d(ctx, d_pos, pos, n_cols));
@@ -930,6 +938,8 @@ int hsgpu_pileup_extract_columns(hsgpu_pileup* p, int32_t contig, int32_t n_cols
     } else if (n > 0) {
         uint32_t* d_idx = nullptr;
         uint8_t* d_code = nullptr;
+        HsTemps cell_temps(ctx);
+        cell_temps.own(d_idx, d_code);
         HS_CUDA(ctx, hs_alloc(ctx, &d_idx, n));
         HS_CUDA(ctx, hs_alloc(ctx, &d_code, n));
         HS_CUDA(ctx, hs_h2d(ctx, d_off, off, n_cols + 1));

@@ -107,6 +107,28 @@ static inline void hs_free(hsgpu_ctx* ctx, T*& p) {
     if (p) cudaFreeAsync((void*)p, ctx->stream);
     p = nullptr;
 }
+// The stream-ordered temporaries of one call. A call frees them itself on its way out (hs_free nulls the pointer);
+// whatever is still allocated when the call returns early -- HS_CUDA / HS_KERNEL / HS_FAIL on an error -- goes back to
+// the context's pool here instead of staying allocated until the context is destroyed.
+struct HsTemps {
+    hsgpu_ctx* ctx;
+    std::vector<void**> slots;
+    explicit HsTemps(hsgpu_ctx* c) : ctx(c) {}
+    template <typename T>
+    void own(T*& p) { slots.push_back(reinterpret_cast<void**>(&p)); }
+    template <typename T, typename... Rest>
+    void own(T*& p, Rest&... rest) {
+        own(p);
+        own(rest...);
+    }
+    ~HsTemps() {
+        for (void** s : slots)
+            if (*s) {
+                cudaFreeAsync(*s, ctx->stream);
+                *s = nullptr;
+            }
+    }
+};
 // several arrays out of ONE stream-ordered allocation (a batch object used to cost ~40 cudaMallocAsync /
 // cudaFreeAsync pairs; the host side of the e2e path is bound by driver calls)
 struct HsCarve {

@@ -1164,6 +1164,8 @@ int hsgpu_partition_tables(hsgpu_pileup* p, int32_t contig, const hsgpu_partitio
     int32_t* d_pos = nullptr;
     hsgpu_distance* d_out = nullptr;
     const int64_t n_out = (int64_t)n_cols * parts->n_parts;
+    HsTemps temps(ctx);
+    temps.own(d_pst, d_pos, d_out);
     HS_CUDA(ctx, hs_alloc(ctx, &d_pst, (int64_t)pst.size()));
     HS_CUDA(ctx, hs_alloc(ctx, &d_pos, n_cols));
     HS_CUDA(ctx, hs_alloc(ctx, &d_out, n_out));
@@ -1481,6 +1483,8 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     int rc = filter_set(p, contig, 1, parts);
     if (rc) return rc;
     int32_t* d_pos = nullptr;
+    HsTemps temps(ctx);
+    temps.own(d_pos);
     HS_CUDA(ctx, hs_alloc(ctx, &d_pos, n_suspects));
     HS_CUDA(ctx, hs_h2d(ctx, d_pos, suspect_pos, n_suspects));
     const int64_t g0 = p->h_col_base[contig];

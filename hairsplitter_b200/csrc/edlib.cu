@@ -1214,6 +1214,9 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     unsigned int *d_bm = nullptr, *d_counter = nullptr;
     int32_t *d_ends = nullptr, *d_starts = nullptr;
     uint64_t* d_peq = nullptr;
+    HsTemps temps(ctx);  // an early error return releases whatever has been allocated by then
+    temps.own(d_q, d_t, d_aln_tmp, d_trace, d_aln, d_ptrace, d_qo, d_to, d_bmo, d_tmpo, d_scan, d_res, d_bm, d_counter, d_ends,
+              d_starts, d_peq);
     HS_CUDA(ctx, hs_alloc(ctx, &d_q, qbytes));
     HS_CUDA(ctx, hs_alloc(ctx, &d_t, tbytes));
     HS_CUDA(ctx, hs_alloc(ctx, &d_qo, n_pairs + 1));
@@ -1227,6 +1230,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     uint8_t* d_route = nullptr;
     int32_t *d_alpha_len = nullptr, *d_plist = nullptr, *d_tasks = nullptr;
     unsigned int* d_batch_alpha = nullptr;
+    temps.own(d_route, d_alpha_len, d_plist, d_tasks, d_batch_alpha);
     HS_CUDA(ctx, hs_alloc(ctx, &d_route, n_pairs));
     HS_CUDA(ctx, hs_h2d(ctx, d_route, route.data(), n_pairs));
     EdArgs a;
@@ -1428,6 +1432,7 @@ extern "C" int hsgpu_edlib_align_batch(hsgpu_ctx* ctx, int32_t n_pairs, const ch
     uint8_t* d_hbuf = nullptr;
     ulonglong2* d_colv = nullptr;
     int* d_colpre = nullptr;
+    temps.own(d_list, d_hbuf, d_colv, d_colpre);
     auto long_setup = [&](const std::vector<int32_t>& list, bool with_columns, int* grid_long) -> cudaError_t {
         hs_free(ctx, d_list); hs_free(ctx, d_hbuf); hs_free(ctx, d_colv); hs_free(ctx, d_colpre);
         d_list = nullptr; d_hbuf = nullptr; d_colv = nullptr; d_colpre = nullptr;

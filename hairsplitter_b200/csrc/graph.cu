@@ -581,6 +581,8 @@ int hsgpu_graph_build(hsgpu_graph* g, int64_t* n_replayed) {
     if (!items.empty()) {
         int64_t *d_items = nullptr, *d_item_off = nullptr;
         float* d_rows = nullptr;
+        HsTemps temps(ctx);
+        temps.own(d_items, d_item_off, d_rows);
         const int64_t ni = (int64_t)items.size();
         HS_CUDA(ctx, hs_alloc(ctx, &d_items, ni));
         HS_CUDA(ctx, hs_alloc(ctx, &d_item_off, ni));
@@ -616,6 +618,8 @@ int hsgpu_graph_build(hsgpu_graph* g, int64_t* n_replayed) {
               graph_csr_kernel<false><<<blocks, GR_WARPS * 32, 0, ctx->stream>>>(total, g->d_read_win, g->d_win_off, g->d_sel_off,
                                                                                   g->d_sel, g->d_deg, nullptr, nullptr));
     int64_t* d_total = nullptr;
+    HsTemps temps(ctx);
+    temps.own(d_total);
     HS_CUDA(ctx, hs_alloc(ctx, &d_total, 1));
     int rc = hs_exclusive_scan_u32_to_i64(ctx, g->d_deg, g->d_adj_off, total, d_total);
     if (rc) return rc;
@@ -669,6 +673,8 @@ int hsgpu_graph_whispers(hsgpu_graph* g, int64_t n_runs, const int32_t* run_wind
     const int64_t n_lab = run_off[n_runs];
     int32_t *d_run_window = nullptr, *d_init = nullptr, *d_rank = nullptr, *d_order = nullptr, *d_out = nullptr;
     int64_t *d_run_off = nullptr, *d_order_base = nullptr;
+    HsTemps temps(ctx);
+    temps.own(d_run_window, d_init, d_rank, d_order, d_out, d_run_off, d_order_base);
     HS_CUDA(ctx, hs_alloc(ctx, &d_run_window, n_runs));
     HS_CUDA(ctx, hs_alloc(ctx, &d_run_off, n_runs + 1));
     HS_CUDA(ctx, hs_alloc(ctx, &d_init, n_lab));

@@ -669,6 +669,8 @@ int hsgpu_pairs_fetch(hsgpu_pairs* h, int32_t contig, int32_t* sim, int32_t* dif
     HS_CUDA(ctx, cudaSetDevice(ctx->device));
     const PairContig& pc = h->h_contigs[contig];
     int32_t *d_s = nullptr, *d_d = nullptr;
+    HsTemps temps(ctx);
+    temps.own(d_s, d_d);
     if (pc.n > 0 && (sim || diff)) {
         // the dense n x n form exists only here, for the caller who asks for it (the later stages of the library read
         // the blocks): it is built on the device and copied out

@@ -976,6 +976,8 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     HS_CUDA(ctx, cudaMemsetAsync(p->d_stats, 0, sizeof(unsigned long long) * 3 * p->n_contigs, ctx->stream));
     // d_totals: codes bytes, tile index entries, irregular reads, most reads over one tile, super-tile index entries
     int64_t* d_totals = nullptr;
+    HsTemps temps(ctx);
+    temps.own(d_totals);
     HS_CUDA(ctx, hs_alloc(ctx, &d_totals, 5));
     HS_CUDA(ctx, cudaMemsetAsync(d_totals, 0, 5 * sizeof(int64_t), ctx->stream));
     HS_CUDA(ctx, cudaMemsetAsync(p->d_next_read, 0, 4 * sizeof(unsigned int), ctx->stream));
@@ -996,6 +998,8 @@ int hsgpu_pileup_build(hsgpu_pileup* p) {
     HS_CUDA(ctx, hs_alloc(ctx, &p->d_tile_reads, p->tile_entries));
     if (p->n_tiles > 0) {
         int32_t* d_super_reads = nullptr;
+        HsTemps index_temps(ctx);
+        index_temps.own(d_super_reads);
         HS_CUDA(ctx, hs_alloc(ctx, &d_super_reads, totals[4]));
         const unsigned sblocks = (unsigned)((p->n_super + 7) / 8), tblocks = (unsigned)((p->n_tiles + 7) / 8);
         HS_KERNEL(ctx, "super_index_kernel<false>", super_index_kernel<false><<<sblocks, 256, 0, ctx->stream>>>(
