@@ -270,16 +270,20 @@ static void gpu_stages(void* user, const std::vector<ColContig>& contigs, std::v
         size_t i = 0;
         while (i < shard[g].size()) {
             std::vector<ContigJob*> batch;
-            double bytes = 0;
+            double blocks = 0, rows = 0, widest = 0;
             while (i < shard[g].size()) {
-                // upper bound of what a contig keeps on the device: the count blocks of every tile pair (8 bytes per
-                // read pair; the band of overlapping reads in practice) and the one-hot operands (2 bytes per read
-                // and SNP of the widest contig, bounded here by its own SNP count)
+                // upper bound of what the batch keeps on the device: the count blocks of every tile pair (8 bytes per
+                // read pair; the band of overlapping reads in practice) and the two one-hot operands, whose rows all
+                // have the stride of the batch's widest contig (hsgpu_pairs_create: k_ld = the largest SNP count) --
+                // so one SNP-rich contig is not batched with hundreds of read-rich ones
                 const ColContig& cc = contigs[shard[g][i]->n];
                 const double r = (double)((cc.read_lines.size() + 127) / 128 * 128);
-                const double need = r * r * 8 + r * 2.0 * (double)((cc.snps.size() + 127) / 128 * 128);
-                if (!batch.empty() && bytes + need > 24e9) break;
-                bytes += need;
+                const double k = (double)((cc.snps.size() + 127) / 128 * 128);
+                const double need = (blocks + r * r * 8) + (rows + r) * 2.0 * std::max(widest, k);
+                if (!batch.empty() && need > 24e9) break;
+                blocks += r * r * 8;
+                rows += r;
+                widest = std::max(widest, k);
                 batch.push_back(shard[g][i++]);
             }
             gpu_shard(st.ctxs[g], contigs, batch, error_rate, sh, stats);
