@@ -75,3 +75,25 @@ def test_two_gpus_give_the_same_files(tmp_path):
         del os.environ["HSGPU_NGPUS"]
     for a, b in zip(ref, ours):
         assert filecmp.cmp(a, b, shallow=False), (a, b)
+
+
+GLUED = os.path.join(ROOT, "oracle", "_ref", "HS_call_variants_glued")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(GLUED)), reason="oracle/_ref not built")
+def test_reference_main_on_libhsgpu_gives_the_reference_files(tmp_path):
+    """The binding INTEGRATION.md describes, compiled and run: the reference's unmodified main() (parsers, OpenMP loop
+    over contigs, merge with the automatic SNPs, output_files -- all from libhsref_cv.so) with generate_msa /
+    call_variants / keep_only_robust_variants bound to integration/glue_call_variants.cpp, which only speaks the C ABI
+    of include/hsgpu.h. Same .col, .vcf and error-rate bytes as the reference executable (ONT contigs with two
+    strains, a HiFi contig with the stricter suspect threshold, a contig with hard clips, a contig without SNPs)."""
+    chunks = [cases.small_case(seed=91, length=20000, depth=50, mean_len=5000, error=0.06), cases.medium_case(),
+              cases.hifi_case(), cases.small_case(seed=5, length=3000, depth=12, mean_len=900, hard=0.4)]
+    for i, c in enumerate(chunks):
+        c.name = f"ctg{i}"
+    files = synth.write_files(chunks, os.path.join(str(tmp_path), "in"))
+    ref = _run(REF, files, str(tmp_path), "ref")
+    glued = _run(GLUED, files, str(tmp_path), "glued", threads=2)
+    for a, b in zip(ref, glued):
+        assert filecmp.cmp(a, b, shallow=False), (a, b)
+    assert open(ref[0], "rb").read().count(b"SNPS\t") > 20

@@ -195,3 +195,36 @@ int main(void) { return 0; }
     r = subprocess.run(["/usr/bin/gcc", "-std=c11", "-I", ref_inc, "-I", os.path.join(ROOT, "include"), "-c", str(src),
                         "-o", str(tmp_path / "layout.o")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+GLUED = os.path.join(ROOT, "oracle", "_ref", "HS_call_variants_glued")
+
+
+@pytest.mark.skipif(not os.path.exists(GLUED), reason="oracle/_ref not built (needs /root/reference)")
+def test_reference_main_binds_to_the_glue(tmp_path):
+    """integration/glue_call_variants.cpp compiled against the reference's headers: the reference's main() (in
+    libhsref_cv.so) must reach the glue's generate_msa through the PLT. Without a GPU that shows as the library's loud
+    failure right after the reference's own parsers have run -- and as the usage text with status 0 when called the
+    way hairsplitter.py probes its dependencies (hairsplitter.py:229-239)."""
+    import subprocess
+    import sys
+    import torch
+    r = subprocess.run([GLUED, "--version"], stdout=subprocess.PIPE)
+    assert r.returncode == 0 and b"Usage" in r.stdout
+    syms = subprocess.run(["nm", "-D", "--defined-only", GLUED], stdout=subprocess.PIPE, text=True).stdout
+    for name in ("generate_msa", "13call_variants", "keep_only_robust_variants"):
+        assert any(name in line and " T " in line for line in syms.splitlines()), name
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: tests/test_gpu_callvariants.py runs the glued executable for real")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    from hairsplitter_b200 import synth
+    chunk = cases.small_case(seed=91, length=4000, depth=10, mean_len=1500, error=0.06)
+    chunk.name = "ctg0"
+    tmp = str(tmp_path)
+    gfa, reads, sam = synth.write_files([chunk], os.path.join(tmp, "in"))
+    r = subprocess.run([GLUED, gfa, reads, sam, "1", tmp, tmp + "/err", "0", "0", tmp + "/a.col", tmp + "/a.vcf", "0.33"],
+                       stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 1
+    assert "Calling variants on each contig" in r.stdout           # the reference's main() got that far by itself
+    assert "hsgpu_ctx_create failed" in r.stdout and "no CPU fallback" in r.stdout  # ... and called into the glue
