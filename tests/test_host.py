@@ -228,3 +228,46 @@ def test_reference_main_binds_to_the_glue(tmp_path):
     assert r.returncode == 1
     assert "Calling variants on each contig" in r.stdout           # the reference's main() got that far by itself
     assert "hsgpu_ctx_create failed" in r.stdout and "no CPU fallback" in r.stdout  # ... and called into the glue
+
+
+MOCK_DIR = os.path.join(ROOT, "oracle", "_ref", "mock_for_glue_test")
+REF_CV = os.path.join(ROOT, "oracle", "_ref", "HS_call_variants")
+
+
+@pytest.mark.skipif(not (os.path.exists(GLUED) and os.path.exists(os.path.join(MOCK_DIR, "libhsgpu.so")) and os.path.exists(REF_CV)),
+                    reason="oracle/_ref not built (needs /root/reference)")
+def test_glue_logic_against_the_reference_with_the_oracle_behind_the_c_abi(tmp_path):
+    """The glue itself, checked where there is no GPU: the glued executable runs with oracle/mock_hsgpu.c (the few entry
+    points the glue calls, computed by the oracle with the semantics include/hsgpu.h documents) in front of the real
+    library -- for this subprocess only. What is under test is the reference-side code: the conversions between
+    Read / Overlap / Column / Partition and the flat arrays of the C ABI, the order of the calls, what the reference's
+    main() gets back. The files must be the reference executable's, byte for byte (one thread), and block for block
+    with two OpenMP threads. The same comparison with the real library is the GPU test
+    tests/test_gpu_callvariants.py::test_reference_main_on_libhsgpu_gives_the_reference_files."""
+    import filecmp
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    from hairsplitter_b200 import synth
+    chunks = [cases.small_case(seed=91, length=20000, depth=50, mean_len=5000, error=0.06), cases.hifi_case(),
+              cases.small_case(seed=5, length=3000, depth=12, mean_len=900, hard=0.4)]
+    for i, c in enumerate(chunks):
+        c.name = f"ctg{i}"
+    tmp = str(tmp_path)
+    files = synth.write_files(chunks, os.path.join(tmp, "in"))
+
+    def run(exe, tag, threads, env=None):
+        out = [os.path.join(tmp, f"{tag}.{e}") for e in ("col", "vcf", "err")]
+        subprocess.run([exe, *files, str(threads), tmp, out[2], "0", "0", out[0], out[1], "0.33"], check=True,
+                       stdout=subprocess.DEVNULL, env=env)
+        return out
+
+    ref = run(REF_CV, "ref", 1)
+    mock_env = dict(os.environ, LD_LIBRARY_PATH=MOCK_DIR)
+    one = run(GLUED, "glued1", 1, mock_env)
+    for a, b in zip(ref, one):
+        assert filecmp.cmp(a, b, shallow=False), (a, b)
+    assert open(ref[0], "rb").read().count(b"SNPS\t") > 20
+    two = run(GLUED, "glued2", 2, mock_env)
+    assert sorted(open(ref[0], "rb").read().split(b"CONTIG\t")) == sorted(open(two[0], "rb").read().split(b"CONTIG\t"))
