@@ -231,3 +231,12 @@ int hsgpu_robust_filter(hsgpu_pileup* p, int32_t contig, const hsgpu_partitions*
     free(all);
     return HSGPU_OK;
 }
+
+/* integration/glue_separate_reads.cpp */
+int hsgpu_read_pair_counts(hsgpu_ctx* ctx, int32_t n_reads, int32_t n_snps, const int64_t* snp_off, const uint32_t* read_idx,
+                           const uint8_t* code, const uint8_t* ref_base, const uint8_t* second_base, int32_t* sim,
+                           int32_t* diff) {
+    (void)ctx;
+    hso_read_pair_counts(n_reads, n_snps, snp_off, read_idx, code, ref_base, second_base, sim, diff);
+    return HSGPU_OK;
+}

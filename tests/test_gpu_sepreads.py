@@ -350,3 +350,29 @@ def test_both_executables_chained_through_the_sidecar(tmp_path):
                                stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
             assert ("binary sidecar" in r.stderr.decode()) == (tag == "sidecar")
             assert open(gro, "rb").read() == want, (tag, rare)
+
+
+GLUED_SR = os.path.join(ROOT, "oracle", "_ref", "HS_separate_reads_glued")
+
+
+@pytest.mark.skipif(not os.path.exists(GLUED_SR), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", ["ont", "amplicon"])
+def test_reference_main_on_libhsgpu_gives_the_reference_gro(tmp_path, case):
+    """INTEGRATION.md section 4 compiled and run: the reference's unmodified main() of HS_separate_reads (from
+    libhsref_sr_open.so, random_device pinned) with list_similarities_and_differences_between_reads3 bound to
+    integration/glue_separate_reads.cpp, i.e. to hsgpu_read_pair_counts -- the tcgen05 kernel -- through the C ABI.
+    The .gro is the committed golden one of the pinned reference."""
+    import gzip
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_sr
+    _, err, low, rare, amp = make_golden_sr.CASES[case]
+    g = os.path.join(ROOT, "tests", "golden")
+    tmp = str(tmp_path)
+    col, out = os.path.join(tmp, case + ".col"), os.path.join(tmp, "glued.gro")
+    with open(col, "wb") as f:
+        f.write(gzip.open(os.path.join(g, f"sr_{case}.col.gz")).read())
+    want = gzip.open(os.path.join(g, f"sr_{case}.gro.gz")).read()
+    subprocess.run([GLUED_SR, col, "1", err, os.path.join(tmp, "no_ploidy"), low, rare, amp, out, "0"], check=True,
+                   stdout=subprocess.DEVNULL)
+    assert open(out, "rb").read() == want

@@ -271,3 +271,36 @@ def test_glue_logic_against_the_reference_with_the_oracle_behind_the_c_abi(tmp_p
     assert open(ref[0], "rb").read().count(b"SNPS\t") > 20
     two = run(GLUED, "glued2", 2, mock_env)
     assert sorted(open(ref[0], "rb").read().split(b"CONTIG\t")) == sorted(open(two[0], "rb").read().split(b"CONTIG\t"))
+
+
+GLUED_SR = os.path.join(ROOT, "oracle", "_ref", "HS_separate_reads_glued")
+
+
+@pytest.mark.skipif(not (os.path.exists(GLUED_SR) and os.path.exists(os.path.join(MOCK_DIR, "libhsgpu.so"))),
+                    reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("case", ["ont", "amplicon"])
+def test_separate_reads_glue_logic_with_the_oracle_behind_the_c_abi(tmp_path, case):
+    """integration/glue_separate_reads.cpp under the reference's own main() of HS_separate_reads (random_device pinned):
+    list_similarities_and_differences_between_reads3 bound to hsgpu_read_pair_counts, here answered by the oracle
+    (oracle/mock_hsgpu.c, this subprocess only). The .gro must be the committed golden one of the pinned reference.
+    Without the stand-in the same executable stops in the glue: no GPU, no fallback. The run with the real library is
+    tests/test_gpu_sepreads.py::test_reference_main_on_libhsgpu_gives_the_reference_gro."""
+    import gzip
+    import subprocess
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_sr
+    _, err, low, rare, amp = make_golden_sr.CASES[case]
+    gold = os.path.join(ROOT, "tests", "golden")
+    tmp = str(tmp_path)
+    col, out = os.path.join(tmp, case + ".col"), os.path.join(tmp, case + ".gro")
+    with open(col, "wb") as f:
+        f.write(gzip.open(os.path.join(gold, f"sr_{case}.col.gz")).read())
+    want = gzip.open(os.path.join(gold, f"sr_{case}.gro.gz")).read()
+    cmd = [GLUED_SR, col, "1", err, os.path.join(tmp, "no_ploidy"), low, rare, amp, out, "0"]
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, env=dict(os.environ, LD_LIBRARY_PATH=MOCK_DIR))
+    assert open(out, "rb").read() == want
+    if not torch.cuda.is_available():
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stdout
