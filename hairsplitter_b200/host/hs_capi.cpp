@@ -216,7 +216,11 @@ int hshost_rewrite_col(const char* col_in, const char* col_out, const char* vcf_
             }
             variants[(int)ci] = std::move(c.snps);
         }
+        const auto t0 = std::chrono::steady_clock::now();
         write_outputs(st, variants, col_out, vcf_out);
+        if (std::getenv("HS_TIMING"))
+            fprintf(stderr, "[hs timing] write_outputs %.3f s\n",
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
         return 0;
     } catch (...) {
         return 1;

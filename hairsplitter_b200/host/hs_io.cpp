@@ -8,7 +8,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <cstring>
 #include <iostream>
 #include <iterator>
@@ -377,28 +379,57 @@ void view_read_sequences(const MappedFile& reads, const Store& st, int64_t conti
 
 // src/call_variants.cpp:1174-1213. Alleles are written as decimal integers, lists end with a comma, every
 // contig block ends with an empty line; the .vcf is reopened, which drops the header written earlier.
-// The text of every contig block is formatted in parallel (one buffer per contig), then written in the iteration
-// order of the container, like the reference's sequential loop.
-static inline void append_uint(string& s, unsigned v) {
-    char buf[12];
-    int n = 0;
-    do {
-        buf[n++] = (char)('0' + v % 10);
-        v /= 10;
-    } while (v);
-    while (n) s += buf[--n];
+// The text of every contig block is formatted in parallel, then written in the iteration order of the container, like
+// the reference's sequential loop. The SNPS lines are the bulk (two numbers per cell, 1.4 GB on BASELINE config 3): their
+// exact size is counted first, every block is formatted once into a buffer of that size, and the blocks go to the file
+// at their offsets from all threads (pwrite) instead of through one stream.
+static inline int uint_digits(unsigned v) {
+    return 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) + (v >= 10000000u) +
+           (v >= 100000000u) + (v >= 1000000000u);
+}
+static inline char* put_uint(char* p, unsigned v) {
+    const int n = uint_digits(v);
+    for (int k = n - 1; k >= 0; k--) {
+        p[k] = (char)('0' + v % 10u);
+        v /= 10u;
+    }
+    return p + n;
+}
+static inline char* put_text(char* p, const string& t) {
+    std::memcpy(p, t.data(), t.size());
+    return p + t.size();
+}
+static bool write_all_at(int fd, const char* data, size_t n, off_t at) {
+    while (n > 0) {
+        const ssize_t w = ::pwrite(fd, data, n, at);
+        if (w <= 0) return false;
+        data += w;
+        n -= (size_t)w;
+        at += w;
+    }
+    return true;
 }
 
 void write_outputs(const Store& st, const std::unordered_map<int, std::vector<Column>>& variants,
                    const string& col_file, const string& vcf_file) {
     std::vector<const std::pair<const int, std::vector<Column>>*> order;
     for (const auto& kv : variants) order.push_back(&kv);
-    std::vector<string> col_text(order.size()), vcf_text(order.size());
-    std::vector<size_t> head_bytes(order.size(), 0);  // CONTIG + READ lines of the block: the sidecar keeps them as text
+    const size_t nb = order.size();
+    const bool timing = std::getenv("HS_TIMING") != nullptr;
+    double t_phase = omp_get_wtime();
+    auto phase = [&](const char* what) {
+        if (!timing) return;
+        const double t = omp_get_wtime();
+        fprintf(stderr, "[hs timing]   write_outputs: %-18s %8.3f s\n", what, t - t_phase);
+        t_phase = t;
+    };
+    std::vector<string> head_text(nb), vcf_text(nb);  // CONTIG + READ lines of the block (the sidecar keeps them as text)
+    std::vector<std::unique_ptr<char[]>> snp_text(nb);
+    std::vector<size_t> snp_bytes(nb, 0);
 #pragma omp parallel for schedule(dynamic, 1)
-    for (size_t i = 0; i < order.size(); i++) {
+    for (size_t i = 0; i < nb; i++) {
         const SeqRec& contig = st.seqs[order[i]->first];
-        string& o = col_text[i];
+        string& o = head_text[i];
         string& v = vcf_text[i];
         {
             std::ostringstream head;  // the depth is a float printed with the stream's default formatting
@@ -407,33 +438,51 @@ void write_outputs(const Store& st, const std::unordered_map<int, std::vector<Co
         }
         for (int64_t id : contig.alns) {
             const Alignment& a = st.alns[id];
-            std::ostringstream line;
-            line << "READ\t" << st.seqs[a.read].name << "\t" << a.pos_1_1 << "\t" << a.pos_1_2 << "\t" << a.pos_2_1 << "\t"
-                 << a.pos_2_2 << "\t" << a.strand << "\n";
-            o += line.str();
+            o += "READ\t";
+            o += st.seqs[a.read].name;
+            for (const int x : {a.pos_1_1, a.pos_1_2, a.pos_2_1, a.pos_2_2}) {
+                o += '\t';
+                o += std::to_string(x);
+            }
+            o += a.strand ? "\t1\n" : "\t0\n";
         }
-        head_bytes[i] = o.size();
-        for (const Column& c : order[i]->second) {
-            o += "SNPS\t";
-            o += std::to_string(c.pos);
-            o += '\t';
-            append_uint(o, (unsigned)(int)c.ref_base);
-            o += '\t';
-            append_uint(o, (unsigned)(int)c.second_base);
-            o += '\t';
-            for (size_t r = 0; r < c.readIdxs.size(); r++) {
-                append_uint(o, (unsigned)c.readIdxs[r]);
-                o += ',';
+        const std::vector<Column>& snps = order[i]->second;
+        std::vector<string> pos_text(snps.size());  // a signed int: printed by the library
+        size_t bytes = 1;                            // the empty line that ends the block
+        for (size_t k = 0; k < snps.size(); k++) {
+            const Column& c = snps[k];
+            pos_text[k] = std::to_string(c.pos);
+            const size_t n_code = std::min(c.content.size(), c.readIdxs.size());
+            bytes += 5 + pos_text[k].size() + 1 + (size_t)uint_digits(c.ref_base) + 1 + (size_t)uint_digits(c.second_base) + 1 +
+                     c.readIdxs.size() + 1 + n_code + 1;
+            for (const uint32_t r : c.readIdxs) bytes += (size_t)uint_digits(r);
+            for (size_t r = 0; r < n_code; r++) bytes += (size_t)uint_digits(c.content[r]);
+        }
+        snp_bytes[i] = bytes;
+        snp_text[i].reset(new char[bytes]);
+        char* p = snp_text[i].get();
+        for (size_t k = 0; k < snps.size(); k++) {
+            const Column& c = snps[k];
+            std::memcpy(p, "SNPS\t", 5);
+            p = put_text(p + 5, pos_text[k]);
+            *p++ = '\t';
+            p = put_uint(p, (unsigned)(int)c.ref_base);
+            *p++ = '\t';
+            p = put_uint(p, (unsigned)(int)c.second_base);
+            *p++ = '\t';
+            for (const uint32_t r : c.readIdxs) {
+                p = put_uint(p, (unsigned)r);
+                *p++ = ',';
             }
-            o += '\t';
+            *p++ = '\t';
             for (size_t r = 0; r < c.content.size() && r < c.readIdxs.size(); r++) {
-                append_uint(o, (unsigned)(int)c.content[r]);
-                o += ',';
+                p = put_uint(p, (unsigned)(int)c.content[r]);
+                *p++ = ',';
             }
-            o += '\n';
+            *p++ = '\n';
             v += contig.name;
             v += '\t';
-            v += std::to_string(c.pos);
+            v += pos_text[k];
             v += "\t.\t";
             v += "ACGT-"[(c.ref_base - '!') % 5];
             v += '\t';
@@ -442,23 +491,51 @@ void write_outputs(const Store& st, const std::unordered_map<int, std::vector<Co
             v += std::to_string(c.readIdxs.size());
             v += '\n';
         }
-        o += '\n';
+        *p++ = '\n';
+        if ((size_t)(p - snp_text[i].get()) != bytes) {  // the count above and the formatting must agree
+            std::cout << "ERROR: internal: .col block size mismatch" << std::endl;
+            std::exit(1);
+        }
         v += '\n';
     }
-    std::ofstream out(col_file, std::ios::binary);
-    std::ofstream vcf(vcf_file, std::ios::binary);
-    for (size_t i = 0; i < order.size(); i++) {
-        out.write(col_text[i].data(), (std::streamsize)col_text[i].size());
-        vcf.write(vcf_text[i].data(), (std::streamsize)vcf_text[i].size());
+    phase("format");
+    // the .col file: every block at its offset
+    std::vector<size_t> at(nb + 1, 0);
+    for (size_t i = 0; i < nb; i++) at[i + 1] = at[i] + head_text[i].size() + snp_bytes[i];
+    {
+        const int fd = ::open(col_file.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        bool ok = fd >= 0 && ::ftruncate(fd, (off_t)at[nb]) == 0;
+        if (ok) {
+#pragma omp parallel for schedule(dynamic, 1)
+            for (size_t i = 0; i < nb; i++) {
+                const bool w = write_all_at(fd, head_text[i].data(), head_text[i].size(), (off_t)at[i]) &&
+                               write_all_at(fd, snp_text[i].get(), snp_bytes[i], (off_t)(at[i] + head_text[i].size()));
+                if (!w) {
+#pragma omp atomic write
+                    ok = false;
+                }
+            }
+        }
+        if (fd >= 0) ::close(fd);
+        if (!ok) {
+            std::cout << "ERROR: cannot write " << col_file << std::endl;
+            std::exit(1);
+        }
     }
-    out.close();
+    phase(".col");
+    {
+        std::ofstream vcf(vcf_file, std::ios::binary);
+        for (size_t i = 0; i < nb; i++) vcf.write(vcf_text[i].data(), (std::streamsize)vcf_text[i].size());
+    }
+    phase(".vcf");
     // the same content once more as flat arrays, for HS_separate_reads (hs_colbin.h)
-    std::vector<ColSidecarBlock> blocks(order.size());
-    for (size_t i = 0; i < order.size(); i++) {
-        blocks[i].head.assign(col_text[i], 0, head_bytes[i]);
+    std::vector<ColSidecarBlock> blocks(nb);
+    for (size_t i = 0; i < nb; i++) {
+        blocks[i].head = std::move(head_text[i]);
         blocks[i].snps = &order[i]->second;
     }
     write_col_sidecar(col_file, blocks);
+    phase("sidecar");
 }
 
 }  // namespace hs

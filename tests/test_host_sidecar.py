@@ -169,3 +169,23 @@ def test_switch_off(lib, tmp_path, monkeypatch):
     assert blocks(col) == blocks(ref)
     monkeypatch.delenv("HS_SIDECAR")
     assert lib.hshost_col_sidecar_enabled() == 1
+
+
+def test_writer_prints_every_number_width(lib, tmp_path):
+    """write_outputs counts the bytes of a block before it formats it: numbers of every width (1 to 10 digits for read
+    indices and positions, 1 to 3 for codes) must come out as the decimal text the reference's stream would print"""
+    idx = [0, 9, 10, 99, 100, 999, 1000, 9999, 10000, 99999, 100000, 999999, 1000000, 9999999, 10000000, 99999999,
+           100000000, 999999999, 1000000000, 2147483647]
+    codes = [33, 99, 100, 157, 255, 0, 1, 9, 10, 200] * 2
+    lines = ["CONTIG\tctgA\t2000\t12.5", "READ\tr0\t0\t10\t5\t1999999999\t1", "READ\tr1\t3\t2147483647\t0\t7\t0"]
+    for pos in (0, 7, 10, 123456, 1999999999):
+        lines.append("SNPS\t%d\t%d\t%d\t%s\t%s" % (pos, 33 + pos % 100, 255 - pos % 100, "".join("%d," % i for i in idx),
+                                                 "".join("%d," % c for c in codes)))
+    text = ("\n".join(lines) + "\n\n").encode()
+    src, out = str(tmp_path / "in.col"), str(tmp_path / "out.col")
+    open(src, "wb").write(text)
+    assert lib.hshost_rewrite_col(src.encode(), out.encode(), str(tmp_path / "out.vcf").encode()) == 0
+    assert open(out, "rb").read() == text
+    _, a = digest(lib, out, 0)
+    dt, b = digest(lib, out, 1)
+    assert dt >= 0 and a[:4] == b[:4] and a[3] == 5 * len(idx)
