@@ -189,3 +189,44 @@ def test_writer_prints_every_number_width(lib, tmp_path):
     _, a = digest(lib, out, 0)
     dt, b = digest(lib, out, 1)
     assert dt >= 0 and a[:4] == b[:4] and a[3] == 5 * len(idx)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_ragged_files_parse_the_same_from_text_and_sidecar(lib, tmp_path, seed):
+    """seeded random .col files with the shapes the golden ones do not have: contigs without reads or without SNPS
+    lines, SNPS lines without cells, single-cell columns, codes over the whole byte range (a code 32 is a blank for
+    parse_column_file, :150-157, and is dropped), large read indices, several filter settings per file"""
+    import numpy as np
+    rng = np.random.default_rng(1000 + seed)
+    lines = []
+    for c in range(int(rng.integers(1, 6))):
+        n_reads = int(rng.integers(0, 40))
+        lines.append("CONTIG\tctg%d_%d\t%d\t%.4g" % (seed, c, int(rng.integers(50, 5000)), float(rng.uniform(0, 300))))
+        for r in range(n_reads):
+            a, b = sorted(int(x) for x in rng.integers(0, 5000, 2))
+            lines.append("READ\tread_%d\t%d\t%d\t%d\t%d\t%d" % (r, int(rng.integers(0, 100)), int(rng.integers(100, 9000)), a, b, int(rng.integers(0, 2))))
+        pos = 0
+        for s in range(int(rng.integers(0, 30)) if n_reads else 0):
+            pos += int(rng.integers(1, 200))
+            k = int(rng.choice([0, 1, 2, n_reads])) if rng.random() < 0.3 else int(rng.integers(0, n_reads + 1))
+            idx = np.sort(rng.choice(n_reads, size=k, replace=False)) if k else np.zeros(0, int)
+            if k and rng.random() < 0.1:
+                idx = idx.astype(np.int64) + int(rng.integers(0, 2**31 - 1 - n_reads))
+            palette = rng.choice(np.arange(0, 256), size=int(rng.integers(1, 5)), replace=False)
+            if rng.random() < 0.2:
+                palette[0] = 32
+            codes = rng.choice(palette, size=k)
+            ref, sec = (int(x) for x in rng.choice(palette, 2))
+            lines.append("SNPS\t%d\t%d\t%d\t%s\t%s" % (pos, ref, sec, "".join("%d," % i for i in idx), "".join("%d," % x for x in codes)))
+        lines.append("")
+    src, out = str(tmp_path / "in.col"), str(tmp_path / "out.col")
+    open(src, "wb").write(("\n".join(lines) + "\n").encode())
+    assert lib.hshost_rewrite_col(src.encode(), out.encode(), str(tmp_path / "out.vcf").encode()) == 0
+    assert os.path.exists(out + ".hsb")
+    for max_coverage, rarest in [(NO_LIMIT, 0.0), (5, 0.0), (NO_LIMIT, 0.3), (1, 0.5)]:
+        _, want = digest(lib, src, 0, max_coverage, rarest)      # the file as generated, text route
+        _, text = digest(lib, out, 0, max_coverage, rarest)      # the drop-in writer's text of the same content
+        dt, side = digest(lib, out, 1, max_coverage, rarest)     # and its sidecar
+        assert dt >= 0 and side[4] == 1
+        assert side[:4] == text[:4]
+        assert text[1:4] == want[1:4]
