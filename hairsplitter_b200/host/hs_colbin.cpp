@@ -52,10 +52,12 @@ uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
 
 // identity of a .col file: size, mtime and a hash over its first and last 64 KiB
 bool col_identity(const std::string& col_path, uint64_t& size, uint64_t& mtime_ns, uint64_t& sig) {
+    struct stat sb;
+    // regular files only: opening a pipe for reading would wait for a writer that never comes
+    if (::stat(col_path.c_str(), &sb) != 0 || !S_ISREG(sb.st_mode)) return false;
     const int fd = ::open(col_path.c_str(), O_RDONLY);
     if (fd < 0) return false;
-    struct stat sb;
-    if (::fstat(fd, &sb) != 0) {
+    if (::fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
         ::close(fd);
         return false;
     }

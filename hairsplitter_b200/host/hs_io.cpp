@@ -504,8 +504,23 @@ void write_outputs(const Store& st, const std::unordered_map<int, std::vector<Co
     for (size_t i = 0; i < nb; i++) at[i + 1] = at[i] + head_text[i].size() + snp_bytes[i];
     {
         const int fd = ::open(col_file.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-        bool ok = fd >= 0 && ::ftruncate(fd, (off_t)at[nb]) == 0;
-        if (ok) {
+        bool ok = fd >= 0;
+        if (ok && ::ftruncate(fd, (off_t)at[nb]) != 0) {
+            // not a regular file (a pipe, a device): one block after the other, like the reference's stream
+            for (size_t i = 0; i < nb && ok; i++) {
+                const char* const piece[2] = {head_text[i].data(), snp_text[i].get()};
+                const size_t piece_bytes[2] = {head_text[i].size(), snp_bytes[i]};
+                for (int k = 0; k < 2; k++) {
+                    const char* data = piece[k];
+                    size_t n = piece_bytes[k];
+                    while (n > 0 && ok) {
+                        const ssize_t w = ::write(fd, data, n);
+                        if (w <= 0) ok = false;
+                        else { data += w; n -= (size_t)w; }
+                    }
+                }
+            }
+        } else if (ok) {
 #pragma omp parallel for schedule(dynamic, 1)
             for (size_t i = 0; i < nb; i++) {
                 const bool w = write_all_at(fd, head_text[i].data(), head_text[i].size(), (off_t)at[i]) &&

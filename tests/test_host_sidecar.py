@@ -230,3 +230,21 @@ def test_random_ragged_files_parse_the_same_from_text_and_sidecar(lib, tmp_path,
         assert dt >= 0 and side[4] == 1
         assert side[:4] == text[:4]
         assert text[1:4] == want[1:4]
+
+
+@pytest.mark.timeout(60)
+def test_col_written_to_a_pipe(lib, tmp_path):
+    """a <col_out> that is not a regular file (the reference writes through a stream, which does not care): the blocks
+    go out one after the other instead of at file offsets, and no sidecar is attempted (its identity check would wait
+    on the pipe for ever)"""
+    import threading
+    ref = golden_col(tmp_path, "ont")
+    fifo = str(tmp_path / "out.col")
+    os.mkfifo(fifo)
+    got = []
+    reader = threading.Thread(target=lambda: got.append(open(fifo, "rb").read()), daemon=True)
+    reader.start()
+    assert lib.hshost_rewrite_col(ref.encode(), fifo.encode(), str(tmp_path / "out.vcf").encode()) == 0
+    reader.join(30)
+    assert got and sorted(got[0].split(b"CONTIG\t")) == sorted(open(ref, "rb").read().split(b"CONTIG\t"))
+    assert not os.path.exists(fifo + ".hsb")
