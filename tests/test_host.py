@@ -304,3 +304,65 @@ def test_separate_reads_glue_logic_with_the_oracle_behind_the_c_abi(tmp_path, ca
     if not torch.cuda.is_available():
         r = subprocess.run(cmd, stdout=subprocess.PIPE, text=True)
         assert r.returncode == 1 and "no CPU fallback" in r.stdout
+
+
+OURS_CV = os.path.join(ROOT, "hairsplitter_b200", "bin", "HS_call_variants")
+HOSTCHECK = os.path.join(ROOT, "oracle", "sr_hostcheck")
+REF_SR_PINNED = os.path.join(ROOT, "oracle", "_ref", "HS_separate_reads_pinned")
+
+
+@pytest.mark.skipif(not (os.path.exists(OURS_CV) and os.path.exists(os.path.join(MOCK_DIR, "libhsgpu.so")) and os.path.exists(REF_CV)),
+                    reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("case", ["ont_multi", "hifi_fastq", "edges"])
+def test_drop_in_executable_host_side_against_the_reference(tmp_path, case):
+    """The HOST side of bin/HS_call_variants end to end where there is no GPU: parsers with parse_SAM's filters, 2-bit
+    packing, 16-bit CIGAR, batching of the contigs, partition building (loops 1-2), the merge with the automatic SNPs,
+    the .col / .vcf writers and the sidecar -- with oracle/mock_hsgpu.c answering the C-ABI calls in this one
+    subprocess (LD_LIBRARY_PATH; the oracle computes what the kernels compute on a B200). Files byte-identical to the
+    reference executable's; the cases are those of the GPU test of the same executable
+    (tests/test_gpu_callvariants.py::test_col_vcf_error_rate_identical_to_reference). Then the chain: the .col and its
+    sidecar go through the host pipeline of HS_separate_reads (oracle/sr_hostcheck: the product's pipeline with the GPU
+    stages computed by the oracle) and the .gro must be the pinned reference's on the same .col."""
+    import filecmp
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    from hairsplitter_b200 import synth
+    from oracle.pyoracle import PIN_SEED
+    if case == "ont_multi":
+        chunks = [cases.small_case(seed=91, length=20000, depth=50, mean_len=5000, error=0.06), cases.medium_case(),
+                  cases.small_case(seed=5, length=3000, depth=12, mean_len=900, hard=0.4)]
+        fastq = False
+    elif case == "hifi_fastq":
+        chunks = [cases.hifi_case(), cases.small_case(seed=12, eqx=True)]
+        fastq = True
+    else:
+        chunks = cases.ragged_cases() + [cases.deep_case()]
+        fastq = False
+    for i, c in enumerate(chunks):
+        c.name = f"ctg{i}"
+    tmp = str(tmp_path)
+    files = synth.write_files(chunks, os.path.join(tmp, "in"), fastq=fastq)
+
+    def run(exe, tag, threads, env=None):
+        out = [os.path.join(tmp, f"{tag}.{e}") for e in ("col", "vcf", "err")]
+        subprocess.run([exe, *files, str(threads), tmp, out[2], "0", "0", out[0], out[1], "0.33"], check=True,
+                       stdout=subprocess.DEVNULL, env=env)
+        return out
+
+    ref = run(REF_CV, "ref", 1)
+    ours = run(OURS_CV, "ours", 4, dict(os.environ, LD_LIBRARY_PATH=MOCK_DIR))
+    for a, b in zip(ref, ours):
+        assert filecmp.cmp(a, b, shallow=False), (a, b)
+    assert os.path.getsize(ref[0]) > 1000
+    assert os.path.exists(ours[0] + ".hsb")
+    if not (os.path.exists(HOSTCHECK) and os.path.exists(REF_SR_PINNED)):
+        return
+    err = open(ref[2]).read().split()[0]
+    want, got = os.path.join(tmp, "ref.gro"), os.path.join(tmp, "ours.gro")
+    subprocess.run([REF_SR_PINNED, ref[0], "1", err, "none", "0", "0", "0", want, "0"], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([HOSTCHECK, ours[0], "2", err, "none", "0", "0", "0", got, "0"], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.PIPE, env=dict(os.environ, HS_PIN_SEED=str(PIN_SEED), HS_TIMING="1"))
+    assert "binary sidecar" in r.stderr.decode()
+    assert open(got, "rb").read() == open(want, "rb").read()
