@@ -137,10 +137,10 @@ static void process_batch(const std::function<hsgpu_ctx*()>& get_ctx, const Stor
 #pragma omp parallel for schedule(dynamic, 1)
         for (int b = 0; b < nc; b++) {
             const SeqRec& contig = st.seqs[st.contigs[batch[b]]];
-            hsgpu_pack_bases_ascii(contig.sequence.data(), (int64_t)contig.sequence.size(), contig_bases.data() + contig_word_off[b]);
+            pack_bases_2bit(contig.sequence.data(), (int64_t)contig.sequence.size(), contig_bases.data() + contig_word_off[b]);
             for (size_t n = 0; n < contig.alns.size(); n++) {
                 const int64_t r = contig_read_off[b] + (int64_t)n;
-                hsgpu_pack_bases_ascii(seqs[b][n].first, (int64_t)seqs[b][n].second, read_bases.data() + read_word_off[r]);
+                pack_bases_2bit(seqs[b][n].first, (int64_t)seqs[b][n].second, read_bases.data() + read_word_off[r]);
                 std::copy(ops[b][n].begin(), ops[b][n].end(), cigar.begin() + cigar_off[r]);
             }
         }

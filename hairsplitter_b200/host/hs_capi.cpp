@@ -229,4 +229,6 @@ int hshost_rewrite_col(const char* col_in, const char* col_out, const char* vcf_
 
 int hshost_col_sidecar_enabled() { return col_sidecar_enabled() ? 1 : 0; }
 
+void hshost_pack_bases_2bit(const char* seq, int64_t n, uint32_t* out) { pack_bases_2bit(seq, n, out); }
+
 }  // extern "C"

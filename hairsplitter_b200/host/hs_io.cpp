@@ -377,6 +377,39 @@ void view_read_sequences(const MappedFile& reads, const Store& st, int64_t conti
     }
 }
 
+namespace {
+struct BaseCodes {
+    uint8_t code[256];
+    BaseCodes() {
+        for (int c = 0; c < 256; c++) code[c] = 3;
+        code[(unsigned char)'A'] = 0;
+        code[(unsigned char)'C'] = 1;
+        code[(unsigned char)'G'] = 2;
+    }
+};
+const BaseCodes kBaseCodes;
+}  // namespace
+
+void pack_bases_2bit(const char* seq, int64_t n, uint32_t* out) {
+    const uint8_t* const lut = kBaseCodes.code;
+    const unsigned char* s = (const unsigned char*)seq;
+    const int64_t full = n / 16;
+    for (int64_t w = 0; w < full; w++, s += 16) {
+        // four independent chains of four bases
+        const uint32_t a = lut[s[0]] | (lut[s[1]] << 2) | (lut[s[2]] << 4) | (lut[s[3]] << 6);
+        const uint32_t b = lut[s[4]] | (lut[s[5]] << 2) | (lut[s[6]] << 4) | (lut[s[7]] << 6);
+        const uint32_t c = lut[s[8]] | (lut[s[9]] << 2) | (lut[s[10]] << 4) | (lut[s[11]] << 6);
+        const uint32_t d = lut[s[12]] | (lut[s[13]] << 2) | (lut[s[14]] << 4) | (lut[s[15]] << 6);
+        out[w] = a | (b << 8) | (c << 16) | (d << 24);
+    }
+    const int rest = (int)(n - 16 * full);
+    if (rest > 0) {
+        uint32_t v = 0;
+        for (int j = 0; j < rest; j++) v |= (uint32_t)lut[s[j]] << (2 * j);
+        out[full] = v;
+    }
+}
+
 // src/call_variants.cpp:1174-1213. Alleles are written as decimal integers, lists end with a comma, every
 // contig block ends with an empty line; the .vcf is reopened, which drops the header written earlier.
 // The text of every contig block is formatted in parallel, then written in the iteration order of the container, like

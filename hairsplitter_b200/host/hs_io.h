@@ -24,6 +24,11 @@ struct MappedFile {
 void parse_reads(const std::string& path, Store& st);
 void parse_assembly(const std::string& path, Store& st);
 void parse_sam(const std::string& path, Store& st, bool amplicon);
+// ASCII bases -> the 2-bit words of hsgpu_pileup_input (16 bases per word, base i in bits 2(i % 16)), in the reference's
+// own Sequence code: A 0, C 1, G 2, anything else 3 (src/sequence.cpp:13-23). Same result as hsgpu_pack_bases_ascii, which
+// takes a branch per base; this one goes through a table, 16 bases per step (the reads of a 60 Mb metagenome at 100x are
+// 6 GB of text).
+void pack_bases_2bit(const char* seq, int64_t n, uint32_t* out_words);
 // SAM CIGAR string -> BAM ops (len<<4 | index in "MIDNSHP=X"); "*" gives no ops. Exits like
 // convert_cigar (src/tools.cpp:27-57) when a length is missing.
 void cigar_ops(const std::string& cigar, std::vector<uint32_t>& ops);

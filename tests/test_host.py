@@ -366,3 +366,24 @@ def test_drop_in_executable_host_side_against_the_reference(tmp_path, case):
                        stderr=subprocess.PIPE, env=dict(os.environ, HS_PIN_SEED=str(PIN_SEED), HS_TIMING="1"))
     assert "binary sidecar" in r.stderr.decode()
     assert open(got, "rb").read() == open(want, "rb").read()
+
+
+def test_host_packer_equals_the_library_packer():
+    """hs::pack_bases_2bit (table-driven, what bin/HS_call_variants packs reads with) against hsgpu_pack_bases_ascii (the
+    C-ABI function, src/sequence.cpp:13-23 semantics): identical words for arbitrary bytes and every length around the
+    16-base word boundaries"""
+    host = C.CDLL(os.path.join(ROOT, "hairsplitter_b200", "libhshost.so"))
+    lib = api.load()
+    for f in (host.hshost_pack_bases_2bit, lib.hsgpu_pack_bases_ascii):
+        f.argtypes = [C.c_char_p, C.c_int64, C.c_void_p]
+        f.restype = None
+    rng = np.random.default_rng(5)
+    raw = rng.integers(0, 256, 4096, dtype=np.uint8).tobytes()
+    acgt = np.frombuffer(b"ACGTNacgt", dtype=np.uint8)[rng.integers(0, 9, 4096)].tobytes()
+    for data in (raw, acgt):
+        for n in list(range(0, 70)) + [4095, 4096]:
+            a = np.full((n + 15) // 16 + 1, 0xDEADBEEF, np.uint32)
+            b = a.copy()
+            lib.hsgpu_pack_bases_ascii(data, n, a.ctypes.data)
+            host.hshost_pack_bases_2bit(data, n, b.ctypes.data)
+            assert np.array_equal(a, b), n
