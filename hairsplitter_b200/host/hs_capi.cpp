@@ -229,6 +229,14 @@ int hshost_rewrite_col(const char* col_in, const char* col_out, const char* vcf_
 
 int hshost_col_sidecar_enabled() { return col_sidecar_enabled() ? 1 : 0; }
 
+// cigar_ops of the host parsers: number of ops, the ops in out (capacity entries at most are written)
+int64_t hshost_cigar_ops(const char* cigar, uint32_t* out, int64_t capacity) {
+    std::vector<uint32_t> ops;
+    cigar_ops(cigar, ops);
+    for (size_t k = 0; k < ops.size() && (int64_t)k < capacity; k++) out[k] = ops[k];
+    return (int64_t)ops.size();
+}
+
 void hshost_pack_bases_2bit(const char* seq, int64_t n, uint32_t* out) { pack_bases_2bit(seq, n, out); }
 
 }  // extern "C"

@@ -126,24 +126,37 @@ void parse_assembly(const string& path, Store& st) {
 void cigar_ops(const string& cigar, std::vector<uint32_t>& ops) {
     ops.clear();
     if (cigar == "*") return;
-    static const string letters = "MIDNSHP=X";
-    string num;
-    for (char c : cigar) {
-        if (c >= '0' && c <= '9') {
-            num += c;
+    // index in "MIDNSHP=X"; a letter no loop of the reference looks at behaves like padding (6)
+    static const struct OpCodes {
+        uint8_t code[256];
+        OpCodes() {
+            for (int c = 0; c < 256; c++) code[c] = 6;
+            const char* letters = "MIDNSHP=X";
+            for (int k = 0; letters[k]; k++) code[(unsigned char)letters[k]] = (uint8_t)k;
+        }
+    } table;
+    const char* const begin = cigar.data();
+    const char* const end = begin + cigar.size();
+    uint32_t n = 0;
+    const char* num = begin;  // first digit of the length being read
+    for (const char* p = begin; p < end; p++) {
+        const unsigned d = (unsigned)(*p - '0');
+        if (d <= 9) {
+            n = n * 10 + d;
             continue;
         }
-        int n = 0;
-        try {
-            n = std::stoi(num);
-        } catch (...) {
-            std::cout << "ERROR : could not convert " << cigar << " to int" << std::endl;
-            std::exit(1);
+        const size_t n_digits = (size_t)(p - num);
+        if (n_digits == 0 || n_digits > 9) {  // no length, or one that may not fit: what std::stoi makes of it
+            try {
+                n = (uint32_t)std::stoi(string(num, n_digits));
+            } catch (...) {
+                std::cout << "ERROR : could not convert " << cigar << " to int" << std::endl;
+                std::exit(1);
+            }
         }
-        size_t op = letters.find(c);
-        if (op == string::npos) op = 6;  // a letter no loop of the reference looks at behaves like padding
-        if (n > 0) ops.push_back(((uint32_t)n << 4) | (uint32_t)op);
-        num.clear();
+        if ((int)n > 0) ops.push_back(((uint32_t)n << 4) | (uint32_t)table.code[(unsigned char)*p]);
+        n = 0;
+        num = p + 1;
     }
 }
 

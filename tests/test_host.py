@@ -387,3 +387,29 @@ def test_host_packer_equals_the_library_packer():
             lib.hsgpu_pack_bases_ascii(data, n, a.ctypes.data)
             host.hshost_pack_bases_2bit(data, n, b.ctypes.data)
             assert np.array_equal(a, b), n
+
+
+def test_host_cigar_parser_semantics():
+    """cigar_ops of the drop-in's parsers (what HS_call_variants feeds the pileup with): lengths of any width, zero
+    lengths dropped (no loop of the reference sees them), letters outside "MIDNSHP=X" as padding, "*" and "" give
+    nothing; on ordinary strings the same ops as the C-ABI parser hsgpu_parse_cigar"""
+    host = C.CDLL(os.path.join(ROOT, "hairsplitter_b200", "libhshost.so"))
+    host.hshost_cigar_ops.argtypes = [C.c_char_p, C.c_void_p, C.c_int64]
+    host.hshost_cigar_ops.restype = C.c_int64
+    lib = api.load()
+    lib.hsgpu_parse_cigar.argtypes = [C.c_char_p, C.c_void_p, C.c_int64]
+    lib.hsgpu_parse_cigar.restype = C.c_int64
+
+    def ops_of(text, fn=host.hshost_cigar_ops):
+        out = np.zeros(len(text) + 8, np.uint32)
+        k = fn(text.encode(), out.ctypes.data, out.size)
+        return [(int(x) >> 4, int(x) & 15) for x in out[:k]]
+
+    assert ops_of("5M0I3D007S2=1X9N4H2P3Z") == [(5, 0), (3, 2), (7, 4), (2, 7), (1, 8), (9, 3), (4, 5), (2, 6), (3, 6)]
+    assert ops_of("*") == [] and ops_of("") == [] and ops_of("12") == []
+    assert ops_of("123456789M1D") == [(123456789, 0), (1, 2)]
+    assert ops_of("0000000012M") == [(12, 0)]  # ten digits: through std::stoi like the reference's own conversion
+    rng = np.random.default_rng(9)
+    for _ in range(20):
+        text = "".join("%d%s" % (rng.integers(1, 5000), "MIDNSHP=X"[rng.integers(0, 9)]) for _ in range(int(rng.integers(1, 400))))
+        assert ops_of(text) == ops_of(text, lib.hsgpu_parse_cigar)
