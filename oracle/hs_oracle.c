@@ -382,8 +382,14 @@ static int rank_column(const uint8_t* codes, int n, kc_t* sorted) {
     return k;
 }
 
+/* The counting loop of call_variants runs on a `short` index (:479): at n = 32767 the increment wraps to -32768, which
+ * compared with the unsigned size ends the loop -- only the first 32768 cells of a column are ever counted (checked
+ * against the compiled reference on a 40000-deep column, tests/test_oracle.py). */
+#define HSO_CELLS_COUNTED 32768
+
 void hso_column_rank(const uint8_t* codes, int n, int32_t* out) {
     kc_t s[256 + 8];
+    if (n > HSO_CELLS_COUNTED) n = HSO_CELLS_COUNTED;
     rank_column(codes, n, s);
     out[0] = s[0].k; out[1] = s[1].k; out[2] = s[0].c; out[3] = s[1].c; out[4] = s[2].c;
 }
@@ -401,6 +407,7 @@ int32_t hso_call_variants(const int64_t* col_off, const uint8_t* code, int32_t L
     for (int32_t pos = 0; pos < L; pos++) {
         const uint8_t* col = code + col_off[pos];
         int n = (int)(col_off[pos + 1] - col_off[pos]);
+        if (n > HSO_CELLS_COUNTED) n = HSO_CELLS_COUNTED; /* :479, see above */
         rank_column(col, n, s);
         for (int i = 0; i < n; i++) depth += (col[i] != ' ');
         ref_base[pos] = s[0].k;      /* :503-507 */

@@ -219,3 +219,31 @@ def test_splitting_long_cigar_ops_does_not_change_the_pileup(oracle):
     for k in ("col_off", "read_idx", "code", "read_end"):
         assert np.array_equal(a[k], b[k])
     assert list(a["stats"]) == list(b["stats"])
+
+
+def test_columns_deeper_than_a_short_are_counted_like_the_reference(oracle, refcv):
+    """call_variants counts a column with a `short` index (src/call_variants.cpp:479): only its first 32768 cells ever
+    reach the histogram and the depth. A 40000-deep column whose variant is carried by the reads beyond the 32768th must
+    stay invisible, one carried by early reads must be called; depth = 32768 per column. The oracle follows the
+    reference here. The CUDA library counts every cell of such a column -- the one known deviation, DESIGN.md 7b (no
+    BASELINE config comes near: the amplicon contig is 2000x)."""
+    from hairsplitter_b200 import synth
+    L, R, counted = 40, 40000, 32768
+    rng = np.random.default_rng(0)
+    contig = rng.integers(0, 4, L).astype(np.uint8)
+    reads = np.tile(contig, (R, 1))
+    reads[counted:, 20] = (contig[20] + 1) % 4   # seen by nobody: these cells are never counted
+    reads[:10, 10] = (contig[10] + 2) % 4        # ten early reads: counted
+    cb = synth.ContigBatch(contig=contig, read_bases=reads.reshape(-1), read_off=np.arange(R + 1, dtype=np.int64) * L,
+                           cigar=np.full(R, (L << 4) | 0, np.uint32), cigar_off=np.arange(R + 1, dtype=np.int64),
+                           start=np.zeros(R, np.int32), strand=np.ones(R, np.uint8), strain=np.zeros(R, np.int32))
+    ref = refcv(cb)
+    md = ref.mean_distance()
+    rv = ref.call_variants(md)
+    o = oracle.pileup(cb)
+    ov = oracle.call_variants(o["col_off"], o["code"], md)
+    assert np.array_equal(rv["ref_base"], ov["ref_base"]) and np.array_equal(rv["second_base"], ov["second_base"])
+    assert np.array_equal(rv["suspects"]["pos"], ov["suspect_pos"]) and ov["suspect_pos"].size >= 1
+    assert rv["depth"] == counted and ov["depth_sum"] == counted * L
+    assert ov["second_base"][20] == 0  # the late variant never entered the histogram: rank 1 is one of the three filler keys
+    ref.close()
